@@ -1,0 +1,303 @@
+"""Synthetic, seeded inputs for the BASELINE.json configurations.
+
+Pure numpy host data: meshes (from assets/*.npz, made by tools/make_mesh_fixtures.py),
+procedural equirectangular environment maps standing in for the reference's git-LFS EXR files
+(studio_garden_4k.exr / kiara_4_mid-morning_4k.exr are 133-byte pointers in the reference
+checkout), camera framing and materials.  The same arrays are handed to the CUDA library and to
+the CPU checkers, so nothing here is on the measured path.
+"""
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSET_DIR = os.path.join(_ROOT, "assets")
+
+U32_MAX = 0xFFFFFFFF
+
+# ids used by every workload (reference convention: enum index == id, main.cpp:1167-1189)
+MATERIAL_BACKGROUND = 0
+MATERIAL_SURFACE = 1
+MATERIAL_CHECKER = 2
+IMAGE_ENV = 7          # any value but 0: zero-initialised materials look up image key 0
+IMAGE_CHECKER = 3
+
+
+@dataclass
+class Mesh:
+    vertices: np.ndarray  # (n, 8) float32: position3 normal3 uv2  == VertexPNT (mesh.h:11-16)
+    indices: np.ndarray   # (m,) uint32, m % 3 == 0
+    smooth: bool = False
+
+    @property
+    def triangle_count(self):
+        return len(self.indices) // 3
+
+    def bounds(self):
+        p = self.vertices[:, 0:3]
+        return p.min(axis=0), p.max(axis=0)
+
+
+@dataclass
+class SceneObject:
+    mesh: int
+    material: int
+    position: tuple = (0.0, 0.0, 0.0)
+    rotation: tuple = (0.0, 0.0, 0.0, 1.0)   # quat x y z w
+    scale: tuple = (1.0, 1.0, 1.0)
+
+
+@dataclass
+class Material:
+    id: int
+    albedo: tuple = (0.0, 0.0, 0.0)
+    albedo_texture: int = U32_MAX
+    emission: tuple = (0.0, 0.0, 0.0)
+    emission_texture: int = U32_MAX
+    roughness: float = 0.0
+
+
+@dataclass
+class Workload:
+    name: str
+    meshes: list
+    objects: list
+    materials: list
+    textures: dict            # id -> (h, w, 4) float32 array
+    background: int
+    camera_position: tuple
+    camera_rotation: tuple
+    film_distance: float
+    width: int
+    height: int
+    spp: int = 1
+    bounces: int = 3
+    notes: dict = field(default_factory=dict)
+
+
+def load_mesh(name, smooth=False):
+    data = np.load(os.path.join(ASSET_DIR, name + ".npz"))
+    return Mesh(np.ascontiguousarray(data["vertices"], dtype=np.float32),
+                np.ascontiguousarray(data["indices"], dtype=np.uint32), smooth)
+
+
+# --------------------------------------------------------------------------------------------
+# procedural meshes (reference src/mesh_generation.cpp; counts match, construction is ours)
+
+def plane_mesh():
+    v = np.array([[-0.5, -0.5, 0, 0, 0, 1, 0, 0], [0.5, -0.5, 0, 0, 0, 1, 1, 0],
+                  [0.5, 0.5, 0, 0, 0, 1, 1, 1], [-0.5, 0.5, 0, 0, 0, 1, 0, 1]], dtype=np.float32)
+    return Mesh(v, np.array([0, 1, 2, 2, 3, 0], dtype=np.uint32))
+
+
+def triangle_mesh():
+    v = np.array([[-0.5, -0.5, 0, 0, 0, 1, 0, 0], [0.5, -0.5, 0, 0, 0, 1, 1, 0],
+                  [0.0, 0.5, 0, 0, 0, 1, 1, 1]], dtype=np.float32)
+    return Mesh(v, np.array([0, 1, 2], dtype=np.uint32))
+
+
+def icosphere_mesh(level, smooth=True):
+    """Unit icosphere, 20 * 4**level triangles, outward winding (shared midpoints)."""
+    t = (1.0 + 5.0 ** 0.5) * 0.5
+    pts = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t),
+           (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    verts = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in pts]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4),
+             (11, 10, 2), (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8),
+             (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(level):
+        cache, new_faces = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for (i, j, k) in faces:
+            a, b, c = mid(i, j), mid(j, k), mid(k, i)
+            new_faces += [(i, a, c), (j, b, a), (k, c, b), (a, b, c)]
+        faces = new_faces
+    p = np.asarray(verts, dtype=np.float32)
+    v = np.zeros((len(p), 8), dtype=np.float32)
+    v[:, 0:3] = p
+    v[:, 3:6] = p
+    return Mesh(v, np.asarray(faces, dtype=np.uint32).reshape(-1), smooth)
+
+
+# --------------------------------------------------------------------------------------------
+# environment maps
+
+def _hash32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+_ENV_CACHE = {}
+
+
+def make_env_map(width=4096, height=2048, variant="studio_garden"):
+    """Seeded procedural equirect RGBA-f32 map: vertical sky gradient, one sun disc whose peak
+    exceeds RADIANCE_CLAMP (10) so the clamp is exercised, and per-texel value noise
+    (seed 0x45BA12F3, the reference's cubemap seed, cubemap.cpp:123).  Row 0 is v = 0."""
+    key = (width, height, variant)
+    if key in _ENV_CACHE:
+        return _ENV_CACHE[key]
+    sun_az, sun_el, tint, seed = {
+        "studio_garden": (0.9, 0.55, (1.0, 0.95, 0.85), 0x45BA12F3),
+        "kiara": (2.4, 0.35, (1.0, 0.85, 0.7), 0x45BA12F4),
+    }[variant]
+    with np.errstate(over="ignore"):
+        ys = (np.arange(height, dtype=np.float32) + 0.5) / np.float32(height)
+        xs = (np.arange(width, dtype=np.float32) + 0.5) / np.float32(width)
+        # image row y <-> uv.y = y/H after the reference's flip: uv.y = 1 - (cos(inc)/2 + 1/2)
+        cos_inc = (1.0 - 2.0 * ys).astype(np.float32)            # +1 = straight up
+        sin_inc = np.sqrt(np.maximum(0.0, 1.0 - cos_inc * cos_inc)).astype(np.float32)
+        az = (xs * np.float32(2.0 * np.pi)).astype(np.float32)
+        sky = 0.35 + 0.65 * np.clip(cos_inc * 0.5 + 0.5, 0, 1) ** 2
+        ground = 0.12 + 0.1 * np.clip(-cos_inc, 0, 1)
+        base = np.where(cos_inc >= 0, sky, ground).astype(np.float32)[:, None]
+        sky_rgb = np.array([0.55, 0.72, 1.0], dtype=np.float32)
+        gnd_rgb = np.array([0.42, 0.36, 0.30], dtype=np.float32)
+        rgb = np.where((cos_inc >= 0)[:, None, None], sky_rgb[None, None, :],
+                       gnd_rgb[None, None, :]) * base[:, :, None]
+        rgb = np.broadcast_to(rgb, (height, width, 3)).astype(np.float32).copy()
+        # sun disc
+        sd = np.array([np.cos(sun_el) * np.cos(sun_az), np.sin(sun_el),
+                       np.cos(sun_el) * np.sin(sun_az)], dtype=np.float32)
+        dx = sin_inc[:, None] * np.cos(az)[None, :]
+        dz = sin_inc[:, None] * np.sin(az)[None, :]
+        dy = np.broadcast_to(cos_inc[:, None], dx.shape)
+        cosang = dx * sd[0] + dy * sd[1] + dz * sd[2]
+        sun = np.clip((cosang - np.float32(0.9985)) / np.float32(0.0015), 0, 1).astype(np.float32)
+        glow = np.clip((cosang - np.float32(0.9)) / np.float32(0.1), 0, 1).astype(np.float32) ** 4
+        rgb += (sun[:, :, None] * np.float32(60.0) + glow[:, :, None] * np.float32(1.5)) * \
+            np.asarray(tint, dtype=np.float32)[None, None, :]
+        # value noise, +-12 %
+        idx = np.arange(width * height, dtype=np.uint32).reshape(height, width)
+        n = _hash32(idx ^ np.uint32(seed)).astype(np.float32) / np.float32(4294967296.0)
+        rgb *= (np.float32(0.88) + np.float32(0.24) * n)[:, :, None]
+    out = np.ones((height, width, 4), dtype=np.float32)
+    out[:, :, 0:3] = rgb
+    out = np.ascontiguousarray(out)
+    _ENV_CACHE[key] = out
+    return out
+
+
+def make_checkerboard(size=256, cells=8):
+    """RGBA-f32 checkerboard (stands in for Image_CheckerBoard, main.cpp:1304)."""
+    y, x = np.mgrid[0:size, 0:size]
+    c = (((x * cells) // size + (y * cells) // size) & 1).astype(np.float32)
+    out = np.ones((size, size, 4), dtype=np.float32)
+    out[:, :, 0] = 0.1 + 0.8 * c
+    out[:, :, 1] = 0.1 + 0.8 * c
+    out[:, :, 2] = 0.15 + 0.7 * c
+    return np.ascontiguousarray(out)
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+
+def frame_camera(bounds_min, bounds_max, distance_factor=1.2):
+    """Camera on +z looking down -z at aabbCentre + (0, 0, 1.2 |diag|)."""
+    lo = np.asarray(bounds_min, dtype=np.float64)
+    hi = np.asarray(bounds_max, dtype=np.float64)
+    centre = (lo + hi) * 0.5
+    diag = float(np.linalg.norm(hi - lo))
+    pos = centre + np.array([0.0, 0.0, distance_factor * diag])
+    return tuple(float(np.float32(v)) for v in pos)
+
+
+def _standard_materials(env_id=IMAGE_ENV):
+    return [
+        Material(MATERIAL_BACKGROUND, emission_texture=env_id),
+        Material(MATERIAL_SURFACE, albedo=(0.18, 0.18, 0.18), roughness=0.6),
+    ]
+
+
+def single_mesh_workload(mesh_name, width, height, spp=1, bounces=3, smooth=True,
+                         env_variant="studio_garden", env_size=(4096, 2048), name=None):
+    mesh = load_mesh(mesh_name, smooth=smooth)
+    lo, hi = mesh.bounds()
+    return Workload(
+        name=name or f"{mesh_name}_{width}x{height}_{spp}spp_{bounces}b",
+        meshes=[mesh],
+        objects=[SceneObject(0, MATERIAL_SURFACE)],
+        materials=_standard_materials(),
+        textures={IMAGE_ENV: make_env_map(env_size[0], env_size[1], env_variant)},
+        background=MATERIAL_BACKGROUND,
+        camera_position=frame_camera(lo, hi),
+        camera_rotation=(0.0, 0.0, 0.0, 1.0),
+        film_distance=0.8,
+        width=width, height=height, spp=spp, bounces=bounces,
+        notes={"mesh": mesh_name, "triangles": mesh.triangle_count, "env": env_variant},
+    )
+
+
+def config1(width=1024, height=768, **kw):
+    """BASELINE configs[0]: bunny + studio_garden, 1024x768, 1 spp (reference: 3 bounces)."""
+    return single_mesh_workload("bunny", width, height, spp=1, bounces=3, smooth=True,
+                                env_variant="studio_garden", name="C1_bunny_1024x768_1spp", **kw)
+
+
+def config2(width=1920, height=1080, **kw):
+    """BASELINE configs[1]: monkey primary rays, flat shading (triangle-ID check)."""
+    return single_mesh_workload("monkey", width, height, spp=1, bounces=1, smooth=False,
+                                env_variant="studio_garden", name="C2_monkey_1920x1080_primary",
+                                **kw)
+
+
+def config3(width=3840, height=2160, spp=64, bounces=5, **kw):
+    """BASELINE configs[2]: bunny + kiara, 4K, 64 spp, 5 bounces."""
+    return single_mesh_workload("bunny", width, height, spp=spp, bounces=bounces, smooth=True,
+                                env_variant="kiara", name="C3_bunny_3840x2160_64spp_5b", **kw)
+
+
+def quat_axis_angle(axis, angle):
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    s = np.sin(angle * 0.5)
+    return (float(a[0] * s), float(a[1] * s), float(a[2] * s), float(np.cos(angle * 0.5)))
+
+
+def multi_object_workload(width=320, height=240, spp=1, bounces=3, count=12, seed=0x1A34C249,
+                          env_size=(512, 256)):
+    """Small instanced scene (<= 32 objects so the verbatim reference can run it): bunnies,
+    icospheres and a textured ground plane with rotations and non-unit uniform scales."""
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    bunny = load_mesh("bunny", smooth=False)
+    sphere = icosphere_mesh(2, smooth=True)
+    plane = plane_mesh()
+    meshes = [bunny, sphere, plane]
+    objects = [SceneObject(2, MATERIAL_CHECKER, position=(0.0, -0.6, 0.0),
+                           rotation=quat_axis_angle((1, 0, 0), -np.pi / 2), scale=(8.0, 8.0, 8.0))]
+    for i in range(count):
+        kind = i % 2
+        pos = (float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-0.4, 0.8)),
+               float(rng.uniform(-1.5, 0.5)))
+        rot = quat_axis_angle(rng.uniform(-1, 1, 3) + 1e-3, rng.uniform(0, 2 * np.pi))
+        if kind == 0:
+            s = float(rng.uniform(2.0, 4.0))
+        else:
+            s = float(rng.uniform(0.15, 0.35))
+        objects.append(SceneObject(kind, MATERIAL_SURFACE, pos, rot, (s, s, s)))
+    materials = _standard_materials() + [
+        Material(MATERIAL_CHECKER, albedo=(0.5, 0.5, 0.5), albedo_texture=IMAGE_CHECKER,
+                 roughness=0.3)]
+    return Workload(
+        name=f"multi_{count}obj_{width}x{height}", meshes=meshes, objects=objects,
+        materials=materials,
+        textures={IMAGE_ENV: make_env_map(env_size[0], env_size[1], "studio_garden"),
+                  IMAGE_CHECKER: make_checkerboard()},
+        background=MATERIAL_BACKGROUND,
+        camera_position=(0.0, 0.4, 4.0), camera_rotation=(0.0, 0.0, 0.0, 1.0),
+        film_distance=0.8, width=width, height=height, spp=spp, bounces=bounces,
+        notes={"objects": len(objects)})
