@@ -1,0 +1,304 @@
+/* sp_b200.h -- C ABI of libspb200.so, the B200 (sm_100a) implementation of vk_cinematic's
+ * CPU "SIMD" path tracer (the sp_ path).
+ *
+ * The entry points keep the reference's names, argument meaning and error behaviour so that the
+ * library drops in where the reference unity-includes sp_scene.cpp, sp_material_system.cpp and
+ * simd_path_tracer.cpp (reference src/main.cpp:235-240).  Each declaration cites the reference
+ * interface it replaces as `file:line` relative to the reference checkout.  The POD types below
+ * are byte-for-byte layout-compatible with the reference's (sizes asserted at the bottom; see
+ * SURVEY.md §8 for the probed values).  A reference-side translation unit that already includes
+ * the reference's own headers defines SP_B200_USE_REFERENCE_TYPES before including this file
+ * (see INTEGRATION.md).
+ *
+ * Everything computes on the GPU.  There is no CPU fallback: every compute entry point aborts
+ * through the log callback (Assert convention, reference src/platform.h:18-22) when no CUDA
+ * device is usable.
+ */
+#ifndef SP_B200_H
+#define SP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef SP_B200_USE_REFERENCE_TYPES
+
+typedef uint8_t u8;
+typedef int32_t i32;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef float f32;
+typedef u32 b32;
+
+/* math_lib.h:12-92 (unions there; plain structs with the same layout here) */
+typedef struct vec2 { f32 x, y; } vec2;
+typedef struct vec3 { f32 x, y, z; } vec3;
+typedef struct vec4 { f32 x, y, z, w; } vec4;
+typedef struct mat4 { vec4 columns[4]; } mat4;
+typedef vec4 quat; /* (x, y, z, w) */
+
+/* platform.h:87-92 */
+typedef struct MemoryArena { void *base; u64 size; u64 capacity; } MemoryArena;
+/* memory_pool.h:3-9 */
+typedef struct MemoryPool { u8 *storage; u32 objectSize; u32 capacity; u32 headIndex; } MemoryPool;
+/* bvh.h:14-18.  `root` holds this library's acceleration-structure handle, not a bvh_Node. */
+typedef struct bvh_Tree { void *root; MemoryPool memoryPool; } bvh_Tree;
+/* aabb.h:3-7 */
+typedef struct Aabb { vec3 min; vec3 max; } Aabb;
+/* mesh.h:11-16 */
+typedef struct VertexPNT { vec3 position; vec3 normal; vec2 textureCoord; } VertexPNT;
+/* asset_loader/asset_loader.h:13-18 */
+typedef struct HdrImage { float *pixels; uint32_t width; uint32_t height; } HdrImage;
+/* tile.h:3-9 */
+typedef struct Tile { u32 minX, minY, maxX, maxY; } Tile;
+/* math_utils.h:184-187 */
+typedef struct RandomNumberGenerator { u32 state; } RandomNumberGenerator;
+/* work_queue.h:4-11 */
+typedef struct WorkQueue {
+    volatile i32 head; volatile i32 tail; u32 objectSize; u32 maxObjects; void *buffer;
+} WorkQueue;
+
+/* sp_metrics.h:3-48 */
+enum {
+    sp_Metric_CyclesElapsed,
+    sp_Metric_PathsTraced,
+    sp_Metric_RaysTraced,
+    sp_Metric_RayHitCount,
+    sp_Metric_RayMissCount,
+    sp_Metric_CyclesElapsed_RayIntersectScene,
+    sp_Metric_CyclesElapsed_RayIntersectBroadphase,
+    sp_Metric_CyclesElapsed_RayIntersectMesh,
+    sp_Metric_CyclesElapsed_RayIntersectMeshMidphase,
+    sp_Metric_CyclesElapsed_RayIntersectTriangle,
+    sp_Metric_RayIntersectMesh_MidphaseAabbTestCount,
+    sp_Metric_RayIntersectMesh_TestsPerformed,
+    SP_MAX_METRICS
+};
+typedef struct sp_Metrics { u64 values[SP_MAX_METRICS]; } sp_Metrics;
+
+/* sp_scene.h:3-29 */
+typedef struct sp_Mesh {
+    VertexPNT *vertices;
+    u32 *indices;
+    u32 vertexCount;
+    u32 indexCount;
+    bvh_Tree midphaseTree;
+    b32 useSmoothShading;
+} sp_Mesh;
+
+#define SP_SCENE_MAX_OBJECTS 32
+typedef struct sp_Scene {
+    vec3 aabbMin[SP_SCENE_MAX_OBJECTS];
+    vec3 aabbMax[SP_SCENE_MAX_OBJECTS];
+    sp_Mesh meshes[SP_SCENE_MAX_OBJECTS];
+    u32 materials[SP_SCENE_MAX_OBJECTS];
+    mat4 invModelMatrices[SP_SCENE_MAX_OBJECTS];
+    mat4 modelMatrices[SP_SCENE_MAX_OBJECTS];
+    u32 objectCount;
+    MemoryArena memoryArena;
+    bvh_Tree broadphaseTree;
+} sp_Scene;
+
+/* ray_intersection.h:3-8 */
+typedef struct RayIntersectTriangleResult { f32 t; vec2 uv; vec3 normal; } RayIntersectTriangleResult;
+/* sp_scene.h:31-37 */
+typedef struct sp_RayIntersectMeshResult {
+    RayIntersectTriangleResult triangleIntersection;
+} sp_RayIntersectMeshResult;
+/* sp_scene.h:39-53 */
+typedef struct sp_RayIntersectSceneResult { f32 t; u32 materialId; vec3 normal; vec2 uv; } sp_RayIntersectSceneResult;
+
+/* sp_material_system.h:3-46 */
+typedef struct sp_Material {
+    vec3 albedo; u32 albedoTexture; vec3 emission; u32 emissionTexture; f32 roughness;
+} sp_Material;
+typedef struct sp_MaterialOutput { vec3 albedo; vec3 emission; f32 roughness; } sp_MaterialOutput;
+typedef struct sp_PathVertex {
+    u32 materialId; vec3 worldPosition; vec3 outgoingDir; vec3 incomingDir; vec3 normal; vec2 uv;
+} sp_PathVertex;
+#define SP_MAX_MATERIALS 32
+#define SP_MAX_IMAGES 16
+typedef struct sp_MaterialSystem {
+    u32 keys[SP_MAX_MATERIALS];
+    sp_Material materials[SP_MAX_MATERIALS];
+    u32 count;
+    u32 imageKeys[SP_MAX_IMAGES];
+    HdrImage images[SP_MAX_IMAGES];
+    u32 imageCount;
+    u32 backgroundMaterialId;
+} sp_MaterialSystem;
+
+/* simd_path_tracer.h:3-46 */
+typedef struct ImagePlane { vec4 *pixels; u32 width; u32 height; } ImagePlane;
+typedef struct Basis { vec3 right; vec3 up; vec3 forward; } Basis;
+typedef struct sp_Camera {
+    Basis basis; vec3 position; vec3 filmCenter; ImagePlane *imagePlane;
+    f32 halfPixelWidth; f32 halfPixelHeight; f32 halfFilmWidth; f32 halfFilmHeight;
+} sp_Camera;
+typedef struct sp_Context { sp_Camera *camera; sp_Scene *scene; sp_MaterialSystem *materialSystem; } sp_Context;
+
+#endif /* SP_B200_USE_REFERENCE_TYPES */
+
+/* ============================ the reference's sp_ surface ============================ */
+
+/* sp_scene.cpp:1-5.  The arena is recorded, never allocated from: acceleration structures live
+ * in library-owned host and device memory. */
+void sp_InitializeScene(sp_Scene *scene, MemoryArena *arena);
+/* sp_scene.cpp:8-19.  Aliases caller memory exactly like the reference (C has no default
+ * arguments: pass useSmoothShading explicitly). */
+sp_Mesh sp_CreateMesh(VertexPNT *vertices, u32 vertexCount, u32 *indices, u32 indexCount,
+                      b32 useSmoothShading);
+/* sp_scene.cpp:21-54.  Snapshots vertices/indices and builds the 4-wide midphase BVH
+ * (replaces bvh_CreateTree, bvh.cpp:51-200).  Arenas unused.  Asserts indexCount % 3 == 0. */
+void sp_BuildMeshMidphase(sp_Mesh *mesh, MemoryArena *arena, MemoryArena *tempArena);
+/* sp_scene.cpp:77-117.  Asserts objectCount < SP_SCENE_MAX_OBJECTS (use sp_b200_AddObject on a
+ * scene handle for larger scenes). */
+void sp_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material, vec3 position,
+                         quat orientation, vec3 scale);
+/* sp_scene.cpp:119-125.  Builds the object-level BVH and uploads the whole scene to the current
+ * device once; later render calls reuse it. */
+void sp_BuildSceneBroadphase(sp_Scene *scene);
+/* sp_scene.cpp:229-339 / 127-227: single-ray forms (one-ray GPU batches; tests use them). */
+sp_RayIntersectSceneResult sp_RayIntersectScene(sp_Scene *scene, vec3 rayOrigin,
+                                                vec3 rayDirection, sp_Metrics *metrics);
+sp_RayIntersectMeshResult sp_RayIntersectMesh(sp_Mesh mesh, vec3 rayOrigin, vec3 rayDirection,
+                                              sp_Metrics *metrics);
+
+/* sp_material_system.cpp:1-13, 15-29, 31-43, 45-57, 59-105 */
+b32 sp_RegisterMaterial(sp_MaterialSystem *materialSystem, sp_Material material, u32 id);
+sp_Material *sp_FindMaterialById(sp_MaterialSystem *materialSystem, u32 id);
+HdrImage *sp_FindTexture(sp_MaterialSystem *materialSystem, u32 id);
+b32 sp_RegisterTexture(sp_MaterialSystem *materialSystem, HdrImage image, u32 id);
+sp_MaterialOutput sp_EvaluateMaterial(sp_MaterialSystem *materialSystem, sp_Material *material,
+                                      sp_PathVertex *vertex);
+
+/* simd_path_tracer.cpp:1-36, 38-63 (pure host arithmetic, same operation order) */
+void sp_ConfigureCamera(sp_Camera *camera, ImagePlane *imagePlane, vec3 position, quat rotation,
+                        f32 filmDistance);
+u32 sp_CalculateFilmPositions(sp_Camera *camera, vec3 *filmPositions, vec2 *pixelPositions,
+                              u32 count);
+/* simd_path_tracer.cpp:107-175 (evaluated on the GPU by the same device code the renderer uses) */
+vec3 ComputeRadianceForPath(sp_PathVertex *path, u32 pathLength, sp_MaterialSystem *materialSystem);
+/* simd_path_tracer.cpp:178-345: the tile-render entry.  Serial XorShift32 stream over the tile's
+ * pixels exactly as the reference (one GPU thread per tile: drop-in fidelity, not speed);
+ * overwrites metrics[CyclesElapsed] with device nanoseconds, increments the counters. */
+void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng, sp_Metrics *metrics);
+
+/* aabb.h:29-58 */
+Aabb TransformAabb(vec3 boxMin, vec3 boxMax, vec3 position, quat orientation, vec3 scale);
+/* tile.h:11-42 */
+u32 ComputeTiles(u32 totalWidth, u32 totalHeight, u32 tileWidth, u32 tileHeight, Tile *tiles,
+                 u32 maxTiles);
+/* work_queue.h:13-44 */
+WorkQueue CreateWorkQueue(MemoryArena *arena, u32 objectSize, u32 maxObjects);
+b32 WorkQueuePush(WorkQueue *queue, void *object, u32 objectSize);
+void *WorkQueuePop(WorkQueue *queue, u32 objectSize);
+
+/* =============================== additions (sp_b200_*) =============================== */
+
+typedef void (*sp_b200_LogFn)(const char *message);
+
+enum { SP_B200_ENV_NEAREST = 0, SP_B200_ENV_BILINEAR = 1 };
+enum { SP_B200_MATH_F64_ROUNDED = 0, SP_B200_MATH_FAST_F32 = 1 };
+
+/* Run-time form of the reference's compile-time knobs (config.h:15-33). */
+typedef struct sp_b200_Params {
+    u32 samplesPerPixel; /* SAMPLES_PER_PIXEL, config.h:23 (default 1024 there; 1 here) */
+    u32 bounceCount;     /* literal 3 at simd_path_tracer.cpp:195; 1..8 */
+    f32 radianceClamp;   /* RADIANCE_CLAMP, config.h:33; 0 disables */
+    u32 envFilter;       /* SP_B200_ENV_*: the reference samples nearest (image.h:3-18) */
+    u32 mathMode;        /* SP_B200_MATH_*: libm stand-ins, see DESIGN.md */
+    u32 cullByDistance;  /* 1: ordered traversal with t-culling; 0: visit every intersected leaf
+                            exactly like bvh_IntersectRay (bvh.cpp:203-311) */
+    u32 tileWidth;       /* TILE_WIDTH / TILE_HEIGHT, config.h:15-16 (cost accounting granularity) */
+    u32 tileHeight;
+} sp_b200_Params;
+
+/* Kernel-side counters of the most recent launch (for the roofline). */
+typedef struct sp_b200_Stats {
+    u64 rays;
+    u64 nodeVisits;     /* 4-wide internal nodes fetched (128 B each) */
+    u64 triangleTests;  /* leaf triangles fetched and tested (48 B each) */
+    u64 objectTests;    /* instances entered (ray transformed to object space) */
+    u64 envClampedLookups; /* env texel indices past the image end (unclamped in image.h:3-18) */
+    f32 kernelMs;       /* CUDA-event time of the dominant kernel of the last call */
+    f32 totalMs;        /* CUDA-event time of the whole call on the device (copies included) */
+} sp_b200_Stats;
+
+int sp_b200_Init(int device);            /* selects the device; 0 on success */
+void sp_b200_Shutdown(void);             /* frees every device and host object */
+void sp_b200_SetLogCallback(sp_b200_LogFn fn);
+void sp_b200_SetStream(void *cudaStream);/* stream all later launches use (0 = default) */
+void sp_b200_DefaultParams(sp_b200_Params *params);
+void sp_b200_SetParams(const sp_b200_Params *params);
+void sp_b200_GetParams(sp_b200_Params *params);
+void sp_b200_GetLastStats(sp_b200_Stats *stats);
+/* Collect node/triangle counters in the next launches (slower kernels; off by default). */
+void sp_b200_EnableStats(int enable);
+/* Forget device copies of HdrImage pixel buffers (they are cached by host pointer). */
+void sp_b200_FlushTextureCache(void);
+/* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
+u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
+
+/* Whole-frame render with per-(pixel,sample) seeding: rows [rowBegin,rowEnd) of the image plane.
+ * hostPixels (RGBA f32, full-image indexing, may be NULL) receives the rows by D2H copy;
+ * devicePixels (device pointer to a full image, may be NULL) receives them in place.
+ * tileRowCost (may be NULL): per tile-row device cost (rays traced), rowEnd-rowBegin rounded up
+ * to tiles.  Returns 0 on success. */
+int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels,
+                       void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);
+/* All rows into ctx->camera->imagePlane->pixels (host). */
+int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics);
+/* Primary-ray closest hits of (sample, frame): per pixel triangle index (-1 = miss), object
+ * index and world t.  Output arrays are host memory, any may be NULL. */
+int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *triangleIndex,
+                        i32 *objectIndex, f32 *t);
+/* Batched sp_RayIntersectScene: origins/directions are n x vec3 host arrays. */
+int sp_b200_RayIntersectSceneBatch(sp_Scene *scene, u32 count, const vec3 *rayOrigins,
+                                   const vec3 *rayDirections, sp_RayIntersectSceneResult *results,
+                                   i32 *triangleIndex, i32 *objectIndex, sp_Metrics *metrics);
+/* bvh_IntersectRay semantics on this library's tree (bvh.cpp:203-311): collects the indices of
+ * every leaf whose box chain the ray passes.  Returns the count; *errorOccurred is set when
+ * more than maxIntersections leaves are hit. */
+u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 rayDirection,
+                                  u32 *leafIndices, u32 maxIntersections, b32 *errorOccurred);
+/* Host-side structure queries on the midphase tree (test hooks, cf. unit_tests/test_bvh.cpp). */
+typedef struct sp_b200_TreeInfo {
+    u32 leafCount; u32 nodeCount; u32 maxDepth; b32 allLeavesReachable;
+    b32 parentsContainChildren; vec3 rootMin; vec3 rootMax;
+} sp_b200_TreeInfo;
+void sp_b200_MeshTreeInfo(sp_Mesh mesh, sp_b200_TreeInfo *info);
+void sp_b200_ReleaseMesh(sp_Mesh *mesh);
+void sp_b200_ReleaseScene(sp_Scene *scene);
+
+#ifdef __cplusplus
+}
+#endif
+
+#ifndef SP_B200_USE_REFERENCE_TYPES
+#if defined(__cplusplus)
+#define SP_B200_SIZE_CHECK(T, N) static_assert(sizeof(T) == (N), #T " layout differs from the reference")
+#else
+#define SP_B200_SIZE_CHECK(T, N) _Static_assert(sizeof(T) == (N), #T " layout differs from the reference")
+#endif
+SP_B200_SIZE_CHECK(vec3, 12);
+SP_B200_SIZE_CHECK(vec4, 16);
+SP_B200_SIZE_CHECK(mat4, 64);
+SP_B200_SIZE_CHECK(VertexPNT, 32);
+SP_B200_SIZE_CHECK(sp_Mesh, 64);
+SP_B200_SIZE_CHECK(sp_Scene, 7104);
+SP_B200_SIZE_CHECK(sp_Material, 36);
+SP_B200_SIZE_CHECK(sp_PathVertex, 60);
+SP_B200_SIZE_CHECK(sp_MaterialSystem, 1616);
+SP_B200_SIZE_CHECK(HdrImage, 16);
+SP_B200_SIZE_CHECK(sp_Camera, 88);
+SP_B200_SIZE_CHECK(Tile, 16);
+SP_B200_SIZE_CHECK(sp_Metrics, 96);
+SP_B200_SIZE_CHECK(sp_RayIntersectSceneResult, 28);
+SP_B200_SIZE_CHECK(RayIntersectTriangleResult, 24);
+#undef SP_B200_SIZE_CHECK
+#endif
+
+#endif /* SP_B200_H */

@@ -49,7 +49,8 @@ void ora_build(ora_Scene *s);
 
 int ora_register_material(ora_Scene *s, uint32_t id, const float *albedo3, uint32_t albedoTexture,
                           const float *emission3, uint32_t emissionTexture, float roughness);
-/* pixels: RGBA f32, row-major.  Aliased, not copied (as the reference does). */
+/* pixels: RGBA f32, row-major.  The checkers copy the image and append width+1 texels equal to
+ * the last one (SampleImageNearest is unclamped, image.h:3-18; see ref_driver.cpp). */
 int ora_register_texture(ora_Scene *s, uint32_t id, const float *pixels, uint32_t width,
                          uint32_t height);
 void ora_set_background(ora_Scene *s, uint32_t materialId);

@@ -13,10 +13,43 @@
 // Build flags: -O2, no -march=native / -mfma / -ffast-math (SURVEY.md §7 hard part 1).
 
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <math.h>
 #include <thread>
 #include <vector>
+
+// Second oracle mode, "deterministic math" (oracle/_ref/libspref_dm.so): the same unmodified
+// reference sources, but the four single-precision libm calls on the path (sinf, cosf, atan2f,
+// powf -- reached through math_utils.h:63-97) are redirected to "evaluate in double, round once
+// to float".  glibc's float functions are not correctly rounded (they differ from the rounded
+// double result for 1.3 % / 8 % / 0.07 % of inputs, DESIGN.md "libm"), and a GPU cannot call
+// glibc; with the redirect both sides compute the same function, so everything else on the path
+// (traversal, shading, accumulation) can be compared bit-for-bit.  The primary mode
+// (libspref.so) keeps glibc's functions and is compared within a stated tolerance.
+#ifdef ORA_DETERMINISTIC_MATH
+static inline float ora_dm_sinf(float x) { return (float)sin((double)x); }
+static inline float ora_dm_cosf(float x) { return (float)cos((double)x); }
+static inline float ora_dm_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+static inline float ora_dm_powf(float x, float y)
+{
+    if (y == 5.0f)
+    {
+        double d = (double)x;
+        double d2 = d * d;
+        return (float)(d2 * d2 * d);
+    }
+    return (float)pow((double)x, (double)y);
+}
+#define sinf ora_dm_sinf
+#define cosf ora_dm_cosf
+#define atan2f ora_dm_atan2f
+#define powf ora_dm_powf
+#define ORA_NAME "reference-dm"
+#else
+#define ORA_NAME "reference"
+#endif
 
 // --- the reference, verbatim -------------------------------------------------------------
 #include "config.h"
@@ -87,7 +120,7 @@ static void *OraAlloc(ora_Scene *s, size_t bytes)
     return p;
 }
 
-extern "C" const char *ora_name(void) { return "reference"; }
+extern "C" const char *ora_name(void) { return ORA_NAME; }
 extern "C" uint32_t ora_max_bounces(void) { return 3; }
 
 extern "C" ora_Scene *ora_create(void)
@@ -174,8 +207,23 @@ extern "C" int ora_register_material(ora_Scene *s, uint32_t id, const float *alb
 extern "C" int ora_register_texture(ora_Scene *s, uint32_t id, const float *pixels,
                                     uint32_t width, uint32_t height)
 {
+    // SampleImageNearest (image.h:3-18) does not clamp: uv.y == 1 (a ray leaving straight down,
+    // which the theta-uniform hemisphere sampler produces about once per 10^4 bounce rays)
+    // indexes row `height`, i.e. up to width+1 texels past the end of the caller's buffer.  In
+    // the reference that is an out-of-bounds heap read.  The harness therefore hands the
+    // reference a private copy of the image followed by width+1 texels equal to the last texel,
+    // which makes the unmodified code return what the GPU's clamped lookup returns
+    // (spb_core.cuh sample_nearest) instead of faulting.
+    size_t texels = (size_t)width * height;
+    size_t padded = texels + width + 1;
+    float *copy = (float *)OraAlloc(s, padded * 4 * sizeof(float));
+    memcpy(copy, pixels, texels * 4 * sizeof(float));
+    for (size_t i = texels; i < padded && texels > 0; ++i)
+    {
+        memcpy(copy + i * 4, pixels + (texels - 1) * 4, 4 * sizeof(float));
+    }
     HdrImage image = {};
-    image.pixels = (float *)pixels;
+    image.pixels = copy;
     image.width = width;
     image.height = height;
     return (int)sp_RegisterTexture(&s->materials, image, id);

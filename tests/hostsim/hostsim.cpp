@@ -1,0 +1,303 @@
+// tests/hostsim/hostsim.cpp -- DEBUGGING AID, NOT PRODUCT, NOT AN ORACLE.
+//
+// Compiles the device arithmetic (vk_cinematic_b200/csrc/spb_core.cuh) and the host builder for
+// the host with g++, behind the oracle harness ABI (oracle/ora_api.h), so the traversal and
+// shading *logic* of the CUDA path can be compared bit-for-bit with the oracle in a container
+// that has no GPU.  The shipped library (libspb200.so) contains none of this and has no CPU
+// path; tests that use this file say "hostsim" in their name and make no parity claim for the
+// GPU -- those are the `-m gpu` tests.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../vk_cinematic_b200/csrc/spb_capture.h"
+#include "../../oracle/ora_api.h"
+
+using namespace spb;
+
+struct ora_Scene
+{
+    std::vector<std::shared_ptr<MeshAccel>> meshes;
+    std::vector<uint32_t> meshSmooth;
+    std::vector<ObjectInstance> objects;
+    FlatScene flat;
+    DScene d;
+    sp_MaterialSystem ms;
+    sp_Camera camera;
+    ImagePlane plane;
+    DMaterials dm;
+    DCamera dc;
+};
+
+static void refresh(ora_Scene *s)
+{
+    const v4f *pix[SPB_MAX_IMAGES] = {};
+    for (uint32_t i = 0; i < s->ms.imageCount && i < SPB_MAX_IMAGES; ++i)
+        pix[i] = (const v4f *)s->ms.images[i].pixels;
+    convert_materials(&s->ms, pix, &s->dm);
+    convert_camera(&s->camera, &s->dc);
+}
+
+extern "C" const char *ora_name(void) { return "hostsim"; }
+extern "C" uint32_t ora_max_bounces(void) { return SPB_MAX_BOUNCES; }
+
+extern "C" ora_Scene *ora_create(void)
+{
+    ora_Scene *s = new ora_Scene();
+    memset(&s->ms, 0, sizeof(s->ms));
+    memset(&s->camera, 0, sizeof(s->camera));
+    memset(&s->plane, 0, sizeof(s->plane));
+    s->camera.imagePlane = &s->plane;
+    s->flat = flatten_scene(s->objects);
+    return s;
+}
+extern "C" void ora_destroy(ora_Scene *s) { delete s; }
+
+extern "C" int ora_add_mesh(ora_Scene *s, const float *vertices, uint32_t vertexCount,
+                            const uint32_t *indices, uint32_t indexCount, uint32_t smooth)
+{
+    s->meshes.push_back(build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount));
+    s->meshSmooth.push_back(smooth);
+    return (int)s->meshes.size() - 1;
+}
+
+extern "C" int ora_add_object(ora_Scene *s, uint32_t mesh, uint32_t material, const float *p,
+                              const float *q, const float *sc)
+{
+    ObjectInstance ob;
+    ob.mesh = s->meshes[mesh];
+    ob.material = material;
+    ob.smooth = s->meshSmooth[mesh];
+    compute_object_transform(ob.mesh.get(), ob.mesh->vertices.data(),
+                             (uint32_t)ob.mesh->vertices.size(), vec3{p[0], p[1], p[2]},
+                             quat{q[0], q[1], q[2], q[3]}, vec3{sc[0], sc[1], sc[2]}, &ob.model,
+                             &ob.invModel, ob.aabbMin, ob.aabbMax);
+    s->objects.push_back(ob);
+    return (int)s->objects.size() - 1;
+}
+
+extern "C" void ora_build(ora_Scene *s)
+{
+    s->flat = flatten_scene(s->objects);
+    s->d.nodes = s->flat.nodes.data();
+    s->d.tris = s->flat.tris.data();
+    s->d.shade = s->flat.shade.data();
+    s->d.objInv = s->flat.objInv.data();
+    s->d.objModel = s->flat.objModel.data();
+    s->d.objInfo = s->flat.objInfo.data();
+    s->d.tlasRoot = s->flat.tlasRoot;
+    s->d.objectCount = s->flat.objectCount;
+}
+
+extern "C" int ora_register_material(ora_Scene *s, uint32_t id, const float *albedo,
+                                     uint32_t albedoTexture, const float *emission,
+                                     uint32_t emissionTexture, float roughness)
+{
+    if (s->ms.count >= SP_MAX_MATERIALS) return 0;
+    sp_Material m = {};
+    m.albedo = vec3{albedo[0], albedo[1], albedo[2]};
+    m.albedoTexture = albedoTexture;
+    m.emission = vec3{emission[0], emission[1], emission[2]};
+    m.emissionTexture = emissionTexture;
+    m.roughness = roughness;
+    uint32_t i = s->ms.count++;
+    s->ms.keys[i] = id;
+    s->ms.materials[i] = m;
+    return 1;
+}
+
+extern "C" int ora_register_texture(ora_Scene *s, uint32_t id, const float *pixels,
+                                    uint32_t width, uint32_t height)
+{
+    if (s->ms.imageCount >= SP_MAX_IMAGES) return 0;
+    uint32_t i = s->ms.imageCount++;
+    s->ms.imageKeys[i] = id;
+    s->ms.images[i].pixels = (float *)pixels;
+    s->ms.images[i].width = width;
+    s->ms.images[i].height = height;
+    return 1;
+}
+
+extern "C" void ora_set_background(ora_Scene *s, uint32_t id) { s->ms.backgroundMaterialId = id; }
+
+extern "C" void ora_configure_camera(ora_Scene *s, const float *p, const float *q,
+                                     float filmDistance, uint32_t width, uint32_t height)
+{
+    s->plane.width = width;
+    s->plane.height = height;
+    configure_camera(&s->camera, &s->plane, vec3{p[0], p[1], p[2]}, quat{q[0], q[1], q[2], q[3]},
+                     filmDistance);
+}
+
+extern "C" uint32_t ora_seed(uint32_t pixelIndex, uint32_t sample, uint32_t frame)
+{
+    return stream_seed(pixelIndex, sample, frame);
+}
+
+static int g_hostsimCull = 1;
+extern "C" void hostsim_set_cull(int cull) { g_hostsimCull = cull; }
+
+template <bool CULL>
+static void render_rows(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uint32_t x1,
+                        uint32_t y1, uint32_t spp, uint32_t bounces, uint32_t frame,
+                        uint32_t tid, uint32_t threads, uint64_t *m)
+{
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    uint32_t width = s->dc.width;
+    float weight = 1.0f / (float)spp;
+    PathCounters pc = {0, 0, 0};
+    uint64_t paths = 0;
+    for (uint32_t y = y0 + tid; y < y1; y += threads)
+        for (uint32_t x = x0; x < x1; ++x)
+        {
+            f3 total = mk3(0, 0, 0);
+            for (uint32_t sample = 0; sample < spp; ++sample)
+            {
+                uint32_t rng = stream_seed(x + y * width, sample, frame);
+                f3 r = trace_path<0, 0, CULL>(s->d, s->dm, s->dc, x, y, rng, bounces, 10.0f,
+                                              stack, stackT, pc, nullptr);
+                total = add3(total, mul3(r, weight));
+                paths++;
+            }
+            float *px = rgba + ((size_t)x + (size_t)y * width) * 4;
+            px[0] = total.x; px[1] = total.y; px[2] = total.z; px[3] = 1.0f;
+        }
+    m[ORA_METRIC_PATHS] = paths;
+    m[ORA_METRIC_RAYS] = pc.rays;
+    m[ORA_METRIC_HITS] = pc.hits;
+    m[ORA_METRIC_MISSES] = pc.misses;
+}
+
+extern "C" void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0,
+                                  uint32_t x1, uint32_t y1, uint32_t spp, uint32_t bounces,
+                                  uint32_t frame, uint32_t threads, uint64_t *metrics)
+{
+    refresh(s);
+    if (threads == 0) threads = 1;
+    std::vector<std::vector<uint64_t>> per(threads, std::vector<uint64_t>(ORA_METRIC_COUNT, 0));
+    auto worker = [&](uint32_t tid) {
+        if (g_hostsimCull)
+            render_rows<true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+        else
+            render_rows<false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : pool) t.join();
+    if (metrics)
+        for (uint32_t t = 0; t < threads; ++t)
+            for (int i = 0; i < ORA_METRIC_COUNT; ++i) metrics[i] += per[t][i];
+}
+
+extern "C" void ora_path_trace_tile(ora_Scene *s, float *rgba, uint32_t minX, uint32_t minY,
+                                    uint32_t maxX, uint32_t maxY, uint32_t spp,
+                                    uint32_t bounces, uint32_t *rngState, uint64_t *metrics)
+{
+    refresh(s);
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    uint32_t width = s->dc.width, height = s->dc.height;
+    if (maxX > width) maxX = width;
+    if (maxY > height) maxY = height;
+    uint32_t rng = *rngState;
+    PathCounters pc = {0, 0, 0};
+    uint64_t paths = 0;
+    float weight = 1.0f / (float)spp;
+    for (uint32_t y = minY; y < maxY; ++y)
+        for (uint32_t x = minX; x < maxX; ++x)
+        {
+            f3 total = mk3(0, 0, 0);
+            for (uint32_t sample = 0; sample < spp; ++sample)
+            {
+                f3 r = trace_path<0, 0, true>(s->d, s->dm, s->dc, x, y, rng, bounces, 10.0f, stack,
+                                              stackT, pc, nullptr);
+                total = add3(total, mul3(r, weight));
+                paths++;
+            }
+            float *px = rgba + ((size_t)x + (size_t)y * width) * 4;
+            px[0] = total.x; px[1] = total.y; px[2] = total.z; px[3] = 1.0f;
+        }
+    *rngState = rng;
+    if (metrics)
+    {
+        metrics[ORA_METRIC_PATHS] += paths;
+        metrics[ORA_METRIC_RAYS] += pc.rays;
+        metrics[ORA_METRIC_HITS] += pc.hits;
+        metrics[ORA_METRIC_MISSES] += pc.misses;
+    }
+}
+
+extern "C" void ora_primary_hits(ora_Scene *s, int32_t *triId, int32_t *objId, float *tOut,
+                                 float *rayDir3, uint32_t sample, uint32_t frame,
+                                 uint32_t threads)
+{
+    refresh(s);
+    uint32_t width = s->dc.width, height = s->dc.height;
+    if (threads == 0) threads = 1;
+    auto worker = [&](uint32_t tid) {
+        uint32_t stack[SPB_STACK_SIZE];
+        float stackT[SPB_STACK_SIZE];
+        for (uint32_t y = tid; y < height; y += threads)
+            for (uint32_t x = 0; x < width; ++x)
+            {
+                uint32_t rng = stream_seed(x + y * width, sample, frame);
+                f3 o, d;
+                primary_ray(s->dc, x, y, rng, o, d);
+                Hit h = g_hostsimCull ? intersect_scene<true>(s->d, o, d, stack, stackT, nullptr)
+                                      : intersect_scene<false>(s->d, o, d, stack, stackT, nullptr);
+                uint32_t index = x + y * width;
+                int32_t tri = -1;
+                if (h.object >= 0) tri = (int32_t)f2u(s->d.tris[(size_t)h.slot * 3].w);
+                if (triId) triId[index] = tri;
+                if (objId) objId[index] = h.object;
+                if (tOut) tOut[index] = h.t;
+                if (rayDir3) { rayDir3[index * 3] = d.x; rayDir3[index * 3 + 1] = d.y; rayDir3[index * 3 + 2] = d.z; }
+            }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : pool) t.join();
+}
+
+extern "C" void ora_intersect_rays(ora_Scene *s, uint32_t n, const float *origins3,
+                                   const float *dirs3, float *out7, int32_t *triId,
+                                   int32_t *objId, uint64_t *metrics)
+{
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        f3 o = mk3(origins3[i * 3], origins3[i * 3 + 1], origins3[i * 3 + 2]);
+        f3 d = mk3(dirs3[i * 3], dirs3[i * 3 + 1], dirs3[i * 3 + 2]);
+        Hit h = g_hostsimCull ? intersect_scene<true>(s->d, o, d, stack, stackT, nullptr)
+                              : intersect_scene<false>(s->d, o, d, stack, stackT, nullptr);
+        float *out = out7 ? out7 + (size_t)i * 7 : nullptr;
+        int32_t tri = -1;
+        if (h.object >= 0)
+        {
+            Surface sf = resolve_hit(s->d, h);
+            tri = (int32_t)sf.triangle;
+            if (out)
+            {
+                out[0] = h.t;
+                memcpy(&out[1], &sf.material, 4);
+                out[2] = sf.normal.x; out[3] = sf.normal.y; out[4] = sf.normal.z;
+                out[5] = sf.uvx; out[6] = sf.uvy;
+            }
+        }
+        else if (out)
+        {
+            out[0] = -1.0f;
+            out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.0f;
+        }
+        if (triId) triId[i] = tri;
+        if (objId) objId[i] = h.object;
+    }
+    (void)metrics;
+}

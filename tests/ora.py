@@ -13,6 +13,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(_ROOT, "oracle")
 PORT_LIB = os.path.join(ORACLE_DIR, "libsporacle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libspref.so")
+REF_DM_LIB = os.path.join(ORACLE_DIR, "_ref", "libspref_dm.so")
 
 METRIC_NAMES = ["cycles", "paths", "rays", "hits", "misses", "cyc_scene", "cyc_broadphase",
                 "cyc_mesh", "cyc_midphase", "cyc_triangle", "midphase_aabb_tests", "mesh_tests"]
@@ -56,10 +57,34 @@ def have_port():
     return os.path.exists(PORT_LIB)
 
 
+class _Missing:
+    """Placeholder for an entry point a library does not export (hostsim exports a subset)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.argtypes = None
+        self.restype = None
+
+    def __call__(self, *a):
+        raise NotImplementedError(self.name)
+
+
+class _Tolerant:
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_missing", {})
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._lib, name)
+        except AttributeError:
+            return self._missing.setdefault(name, _Missing(name))
+
+
 class OracleLib:
     def __init__(self, path):
         self.path = path
-        lib = C.CDLL(path)
+        lib = _Tolerant(C.CDLL(path))
         self.lib = lib
         lib.ora_name.restype = C.c_char_p
         lib.ora_max_bounces.restype = C.c_uint32
@@ -360,8 +385,25 @@ class OracleScene:
                 "parents_contain_children": bool(out[5])}
 
 
+HOSTSIM_LIB = os.path.join(_ROOT, "tests", "hostsim", "libhostsim.so")
+
+
+def build_hostsim():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "tests", "hostsim")])
+
+
+def load_hostsim():
+    o = OracleLib(HOSTSIM_LIB)
+    o.lib.hostsim_set_cull.argtypes = [C.c_int]
+    return o
+
+
 def load_ref():
     return OracleLib(REF_LIB)
+
+
+def load_ref_dm():
+    return OracleLib(REF_DM_LIB)
 
 
 def load_port():

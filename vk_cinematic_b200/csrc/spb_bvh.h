@@ -1,0 +1,37 @@
+// spb_bvh.h -- host builder of the 4-wide BVH the traversal kernels consume.
+//
+// Replaces bvh_CreateTree (reference src/bvh.cpp:51-200, an O(n^2 log n) agglomerative build)
+// with a binned-SAH top-down build collapsed to 4 children per node.  What is kept from the
+// reference is the *predicate structure*, not the topology: every primitive sits alone in a
+// child slot whose box is exactly the primitive's own AABB, so the slab test performed at the
+// parent is the per-leaf test of bvh_IntersectRay (bvh.cpp:236-255), and a primitive is
+// reported iff its own box passes -- independent of how the tree above it is shaped.
+#pragma once
+
+#include <stdint.h>
+#include <vector>
+
+namespace spb {
+
+struct Node4
+{
+    float bmin[3][4]; // [axis][lane]
+    float bmax[3][4];
+    uint32_t ref[4];  // SPB_REF_EMPTY, SPB_REF_LEAF | slot, or node index (local to this tree)
+    uint32_t meta[4]; // meta[0] = child count, meta[1] = depth of this node
+};
+static_assert(sizeof(Node4) == 128, "node must be 128 bytes (8 x 16-byte loads)");
+
+struct Bvh4
+{
+    std::vector<Node4> nodes;       // breadth-first order: the first nodes are the top levels
+    std::vector<uint32_t> slotPrim; // leaf slot -> primitive index (slots in breadth-first order)
+    uint32_t maxDepth = 0;
+    float rootMin[3] = {0, 0, 0};
+    float rootMax[3] = {0, 0, 0};
+};
+
+// aabbMin/aabbMax: count x 3 floats.  count == 0 gives an empty tree (no nodes).
+Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count);
+
+} // namespace spb

@@ -1,0 +1,819 @@
+// spb_core.cuh -- the arithmetic of the sp_ path, written once for the device.
+//
+// Every function here states the reference lines whose *operation order* it reproduces; the
+// translation units that include this header are compiled with -fmad=false (nvcc) so no
+// multiply-add is contracted, and IEEE division / square root (nvcc defaults).  The header also
+// compiles as plain C++ (g++ -ffp-contract=off) for tests/hostsim, a debugging aid that lets the
+// traversal and shading logic be checked bit-for-bit against the oracle without a GPU.  The
+// shipped library never runs this code on the host.
+#pragma once
+
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define SPB_HD __host__ __device__ __forceinline__
+#define SPB_ALIGN16 __align__(16)
+#else
+#define SPB_HD inline
+#define SPB_ALIGN16 alignas(16)
+#endif
+
+namespace spb {
+
+#if defined(__CUDACC__)
+typedef float4 v4f;
+typedef uint4 v4u;
+#else
+struct SPB_ALIGN16 v4f { float x, y, z, w; };
+struct SPB_ALIGN16 v4u { uint32_t x, y, z, w; };
+#endif
+
+SPB_HD v4f ld4(const v4f *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+SPB_HD v4u ld4u(const v4u *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+SPB_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+SPB_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// constants (math_utils.h:6-7)
+#define SPB_PI 3.14159265359f
+#define SPB_EPSILON FLT_EPSILON
+
+#define SPB_REF_EMPTY 0xFFFFFFFFu
+#define SPB_REF_LEAF 0x80000000u
+#define SPB_STACK_SIZE 96
+#define SPB_MAX_BOUNCES 8
+#define SPB_MAX_MATERIALS 32
+#define SPB_MAX_IMAGES 16
+
+// ------------------------------------------------------------------------------------------
+// vec3 with the reference's evaluation order (math_lib.h:178-215, 266-286, 461-521)
+struct f3 { float x, y, z; };
+
+SPB_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+SPB_HD f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+SPB_HD f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+SPB_HD f3 mul3(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+SPB_HD f3 neg3(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+SPB_HD f3 had3(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+SPB_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SPB_HD f3 cross3(f3 a, f3 b)
+{
+    return mk3((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+}
+// Min/Max as `a < b ? a : b` / `a > b ? a : b` (math_utils.h:9-19): NaN picks b.
+SPB_HD float rmin(float a, float b) { return a < b ? a : b; }
+SPB_HD float rmax(float a, float b) { return a > b ? a : b; }
+
+// Normalize (math_lib.h:503-512): zero vector unless length > FLT_EPSILON; multiply by reciprocal
+SPB_HD f3 normalize3(f3 v, float *lengthOut = nullptr)
+{
+    float length = sqrtf(dot3(v, v));
+    if (lengthOut) *lengthOut = length;
+    f3 r = mk3(0.0f, 0.0f, 0.0f);
+    if (length > SPB_EPSILON)
+    {
+        r = mul3(v, 1.0f / length);
+    }
+    return r;
+}
+
+// mat4 * vec4 (math_lib.h:381-398 with Dot at :238-248): columns m[0..3]; row i dotted with
+// (v, w) left to right, including the w term (it can flip the sign of a zero).
+struct m4 { v4f c[4]; };
+SPB_HD f3 xform(const m4 &m, f3 v, float w)
+{
+    f3 r;
+    r.x = m.c[0].x * v.x + m.c[1].x * v.y + m.c[2].x * v.z + m.c[3].x * w;
+    r.y = m.c[0].y * v.x + m.c[1].y * v.y + m.c[2].y * v.z + m.c[3].y * w;
+    r.z = m.c[0].z * v.x + m.c[1].z * v.y + m.c[2].z * v.z + m.c[3].z * w;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// libm stand-ins.  MATH == 0: evaluate in double and round once to float -- agrees with glibc's
+// sinf/cosf/atan2f/powf wherever those are correctly rounded (98.7 % / 92 % / 99.93 % of inputs,
+// measured; DESIGN.md "libm") and is what the oracle's deterministic-math mode computes.
+// MATH == 1: CUDA's single-precision functions.
+template <int MATH> SPB_HD float m_sin(float x) { return MATH == 0 ? (float)sin((double)x) : sinf(x); }
+template <int MATH> SPB_HD float m_cos(float x) { return MATH == 0 ? (float)cos((double)x) : cosf(x); }
+template <int MATH> SPB_HD float m_atan2(float y, float x)
+{
+    return MATH == 0 ? (float)atan2((double)y, (double)x) : atan2f(y, x);
+}
+// Pow(x, 5.0f) (simd_path_tracer.cpp:65-70): x^5 by three double multiplies, one rounding
+template <int MATH> SPB_HD float m_pow5(float x)
+{
+    if (MATH == 0)
+    {
+        double d = (double)x;
+        double d2 = d * d;
+        return (float)(d2 * d2 * d);
+    }
+    return powf(x, 5.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// RNG (math_utils.h:184-214)
+SPB_HD uint32_t xorshift32(uint32_t &state)
+{
+    uint32_t x = state;
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    state = x;
+    return x;
+}
+SPB_HD float rand_unilateral(uint32_t &state)
+{
+    // (f32)(x >> 1) / (f32)(U32_MAX >> 1); the denominator rounds to 2^31
+    return (float)(xorshift32(state) >> 1) / 2147483648.0f;
+}
+SPB_HD float rand_bilateral(uint32_t &state) { return -1.0f + 2.0f * rand_unilateral(state); }
+
+// Seed of the (pixel, sample, frame) stream; never 0 (XorShift32's fixed point).
+SPB_HD uint32_t stream_seed(uint32_t pixelIndex, uint32_t sample, uint32_t frame)
+{
+    uint32_t h = pixelIndex * 0x9E3779B1u;
+    h ^= sample * 0x85EBCA77u;
+    h ^= frame * 0xC2B2AE3Du;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    h *= 0x846CA68Bu;
+    h ^= h >> 16;
+    return h | 1u;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-side scene description (built and owned by spb_host.cpp)
+struct DCamera
+{
+    f3 right, up, position, filmCenter;
+    float halfPixelWidth, halfPixelHeight, halfFilmWidth, halfFilmHeight;
+    uint32_t width, height;
+};
+
+struct DImage { const v4f *pixels; uint32_t width, height, pad; };
+
+struct DMaterials
+{
+    uint32_t count;
+    uint32_t backgroundId;
+    uint32_t imageCount;
+    uint32_t pad;
+    uint32_t keys[SPB_MAX_MATERIALS];
+    float albedo[SPB_MAX_MATERIALS][3];
+    float emission[SPB_MAX_MATERIALS][3];
+    float roughness[SPB_MAX_MATERIALS];
+    int32_t albedoImage[SPB_MAX_MATERIALS];   // resolved sp_FindTexture result, -1 = none
+    int32_t emissionImage[SPB_MAX_MATERIALS];
+    DImage images[SPB_MAX_IMAGES];
+};
+
+// Node = 8 x 16 B: child boxes SoA (min x,y,z then max x,y,z, four lanes each), 4 child refs,
+// 16 B of metadata.  A child is either another node, one primitive (SPB_REF_LEAF | slot) whose
+// box is the primitive's own AABB -- which makes the parent's slab test the reference's
+// per-leaf test (bvh.cpp:236-255) -- or SPB_REF_EMPTY.
+struct DScene
+{
+    const v4f *nodes;      // 8 per node
+    const v4f *tris;       // 3 per triangle slot: (v0, bits triIndex) (v1, -) (v2, -)
+    const v4f *shade;      // 4 per triangle: (n0,uv0.x) (n1,uv0.y) (n2,uv1.x) (uv1.y,uv2.x,uv2.y,-)
+    const v4f *objInv;     // 4 per object: inverse model matrix columns
+    const v4f *objModel;   // 4 per object: model matrix columns
+    const v4u *objInfo;    // x = mesh root node (or EMPTY), y = shade base, z = smooth flag, w = material
+    uint32_t tlasRoot;     // node index or SPB_REF_EMPTY
+    uint32_t objectCount;
+};
+
+struct Counters
+{
+    uint32_t nodeVisits, triangleTests, objectTests, envClamped;
+};
+
+// ------------------------------------------------------------------------------------------
+// camera (simd_path_tracer.cpp:38-63, 216-230)
+SPB_HD void primary_ray(const DCamera &cam, uint32_t x, uint32_t y, uint32_t &rng, f3 &origin,
+                        f3 &direction)
+{
+    // Vec2(halfPixelWidth * RandomBilateral(rng), halfPixelHeight * RandomBilateral(rng)):
+    // g++ evaluates the arguments right to left, so the first draw jitters y (pinned by
+    // tests/test_oracle_ref.py::test_jitter_draw_order).
+    float by = rand_bilateral(rng);
+    float bx = rand_bilateral(rng);
+    float px = ((float)x + 0.5f) + cam.halfPixelWidth * bx;
+    float py = ((float)y + 0.5f) + cam.halfPixelHeight * by;
+
+    float fx = px / (float)cam.width;
+    float fy = py / (float)cam.height;
+    fy = 1.0f - fy;
+    fx = fx * 2.0f - 1.0f;
+    fy = fy * 2.0f - 1.0f;
+    f3 filmP = mul3(cam.right, cam.halfFilmWidth * fx);
+    filmP = add3(filmP, mul3(cam.up, cam.halfFilmHeight * fy));
+    filmP = add3(filmP, cam.filmCenter);
+
+    origin = cam.position;
+    direction = normalize3(sub3(filmP, cam.position));
+}
+
+// ------------------------------------------------------------------------------------------
+// slab test of one lane of a 4-wide node (simd.h:198-271): per axis t0 = (min-o)*inv,
+// t1 = (max-o)*inv, tmin = minps(t0,t1), tmax = maxps(t0,t1) (second operand on NaN), then
+// Max(0, max3(tmin)) <= min3(tmax) with the scalar Max/Min.  tnear is the left-hand side.
+SPB_HD bool slab_exact(float bminx, float bminy, float bminz, float bmaxx, float bmaxy,
+                       float bmaxz, f3 o, f3 inv, float &tnear)
+{
+    float t0x = (bminx - o.x) * inv.x, t1x = (bmaxx - o.x) * inv.x;
+    float t0y = (bminy - o.y) * inv.y, t1y = (bmaxy - o.y) * inv.y;
+    float t0z = (bminz - o.z) * inv.z, t1z = (bmaxz - o.z) * inv.z;
+    float tminx = rmin(t0x, t1x), tmaxx = rmax(t0x, t1x);
+    float tminy = rmin(t0y, t1y), tmaxy = rmax(t0y, t1y);
+    float tminz = rmin(t0z, t1z), tmaxz = rmax(t0z, t1z);
+    tnear = rmax(0.0f, rmax(tminx, rmax(tminy, tminz)));
+    float tfar = rmin(tmaxx, rmin(tmaxy, tmaxz));
+    return tnear <= tfar;
+}
+// Same predicate when no product can be NaN (all inv components finite): hardware min/max.
+SPB_HD bool slab_fast(float bminx, float bminy, float bminz, float bmaxx, float bmaxy,
+                      float bmaxz, f3 o, f3 inv, float &tnear)
+{
+    float t0x = (bminx - o.x) * inv.x, t1x = (bmaxx - o.x) * inv.x;
+    float t0y = (bminy - o.y) * inv.y, t1y = (bmaxy - o.y) * inv.y;
+    float t0z = (bminz - o.z) * inv.z, t1z = (bmaxz - o.z) * inv.z;
+    tnear = fmaxf(0.0f, fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))));
+    float tfar = fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z)));
+    return tnear <= tfar;
+}
+
+// Moller-Trumbore (ray_intersection.cpp:156-190).  Returns true when the reference would set
+// result.t; the caller applies t > 0 (sp_scene.cpp:189).
+SPB_HD bool ray_triangle_mt(f3 o, f3 d, f3 a, f3 b, f3 c, float &t, float &u, float &v)
+{
+    f3 T = sub3(o, a);
+    f3 e1 = sub3(b, a);
+    f3 e2 = sub3(c, a);
+    f3 p = cross3(d, e2);
+    f3 q = cross3(T, e1);
+    f3 n = cross3(e1, e2);
+    float mx = dot3(q, e2), my = dot3(p, T), mz = dot3(q, d);
+    float det = 1.0f / dot3(p, e1);
+    t = det * mx;
+    u = det * my;
+    v = det * mz;
+    float w = 1.0f - u - v;
+    float f = dot3(d, n);
+    return (u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f &&
+            f < 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// traversal
+
+struct Hit
+{
+    float t;        // world t (sp_scene.cpp:302) or -1
+    int32_t object; // object index or -1
+    uint32_t slot;  // triangle slot in DScene::tris
+    float u, v;     // barycentrics of the winning triangle
+    f3 localOrigin, localDirection; // the object-space ray the winner was found with
+    float localT;
+};
+
+SPB_HD void sort2(float &ta, uint32_t &ra, float &tb, uint32_t &rb)
+{
+    if (tb < ta)
+    {
+        float t = ta; ta = tb; tb = t;
+        uint32_t r = ra; ra = rb; rb = r;
+    }
+}
+
+// One BVH over `nodes` starting at node `root`.  LEAF(slot, tnear) is invoked for every
+// primitive child whose own box passes the slab predicate; it returns the updated cull
+// distance (or the old one).  With CULL the near child is visited first and subtrees whose
+// entry distance exceeds the cull distance are skipped; without it every intersected leaf is
+// visited, like bvh_IntersectRay (bvh.cpp:203-311).
+template <bool CULL, bool EXACT, class LeafFn>
+SPB_HD void traverse(const v4f *nodes, uint32_t root, f3 o, f3 inv, float tcull, uint32_t *stack,
+                     float *stackT, int stackBase, int stackLimit, Counters *counters,
+                     LeafFn &leaf)
+{
+    int sp = stackBase;
+    uint32_t node = root;
+    const float inf = u2f(0x7F800000u);
+    for (;;)
+    {
+        const v4f *n = nodes + (size_t)node * 8;
+        v4f minx = ld4(n + 0), miny = ld4(n + 1), minz = ld4(n + 2);
+        v4f maxx = ld4(n + 3), maxy = ld4(n + 4), maxz = ld4(n + 5);
+        v4u refs = ld4u((const v4u *)(n + 6));
+        if (counters) counters->nodeVisits++;
+
+        float tn0, tn1, tn2, tn3;
+        bool h0, h1, h2, h3;
+        if (EXACT)
+        {
+            h0 = slab_exact(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, o, inv, tn0);
+            h1 = slab_exact(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, o, inv, tn1);
+            h2 = slab_exact(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, o, inv, tn2);
+            h3 = slab_exact(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, o, inv, tn3);
+        }
+        else
+        {
+            h0 = slab_fast(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, o, inv, tn0);
+            h1 = slab_fast(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, o, inv, tn1);
+            h2 = slab_fast(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, o, inv, tn2);
+            h3 = slab_fast(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, o, inv, tn3);
+        }
+        h0 = h0 && refs.x != SPB_REF_EMPTY;
+        h1 = h1 && refs.y != SPB_REF_EMPTY;
+        h2 = h2 && refs.z != SPB_REF_EMPTY;
+        h3 = h3 && refs.w != SPB_REF_EMPTY;
+
+        // primitives first (in child order), so the cull distance shrinks before descending
+        if (h0 && (refs.x & SPB_REF_LEAF)) { if (!CULL || tn0 <= tcull) tcull = leaf(refs.x & ~SPB_REF_LEAF, tcull); h0 = false; }
+        if (h1 && (refs.y & SPB_REF_LEAF)) { if (!CULL || tn1 <= tcull) tcull = leaf(refs.y & ~SPB_REF_LEAF, tcull); h1 = false; }
+        if (h2 && (refs.z & SPB_REF_LEAF)) { if (!CULL || tn2 <= tcull) tcull = leaf(refs.z & ~SPB_REF_LEAF, tcull); h2 = false; }
+        if (h3 && (refs.w & SPB_REF_LEAF)) { if (!CULL || tn3 <= tcull) tcull = leaf(refs.w & ~SPB_REF_LEAF, tcull); h3 = false; }
+
+        if (CULL)
+        {
+            h0 = h0 && tn0 <= tcull;
+            h1 = h1 && tn1 <= tcull;
+            h2 = h2 && tn2 <= tcull;
+            h3 = h3 && tn3 <= tcull;
+        }
+        float k0 = h0 ? tn0 : inf, k1 = h1 ? tn1 : inf, k2 = h2 ? tn2 : inf, k3 = h3 ? tn3 : inf;
+        uint32_t r0 = h0 ? refs.x : SPB_REF_EMPTY, r1 = h1 ? refs.y : SPB_REF_EMPTY;
+        uint32_t r2 = h2 ? refs.z : SPB_REF_EMPTY, r3 = h3 ? refs.w : SPB_REF_EMPTY;
+        if (CULL)
+        {
+            // 5-exchange network, ascending by entry distance; invalid lanes (inf) sink
+            sort2(k0, r0, k1, r1);
+            sort2(k2, r2, k3, r3);
+            sort2(k0, r0, k2, r2);
+            sort2(k1, r1, k3, r3);
+            sort2(k1, r1, k2, r2);
+        }
+        // push far to near; continue with the nearest
+        // (the builder bounds the depth so the limit is never reached; an entry that would
+        // overflow is dropped rather than written out of bounds)
+        if (r3 != SPB_REF_EMPTY && sp < stackLimit) { stack[sp] = r3; if (CULL) stackT[sp] = k3; sp++; }
+        if (r2 != SPB_REF_EMPTY && sp < stackLimit) { stack[sp] = r2; if (CULL) stackT[sp] = k2; sp++; }
+        if (r1 != SPB_REF_EMPTY && sp < stackLimit) { stack[sp] = r1; if (CULL) stackT[sp] = k1; sp++; }
+        if (r0 != SPB_REF_EMPTY)
+        {
+            node = r0;
+            continue;
+        }
+        // pop
+        bool found = false;
+        while (sp > stackBase)
+        {
+            sp--;
+            if (!CULL || stackT[sp] <= tcull)
+            {
+                node = stack[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+}
+
+// Slack applied to the running closest distance before it is used to skip subtrees: the slab
+// entry distance of a triangle's own box and its Moller-Trumbore t are different roundings of
+// the same quantity, so a strict comparison could drop an equal-distance winner.
+#define SPB_CULL_SLACK 1.0009765625f /* 1 + 2^-10 */
+
+// sp_RayIntersectMesh (sp_scene.cpp:127-227) on one object-space ray.
+template <bool CULL, bool EXACT>
+SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float tcull,
+                           uint32_t *stack, float *stackT, int stackBase, Counters *counters,
+                           float &bestT, uint32_t &bestSlot, float &bestU, float &bestV)
+{
+    bestT = -1.0f;
+    bestSlot = 0;
+    bestU = bestV = 0.0f;
+    if (meshRoot == SPB_REF_EMPTY) return;
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // Inverse(), math_lib.h:911-915
+    auto leaf = [&](uint32_t slot, float cull) -> float {
+        const v4f *tp = S.tris + (size_t)slot * 3;
+        v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
+        if (counters) counters->triangleTests++;
+        float t, u, v;
+        if (ray_triangle_mt(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
+        {
+            if (t > 0.0f)
+            {
+                if (t < bestT || bestT < 0.0f)
+                {
+                    bestT = t;
+                    bestSlot = slot;
+                    bestU = u;
+                    bestV = v;
+                    float c2 = t * SPB_CULL_SLACK;
+                    if (c2 < cull) cull = c2;
+                }
+            }
+        }
+        return cull;
+    };
+    traverse<CULL, EXACT>(S.nodes, meshRoot, o, inv, tcull, stack, stackT, stackBase, SPB_STACK_SIZE, counters, leaf);
+}
+
+SPB_HD m4 load_m4(const v4f *p)
+{
+    m4 m;
+    m.c[0] = ld4(p + 0);
+    m.c[1] = ld4(p + 1);
+    m.c[2] = ld4(p + 2);
+    m.c[3] = ld4(p + 3);
+    return m;
+}
+
+SPB_HD bool any_nonfinite_inv(f3 d)
+{
+    // 1/d is +-inf when |d| is zero or a tiny denormal; only then can (b-o)*inv be NaN
+    const float tiny = 2.938736e-39f; // 1/tiny is still finite (FLT_MAX ~ 3.4e38)
+    return !(fabsf(d.x) > tiny && fabsf(d.y) > tiny && fabsf(d.z) > tiny);
+}
+
+// sp_RayIntersectScene (sp_scene.cpp:229-339): closest hit over all objects whose world AABB the
+// ray passes.  The winner's surface attributes are resolved afterwards by resolve_hit().
+template <bool CULL>
+SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT,
+                           Counters *counters)
+{
+    Hit best;
+    best.t = -1.0f;
+    best.object = -1;
+    best.slot = 0;
+    best.u = best.v = 0.0f;
+    best.localOrigin = best.localDirection = mk3(0, 0, 0);
+    best.localT = -1.0f;
+    if (S.tlasRoot == SPB_REF_EMPTY) return best;
+
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float inf = u2f(0x7F800000u);
+    const bool worldExact = any_nonfinite_inv(d);
+
+    auto objectLeaf = [&](uint32_t objectIndex, float cull) -> float {
+        v4u info = ld4u(S.objInfo + objectIndex);
+        m4 invModel = load_m4(S.objInv + (size_t)objectIndex * 4);
+        if (counters) counters->objectTests++;
+        // sp_scene.cpp:274-276
+        f3 lo = xform(invModel, o, 1.0f);
+        float scaleLen;
+        f3 ld = normalize3(xform(invModel, d, 0.0f), &scaleLen);
+
+        // distance bound in object space: |M^-1 d| maps world t to local t exactly (affine)
+        float localCull = inf;
+        if (CULL && best.t >= 0.0f) localCull = best.t * scaleLen * SPB_CULL_SLACK;
+
+        float lt, lu, lv;
+        uint32_t lslot;
+        // the object traversal continues on the same stack above the entries of the TLAS
+        int base = SPB_STACK_SIZE / 3;
+        if (any_nonfinite_inv(ld))
+            intersect_mesh<CULL, true>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
+        else
+            intersect_mesh<CULL, false>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
+
+        if (lt >= 0.0f)
+        {
+            // sp_scene.cpp:296-306
+            m4 model = load_m4(S.objModel + (size_t)objectIndex * 4);
+            f3 localHit = add3(lo, mul3(ld, lt));
+            f3 worldHit = xform(model, localHit, 1.0f);
+            float t = dot3(sub3(worldHit, o), d);
+            if (t < best.t || best.t < 0.0f)
+            {
+                best.t = t;
+                best.object = (int32_t)objectIndex;
+                best.slot = lslot;
+                best.u = lu;
+                best.v = lv;
+                best.localOrigin = lo;
+                best.localDirection = ld;
+                best.localT = lt;
+                float c2 = t * SPB_CULL_SLACK;
+                if (t > 0.0f && c2 < cull) cull = c2;
+            }
+        }
+        return cull;
+    };
+
+    if (worldExact)
+        traverse<CULL, true>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf);
+    else
+        traverse<CULL, false>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf);
+    return best;
+}
+
+struct Surface
+{
+    f3 normal;       // world normal (sp_scene.cpp:309-312)
+    float uvx, uvy;  // interpolated texture coordinates (sp_scene.cpp:199-205)
+    uint32_t material;
+    uint32_t triangle; // triangle index within its mesh
+};
+
+// Attributes of the winning triangle (sp_scene.cpp:196-216, 309-312); recomputing e1 x e2 from
+// the same vertices gives the same bits as the value Moller-Trumbore returned.
+SPB_HD Surface resolve_hit(const DScene &S, const Hit &hit)
+{
+    Surface s;
+    v4u info = ld4u(S.objInfo + hit.object);
+    const v4f *tp = S.tris + (size_t)hit.slot * 3;
+    v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
+    uint32_t tri = f2u(a.w);
+    const v4f *sp = S.shade + ((size_t)info.y + tri) * 4;
+    v4f s0 = ld4(sp + 0), s1 = ld4(sp + 1), s2 = ld4(sp + 2), s3 = ld4(sp + 3);
+
+    float u = hit.u, v = hit.v;
+    float w = 1.0f - u - v;
+    // uv = uv0 * w + uv1 * u + uv2 * v
+    s.uvx = s0.w * w + s2.w * u + s3.y * v;
+    s.uvy = s1.w * w + s3.x * u + s3.z * v;
+
+    f3 localNormal;
+    if (info.z != 0)
+    {
+        f3 n0 = mk3(s0.x, s0.y, s0.z), n1 = mk3(s1.x, s1.y, s1.z), n2 = mk3(s2.x, s2.y, s2.z);
+        localNormal = normalize3(add3(add3(mul3(n0, w), mul3(n1, u)), mul3(n2, v)));
+    }
+    else
+    {
+        f3 pa = mk3(a.x, a.y, a.z);
+        localNormal = cross3(sub3(mk3(b.x, b.y, b.z), pa), sub3(mk3(c.x, c.y, c.z), pa));
+    }
+    m4 model = load_m4(S.objModel + (size_t)hit.object * 4);
+    s.normal = normalize3(xform(model, localNormal, 0.0f));
+    s.material = info.w;
+    s.triangle = tri;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// materials and shading
+
+// SampleImageNearest (image.h:3-18).  The reference does not clamp; an index past the end of
+// the image (v == 1 exactly) is undefined there, clamped to the last texel and counted here.
+SPB_HD f3 sample_nearest(const DImage &img, float u, float v, Counters *counters)
+{
+    float fx = u * (float)img.width;
+    float fy = v * (float)img.height;
+    float flx = floorf(fx), fly = floorf(fy);
+    // (u32) of a negative float is undefined in C; saturate at 0
+    uint32_t x = flx > 0.0f ? (flx < 4294967040.0f ? (uint32_t)flx : 0xFFFFFF00u) : 0u;
+    uint32_t y = fly > 0.0f ? (fly < 4294967040.0f ? (uint32_t)fly : 0xFFFFFF00u) : 0u;
+    uint64_t index = (uint64_t)y * img.width + x;
+    uint64_t last = (uint64_t)img.width * img.height - 1;
+    if (index > last)
+    {
+        index = last;
+        if (counters) counters->envClamped++;
+    }
+    v4f p = ld4(img.pixels + index);
+    return mk3(p.x, p.y, p.z);
+}
+
+// SampleImageBilinear (image.h:34-73), clamp-to-edge, Lerp(a,b,t) = a*(1-t) + b*t
+SPB_HD f3 sample_bilinear(const DImage &img, float u, float v)
+{
+    float px = (u * (float)img.width) - 0.5f;
+    float py = (v * (float)img.height) - 0.5f;
+    px = rmax(px, 0.0f);
+    py = rmax(py, 0.0f);
+    uint32_t x0 = (uint32_t)floorf(px), y0 = (uint32_t)floorf(py);
+    if (x0 > img.width - 1) x0 = img.width - 1;
+    if (y0 > img.height - 1) y0 = img.height - 1;
+    uint32_t x1 = x0 + 1, y1 = y0 + 1;
+    float fx = px - (float)x0, fy = py - (float)y0;
+    if (x1 > img.width - 1) x1 = img.width - 1;
+    if (y1 > img.height - 1) y1 = img.height - 1;
+    v4f s0 = ld4(img.pixels + (size_t)y0 * img.width + x0);
+    v4f s1 = ld4(img.pixels + (size_t)y0 * img.width + x1);
+    v4f s2 = ld4(img.pixels + (size_t)y1 * img.width + x0);
+    v4f s3 = ld4(img.pixels + (size_t)y1 * img.width + x1);
+    float ax = 1.0f - fx, ay = 1.0f - fy;
+    f3 t0 = mk3(s0.x * ax + s1.x * fx, s0.y * ax + s1.y * fx, s0.z * ax + s1.z * fx);
+    f3 t1 = mk3(s2.x * ax + s3.x * fx, s2.y * ax + s3.y * fx, s2.z * ax + s3.z * fx);
+    return mk3(t0.x * ay + t1.x * fy, t0.y * ay + t1.y * fy, t0.z * ay + t1.z * fy);
+}
+
+struct MaterialOut { f3 albedo, emission; float roughness; };
+
+// sp_FindMaterialById + sp_EvaluateMaterial (sp_material_system.cpp:15-29, 59-105) and the
+// missing-material fallback of ComputeRadianceForPath (simd_path_tracer.cpp:122-133)
+template <int MATH, int ENVFILTER>
+SPB_HD MaterialOut evaluate_material(const DMaterials &M, uint32_t materialId, f3 outgoingDir,
+                                     float uvx, float uvy, Counters *counters)
+{
+    MaterialOut out;
+    out.albedo = mk3(0, 0, 0);
+    out.emission = mk3(0, 0, 0);
+    out.roughness = 0.0f;
+    int slot = -1;
+    for (uint32_t i = 0; i < M.count; ++i)
+    {
+        if (M.keys[i] == materialId)
+        {
+            slot = (int)i;
+            break;
+        }
+    }
+    if (slot < 0)
+    {
+        out.emission = mk3(1.0f, 0.0f, 1.0f);
+        return out;
+    }
+    int ai = M.albedoImage[slot];
+    if (ai >= 0)
+        out.albedo = sample_nearest(M.images[ai], uvx, uvy, counters);
+    else
+        out.albedo = mk3(M.albedo[slot][0], M.albedo[slot][1], M.albedo[slot][2]);
+
+    int ei = M.emissionImage[slot];
+    if (ei >= 0)
+    {
+        // ToSphericalCoordinates(-outgoingDir) (math_lib.h:849-860), MapToEquirectangular
+        // (math_lib.h:873-884), then uv.y = 1 - uv.y (sp_material_system.cpp:88-93)
+        f3 dir = neg3(outgoingDir);
+        float inc = m_atan2<MATH>(sqrtf(dir.x * dir.x + dir.z * dir.z), dir.y);
+        float az = m_atan2<MATH>(dir.z, dir.x);
+        if (az < 0.0f) az += 2.0f * SPB_PI;
+        float eu = az / (2.0f * SPB_PI);
+        float ev = m_cos<MATH>(inc) * 0.5f + 0.5f;
+        ev = 1.0f - ev;
+        if (ENVFILTER == 0)
+            out.emission = sample_nearest(M.images[ei], eu, ev, counters);
+        else
+            out.emission = sample_bilinear(M.images[ei], eu, ev);
+    }
+    else
+        out.emission = mk3(M.emission[slot][0], M.emission[slot][1], M.emission[slot][2]);
+    out.roughness = M.roughness[slot];
+    return out;
+}
+
+// One iteration of ComputeRadianceForPath (simd_path_tracer.cpp:113-171) split in two: the part
+// that does not depend on the radiance arriving from the next vertex (emission E, BRDF weight
+// W = kD*albedo/pi + specular, cosine) is evaluated when the vertex is created ...
+struct VertexTerms { f3 E, W; float cosine; };
+
+template <int MATH, int ENVFILTER>
+SPB_HD VertexTerms vertex_terms(const DMaterials &M, uint32_t materialId, f3 L, f3 N, f3 V,
+                                float uvx, float uvy, Counters *counters)
+{
+    MaterialOut mo = evaluate_material<MATH, ENVFILTER>(M, materialId, V, uvx, uvy, counters);
+    VertexTerms vt;
+    vt.E = mo.emission;
+    vt.cosine = rmax(0.0f, dot3(N, L));
+
+    f3 H = normalize3(add3(L, V));
+    // FresnelSchlick(Max(Dot(H,V),0), F0 = 0.04) (simd_path_tracer.cpp:65-70)
+    float p5 = m_pow5<MATH>(1.0f - rmax(dot3(H, V), 0.0f));
+    float Fx = 0.04f + (1.0f - 0.04f) * p5;
+    f3 F = mk3(Fx, Fx, Fx);
+    f3 kD = mk3(1.0f - F.x, 1.0f - F.y, 1.0f - F.z);
+    float oneOverPI = 1.0f / SPB_PI;
+
+    float roughness = mo.roughness;
+    // DistributionGGX (:72-84)
+    float a = roughness * roughness;
+    float a2 = a * a;
+    float NdotH = rmax(dot3(N, H), 0.0f);
+    float NdotH2 = NdotH * NdotH;
+    float dd = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    dd = SPB_PI * dd * dd;
+    float NDF = a2 / dd;
+    // GeometrySmith (:86-105)
+    float NdotV = rmax(dot3(N, V), 0.0f);
+    float NdotL = rmax(dot3(N, L), 0.0f);
+    float r1 = (roughness + 1.0f);
+    float k = (r1 * r1) / 8.0f;
+    float ggx2 = NdotV / (NdotV * (1.0f - k) + k);
+    float ggx1 = NdotL / (NdotL * (1.0f - k) + k);
+    float G = ggx1 * ggx2;
+
+    f3 numerator = mul3(F, NDF * G);
+    float denominator = 4.0f * rmax(dot3(N, V), 0.0f) * rmax(dot3(N, L), 0.0f) + 0.0001f;
+    f3 specular = mul3(numerator, 1.0f / denominator);
+    vt.W = add3(mul3(had3(kD, mo.albedo), oneOverPI), specular);
+    return vt;
+}
+
+// ... and the part that does (clamp, multiply, add emission) runs back to front afterwards.
+SPB_HD f3 fold_radiance(const VertexTerms &vt, f3 incoming, float clampValue)
+{
+    if (clampValue > 0.0f)
+    {
+        incoming.x = rmin(rmax(incoming.x, 0.0f), clampValue);
+        incoming.y = rmin(rmax(incoming.y, 0.0f), clampValue);
+        incoming.z = rmin(rmax(incoming.z, 0.0f), clampValue);
+    }
+    return add3(vt.E, mul3(had3(vt.W, incoming), vt.cosine));
+}
+
+// RandomDirectionOnHemisphere (math_lib.h:932-946)
+template <int MATH>
+SPB_HD f3 random_hemisphere(f3 normal, uint32_t &rng)
+{
+    float theta = SPB_PI * rand_unilateral(rng);
+    float phi = SPB_PI * rand_bilateral(rng);
+    float st = m_sin<MATH>(theta);
+    f3 dir;
+    dir.x = st * m_cos<MATH>(phi);
+    dir.z = st * m_sin<MATH>(phi);
+    dir.y = m_cos<MATH>(theta);
+    if (dot3(dir, normal) < 0.0f) dir = neg3(dir);
+    return dir;
+}
+
+struct PathCounters { uint32_t rays, hits, misses; };
+
+// One light path = one iteration of the sample loop of sp_PathTraceTile
+// (simd_path_tracer.cpp:216-320).  `rng` continues the caller's stream.
+template <int MATH, int ENVFILTER, bool CULL>
+SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, uint32_t x,
+                     uint32_t y, uint32_t &rng, uint32_t bounceCount, float clampValue,
+                     uint32_t *stack, float *stackT, PathCounters &pc, Counters *counters)
+{
+    f3 o, d;
+    primary_ray(cam, x, y, rng, o, d);
+
+    VertexTerms path[SPB_MAX_BOUNCES];
+    uint32_t pathLength = 0;
+    for (uint32_t bounce = 0; bounce < bounceCount; ++bounce)
+    {
+        Hit hit = intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+        pc.rays++;
+        f3 V = neg3(d);
+        if (hit.t > 0.0f)
+        {
+            Surface sf = resolve_hit(S, hit);
+            f3 P = add3(o, mul3(d, hit.t));
+            f3 L = random_hemisphere<MATH>(sf.normal, rng);
+            path[pathLength++] =
+                vertex_terms<MATH, ENVFILTER>(M, sf.material, L, sf.normal, V, sf.uvx, sf.uvy, counters);
+            o = add3(P, mul3(sf.normal, 0.0001f));
+            d = L;
+            pc.hits++;
+        }
+        else
+        {
+            f3 zero = mk3(0.0f, 0.0f, 0.0f);
+            path[pathLength++] =
+                vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, V, 0.0f, 0.0f, counters);
+            pc.misses++;
+            break;
+        }
+    }
+    f3 radiance = mk3(0.0f, 0.0f, 0.0f);
+    for (int i = (int)pathLength - 1; i >= 0; --i)
+    {
+        radiance = fold_radiance(path[i], radiance, clampValue);
+    }
+    return radiance;
+}
+
+} // namespace spb
