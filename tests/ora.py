@@ -12,6 +12,7 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(_ROOT, "oracle")
 PORT_LIB = os.path.join(ORACLE_DIR, "libsporacle.so")
+PORT_DM_LIB = os.path.join(ORACLE_DIR, "libsporacle_dm.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libspref.so")
 REF_DM_LIB = os.path.join(ORACLE_DIR, "_ref", "libspref_dm.so")
 
@@ -408,3 +409,7 @@ def load_ref_dm():
 
 def load_port():
     return OracleLib(PORT_LIB)
+
+
+def load_port_dm():
+    return OracleLib(PORT_DM_LIB)

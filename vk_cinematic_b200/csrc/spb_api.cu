@@ -1,0 +1,1105 @@
+// spb_api.cu -- the C ABI of libspb200.so (include/sp_b200.h): scene capture, one-time upload,
+// kernel launches, result copies.  Host logic only; the arithmetic of the path lives in
+// spb_core.cuh and runs in the kernels of spb_kernels.cu.  There is no CPU implementation of any
+// compute entry point in this library: without a usable CUDA device they abort.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "spb_capture.h"
+#include "spb_kernels.cuh"
+
+using namespace spb;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// logging / failure (reference convention: Assert -> LogMessage(file:line) -> abort,
+// platform.h:18-22; tolerate a NULL sink)
+sp_b200_LogFn g_log = nullptr;
+
+void log_message(const char *fmt, ...)
+{
+    char buffer[1024];
+    va_list args;
+    va_start(args, fmt);
+    vsnprintf(buffer, sizeof(buffer), fmt, args);
+    va_end(args);
+    if (g_log) g_log(buffer);
+    else fprintf(stderr, "[sp_b200] %s\n", buffer);
+}
+
+#define SPB_ASSERT(X)                                                                   \
+    do {                                                                                \
+        if (!(X)) {                                                                     \
+            log_message("%s:%d: Assertion failed!\n\t%s", __FILE__, __LINE__, #X);      \
+            abort();                                                                    \
+        }                                                                               \
+    } while (0)
+
+#define SPB_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t err__ = (call);                                                     \
+        if (err__ != cudaSuccess) {                                                     \
+            log_message("%s:%d: CUDA error %s (%s) in %s -- libspb200 has no CPU path", \
+                        __FILE__, __LINE__, cudaGetErrorName(err__),                    \
+                        cudaGetErrorString(err__), #call);                              \
+            abort();                                                                    \
+        }                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+struct DeviceBuffer
+{
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need)
+    {
+        if (need <= bytes) return;
+        if (ptr) SPB_CUDA(cudaFree(ptr));
+        size_t grow = need + need / 4;
+        SPB_CUDA(cudaMalloc(&ptr, grow));
+        bytes = grow;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+struct DeviceScene
+{
+    uint32_t magic = 0x4E435353u; // "SSCN"
+    DeviceBuffer nodes, tris, shade, objInv, objModel, objInfo;
+    DScene d;
+    uint64_t triangleCount = 0;
+    uint32_t nodeCount = 0;
+    uint32_t maxDepth = 0;
+    size_t deviceBytes = 0;
+    ~DeviceScene()
+    {
+        nodes.release(); tris.release(); shade.release();
+        objInv.release(); objModel.release(); objInfo.release();
+    }
+};
+
+struct TextureEntry
+{
+    DeviceBuffer buffer;
+    uint32_t width = 0, height = 0;
+};
+
+struct Library
+{
+    std::recursive_mutex mutex;
+    bool initialized = false;
+    int device = 0;
+    cudaStream_t stream = 0;
+    sp_b200_Params params;
+    bool statsEnabled = false;
+    sp_b200_Stats lastStats;
+    std::map<void *, std::shared_ptr<MeshAccel>> meshes;
+    std::map<void *, std::unique_ptr<DeviceScene>> scenes;
+    std::map<const float *, std::unique_ptr<TextureEntry>> textures;
+    std::unique_ptr<DeviceScene> emptyScene;
+    DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
+    cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
+
+    Library()
+    {
+        memset(&lastStats, 0, sizeof(lastStats));
+        params.samplesPerPixel = 1;
+        params.bounceCount = 3;
+        params.radianceClamp = 10.0f;
+        params.envFilter = SP_B200_ENV_NEAREST;
+        params.mathMode = SP_B200_MATH_F64_ROUNDED;
+        params.cullByDistance = 1;
+        params.tileWidth = 64;
+        params.tileHeight = 64;
+    }
+};
+
+Library &lib()
+{
+    static Library *instance = new Library(); // never destroyed: safe at process exit
+    return *instance;
+}
+
+void ensure_init()
+{
+    Library &L = lib();
+    if (L.initialized) return;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+    {
+        log_message("libspb200: no usable CUDA device (%s). This library is GPU-only; there is "
+                    "no CPU fallback.", err != cudaSuccess ? cudaGetErrorString(err) : "0 devices");
+        abort();
+    }
+    SPB_CUDA(cudaSetDevice(L.device));
+    SPB_CUDA(cudaEventCreate(&L.evStart));
+    SPB_CUDA(cudaEventCreate(&L.evKernel0));
+    SPB_CUDA(cudaEventCreate(&L.evKernel1));
+    SPB_CUDA(cudaEventCreate(&L.evEnd));
+    L.initialized = true;
+}
+
+KernelConfig kernel_config()
+{
+    Library &L = lib();
+    KernelConfig c;
+    c.math = L.params.mathMode == SP_B200_MATH_FAST_F32 ? 1 : 0;
+    c.envFilter = L.params.envFilter == SP_B200_ENV_BILINEAR ? 1 : 0;
+    c.cull = L.params.cullByDistance ? 1 : 0;
+    c.stats = L.statsEnabled ? 1 : 0;
+    return c;
+}
+
+template <class T>
+void upload(DeviceBuffer &dst, const std::vector<T> &src, cudaStream_t stream)
+{
+    size_t bytes = src.size() * sizeof(T);
+    dst.ensure(bytes ? bytes : 16);
+    if (bytes) SPB_CUDA(cudaMemcpyAsync(dst.ptr, src.data(), bytes, cudaMemcpyHostToDevice, stream));
+}
+
+std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
+{
+    Library &L = lib();
+    auto ds = std::make_unique<DeviceScene>();
+    upload(ds->nodes, fs.nodes, L.stream);
+    upload(ds->tris, fs.tris, L.stream);
+    upload(ds->shade, fs.shade, L.stream);
+    upload(ds->objInv, fs.objInv, L.stream);
+    upload(ds->objModel, fs.objModel, L.stream);
+    upload(ds->objInfo, fs.objInfo, L.stream);
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    ds->d.nodes = (const v4f *)ds->nodes.ptr;
+    ds->d.tris = (const v4f *)ds->tris.ptr;
+    ds->d.shade = (const v4f *)ds->shade.ptr;
+    ds->d.objInv = (const v4f *)ds->objInv.ptr;
+    ds->d.objModel = (const v4f *)ds->objModel.ptr;
+    ds->d.objInfo = (const v4u *)ds->objInfo.ptr;
+    ds->d.tlasRoot = fs.tlasRoot;
+    ds->d.objectCount = fs.objectCount;
+    ds->triangleCount = fs.triangleCount;
+    ds->nodeCount = (uint32_t)(fs.nodes.size() / 8);
+    ds->maxDepth = fs.maxDepth;
+    ds->deviceBytes = (fs.nodes.size() + fs.tris.size() + fs.shade.size() + fs.objInv.size() +
+                       fs.objModel.size()) * sizeof(v4f) + fs.objInfo.size() * sizeof(v4u);
+    return ds;
+}
+
+std::shared_ptr<MeshAccel> find_mesh(const sp_Mesh &mesh)
+{
+    Library &L = lib();
+    if (!mesh.midphaseTree.root) return nullptr;
+    auto it = L.meshes.find(mesh.midphaseTree.root);
+    if (it == L.meshes.end())
+    {
+        log_message("sp_Mesh::midphaseTree was not built by sp_BuildMeshMidphase of libspb200");
+        abort();
+    }
+    return it->second;
+}
+
+DeviceScene *find_scene(sp_Scene *scene)
+{
+    Library &L = lib();
+    if (scene && scene->broadphaseTree.root)
+    {
+        auto it = L.scenes.find(scene->broadphaseTree.root);
+        if (it == L.scenes.end())
+        {
+            log_message("sp_Scene::broadphaseTree was not built by sp_BuildSceneBroadphase of libspb200");
+            abort();
+        }
+        return it->second.get();
+    }
+    // a scene that was never built behaves like the reference's NULL root (bvh.cpp:218-229):
+    // every ray misses
+    if (!L.emptyScene)
+    {
+        std::vector<ObjectInstance> none;
+        L.emptyScene = upload_scene(flatten_scene(none));
+    }
+    return L.emptyScene.get();
+}
+
+// Device copies of HdrImage pixel buffers, keyed by the host pointer (the reference aliases the
+// caller's pixels; contents are assumed immutable until sp_b200_FlushTextureCache).
+const v4f *device_texture(const HdrImage &image)
+{
+    Library &L = lib();
+    if (!image.pixels || image.width == 0 || image.height == 0) return nullptr;
+    auto it = L.textures.find(image.pixels);
+    if (it != L.textures.end() && it->second->width == image.width && it->second->height == image.height)
+        return (const v4f *)it->second->buffer.ptr;
+    auto entry = std::make_unique<TextureEntry>();
+    size_t bytes = (size_t)image.width * image.height * 16;
+    entry->buffer.ensure(bytes);
+    entry->width = image.width;
+    entry->height = image.height;
+    SPB_CUDA(cudaMemcpyAsync(entry->buffer.ptr, image.pixels, bytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    const v4f *p = (const v4f *)entry->buffer.ptr;
+    L.textures[image.pixels] = std::move(entry);
+    return p;
+}
+
+// Uploads the material system (textures resolved) and returns the device pointer.
+const DMaterials *upload_materials(const sp_MaterialSystem *ms, size_t *bytesOut = nullptr)
+{
+    Library &L = lib();
+    static sp_MaterialSystem emptySystem; // zero-initialised
+    if (!ms) ms = &emptySystem;
+    const v4f *pixels[SPB_MAX_IMAGES] = {};
+    for (uint32_t i = 0; i < ms->imageCount && i < SPB_MAX_IMAGES; ++i)
+        pixels[i] = device_texture(ms->images[i]);
+    DMaterials dm;
+    convert_materials(ms, pixels, &dm);
+    // an image that could not be uploaded (NULL pixels) must not be sampled
+    for (uint32_t i = 0; i < dm.count; ++i)
+    {
+        if (dm.albedoImage[i] >= 0 && !dm.images[dm.albedoImage[i]].pixels) dm.albedoImage[i] = -1;
+        if (dm.emissionImage[i] >= 0 && !dm.images[dm.emissionImage[i]].pixels) dm.emissionImage[i] = -1;
+    }
+    L.materials.ensure(sizeof(DMaterials));
+    SPB_CUDA(cudaMemcpyAsync(L.materials.ptr, &dm, sizeof(dm), cudaMemcpyHostToDevice, L.stream));
+    if (bytesOut) *bytesOut = sizeof(dm);
+    return (const DMaterials *)L.materials.ptr;
+}
+
+unsigned long long *reset_counters(size_t extraSlots = 0)
+{
+    Library &L = lib();
+    size_t bytes = (CTR_COUNT + extraSlots) * sizeof(unsigned long long);
+    L.counters.ensure(bytes);
+    SPB_CUDA(cudaMemsetAsync(L.counters.ptr, 0, bytes, L.stream));
+    return (unsigned long long *)L.counters.ptr;
+}
+
+void add_metrics(sp_Metrics *metrics, const unsigned long long *c, float kernelMs)
+{
+    if (!metrics) return;
+    // counters are incremented, CyclesElapsed is overwritten (simd_path_tracer.cpp:242,320,344);
+    // "cycles" are device nanoseconds here
+    metrics->values[sp_Metric_CyclesElapsed] = (u64)((double)kernelMs * 1.0e6);
+    metrics->values[sp_Metric_PathsTraced] += c[CTR_PATHS];
+    metrics->values[sp_Metric_RaysTraced] += c[CTR_RAYS];
+    metrics->values[sp_Metric_RayHitCount] += c[CTR_HITS];
+    metrics->values[sp_Metric_RayMissCount] += c[CTR_MISSES];
+    metrics->values[sp_Metric_RayIntersectMesh_MidphaseAabbTestCount] += c[CTR_NODE_VISITS] * 4;
+    metrics->values[sp_Metric_RayIntersectMesh_TestsPerformed] += c[CTR_OBJECT_TESTS];
+}
+
+void record_stats(const unsigned long long *c, float kernelMs, float totalMs)
+{
+    Library &L = lib();
+    L.lastStats.rays = c[CTR_RAYS];
+    L.lastStats.nodeVisits = c[CTR_NODE_VISITS];
+    L.lastStats.triangleTests = c[CTR_TRIANGLE_TESTS];
+    L.lastStats.objectTests = c[CTR_OBJECT_TESTS];
+    L.lastStats.envClampedLookups = c[CTR_ENV_CLAMPED];
+    L.lastStats.kernelMs = kernelMs;
+    L.lastStats.totalMs = totalMs;
+}
+
+spbh::M4 to_m4(const mat4 &m)
+{
+    spbh::M4 r;
+    for (int c = 0; c < 4; ++c) r.c[c] = spbh::V4{m.columns[c].x, m.columns[c].y, m.columns[c].z, m.columns[c].w};
+    return r;
+}
+mat4 from_m4(const spbh::M4 &m)
+{
+    mat4 r;
+    for (int c = 0; c < 4; ++c) r.columns[c] = vec4{m.c[c].x, m.c[c].y, m.c[c].z, m.c[c].w};
+    return r;
+}
+
+// device scene holding just this mesh as object 0 with an identity transform
+DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t smooth)
+{
+    if (!accel->deviceScene)
+    {
+        ObjectInstance ob;
+        ob.mesh = accel;
+        ob.material = 0;
+        ob.smooth = smooth;
+        ob.model = spbh::identity();
+        ob.invModel = spbh::identity();
+        for (int k = 0; k < 3; ++k)
+        {
+            ob.aabbMin[k] = accel->bvh.rootMin[k];
+            ob.aabbMax[k] = accel->bvh.rootMax[k];
+        }
+        std::vector<ObjectInstance> one(1, ob);
+        accel->deviceScene = upload_scene(flatten_scene(one)).release();
+    }
+    return (DeviceScene *)accel->deviceScene;
+}
+
+} // namespace
+
+// =============================================================================================
+// library control
+
+extern "C" int sp_b200_Init(int device)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (L.initialized && device != L.device)
+    {
+        log_message("sp_b200_Init: already initialised on device %d", L.device);
+        return 1;
+    }
+    L.device = device;
+    ensure_init();
+    return 0;
+}
+
+extern "C" void sp_b200_Shutdown(void)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (L.initialized) cudaDeviceSynchronize();
+    for (auto &m : L.meshes)
+        if (m.second->deviceScene)
+        {
+            delete (DeviceScene *)m.second->deviceScene;
+            m.second->deviceScene = nullptr;
+        }
+    L.meshes.clear();
+    L.scenes.clear();
+    L.textures.clear();
+    L.emptyScene.reset();
+    L.image.release(); L.counters.release(); L.materials.release();
+    L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
+    if (L.initialized)
+    {
+        cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
+        cudaEventDestroy(L.evKernel1); cudaEventDestroy(L.evEnd);
+    }
+    L.initialized = false;
+}
+
+extern "C" void sp_b200_SetLogCallback(sp_b200_LogFn fn) { g_log = fn; }
+extern "C" void sp_b200_SetStream(void *cudaStream) { lib().stream = (cudaStream_t)cudaStream; }
+
+extern "C" void sp_b200_DefaultParams(sp_b200_Params *params) { *params = Library().params; }
+
+extern "C" void sp_b200_SetParams(const sp_b200_Params *params)
+{
+    SPB_ASSERT(params->samplesPerPixel >= 1);
+    SPB_ASSERT(params->bounceCount >= 1 && params->bounceCount <= SPB_MAX_BOUNCES);
+    SPB_ASSERT(params->tileWidth >= 1 && params->tileHeight >= 4 && params->tileHeight % 4 == 0);
+    lib().params = *params;
+}
+extern "C" void sp_b200_GetParams(sp_b200_Params *params) { *params = lib().params; }
+extern "C" void sp_b200_GetLastStats(sp_b200_Stats *stats) { *stats = lib().lastStats; }
+extern "C" void sp_b200_EnableStats(int enable) { lib().statsEnabled = enable != 0; }
+
+extern "C" void sp_b200_FlushTextureCache(void)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (L.initialized) cudaDeviceSynchronize();
+    L.textures.clear();
+}
+
+extern "C" u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame)
+{
+    return stream_seed(pixelIndex, sample, frame); // integer-only: identical on host and device
+}
+
+// =============================================================================================
+// scene construction (sp_scene.cpp)
+
+extern "C" void sp_InitializeScene(sp_Scene *scene, MemoryArena *arena)
+{
+    // The reference sub-allocates 512 KiB for the broadphase (sp_scene.cpp:1-5); the library keeps
+    // its structures in its own memory and only records an empty arena.
+    (void)arena;
+    scene->memoryArena.base = nullptr;
+    scene->memoryArena.size = 0;
+    scene->memoryArena.capacity = 0;
+}
+
+extern "C" sp_Mesh sp_CreateMesh(VertexPNT *vertices, u32 vertexCount, u32 *indices,
+                                 u32 indexCount, b32 useSmoothShading)
+{
+    sp_Mesh result;
+    memset(&result, 0, sizeof(result));
+    result.vertices = vertices;
+    result.vertexCount = vertexCount;
+    result.indices = indices;
+    result.indexCount = indexCount;
+    result.useSmoothShading = useSmoothShading;
+    return result;
+}
+
+extern "C" void sp_BuildMeshMidphase(sp_Mesh *mesh, MemoryArena *arena, MemoryArena *tempArena)
+{
+    (void)arena;
+    (void)tempArena;
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    SPB_ASSERT(mesh->indexCount % 3 == 0);
+    for (u32 i = 0; i < mesh->indexCount; ++i) SPB_ASSERT(mesh->indices[i] < mesh->vertexCount);
+    std::shared_ptr<MeshAccel> accel =
+        build_mesh_accel(mesh->vertices, mesh->vertexCount, mesh->indices, mesh->indexCount);
+    void *handle = accel.get();
+    L.meshes[handle] = accel;
+    mesh->midphaseTree.root = handle;
+    mesh->midphaseTree.memoryPool.storage = nullptr;
+    mesh->midphaseTree.memoryPool.objectSize = (u32)sizeof(Node4);
+    mesh->midphaseTree.memoryPool.capacity = (u32)accel->bvh.nodes.size();
+    mesh->midphaseTree.memoryPool.headIndex = 0xFFFFFFFFu;
+}
+
+extern "C" void sp_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material, vec3 position,
+                                    quat orientation, vec3 scale)
+{
+    SPB_ASSERT(mesh.vertices != NULL);
+    SPB_ASSERT(mesh.vertexCount > 0);
+    spbh::M4 model, invModel;
+    float mn[3], mx[3];
+    compute_object_transform(nullptr, mesh.vertices, mesh.vertexCount, position, orientation,
+                             scale, &model, &invModel, mn, mx);
+    SPB_ASSERT(scene->objectCount < SP_SCENE_MAX_OBJECTS);
+    u32 index = scene->objectCount++;
+    scene->aabbMin[index] = vec3{mn[0], mn[1], mn[2]};
+    scene->aabbMax[index] = vec3{mx[0], mx[1], mx[2]};
+    scene->invModelMatrices[index] = from_m4(invModel);
+    scene->modelMatrices[index] = from_m4(model);
+    scene->meshes[index] = mesh;
+    scene->materials[index] = material;
+}
+
+extern "C" void sp_b200_ReleaseScene(sp_Scene *scene)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (scene->broadphaseTree.root)
+    {
+        if (L.initialized) cudaDeviceSynchronize();
+        L.scenes.erase(scene->broadphaseTree.root);
+        scene->broadphaseTree.root = nullptr;
+    }
+}
+
+extern "C" void sp_b200_ReleaseMesh(sp_Mesh *mesh)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    auto it = L.meshes.find(mesh->midphaseTree.root);
+    if (it != L.meshes.end())
+    {
+        if (it->second->deviceScene)
+        {
+            if (L.initialized) cudaDeviceSynchronize();
+            delete (DeviceScene *)it->second->deviceScene;
+            it->second->deviceScene = nullptr;
+        }
+        L.meshes.erase(it);
+    }
+    mesh->midphaseTree.root = nullptr;
+}
+
+extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    // a rebuild of the same sp_Scene replaces its previous device copy (the reference app
+    // rebuilds per render, main.cpp:1545-1552)
+    if (scene->broadphaseTree.root && L.scenes.count(scene->broadphaseTree.root))
+        sp_b200_ReleaseScene(scene);
+    scene->broadphaseTree.root = nullptr;
+
+    std::vector<ObjectInstance> objects(scene->objectCount);
+    for (u32 i = 0; i < scene->objectCount; ++i)
+    {
+        ObjectInstance &ob = objects[i];
+        ob.mesh = find_mesh(scene->meshes[i]);
+        ob.material = scene->materials[i];
+        ob.smooth = scene->meshes[i].useSmoothShading ? 1u : 0u;
+        ob.model = to_m4(scene->modelMatrices[i]);
+        ob.invModel = to_m4(scene->invModelMatrices[i]);
+        ob.aabbMin[0] = scene->aabbMin[i].x; ob.aabbMin[1] = scene->aabbMin[i].y; ob.aabbMin[2] = scene->aabbMin[i].z;
+        ob.aabbMax[0] = scene->aabbMax[i].x; ob.aabbMax[1] = scene->aabbMax[i].y; ob.aabbMax[2] = scene->aabbMax[i].z;
+    }
+    FlatScene fs = flatten_scene(objects);
+    std::unique_ptr<DeviceScene> ds = upload_scene(fs);
+    void *handle = ds.get();
+    scene->broadphaseTree.root = handle;
+    scene->broadphaseTree.memoryPool.storage = nullptr;
+    scene->broadphaseTree.memoryPool.objectSize = (u32)sizeof(Node4);
+    scene->broadphaseTree.memoryPool.capacity = ds->nodeCount;
+    scene->broadphaseTree.memoryPool.headIndex = 0xFFFFFFFFu;
+    L.scenes[handle] = std::move(ds);
+}
+
+// =============================================================================================
+// ray queries
+
+extern "C" int sp_b200_RayIntersectSceneBatch(sp_Scene *scene, u32 count, const vec3 *rayOrigins,
+                                              const vec3 *rayDirections,
+                                              sp_RayIntersectSceneResult *results,
+                                              i32 *triangleIndex, i32 *objectIndex,
+                                              sp_Metrics *metrics)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    if (count == 0) return 0;
+    DeviceScene *ds = find_scene(scene);
+    size_t rayBytes = (size_t)count * 12;
+    L.scratchA.ensure(rayBytes);
+    L.scratchB.ensure(rayBytes);
+    L.scratchC.ensure((size_t)count * sizeof(HitRecord));
+    unsigned long long *ctr = reset_counters();
+    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, rayOrigins, rayBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(L.scratchB.ptr, rayDirections, rayBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    launch_intersect_batch(kernel_config(), ds->d, count, (const float *)L.scratchA.ptr,
+                           (const float *)L.scratchB.ptr, (HitRecord *)L.scratchC.ptr, ctr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    std::vector<HitRecord> host(count);
+    unsigned long long c[CTR_COUNT];
+    SPB_CUDA(cudaMemcpyAsync(host.data(), L.scratchC.ptr, (size_t)count * sizeof(HitRecord), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    float kernelMs = 0, totalMs = 0;
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    for (u32 i = 0; i < count; ++i)
+    {
+        if (results)
+        {
+            results[i].t = host[i].t;
+            results[i].materialId = host[i].materialId;
+            results[i].normal = vec3{host[i].nx, host[i].ny, host[i].nz};
+            results[i].uv = vec2{host[i].u, host[i].v};
+        }
+        if (triangleIndex) triangleIndex[i] = host[i].triangle;
+        if (objectIndex) objectIndex[i] = host[i].object;
+    }
+    if (metrics)
+    {
+        // sp_RayIntersectScene itself only touches the intersection counters
+        metrics->values[sp_Metric_RayIntersectMesh_MidphaseAabbTestCount] += c[CTR_NODE_VISITS] * 4;
+        metrics->values[sp_Metric_RayIntersectMesh_TestsPerformed] += c[CTR_OBJECT_TESTS];
+        metrics->values[sp_Metric_CyclesElapsed_RayIntersectScene] += (u64)((double)kernelMs * 1.0e6);
+    }
+    record_stats(c, kernelMs, totalMs);
+    return 0;
+}
+
+extern "C" sp_RayIntersectSceneResult sp_RayIntersectScene(sp_Scene *scene, vec3 rayOrigin,
+                                                           vec3 rayDirection, sp_Metrics *metrics)
+{
+    sp_RayIntersectSceneResult result;
+    memset(&result, 0, sizeof(result));
+    sp_b200_RayIntersectSceneBatch(scene, 1, &rayOrigin, &rayDirection, &result, nullptr, nullptr, metrics);
+    return result;
+}
+
+extern "C" sp_RayIntersectMeshResult sp_RayIntersectMesh(sp_Mesh mesh, vec3 rayOrigin,
+                                                         vec3 rayDirection, sp_Metrics *metrics)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    sp_RayIntersectMeshResult result;
+    memset(&result, 0, sizeof(result));
+    result.triangleIntersection.t = -1.0f;
+    std::shared_ptr<MeshAccel> accel = find_mesh(mesh);
+    if (!accel) return result; // midphase never built: NULL root, no intersections
+    DeviceScene *ds = mesh_device_scene(accel, mesh.useSmoothShading);
+    L.scratchA.ensure(32);
+    L.scratchC.ensure(sizeof(HitRecord));
+    float ray[6] = {rayOrigin.x, rayOrigin.y, rayOrigin.z, rayDirection.x, rayDirection.y, rayDirection.z};
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, ray, sizeof(ray), cudaMemcpyHostToDevice, L.stream));
+    launch_intersect_mesh(kernel_config(), ds->d, mesh.useSmoothShading ? 1u : 0u,
+                          (const float *)L.scratchA.ptr, (const float *)L.scratchA.ptr + 3,
+                          (HitRecord *)L.scratchC.ptr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    HitRecord h;
+    SPB_CUDA(cudaMemcpyAsync(&h, L.scratchC.ptr, sizeof(h), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    result.triangleIntersection.t = h.t;
+    result.triangleIntersection.uv = vec2{h.u, h.v};
+    result.triangleIntersection.normal = vec3{h.nx, h.ny, h.nz};
+    (void)metrics;
+    return result;
+}
+
+extern "C" u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 rayDirection,
+                                             u32 *leafIndices, u32 maxIntersections,
+                                             b32 *errorOccurred)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    if (errorOccurred) *errorOccurred = 0;
+    std::shared_ptr<MeshAccel> accel = find_mesh(mesh);
+    if (!accel) return 0;
+    DeviceScene *ds = mesh_device_scene(accel, mesh.useSmoothShading);
+    L.scratchA.ensure(32);
+    L.scratchB.ensure((size_t)(maxIntersections ? maxIntersections : 1) * 4);
+    L.scratchC.ensure(16);
+    float ray[6] = {rayOrigin.x, rayOrigin.y, rayOrigin.z, rayDirection.x, rayDirection.y, rayDirection.z};
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, ray, sizeof(ray), cudaMemcpyHostToDevice, L.stream));
+    launch_collect_leaves(ds->d, (const float *)L.scratchA.ptr, (const float *)L.scratchA.ptr + 3,
+                          (uint32_t *)L.scratchB.ptr, maxIntersections, (uint32_t *)L.scratchC.ptr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    uint32_t ce[2];
+    SPB_CUDA(cudaMemcpyAsync(ce, L.scratchC.ptr, sizeof(ce), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    if (ce[0] && leafIndices)
+        SPB_CUDA(cudaMemcpy(leafIndices, L.scratchB.ptr, (size_t)ce[0] * 4, cudaMemcpyDeviceToHost));
+    if (errorOccurred) *errorOccurred = ce[1];
+    return ce[0];
+}
+
+extern "C" void sp_b200_MeshTreeInfo(sp_Mesh mesh, sp_b200_TreeInfo *info)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    memset(info, 0, sizeof(*info));
+    std::shared_ptr<MeshAccel> accel = find_mesh(mesh);
+    if (!accel) return;
+    const Bvh4 &bvh = accel->bvh;
+    info->leafCount = (u32)bvh.slotPrim.size();
+    info->nodeCount = (u32)bvh.nodes.size();
+    info->maxDepth = bvh.maxDepth;
+    info->rootMin = vec3{bvh.rootMin[0], bvh.rootMin[1], bvh.rootMin[2]};
+    info->rootMax = vec3{bvh.rootMax[0], bvh.rootMax[1], bvh.rootMax[2]};
+    // reachability and containment by walking the tree (cf. test_bvh.cpp:74-163)
+    std::vector<uint8_t> seen(accel->triangleCount, 0);
+    bool contained = true;
+    std::vector<uint32_t> work;
+    if (!bvh.nodes.empty()) work.push_back(0);
+    while (!work.empty())
+    {
+        uint32_t ni = work.back();
+        work.pop_back();
+        const Node4 &n = bvh.nodes[ni];
+        for (int k = 0; k < 4; ++k)
+        {
+            uint32_t r = n.ref[k];
+            if (r == SPB_REF_EMPTY) continue;
+            if (r & SPB_REF_LEAF)
+            {
+                uint32_t prim = bvh.slotPrim[r & ~SPB_REF_LEAF];
+                if (prim < seen.size()) seen[prim] = 1;
+                continue;
+            }
+            const Node4 &c = bvh.nodes[r];
+            for (int j = 0; j < 4; ++j)
+            {
+                if (c.ref[j] == SPB_REF_EMPTY) continue;
+                for (int a = 0; a < 3; ++a)
+                    if (c.bmin[a][j] < n.bmin[a][k] || c.bmax[a][j] > n.bmax[a][k]) contained = false;
+            }
+            work.push_back(r);
+        }
+    }
+    bool all = true;
+    for (uint8_t s : seen) all = all && s;
+    info->allLeavesReachable = all;
+    info->parentsContainChildren = contained;
+}
+
+// =============================================================================================
+// materials (sp_material_system.cpp) -- table maintenance is plain host code, evaluation is GPU
+
+extern "C" b32 sp_RegisterMaterial(sp_MaterialSystem *materialSystem, sp_Material material, u32 id)
+{
+    if (materialSystem->count >= SP_MAX_MATERIALS) return 0;
+    u32 index = materialSystem->count++;
+    materialSystem->keys[index] = id;
+    materialSystem->materials[index] = material;
+    return 1;
+}
+
+extern "C" sp_Material *sp_FindMaterialById(sp_MaterialSystem *materialSystem, u32 id)
+{
+    for (u32 i = 0; i < materialSystem->count; ++i)
+        if (materialSystem->keys[i] == id) return materialSystem->materials + i;
+    return NULL;
+}
+
+extern "C" HdrImage *sp_FindTexture(sp_MaterialSystem *materialSystem, u32 id)
+{
+    for (u32 i = 0; i < materialSystem->imageCount; ++i)
+        if (materialSystem->imageKeys[i] == id) return materialSystem->images + i;
+    return NULL;
+}
+
+extern "C" b32 sp_RegisterTexture(sp_MaterialSystem *materialSystem, HdrImage image, u32 id)
+{
+    if (materialSystem->imageCount >= SP_MAX_IMAGES) return 0;
+    u32 index = materialSystem->imageCount++;
+    materialSystem->imageKeys[index] = id;
+    materialSystem->images[index] = image;
+    return 1;
+}
+
+static void pack_vertex(const sp_PathVertex &v, float *p)
+{
+    memcpy(&p[0], &v.materialId, 4);
+    p[1] = v.worldPosition.x; p[2] = v.worldPosition.y; p[3] = v.worldPosition.z;
+    p[4] = v.outgoingDir.x; p[5] = v.outgoingDir.y; p[6] = v.outgoingDir.z;
+    p[7] = v.incomingDir.x; p[8] = v.incomingDir.y; p[9] = v.incomingDir.z;
+    p[10] = v.normal.x; p[11] = v.normal.y; p[12] = v.normal.z;
+    p[13] = v.uv.x; p[14] = v.uv.y;
+}
+
+extern "C" sp_MaterialOutput sp_EvaluateMaterial(sp_MaterialSystem *materialSystem,
+                                                 sp_Material *material, sp_PathVertex *vertex)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    // evaluate `material` itself (it need not be registered): a one-entry table sharing the
+    // caller's textures
+    sp_MaterialSystem single = *materialSystem;
+    single.count = 1;
+    single.keys[0] = 0;
+    single.materials[0] = *material;
+    const DMaterials *dm = upload_materials(&single);
+    float packed[15];
+    pack_vertex(*vertex, packed);
+    L.scratchA.ensure(sizeof(packed));
+    L.scratchC.ensure(32);
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, packed, sizeof(packed), cudaMemcpyHostToDevice, L.stream));
+    launch_evaluate_material(kernel_config(), dm, 0, (const float *)L.scratchA.ptr, (float *)L.scratchC.ptr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    float out[7];
+    SPB_CUDA(cudaMemcpyAsync(out, L.scratchC.ptr, sizeof(out), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    sp_MaterialOutput r;
+    r.albedo = vec3{out[0], out[1], out[2]};
+    r.emission = vec3{out[3], out[4], out[5]};
+    r.roughness = out[6];
+    return r;
+}
+
+extern "C" vec3 ComputeRadianceForPath(sp_PathVertex *path, u32 pathLength,
+                                       sp_MaterialSystem *materialSystem)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    const DMaterials *dm = upload_materials(materialSystem);
+    std::vector<float> packed((size_t)(pathLength ? pathLength : 1) * 15);
+    for (u32 i = 0; i < pathLength; ++i) pack_vertex(path[i], &packed[(size_t)i * 15]);
+    L.scratchA.ensure(packed.size() * 4);
+    L.scratchC.ensure(16);
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, L.stream));
+    launch_radiance_for_path(kernel_config(), dm, (const float *)L.scratchA.ptr, pathLength,
+                             L.params.radianceClamp, (float *)L.scratchC.ptr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    float out[3];
+    SPB_CUDA(cudaMemcpyAsync(out, L.scratchC.ptr, sizeof(out), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    return vec3{out[0], out[1], out[2]};
+}
+
+// =============================================================================================
+// camera, tiles, queue: plain host code with the reference's arithmetic
+
+extern "C" void sp_ConfigureCamera(sp_Camera *camera, ImagePlane *imagePlane, vec3 position,
+                                   quat rotation, f32 filmDistance)
+{
+    configure_camera(camera, imagePlane, position, rotation, filmDistance);
+}
+
+extern "C" u32 sp_CalculateFilmPositions(sp_Camera *camera, vec3 *filmPositions,
+                                         vec2 *pixelPositions, u32 count)
+{
+    // simd_path_tracer.cpp:38-63
+    ImagePlane *imagePlane = camera->imagePlane;
+    for (u32 i = 0; i < count; ++i)
+    {
+        f32 fx = pixelPositions[i].x / (f32)imagePlane->width;
+        f32 fy = pixelPositions[i].y / (f32)imagePlane->height;
+        fy = 1.0f - fy;
+        fx = fx * 2.0f - 1.0f;
+        fy = fy * 2.0f - 1.0f;
+        f32 sx = camera->halfFilmWidth * fx, sy = camera->halfFilmHeight * fy;
+        vec3 p = {camera->basis.right.x * sx, camera->basis.right.y * sx, camera->basis.right.z * sx};
+        p.x = p.x + camera->basis.up.x * sy; p.y = p.y + camera->basis.up.y * sy; p.z = p.z + camera->basis.up.z * sy;
+        p.x = p.x + camera->filmCenter.x; p.y = p.y + camera->filmCenter.y; p.z = p.z + camera->filmCenter.z;
+        filmPositions[i] = p;
+    }
+    return count;
+}
+
+extern "C" Aabb TransformAabb(vec3 boxMin, vec3 boxMax, vec3 position, quat orientation, vec3 scale)
+{
+    spbh::V3 lo, hi;
+    spbh::transform_aabb(spbh::v3(boxMin.x, boxMin.y, boxMin.z), spbh::v3(boxMax.x, boxMax.y, boxMax.z),
+                         spbh::v3(position.x, position.y, position.z),
+                         spbh::V4{orientation.x, orientation.y, orientation.z, orientation.w},
+                         spbh::v3(scale.x, scale.y, scale.z), &lo, &hi);
+    Aabb r;
+    r.min = vec3{lo.x, lo.y, lo.z};
+    r.max = vec3{hi.x, hi.y, hi.z};
+    return r;
+}
+
+extern "C" u32 ComputeTiles(u32 totalWidth, u32 totalHeight, u32 tileWidth, u32 tileHeight,
+                            Tile *tiles, u32 maxTiles)
+{
+    // tile.h:11-42 (the counts come from a float Ceil there, hence the float division)
+    u32 tileCountY = (u32)ceilf((f32)totalHeight / (f32)tileHeight);
+    u32 tileCountX = (u32)ceilf((f32)totalWidth / (f32)tileWidth);
+    for (u32 tileY = 0; tileY < tileCountY; ++tileY)
+    {
+        for (u32 tileX = 0; tileX < tileCountX; ++tileX)
+        {
+            u32 index = tileX + tileY * tileCountX;
+            if (index >= maxTiles) break;
+            Tile tile;
+            tile.minX = tileX * tileWidth;
+            tile.minY = tileY * tileHeight;
+            tile.maxX = tile.minX + tileWidth < totalWidth ? tile.minX + tileWidth : totalWidth;
+            tile.maxY = tile.minY + tileHeight < totalHeight ? tile.minY + tileHeight : totalHeight;
+            tiles[index] = tile;
+        }
+    }
+    u32 total = tileCountY * tileCountX;
+    return total < maxTiles ? total : maxTiles;
+}
+
+extern "C" WorkQueue CreateWorkQueue(MemoryArena *arena, u32 objectSize, u32 maxObjects)
+{
+    // work_queue.h:13-22; AllocateBytes from the caller's arena (platform.h:107-114)
+    WorkQueue result;
+    memset(&result, 0, sizeof(result));
+    u64 length = (u64)objectSize * maxObjects;
+    SPB_ASSERT(arena->size + length <= arena->capacity);
+    result.buffer = (u8 *)arena->base + arena->size;
+    arena->size += length;
+    result.objectSize = objectSize;
+    result.maxObjects = maxObjects;
+    return result;
+}
+
+extern "C" b32 WorkQueuePush(WorkQueue *queue, void *object, u32 objectSize)
+{
+    SPB_ASSERT(objectSize == queue->objectSize);
+    SPB_ASSERT(queue->tail < (i32)queue->maxObjects);
+    memcpy((u8 *)queue->buffer + (size_t)objectSize * queue->tail, object, objectSize);
+    queue->tail++;
+    return 1;
+}
+
+extern "C" void *WorkQueuePop(WorkQueue *queue, u32 objectSize)
+{
+    SPB_ASSERT(objectSize == queue->objectSize);
+    SPB_ASSERT(queue->head != queue->tail);
+    i32 index = __atomic_fetch_add(&queue->head, 1, __ATOMIC_SEQ_CST); // intrinsics.h:5-16
+    return (u8 *)queue->buffer + (size_t)index * objectSize;
+}
+
+// =============================================================================================
+// rendering
+
+extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame,
+                                  f32 *hostPixels, void *devicePixels, sp_Metrics *metrics,
+                                  u64 *tileRowCost)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    DCamera cam;
+    convert_camera(ctx->camera, &cam);
+    if (rowEnd > cam.height) rowEnd = cam.height;
+    if (rowBegin >= rowEnd || cam.width == 0) return 0;
+    DeviceScene *ds = find_scene(ctx->scene);
+
+    size_t imageBytes = (size_t)cam.width * cam.height * 16;
+    v4f *image = (v4f *)devicePixels;
+    if (!image)
+    {
+        L.image.ensure(imageBytes);
+        image = (v4f *)L.image.ptr;
+    }
+    u32 tileH = L.params.tileHeight;
+    u32 firstTileRow = rowBegin / tileH;
+    u32 tileRows = (rowEnd - 1) / tileH - firstTileRow + 1;
+
+    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    const DMaterials *dm = upload_materials(ctx->materialSystem);
+    unsigned long long *ctr = reset_counters(tileRows);
+
+    RenderArgs args;
+    args.scene = ds->d;
+    args.materials = dm;
+    args.camera = cam;
+    args.x0 = 0;
+    args.x1 = cam.width;
+    args.y0 = rowBegin;
+    args.y1 = rowEnd;
+    args.spp = L.params.samplesPerPixel;
+    args.bounces = L.params.bounceCount;
+    args.frame = frame;
+    args.clampValue = L.params.radianceClamp;
+    args.out = image;
+    args.counters = ctr;
+    args.tileRowCost = ctr + CTR_COUNT;
+    args.tileHeight = tileH;
+    // the kernel tiles the rectangle from y0 in 16-row CTAs; keep CTA rows inside one tile row
+    // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
+    SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);
+
+    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    launch_render(kernel_config(), args, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+
+    std::vector<unsigned long long> c(CTR_COUNT + tileRows);
+    SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
+    if (hostPixels)
+    {
+        size_t offset = (size_t)rowBegin * cam.width;
+        SPB_CUDA(cudaMemcpyAsync(hostPixels + offset * 4, image + offset,
+                                 (size_t)(rowEnd - rowBegin) * cam.width * 16,
+                                 cudaMemcpyDeviceToHost, L.stream));
+    }
+    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    float kernelMs = 0, totalMs = 0;
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    add_metrics(metrics, c.data(), kernelMs);
+    record_stats(c.data(), kernelMs, totalMs);
+    if (tileRowCost)
+        for (u32 i = 0; i < tileRows; ++i) tileRowCost[i] = c[CTR_COUNT + i];
+    return 0;
+}
+
+extern "C" int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics)
+{
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    ImagePlane *plane = ctx->camera->imagePlane;
+    return sp_b200_RenderRows(ctx, 0, plane->height, frame, (f32 *)plane->pixels, nullptr, metrics, nullptr);
+}
+
+extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng,
+                                 sp_Metrics *metrics)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    DCamera cam;
+    convert_camera(ctx->camera, &cam);
+    ImagePlane *plane = ctx->camera->imagePlane;
+    // simd_path_tracer.cpp:188-191
+    u32 minX = tile.minX, minY = tile.minY;
+    u32 maxX = tile.maxX < plane->width ? tile.maxX : plane->width;
+    u32 maxY = tile.maxY < plane->height ? tile.maxY : plane->height;
+    DeviceScene *ds = find_scene(ctx->scene);
+
+    size_t imageBytes = (size_t)cam.width * cam.height * 16;
+    L.image.ensure(imageBytes ? imageBytes : 16);
+    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    const DMaterials *dm = upload_materials(ctx->materialSystem);
+    unsigned long long *ctr = reset_counters();
+    uint32_t tileData[5] = {minX, minY, maxX, maxY, rng->state};
+    L.scratchA.ensure(sizeof(tileData));
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, tileData, sizeof(tileData), cudaMemcpyHostToDevice, L.stream));
+
+    TileArgs args;
+    args.scene = ds->d;
+    args.materials = dm;
+    args.camera = cam;
+    args.tiles = (const uint32_t *)L.scratchA.ptr;
+    args.rngStates = (uint32_t *)L.scratchA.ptr + 4;
+    args.count = 1;
+    args.spp = L.params.samplesPerPixel;
+    args.bounces = L.params.bounceCount;
+    args.clampValue = L.params.radianceClamp;
+    args.out = (v4f *)L.image.ptr;
+    args.counters = ctr;
+    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    launch_tiles_serial(kernel_config(), args, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+
+    unsigned long long c[CTR_COUNT];
+    SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(&rng->state, (uint32_t *)L.scratchA.ptr + 4, 4, cudaMemcpyDeviceToHost, L.stream));
+    if (maxX > minX && maxY > minY && plane->pixels)
+    {
+        size_t pitch = (size_t)cam.width * 16;
+        size_t offset = (size_t)minY * cam.width + minX;
+        SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
+                                   pitch, (size_t)(maxX - minX) * 16, maxY - minY,
+                                   cudaMemcpyDeviceToHost, L.stream));
+    }
+    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    float kernelMs = 0, totalMs = 0;
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    add_metrics(metrics, c, kernelMs);
+    record_stats(c, kernelMs, totalMs);
+}
+
+extern "C" int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *triangleIndex,
+                                   i32 *objectIndex, f32 *t)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    DCamera cam;
+    convert_camera(ctx->camera, &cam);
+    DeviceScene *ds = find_scene(ctx->scene);
+    size_t n = (size_t)cam.width * cam.height;
+    if (n == 0) return 0;
+    L.scratchA.ensure(n * 4);
+    L.scratchB.ensure(n * 4);
+    L.scratchC.ensure(n * 4);
+    unsigned long long *ctr = reset_counters();
+    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    launch_primary_hits(kernel_config(), ds->d, cam, sample, frame, (int32_t *)L.scratchA.ptr,
+                        (int32_t *)L.scratchB.ptr, (float *)L.scratchC.ptr, ctr, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    unsigned long long c[CTR_COUNT];
+    SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
+    if (triangleIndex) SPB_CUDA(cudaMemcpyAsync(triangleIndex, L.scratchA.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
+    if (objectIndex) SPB_CUDA(cudaMemcpyAsync(objectIndex, L.scratchB.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
+    if (t) SPB_CUDA(cudaMemcpyAsync(t, L.scratchC.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    float kernelMs = 0, totalMs = 0;
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    record_stats(c, kernelMs, totalMs);
+    return 0;
+}

@@ -1,0 +1,91 @@
+// spb_kernels.cuh -- launch interface between the C ABI (spb_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "spb_core.cuh"
+
+namespace spb {
+
+// slots of the device counter block every kernel accumulates into
+enum
+{
+    CTR_PATHS = 0, CTR_RAYS, CTR_HITS, CTR_MISSES, CTR_NODE_VISITS, CTR_TRIANGLE_TESTS,
+    CTR_OBJECT_TESTS, CTR_ENV_CLAMPED, CTR_CLOCK_SUM, CTR_COUNT
+};
+
+struct KernelConfig
+{
+    int math;      // SP_B200_MATH_*
+    int envFilter; // SP_B200_ENV_*
+    int cull;      // 0 / 1
+    int stats;     // 0 / 1: count node visits and triangle tests
+};
+
+struct RenderArgs
+{
+    DScene scene;
+    const DMaterials *materials;
+    DCamera camera;
+    uint32_t x0, y0, x1, y1; // pixel rectangle
+    uint32_t spp, bounces, frame;
+    float clampValue;
+    v4f *out;                         // full image, indexed x + y * camera.width
+    unsigned long long *counters;     // CTR_COUNT slots
+    unsigned long long *tileRowCost;  // may be null; rays per tile row, row 0 = y0 / tileHeight
+    uint32_t tileHeight;
+};
+
+void launch_render(const KernelConfig &cfg, const RenderArgs &args, cudaStream_t stream);
+
+// sp_PathTraceTile semantics: one serial XorShift32 stream per tile (simd_path_tracer.cpp:178-345)
+struct TileArgs
+{
+    DScene scene;
+    const DMaterials *materials;
+    DCamera camera;
+    const uint32_t *tiles;  // count x 4: minX minY maxX maxY (already clamped to the image)
+    uint32_t *rngStates;    // count, in/out
+    uint32_t count;
+    uint32_t spp, bounces;
+    float clampValue;
+    v4f *out;
+    unsigned long long *counters; // count x CTR_COUNT (per tile)
+};
+void launch_tiles_serial(const KernelConfig &cfg, const TileArgs &args, cudaStream_t stream);
+
+struct HitRecord
+{
+    float t;
+    uint32_t materialId;
+    float nx, ny, nz;
+    float u, v;
+    int32_t triangle;
+    int32_t object;
+};
+
+void launch_primary_hits(const KernelConfig &cfg, const DScene &scene, const DCamera &camera,
+                         uint32_t sample, uint32_t frame, int32_t *tri, int32_t *obj, float *t,
+                         unsigned long long *counters, cudaStream_t stream);
+void launch_intersect_batch(const KernelConfig &cfg, const DScene &scene, uint32_t count,
+                            const float *origins3, const float *dirs3, HitRecord *out,
+                            unsigned long long *counters, cudaStream_t stream);
+// sp_RayIntersectMesh: object-space ray against object 0's mesh; normal left in object space
+void launch_intersect_mesh(const KernelConfig &cfg, const DScene &scene, uint32_t smooth,
+                           const float *origin3, const float *dir3, HitRecord *out,
+                           cudaStream_t stream);
+// bvh_IntersectRay semantics on object 0's mesh: every leaf whose own box the ray passes
+void launch_collect_leaves(const DScene &scene, const float *origin3, const float *dir3,
+                           uint32_t *leaves, uint32_t maxLeaves, uint32_t *countAndError,
+                           cudaStream_t stream);
+// ComputeRadianceForPath over n vertices of 15 floats (materialId bits, P3, out3, in3, n3, uv2)
+void launch_radiance_for_path(const KernelConfig &cfg, const DMaterials *materials,
+                              const float *path15, uint32_t n, float clampValue, float *out3,
+                              cudaStream_t stream);
+// sp_EvaluateMaterial with an explicit material (not looked up by id); out7 = albedo3 emission3 r
+void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materials,
+                              uint32_t materialSlot, const float *vertex15, float *out7,
+                              cudaStream_t stream);
+
+} // namespace spb
