@@ -237,6 +237,8 @@ void sp_b200_GetParams(sp_b200_Params *params);
 void sp_b200_GetLastStats(sp_b200_Stats *stats);
 /* Collect node/triangle counters in the next launches (slower kernels; off by default). */
 void sp_b200_EnableStats(int enable);
+/* Kernels launched by this library since it was loaded (a count of real launches). */
+u64 sp_b200_KernelLaunchCount(void);
 /* Forget device copies of HdrImage pixel buffers (they are cached by host pointer). */
 void sp_b200_FlushTextureCache(void);
 /* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
@@ -270,6 +272,8 @@ typedef struct sp_b200_TreeInfo {
     b32 parentsContainChildren; vec3 rootMin; vec3 rootMax;
 } sp_b200_TreeInfo;
 void sp_b200_MeshTreeInfo(sp_Mesh mesh, sp_b200_TreeInfo *info);
+/* Bytes sp_BuildSceneBroadphase uploaded for this scene (nodes, triangles, shading data, instances). */
+u64 sp_b200_SceneDeviceBytes(sp_Scene *scene);
 void sp_b200_ReleaseMesh(sp_Mesh *mesh);
 void sp_b200_ReleaseScene(sp_Scene *scene);
 

@@ -77,6 +77,12 @@ void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uint
 double ora_render_tiles(ora_Scene *s, float *rgba, uint32_t tileW, uint32_t tileH, uint32_t spp,
                         uint32_t bounces, uint32_t threads, uint64_t *metrics);
 
+/* The same native scheduling over a SUBSET of the frame's tiles (a bounded sample of a large
+ * workload): tiles = count x 4 u32 (minX minY maxX maxY, as ComputeTiles produced them), every
+ * tile seeded 0xF51C0E49.  Returns wall seconds. */
+double ora_render_tile_list(ora_Scene *s, float *rgba, const uint32_t *tiles, uint32_t count,
+                            uint32_t spp, uint32_t bounces, uint32_t threads, uint64_t *metrics);
+
 /* One sp_PathTraceTile call with the caller's rng state (in/out). */
 void ora_path_trace_tile(ora_Scene *s, float *rgba, uint32_t minX, uint32_t minY, uint32_t maxX,
                          uint32_t maxY, uint32_t spp, uint32_t bounces, uint32_t *rngState,

@@ -385,6 +385,54 @@ extern "C" double ora_render_tiles(ora_Scene *s, float *rgba, uint32_t tileW, ui
     return std::chrono::duration<double>(end - begin).count();
 }
 
+extern "C" double ora_render_tile_list(ora_Scene *s, float *rgba, const uint32_t *tileList,
+                                       uint32_t count, uint32_t spp, uint32_t bounces,
+                                       uint32_t threads, uint64_t *metrics)
+{
+    OraRequireBounces(bounces);
+    g_oraSamplesPerPixel = spp;
+    s->imagePlane.pixels = (vec4 *)rgba;
+    if (threads == 0) threads = 1;
+
+    MemoryArena queueArena;
+    size_t queueBytes = sizeof(OraTask) * (size_t)count + 64;
+    std::vector<u8> queueStorage(queueBytes);
+    InitializeMemoryArena(&queueArena, queueStorage.data(), queueBytes);
+    WorkQueue queue = CreateWorkQueue(&queueArena, sizeof(OraTask), count ? count : 1);
+    std::vector<sp_Metrics> tileMetrics(count ? count : 1);
+    memset(tileMetrics.data(), 0, sizeof(sp_Metrics) * tileMetrics.size());
+
+    auto begin = std::chrono::steady_clock::now();
+    for (u32 i = 0; i < count; ++i)
+    {
+        Tile tile = {tileList[i * 4 + 0], tileList[i * 4 + 1], tileList[i * 4 + 2], tileList[i * 4 + 3]};
+        OraTask task = {&s->ctx, tile};
+        WorkQueuePush(&queue, &task, sizeof(task));
+    }
+    auto worker = [&]() {
+        for (;;)
+        {
+            i32 index = AtomicExchangeAdd(&queue.head, 1);
+            if (index >= queue.tail) break;
+            OraTask *task = (OraTask *)((u8 *)queue.buffer + (size_t)index * sizeof(OraTask));
+            RandomNumberGenerator rng = {};
+            rng.state = 0xF51C0E49; // main.cpp:738-739
+            sp_Metrics m = {};
+            sp_PathTraceTile(task->context, task->tile, &rng, &m);
+            tileMetrics[index] = m;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (u32 t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    auto end = std::chrono::steady_clock::now();
+    for (u32 i = 0; i < count; ++i) OraAddMetrics(metrics, tileMetrics[i]);
+    s->imagePlane.pixels = NULL;
+    g_oraSamplesPerPixel = 1;
+    return std::chrono::duration<double>(end - begin).count();
+}
+
 extern "C" void ora_path_trace_tile(ora_Scene *s, float *rgba, uint32_t minX, uint32_t minY,
                                     uint32_t maxX, uint32_t maxY, uint32_t spp,
                                     uint32_t bounces, uint32_t *rngState, uint64_t *metrics)

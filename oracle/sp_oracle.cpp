@@ -985,6 +985,34 @@ extern "C" double ora_render_tiles(ora_Scene *s, float *rgba, uint32_t tileW, ui
     return std::chrono::duration<double>(end - begin).count();
 }
 
+extern "C" double ora_render_tile_list(ora_Scene *s, float *rgba, const uint32_t *tileList,
+                                       uint32_t count, uint32_t spp, uint32_t bounces,
+                                       uint32_t threads, uint64_t *metrics)
+{
+    // as ora_render_tiles, over a caller-chosen subset of the frame's tiles
+    if (threads == 0) threads = 1;
+    std::vector<Counters64> per(count ? count : 1);
+    memset(per.data(), 0, sizeof(Counters64) * per.size());
+    int head = 0;
+    auto begin = std::chrono::steady_clock::now();
+    run_threads(threads, [&](uint32_t) {
+        Scratch sc;
+        for (;;)
+        {
+            int i = __atomic_fetch_add(&head, 1, __ATOMIC_SEQ_CST);
+            if (i >= (int)count) break;
+            const uint32_t *t = tileList + (size_t)i * 4;
+            uint32_t rng = 0xF51C0E49u;
+            trace_tile(s, rgba, t[0], t[1], t[2], t[3], spp, bounces, &rng, &per[i], &sc);
+        }
+    });
+    auto end = std::chrono::steady_clock::now();
+    if (metrics)
+        for (uint32_t t = 0; t < count; ++t)
+            for (int i = 0; i < ORA_METRIC_COUNT; ++i) metrics[i] += per[t].v[i];
+    return std::chrono::duration<double>(end - begin).count();
+}
+
 extern "C" void ora_path_trace_tile(ora_Scene *s, float *rgba, uint32_t minX, uint32_t minY,
                                     uint32_t maxX, uint32_t maxY, uint32_t spp,
                                     uint32_t bounces, uint32_t *rngState, uint64_t *metrics)

@@ -104,6 +104,8 @@ class OracleLib:
         lib.ora_render_seeded.argtypes = [C.c_void_p, _f] + [C.c_uint32] * 8 + [_u64]
         lib.ora_render_tiles.argtypes = [C.c_void_p, _f] + [C.c_uint32] * 5 + [_u64]
         lib.ora_render_tiles.restype = C.c_double
+        lib.ora_render_tile_list.argtypes = [C.c_void_p, _f, _u] + [C.c_uint32] * 4 + [_u64]
+        lib.ora_render_tile_list.restype = C.c_double
         lib.ora_path_trace_tile.argtypes = [C.c_void_p, _f] + [C.c_uint32] * 6 + [_u, _u64]
         lib.ora_primary_hits.argtypes = [C.c_void_p, _i, _i, _f, _f, C.c_uint32, C.c_uint32,
                                          C.c_uint32]
@@ -320,6 +322,17 @@ class OracleScene:
         metrics = np.zeros(12, np.uint64)
         secs = self.lib.ora_render_tiles(self.h, _fp(image), tile_w, tile_h, spp, bounces, threads,
                                          metrics.ctypes.data_as(_u64))
+        return image, metrics, secs
+
+    def render_tile_list(self, tiles, spp=1, bounces=3, threads=None, image=None):
+        """tiles: (n, 4) uint32 (minX minY maxX maxY).  Returns image, metrics, wall seconds."""
+        threads = threads or os.cpu_count() or 1
+        if image is None:
+            image = np.zeros((self.height, self.width, 4), np.float32)
+        t = np.ascontiguousarray(tiles, dtype=np.uint32).reshape(-1, 4)
+        metrics = np.zeros(12, np.uint64)
+        secs = self.lib.ora_render_tile_list(self.h, _fp(image), _up(t), len(t), spp, bounces,
+                                             threads, metrics.ctypes.data_as(_u64))
         return image, metrics, secs
 
     def path_trace_tile(self, image, tile, spp, bounces, rng_state):

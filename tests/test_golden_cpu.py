@@ -1,0 +1,101 @@
+"""The oracle port (and the hostsim build of the device arithmetic) against the committed golden
+fixtures, which tools/make_golden.py produced from the UNMODIFIED reference (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+
+from vk_cinematic_b200 import workloads as W
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a, dtype=np.float32).view(np.uint32),
+                          np.ascontiguousarray(b, dtype=np.float32).view(np.uint32))
+
+
+def test_g1_port_image_and_hits(port, port_dm):
+    g = gold("g1_bunny_96x64.npz")
+    wl = W.config1(96, 64, env_size=(512, 256))
+    for L, key in ((port, "ref"), (port_dm, "ref_dm")):
+        s = L.scene().load_workload(wl)
+        img, m = s.render_seeded(spp=2, bounces=3, frame=1)
+        assert same_bits(img, g["image_" + key]) and np.array_equal(m[1:5], g["metrics_" + key])
+        tile = np.zeros_like(img)
+        state, tm = s.path_trace_tile(tile, (16, 8, 48, 40), 2, 3, 0xF51C0E49)
+        assert state == int(g["tile_state_" + key]) and same_bits(tile, g["tile_image_" + key])
+        assert np.array_equal(tm[1:5], g["tile_metrics_" + key])
+        if key == "ref":
+            ph = s.primary_hits(sample=0, frame=1)
+            assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+        s.close()
+
+
+def test_g2_port_monkey_primary(port):
+    g = gold("g2_monkey_160x90_primary.npz")
+    s = port.scene().load_workload(W.config2(160, 90, env_size=(64, 32)))
+    ph = s.primary_hits()
+    assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+    s.close()
+
+
+def test_g3_port_rays_and_image(port, port_dm):
+    g = gold("g3_multi_80x60.npz")
+    wl = W.multi_object_workload(width=80, height=60, spp=2, env_size=(256, 128))
+    s = port.scene().load_workload(wl)
+    r = s.intersect_rays(g["origins"], g["dirs"])
+    assert same_bits(r["t"], g["rays_t"]) and np.array_equal(r["tri"], g["rays_tri"])
+    assert np.array_equal(r["obj"], g["rays_obj"]) and np.array_equal(r["material"], g["rays_material"])
+    assert same_bits(r["normal"], g["rays_normal"]) and same_bits(r["uv"], g["rays_uv"])
+    img, m = s.render_seeded(spp=2, bounces=3, frame=5)
+    assert same_bits(img, g["image_ref"])
+    s.close()
+    s = port_dm.scene().load_workload(wl)
+    img, m = s.render_seeded(spp=2, bounces=3, frame=5)
+    assert same_bits(img, g["image_ref_dm"]) and np.array_equal(m[1:5], g["metrics_ref_dm"])
+    s.close()
+
+
+# hostsim = vk_cinematic_b200/csrc/spb_core.cuh + the host builder compiled for the host: the
+# LOGIC of the CUDA path (not the GPU) against the reference's outputs.  No GPU parity claim.
+
+@pytest.mark.parametrize("cull", [1, 0])
+def test_hostsim_logic_against_golden(hostsim, cull):
+    hostsim.lib.hostsim_set_cull(cull)
+    g = gold("g1_bunny_96x64.npz")
+    s = hostsim.scene().load_workload(W.config1(96, 64, env_size=(512, 256)))
+    img, m = s.render_seeded(spp=2, bounces=3, frame=1)
+    assert same_bits(img, g["image_ref_dm"]) and np.array_equal(m[1:5], g["metrics_ref_dm"])
+    ph = s.primary_hits(sample=0, frame=1)
+    assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+    tile = np.zeros_like(img)
+    state, tm = s.path_trace_tile(tile, (16, 8, 48, 40), 2, 3, 0xF51C0E49)
+    assert state == int(g["tile_state_ref_dm"]) and same_bits(tile, g["tile_image_ref_dm"])
+    s.close()
+
+    g = gold("g3_multi_80x60.npz")
+    s = hostsim.scene().load_workload(
+        W.multi_object_workload(width=80, height=60, spp=2, env_size=(256, 128)))
+    r = s.intersect_rays(g["origins"], g["dirs"])
+    assert same_bits(r["t"], g["rays_t"]) and np.array_equal(r["tri"], g["rays_tri"])
+    assert np.array_equal(r["obj"], g["rays_obj"]) and same_bits(r["normal"], g["rays_normal"])
+    img, m = s.render_seeded(spp=2, bounces=3, frame=5)
+    assert same_bits(img, g["image_ref_dm"])
+    s.close()
+    hostsim.lib.hostsim_set_cull(1)
+
+
+def test_hostsim_five_bounces_against_port(hostsim, port_dm):
+    wl = W.config1(64, 48, env_size=(256, 128))
+    a = port_dm.scene().load_workload(wl)
+    b = hostsim.scene().load_workload(wl)
+    ia, ma = a.render_seeded(spp=2, bounces=5, frame=2)
+    ib, mb = b.render_seeded(spp=2, bounces=5, frame=2)
+    assert same_bits(ia, ib) and np.array_equal(ma[1:5], mb[1:5])
+    a.close()
+    b.close()

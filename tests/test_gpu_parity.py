@@ -1,0 +1,397 @@
+"""Parity of the CUDA path with the oracle, through libspb200.so's C ABI (needs a B200).
+
+Oracles: oracle/_ref/libspref*.so (the reference's unmodified sources; prebuilt .so files travel
+with the snapshot) when present, else the port (oracle/libsporacle*.so, shown bit-equal to the
+reference by tests/test_oracle_kat.py).  Bars:
+  * integer / index work (triangle ids, object ids, hit counters, rng state): exact;
+  * floating point in deterministic-math mode (mathMode 0 vs the *_dm checkers, which compute
+    sin/cos/atan2/pow as "double, rounded once" on both sides): bit-exact images;
+  * floating point against glibc's libm (the plain reference): per-pixel and RMSE tolerances
+    written in the tests below.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ora
+from vk_cinematic_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EPS = np.finfo(np.float32).eps
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def same_bits(a, b):
+    return np.array_equal(bits(a), bits(b))
+
+
+def best(dm):
+    """The strongest available checker: the reference itself, else the port."""
+    if ora.have_ref():
+        return ora.load_ref_dm() if dm else ora.load_ref()
+    return ora.load_port_dm() if dm else ora.load_port()
+
+
+@pytest.fixture()
+def params(gpu_sp):
+    gpu_sp.set_params(samplesPerPixel=1, bounceCount=3, radianceClamp=10.0, envFilter=0, mathMode=0,
+                      cullByDistance=1, tileWidth=64, tileHeight=64)
+    gpu_sp.lib.sp_b200_EnableStats(0)
+    yield gpu_sp
+    gpu_sp.set_params(samplesPerPixel=1, bounceCount=3, radianceClamp=10.0, envFilter=0, mathMode=0,
+                      cullByDistance=1, tileWidth=64, tileHeight=64)
+    gpu_sp.lib.sp_b200_EnableStats(0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's unit tests, restated against the C ABI
+
+TRI_VERTS = np.array([[-0.5, -0.5, 0, 0, 0, 1, 0, 0], [0.5, -0.5, 0, 0, 0, 1, 0, 0],
+                      [0.0, 0.5, 0, 0, 0, 1, 0, 0]], np.float32)
+
+
+def test_ray_intersect_scene_two_objects(params):
+    """test_simd_path_tracer.cpp:216-276"""
+    sp = params
+    r = sp.Renderer()
+    m = r.add_mesh(TRI_VERTS, [0, 1, 2])
+    r.add_object(m, 53, (0, 2, -5))
+    r.add_object(m, 53, (0, 2, -15), W.quat_axis_angle((0, 1, 0), 3.14159265359 * 0.25), (2, 2, 2))
+    r.build()
+    met = sp.sp_Metrics()
+    res = sp.lib.sp_RayIntersectScene(C.byref(r.scene), sp.V3((0, 2, 0)), sp.V3((0, 0, -1)), C.byref(met))
+    assert res.t >= 0.0 and res.materialId == 53 and abs(res.t - 5.0) < 1e-5
+    chk = best(False).scene()
+    cm = chk.add_mesh(TRI_VERTS, [0, 1, 2])
+    chk.add_object(cm, 53, (0, 2, -5))
+    chk.add_object(cm, 53, (0, 2, -15), W.quat_axis_angle((0, 1, 0), 3.14159265359 * 0.25), (2, 2, 2))
+    chk.build()
+    rng = np.random.RandomState(2)
+    o = np.tile(np.float32((0, 2, 0)), (256, 1)) + rng.uniform(-0.3, 0.3, (256, 3)).astype(np.float32)
+    d = np.float32((0, 0, -1)) + rng.uniform(-0.08, 0.08, (256, 3)).astype(np.float32)
+    d = (d / np.linalg.norm(d, axis=1)[:, None]).astype(np.float32)
+    g, e = r.intersect_rays(o, d), chk.intersect_rays(o, d)
+    assert same_bits(g["t"], e["t"]) and np.array_equal(g["obj"], e["obj"])
+    assert same_bits(g["normal"], e["normal"]) and np.array_equal(g["material"], e["material"])
+    assert (e["obj"] == 0).any() and (e["obj"] == 1).any()
+    chk.close()
+    r.close()
+
+
+def test_ray_intersect_mesh_single_triangle(params):
+    """test_simd_path_tracer.cpp:370-396 (+ :398-423: one triangle -> root bounds = its AABB)"""
+    sp = params
+    r = sp.Renderer()
+    r.add_mesh(TRI_VERTS, [0, 1, 2])
+    res = sp.lib.sp_RayIntersectMesh(r.meshes[0], sp.V3((0, 0, 10)), sp.V3((0, 0, -1)), None)
+    ti = res.triangleIntersection
+    assert ti.t == 10.0 and ti.normal.tuple() == (0.0, 0.0, 1.0)
+    res = sp.lib.sp_RayIntersectMesh(r.meshes[0], sp.V3((2, 0, 10)), sp.V3((0, 0, -1)), None)
+    assert res.triangleIntersection.t == -1.0
+    info = sp.sp_b200_TreeInfo()
+    sp.lib.sp_b200_MeshTreeInfo(r.meshes[0], C.byref(info))
+    assert info.leafCount == 1 and info.rootMin.tuple() == (-0.5, -0.5, 0.0)
+    assert info.rootMax.tuple() == (0.5, 0.5, 0.0)
+    r.close()
+
+
+def test_path_trace_tile_magenta_bounds_metrics(params):
+    """test_simd_path_tracer.cpp:49-135, 333-368: zero-initialised context, rng state 0"""
+    sp = params
+    pixels = np.zeros((4, 4, 4), np.float32)
+    plane = sp.ImagePlane(pixels.ctypes.data_as(C.POINTER(sp.vec4)), 4, 4)
+    cam = sp.sp_Camera()
+    cam.imagePlane = C.pointer(plane)
+    scene, ms = sp.sp_Scene(), sp.sp_MaterialSystem()
+    ctx = sp.sp_Context(C.pointer(cam), C.pointer(scene), C.pointer(ms))
+    rng, met = sp.RandomNumberGenerator(0), sp.sp_Metrics()
+    sp.lib.sp_PathTraceTile(C.byref(ctx), sp.Tile(0, 0, 4, 4), C.byref(rng), C.byref(met))
+    assert np.abs(pixels - np.float32((1, 0, 1, 1))).max() <= EPS
+    pixels[:] = 0
+    met = sp.sp_Metrics()
+    sp.lib.sp_PathTraceTile(C.byref(ctx), sp.Tile(1, 1, 3, 3), C.byref(rng), C.byref(met))
+    exp = np.zeros((4, 4, 4), np.float32)
+    exp[1:3, 1:3] = (1, 0, 1, 1)
+    assert np.array_equal(pixels, exp)
+    assert met.values[sp.sp_Metric_CyclesElapsed] > 0
+    assert met.values[sp.sp_Metric_PathsTraced] == 4 and met.values[sp.sp_Metric_RayMissCount] == 4
+    # a tile reaching past the image is clamped (simd_path_tracer.cpp:188-191)
+    pixels[:] = 0
+    sp.lib.sp_PathTraceTile(C.byref(ctx), sp.Tile(2, 2, 9, 9), C.byref(rng), C.byref(met))
+    assert pixels[2:, 2:, 3].min() == 1.0 and pixels[:2].max() == 0.0
+
+
+def test_material_albedo_texture_and_light_path(params):
+    """test_simd_path_tracer.cpp:278-331 (light path restated with roughness > 0)"""
+    sp = params
+    img = np.zeros((1, 1, 4), np.float32)
+    img[0, 0] = (1, 0, 0, 1)
+    ms = sp.sp_MaterialSystem()
+    sp.lib.sp_RegisterTexture(C.byref(ms), sp.HdrImage(img.ctypes.data_as(C.POINTER(C.c_float)), 1, 1), 1)
+    mat = sp.sp_Material(sp.V3((0, 0, 0)), 1, sp.V3((0, 0, 0)), sp.U32_MAX, 0.0)
+    vert = sp.sp_PathVertex()
+    out = sp.lib.sp_EvaluateMaterial(C.byref(ms), C.byref(mat), C.byref(vert))
+    assert out.albedo.tuple() == (1.0, 0.0, 0.0)
+
+    chk = best(True).scene()
+    ms = sp.sp_MaterialSystem()
+    for mid, kw in ((0, dict(emission=(1, 1, 1))), (1, dict(albedo=(0.18, 0.18, 0.18), roughness=0.6)),
+                    (2, dict(albedo=(0.7, 0.2, 0.1), emission=(0.3, 0.0, 0.2), roughness=0.25))):
+        m = sp.sp_Material(sp.V3(kw.get("albedo", (0, 0, 0))), sp.U32_MAX, sp.V3(kw.get("emission", (0, 0, 0))),
+                           sp.U32_MAX, kw.get("roughness", 0.0))
+        sp.lib.sp_RegisterMaterial(C.byref(ms), m, mid)
+        chk.register_material(mid, **kw)
+    rng = np.random.RandomState(9)
+    for _ in range(40):
+        n = int(rng.randint(1, 5))
+        path, cpath = (sp.sp_PathVertex * n)(), []
+        for i in range(n):
+            v = {k: tuple(float(x) for x in (lambda a: a / np.linalg.norm(a))(rng.normal(size=3)))
+                 for k in ("outgoingDir", "incomingDir", "normal")}
+            v["materialId"] = int(rng.choice([1, 2, 7])) if i < n - 1 else 0   # 7: unregistered -> magenta
+            path[i].materialId = v["materialId"]
+            path[i].outgoingDir, path[i].incomingDir, path[i].normal = (sp.V3(v[k]) for k in
+                                                                       ("outgoingDir", "incomingDir", "normal"))
+            cpath.append(v)
+        got = sp.lib.ComputeRadianceForPath(path, n, C.byref(ms))
+        assert same_bits(np.float32(got.tuple()), chk.radiance_for_path(cpath))
+    chk.close()
+
+
+def test_bilinear_environment_lookup(params):
+    """image.h:34-73 (SampleImageBilinear) as the env filter the north star asks for: emission of
+    a material with an emission texture under envFilter = bilinear equals the oracle's bilinear
+    sample at the oracle's equirect uv (v flipped, sp_material_system.cpp:88-93)."""
+    sp = params
+    chk = best(True)
+    env = W.make_env_map(64, 32, "kiara")
+    ms = sp.sp_MaterialSystem()
+    sp.lib.sp_RegisterTexture(C.byref(ms), sp.HdrImage(env.ctypes.data_as(C.POINTER(C.c_float)), 64, 32), 4)
+    mat = sp.sp_Material(sp.V3((0, 0, 0)), sp.U32_MAX, sp.V3((0, 0, 0)), 4, 0.0)
+    rng = np.random.RandomState(4)
+    for flt in (0, 1):
+        sp.set_params(envFilter=flt)
+        for _ in range(64):
+            d = rng.normal(size=3)
+            d = np.float32(d / np.linalg.norm(d))
+            vert = sp.sp_PathVertex()
+            vert.outgoingDir = sp.V3(d)
+            out = sp.lib.sp_EvaluateMaterial(C.byref(ms), C.byref(mat), C.byref(vert))
+            uv = chk.map_equirect(chk.to_spherical(-d))
+            u, v = np.float32(uv[0]), np.float32(1.0) - np.float32(uv[1])
+            exp = (chk.sample_bilinear if flt else chk.sample_nearest)(env, u, v)[0:3]
+            assert same_bits(np.float32(out.emission.tuple()), exp), (flt, d)
+    sp.lib.sp_b200_FlushTextureCache()
+
+
+def test_intersected_leaves_match_bvh_query(params):
+    """bvh_IntersectRay semantics (bvh.cpp:203-311; test_bvh.cpp:99-122,265-292): the set of
+    leaves reported for a ray equals the reference's, independent of tree topology; too small a
+    buffer sets errorOccurred."""
+    sp = params
+    chk = best(False)
+    mesh = W.icosphere_mesh(2)
+    r = sp.Renderer()
+    r.add_mesh(mesh.vertices, mesh.indices)
+    p = mesh.vertices[:, 0:3][mesh.indices.reshape(-1, 3)]
+    mn, mx = p.min(axis=1), p.max(axis=1)
+    rng = np.random.RandomState(6)
+    for k in range(24):
+        o = rng.uniform(-2, 2, 3).astype(np.float32)
+        d = -o + rng.uniform(-0.5, 0.5, 3).astype(np.float32)
+        d = np.float32(d / np.linalg.norm(d))
+        if k == 0:
+            o, d = np.float32((0, 0, 3)), np.float32((0, 0, -1))
+        leaves = np.zeros(128, np.uint32)
+        err = C.c_uint32(0)
+        n = sp.lib.sp_b200_MeshIntersectedLeaves(r.meshes[0], sp.V3(o), sp.V3(d), leaves.ctypes.data, 128,
+                                                 C.byref(err))
+        e = chk.bvh_query(mn, mx, o, d, 128)
+        assert not err.value and sorted(leaves[:n].tolist()) == sorted(e["leaves"].tolist())
+        if n > 1:
+            n2 = sp.lib.sp_b200_MeshIntersectedLeaves(r.meshes[0], sp.V3(o), sp.V3(d), leaves.ctypes.data, 1,
+                                                      C.byref(err))
+            assert n2 == 1 and err.value
+    r.close()
+
+
+def test_empty_and_unbuilt_scenes(params):
+    """bvh.cpp:218-229 NULL root: every ray misses; background evaluated per pixel"""
+    sp = params
+    wl = W.config1(64, 48, env_size=(64, 32))
+    wl.objects = []
+    r = sp.Renderer().load_workload(wl)
+    img, m = r.render_frame()
+    chk = best(True).scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=1, bounces=3)
+    assert same_bits(img, cimg) and m[sp.sp_Metric_RayMissCount] == 64 * 48
+    chk.close()
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures made from the unmodified reference (tools/make_golden.py)
+
+def test_golden_fixtures(params):
+    sp = params
+    g = np.load(os.path.join(GOLD, "g1_bunny_96x64.npz"))
+    r = sp.Renderer().load_workload(W.config1(96, 64, env_size=(512, 256)))
+    for cull in (1, 0):
+        sp.set_params(samplesPerPixel=2, cullByDistance=cull)
+        img, m = r.render_frame(frame=1)
+        assert same_bits(img, g["image_ref_dm"])
+        assert np.array_equal(m[1:5], g["metrics_ref_dm"])
+        ph = r.primary_hits(sample=0, frame=1)
+        assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+        r.image[:] = 0
+        state, tm = r.path_trace_tile((16, 8, 48, 40), 0xF51C0E49)
+        assert state == int(g["tile_state_ref_dm"]) and same_bits(r.image, g["tile_image_ref_dm"])
+        assert np.array_equal(tm[1:5], g["tile_metrics_ref_dm"])
+    r.close()
+    sp.set_params(samplesPerPixel=1, cullByDistance=1)
+    g = np.load(os.path.join(GOLD, "g2_monkey_160x90_primary.npz"))
+    r = sp.Renderer().load_workload(W.config2(160, 90, env_size=(64, 32)))
+    ph = r.primary_hits()
+    assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+    r.close()
+    g = np.load(os.path.join(GOLD, "g3_multi_80x60.npz"))
+    r = sp.Renderer().load_workload(W.multi_object_workload(width=80, height=60, spp=2, env_size=(256, 128)))
+    for cull in (1, 0):
+        sp.set_params(samplesPerPixel=2, cullByDistance=cull)
+        q = r.intersect_rays(g["origins"], g["dirs"])
+        assert same_bits(q["t"], g["rays_t"]) and np.array_equal(q["tri"], g["rays_tri"])
+        assert np.array_equal(q["obj"], g["rays_obj"]) and np.array_equal(q["material"], g["rays_material"])
+        assert same_bits(q["normal"], g["rays_normal"]) and same_bits(q["uv"], g["rays_uv"])
+        img, m = r.render_frame(frame=5)
+        assert same_bits(img, g["image_ref_dm"]) and np.array_equal(m[1:5], g["metrics_ref_dm"])
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configurations at full size
+
+def test_c2_monkey_primary_triangle_ids_full_size(params):
+    """BASELINE configs[1]: monkey 1920x1080 primary rays.  Closest-hit triangle ids must match
+    the reference except on equal-t ties; stated bound on the mismatch rate: < 1e-4."""
+    sp = params
+    wl = W.config2(1920, 1080, env_size=(64, 32))
+    r = sp.Renderer().load_workload(wl)
+    chk = best(False).scene().load_workload(wl)
+    e = chk.primary_hits()
+    for cull in (1, 0):
+        sp.set_params(cullByDistance=cull)
+        g = r.primary_hits()
+        assert same_bits(g["t"], e["t"])                      # hit / miss and distance: exact
+        mism = g["tri"] != e["tri"]
+        assert mism.mean() < 1e-4
+        assert (e["tri"] >= 0).sum() > 200000
+        # every mismatch is a tie: same t bits were already asserted; both must be hits
+        assert np.all(g["tri"][mism] >= 0) and np.all(e["tri"][mism] >= 0)
+    chk.close()
+    r.close()
+
+
+def test_c1_bunny_image_full_size(params):
+    """BASELINE configs[0]: bunny + studio_garden env (4096x2048), 1024x768, 1 spp, 3 bounces.
+    vs reference-dm: bit-exact.  vs the plain reference (glibc sinf/cosf/atan2f/powf, which are
+    not correctly rounded): stated tolerance -- at most 2 % of pixels may differ by more than
+    1e-3 relative (a last-ulp difference in a bounce direction can change which texel of the
+    noisy env map a path ends on), and whole-image RMSE <= 2 % of the mean radiance."""
+    sp = params
+    wl = W.config1(1024, 768)
+    r = sp.Renderer().load_workload(wl)
+    img, m = r.render_frame(frame=0)
+    img = img.copy()
+    chk = best(True).scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=1, bounces=3, frame=0)
+    chk.close()
+    assert same_bits(img, cimg) and np.array_equal(m[1:5], cm[1:5])
+    chk = best(False).scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=1, bounces=3, frame=0)
+    chk.close()
+    d = np.abs(img[..., :3].astype(np.float64) - cimg[..., :3])
+    rel = (d / np.maximum(np.abs(cimg[..., :3]), 1e-3)).max(axis=2)
+    rmse = float(np.sqrt((d ** 2).mean()))
+    assert (rel > 1e-3).mean() < 0.02, (rel > 1e-3).mean()
+    assert rmse <= 0.02 * float(cimg[..., :3].mean()), rmse
+    assert abs(int(m[2]) - int(cm[2])) <= 1e-3 * int(cm[2])   # rays traced: path topology
+    # fast f32 math mode (CUDA sinf/cosf/atan2f/powf): same tolerance against the reference
+    sp.set_params(mathMode=1)
+    img1, m1 = r.render_frame(frame=0)
+    d = np.abs(img1[..., :3].astype(np.float64) - cimg[..., :3])
+    rel = (d / np.maximum(np.abs(cimg[..., :3]), 1e-3)).max(axis=2)
+    assert (rel > 1e-3).mean() < 0.02 and float(np.sqrt((d ** 2).mean())) <= 0.02 * float(cimg[..., :3].mean())
+    r.close()
+
+
+def test_multi_object_scene_vs_reference(params):
+    """Instanced scene (13 objects, rotations, non-unit scales, textured plane): image, object
+    and triangle ids against the reference."""
+    sp = params
+    wl = W.multi_object_workload(width=320, height=240, spp=2)
+    r = sp.Renderer().load_workload(wl)
+    chk = best(True).scene().load_workload(wl)
+    sp.set_params(samplesPerPixel=2)
+    img, m = r.render_frame(frame=1)
+    cimg, cm = chk.render_seeded(spp=2, bounces=3, frame=1)
+    assert same_bits(img, cimg) and np.array_equal(m[1:5], cm[1:5])
+    g, e = r.primary_hits(), chk.primary_hits()
+    assert np.array_equal(g["obj"], e["obj"]) and np.array_equal(g["tri"], e["tri"]) and same_bits(g["t"], e["t"])
+    chk.close()
+    r.close()
+
+
+def test_five_bounces_vs_port(params):
+    """BASELINE config 3 asks for 5 bounces; the reference is fixed at 3 (literal at
+    simd_path_tracer.cpp:195), so the checker is the port, shown equal to the reference at 3."""
+    sp = params
+    wl = W.config3(256, 144, spp=4, bounces=5, env_size=(1024, 512))
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=4, bounceCount=5)
+    img, m = r.render_frame(frame=2)
+    chk = ora.load_port_dm().scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=4, bounces=5, frame=2)
+    assert same_bits(img, cimg) and np.array_equal(m[1:5], cm[1:5])
+    chk.close()
+    r.close()
+
+
+def test_c3_full_size_properties(params):
+    """BASELINE configs[2] at full size (3840x2160, 64 spp, 5 bounces) through size-independent
+    properties: (a) rendering in strips equals rendering the whole frame, bit for bit (what the
+    multi-GPU split relies on); (b) seeded rectangles of the frame equal the oracle port
+    bit-for-bit; (c) every pixel finite, alpha 1; (d) rays = hits + misses, paths = W*H*spp."""
+    sp = params
+    wl = W.config3()
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=64, bounceCount=5)
+    full, m = r.render_frame(frame=0)
+    full = full.copy()
+    assert np.isfinite(full).all() and (full[..., 3] == 1.0).all()
+    assert m[sp.sp_Metric_PathsTraced] == 3840 * 2160 * 64
+    assert m[sp.sp_Metric_RaysTraced] == m[sp.sp_Metric_RayHitCount] + m[sp.sp_Metric_RayMissCount]
+    r.image[:] = 0
+    total = np.zeros(12, np.uint64)
+    for (b, e) in ((0, 576), (576, 1280), (1280, 2160)):
+        mm, cost = r.render_rows(b, e, frame=0, want_cost=True)
+        total += mm
+        assert int(cost.sum()) == int(mm[sp.sp_Metric_RaysTraced])
+    assert same_bits(r.image, full) and np.array_equal(total[1:5], m[1:5])
+    chk = ora.load_port_dm().scene().load_workload(wl)
+    cimg = np.zeros_like(full)
+    rng = np.random.RandomState(8)
+    rects = [(1800, 1000, 1816, 1016), (0, 0, 16, 8), (3824, 2152, 3840, 2160)]
+    rects += [(x, y, x + 12, y + 12) for x, y in zip(rng.randint(1200, 2600, 5), rng.randint(400, 1700, 5))]
+    for rect in rects:
+        chk.render_seeded(spp=64, bounces=5, frame=0, rect=rect, image=cimg)
+        x0, y0, x1, y1 = rect
+        assert same_bits(full[y0:y1, x0:x1], cimg[y0:y1, x0:x1]), rect
+    chk.close()
+    r.close()

@@ -1,0 +1,414 @@
+"""The oracle pinned against the reference's own known-answer tests and against the reference
+itself (CPU only).
+
+Every KAT below restates a test of the reference's suites (file:line in each docstring) and runs
+on BOTH checkers: oracle/libsporacle.so (the port, oracle/sp_oracle.cpp) and, when built,
+oracle/_ref/libspref.so (the reference's unmodified sources).  The last section shows the port
+equal to the reference bit-for-bit on rendered images, hit ids and ray batches.
+"""
+import numpy as np
+import pytest
+
+import ora
+from vk_cinematic_b200 import workloads as W
+
+EPS = np.finfo(np.float32).eps
+PI = np.float32(3.14159265359)
+
+
+@pytest.fixture(params=["port", "ref"])
+def chk(request, port):
+    if request.param == "port":
+        return port
+    if not ora.have_ref():
+        pytest.skip("oracle/_ref not built")
+    return ora.load_ref()
+
+
+# ---------------------------------------------------------------------------------------------
+# unit_tests/unit_tests.cpp
+
+def test_compute_tiles(chk):
+    """unit_tests.cpp:40-79"""
+    n, t = chk.compute_tiles(10, 10, 2, 2, 64)
+    assert n == 25 and tuple(t[0]) == (0, 0, 2, 2) and tuple(t[1]) == (2, 0, 4, 2)
+    n, t = chk.compute_tiles(9, 9, 2, 2, 64)
+    assert n == 25 and tuple(t[24]) == (8, 8, 9, 9)
+    n, t = chk.compute_tiles(10, 10, 2, 2, 10)
+    assert n == 10
+
+
+def test_to_spherical_table(chk):
+    """unit_tests.cpp:144-175 (TEST_ASSERT_EQUAL_FLOAT: Unity's relative 1e-5 tolerance)"""
+    s = np.float32(1.0) / np.sqrt(np.float32(2.0))
+    dirs = [(1, 0, 0), (0, 0, -1), (0, 1, 0), (0, s, s), (-1, 0, 0)]
+    exp = [(0.0, PI * 0.5), (-PI * 0.5, PI * 0.5), (0.0, 0.0), (PI * 0.5, PI * 0.25), (PI, PI * 0.5)]
+    for d, e in zip(dirs, exp):
+        got = chk.to_spherical(d)
+        assert np.allclose(got, np.float32(e), rtol=1e-5, atol=1e-6), (d, got, e)
+
+
+def test_map_to_equirectangular_table(chk):
+    """unit_tests.cpp:177-209"""
+    ins = [(0.0, 0.0), (0.0, PI), (0.0, PI * 0.5), (PI * 0.5, PI * 0.5), (PI, PI * 0.5),
+           (PI * -0.5, PI * 0.5)]
+    exp = [(0.0, 1.0), (0.0, 0.0), (0.0, 0.5), (0.25, 0.5), (0.5, 0.5), (0.75, 0.5)]
+    for i, e in zip(ins, exp):
+        got = chk.map_equirect(i)
+        assert np.allclose(got, e, rtol=1e-5, atol=1e-6), (i, got, e)
+
+
+def test_spherical_to_cartesian_table(chk):
+    """unit_tests.cpp:245-280"""
+    s = np.float32(1.0) / np.sqrt(np.float32(2.0))
+    ins = [(0.0, PI * 0.5), (-PI * 0.5, PI * 0.5), (0.0, 0.0), (PI * 0.5, PI * 0.25), (PI, PI * 0.5)]
+    exp = [(1, 0, 0), (0, 0, -1), (0, 1, 0), (0, s, s), (-1, 0, 0)]
+    for i, e in zip(ins, exp):
+        got = chk.spherical_to_cartesian(i)
+        assert np.abs(got - np.float32(e)).max() <= EPS, (i, got, e)
+        assert abs(float(np.linalg.norm(got.astype(np.float64))) - 1.0) < 1e-5
+
+
+TRI = [(-0.5, -0.5, -5.0), (0.5, -0.5, -5.0), (0.0, 0.5, -5.0)]
+
+
+def test_ray_triangle_mt_kats(chk):
+    """unit_tests.cpp:348-426: t = 6, n = (0,0,1), u = v = 0, misses give t = -1"""
+    r = chk.ray_triangle_mt((0, 0, 1), (0, 0, -1), *TRI)
+    assert abs(r[0] - 6.0) <= EPS and np.abs(r[3:6] - (0, 0, 1)).max() <= EPS
+    off = np.float32((5, 0, 0))
+    r = chk.ray_triangle_mt((0, 0, 1), (0, 0, -1), *[np.float32(v) + off for v in TRI])
+    assert r[0] == -1.0
+    off = np.float32((0.5, 0.5, 0))
+    r = chk.ray_triangle_mt((0, 0, 1), (0, 0, -1), *[np.float32(v) + off for v in TRI])
+    assert abs(r[0] - 6.0) <= EPS and abs(r[1]) <= EPS and abs(r[2]) <= EPS
+    r = chk.ray_triangle_mt((0.5, 0.5, 1), (0, 0, -1), *TRI)  # barycentric-range issue
+    assert r[0] == -1.0
+
+
+def test_nearest_and_bilinear_sampling(chk):
+    """unit_tests.cpp:428-478"""
+    img = np.zeros((1, 2, 4), np.float32)
+    img[0, 1] = 1
+    assert chk.sample_nearest(img, 0.5, 0.5)[0] == 1.0
+    cb = np.zeros((2, 2, 4), np.float32)
+    cb[0, 1] = 1
+    cb[1, 0] = 1
+    assert chk.sample_bilinear(cb, 0.5, 0.5)[0] == 0.5
+    assert chk.sample_bilinear(cb, 1.0, 0.5)[0] == 0.5
+    assert chk.sample_bilinear(cb, 0.0, 0.5)[0] == 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# unit_tests/test_simd_path_tracer.cpp
+
+def test_configure_camera(chk):
+    """test_simd_path_tracer.cpp:137-168"""
+    c = chk.camera_fields((0, 2, 0), (0, 0, 0, 1), 0.1, 4, 2)
+    assert np.abs(c["right"] - (1, 0, 0)).max() <= EPS
+    assert np.abs(c["up"] - (0, 1, 0)).max() <= EPS
+    assert np.abs(c["forward"] - (0, 0, -1)).max() <= EPS
+    assert np.abs(c["filmCenter"] - np.float32((0, 2, -0.1))).max() <= EPS
+    assert c["halfPixelWidth"] == 0.125 and c["halfPixelHeight"] == 0.25
+    assert c["halfFilmWidth"] == 0.5 and c["halfFilmHeight"] == 0.25
+
+
+def test_calculate_film_positions(chk):
+    """test_simd_path_tracer.cpp:170-200"""
+    s = chk.scene()
+    s.configure_camera((0, 2, 0), (0, 0, 0, 1), 0.1, 4, 4)
+    p = s.film_positions([(0.5, 0.5), (1.5, 0.5), (0.5, 1.5), (3.5, 3.5)])
+    assert np.abs(p[0] - np.float32((-0.375, 2.375, -0.1))).max() <= EPS
+    assert np.abs(p[3] - np.float32((0.375, 1.625, -0.1))).max() <= EPS
+    s.close()
+
+
+def test_transform_aabb(chk):
+    """test_simd_path_tracer.cpp:202-214"""
+    mn, mx = chk.transform_aabb((-0.5,) * 3, (0.5,) * 3, (5, 0, 0), (0, 0, 0, 1), (1, 1, 1))
+    assert np.abs(mn - (4.5, -0.5, -0.5)).max() <= EPS and np.abs(mx - (5.5, 0.5, 0.5)).max() <= EPS
+
+
+TRI_VERTS = np.array([[-0.5, -0.5, 0, 0, 0, 1, 0, 0], [0.5, -0.5, 0, 0, 0, 1, 0, 0],
+                      [0.0, 0.5, 0, 0, 0, 1, 0, 0]], np.float32)
+
+
+def two_triangle_scene(chk):
+    s = chk.scene()
+    m = s.add_mesh(TRI_VERTS, [0, 1, 2])
+    s.add_object(m, 53, (0, 2, -5), (0, 0, 0, 1), (1, 1, 1))
+    s.add_object(m, 53, (0, 2, -15), W.quat_axis_angle((0, 1, 0), float(PI) * 0.25), (2, 2, 2))
+    s.build()
+    return s
+
+
+def test_ray_intersect_scene_two_objects(chk):
+    """test_simd_path_tracer.cpp:216-276: hit with material 53 (t = 5 on the near triangle)"""
+    s = two_triangle_scene(chk)
+    r = s.intersect_rays([(0, 2, 0)], [(0, 0, -1)])
+    assert r["t"][0] >= 0.0 and r["material"][0] == 53
+    assert abs(r["t"][0] - 5.0) < 1e-5 and r["obj"][0] == 0 and r["tri"][0] == 0
+    s.close()
+
+
+def test_path_trace_tile_magenta_and_bounds(chk):
+    """test_simd_path_tracer.cpp:49-135: no material -> magenta; only in-tile pixels written.
+    rng state 0 as in the reference test (XorShift32's fixed point)."""
+    s = chk.scene()
+    s.configure_camera((0, 0, 0), (0, 0, 0, 1), 0.0, 4, 4)
+    # the reference test leaves the camera zero-initialised apart from the image plane; a
+    # configured camera gives the same result: every ray misses the empty scene
+    img = np.zeros((4, 4, 4), np.float32)
+    s.path_trace_tile(img, (0, 0, 4, 4), 1, 3, 0)
+    assert np.abs(img - np.float32((1, 0, 1, 1))).max() <= EPS
+    img = np.zeros((4, 4, 4), np.float32)
+    state, m = s.path_trace_tile(img, (1, 1, 3, 3), 1, 3, 0)
+    exp = np.zeros((4, 4, 4), np.float32)
+    exp[1:3, 1:3] = (1, 0, 1, 1)
+    assert np.abs(img - exp).max() <= EPS
+    assert m[0] > 0  # TestMetrics, :333-368
+    s.close()
+
+
+def test_light_path_radiance(chk):
+    """test_simd_path_tracer.cpp:278-306 restated with roughness > 0 (the reference test predates
+    the GGX term and yields NaN = 0/0 at roughness 0).  Value: emission 1 through a
+    Lambert+GGX vertex at normal incidence; L = N, V = 0 -> H = N, F = 1 (Schlick at 0) so
+    kD = 0 and the result is the specular term alone."""
+    s = chk.scene()
+    s.register_material(0, emission=(1, 1, 1))
+    s.register_material(1, albedo=(0.18, 0.18, 0.18), roughness=0.6)
+    rad = s.radiance_for_path([
+        {"materialId": 1, "normal": (0, 1, 0), "incomingDir": (0, 1, 0)},
+        {"materialId": 0}])
+    a2 = np.float32(0.6) ** 4
+    ndf = a2 / (PI * a2 * a2)
+    assert np.all(np.isfinite(rad)) and rad[0] == rad[1] == rad[2]
+    # G = 0 (NdotV = 0) -> specular 0; diffuse: kD = 1 - F, F = 0.04 + 0.96 * 1 = 1 -> 0
+    assert rad[0] == 0.0
+    # with an outgoing direction the Lambert term appears: F(H.V = 1) = 0.04
+    rad = s.radiance_for_path([
+        {"materialId": 1, "normal": (0, 1, 0), "incomingDir": (0, 1, 0), "outgoingDir": (0, 1, 0)},
+        {"materialId": 0}])
+    k = (np.float32(1.6) ** 2) / 8
+    g = (1 / (1 * (1 - k) + k)) ** 2
+    expect = 0.96 * 0.18 / np.pi + ndf * g * 0.04 / 4.0001
+    assert abs(rad[0] - expect) < 1e-5
+    s.close()
+
+
+def test_material_albedo_texture(chk):
+    """test_simd_path_tracer.cpp:308-331 through a 2-vertex path: albedo (1,0,0) texture"""
+    s = chk.scene()
+    img = np.zeros((1, 1, 4), np.float32)
+    img[0, 0] = (1, 0, 0, 1)
+    s.register_texture(1, img)
+    s.register_material(0, emission=(1, 1, 1))
+    s.register_material(1, albedo_texture=1, roughness=0.6)
+    rad = s.radiance_for_path([
+        {"materialId": 1, "normal": (0, 1, 0), "incomingDir": (0, 1, 0), "outgoingDir": (0, 1, 0)},
+        {"materialId": 0}])
+    assert rad[0] > rad[1] and rad[1] == rad[2] and rad[1] > 0  # red albedo + grey specular
+    s.close()
+
+
+def test_ray_aabb_kats(chk):
+    """test_simd_path_tracer.cpp:425-485: t = 9.5; masks 0xF, 0, 0; the recorded SSE-vs-scalar
+    discrepancy vector (mask 1, scalar -1)"""
+    assert abs(chk.ray_aabb_scalar((-0.5,) * 3, (0.5,) * 3, (0, 0, 10), (0, 0, -1)) - 9.5) <= EPS
+    mins = [(-0.5, -0.5, -0.5), (-0.5, -0.5, 1.0), (-0.5, -0.5, 2.5), (-0.5, -0.5, 4.0)]
+    maxs = [(0.5, 0.5, 0.5), (0.5, 0.5, 2.0), (0.5, 0.5, 3.5), (0.5, 0.5, 5.0)]
+    with np.errstate(divide="ignore"):
+        inv = lambda d: np.float32(1.0) / np.float32(d)  # noqa: E731
+        assert chk.ray_aabb4(mins, maxs, (0, 0, 10), inv((0, 0, -1))) == 0xF
+        assert chk.ray_aabb4(mins, maxs, (0, 0, 10), inv((1, 0, 0))) == 0
+        assert chk.ray_aabb4(mins, maxs, (0, 0, 10), inv((0, 0, 1))) == 0
+        bmin = [(-0.375038534, 0.843911469, 0.264082730)] + [(0, 0, 0)] * 3
+        bmax = [(-0.238676921, 0.916244209, 0.386187375)] + [(0, 0, 0)] * 3
+        o = (-2.68516445, -1.71131170, -1.71610022)
+        d = (0.576836348, 0.652352035, 0.491626590)
+        assert chk.ray_aabb4(bmin, bmax, o, inv(d)) & 1 == 1
+        assert chk.ray_aabb_scalar(bmin[0], bmax[0], o, d) == -1.0
+
+
+def test_ray_aabb_compare_seeded(chk):
+    """test_simd_path_tracer.cpp:487-528: 32 rays, seed 0x1A34C249, 4-wide == scalar"""
+    state = 0x1A34C249
+    bmin = [(-2.0, -0.1, -0.5)] + [(0, 0, 0)] * 3
+    bmax = [(-0.5, 0.4, 3.0)] + [(0, 0, 0)] * 3
+
+    def lerp(a, b, t):
+        return np.float32(a) * (np.float32(1) - t) + np.float32(b) * t
+    for _ in range(32):
+        pts = []
+        for _k in range(6):
+            r, state = chk.random_bilateral(state)
+            pts.append(lerp(-10.0, 10.0, r))
+        p, q = np.float32(pts[0:3]), np.float32(pts[3:6])
+        d = q - p
+        d = d * (np.float32(1) / np.sqrt((d * d).sum(dtype=np.float32)))
+        t = chk.ray_aabb_scalar(bmin[0], bmax[0], p, d)
+        mask = chk.ray_aabb4(bmin, bmax, p, np.float32(1) / d) & 1
+        assert mask == (1 if t >= 0 else 0)
+
+
+def test_random_direction_on_hemisphere(chk):
+    """test_simd_path_tracer.cpp:530-544: 1000 chained samples, seed 123456789"""
+    state, normal = 123456789, np.float32((0, -1, 0))
+    for _ in range(1000):
+        v, state = chk.hemisphere(state, normal)
+        assert abs(float(np.sqrt((v.astype(np.float64) ** 2).sum())) - 1.0) <= 4 * EPS
+        assert float(np.dot(v, normal)) >= 0.0
+        normal = v
+
+
+def test_xorshift_fixed_point_and_range(chk):
+    """math_utils.h:184-214: state 0 is a fixed point (the reference's tests run with it);
+    unilateral in [0, 1], bilateral in [-1, 1]"""
+    r, s = chk.xorshift32(0)
+    assert (r, s) == (0, 0)
+    u, _ = chk.random_unilateral(0)
+    b, _ = chk.random_bilateral(0)
+    assert u == 0.0 and b == -1.0
+    r, s = chk.xorshift32(1)
+    assert r == s == 270369  # 1 -> x ^= x<<13; x ^= x>>17; x ^= x<<5
+    u, _ = chk.random_unilateral(0xFFFFFFFF)
+    assert 0.0 <= u <= 1.0
+
+
+# ---------------------------------------------------------------------------------------------
+# unit_tests/test_bvh.cpp
+
+def grid4x4():
+    mn, mx = [], []
+    for z in range(4):
+        for x in range(4):
+            c = np.float32((-10.0 + 20.0 * x / 3.0, 0.0, -10.0 + 20.0 * z / 3.0))
+            mn.append(c - np.float32(0.5))
+            mx.append(c + np.float32(0.5))
+    return np.float32(mn), np.float32(mx)
+
+
+def test_bvh_single_and_pair(chk):
+    """test_bvh.cpp:36-70: root bounds of one box and of two"""
+    r = chk.bvh_query([(-0.5,) * 3], [(0.5,) * 3], (0, 0, 10), (0, 0, -1), 4)
+    assert np.abs(r["root_min"] + 0.5).max() <= EPS and np.abs(r["root_max"] - 0.5).max() <= EPS
+    r = chk.bvh_query([(-0.5,) * 3, (1,) * 3], [(0.5,) * 3, (2,) * 3], (0, 0, 10), (0, 0, -1), 4)
+    assert np.abs(r["root_min"] + 0.5).max() <= EPS and np.abs(r["root_max"] - 2).max() <= EPS
+
+
+def test_bvh_all_leaves_reachable(chk):
+    """test_bvh.cpp:99-122: 31 boxes on a line; a ray along the line reports all 31"""
+    c = np.zeros((31, 3), np.float32)
+    c[:, 0] = np.arange(31)
+    r = chk.bvh_query(c - 0.25, c + 0.25, (-5, 0, 0), (1, 0, 0), 64)
+    assert sorted(r["leaves"].tolist()) == list(range(31)) and not r["error"]
+
+
+def test_bvh_grid_row_and_root(chk):
+    """test_bvh.cpp:181-244: a row ray hits 4 leaves; root bounds (-10.5,-0.5,-10.5)..(10.5,..)"""
+    mn, mx = grid4x4()
+    r = chk.bvh_query(mn, mx, (-20, 0, -10), (1, 0, 0), 4)
+    assert r["count"] == 4 and not r["error"] and sorted(r["leaves"].tolist()) == [0, 1, 2, 3]
+    assert np.abs(r["root_min"] - (-10.5, -0.5, -10.5)).max() <= EPS
+    assert np.abs(r["root_max"] - (10.5, 0.5, 10.5)).max() <= EPS
+
+
+def test_bvh_empty_and_oversubscription(chk):
+    """test_bvh.cpp:247-292"""
+    r = chk.bvh_query(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), (0, 0, 10),
+                      (0, 0, -1), 4)
+    assert r["count"] == 0
+    mn = [(-0.5, -0.5, -0.5), (-0.5, -0.5, -1.5)]
+    mx = [(0.5, 0.5, 0.5), (0.5, 0.5, -0.5)]
+    r = chk.bvh_query(mn, mx, (0, 0, 10), (0, 0, -1), 4)
+    assert r["count"] == 2 and not r["error"]
+    r = chk.bvh_query(mn, mx, (0, 0, 10), (0, 0, -1), 1)
+    assert r["count"] == 1 and r["error"]
+
+
+def test_mesh_tree_stats_icosphere(chk):
+    """integration_tests.cpp:60-85: every leaf of an icosphere midphase is reachable; parents
+    contain children (test_bvh.cpp:124-179)"""
+    m = W.icosphere_mesh(2)
+    s = chk.scene()
+    s.add_mesh(m.vertices, m.indices, True)
+    st = s.mesh_tree_stats(0)
+    assert st["leaves"] == 320 and st["all_reachable"] and st["parents_contain_children"]
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the port against the reference itself
+
+def test_jitter_draw_order(port):
+    """SURVEY.md §7 hard part 1: Vec2(hw*RandomBilateral(rng), hh*RandomBilateral(rng)) --
+    g++ evaluates right to left, so the FIRST draw jitters y.  Pinned through primary-ray
+    directions: the ray through pixel (x, y) must be the one built with y <- first draw."""
+    s = port.scene()
+    w, h = 8, 6
+    s.configure_camera((0, 0, 0), (0, 0, 0, 1), 0.8, w, h)
+    ph = s.primary_hits(sample=0, frame=0, threads=1, want_dirs=True)
+    cam = port.camera_fields((0, 0, 0), (0, 0, 0, 1), 0.8, w, h)
+    x, y = 5, 2
+    state = port.seed(x + y * w, 0, 0)
+    b1, state = port.random_bilateral(state)
+    b2, state = port.random_bilateral(state)
+    px = np.float32(x + 0.5) + cam["halfPixelWidth"] * b2
+    py = np.float32(y + 0.5) + cam["halfPixelHeight"] * b1
+    film = s.film_positions([(px, py)])[0]
+    d = film - cam["position"]
+    d = d * (np.float32(1) / np.sqrt((d * d).sum(dtype=np.float32)))
+    assert np.array_equal(d.view(np.uint32), ph["dir"][y, x].view(np.uint32))
+    s.close()
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32),
+                          np.ascontiguousarray(b).view(np.uint32))
+
+
+@pytest.mark.parametrize("dm", [False, True])
+def test_port_equals_reference_image(port, port_dm, ref, ref_dm, dm):
+    """The restatement renders the same bits as the unmodified reference (bunny 96x64, 2 spp,
+    smooth shading, env lookups), in both math modes."""
+    wl = W.config1(96, 64, env_size=(512, 256))
+    a = (ref_dm if dm else ref).scene().load_workload(wl)
+    b = (port_dm if dm else port).scene().load_workload(wl)
+    ia, ma = a.render_seeded(spp=2, bounces=3, frame=1)
+    ib, mb = b.render_seeded(spp=2, bounces=3, frame=1)
+    assert _same_bits(ia, ib) and np.array_equal(ma[1:5], mb[1:5])
+    ta, tb = np.zeros_like(ia), np.zeros_like(ia)
+    sa, _ = a.path_trace_tile(ta, (16, 8, 48, 40), 2, 3, 0xF51C0E49)
+    sb, _ = b.path_trace_tile(tb, (16, 8, 48, 40), 2, 3, 0xF51C0E49)
+    assert sa == sb and _same_bits(ta, tb)
+    a.close()
+    b.close()
+
+
+def test_port_equals_reference_multi_object(port, ref):
+    wl = W.multi_object_workload(width=80, height=60, spp=2, env_size=(256, 128))
+    a = ref.scene().load_workload(wl)
+    b = port.scene().load_workload(wl)
+    ia, ma = a.render_seeded(spp=2, bounces=3, frame=5)
+    ib, mb = b.render_seeded(spp=2, bounces=3, frame=5)
+    assert _same_bits(ia, ib) and np.array_equal(ma[1:5], mb[1:5])
+    pa, pb = a.primary_hits(), b.primary_hits()
+    assert np.array_equal(pa["tri"], pb["tri"]) and np.array_equal(pa["obj"], pb["obj"])
+    assert _same_bits(pa["t"], pb["t"])
+    a.close()
+    b.close()
+
+
+def test_port_five_bounces_extends_three(port):
+    """The port at 5 bounces (BASELINE config 3; the reference is fixed at 3): paths that end
+    within 3 bounces are unchanged -- pixels whose every sample terminated early are identical."""
+    wl = W.config1(64, 48, env_size=(256, 128))
+    s = port.scene().load_workload(wl)
+    i3, m3 = s.render_seeded(spp=1, bounces=3, frame=0)
+    i5, m5 = s.render_seeded(spp=1, bounces=5, frame=0)
+    assert m5[2] >= m3[2] and m5[1] == m3[1]
+    same = (i3.view(np.uint32) == i5.view(np.uint32)).all(axis=2)
+    assert same.mean() > 0.8  # background + short paths
+    assert np.all(np.isfinite(i5))
+    s.close()

@@ -8,5 +8,6 @@ raises if it, or any symbol include/sp_b200.h declares, is missing -- there is n
 """
 from . import sp  # noqa: F401  (loads and checks the shared library)
 from . import workloads  # noqa: F401
+from . import strips  # noqa: F401
 
-__all__ = ["sp", "workloads"]
+__all__ = ["sp", "workloads", "strips"]

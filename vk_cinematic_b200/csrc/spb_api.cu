@@ -410,6 +410,7 @@ extern "C" void sp_b200_SetParams(const sp_b200_Params *params)
 extern "C" void sp_b200_GetParams(sp_b200_Params *params) { *params = lib().params; }
 extern "C" void sp_b200_GetLastStats(sp_b200_Stats *stats) { *stats = lib().lastStats; }
 extern "C" void sp_b200_EnableStats(int enable) { lib().statsEnabled = enable != 0; }
+extern "C" u64 sp_b200_KernelLaunchCount(void) { return g_kernelLaunches; }
 
 extern "C" void sp_b200_FlushTextureCache(void)
 {
@@ -498,6 +499,15 @@ extern "C" void sp_b200_ReleaseScene(sp_Scene *scene)
         L.scenes.erase(scene->broadphaseTree.root);
         scene->broadphaseTree.root = nullptr;
     }
+}
+
+extern "C" u64 sp_b200_SceneDeviceBytes(sp_Scene *scene)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (!scene || !scene->broadphaseTree.root) return 0;
+    auto it = L.scenes.find(scene->broadphaseTree.root);
+    return it == L.scenes.end() ? 0 : (u64)it->second->deviceBytes;
 }
 
 extern "C" void sp_b200_ReleaseMesh(sp_Mesh *mesh)

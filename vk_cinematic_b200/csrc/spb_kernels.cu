@@ -12,6 +12,8 @@
 
 namespace spb {
 
+unsigned long long g_kernelLaunches = 0;
+
 __device__ __forceinline__ unsigned warp_sum(unsigned v)
 {
     return __reduce_add_sync(0xFFFFFFFFu, v);
@@ -54,6 +56,7 @@ SPB_DECL_RENDER(1, 1)
 void launch_render(const KernelConfig &cfg, const RenderArgs &args, cudaStream_t stream)
 {
     if (args.x1 <= args.x0 || args.y1 <= args.y0) return;
+    g_kernelLaunches++;
     if (cfg.math == 0 && cfg.envFilter == 0) launch_render_m0e0(cfg, args, stream);
     else if (cfg.math == 0) launch_render_m0e1(cfg, args, stream);
     else if (cfg.envFilter == 0) launch_render_m1e0(cfg, args, stream);
@@ -63,6 +66,7 @@ void launch_render(const KernelConfig &cfg, const RenderArgs &args, cudaStream_t
 void launch_tiles_serial(const KernelConfig &cfg, const TileArgs &args, cudaStream_t stream)
 {
     if (args.count == 0) return;
+    g_kernelLaunches++;
     if (cfg.math == 0 && cfg.envFilter == 0) launch_tiles_m0e0(cfg, args, stream);
     else if (cfg.math == 0) launch_tiles_m0e1(cfg, args, stream);
     else if (cfg.envFilter == 0) launch_tiles_m1e0(cfg, args, stream);
@@ -121,6 +125,7 @@ void launch_primary_hits(const KernelConfig &cfg, const DScene &scene, const DCa
                          unsigned long long *counters, cudaStream_t stream)
 {
     if (camera.width == 0 || camera.height == 0) return;
+    g_kernelLaunches++;
     dim3 grid((camera.width + 15) / 16, (camera.height + 15) / 16);
     if (cfg.cull)
     {
@@ -189,6 +194,7 @@ void launch_intersect_batch(const KernelConfig &cfg, const DScene &scene, uint32
                             unsigned long long *counters, cudaStream_t stream)
 {
     if (count == 0) return;
+    g_kernelLaunches++;
     unsigned blocks = (count + 127) / 128;
     if (cfg.cull)
     {
@@ -259,6 +265,7 @@ void launch_intersect_mesh(const KernelConfig &cfg, const DScene &scene, uint32_
                            const float *origin3, const float *dir3, HitRecord *out,
                            cudaStream_t stream)
 {
+    g_kernelLaunches++;
     if (cfg.cull) k_intersect_mesh<true><<<1, 1, 0, stream>>>(scene, smooth, origin3, dir3, out);
     else k_intersect_mesh<false><<<1, 1, 0, stream>>>(scene, smooth, origin3, dir3, out);
 }
@@ -294,6 +301,7 @@ void launch_collect_leaves(const DScene &scene, const float *origin3, const floa
                            uint32_t *leaves, uint32_t maxLeaves, uint32_t *countAndError,
                            cudaStream_t stream)
 {
+    g_kernelLaunches++;
     k_collect_leaves<<<1, 1, 0, stream>>>(scene, origin3, dir3, leaves, maxLeaves, countAndError);
 }
 
@@ -329,6 +337,7 @@ void launch_radiance_for_path(const KernelConfig &cfg, const DMaterials *materia
                               const float *path15, uint32_t n, float clampValue, float *out3,
                               cudaStream_t stream)
 {
+    g_kernelLaunches++;
     KernelConfig c = cfg;
     c.cull = 0;
     c.stats = 0;
@@ -358,6 +367,7 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
                               uint32_t materialSlot, const float *vertex15, float *out7,
                               cudaStream_t stream)
 {
+    g_kernelLaunches++;
     KernelConfig c = cfg;
     c.cull = 0;
     c.stats = 0;

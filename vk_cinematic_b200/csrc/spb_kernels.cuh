@@ -37,6 +37,9 @@ struct RenderArgs
     uint32_t tileHeight;
 };
 
+// number of kernels this library has launched since load (bench.py's gpu_launches)
+extern unsigned long long g_kernelLaunches;
+
 void launch_render(const KernelConfig &cfg, const RenderArgs &args, cudaStream_t stream);
 
 // sp_PathTraceTile semantics: one serial XorShift32 stream per tile (simd_path_tracer.cpp:178-345)

@@ -234,6 +234,7 @@ _SIGNATURES = {
     "sp_b200_GetParams": (None, [_P(sp_b200_Params)]),
     "sp_b200_GetLastStats": (None, [_P(sp_b200_Stats)]),
     "sp_b200_EnableStats": (None, [C.c_int]),
+    "sp_b200_KernelLaunchCount": (u64, []),
     "sp_b200_FlushTextureCache": (None, []),
     "sp_b200_Seed": (u32, [u32, u32, u32]),
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
@@ -244,6 +245,7 @@ _SIGNATURES = {
                                                  C.c_void_p, C.c_void_p, C.c_void_p, _P(sp_Metrics)]),
     "sp_b200_MeshIntersectedLeaves": (u32, [sp_Mesh, vec3, vec3, C.c_void_p, u32, _P(u32)]),
     "sp_b200_MeshTreeInfo": (None, [sp_Mesh, _P(sp_b200_TreeInfo)]),
+    "sp_b200_SceneDeviceBytes": (u64, [_P(sp_Scene)]),
     "sp_b200_ReleaseMesh": (None, [_P(sp_Mesh)]),
     "sp_b200_ReleaseScene": (None, [_P(sp_Scene)]),
 }
