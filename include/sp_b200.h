@@ -202,6 +202,10 @@ typedef void (*sp_b200_LogFn)(const char *message);
 
 enum { SP_B200_ENV_NEAREST = 0, SP_B200_ENV_BILINEAR = 1 };
 enum { SP_B200_MATH_F64_ROUNDED = 0, SP_B200_MATH_FAST_F32 = 1 };
+/* WAVEFRONT: ray generation / traversal / shading as separate kernels over compact device
+ * queues with warp-level lane refill (the default).  PER_PIXEL: one thread walks all samples and
+ * bounces of a pixel (kept as a cross-check; both give bit-identical images). */
+enum { SP_B200_RENDER_WAVEFRONT = 0, SP_B200_RENDER_PER_PIXEL = 1 };
 
 /* Run-time form of the reference's compile-time knobs (config.h:15-33). */
 typedef struct sp_b200_Params {
@@ -214,6 +218,8 @@ typedef struct sp_b200_Params {
                             exactly like bvh_IntersectRay (bvh.cpp:203-311) */
     u32 tileWidth;       /* TILE_WIDTH / TILE_HEIGHT, config.h:15-16 (cost accounting granularity) */
     u32 tileHeight;
+    u32 renderMode;      /* SP_B200_RENDER_*: how sp_b200_Render* schedules the work on the GPU */
+    u32 samplesPerPass;  /* wavefront mode: samples per pixel traced per pass; 0 = automatic */
 } sp_b200_Params;
 
 /* Kernel-side counters of the most recent launch (for the roofline). */

@@ -139,8 +139,18 @@ extern "C" uint32_t ora_seed(uint32_t pixelIndex, uint32_t sample, uint32_t fram
 
 static int g_hostsimCull = 1;
 extern "C" void hostsim_set_cull(int cull) { g_hostsimCull = cull; }
+// 1: traverse with the resumable state machine the wavefront kernels use (trav_step)
+static int g_hostsimStepped = 0;
+extern "C" void hostsim_set_stepped(int stepped) { g_hostsimStepped = stepped; }
 
 template <bool CULL>
+static Hit hs_intersect(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT)
+{
+    return g_hostsimStepped ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, nullptr)
+                            : intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+}
+
+template <bool CULL, bool STEPPED>
 static void render_rows(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uint32_t x1,
                         uint32_t y1, uint32_t spp, uint32_t bounces, uint32_t frame,
                         uint32_t tid, uint32_t threads, uint64_t *m)
@@ -158,8 +168,8 @@ static void render_rows(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uin
             for (uint32_t sample = 0; sample < spp; ++sample)
             {
                 uint32_t rng = stream_seed(x + y * width, sample, frame);
-                f3 r = trace_path<0, 0, CULL>(s->d, s->dm, s->dc, x, y, rng, bounces, 10.0f,
-                                              stack, stackT, pc, nullptr);
+                f3 r = trace_path<0, 0, CULL, STEPPED>(s->d, s->dm, s->dc, x, y, rng, bounces, 10.0f,
+                                                       stack, stackT, pc, nullptr);
                 total = add3(total, mul3(r, weight));
                 paths++;
             }
@@ -180,10 +190,14 @@ extern "C" void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32
     if (threads == 0) threads = 1;
     std::vector<std::vector<uint64_t>> per(threads, std::vector<uint64_t>(ORA_METRIC_COUNT, 0));
     auto worker = [&](uint32_t tid) {
-        if (g_hostsimCull)
-            render_rows<true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+        if (g_hostsimCull && g_hostsimStepped)
+            render_rows<true, true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+        else if (g_hostsimCull)
+            render_rows<true, false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+        else if (g_hostsimStepped)
+            render_rows<false, true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
         else
-            render_rows<false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+            render_rows<false, false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
     };
     std::vector<std::thread> pool;
     for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
@@ -248,8 +262,8 @@ extern "C" void ora_primary_hits(ora_Scene *s, int32_t *triId, int32_t *objId, f
                 uint32_t rng = stream_seed(x + y * width, sample, frame);
                 f3 o, d;
                 primary_ray(s->dc, x, y, rng, o, d);
-                Hit h = g_hostsimCull ? intersect_scene<true>(s->d, o, d, stack, stackT, nullptr)
-                                      : intersect_scene<false>(s->d, o, d, stack, stackT, nullptr);
+                Hit h = g_hostsimCull ? hs_intersect<true>(s->d, o, d, stack, stackT)
+                                      : hs_intersect<false>(s->d, o, d, stack, stackT);
                 uint32_t index = x + y * width;
                 int32_t tri = -1;
                 if (h.object >= 0) tri = (int32_t)f2u(s->d.tris[(size_t)h.slot * 3].w);
@@ -275,8 +289,8 @@ extern "C" void ora_intersect_rays(ora_Scene *s, uint32_t n, const float *origin
     {
         f3 o = mk3(origins3[i * 3], origins3[i * 3 + 1], origins3[i * 3 + 2]);
         f3 d = mk3(dirs3[i * 3], dirs3[i * 3 + 1], dirs3[i * 3 + 2]);
-        Hit h = g_hostsimCull ? intersect_scene<true>(s->d, o, d, stack, stackT, nullptr)
-                              : intersect_scene<false>(s->d, o, d, stack, stackT, nullptr);
+        Hit h = g_hostsimCull ? hs_intersect<true>(s->d, o, d, stack, stackT)
+                              : hs_intersect<false>(s->d, o, d, stack, stackT);
         float *out = out7 ? out7 + (size_t)i * 7 : nullptr;
         int32_t tri = -1;
         if (h.object >= 0)

@@ -409,6 +409,7 @@ def build_hostsim():
 def load_hostsim():
     o = OracleLib(HOSTSIM_LIB)
     o.lib.hostsim_set_cull.argtypes = [C.c_int]
+    o.lib.hostsim_set_stepped.argtypes = [C.c_int]
     return o
 
 

@@ -64,9 +64,13 @@ def test_g3_port_rays_and_image(port, port_dm):
 # hostsim = vk_cinematic_b200/csrc/spb_core.cuh + the host builder compiled for the host: the
 # LOGIC of the CUDA path (not the GPU) against the reference's outputs.  No GPU parity claim.
 
+@pytest.mark.parametrize("stepped", [0, 1])
 @pytest.mark.parametrize("cull", [1, 0])
-def test_hostsim_logic_against_golden(hostsim, cull):
+def test_hostsim_logic_against_golden(hostsim, cull, stepped):
+    """stepped = 1 traverses with the resumable state machine of the wavefront kernels
+    (spb_core.cuh trav_step), 0 with the recursive-descent form of the per-pixel kernels."""
     hostsim.lib.hostsim_set_cull(cull)
+    hostsim.lib.hostsim_set_stepped(stepped)
     g = gold("g1_bunny_96x64.npz")
     s = hostsim.scene().load_workload(W.config1(96, 64, env_size=(512, 256)))
     img, m = s.render_seeded(spp=2, bounces=3, frame=1)
@@ -88,6 +92,7 @@ def test_hostsim_logic_against_golden(hostsim, cull):
     assert same_bits(img, g["image_ref_dm"])
     s.close()
     hostsim.lib.hostsim_set_cull(1)
+    hostsim.lib.hostsim_set_stepped(0)
 
 
 def test_hostsim_five_bounces_against_port(hostsim, port_dm):

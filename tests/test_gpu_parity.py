@@ -39,14 +39,17 @@ def best(dm):
     return ora.load_port_dm() if dm else ora.load_port()
 
 
-@pytest.fixture()
-def params(gpu_sp):
+@pytest.fixture(params=["wavefront", "per_pixel"])
+def params(gpu_sp, request):
+    """Every test runs under both schedulers of sp_b200_Render*: the wavefront kernels (default)
+    and the one-thread-per-pixel kernel."""
+    mode = 0 if request.param == "wavefront" else 1
     gpu_sp.set_params(samplesPerPixel=1, bounceCount=3, radianceClamp=10.0, envFilter=0, mathMode=0,
-                      cullByDistance=1, tileWidth=64, tileHeight=64)
+                      cullByDistance=1, tileWidth=64, tileHeight=64, renderMode=mode, samplesPerPass=0)
     gpu_sp.lib.sp_b200_EnableStats(0)
     yield gpu_sp
     gpu_sp.set_params(samplesPerPixel=1, bounceCount=3, radianceClamp=10.0, envFilter=0, mathMode=0,
-                      cullByDistance=1, tileWidth=64, tileHeight=64)
+                      cullByDistance=1, tileWidth=64, tileHeight=64, renderMode=0, samplesPerPass=0)
     gpu_sp.lib.sp_b200_EnableStats(0)
 
 
@@ -394,4 +397,34 @@ def test_c3_full_size_properties(params):
         x0, y0, x1, y1 = rect
         assert same_bits(full[y0:y1, x0:x1], cimg[y0:y1, x0:x1]), rect
     chk.close()
+    r.close()
+
+
+def test_wavefront_pass_split_and_stats(gpu_sp):
+    """Wavefront scheduling details: any samples-per-pass split gives the same bits (the sample
+    order of the accumulation is kept, simd_path_tracer.cpp:321); the stats launch counts the same
+    rays; per-tile-row cost sums to the rays traced."""
+    sp = gpu_sp
+    wl = W.config1(200, 150, env_size=(256, 128))
+    r = sp.Renderer().load_workload(wl)
+    ref_img = None
+    for spass in (0, 1, 3, 7):
+        sp.set_params(samplesPerPixel=7, bounceCount=4, renderMode=0, samplesPerPass=spass, mathMode=0,
+                      envFilter=0, cullByDistance=1, radianceClamp=10.0)
+        img, m = r.render_frame(frame=3)
+        if ref_img is None:
+            ref_img, ref_m = img.copy(), m.copy()
+        assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
+    sp.set_params(renderMode=1)
+    img, m = r.render_frame(frame=3)
+    assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
+    sp.set_params(renderMode=0, samplesPerPass=2)
+    sp.lib.sp_b200_EnableStats(1)
+    mm, cost = r.render_rows(0, 150, frame=3, want_cost=True)
+    st = sp.last_stats()
+    sp.lib.sp_b200_EnableStats(0)
+    assert int(st.rays) == int(ref_m[2]) and st.nodeVisits > st.rays and st.triangleTests > 0
+    assert int(cost.sum()) == int(ref_m[2]) and len(cost) == 3
+    assert same_bits(r.image, ref_img)
+    sp.set_params(samplesPerPixel=1, bounceCount=3, samplesPerPass=0)
     r.close()

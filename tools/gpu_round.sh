@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU session: parity tests, smoke, bench, launch list and one full ncu capture of the top kernel.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu_${TAG}.txt 2>&1
+nproc >> gpurun_out/gpu_${TAG}.txt
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${TAG}.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu_${TAG}.log
+timeout 300 python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke_${TAG}.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+echo "bench exit $?" >> gpurun_out/bench_${TAG}.err
+timeout 600 python bench.py --steps 5 --warmup 3 --render-mode 1 --no-cpu-baseline > gpurun_out/bench_perpixel_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --steps 2 --warmup 3 --spp 8 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 8 -c 2 -f -o gpurun_out/prof_${TAG} \
+    python bench.py --steps 1 --warmup 3 --spp 8 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
+ls -la gpurun_out
+tail -5 gpurun_out/pytest_gpu_${TAG}.log; cat gpurun_out/smoke_${TAG}.log | tail -3; cat gpurun_out/bench_${TAG}.json | cut -c1-300; cat gpurun_out/bench_${TAG}.err | tail -5

@@ -113,6 +113,8 @@ struct Library
     std::map<const float *, std::unique_ptr<TextureEntry>> textures;
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
+    // wavefront working set (DESIGN.md "Data layout")
+    DeviceBuffer wRays[2], wHitRec, wHitObj, wHitQ, wMissQ, wTerms, wRad, wCtr;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -126,6 +128,8 @@ struct Library
         params.cullByDistance = 1;
         params.tileWidth = 64;
         params.tileHeight = 64;
+        params.renderMode = SP_B200_RENDER_WAVEFRONT;
+        params.samplesPerPass = 0;
     }
 };
 
@@ -351,6 +355,86 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
     return (DeviceScene *)accel->deviceScene;
 }
 
+// Wavefront render of args' rectangle: passes of S samples, each a fixed sequence of kernels
+// over device queues (spb_wavefront.cu).  Nothing is read back between kernels.
+void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
+{
+    Library &L = lib();
+    const uint32_t width = ra.x1 - ra.x0, height = ra.y1 - ra.y0;
+    const uint32_t stripPixels = width * height;
+    const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
+    const uint32_t itemsPerSample = blocksX * blocksY * 32;
+    const uint32_t spp = ra.spp, bounces = ra.bounces;
+
+    // samples per pass: enough paths in flight to fill the GPU, bounded working set
+    uint32_t S = L.params.samplesPerPass;
+    if (S == 0)
+    {
+        const uint64_t targetItems = 16u << 20; // 16 Mi paths per pass
+        S = (uint32_t)(targetItems / (itemsPerSample ? itemsPerSample : 1));
+        if (S < 1) S = 1;
+    }
+    if (S > spp) S = spp;
+    SPB_ASSERT((uint64_t)itemsPerSample * S < 0xFFFFFFFFull);
+    const uint32_t capacity = itemsPerSample * S; // ray slots and path ids both fit
+    const uint32_t passes = (spp + S - 1) / S;
+
+    L.wRays[0].ensure((size_t)capacity * 32);
+    L.wRays[1].ensure((size_t)capacity * 32);
+    L.wHitRec.ensure((size_t)capacity * 16);
+    L.wHitObj.ensure((size_t)capacity * 4);
+    L.wHitQ.ensure((size_t)capacity * 4);
+    L.wMissQ.ensure((size_t)capacity * 4);
+    L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
+    L.wRad.ensure((size_t)capacity * 16);
+    const size_t ctrWords = (size_t)passes * bounces * WCTR_STRIDE;
+    L.wCtr.ensure(ctrWords * 4);
+    SPB_CUDA(cudaMemsetAsync(L.wCtr.ptr, 0, ctrWords * 4, L.stream));
+
+    WaveArgs a;
+    a.scene = ra.scene;
+    a.materials = ra.materials;
+    a.camera = ra.camera;
+    a.x0 = ra.x0; a.y0 = ra.y0; a.x1 = ra.x1; a.y1 = ra.y1;
+    a.stripPixels = stripPixels;
+    a.blocksX = blocksX;
+    a.itemsPerSample = itemsPerSample;
+    a.spp = spp;
+    a.bounces = bounces;
+    a.frame = ra.frame;
+    a.pathCapacity = capacity;
+    a.clampValue = ra.clampValue;
+    a.rays[0] = (v4f *)L.wRays[0].ptr;
+    a.rays[1] = (v4f *)L.wRays[1].ptr;
+    a.hitRec = (v4f *)L.wHitRec.ptr;
+    a.hitObj = (uint32_t *)L.wHitObj.ptr;
+    a.hitQ = (uint32_t *)L.wHitQ.ptr;
+    a.missQ = (uint32_t *)L.wMissQ.ptr;
+    a.pathTerms = (v4f *)L.wTerms.ptr;
+    a.rad = (v4f *)L.wRad.ptr;
+    a.out = ra.out;
+    a.stats = L.statsEnabled ? ra.counters : nullptr;
+    a.tileRowCost = ra.tileRowCost;
+    a.tileHeight = ra.tileHeight;
+
+    KernelConfig cfg = kernel_config();
+    for (uint32_t pass = 0; pass < passes; ++pass)
+    {
+        a.firstSample = pass * S;
+        a.samplesThisPass = spp - a.firstSample < S ? spp - a.firstSample : S;
+        a.workItems = itemsPerSample * a.samplesThisPass;
+        a.ctr = (uint32_t *)L.wCtr.ptr + (size_t)pass * bounces * WCTR_STRIDE;
+        launch_wave_trace(cfg, a, 0, true, L.stream);
+        for (uint32_t b = 0; b < bounces; ++b)
+        {
+            launch_wave_shade(cfg, a, b, L.stream);
+            if (b + 1 < bounces) launch_wave_trace(cfg, a, b + 1, false, L.stream);
+        }
+        launch_wave_accumulate(a, L.stream);
+    }
+    countersOut.resize(ctrWords);
+}
+
 } // namespace
 
 // =============================================================================================
@@ -387,6 +471,8 @@ extern "C" void sp_b200_Shutdown(void)
     L.emptyScene.reset();
     L.image.release(); L.counters.release(); L.materials.release();
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
+    L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release(); L.wHitObj.release();
+    L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
     if (L.initialized)
     {
         cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
@@ -405,6 +491,7 @@ extern "C" void sp_b200_SetParams(const sp_b200_Params *params)
     SPB_ASSERT(params->samplesPerPixel >= 1);
     SPB_ASSERT(params->bounceCount >= 1 && params->bounceCount <= SPB_MAX_BOUNCES);
     SPB_ASSERT(params->tileWidth >= 1 && params->tileHeight >= 4 && params->tileHeight % 4 == 0);
+    SPB_ASSERT(params->renderMode <= SP_B200_RENDER_PER_PIXEL);
     lib().params = *params;
 }
 extern "C" void sp_b200_GetParams(sp_b200_Params *params) { *params = lib().params; }
@@ -977,19 +1064,26 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     args.clampValue = L.params.radianceClamp;
     args.out = image;
     args.counters = ctr;
-    args.tileRowCost = ctr + CTR_COUNT;
+    args.tileRowCost = tileRowCost ? ctr + CTR_COUNT : nullptr;
     args.tileHeight = tileH;
     // the kernel tiles the rectangle from y0 in 16-row CTAs; keep CTA rows inside one tile row
     // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
     SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);
 
+    std::vector<unsigned long long> c(CTR_COUNT + tileRows);
+    std::vector<uint32_t> waveCounters;
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
-    launch_render(kernel_config(), args, L.stream);
+    if (L.params.renderMode == SP_B200_RENDER_PER_PIXEL)
+        launch_render(kernel_config(), args, L.stream);
+    else
+        render_wavefront(args, waveCounters);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
 
-    std::vector<unsigned long long> c(CTR_COUNT + tileRows);
     SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
+    if (!waveCounters.empty())
+        SPB_CUDA(cudaMemcpyAsync(waveCounters.data(), L.wCtr.ptr, waveCounters.size() * 4,
+                                 cudaMemcpyDeviceToHost, L.stream));
     if (hostPixels)
     {
         size_t offset = (size_t)rowBegin * cam.width;
@@ -1002,6 +1096,22 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     float kernelMs = 0, totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
     SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    if (!waveCounters.empty())
+    {
+        // queue lengths are the path counters: rays = rays entering each traversal, and every
+        // ray ends in exactly one of the hit / miss queues
+        unsigned long long rays = 0, hits = 0, misses = 0;
+        for (size_t i = 0; i + WCTR_STRIDE <= waveCounters.size(); i += WCTR_STRIDE)
+        {
+            hits += waveCounters[i + WCTR_HITS];
+            misses += waveCounters[i + WCTR_MISSES];
+        }
+        rays = hits + misses;
+        c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * L.params.samplesPerPixel;
+        c[CTR_RAYS] = rays;
+        c[CTR_HITS] = hits;
+        c[CTR_MISSES] = misses;
+    }
     add_metrics(metrics, c.data(), kernelMs);
     record_stats(c.data(), kernelMs, totalMs);
     if (tileRowCost)

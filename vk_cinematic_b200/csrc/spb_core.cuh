@@ -548,6 +548,268 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
     return best;
 }
 
+// ------------------------------------------------------------------------------------------
+// Resumable traversal: the same closest-hit query as intersect_scene(), written as a state
+// machine so that a warp can advance 32 independent rays one node visit at a time, retire the
+// finished ones and refill their lanes (spb_wavefront.cu).  One loop body serves both levels:
+// in the TLAS a "leaf" child is an object and is pushed on the stack (objects pop in child order
+// before the internal children, which pop near to far -- the order intersect_scene() uses);
+// inside an object a leaf child is a triangle and is tested at once, in child order, before the
+// internal children are culled against the shortened distance.  Only the fast slab form is used
+// here: a ray (world or object space) whose reciprocal direction is not finite sets `slow` and
+// the caller finishes it with intersect_scene(), which has the exact form.
+#define SPB_NODE_DONE 0xFFFFFFFEu
+
+struct Trav
+{
+    f3 o, d, inv;     // ray in the current space (world in the TLAS, object space inside an object)
+    f3 wo, wd;        // the world ray
+    float tcull;      // cull distance in the current space
+    float worldCull;  // TLAS cull distance, parked while inside an object
+    uint32_t node;    // node to visit next; SPB_NODE_DONE when the query is finished
+    int sp;           // stack pointer
+    int blasBase;     // -1 in the TLAS, else the stack pointer at object entry
+    uint32_t object;  // object being traversed
+    float lT, lU, lV; // closest hit inside the current object (object space)
+    uint32_t lSlot;
+    float bT, bU, bV; // closest hit so far (world t)
+    uint32_t bSlot;
+    int32_t bObject;
+    uint32_t slow;
+};
+
+SPB_HD void trav_begin(const DScene &S, f3 o, f3 d, Trav &st)
+{
+    st.wo = o;
+    st.wd = d;
+    st.o = o;
+    st.d = d;
+    st.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    st.tcull = u2f(0x7F800000u);
+    st.worldCull = st.tcull;
+    st.sp = 0;
+    st.blasBase = -1;
+    st.object = 0;
+    st.lT = -1.0f; st.lU = st.lV = 0.0f; st.lSlot = 0;
+    st.bT = -1.0f; st.bU = st.bV = 0.0f; st.bSlot = 0; st.bObject = -1;
+    st.slow = 0;
+    st.node = S.tlasRoot == SPB_REF_EMPTY ? SPB_NODE_DONE : S.tlasRoot;
+    if (st.node != SPB_NODE_DONE && any_nonfinite_inv(d))
+    {
+        st.slow = 1;
+        st.node = SPB_NODE_DONE;
+    }
+}
+
+// Pops until there is a node to visit (st.node) or the query ends (SPB_NODE_DONE).
+template <bool CULL>
+SPB_HD void trav_pop(const DScene &S, Trav &st, uint32_t *stack, float *stackT, Counters *counters)
+{
+    const float inf = u2f(0x7F800000u);
+    for (;;)
+    {
+        int base = st.blasBase >= 0 ? st.blasBase : 0;
+        if (st.sp == base)
+        {
+            if (st.blasBase < 0)
+            {
+                st.node = SPB_NODE_DONE;
+                return;
+            }
+            // leave the object: sp_scene.cpp:296-322 on its closest hit
+            if (st.lT >= 0.0f)
+            {
+                m4 model = load_m4(S.objModel + (size_t)st.object * 4);
+                f3 localHit = add3(st.o, mul3(st.d, st.lT));
+                f3 worldHit = xform(model, localHit, 1.0f);
+                float t = dot3(sub3(worldHit, st.wo), st.wd);
+                if (t < st.bT || st.bT < 0.0f)
+                {
+                    st.bT = t;
+                    st.bObject = (int32_t)st.object;
+                    st.bSlot = st.lSlot;
+                    st.bU = st.lU;
+                    st.bV = st.lV;
+                    float c2 = t * SPB_CULL_SLACK;
+                    if (t > 0.0f && c2 < st.worldCull) st.worldCull = c2;
+                }
+            }
+            st.o = st.wo;
+            st.d = st.wd;
+            st.inv = mk3(1.0f / st.wd.x, 1.0f / st.wd.y, 1.0f / st.wd.z);
+            st.tcull = st.worldCull;
+            st.blasBase = -1;
+            continue;
+        }
+        st.sp--;
+        uint32_t ref = stack[st.sp];
+        if (CULL && !(stackT[st.sp] <= st.tcull)) continue;
+        if (!(ref & SPB_REF_LEAF))
+        {
+            st.node = ref;
+            return;
+        }
+        // enter an object (sp_scene.cpp:274-276)
+        uint32_t objectIndex = ref & ~SPB_REF_LEAF;
+        v4u info = ld4u(S.objInfo + objectIndex);
+        if (counters) counters->objectTests++;
+        if (info.x == SPB_REF_EMPTY) continue;
+        m4 invModel = load_m4(S.objInv + (size_t)objectIndex * 4);
+        f3 lo = xform(invModel, st.wo, 1.0f);
+        float scaleLen;
+        f3 ld = normalize3(xform(invModel, st.wd, 0.0f), &scaleLen);
+        if (any_nonfinite_inv(ld))
+        {
+            st.slow = 1;
+            st.node = SPB_NODE_DONE;
+            return;
+        }
+        st.worldCull = st.tcull;
+        st.tcull = inf;
+        if (CULL && st.bT >= 0.0f) st.tcull = st.bT * scaleLen * SPB_CULL_SLACK;
+        st.o = lo;
+        st.d = ld;
+        st.inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+        st.object = objectIndex;
+        st.blasBase = st.sp;
+        st.lT = -1.0f;
+        st.lSlot = 0;
+        st.lU = st.lV = 0.0f;
+        st.node = info.x;
+        return;
+    }
+}
+
+// One node visit followed by the pops that find the next node.
+template <bool CULL>
+SPB_HD void trav_step(const DScene &S, Trav &st, uint32_t *stack, float *stackT, Counters *counters)
+{
+    const float inf = u2f(0x7F800000u);
+    const v4f *n = S.nodes + (size_t)st.node * 8;
+    v4f minx = ld4(n + 0), miny = ld4(n + 1), minz = ld4(n + 2);
+    v4f maxx = ld4(n + 3), maxy = ld4(n + 4), maxz = ld4(n + 5);
+    v4u refs = ld4u((const v4u *)(n + 6));
+    if (counters) counters->nodeVisits++;
+
+    float tn0, tn1, tn2, tn3;
+    bool h0 = slab_fast(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st.o, st.inv, tn0);
+    bool h1 = slab_fast(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, st.o, st.inv, tn1);
+    bool h2 = slab_fast(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, st.o, st.inv, tn2);
+    bool h3 = slab_fast(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, st.o, st.inv, tn3);
+    h0 = h0 && refs.x != SPB_REF_EMPTY;
+    h1 = h1 && refs.y != SPB_REF_EMPTY;
+    h2 = h2 && refs.z != SPB_REF_EMPTY;
+    h3 = h3 && refs.w != SPB_REF_EMPTY;
+    const bool inObject = st.blasBase >= 0;
+
+    // leaf children that passed their own box, as a 4-bit list in child order
+    unsigned pend = (h0 && (refs.x & SPB_REF_LEAF) ? 1u : 0u) | (h1 && (refs.y & SPB_REF_LEAF) ? 2u : 0u) |
+                    (h2 && (refs.z & SPB_REF_LEAF) ? 4u : 0u) | (h3 && (refs.w & SPB_REF_LEAF) ? 8u : 0u);
+    if (pend & 1u) h0 = false;
+    if (pend & 2u) h1 = false;
+    if (pend & 4u) h2 = false;
+    if (pend & 8u) h3 = false;
+
+    if (inObject)
+    {
+        // triangles at once, in child order (sp_scene.cpp:161-196); the cull distance shrinks
+        // before the internal children are looked at
+        unsigned todo = pend;
+        while (todo)
+        {
+            unsigned k = todo & 1u ? 0u : (todo & 2u ? 1u : (todo & 4u ? 2u : 3u));
+            todo &= todo - 1u;
+            uint32_t ref = k == 0 ? refs.x : (k == 1 ? refs.y : (k == 2 ? refs.z : refs.w));
+            float tn = k == 0 ? tn0 : (k == 1 ? tn1 : (k == 2 ? tn2 : tn3));
+            if (CULL && !(tn <= st.tcull)) continue;
+            uint32_t slot = ref & ~SPB_REF_LEAF;
+            const v4f *tp = S.tris + (size_t)slot * 3;
+            v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
+            if (counters) counters->triangleTests++;
+            float t, u, v;
+            if (ray_triangle_mt(st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
+            {
+                if (t > 0.0f && (t < st.lT || st.lT < 0.0f))
+                {
+                    st.lT = t;
+                    st.lSlot = slot;
+                    st.lU = u;
+                    st.lV = v;
+                    float c2 = t * SPB_CULL_SLACK;
+                    if (c2 < st.tcull) st.tcull = c2;
+                }
+            }
+        }
+        pend = 0;
+    }
+
+    if (CULL)
+    {
+        h0 = h0 && tn0 <= st.tcull;
+        h1 = h1 && tn1 <= st.tcull;
+        h2 = h2 && tn2 <= st.tcull;
+        h3 = h3 && tn3 <= st.tcull;
+    }
+    float k0 = h0 ? tn0 : inf, k1 = h1 ? tn1 : inf, k2 = h2 ? tn2 : inf, k3 = h3 ? tn3 : inf;
+    uint32_t r0 = h0 ? refs.x : SPB_REF_EMPTY, r1 = h1 ? refs.y : SPB_REF_EMPTY;
+    uint32_t r2 = h2 ? refs.z : SPB_REF_EMPTY, r3 = h3 ? refs.w : SPB_REF_EMPTY;
+    if (CULL)
+    {
+        sort2(k0, r0, k1, r1);
+        sort2(k2, r2, k3, r3);
+        sort2(k0, r0, k2, r2);
+        sort2(k1, r1, k3, r3);
+        sort2(k1, r1, k2, r2);
+    }
+    if (r3 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r3; if (CULL) stackT[st.sp] = k3; st.sp++; }
+    if (r2 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r2; if (CULL) stackT[st.sp] = k2; st.sp++; }
+    if (r1 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r1; if (CULL) stackT[st.sp] = k1; st.sp++; }
+    if (inObject)
+    {
+        if (r0 != SPB_REF_EMPTY)
+        {
+            st.node = r0;
+            return;
+        }
+    }
+    else
+    {
+        if (r0 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r0; if (CULL) stackT[st.sp] = k0; st.sp++; }
+        // objects on top, last child first, so that they pop in child order
+        if ((pend & 8u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.w; if (CULL) stackT[st.sp] = tn3; st.sp++; }
+        if ((pend & 4u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.z; if (CULL) stackT[st.sp] = tn2; st.sp++; }
+        if ((pend & 2u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.y; if (CULL) stackT[st.sp] = tn1; st.sp++; }
+        if ((pend & 1u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.x; if (CULL) stackT[st.sp] = tn0; st.sp++; }
+    }
+    trav_pop<CULL>(S, st, stack, stackT, counters);
+}
+
+SPB_HD Hit trav_result(const Trav &st)
+{
+    Hit h;
+    h.t = st.bT;
+    h.object = st.bObject;
+    h.slot = st.bSlot;
+    h.u = st.bU;
+    h.v = st.bV;
+    h.localOrigin = h.localDirection = mk3(0, 0, 0);
+    h.localT = -1.0f;
+    return h;
+}
+
+// The state machine run to completion for one ray (what each lane of k_trace does, unrolled in
+// time); hostsim uses it to check the machine against intersect_scene() and the oracle.
+template <bool CULL>
+SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT,
+                                   Counters *counters)
+{
+    Trav st;
+    trav_begin(S, o, d, st);
+    while (st.node != SPB_NODE_DONE) trav_step<CULL>(S, st, stack, stackT, counters);
+    if (st.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+    return trav_result(st);
+}
+
 struct Surface
 {
     f3 normal;       // world normal (sp_scene.cpp:309-312)
@@ -773,7 +1035,7 @@ struct PathCounters { uint32_t rays, hits, misses; };
 
 // One light path = one iteration of the sample loop of sp_PathTraceTile
 // (simd_path_tracer.cpp:216-320).  `rng` continues the caller's stream.
-template <int MATH, int ENVFILTER, bool CULL>
+template <int MATH, int ENVFILTER, bool CULL, bool STEPPED = false>
 SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, uint32_t x,
                      uint32_t y, uint32_t &rng, uint32_t bounceCount, float clampValue,
                      uint32_t *stack, float *stackT, PathCounters &pc, Counters *counters)
@@ -785,7 +1047,8 @@ SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, u
     uint32_t pathLength = 0;
     for (uint32_t bounce = 0; bounce < bounceCount; ++bounce)
     {
-        Hit hit = intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+        Hit hit = STEPPED ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, counters)
+                          : intersect_scene<CULL>(S, o, d, stack, stackT, counters);
         pc.rays++;
         f3 V = neg3(d);
         if (hit.t > 0.0f)

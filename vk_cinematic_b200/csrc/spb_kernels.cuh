@@ -91,4 +91,48 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
                               uint32_t materialSlot, const float *vertex15, float *out7,
                               cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------
+// wavefront renderer (spb_wavefront.cu)
+
+#define SPB_TRACE_THREADS 256
+// a warp keeps walking until fewer than this many of its lanes still have a node to visit,
+// then retires the finished lanes and refills them from the queue
+#ifndef SPB_REFILL_THRESHOLD
+#define SPB_REFILL_THRESHOLD 20u
+#endif
+
+// per-(pass, bounce) device counters
+enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_STRIDE };
+
+struct WaveArgs
+{
+    DScene scene;
+    const DMaterials *materials;
+    DCamera camera;
+    uint32_t x0, y0, x1, y1;   // pixel rectangle of the strip
+    uint32_t stripPixels;      // (x1 - x0) * (y1 - y0)
+    uint32_t blocksX;          // 8x4 pixel blocks per row of the strip
+    uint32_t itemsPerSample;   // blocksX * blocksY * 32 (primary work items of one sample)
+    uint32_t workItems;        // itemsPerSample * samplesThisPass
+    uint32_t samplesThisPass, firstSample, spp, bounces, frame;
+    uint32_t pathCapacity;     // paths per pass the per-path arrays are sized for
+    float clampValue;
+    v4f *rays[2];              // ray records, two float4 each: (o, rng bits) (d, path id)
+    v4f *hitRec;               // per ray slot: t, u, v, triangle slot bits
+    uint32_t *hitObj;          // per ray slot: object index
+    uint32_t *hitQ, *missQ;    // compact lists of ray slots
+    v4f *pathTerms;            // [bounce][path] two float4: (E, cosine) (W, -)
+    v4f *rad;                  // [sample in pass][pixel in strip]
+    v4f *out;                  // full image
+    uint32_t *ctr;             // this pass's counters: bounces x WCTR_STRIDE
+    unsigned long long *stats; // CTR_* slots, may be null
+    unsigned long long *tileRowCost; // may be null
+    uint32_t tileHeight;
+};
+
+void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,
+                       cudaStream_t stream);
+void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
+void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
+
 } // namespace spb

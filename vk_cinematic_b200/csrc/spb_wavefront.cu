@@ -1,0 +1,444 @@
+// spb_wavefront.cu -- the wavefront form of the integrator (the production render path).
+//
+// One frame strip is rendered in passes of S samples per pixel.  A pass is a short sequence of
+// kernels over compact device queues (DESIGN.md "Wavefront"):
+//
+//   k_trace<PRIMARY>   ray generation fused with the first traversal: persistent warps pull
+//                      (pixel, sample) items, generate the camera ray (simd_path_tracer.cpp:
+//                      216-230) and walk the BVH with the resumable state machine of
+//                      spb_core.cuh.  A lane whose ray is finished is retired (hit record +
+//                      hit/miss queue entry) and refilled from the queue once fewer than
+//                      REFILL_THRESHOLD lanes are still walking -- warp-level compaction and
+//                      regeneration, so the SIMT lanes stay full although path lengths differ.
+//   k_shade_miss       escaped rays: background material, equirect environment lookup
+//                      (sp_material_system.cpp:59-105), fold the path back to the eye
+//                      (simd_path_tracer.cpp:113-171).
+//   k_shade_hit        surface hits: normal / uv interpolation (sp_scene.cpp:196-216), BSDF terms
+//                      and hemisphere sample (math_lib.h:932-946), next ray appended to the
+//                      bounce queue (or, on the last bounce, the path folded back).
+//   k_trace            the same traversal kernel over the bounce queue.
+//   k_accumulate       total += radiance_s * (1/spp) in sample order (simd_path_tracer.cpp:321).
+//
+// All queues and per-path records live in HBM; nothing returns to the host between kernels (the
+// queue lengths are read by the next kernel from device memory).  Arithmetic per path is the
+// same sequence of operations as trace_path() in spb_core.cuh, so results are bit-identical to
+// the per-pixel kernel and to the oracle in deterministic-math mode.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
+#include "spb_kernels.cuh"
+
+namespace spb {
+
+#define SPB_FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Warp-aggregated queue append: one atomic per warp, returns this lane's slot (valid if `want`).
+__device__ __forceinline__ unsigned warp_append(uint32_t *counter, bool want)
+{
+    unsigned mask = __ballot_sync(SPB_FULL, want);
+    if (!mask) return 0;
+    unsigned leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(SPB_FULL, base, leader);
+    return base + __popc(mask & lanemask_lt());
+}
+
+__device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, uint32_t rng, uint32_t path)
+{
+    v4f a, b;
+    a.x = o.x; a.y = o.y; a.z = o.z; a.w = u2f(rng);
+    b.x = d.x; b.y = d.y; b.z = d.z; b.w = u2f(path);
+    rays[(size_t)slot * 2 + 0] = a;
+    rays[(size_t)slot * 2 + 1] = b;
+}
+
+// The rare ray whose reciprocal direction is not finite (axis-parallel): exact slab form.
+template <bool CULL>
+__device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT)
+{
+    return intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool CULL, bool STATS, bool PRIMARY>
+__global__ void __launch_bounds__(SPB_TRACE_THREADS, 2)
+k_trace(WaveArgs a, uint32_t bounce)
+{
+    const unsigned lane = lane_id();
+    uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
+    const unsigned total = PRIMARY ? a.workItems : ctr[WCTR_RAYS];
+    uint32_t *cursor = &ctr[WCTR_CURSOR];
+    v4f *rays = a.rays[bounce & 1u];
+
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    Counters cnt = {0, 0, 0, 0};
+    Trav st;
+    st.node = SPB_NODE_DONE;
+    st.slow = 0;
+    bool have = false;
+    unsigned slot = 0;
+    bool exhausted = false; // warp-uniform: the queue has been handed out completely
+
+    for (;;)
+    {
+        // ---- retire finished lanes: hit record + queue entry
+        const bool finished = have && st.node == SPB_NODE_DONE;
+        if (__any_sync(SPB_FULL, finished))
+        {
+            Hit h;
+            h.t = -1.0f;
+            if (finished)
+            {
+                if (st.slow) h = slow_intersect<CULL>(a.scene, st.wo, st.wd, stack, stackT);
+                else h = trav_result(st);
+            }
+            const bool isHit = finished && h.t > 0.0f;
+            const bool isMiss = finished && !isHit;
+            unsigned hs = warp_append(&ctr[WCTR_HITS], isHit);
+            unsigned ms = warp_append(&ctr[WCTR_MISSES], isMiss);
+            if (isHit)
+            {
+                v4f r;
+                r.x = h.t; r.y = h.u; r.z = h.v; r.w = u2f(h.slot);
+                a.hitRec[slot] = r;
+                a.hitObj[slot] = (uint32_t)h.object;
+                a.hitQ[hs] = slot;
+            }
+            if (isMiss) a.missQ[ms] = slot;
+            if (finished) have = false;
+        }
+
+        // ---- refill idle lanes from the queue (regeneration)
+        if (!exhausted)
+        {
+            unsigned need = __ballot_sync(SPB_FULL, !have);
+            if (need)
+            {
+                unsigned n = __popc(need), leader = __ffs(need) - 1, base = 0;
+                if (lane == leader) base = atomicAdd(cursor, n);
+                base = __shfl_sync(SPB_FULL, base, leader);
+                if (base + n >= total) exhausted = true;
+                unsigned idx = base + __popc(need & lanemask_lt());
+                if (!have && idx < total)
+                {
+                    f3 o, d;
+                    bool valid = true;
+                    if (PRIMARY)
+                    {
+                        // item -> (sample, 8x4 pixel block, lane in block): neighbouring lanes
+                        // trace neighbouring pixels
+                        unsigned sLocal = idx / a.itemsPerSample;
+                        unsigned r = idx - sLocal * a.itemsPerSample;
+                        unsigned block = r >> 5, l = r & 31u;
+                        unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
+                        unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
+                        valid = x < a.x1 && y < a.y1;
+                        if (valid)
+                        {
+                            uint32_t pixelIndex = x + y * a.camera.width;
+                            uint32_t rng = stream_seed(pixelIndex, a.firstSample + sLocal, a.frame);
+                            primary_ray(a.camera, x, y, rng, o, d);
+                            uint32_t path = sLocal * a.stripPixels + (y - a.y0) * (a.x1 - a.x0) + (x - a.x0);
+                            store_ray(rays, idx, o, d, rng, path);
+                        }
+                    }
+                    else
+                    {
+                        v4f ra = rays[(size_t)idx * 2 + 0], rb = rays[(size_t)idx * 2 + 1];
+                        o = mk3(ra.x, ra.y, ra.z);
+                        d = mk3(rb.x, rb.y, rb.z);
+                    }
+                    if (valid)
+                    {
+                        trav_begin(a.scene, o, d, st);
+                        have = true;
+                        slot = idx;
+                    }
+                }
+            }
+        }
+
+        // ---- walk: one node visit per iteration for every lane that still has a node
+        unsigned walking = __ballot_sync(SPB_FULL, have && st.node != SPB_NODE_DONE);
+        if (!walking)
+        {
+            if (!__any_sync(SPB_FULL, have) && exhausted) break;
+            continue; // everything fetched finished at once (e.g. rays that miss the root)
+        }
+        do
+        {
+            if (have && st.node != SPB_NODE_DONE)
+                trav_step<CULL>(a.scene, st, stack, stackT, STATS ? &cnt : nullptr);
+            walking = __ballot_sync(SPB_FULL, have && st.node != SPB_NODE_DONE);
+        } while (walking && ((unsigned)__popc(walking) >= SPB_REFILL_THRESHOLD || exhausted));
+    }
+
+    if (STATS)
+    {
+        unsigned n = __reduce_add_sync(SPB_FULL, cnt.nodeVisits), t = __reduce_add_sync(SPB_FULL, cnt.triangleTests),
+                 ob = __reduce_add_sync(SPB_FULL, cnt.objectTests);
+        if (lane == 0)
+        {
+            atomicAdd(&a.stats[CTR_NODE_VISITS], (unsigned long long)n);
+            atomicAdd(&a.stats[CTR_TRIANGLE_TESTS], (unsigned long long)t);
+            atomicAdd(&a.stats[CTR_OBJECT_TESTS], (unsigned long long)ob);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_terms(v4f *pathTerms, size_t index, const VertexTerms &vt)
+{
+    v4f a, b;
+    a.x = vt.E.x; a.y = vt.E.y; a.z = vt.E.z; a.w = vt.cosine;
+    b.x = vt.W.x; b.y = vt.W.y; b.z = vt.W.z; b.w = 0.0f;
+    pathTerms[index * 2 + 0] = a;
+    pathTerms[index * 2 + 1] = b;
+}
+
+__device__ __forceinline__ VertexTerms load_terms(const v4f *pathTerms, size_t index)
+{
+    v4f a = pathTerms[index * 2 + 0], b = pathTerms[index * 2 + 1];
+    VertexTerms vt;
+    vt.E = mk3(a.x, a.y, a.z);
+    vt.cosine = a.w;
+    vt.W = mk3(b.x, b.y, b.z);
+    return vt;
+}
+
+// radiance of the finished path: fold the last vertex, then the stored ones back to the eye
+__device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms &last, uint32_t bounce,
+                                            uint32_t path)
+{
+    f3 radiance = fold_radiance(last, mk3(0.0f, 0.0f, 0.0f), a.clampValue);
+    for (int i = (int)bounce - 1; i >= 0; --i)
+        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
+    v4f r;
+    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
+    a.rad[path] = r;
+}
+
+// rays per tile row (strip rebalancing feedback): one atomic per distinct row per warp
+__device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active)
+{
+    if (!a.tileRowCost) return;
+    unsigned pix = path % a.stripPixels;
+    unsigned row = active ? ((a.y0 + pix / (a.x1 - a.x0)) / a.tileHeight - a.y0 / a.tileHeight) : 0xFFFFFFFFu;
+    unsigned peers = __match_any_sync(__activemask(), row);
+    if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
+        atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers));
+}
+
+template <int MATH, int ENVFILTER>
+__global__ void __launch_bounds__(256)
+k_shade_miss(WaveArgs a, uint32_t bounce)
+{
+    const uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
+    const unsigned total = ctr[WCTR_MISSES];
+    const v4f *rays = a.rays[bounce & 1u];
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned rounds = (total + stride - 1) / stride;
+    for (unsigned k = 0; k < rounds; ++k)
+    {
+        unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool active = i < total;
+        uint32_t path = 0;
+        if (active)
+        {
+            unsigned slot = a.missQ[i];
+            v4f rb = rays[(size_t)slot * 2 + 1];
+            path = f2u(rb.w);
+            f3 V = neg3(mk3(rb.x, rb.y, rb.z));
+            f3 zero = mk3(0.0f, 0.0f, 0.0f);
+            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, V, 0.0f, 0.0f, &cnt);
+            finish_path(a, vt, bounce, path);
+        }
+        count_row(a, path, active);
+    }
+    if (a.stats)
+    {
+        unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
+        if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
+    }
+}
+
+template <int MATH, int ENVFILTER>
+__global__ void __launch_bounds__(256)
+k_shade_hit(WaveArgs a, uint32_t bounce)
+{
+    uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
+    const unsigned total = ctr[WCTR_HITS];
+    const v4f *rays = a.rays[bounce & 1u];
+    v4f *nextRays = a.rays[(bounce + 1u) & 1u];
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    const bool last = bounce + 1 >= a.bounces;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned rounds = (total + stride - 1) / stride;
+    for (unsigned k = 0; k < rounds; ++k)
+    {
+        unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool active = i < total;
+        f3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0);
+        uint32_t rng = 0, path = 0;
+        if (active)
+        {
+            unsigned slot = a.hitQ[i];
+            v4f ra = rays[(size_t)slot * 2 + 0], rb = rays[(size_t)slot * 2 + 1];
+            v4f hr = a.hitRec[slot];
+            f3 o = mk3(ra.x, ra.y, ra.z), d = mk3(rb.x, rb.y, rb.z);
+            rng = f2u(ra.w);
+            path = f2u(rb.w);
+            Hit hit;
+            hit.t = hr.x; hit.u = hr.y; hit.v = hr.z; hit.slot = f2u(hr.w);
+            hit.object = (int32_t)a.hitObj[slot];
+            // simd_path_tracer.cpp:268-289
+            Surface sf = resolve_hit(a.scene, hit);
+            f3 V = neg3(d);
+            f3 P = add3(o, mul3(d, hit.t));
+            f3 L = random_hemisphere<MATH>(sf.normal, rng);
+            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, sf.material, L, sf.normal, V, sf.uvx, sf.uvy, &cnt);
+            if (last)
+            {
+                finish_path(a, vt, bounce, path);
+            }
+            else
+            {
+                store_terms(a.pathTerms, (size_t)bounce * a.pathCapacity + path, vt);
+                no = add3(P, mul3(sf.normal, 0.0001f));
+                nd = L;
+            }
+        }
+        if (!last)
+        {
+            unsigned dst = warp_append(&ctr[WCTR_STRIDE + WCTR_RAYS], active);
+            if (active) store_ray(nextRays, dst, no, nd, rng, path);
+        }
+        count_row(a, path, active);
+    }
+    if (a.stats)
+    {
+        unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
+        if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
+    }
+}
+
+// total += radiance_s * (1 / spp), s in order (simd_path_tracer.cpp:216-321, 335-339)
+__global__ void __launch_bounds__(256)
+k_accumulate(WaveArgs a)
+{
+    const unsigned width = a.x1 - a.x0;
+    const float weight = 1.0f / (float)a.spp;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.stripPixels; p += gridDim.x * blockDim.x)
+    {
+        unsigned y = a.y0 + p / width, x = a.x0 + p % width;
+        size_t pixel = (size_t)x + (size_t)y * a.camera.width;
+        f3 total = mk3(0.0f, 0.0f, 0.0f);
+        if (a.firstSample != 0)
+        {
+            v4f prev = a.out[pixel];
+            total = mk3(prev.x, prev.y, prev.z);
+        }
+        for (unsigned s = 0; s < a.samplesThisPass; ++s)
+        {
+            v4f r = a.rad[(size_t)s * a.stripPixels + p];
+            total = add3(total, mul3(mk3(r.x, r.y, r.z), weight));
+        }
+        v4f o;
+        o.x = total.x; o.y = total.y; o.z = total.z; o.w = 1.0f;
+        a.out[pixel] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool CULL, bool STATS, bool PRIMARY>
+static void launch_trace_t(const WaveArgs &a, uint32_t bounce, unsigned grid, cudaStream_t stream)
+{
+    k_trace<CULL, STATS, PRIMARY><<<grid, SPB_TRACE_THREADS, 0, stream>>>(a, bounce);
+}
+
+template <bool CULL, bool STATS, bool PRIMARY>
+static unsigned trace_grid_t()
+{
+    static unsigned cached = 0;
+    if (!cached)
+    {
+        int device = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, PRIMARY>, SPB_TRACE_THREADS, 0);
+        if (perSm < 1) perSm = 1;
+        cached = (unsigned)(sms * perSm); // persistent: every CTA resident, a multiple of the SM count
+    }
+    return cached;
+}
+
+#define SPB_TRACE_DISPATCH(CALL)                                                   \
+    do {                                                                           \
+        int key = (cfg.cull ? 4 : 0) | (cfg.stats ? 2 : 0) | (primary ? 1 : 0);    \
+        switch (key) {                                                             \
+        case 0: CALL(false, false, false); break;                                  \
+        case 1: CALL(false, false, true); break;                                   \
+        case 2: CALL(false, true, false); break;                                   \
+        case 3: CALL(false, true, true); break;                                    \
+        case 4: CALL(true, false, false); break;                                   \
+        case 5: CALL(true, false, true); break;                                    \
+        case 6: CALL(true, true, false); break;                                    \
+        default: CALL(true, true, true); break;                                    \
+        }                                                                          \
+    } while (0)
+
+void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, bool primary,
+                       cudaStream_t stream)
+{
+    g_kernelLaunches++;
+#define SPB_CALL(C, S, P) launch_trace_t<C, S, P>(a, bounce, trace_grid_t<C, S, P>(), stream)
+    SPB_TRACE_DISPATCH(SPB_CALL);
+#undef SPB_CALL
+}
+
+static unsigned shade_grid()
+{
+    static unsigned cached = 0;
+    if (!cached)
+    {
+        int device = 0, sms = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cached = (unsigned)sms * 8u;
+    }
+    return cached;
+}
+
+void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, cudaStream_t stream)
+{
+    g_kernelLaunches += 2;
+    unsigned grid = shade_grid();
+    int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
+    switch (key)
+    {
+    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
+    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    }
+}
+
+void launch_wave_accumulate(const WaveArgs &a, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    k_accumulate<<<shade_grid(), 256, 0, stream>>>(a);
+}
+
+} // namespace spb

@@ -175,12 +175,14 @@ class sp_Context(C.Structure):
 
 SP_B200_ENV_NEAREST, SP_B200_ENV_BILINEAR = 0, 1
 SP_B200_MATH_F64_ROUNDED, SP_B200_MATH_FAST_F32 = 0, 1
+SP_B200_RENDER_WAVEFRONT, SP_B200_RENDER_PER_PIXEL = 0, 1
 
 
 class sp_b200_Params(C.Structure):
     _fields_ = [("samplesPerPixel", u32), ("bounceCount", u32), ("radianceClamp", f32),
                 ("envFilter", u32), ("mathMode", u32), ("cullByDistance", u32),
-                ("tileWidth", u32), ("tileHeight", u32)]
+                ("tileWidth", u32), ("tileHeight", u32), ("renderMode", u32),
+                ("samplesPerPass", u32)]
 
 
 class sp_b200_Stats(C.Structure):
