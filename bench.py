@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--math", type=int, default=0, help="0: double-rounded libm stand-ins (parity mode), 1: CUDA f32")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
+    ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -266,6 +267,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     assert sp.lib.sp_b200_Init(local) == 0
     stream = torch.cuda.current_stream()
@@ -366,6 +368,15 @@ def main():
                 host_image.copy_(image, non_blocking=True)
                 torch.cuda.synchronize()
         return m
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": float(np.mean(kernel_ms)),
+                              "rays_per_step": rays / args.steps, "launches": int(launches), "strips": [list(map(int, b)) for b in bounds]}), flush=True)
+        r.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     scene_bytes = int(env_pinned.numel() * 4) + int(sp.lib.sp_b200_SceneDeviceBytes(r.scene)) + 2048
     for _ in range(2):
         e2e_step(frame)

@@ -385,7 +385,9 @@ def test_c3_full_size_properties(params):
     for (b, e) in ((0, 576), (576, 1280), (1280, 2160)):
         mm, cost = r.render_rows(b, e, frame=0, want_cost=True)
         total += mm
-        assert int(cost.sum()) == int(mm[sp.sp_Metric_RaysTraced])
+        # cost units: 1 per escaped ray, 6 per surface hit (wavefront) / rays (per-pixel kernel)
+        assert int(cost.sum()) in (int(mm[sp.sp_Metric_RaysTraced]),
+                                   int(mm[sp.sp_Metric_RayMissCount]) + 6 * int(mm[sp.sp_Metric_RayHitCount]))
     assert same_bits(r.image, full) and np.array_equal(total[1:5], m[1:5])
     chk = ora.load_port_dm().scene().load_workload(wl)
     cimg = np.zeros_like(full)
@@ -424,7 +426,7 @@ def test_wavefront_pass_split_and_stats(gpu_sp):
     st = sp.last_stats()
     sp.lib.sp_b200_EnableStats(0)
     assert int(st.rays) == int(ref_m[2]) and st.nodeVisits > st.rays and st.triangleTests > 0
-    assert int(cost.sum()) == int(ref_m[2]) and len(cost) == 3
+    assert int(cost.sum()) == int(ref_m[4]) + 6 * int(ref_m[3]) and len(cost) == 3
     assert same_bits(r.image, ref_img)
     sp.set_params(samplesPerPixel=1, bounceCount=3, samplesPerPass=0)
     r.close()

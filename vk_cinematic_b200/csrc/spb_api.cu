@@ -114,7 +114,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitObj, wHitQ, wMissQ, wTerms, wRad, wCtr;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -382,7 +382,6 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     L.wRays[0].ensure((size_t)capacity * 32);
     L.wRays[1].ensure((size_t)capacity * 32);
     L.wHitRec.ensure((size_t)capacity * 16);
-    L.wHitObj.ensure((size_t)capacity * 4);
     L.wHitQ.ensure((size_t)capacity * 4);
     L.wMissQ.ensure((size_t)capacity * 4);
     L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
@@ -407,7 +406,6 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     a.rays[0] = (v4f *)L.wRays[0].ptr;
     a.rays[1] = (v4f *)L.wRays[1].ptr;
     a.hitRec = (v4f *)L.wHitRec.ptr;
-    a.hitObj = (uint32_t *)L.wHitObj.ptr;
     a.hitQ = (uint32_t *)L.wHitQ.ptr;
     a.missQ = (uint32_t *)L.wMissQ.ptr;
     a.pathTerms = (v4f *)L.wTerms.ptr;
@@ -471,7 +469,7 @@ extern "C" void sp_b200_Shutdown(void)
     L.emptyScene.reset();
     L.image.release(); L.counters.release(); L.materials.release();
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
-    L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release(); L.wHitObj.release();
+    L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
     if (L.initialized)
     {

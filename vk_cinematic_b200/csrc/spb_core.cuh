@@ -47,6 +47,29 @@ SPB_HD v4u ld4u(const v4u *p)
     return *p;
 #endif
 }
+// Pull a line towards L1 ahead of use (a popped node is fetched by 32 lanes at once and the
+// slowest lane sets the pace, so the expected miss is issued as soon as the address is known).
+SPB_HD void prefetch_l1(const void *p)
+{
+#if defined(__CUDA_ARCH__) && defined(SPB_PREFETCH)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+// 32-byte load through the read-only path (LDG.E.256 on sm_100a): half as many L1 wavefronts per
+// node as 16-byte loads when every lane of a warp reads a different node.
+SPB_HD void ld8(const v4f *p, v4f &a, v4f &b)
+{
+#if defined(__CUDA_ARCH__) && !defined(SPB_NO_LD256)
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+#else
+    a = ld4(p);
+    b = ld4(p + 1);
+#endif
+}
 SPB_HD uint32_t f2u(float f)
 {
 #if defined(__CUDA_ARCH__)
@@ -550,145 +573,160 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
 
 // ------------------------------------------------------------------------------------------
 // Resumable traversal: the same closest-hit query as intersect_scene(), written as a state
-// machine so that a warp can advance 32 independent rays one node visit at a time, retire the
-// finished ones and refill their lanes (spb_wavefront.cu).  One loop body serves both levels:
-// in the TLAS a "leaf" child is an object and is pushed on the stack (objects pop in child order
-// before the internal children, which pop near to far -- the order intersect_scene() uses);
-// inside an object a leaf child is a triangle and is tested at once, in child order, before the
-// internal children are culled against the shortened distance.  Only the fast slab form is used
-// here: a ray (world or object space) whose reciprocal direction is not finite sets `slow` and
-// the caller finishes it with intersect_scene(), which has the exact form.
+// machine so that a warp can advance 32 independent rays one step at a time, retire the
+// finished ones and refill their lanes (spb_wavefront.cu).  A step is either a NODE step (fetch
+// a 4-wide node, slab-test its children, push the children that pass, nearest on top) or a LEAF
+// step (inside an object: Moller-Trumbore on one triangle whose own box passed; in the TLAS:
+// enter one object).  Leaves go through the stack like nodes, so a warp can run the two kinds of
+// step separately with most of its lanes active; entries are visited near to far and skipped when
+// their entry distance exceeds the closest hit so far.  The closest hit is the minimum over the
+// same set of (own box passes) && (Moller-Trumbore accepts) && (t > 0) triangles as
+// intersect_scene(); only the winner among exactly equal t can differ (order of visits).
+// Only the fast slab form is used here: a ray (world or object space) whose reciprocal direction
+// is not finite sets `slow` and the caller finishes it with intersect_scene().
 #define SPB_NODE_DONE 0xFFFFFFFEu
+// the walk inside an object has ended: trav_exit() must run before anything else (kept as a
+// separate step so that a warp can run it for several lanes at once)
+#define SPB_NODE_EXIT 0xFFFFFFFDu
 
+// One stack entry: reference and entry distance together (one 8-byte local load per pop).
+struct TravEntry { uint32_t ref; float tnear; };
+
+// Hot state: what every NODE / LEAF step touches.
 struct Trav
 {
     f3 o, d, inv;     // ray in the current space (world in the TLAS, object space inside an object)
-    f3 wo, wd;        // the world ray
     float tcull;      // cull distance in the current space
-    float worldCull;  // TLAS cull distance, parked while inside an object
-    uint32_t node;    // node to visit next; SPB_NODE_DONE when the query is finished
+    uint32_t cur;     // entry to process next: node index, SPB_REF_LEAF | slot, SPB_NODE_EXIT, SPB_NODE_DONE
     int sp;           // stack pointer
     int blasBase;     // -1 in the TLAS, else the stack pointer at object entry
-    uint32_t object;  // object being traversed
-    float lT, lU, lV; // closest hit inside the current object (object space)
+    float lT;         // closest hit inside the current object (object space)
     uint32_t lSlot;
-    float bT, bU, bV; // closest hit so far (world t)
+};
+
+// Cold state: touched only when an object is entered or left and when the ray is retired (the
+// trace kernel keeps it in shared memory, off the register file).
+struct TravCold
+{
+    float worldCull;  // TLAS cull distance, parked while inside an object
+    uint32_t object;  // object being traversed
+    float bT;         // closest hit so far (world t)
     uint32_t bSlot;
     int32_t bObject;
     uint32_t slow;
 };
 
-SPB_HD void trav_begin(const DScene &S, f3 o, f3 d, Trav &st)
+SPB_HD bool trav_is_node(const Trav &st) { return (st.cur & SPB_REF_LEAF) == 0; } // DONE / EXIT have the bit set
+SPB_HD bool trav_is_walking(const Trav &st) { return st.cur < SPB_NODE_EXIT; }
+
+SPB_HD void trav_begin(const DScene &S, f3 o, f3 d, Trav &st, TravCold &c)
 {
-    st.wo = o;
-    st.wd = d;
     st.o = o;
     st.d = d;
     st.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     st.tcull = u2f(0x7F800000u);
-    st.worldCull = st.tcull;
     st.sp = 0;
     st.blasBase = -1;
-    st.object = 0;
-    st.lT = -1.0f; st.lU = st.lV = 0.0f; st.lSlot = 0;
-    st.bT = -1.0f; st.bU = st.bV = 0.0f; st.bSlot = 0; st.bObject = -1;
-    st.slow = 0;
-    st.node = S.tlasRoot == SPB_REF_EMPTY ? SPB_NODE_DONE : S.tlasRoot;
-    if (st.node != SPB_NODE_DONE && any_nonfinite_inv(d))
+    st.lT = -1.0f; st.lSlot = 0;
+    c.worldCull = st.tcull;
+    c.object = 0;
+    c.bT = -1.0f; c.bSlot = 0; c.bObject = -1;
+    c.slow = 0;
+    st.cur = S.tlasRoot == SPB_REF_EMPTY ? SPB_NODE_DONE : S.tlasRoot;
+    if (st.cur != SPB_NODE_DONE && any_nonfinite_inv(d))
     {
-        st.slow = 1;
-        st.node = SPB_NODE_DONE;
+        c.slow = 1;
+        st.cur = SPB_NODE_DONE;
     }
 }
 
-// Pops until there is a node to visit (st.node) or the query ends (SPB_NODE_DONE).
-template <bool CULL>
-SPB_HD void trav_pop(const DScene &S, Trav &st, uint32_t *stack, float *stackT, Counters *counters)
+// `ray` points at the world ray record (two float4: origin, direction); it is only read when an
+// object is entered or left, so the world ray does not occupy registers during the walk.
+SPB_HD void trav_world_ray(const v4f *ray, f3 &wo, f3 &wd)
 {
-    const float inf = u2f(0x7F800000u);
+    v4f a = ray[0], b = ray[1];
+    wo = mk3(a.x, a.y, a.z);
+    wd = mk3(b.x, b.y, b.z);
+}
+
+// Pops until there is an entry to process (st.cur), the walk inside an object ends
+// (SPB_NODE_EXIT) or the query ends (SPB_NODE_DONE).
+template <bool CULL>
+SPB_HD void trav_pop(Trav &st, const TravEntry *stack)
+{
     for (;;)
     {
         int base = st.blasBase >= 0 ? st.blasBase : 0;
         if (st.sp == base)
         {
-            if (st.blasBase < 0)
-            {
-                st.node = SPB_NODE_DONE;
-                return;
-            }
-            // leave the object: sp_scene.cpp:296-322 on its closest hit
-            if (st.lT >= 0.0f)
-            {
-                m4 model = load_m4(S.objModel + (size_t)st.object * 4);
-                f3 localHit = add3(st.o, mul3(st.d, st.lT));
-                f3 worldHit = xform(model, localHit, 1.0f);
-                float t = dot3(sub3(worldHit, st.wo), st.wd);
-                if (t < st.bT || st.bT < 0.0f)
-                {
-                    st.bT = t;
-                    st.bObject = (int32_t)st.object;
-                    st.bSlot = st.lSlot;
-                    st.bU = st.lU;
-                    st.bV = st.lV;
-                    float c2 = t * SPB_CULL_SLACK;
-                    if (t > 0.0f && c2 < st.worldCull) st.worldCull = c2;
-                }
-            }
-            st.o = st.wo;
-            st.d = st.wd;
-            st.inv = mk3(1.0f / st.wd.x, 1.0f / st.wd.y, 1.0f / st.wd.z);
-            st.tcull = st.worldCull;
-            st.blasBase = -1;
-            continue;
+            st.cur = st.blasBase < 0 ? SPB_NODE_DONE : SPB_NODE_EXIT;
+            return;
         }
         st.sp--;
-        uint32_t ref = stack[st.sp];
-        if (CULL && !(stackT[st.sp] <= st.tcull)) continue;
-        if (!(ref & SPB_REF_LEAF))
-        {
-            st.node = ref;
-            return;
-        }
-        // enter an object (sp_scene.cpp:274-276)
-        uint32_t objectIndex = ref & ~SPB_REF_LEAF;
-        v4u info = ld4u(S.objInfo + objectIndex);
-        if (counters) counters->objectTests++;
-        if (info.x == SPB_REF_EMPTY) continue;
-        m4 invModel = load_m4(S.objInv + (size_t)objectIndex * 4);
-        f3 lo = xform(invModel, st.wo, 1.0f);
-        float scaleLen;
-        f3 ld = normalize3(xform(invModel, st.wd, 0.0f), &scaleLen);
-        if (any_nonfinite_inv(ld))
-        {
-            st.slow = 1;
-            st.node = SPB_NODE_DONE;
-            return;
-        }
-        st.worldCull = st.tcull;
-        st.tcull = inf;
-        if (CULL && st.bT >= 0.0f) st.tcull = st.bT * scaleLen * SPB_CULL_SLACK;
-        st.o = lo;
-        st.d = ld;
-        st.inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-        st.object = objectIndex;
-        st.blasBase = st.sp;
-        st.lT = -1.0f;
-        st.lSlot = 0;
-        st.lU = st.lV = 0.0f;
-        st.node = info.x;
+        TravEntry e = stack[st.sp];
+        if (CULL && !(e.tnear <= st.tcull)) continue;
+        st.cur = e.ref;
         return;
     }
 }
 
-// One node visit followed by the pops that find the next node.
+// EXIT step (st.cur == SPB_NODE_EXIT): leave the object -- sp_scene.cpp:296-322 on its closest
+// hit -- and go on with the TLAS entries below.
 template <bool CULL>
-SPB_HD void trav_step(const DScene &S, Trav &st, uint32_t *stack, float *stackT, Counters *counters)
+SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, const TravEntry *stack)
+{
+    f3 wo, wd;
+    trav_world_ray(ray, wo, wd);
+    float worldCull = c.worldCull;
+    if (st.lT >= 0.0f)
+    {
+        m4 model = load_m4(S.objModel + (size_t)c.object * 4);
+        f3 localHit = add3(st.o, mul3(st.d, st.lT));
+        f3 worldHit = xform(model, localHit, 1.0f);
+        float t = dot3(sub3(worldHit, wo), wd);
+        float bT = c.bT;
+        if (t < bT || bT < 0.0f)
+        {
+            c.bT = t;
+            c.bObject = (int32_t)c.object;
+            c.bSlot = st.lSlot;
+            float c2 = t * SPB_CULL_SLACK;
+            if (t > 0.0f && c2 < worldCull) worldCull = c2;
+        }
+    }
+    st.o = wo;
+    st.d = wd;
+    st.inv = mk3(1.0f / wd.x, 1.0f / wd.y, 1.0f / wd.z);
+    st.tcull = worldCull;
+    st.blasBase = -1;
+    trav_pop<CULL>(st, stack);
+}
+
+SPB_HD void trav_push(Trav &st, TravEntry *stack, uint32_t ref, float tnear)
+{
+    if (ref != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE)
+    {
+        TravEntry e;
+        e.ref = ref;
+        e.tnear = tnear;
+        stack[st.sp] = e;
+        st.sp++;
+    }
+}
+
+// NODE step: st.cur is a node index.
+template <bool CULL>
+SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *counters)
 {
     const float inf = u2f(0x7F800000u);
-    const v4f *n = S.nodes + (size_t)st.node * 8;
-    v4f minx = ld4(n + 0), miny = ld4(n + 1), minz = ld4(n + 2);
-    v4f maxx = ld4(n + 3), maxy = ld4(n + 4), maxz = ld4(n + 5);
-    v4u refs = ld4u((const v4u *)(n + 6));
+    const v4f *n = S.nodes + (size_t)st.cur * 8;
+    v4f minx, miny, minz, maxx, maxy, maxz, refsf, meta;
+    ld8(n + 0, minx, miny);
+    ld8(n + 2, minz, maxx);
+    ld8(n + 4, maxy, maxz);
+    ld8(n + 6, refsf, meta);
+    v4u refs;
+    refs.x = f2u(refsf.x); refs.y = f2u(refsf.y); refs.z = f2u(refsf.z); refs.w = f2u(refsf.w);
     if (counters) counters->nodeVisits++;
 
     float tn0, tn1, tn2, tn3;
@@ -700,49 +738,6 @@ SPB_HD void trav_step(const DScene &S, Trav &st, uint32_t *stack, float *stackT,
     h1 = h1 && refs.y != SPB_REF_EMPTY;
     h2 = h2 && refs.z != SPB_REF_EMPTY;
     h3 = h3 && refs.w != SPB_REF_EMPTY;
-    const bool inObject = st.blasBase >= 0;
-
-    // leaf children that passed their own box, as a 4-bit list in child order
-    unsigned pend = (h0 && (refs.x & SPB_REF_LEAF) ? 1u : 0u) | (h1 && (refs.y & SPB_REF_LEAF) ? 2u : 0u) |
-                    (h2 && (refs.z & SPB_REF_LEAF) ? 4u : 0u) | (h3 && (refs.w & SPB_REF_LEAF) ? 8u : 0u);
-    if (pend & 1u) h0 = false;
-    if (pend & 2u) h1 = false;
-    if (pend & 4u) h2 = false;
-    if (pend & 8u) h3 = false;
-
-    if (inObject)
-    {
-        // triangles at once, in child order (sp_scene.cpp:161-196); the cull distance shrinks
-        // before the internal children are looked at
-        unsigned todo = pend;
-        while (todo)
-        {
-            unsigned k = todo & 1u ? 0u : (todo & 2u ? 1u : (todo & 4u ? 2u : 3u));
-            todo &= todo - 1u;
-            uint32_t ref = k == 0 ? refs.x : (k == 1 ? refs.y : (k == 2 ? refs.z : refs.w));
-            float tn = k == 0 ? tn0 : (k == 1 ? tn1 : (k == 2 ? tn2 : tn3));
-            if (CULL && !(tn <= st.tcull)) continue;
-            uint32_t slot = ref & ~SPB_REF_LEAF;
-            const v4f *tp = S.tris + (size_t)slot * 3;
-            v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
-            if (counters) counters->triangleTests++;
-            float t, u, v;
-            if (ray_triangle_mt(st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
-            {
-                if (t > 0.0f && (t < st.lT || st.lT < 0.0f))
-                {
-                    st.lT = t;
-                    st.lSlot = slot;
-                    st.lU = u;
-                    st.lV = v;
-                    float c2 = t * SPB_CULL_SLACK;
-                    if (c2 < st.tcull) st.tcull = c2;
-                }
-            }
-        }
-        pend = 0;
-    }
-
     if (CULL)
     {
         h0 = h0 && tn0 <= st.tcull;
@@ -761,37 +756,109 @@ SPB_HD void trav_step(const DScene &S, Trav &st, uint32_t *stack, float *stackT,
         sort2(k1, r1, k3, r3);
         sort2(k1, r1, k2, r2);
     }
-    if (r3 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r3; if (CULL) stackT[st.sp] = k3; st.sp++; }
-    if (r2 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r2; if (CULL) stackT[st.sp] = k2; st.sp++; }
-    if (r1 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r1; if (CULL) stackT[st.sp] = k1; st.sp++; }
-    if (inObject)
+    else
     {
-        if (r0 != SPB_REF_EMPTY)
+        // no distance order: keep child order, valid entries first
+        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
+        if (r1 == SPB_REF_EMPTY) { r1 = r2; r2 = SPB_REF_EMPTY; }
+        if (r2 == SPB_REF_EMPTY) { r2 = r3; r3 = SPB_REF_EMPTY; }
+        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
+        if (r1 == SPB_REF_EMPTY) { r1 = r2; r2 = SPB_REF_EMPTY; }
+        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
+    }
+    trav_push(st, stack, r3, k3);
+    trav_push(st, stack, r2, k2);
+    trav_push(st, stack, r1, k1);
+    if (r0 != SPB_REF_EMPTY)
+    {
+        st.cur = r0;
+        return;
+    }
+    trav_pop<CULL>(st, stack);
+}
+
+// LEAF step: st.cur is SPB_REF_LEAF | slot.
+template <bool CULL>
+SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, TravEntry *stack,
+                      Counters *counters)
+{
+    const float inf = u2f(0x7F800000u);
+    uint32_t index = st.cur & ~SPB_REF_LEAF;
+    if (st.blasBase >= 0)
+    {
+        // a triangle whose own box the ray passes (sp_scene.cpp:161-196)
+        const v4f *tp = S.tris + (size_t)index * 3;
+        v4f a = ld4(tp + 0), b = ld4(tp + 1), cc = ld4(tp + 2);
+        if (counters) counters->triangleTests++;
+        float t, u, v;
+        if (ray_triangle_mt(st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(cc.x, cc.y, cc.z), t, u, v))
         {
-            st.node = r0;
-            return;
+            if (t > 0.0f && (t < st.lT || st.lT < 0.0f))
+            {
+                st.lT = t;
+                st.lSlot = index;
+                float c2 = t * SPB_CULL_SLACK;
+                if (c2 < st.tcull) st.tcull = c2;
+            }
         }
     }
     else
     {
-        if (r0 != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE) { stack[st.sp] = r0; if (CULL) stackT[st.sp] = k0; st.sp++; }
-        // objects on top, last child first, so that they pop in child order
-        if ((pend & 8u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.w; if (CULL) stackT[st.sp] = tn3; st.sp++; }
-        if ((pend & 4u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.z; if (CULL) stackT[st.sp] = tn2; st.sp++; }
-        if ((pend & 2u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.y; if (CULL) stackT[st.sp] = tn1; st.sp++; }
-        if ((pend & 1u) && st.sp < SPB_STACK_SIZE) { stack[st.sp] = refs.x; if (CULL) stackT[st.sp] = tn0; st.sp++; }
+        // enter an object (sp_scene.cpp:274-276)
+        v4u info = ld4u(S.objInfo + index);
+        if (counters) counters->objectTests++;
+        if (info.x != SPB_REF_EMPTY)
+        {
+            m4 invModel = load_m4(S.objInv + (size_t)index * 4);
+            f3 wo, wd;
+            trav_world_ray(ray, wo, wd);
+            f3 lo = xform(invModel, wo, 1.0f);
+            float scaleLen;
+            f3 ld = normalize3(xform(invModel, wd, 0.0f), &scaleLen);
+            if (any_nonfinite_inv(ld))
+            {
+                c.slow = 1;
+                st.cur = SPB_NODE_DONE;
+                return;
+            }
+            c.worldCull = st.tcull;
+            st.tcull = inf;
+            float bT = c.bT;
+            if (CULL && bT >= 0.0f) st.tcull = bT * scaleLen * SPB_CULL_SLACK;
+            st.o = lo;
+            st.d = ld;
+            st.inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+            c.object = index;
+            st.blasBase = st.sp;
+            st.lT = -1.0f;
+            st.lSlot = 0;
+            st.cur = info.x;
+            return;
+        }
     }
-    trav_pop<CULL>(S, st, stack, stackT, counters);
+    trav_pop<CULL>(st, stack);
 }
 
-SPB_HD Hit trav_result(const Trav &st)
+// Barycentrics of the winning triangle, recomputed from the same inputs with the same code the
+// traversal ran (so the same bits): the traversal itself carries only (t, slot, object).
+SPB_HD void hit_barycentrics(const DScene &S, f3 o, f3 d, Hit &hit)
+{
+    m4 invModel = load_m4(S.objInv + (size_t)hit.object * 4);
+    f3 lo = xform(invModel, o, 1.0f);
+    f3 ld = normalize3(xform(invModel, d, 0.0f));
+    const v4f *tp = S.tris + (size_t)hit.slot * 3;
+    v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
+    float t;
+    ray_triangle_mt(lo, ld, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, hit.u, hit.v);
+}
+
+SPB_HD Hit trav_result(const TravCold &c)
 {
     Hit h;
-    h.t = st.bT;
-    h.object = st.bObject;
-    h.slot = st.bSlot;
-    h.u = st.bU;
-    h.v = st.bV;
+    h.t = c.bT;
+    h.object = c.bObject;
+    h.slot = c.bSlot;
+    h.u = h.v = 0.0f;
     h.localOrigin = h.localDirection = mk3(0, 0, 0);
     h.localT = -1.0f;
     return h;
@@ -804,10 +871,22 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
                                    Counters *counters)
 {
     Trav st;
-    trav_begin(S, o, d, st);
-    while (st.node != SPB_NODE_DONE) trav_step<CULL>(S, st, stack, stackT, counters);
-    if (st.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
-    return trav_result(st);
+    TravCold cold;
+    TravEntry entries[SPB_STACK_SIZE];
+    trav_begin(S, o, d, st, cold);
+    v4f ray[2];
+    ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
+    ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
+    while (st.cur != SPB_NODE_DONE)
+    {
+        if (st.cur == SPB_NODE_EXIT) trav_exit<CULL>(S, st, cold, ray, entries);
+        else if (trav_is_node(st)) trav_node<CULL>(S, st, entries, counters);
+        else trav_leaf<CULL>(S, st, cold, ray, entries, counters);
+    }
+    if (cold.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+    Hit h = trav_result(cold);
+    if (h.object >= 0) hit_barycentrics(S, o, d, h);
+    return h;
 }
 
 struct Surface

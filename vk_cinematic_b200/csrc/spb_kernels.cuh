@@ -94,14 +94,24 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
 // ---------------------------------------------------------------------------------------------
 // wavefront renderer (spb_wavefront.cu)
 
-#define SPB_TRACE_THREADS 256
+#ifndef SPB_TRACE_THREADS
+#define SPB_TRACE_THREADS 128
+#endif
+#ifndef SPB_TRACE_MIN_BLOCKS
+#define SPB_TRACE_MIN_BLOCKS 5
+#endif
+// tile-row cost units (sp_b200_RenderRows tileRowCost): per escaped ray / per surface hit
+#define SPB_COST_MISS 1u
+#define SPB_COST_HIT 6u
 // a warp keeps walking until fewer than this many of its lanes still have a node to visit,
 // then retires the finished lanes and refills them from the queue
 #ifndef SPB_REFILL_THRESHOLD
-#define SPB_REFILL_THRESHOLD 20u
+#define SPB_REFILL_THRESHOLD 12u
 #endif
 
 // per-(pass, bounce) device counters
+// RAYS: rays queued for this bounce; HITS / MISSES: lengths of the hit / miss queues;
+// CURSOR: work hand-out position of the trace kernel
 enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_STRIDE };
 
 struct WaveArgs
@@ -118,8 +128,7 @@ struct WaveArgs
     uint32_t pathCapacity;     // paths per pass the per-path arrays are sized for
     float clampValue;
     v4f *rays[2];              // ray records, two float4 each: (o, rng bits) (d, path id)
-    v4f *hitRec;               // per ray slot: t, u, v, triangle slot bits
-    uint32_t *hitObj;          // per ray slot: object index
+    v4f *hitRec;               // per ray slot: t, triangle slot bits, object index bits, -
     uint32_t *hitQ, *missQ;    // compact lists of ray slots
     v4f *pathTerms;            // [bounce][path] two float4: (E, cosine) (W, -)
     v4f *rad;                  // [sample in pass][pixel in strip]

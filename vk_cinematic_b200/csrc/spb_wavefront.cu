@@ -62,14 +62,22 @@ __device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, 
 
 // The rare ray whose reciprocal direction is not finite (axis-parallel): exact slab form.
 template <bool CULL>
-__device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT)
+__device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 {
-    return intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    Hit h = intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+    return h;
 }
 
 // ---------------------------------------------------------------------------------------------
+// Traversal kernel.  Persistent warps; every lane owns one ray at a time.  Each iteration of the
+// inner loop the warp runs ONE kind of step -- node visits or leaf work (triangle tests / object
+// entry) -- whichever more of its lanes are waiting for, so both code paths execute with most
+// lanes active.  When fewer than SPB_REFILL_THRESHOLD lanes still have work, finished lanes are
+// retired (hit record, hit/miss queue) and refilled from the ray queue.
 template <bool CULL, bool STATS, bool PRIMARY>
-__global__ void __launch_bounds__(SPB_TRACE_THREADS, 2)
+__global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(WaveArgs a, uint32_t bounce)
 {
     const unsigned lane = lane_id();
@@ -78,28 +86,41 @@ k_trace(WaveArgs a, uint32_t bounce)
     uint32_t *cursor = &ctr[WCTR_CURSOR];
     v4f *rays = a.rays[bounce & 1u];
 
-    uint32_t stack[SPB_STACK_SIZE];
-    float stackT[SPB_STACK_SIZE];
+
+    // per-lane stack in local memory; state that is touched only when an object is entered or
+    // left, or the ray retired, lives in shared memory (6 + 1 words per lane, conflict-free stride)
+    TravEntry stack[SPB_STACK_SIZE];
+    __shared__ TravCold coldAll[SPB_TRACE_THREADS];
+    __shared__ unsigned slotAll[SPB_TRACE_THREADS];
+    TravCold &cold = coldAll[threadIdx.x];
+    unsigned &slot = slotAll[threadIdx.x];
     Counters cnt = {0, 0, 0, 0};
     Trav st;
-    st.node = SPB_NODE_DONE;
-    st.slow = 0;
+    st.cur = SPB_NODE_DONE;
+    cold.slow = 0;
+    slot = 0;
     bool have = false;
-    unsigned slot = 0;
     bool exhausted = false; // warp-uniform: the queue has been handed out completely
 
     for (;;)
     {
         // ---- retire finished lanes: hit record + queue entry
-        const bool finished = have && st.node == SPB_NODE_DONE;
+        const bool finished = have && st.cur == SPB_NODE_DONE;
         if (__any_sync(SPB_FULL, finished))
         {
             Hit h;
             h.t = -1.0f;
+            h.slot = 0;
+            h.object = -1;
             if (finished)
             {
-                if (st.slow) h = slow_intersect<CULL>(a.scene, st.wo, st.wd, stack, stackT);
-                else h = trav_result(st);
+                if (cold.slow)
+                {
+                    f3 wo, wd;
+                    trav_world_ray(rays + (size_t)slot * 2, wo, wd);
+                    h = slow_intersect<CULL>(a.scene, wo, wd);
+                }
+                else h = trav_result(cold);
             }
             const bool isHit = finished && h.t > 0.0f;
             const bool isMiss = finished && !isHit;
@@ -107,11 +128,11 @@ k_trace(WaveArgs a, uint32_t bounce)
             unsigned ms = warp_append(&ctr[WCTR_MISSES], isMiss);
             if (isHit)
             {
+                unsigned mySlot = slot;
                 v4f r;
-                r.x = h.t; r.y = h.u; r.z = h.v; r.w = u2f(h.slot);
-                a.hitRec[slot] = r;
-                a.hitObj[slot] = (uint32_t)h.object;
-                a.hitQ[hs] = slot;
+                r.x = h.t; r.y = u2f(h.slot); r.z = u2f((uint32_t)h.object); r.w = 0.0f;
+                a.hitRec[mySlot] = r;
+                a.hitQ[hs] = mySlot;
             }
             if (isMiss) a.missQ[ms] = slot;
             if (finished) have = false;
@@ -153,13 +174,11 @@ k_trace(WaveArgs a, uint32_t bounce)
                     }
                     else
                     {
-                        v4f ra = rays[(size_t)idx * 2 + 0], rb = rays[(size_t)idx * 2 + 1];
-                        o = mk3(ra.x, ra.y, ra.z);
-                        d = mk3(rb.x, rb.y, rb.z);
+                        trav_world_ray(rays + (size_t)idx * 2, o, d);
                     }
                     if (valid)
                     {
-                        trav_begin(a.scene, o, d, st);
+                        trav_begin(a.scene, o, d, st, cold);
                         have = true;
                         slot = idx;
                     }
@@ -167,20 +186,37 @@ k_trace(WaveArgs a, uint32_t bounce)
             }
         }
 
-        // ---- walk: one node visit per iteration for every lane that still has a node
-        unsigned walking = __ballot_sync(SPB_FULL, have && st.node != SPB_NODE_DONE);
+        // ---- walk
+        // lanes whose walk inside an object has ended leave it together (the exit arithmetic
+        // would otherwise run for one or two lanes at a time)
+        if (have && st.cur == SPB_NODE_EXIT)
+            trav_exit<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack);
+        unsigned walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         if (!walking)
         {
             if (!__any_sync(SPB_FULL, have) && exhausted) break;
-            continue; // everything fetched finished at once (e.g. rays that miss the root)
+            continue; // everything in flight finished at once
         }
         do
         {
-            if (have && st.node != SPB_NODE_DONE)
-                trav_step<CULL>(a.scene, st, stack, stackT, STATS ? &cnt : nullptr);
-            walking = __ballot_sync(SPB_FULL, have && st.node != SPB_NODE_DONE);
+            const bool live = have && trav_is_walking(st);
+            const bool wantNode = live && trav_is_node(st);
+            const bool wantLeaf = live && !wantNode;
+            unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
+            unsigned leafMask = walking & ~nodeMask;
+            if (__popc(nodeMask) >= __popc(leafMask))
+            {
+                if (wantNode) trav_node<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr);
+            }
+            else
+            {
+                if (wantLeaf)
+                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+            }
+            walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         } while (walking && ((unsigned)__popc(walking) >= SPB_REFILL_THRESHOLD || exhausted));
     }
+
 
     if (STATS)
     {
@@ -227,15 +263,17 @@ __device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms
     a.rad[path] = r;
 }
 
-// rays per tile row (strip rebalancing feedback): one atomic per distinct row per warp
-__device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active)
+// cost per tile row (strip rebalancing feedback): SPB_COST_MISS units per escaped ray,
+// SPB_COST_HIT per surface hit (a hit costs a shading step and, unless it is the last bounce, a
+// far more expensive incoherent traversal); one atomic per distinct row per warp
+__device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active, unsigned weight)
 {
     if (!a.tileRowCost) return;
     unsigned pix = path % a.stripPixels;
     unsigned row = active ? ((a.y0 + pix / (a.x1 - a.x0)) / a.tileHeight - a.y0 / a.tileHeight) : 0xFFFFFFFFu;
-    unsigned peers = __match_any_sync(__activemask(), row);
+    unsigned peers = __match_any_sync(SPB_FULL, row);
     if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
-        atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers));
+        atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
 }
 
 template <int MATH, int ENVFILTER>
@@ -264,7 +302,7 @@ k_shade_miss(WaveArgs a, uint32_t bounce)
             VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, V, 0.0f, 0.0f, &cnt);
             finish_path(a, vt, bounce, path);
         }
-        count_row(a, path, active);
+        count_row(a, path, active, SPB_COST_MISS);
     }
     if (a.stats)
     {
@@ -301,8 +339,8 @@ k_shade_hit(WaveArgs a, uint32_t bounce)
             rng = f2u(ra.w);
             path = f2u(rb.w);
             Hit hit;
-            hit.t = hr.x; hit.u = hr.y; hit.v = hr.z; hit.slot = f2u(hr.w);
-            hit.object = (int32_t)a.hitObj[slot];
+            hit.t = hr.x; hit.slot = f2u(hr.y); hit.object = (int32_t)f2u(hr.z);
+            hit_barycentrics(a.scene, o, d, hit);
             // simd_path_tracer.cpp:268-289
             Surface sf = resolve_hit(a.scene, hit);
             f3 V = neg3(d);
@@ -325,7 +363,7 @@ k_shade_hit(WaveArgs a, uint32_t bounce)
             unsigned dst = warp_append(&ctr[WCTR_STRIDE + WCTR_RAYS], active);
             if (active) store_ray(nextRays, dst, no, nd, rng, path);
         }
-        count_row(a, path, active);
+        count_row(a, path, active, SPB_COST_HIT);
     }
     if (a.stats)
     {
