@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--bounces", type=int, default=5)
     ap.add_argument("--math", type=int, default=0, help="0: double-rounded libm stand-ins (parity mode), 1: CUDA f32")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5", "c5u"],
+                    help="c3: BASELINE configs[2] (default, the bench line); c5: configs[4] instanced stress scene; "
+                         "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
@@ -66,10 +69,14 @@ def parse_args():
 
 
 def workload_config(args):
+    name = ("C3: bunny.obj (4968 tris) + kiara-like 4096x2048 equirect env, "
+            f"{args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces (BASELINE.json configs[2])")
+    if getattr(args, "workload", "c3") != "c3":
+        name = (f"C5: 64 bunnies + 118 level-6 icospheres (9.98 M triangles, "
+                f"{'unique sphere meshes' if args.workload == 'c5u' else 'instanced'}), "
+                f"{args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces (BASELINE.json configs[4])")
     return {
-        "workload": "C3: bunny.obj (4968 tris) + kiara-like 4096x2048 equirect env, "
-                    f"{args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces "
-                    "(BASELINE.json configs[2])",
+        "workload": name,
         "width": args.width, "height": args.height, "spp": args.spp, "bounces": args.bounces,
         "rng": "XorShift32 stream per (pixel, sample, frame), seed = sp_b200_Seed",
         "math_mode": "f64-rounded sin/cos/atan2/pow (bit-parity mode)" if args.math == 0 else "CUDA f32 libm",
@@ -273,7 +280,11 @@ def main():
     stream = torch.cuda.current_stream()
     sp.lib.sp_b200_SetStream(stream.cuda_stream)
 
-    wl = W.config3(args.width, args.height, spp=args.spp, bounces=args.bounces)
+    if args.workload == "c3":
+        wl = W.config3(args.width, args.height, spp=args.spp, bounces=args.bounces)
+    else:
+        wl = W.config5(args.width, args.height, spp=args.spp, bounces=args.bounces,
+                       unique_spheres=args.workload == "c5u")
     H, Wd = wl.height, wl.width
     # pinned host buffers: environment map (input) and the image plane (output)
     env_key = W.IMAGE_ENV

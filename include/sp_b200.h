@@ -153,10 +153,16 @@ sp_Mesh sp_CreateMesh(VertexPNT *vertices, u32 vertexCount, u32 *indices, u32 in
 /* sp_scene.cpp:21-54.  Snapshots vertices/indices and builds the 4-wide midphase BVH
  * (replaces bvh_CreateTree, bvh.cpp:51-200).  Arenas unused.  Asserts indexCount % 3 == 0. */
 void sp_BuildMeshMidphase(sp_Mesh *mesh, MemoryArena *arena, MemoryArena *tempArena);
-/* sp_scene.cpp:77-117.  Asserts objectCount < SP_SCENE_MAX_OBJECTS (use sp_b200_AddObject on a
- * scene handle for larger scenes). */
+/* sp_scene.cpp:77-117.  Asserts objectCount < SP_SCENE_MAX_OBJECTS like the reference (use
+ * sp_b200_AddObjectToScene for larger scenes). */
 void sp_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material, vec3 position,
                          quat orientation, vec3 scale);
+/* sp_AddObjectToScene without the 32-object cap: objects beyond the fixed table of sp_Scene are
+ * kept by the library (per sp_Scene) and joined in by sp_BuildSceneBroadphase.  Returns the
+ * object's index.  sp_b200_SceneObjectCount = table + kept objects. */
+u32 sp_b200_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material, vec3 position,
+                             quat orientation, vec3 scale);
+u32 sp_b200_SceneObjectCount(sp_Scene *scene);
 /* sp_scene.cpp:119-125.  Builds the object-level BVH and uploads the whole scene to the current
  * device once; later render calls reuse it. */
 void sp_BuildSceneBroadphase(sp_Scene *scene);

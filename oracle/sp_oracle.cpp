@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -333,6 +334,79 @@ static Tree grow_tree(const V3 *mins, const V3 *maxs, uint32_t count)
         else break;
     }
     tree.root = last;
+    return tree;
+}
+
+// Scalable builder for inputs the reference's O(n^2 log n) agglomeration cannot finish (the
+// C5-style scenes, which the reference cannot run at all: 32-object table, sp_scene.h:15).  The set
+// of leaves a ray reports does not depend on the tree above them (a leaf is reported iff its box
+// chain passes, and the chain passes whenever the leaf's own box does -- SURVEY.md 7.2), so a
+// median-split 4-ary tree gives the same closest hit; only the order among exactly equal t can
+// differ from what the reference's tree would give.
+static int grow_fast_rec(Tree &tree, const V3 *mins, const V3 *maxs, std::vector<uint32_t> &order,
+                         uint32_t first, uint32_t count)
+{
+    if (count == 1)
+    {
+        TreeNode n;
+        n.mn = mins[order[first]];
+        n.mx = maxs[order[first]];
+        n.child[0] = n.child[1] = n.child[2] = n.child[3] = -1;
+        n.leaf = order[first];
+        tree.nodes.push_back(n);
+        return (int)tree.nodes.size() - 1;
+    }
+    auto split = [&](uint32_t f, uint32_t c) -> uint32_t {
+        V3 lo = P3(INFINITY, INFINITY, INFINITY), hi = P3(-INFINITY, -INFINITY, -INFINITY);
+        for (uint32_t i = f; i < f + c; ++i)
+        {
+            V3 ctr = times(plus(mins[order[i]], maxs[order[i]]), 0.5f);
+            lo = lo3(lo, ctr);
+            hi = hi3(hi, ctr);
+        }
+        V3 e = minus(hi, lo);
+        int axis = e.y > e.x ? (e.z > e.y ? 2 : 1) : (e.z > e.x ? 2 : 0);
+        uint32_t mid = f + c / 2;
+        std::nth_element(order.begin() + f, order.begin() + mid, order.begin() + f + c,
+            [&](uint32_t a, uint32_t b) {
+                float ca = axis == 0 ? mins[a].x + maxs[a].x : axis == 1 ? mins[a].y + maxs[a].y : mins[a].z + maxs[a].z;
+                float cb = axis == 0 ? mins[b].x + maxs[b].x : axis == 1 ? mins[b].y + maxs[b].y : mins[b].z + maxs[b].z;
+                return ca < cb || (ca == cb && a < b);
+            });
+        return mid;
+    };
+    uint32_t part[5] = {first, 0, 0, 0, first + count};
+    part[2] = split(first, count);
+    part[1] = part[2] - first >= 2 ? split(first, part[2] - first) : part[2];
+    part[3] = part[4] - part[2] >= 2 ? split(part[2], part[4] - part[2]) : part[4];
+    TreeNode parent;
+    parent.leaf = 0xFFFFFFFFu;
+    parent.child[0] = parent.child[1] = parent.child[2] = parent.child[3] = -1;
+    parent.mn = P3(INFINITY, INFINITY, INFINITY);
+    parent.mx = P3(-INFINITY, -INFINITY, -INFINITY);
+    int kids = 0;
+    for (int k = 0; k < 4; ++k)
+    {
+        if (part[k + 1] == part[k]) continue;
+        int c = grow_fast_rec(tree, mins, maxs, order, part[k], part[k + 1] - part[k]);
+        parent.child[kids++] = c;
+        parent.mn = lo3(parent.mn, tree.nodes[c].mn);
+        parent.mx = hi3(parent.mx, tree.nodes[c].mx);
+    }
+    tree.nodes.push_back(parent);
+    return (int)tree.nodes.size() - 1;
+}
+
+static const uint32_t kFastBuildThreshold = 24000; // above the monkey (15 744 triangles)
+
+static Tree grow_tree_any(const V3 *mins, const V3 *maxs, uint32_t count)
+{
+    if (count <= kFastBuildThreshold) return grow_tree(mins, maxs, count);
+    Tree tree;
+    tree.nodes.reserve((size_t)count * 2);
+    std::vector<uint32_t> order(count);
+    for (uint32_t i = 0; i < count; ++i) order[i] = i;
+    tree.root = grow_fast_rec(tree, mins, maxs, order, 0, count);
     return tree;
 }
 
@@ -830,7 +904,7 @@ extern "C" int ora_add_mesh(ora_Scene *s, const float *vertices, uint32_t vertex
         mn[i] = lo3(a, lo3(b, c));
         mx[i] = hi3(a, hi3(b, c));
     }
-    mesh.mid = grow_tree(mn.data(), mx.data(), tris);
+    mesh.mid = grow_tree_any(mn.data(), mx.data(), tris);
     s->meshes.push_back(std::move(mesh));
     return (int)s->meshes.size() - 1;
 }
@@ -859,7 +933,7 @@ extern "C" void ora_build(ora_Scene *s)
 {
     std::vector<V3> mn(s->objects.size()), mx(s->objects.size());
     for (size_t i = 0; i < s->objects.size(); ++i) { mn[i] = s->objects[i].bmin; mx[i] = s->objects[i].bmax; }
-    s->broad = grow_tree(mn.data(), mx.data(), (uint32_t)s->objects.size());
+    s->broad = grow_tree_any(mn.data(), mx.data(), (uint32_t)s->objects.size());
 }
 
 extern "C" int ora_register_material(ora_Scene *s, uint32_t id, const float *albedo,

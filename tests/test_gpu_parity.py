@@ -402,6 +402,27 @@ def test_c3_full_size_properties(params):
     r.close()
 
 
+def test_c5_instanced_scene(params):
+    """BASELINE configs[4] shape (182 objects, 9.98 M instanced triangles; reduced resolution and
+    sample count so the CPU checker finishes in seconds): objects beyond the reference's table of
+    32 go through sp_b200_AddObjectToScene.  Checker: the port (the reference cannot hold the
+    scene).  Bit-exact image, object ids and triangle ids."""
+    sp = params
+    wl = W.config5(480, 270, spp=2, bounces=5, env_size=(512, 256))
+    r = sp.Renderer().load_workload(wl)
+    assert sp.lib.sp_b200_SceneObjectCount(C.byref(r.scene)) == 182 and r.scene.objectCount == 32
+    sp.set_params(samplesPerPixel=2, bounceCount=5)
+    img, m = r.render_frame(frame=4)
+    chk = ora.load_port_dm().scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=2, bounces=5, frame=4)
+    assert same_bits(img, cimg) and np.array_equal(m[1:5], cm[1:5])
+    g, e = r.primary_hits(), chk.primary_hits()
+    assert np.array_equal(g["obj"], e["obj"]) and np.array_equal(g["tri"], e["tri"]) and same_bits(g["t"], e["t"])
+    assert len(np.unique(e["obj"])) > 100
+    chk.close()
+    r.close()
+
+
 def test_wavefront_pass_split_and_stats(gpu_sp):
     """Wavefront scheduling details: any samples-per-pass split gives the same bits (the sample
     order of the accumulation is kept, simd_path_tracer.cpp:321); the stats launch counts the same

@@ -110,6 +110,9 @@ struct Library
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
+    // objects beyond the reference's fixed table of 32 (sp_b200_AddObjectToScene), per sp_Scene
+    struct ExtraObject { sp_Mesh mesh; u32 material; spbh::M4 model, invModel; float mn[3], mx[3]; };
+    std::map<sp_Scene *, std::vector<ExtraObject>> extraObjects;
     std::map<const float *, std::unique_ptr<TextureEntry>> textures;
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
@@ -574,10 +577,44 @@ extern "C" void sp_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material,
     scene->materials[index] = material;
 }
 
+extern "C" u32 sp_b200_AddObjectToScene(sp_Scene *scene, sp_Mesh mesh, u32 material, vec3 position,
+                                        quat orientation, vec3 scale)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (scene->objectCount < SP_SCENE_MAX_OBJECTS)
+    {
+        // the fixed table is not full: anything kept beyond it belongs to an earlier build
+        L.extraObjects.erase(scene);
+        sp_AddObjectToScene(scene, mesh, material, position, orientation, scale);
+        return scene->objectCount - 1;
+    }
+    SPB_ASSERT(mesh.vertices != NULL);
+    SPB_ASSERT(mesh.vertexCount > 0);
+    Library::ExtraObject ex;
+    ex.mesh = mesh;
+    ex.material = material;
+    compute_object_transform(nullptr, mesh.vertices, mesh.vertexCount, position, orientation, scale,
+                             &ex.model, &ex.invModel, ex.mn, ex.mx);
+    std::vector<Library::ExtraObject> &list = L.extraObjects[scene];
+    list.push_back(ex);
+    return SP_SCENE_MAX_OBJECTS + (u32)list.size() - 1;
+}
+
+extern "C" u32 sp_b200_SceneObjectCount(sp_Scene *scene)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    auto it = L.extraObjects.find(scene);
+    u32 extra = (it != L.extraObjects.end() && scene->objectCount == SP_SCENE_MAX_OBJECTS) ? (u32)it->second.size() : 0;
+    return scene->objectCount + extra;
+}
+
 extern "C" void sp_b200_ReleaseScene(sp_Scene *scene)
 {
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    L.extraObjects.erase(scene);
     if (scene->broadphaseTree.root)
     {
         if (L.initialized) cudaDeviceSynchronize();
@@ -621,7 +658,10 @@ extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
     // a rebuild of the same sp_Scene replaces its previous device copy (the reference app
     // rebuilds per render, main.cpp:1545-1552)
     if (scene->broadphaseTree.root && L.scenes.count(scene->broadphaseTree.root))
-        sp_b200_ReleaseScene(scene);
+    {
+        if (L.initialized) cudaDeviceSynchronize();
+        L.scenes.erase(scene->broadphaseTree.root);
+    }
     scene->broadphaseTree.root = nullptr;
 
     std::vector<ObjectInstance> objects(scene->objectCount);
@@ -635,6 +675,21 @@ extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
         ob.invModel = to_m4(scene->invModelMatrices[i]);
         ob.aabbMin[0] = scene->aabbMin[i].x; ob.aabbMin[1] = scene->aabbMin[i].y; ob.aabbMin[2] = scene->aabbMin[i].z;
         ob.aabbMax[0] = scene->aabbMax[i].x; ob.aabbMax[1] = scene->aabbMax[i].y; ob.aabbMax[2] = scene->aabbMax[i].z;
+    }
+    auto extra = L.extraObjects.find(scene);
+    if (extra != L.extraObjects.end() && scene->objectCount == SP_SCENE_MAX_OBJECTS)
+    {
+        for (const Library::ExtraObject &ex : extra->second)
+        {
+            ObjectInstance ob;
+            ob.mesh = find_mesh(ex.mesh);
+            ob.material = ex.material;
+            ob.smooth = ex.mesh.useSmoothShading ? 1u : 0u;
+            ob.model = ex.model;
+            ob.invModel = ex.invModel;
+            for (int k = 0; k < 3; ++k) { ob.aabbMin[k] = ex.mn[k]; ob.aabbMax[k] = ex.mx[k]; }
+            objects.push_back(ob);
+        }
     }
     FlatScene fs = flatten_scene(objects);
     std::unique_ptr<DeviceScene> ds = upload_scene(fs);

@@ -210,6 +210,8 @@ _SIGNATURES = {
     "sp_CreateMesh": (sp_Mesh, [_P(VertexPNT), u32, _P(u32), u32, u32]),
     "sp_BuildMeshMidphase": (None, [_P(sp_Mesh), _P(MemoryArena), _P(MemoryArena)]),
     "sp_AddObjectToScene": (None, [_P(sp_Scene), sp_Mesh, u32, vec3, quat, vec3]),
+    "sp_b200_AddObjectToScene": (u32, [_P(sp_Scene), sp_Mesh, u32, vec3, quat, vec3]),
+    "sp_b200_SceneObjectCount": (u32, [_P(sp_Scene)]),
     "sp_BuildSceneBroadphase": (None, [_P(sp_Scene)]),
     "sp_RayIntersectScene": (sp_RayIntersectSceneResult, [_P(sp_Scene), vec3, vec3, _P(sp_Metrics)]),
     "sp_RayIntersectMesh": (sp_RayIntersectMeshResult, [sp_Mesh, vec3, vec3, _P(sp_Metrics)]),
@@ -349,9 +351,8 @@ class Renderer:
         return len(self.meshes) - 1
 
     def add_object(self, mesh, material, position=(0, 0, 0), rotation=(0, 0, 0, 1), scale=(1, 1, 1)):
-        lib.sp_AddObjectToScene(C.byref(self.scene), self.meshes[mesh], material, V3(position),
-                                Q(rotation), V3(scale))
-        return self.scene.objectCount - 1
+        return lib.sp_b200_AddObjectToScene(C.byref(self.scene), self.meshes[mesh], material, V3(position),
+                                            Q(rotation), V3(scale))
 
     def build(self):
         lib.sp_BuildSceneBroadphase(C.byref(self.scene))

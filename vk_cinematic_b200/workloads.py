@@ -301,3 +301,47 @@ def multi_object_workload(width=320, height=240, spp=1, bounces=3, count=12, see
         camera_position=(0.0, 0.4, 4.0), camera_rotation=(0.0, 0.0, 0.0, 1.0),
         film_distance=0.8, width=width, height=height, spp=spp, bounces=bounces,
         notes={"objects": len(objects)})
+
+
+def config5(width=3840, height=2160, spp=16, bounces=5, bunnies=64, spheres=118, sphere_level=6,
+            unique_spheres=False, seed=0x1A34C249, env_size=(4096, 2048)):
+    """BASELINE configs[4]: procedural instanced scene, ~10 M triangles at the defaults
+    (64 bunnies x 4 968 + 118 icospheres x 81 920 = 9.98 M), on a seeded jittered grid
+    (XorShift-style seed 0x1A34C249, the reference's perf-test seed, perf_tests.cpp:57).
+    The reference cannot run it (32-object table, sp_scene.h:15; O(n^2 log n) build), so the
+    checker is the port.  unique_spheres=True gives every sphere its own mesh (no instancing):
+    the BVH then no longer fits L2 -- the HBM-bound variant."""
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    bunny = load_mesh("bunny", smooth=True)
+    meshes = [bunny]
+    count = bunnies + spheres
+    side = int(np.ceil(count ** (1.0 / 3.0)))
+    cells = [(i, j, k) for i in range(side) for j in range(side) for k in range(side)]
+    order = rng.permutation(len(cells))[:count]
+    objects = []
+    sphere_meshes = 0
+    for n, ci in enumerate(order):
+        cell = np.array(cells[ci], dtype=np.float64)
+        pos = (cell - (side - 1) / 2.0) * 1.0 + rng.uniform(-0.18, 0.18, 3)
+        rot = quat_axis_angle(rng.uniform(-1, 1, 3) + 1e-3, rng.uniform(0, 2 * np.pi))
+        if n < bunnies:
+            sc = float(rng.uniform(2.2, 3.2))
+            objects.append(SceneObject(0, MATERIAL_SURFACE, tuple(pos), rot, (sc, sc, sc)))
+        else:
+            if unique_spheres or sphere_meshes == 0:
+                meshes.append(icosphere_mesh(sphere_level, smooth=True))
+                sphere_meshes += 1
+            sc = float(rng.uniform(0.25, 0.38))
+            objects.append(SceneObject(len(meshes) - 1, MATERIAL_CHECKER if n % 3 == 0 else MATERIAL_SURFACE,
+                                       tuple(pos), rot, (sc, sc, sc)))
+    tris = sum(meshes[o.mesh].triangle_count for o in objects)
+    materials = _standard_materials() + [
+        Material(MATERIAL_CHECKER, albedo=(0.6, 0.3, 0.2), roughness=0.35)]
+    dist = 1.15 * side
+    return Workload(
+        name=f"C5_{count}obj_{tris}tris_{width}x{height}_{spp}spp", meshes=meshes, objects=objects,
+        materials=materials, textures={IMAGE_ENV: make_env_map(env_size[0], env_size[1], "studio_garden")},
+        background=MATERIAL_BACKGROUND, camera_position=(0.0, 0.0, float(dist)),
+        camera_rotation=(0.0, 0.0, 0.0, 1.0), film_distance=0.8, width=width, height=height,
+        spp=spp, bounces=bounces,
+        notes={"objects": count, "instanced_triangles": int(tris), "unique_meshes": len(meshes)})
