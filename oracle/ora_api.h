@@ -71,6 +71,14 @@ void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uint
                        uint32_t y1, uint32_t spp, uint32_t bounces, uint32_t frame,
                        uint32_t threads, uint64_t *metrics);
 
+/* PORT ONLY.  mask[width*height] (u8): 1 for every pixel of the rectangle on whose paths (same
+ * seeds as ora_render_seeded) some sp_RayIntersectScene call ended with two candidates of
+ * bit-equal closest t -- the one case where the winner depends on visiting order, i.e. on tree
+ * topology, which the reference's algorithm does not fix (bvh.cpp:51-200 vs any other builder).
+ * Parity tests accept a differing pixel only where this mask is set. */
+void ora_tie_mask(ora_Scene *s, uint8_t *mask, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                  uint32_t spp, uint32_t bounces, uint32_t frame, uint32_t threads);
+
 /* The reference's native scheduling (main.cpp:731-759,819-844): tileW x tileH tiles popped from
  * the work queue by `threads` workers, every tile seeded 0xF51C0E49, spp samples per pixel.
  * Returns wall seconds (steady_clock, submit -> last tile done). */

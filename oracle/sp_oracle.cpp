@@ -510,6 +510,10 @@ struct Counters64 { uint64_t v[ORA_METRIC_COUNT]; };
 struct Scratch
 {
     std::vector<int> leaves, objLeaves, st[2], st2[2];
+    // tie bookkeeping for ora_tie_mask(): how many scene queries ended with two candidates of
+    // exactly equal t (the only case where visiting order picks the winner)
+    uint64_t ties = 0;
+    bool meshTie = false;
 };
 
 // TransformAabb, aabb.h:29-58
@@ -587,8 +591,10 @@ static MeshHit hit_mesh(const Mesh &mesh, V3 o, V3 d, Counters64 *m, Scratch *sc
         m->v[ORA_METRIC_CYC_TRIANGLE] += tick() - t1;
         if (h.t > 0.0f)
         {
+            if (h.t == best.tri.t) sc->meshTie = true; // equal t: the first one visited stays
             if (h.t < best.tri.t || best.tri.t < 0.0f)
             {
+                sc->meshTie = false;
                 best.tri = h;
                 best.triangle = (int)tri;
                 float w = 1.0f - h.uv.x - h.uv.y;
@@ -615,6 +621,7 @@ static SceneHit hit_scene(const ora_Scene *s, V3 o, V3 d, Counters64 *m, Scratch
     r.t = -1.0f;
     r.object = r.triangle = -1;
     uint64_t b0 = tick();
+    bool tied = false;
     Query q = walk_tree(s->broad, o, d, sc->objLeaves, 0, sc->st2);
     m->v[ORA_METRIC_CYC_BROADPHASE] += tick() - b0;
     for (uint32_t i = 0; i < q.count; ++i)
@@ -624,6 +631,7 @@ static SceneHit hit_scene(const ora_Scene *s, V3 o, V3 d, Counters64 *m, Scratch
         V3 lo = apply_point(o, ob.invModel);
         V3 ld = unit(apply_vector(d, ob.invModel));
         uint64_t m0 = tick();
+        sc->meshTie = false;
         MeshHit mh = hit_mesh(s->meshes[ob.mesh], lo, ld, m, sc);
         m->v[ORA_METRIC_CYC_MESH] += tick() - m0;
         m->v[ORA_METRIC_MESH_TESTS]++;
@@ -633,8 +641,10 @@ static SceneHit hit_scene(const ora_Scene *s, V3 o, V3 d, Counters64 *m, Scratch
             V3 wh = apply_point(lh, ob.model);
             float t = inner(minus(wh, o), d);
             V3 wn = unit(apply_vector(mh.tri.n, ob.model));
+            if (t == r.t) tied = true;
             if (t < r.t || r.t < 0.0f)
             {
+                tied = sc->meshTie;
                 r.t = t;
                 r.material = ob.material;
                 r.n = wn;
@@ -645,6 +655,7 @@ static SceneHit hit_scene(const ora_Scene *s, V3 o, V3 d, Counters64 *m, Scratch
         }
     }
     m->v[ORA_METRIC_CYC_SCENE] += tick() - start;
+    if (tied) sc->ties++;
     return r;
 }
 
@@ -1022,6 +1033,35 @@ extern "C" void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32
     if (metrics)
         for (uint32_t t = 0; t < threads; ++t)
             for (int i = 0; i < ORA_METRIC_COUNT; ++i) metrics[i] += per[t].v[i];
+}
+
+// Pixels of the rectangle on whose paths (any sample, any bounce) a scene query ended in an exact
+// tie: two triangles, or two objects, with bit-equal closest t.  There the winner depends on the
+// order candidates are visited in (tree topology), which the reference does not define -- the
+// parity tests accept a differing pixel only where this mask is set.  Port only.
+extern "C" void ora_tie_mask(ora_Scene *s, uint8_t *mask, uint32_t x0, uint32_t y0, uint32_t x1,
+                             uint32_t y1, uint32_t spp, uint32_t bounces, uint32_t frame,
+                             uint32_t threads)
+{
+    if (threads == 0) threads = 1;
+    uint32_t width = s->cam.width;
+    run_threads(threads, [&](uint32_t tid) {
+        Scratch sc;
+        std::vector<PathVertex> path(bounces + 1);
+        Counters64 m;
+        memset(&m, 0, sizeof(m));
+        for (uint32_t y = y0 + tid; y < y1; y += threads)
+            for (uint32_t x = x0; x < x1; ++x)
+            {
+                uint64_t before = sc.ties;
+                for (uint32_t k = 0; k < spp; ++k)
+                {
+                    uint32_t rng = ora_seed(x + y * width, k, frame);
+                    one_path(s, x, y, &rng, bounces, 10.0f, &m, &sc, path.data());
+                }
+                mask[(size_t)x + (size_t)y * width] = sc.ties != before ? 1 : 0;
+            }
+    });
 }
 
 extern "C" double ora_render_tiles(ora_Scene *s, float *rgba, uint32_t tileW, uint32_t tileH,

@@ -102,6 +102,7 @@ class OracleLib:
         lib.ora_seed.argtypes = [C.c_uint32] * 3
         lib.ora_seed.restype = C.c_uint32
         lib.ora_render_seeded.argtypes = [C.c_void_p, _f] + [C.c_uint32] * 8 + [_u64]
+        lib.ora_tie_mask.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)] + [C.c_uint32] * 8
         lib.ora_render_tiles.argtypes = [C.c_void_p, _f] + [C.c_uint32] * 5 + [_u64]
         lib.ora_render_tiles.restype = C.c_double
         lib.ora_render_tile_list.argtypes = [C.c_void_p, _f, _u] + [C.c_uint32] * 4 + [_u64]
@@ -315,6 +316,16 @@ class OracleScene:
         self.lib.ora_render_seeded(self.h, _fp(image), x0, y0, x1, y1, spp, bounces, frame,
                                    threads, metrics.ctypes.data_as(_u64))
         return image, metrics
+
+    def tie_mask(self, spp=1, bounces=3, frame=0, threads=None, rect=None):
+        """uint8 (H, W): 1 where some scene query on the pixel's paths ended in an exact-t tie (port
+        only; the verbatim reference cannot report it)."""
+        threads = threads or os.cpu_count() or 1
+        mask = np.zeros((self.height, self.width), np.uint8)
+        x0, y0, x1, y1 = rect or (0, 0, self.width, self.height)
+        self.lib.ora_tie_mask(self.h, mask.ctypes.data_as(C.POINTER(C.c_uint8)), x0, y0, x1, y1, spp,
+                              bounces, frame, threads)
+        return mask
 
     def render_tiles(self, tile_w=64, tile_h=64, spp=1, bounces=3, threads=None):
         threads = threads or os.cpu_count() or 1

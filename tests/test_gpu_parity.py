@@ -32,6 +32,22 @@ def same_bits(a, b):
     return np.array_equal(bits(a), bits(b))
 
 
+def assert_same_image_up_to_ties(img, cimg, chk, spp, bounces, frame, bound=1e-4):
+    """Bit-equal images except at pixels where the checker itself met two candidates with bit-equal
+    closest t on one of the pixel's paths (ora_tie_mask): there the winner depends on the order
+    the tree presents them in, which differs between the reference's agglomerative tree and any
+    other builder.  The number of such differing pixels is bounded (BASELINE.json: < 1e-4)."""
+    diff = np.any(bits(img) != bits(cimg), axis=-1)
+    if not diff.any():
+        return 0
+    ties = chk.tie_mask(spp=spp, bounces=bounces, frame=frame).astype(bool)
+    unexplained = diff & ~ties
+    assert not unexplained.any(), f"{int(unexplained.sum())} differing pixels without an exact-t tie: " \
+                                  f"{list(zip(*np.nonzero(unexplained)))[:8]}"
+    assert diff.sum() <= max(1, int(bound * diff.size)), f"{int(diff.sum())} tie pixels differ (bound {bound})"
+    return int(diff.sum())
+
+
 def best(dm):
     """The strongest available checker: the reference itself, else the port."""
     if ora.have_ref():
@@ -406,7 +422,8 @@ def test_c5_instanced_scene(params):
     """BASELINE configs[4] shape (182 objects, 9.98 M instanced triangles; reduced resolution and
     sample count so the CPU checker finishes in seconds): objects beyond the reference's table of
     32 go through sp_b200_AddObjectToScene.  Checker: the port (the reference cannot hold the
-    scene).  Bit-exact image, object ids and triangle ids."""
+    scene).  Bit-exact image, object ids, hit distances and triangle ids, except where the checker
+    reports an exact-t tie between two candidates (bounded at 1e-4 of the pixels)."""
     sp = params
     wl = W.config5(480, 270, spp=2, bounces=5, env_size=(512, 256))
     r = sp.Renderer().load_workload(wl)
@@ -415,9 +432,13 @@ def test_c5_instanced_scene(params):
     img, m = r.render_frame(frame=4)
     chk = ora.load_port_dm().scene().load_workload(wl)
     cimg, cm = chk.render_seeded(spp=2, bounces=5, frame=4)
-    assert same_bits(img, cimg) and np.array_equal(m[1:5], cm[1:5])
+    # tiny sphere triangles: a few rays per frame meet two edge-sharing triangles at bit-equal t
+    ntie = assert_same_image_up_to_ties(img, cimg, chk, 2, 5, 4)
+    assert m[1] == cm[1] and np.all(np.abs(m[2:5].astype(np.int64) - cm[2:5].astype(np.int64)) <= ntie * 2 * 5)
     g, e = r.primary_hits(), chk.primary_hits()
-    assert np.array_equal(g["obj"], e["obj"]) and np.array_equal(g["tri"], e["tri"]) and same_bits(g["t"], e["t"])
+    # closest-hit ids: equal except equal-t ties (t itself must be bit-equal everywhere)
+    assert np.array_equal(g["obj"], e["obj"]) and same_bits(g["t"], e["t"])
+    assert (g["tri"] != e["tri"]).sum() <= 1e-4 * g["tri"].size
     assert len(np.unique(e["obj"])) > 100
     chk.close()
     r.close()

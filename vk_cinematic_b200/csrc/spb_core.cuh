@@ -446,6 +446,17 @@ SPB_HD void traverse(const v4f *nodes, uint32_t root, f3 o, f3 inv, float tcull,
 // the same quantity, so a strict comparison could drop an equal-distance winner.
 #define SPB_CULL_SLACK 1.0009765625f /* 1 + 2^-10 */
 
+// A WORLD distance (sp_scene.cpp:296-302: t = Dot(M * localHit - origin, dir)) comes out of a
+// transform and a subtraction of coordinates, so its error is absolute -- a few ulps of the
+// coordinates involved -- not relative to t.  For a short ray far from the scene origin that can
+// exceed the relative slack, so every bound derived from a world t is first padded by 2^-16 of
+// (|origin|_1 + |t|) (>= 100x the worst rounding of the transform chain).  Only object entry and
+// exit pay for it.
+SPB_HD float cull_pad(f3 worldOrigin, float t)
+{
+    return 1.52587890625e-05f * (fabsf(worldOrigin.x) + fabsf(worldOrigin.y) + fabsf(worldOrigin.z) + fabsf(t));
+}
+
 // sp_RayIntersectMesh (sp_scene.cpp:127-227) on one object-space ray.
 template <bool CULL, bool EXACT>
 SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float tcull,
@@ -529,7 +540,7 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
 
         // distance bound in object space: |M^-1 d| maps world t to local t exactly (affine)
         float localCull = inf;
-        if (CULL && best.t >= 0.0f) localCull = best.t * scaleLen * SPB_CULL_SLACK;
+        if (CULL && best.t >= 0.0f) localCull = (best.t + cull_pad(o, best.t)) * scaleLen * SPB_CULL_SLACK;
 
         float lt, lu, lv;
         uint32_t lslot;
@@ -557,7 +568,7 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
                 best.localOrigin = lo;
                 best.localDirection = ld;
                 best.localT = lt;
-                float c2 = t * SPB_CULL_SLACK;
+                float c2 = (t + cull_pad(o, t)) * SPB_CULL_SLACK;
                 if (t > 0.0f && c2 < cull) cull = c2;
             }
         }
@@ -690,7 +701,7 @@ SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, co
             c.bT = t;
             c.bObject = (int32_t)c.object;
             c.bSlot = st.lSlot;
-            float c2 = t * SPB_CULL_SLACK;
+            float c2 = (t + cull_pad(wo, t)) * SPB_CULL_SLACK;
             if (t > 0.0f && c2 < worldCull) worldCull = c2;
         }
     }
@@ -824,7 +835,7 @@ SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, Tr
             c.worldCull = st.tcull;
             st.tcull = inf;
             float bT = c.bT;
-            if (CULL && bT >= 0.0f) st.tcull = bT * scaleLen * SPB_CULL_SLACK;
+            if (CULL && bT >= 0.0f) st.tcull = (bT + cull_pad(wo, bT)) * scaleLen * SPB_CULL_SLACK;
             st.o = lo;
             st.d = ld;
             st.inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
