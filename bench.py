@@ -62,6 +62,7 @@ def parse_args():
                          "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
+    ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -295,6 +296,8 @@ def main():
     sp.set_params(samplesPerPixel=args.spp, bounceCount=args.bounces, cullByDistance=1,
                   mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=64,
                   renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
+    if args.paths_per_pass:
+        sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
     TH = 64
     image = torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev)
 

@@ -225,7 +225,8 @@ typedef struct sp_b200_Params {
     u32 tileWidth;       /* TILE_WIDTH / TILE_HEIGHT, config.h:15-16 (cost accounting granularity) */
     u32 tileHeight;
     u32 renderMode;      /* SP_B200_RENDER_*: how sp_b200_Render* schedules the work on the GPU */
-    u32 samplesPerPass;  /* wavefront mode: samples per pixel traced per pass; 0 = automatic */
+    u32 samplesPerPass;  /* wavefront mode: samples per pixel traced per pass; 0 = automatic (all
+                            of them, in bands of rows sized by sp_b200_SetPathsPerPass) */
 } sp_b200_Params;
 
 /* Kernel-side counters of the most recent launch (for the roofline). */
@@ -253,6 +254,9 @@ void sp_b200_EnableStats(int enable);
 u64 sp_b200_KernelLaunchCount(void);
 /* Forget device copies of HdrImage pixel buffers (they are cached by host pointer). */
 void sp_b200_FlushTextureCache(void);
+/* Wavefront mode: paths kept in flight per pass (band height x samples per pass are derived from
+ * it); 0 restores the default (32 Mi).  Results do not depend on it. */
+void sp_b200_SetPathsPerPass(u32 paths);
 /* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
 u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
 

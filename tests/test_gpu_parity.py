@@ -459,6 +459,14 @@ def test_wavefront_pass_split_and_stats(gpu_sp):
         if ref_img is None:
             ref_img, ref_m = img.copy(), m.copy()
         assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
+    # bands of rows: 200 x 150 at 7 spp in passes of at most 4096 / 20000 paths (several bands,
+    # the last one ragged; with 4096 the samples of a pixel are split over passes as well)
+    for paths in (4096, 20000):
+        sp.lib.sp_b200_SetPathsPerPass(paths)
+        sp.set_params(samplesPerPass=0)
+        img, m = r.render_frame(frame=3)
+        assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
+    sp.lib.sp_b200_SetPathsPerPass(0)
     sp.set_params(renderMode=1)
     img, m = r.render_frame(frame=3)
     assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])

@@ -11,7 +11,6 @@ timeout 300 python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/smok
 echo "smoke exit $?" >> gpurun_out/smoke_${TAG}.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 echo "bench exit $?" >> gpurun_out/bench_${TAG}.err
-timeout 600 python bench.py --steps 5 --warmup 3 --render-mode 1 --no-cpu-baseline > gpurun_out/bench_perpixel_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --spp 8 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 8 -c 2 -f -o gpurun_out/prof_${TAG} \

@@ -107,6 +107,7 @@ struct Library
     cudaStream_t stream = 0;
     sp_b200_Params params;
     bool statsEnabled = false;
+    uint32_t pathsPerPass = 0; // 0: default (render_wavefront)
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
@@ -358,29 +359,30 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
     return (DeviceScene *)accel->deviceScene;
 }
 
-// Wavefront render of args' rectangle: passes of S samples, each a fixed sequence of kernels
-// over device queues (spb_wavefront.cu).  Nothing is read back between kernels.
+// Wavefront render of args' rectangle.  The rectangle is cut into bands of whole 4-pixel block
+// rows; a band is rendered in passes of S samples per pixel (all of them when they fit), each pass
+// a fixed sequence of kernels over device queues (spb_wavefront.cu).  Nothing is read back between
+// kernels.  Band height and S are chosen so that one pass keeps about 32 Mi paths in flight.
 void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
 {
     Library &L = lib();
     const uint32_t width = ra.x1 - ra.x0, height = ra.y1 - ra.y0;
-    const uint32_t stripPixels = width * height;
     const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
-    const uint32_t itemsPerSample = blocksX * blocksY * 32;
     const uint32_t spp = ra.spp, bounces = ra.bounces;
 
-    // samples per pass: enough paths in flight to fill the GPU, bounded working set
-    uint32_t S = L.params.samplesPerPass;
-    if (S == 0)
-    {
-        const uint64_t targetItems = 16u << 20; // 16 Mi paths per pass
-        S = (uint32_t)(targetItems / (itemsPerSample ? itemsPerSample : 1));
-        if (S < 1) S = 1;
-    }
+    const uint64_t targetItems = L.pathsPerPass ? L.pathsPerPass : (32u << 20);
+    const uint64_t rowItems = (uint64_t)blocksX * 32; // items of one block row, one sample
+    uint32_t S = L.params.samplesPerPass ? L.params.samplesPerPass : spp;
     if (S > spp) S = spp;
-    SPB_ASSERT((uint64_t)itemsPerSample * S < 0xFFFFFFFFull);
-    const uint32_t capacity = itemsPerSample * S; // ray slots and path ids both fit
+    if (rowItems * S > targetItems) S = (uint32_t)(targetItems / rowItems);
+    if (S < 1) S = 1;
+    uint32_t bandBlocksY = (uint32_t)(targetItems / (rowItems * S));
+    if (bandBlocksY < 1) bandBlocksY = 1;
+    if (bandBlocksY > blocksY) bandBlocksY = blocksY;
+    const uint32_t bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
     const uint32_t passes = (spp + S - 1) / S;
+    SPB_ASSERT(rowItems * bandBlocksY * S < 0xFFFFFFFFull);
+    const uint32_t capacity = (uint32_t)(rowItems * bandBlocksY * S); // ray slots and path ids both fit
 
     L.wRays[0].ensure((size_t)capacity * 32);
     L.wRays[1].ensure((size_t)capacity * 32);
@@ -389,7 +391,7 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     L.wMissQ.ensure((size_t)capacity * 4);
     L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
     L.wRad.ensure((size_t)capacity * 16);
-    const size_t ctrWords = (size_t)passes * bounces * WCTR_STRIDE;
+    const size_t ctrWords = (size_t)bands * passes * bounces * WCTR_STRIDE;
     L.wCtr.ensure(ctrWords * 4);
     SPB_CUDA(cudaMemsetAsync(L.wCtr.ptr, 0, ctrWords * 4, L.stream));
 
@@ -397,10 +399,8 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     a.scene = ra.scene;
     a.materials = ra.materials;
     a.camera = ra.camera;
-    a.x0 = ra.x0; a.y0 = ra.y0; a.x1 = ra.x1; a.y1 = ra.y1;
-    a.stripPixels = stripPixels;
+    a.x0 = ra.x0; a.x1 = ra.x1;
     a.blocksX = blocksX;
-    a.itemsPerSample = itemsPerSample;
     a.spp = spp;
     a.bounces = bounces;
     a.frame = ra.frame;
@@ -417,21 +417,33 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     a.stats = L.statsEnabled ? ra.counters : nullptr;
     a.tileRowCost = ra.tileRowCost;
     a.tileHeight = ra.tileHeight;
+    a.costRow0 = ra.y0 / (ra.tileHeight ? ra.tileHeight : 1);
 
     KernelConfig cfg = kernel_config();
-    for (uint32_t pass = 0; pass < passes; ++pass)
+    uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
+    for (uint32_t band = 0; band < bands; ++band)
     {
-        a.firstSample = pass * S;
-        a.samplesThisPass = spp - a.firstSample < S ? spp - a.firstSample : S;
-        a.workItems = itemsPerSample * a.samplesThisPass;
-        a.ctr = (uint32_t *)L.wCtr.ptr + (size_t)pass * bounces * WCTR_STRIDE;
-        launch_wave_trace(cfg, a, 0, true, L.stream);
-        for (uint32_t b = 0; b < bounces; ++b)
+        const uint32_t by0 = band * bandBlocksY;
+        const uint32_t by1 = by0 + bandBlocksY < blocksY ? by0 + bandBlocksY : blocksY;
+        a.y0 = ra.y0 + by0 * 4;
+        a.y1 = ra.y0 + by1 * 4 < ra.y1 ? ra.y0 + by1 * 4 : ra.y1;
+        a.stripPixels = width * (a.y1 - a.y0);
+        a.itemsPerSample = blocksX * (by1 - by0) * 32;
+        for (uint32_t pass = 0; pass < passes; ++pass)
         {
-            launch_wave_shade(cfg, a, b, L.stream);
-            if (b + 1 < bounces) launch_wave_trace(cfg, a, b + 1, false, L.stream);
+            a.firstSample = pass * S;
+            a.samplesThisPass = spp - a.firstSample < S ? spp - a.firstSample : S;
+            a.workItems = a.itemsPerSample * a.samplesThisPass;
+            a.ctr = ctr;
+            ctr += (size_t)bounces * WCTR_STRIDE;
+            launch_wave_trace(cfg, a, 0, true, L.stream);
+            for (uint32_t b = 0; b < bounces; ++b)
+            {
+                launch_wave_shade(cfg, a, b, L.stream);
+                if (b + 1 < bounces) launch_wave_trace(cfg, a, b + 1, false, L.stream);
+            }
+            launch_wave_accumulate(a, L.stream);
         }
-        launch_wave_accumulate(a, L.stream);
     }
     countersOut.resize(ctrWords);
 }
@@ -507,6 +519,8 @@ extern "C" void sp_b200_FlushTextureCache(void)
     if (L.initialized) cudaDeviceSynchronize();
     L.textures.clear();
 }
+
+extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
 
 extern "C" u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame)
 {

@@ -119,11 +119,11 @@ struct WaveArgs
     DScene scene;
     const DMaterials *materials;
     DCamera camera;
-    uint32_t x0, y0, x1, y1;   // pixel rectangle of the strip
+    uint32_t x0, y0, x1, y1;   // pixel rectangle of the band this pass renders
     uint32_t stripPixels;      // (x1 - x0) * (y1 - y0)
-    uint32_t blocksX;          // 8x4 pixel blocks per row of the strip
-    uint32_t itemsPerSample;   // blocksX * blocksY * 32 (primary work items of one sample)
-    uint32_t workItems;        // itemsPerSample * samplesThisPass
+    uint32_t blocksX;          // 8x4 pixel blocks per row of the band
+    uint32_t itemsPerSample;   // blocksX * blocksY * 32 (pixels of the band incl. block padding)
+    uint32_t workItems;        // itemsPerSample * samplesThisPass; item = pixel * samplesThisPass + sample
     uint32_t samplesThisPass, firstSample, spp, bounces, frame;
     uint32_t pathCapacity;     // paths per pass the per-path arrays are sized for
     float clampValue;
@@ -131,12 +131,13 @@ struct WaveArgs
     v4f *hitRec;               // per ray slot: t, triangle slot bits, object index bits, -
     uint32_t *hitQ, *missQ;    // compact lists of ray slots
     v4f *pathTerms;            // [bounce][path] two float4: (E, cosine) (W, -)
-    v4f *rad;                  // [sample in pass][pixel in strip]
+    v4f *rad;                  // [path]: pixel-major (8x4-block order), samplesThisPass per pixel
     v4f *out;                  // full image
     uint32_t *ctr;             // this pass's counters: bounces x WCTR_STRIDE
     unsigned long long *stats; // CTR_* slots, may be null
     unsigned long long *tileRowCost; // may be null
     uint32_t tileHeight;
+    uint32_t costRow0;         // tile row that tileRowCost[0] stands for
 };
 
 void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,

@@ -60,6 +60,20 @@ __device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, 
     rays[(size_t)slot * 2 + 1] = b;
 }
 
+// Primary work item / path id -> pixel and sample-in-pass.  Items enumerate the band's pixels in
+// 8x4-block order (block row-major, then row-major inside the block), samplesThisPass consecutive
+// items per pixel.  Pixels past the band's edge (block padding) are holes.
+__device__ __forceinline__ void item_pixel(const WaveArgs &a, unsigned item, unsigned &x, unsigned &y,
+                                           unsigned &sLocal)
+{
+    unsigned pi = item / a.samplesThisPass;
+    sLocal = item - pi * a.samplesThisPass;
+    unsigned block = pi >> 5, l = pi & 31u;
+    unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
+    x = a.x0 + bx * 8 + (l & 7u);
+    y = a.y0 + by * 4 + (l >> 3);
+}
+
 // The rare ray whose reciprocal direction is not finite (axis-parallel): exact slab form.
 template <bool CULL>
 __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
@@ -155,21 +169,20 @@ k_trace(WaveArgs a, uint32_t bounce)
                     bool valid = true;
                     if (PRIMARY)
                     {
-                        // item -> (sample, 8x4 pixel block, lane in block): neighbouring lanes
-                        // trace neighbouring pixels
-                        unsigned sLocal = idx / a.itemsPerSample;
-                        unsigned r = idx - sLocal * a.itemsPerSample;
-                        unsigned block = r >> 5, l = r & 31u;
-                        unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
-                        unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
+                        // item -> (pixel in 8x4-block order, sample): neighbouring lanes trace
+                        // the samples of one pixel, then the neighbouring pixel.  The reference's
+                        // jitter is +-0.5/width of a PIXEL (simd_path_tracer.cpp:222-226), so the
+                        // samples of a pixel walk the same nodes: node fetches of a warp coalesce
+                        // into one L1 wavefront and its lanes stay together.
+                        unsigned x, y, sLocal;
+                        item_pixel(a, idx, x, y, sLocal);
                         valid = x < a.x1 && y < a.y1;
                         if (valid)
                         {
                             uint32_t pixelIndex = x + y * a.camera.width;
                             uint32_t rng = stream_seed(pixelIndex, a.firstSample + sLocal, a.frame);
                             primary_ray(a.camera, x, y, rng, o, d);
-                            uint32_t path = sLocal * a.stripPixels + (y - a.y0) * (a.x1 - a.x0) + (x - a.x0);
-                            store_ray(rays, idx, o, d, rng, path);
+                            store_ray(rays, idx, o, d, rng, idx); // path id == primary item
                         }
                     }
                     else
@@ -269,8 +282,9 @@ __device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms
 __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active, unsigned weight)
 {
     if (!a.tileRowCost) return;
-    unsigned pix = path % a.stripPixels;
-    unsigned row = active ? ((a.y0 + pix / (a.x1 - a.x0)) / a.tileHeight - a.y0 / a.tileHeight) : 0xFFFFFFFFu;
+    unsigned x, y, sLocal;
+    item_pixel(a, path, x, y, sLocal);
+    unsigned row = active ? (y / a.tileHeight - a.costRow0) : 0xFFFFFFFFu;
     unsigned peers = __match_any_sync(SPB_FULL, row);
     if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
         atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
@@ -380,8 +394,11 @@ k_accumulate(WaveArgs a)
     const float weight = 1.0f / (float)a.spp;
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.stripPixels; p += gridDim.x * blockDim.x)
     {
-        unsigned y = a.y0 + p / width, x = a.x0 + p % width;
-        size_t pixel = (size_t)x + (size_t)y * a.camera.width;
+        unsigned ly = p / width, lx = p - ly * width;
+        size_t pixel = (size_t)(a.x0 + lx) + (size_t)(a.y0 + ly) * a.camera.width;
+        // position of the pixel in 8x4-block order (item_pixel's inverse)
+        unsigned pi = ((ly >> 2) * a.blocksX + (lx >> 3)) * 32u + (ly & 3u) * 8u + (lx & 7u);
+        const v4f *rad = a.rad + (size_t)pi * a.samplesThisPass;
         f3 total = mk3(0.0f, 0.0f, 0.0f);
         if (a.firstSample != 0)
         {
@@ -390,7 +407,7 @@ k_accumulate(WaveArgs a)
         }
         for (unsigned s = 0; s < a.samplesThisPass; ++s)
         {
-            v4f r = a.rad[(size_t)s * a.stripPixels + p];
+            v4f r = rad[s];
             total = add3(total, mul3(mk3(r.x, r.y, r.z), weight));
         }
         v4f o;
