@@ -257,6 +257,10 @@ void sp_b200_FlushTextureCache(void);
 /* Wavefront mode: paths kept in flight per pass (band height x samples per pass are derived from
  * it); 0 restores the default (32 Mi).  Results do not depend on it. */
 void sp_b200_SetPathsPerPass(u32 paths);
+/* Wavefront mode: pixels outside the padded screen rectangle of the scene's world bounds are
+ * evaluated by a queue-less kernel (their rays cannot hit anything).  On by default; results do
+ * not depend on it. */
+void sp_b200_SetSkyCulling(int enable);
 /* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
 u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
 

@@ -467,6 +467,14 @@ def test_wavefront_pass_split_and_stats(gpu_sp):
         img, m = r.render_frame(frame=3)
         assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
     sp.lib.sp_b200_SetPathsPerPass(0)
+    # sky culling off: every pixel through the queues -- same bits, same counters, same row costs
+    sp.lib.sp_b200_SetSkyCulling(0)
+    img, m = r.render_frame(frame=3)
+    assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])
+    _, cost_all = r.render_rows(0, 150, frame=3, want_cost=True)
+    sp.lib.sp_b200_SetSkyCulling(1)
+    _, cost_sky = r.render_rows(0, 150, frame=3, want_cost=True)
+    assert np.array_equal(cost_all, cost_sky)
     sp.set_params(renderMode=1)
     img, m = r.render_frame(frame=3)
     assert same_bits(img, ref_img) and np.array_equal(m[1:5], ref_m[1:5])

@@ -86,6 +86,8 @@ struct DeviceScene
     uint32_t nodeCount = 0;
     uint32_t maxDepth = 0;
     size_t deviceBytes = 0;
+    float worldMin[3] = {0, 0, 0}, worldMax[3] = {0, 0, 0}; // union of the objects' world AABBs
+    bool hasBounds = false;
     ~DeviceScene()
     {
         nodes.release(); tris.release(); shade.release();
@@ -108,6 +110,7 @@ struct Library
     sp_b200_Params params;
     bool statsEnabled = false;
     uint32_t pathsPerPass = 0; // 0: default (render_wavefront)
+    bool skyCulling = true;    // sp_b200_SetSkyCulling
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
@@ -204,6 +207,8 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     ds->triangleCount = fs.triangleCount;
     ds->nodeCount = (uint32_t)(fs.nodes.size() / 8);
     ds->maxDepth = fs.maxDepth;
+    for (int k = 0; k < 3; ++k) { ds->worldMin[k] = fs.worldMin[k]; ds->worldMax[k] = fs.worldMax[k]; }
+    ds->hasBounds = fs.objectCount > 0;
     ds->deviceBytes = (fs.nodes.size() + fs.tris.size() + fs.shade.size() + fs.objInv.size() +
                        fs.objModel.size()) * sizeof(v4f) + fs.objInfo.size() * sizeof(v4u);
     return ds;
@@ -359,17 +364,105 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
     return (DeviceScene *)accel->deviceScene;
 }
 
-// Wavefront render of args' rectangle.  The rectangle is cut into bands of whole 4-pixel block
+// Screen rectangle (pixels, half-open) outside which no camera ray of the frame can touch the
+// scene: the projection of the world bounds' corners through the camera of sp_ConfigureCamera /
+// sp_CalculateFilmPositions (simd_path_tracer.cpp:1-63), evaluated in double and padded by 4 pixels
+// + 1 % of its size -- three orders of magnitude more than the +-0.5/width-pixel jitter and any
+// float rounding of ray generation or intersection.  A ray outside it misses every triangle by that
+// margin, so its closest hit is "none" whatever the box tests say.  Returns false when the bounds
+// are not safely in front of the camera (then nothing is culled).
+struct PixelRect { uint32_t x0, y0, x1, y1; };
+bool scene_screen_rect(const RenderArgs &ra, PixelRect *rect)
+{
+    const DCamera &c = ra.camera;
+    if (!ra.hasBounds) { rect->x0 = rect->y0 = rect->x1 = rect->y1 = 0; return true; } // empty scene
+    double F[3] = {(double)c.filmCenter.x - c.position.x, (double)c.filmCenter.y - c.position.y,
+                   (double)c.filmCenter.z - c.position.z};
+    double dist = sqrt(F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+    if (!(dist > 0.0) || !(c.halfFilmWidth > 0.0f) || !(c.halfFilmHeight > 0.0f)) return false;
+    double fwd[3] = {F[0] / dist, F[1] / dist, F[2] / dist};
+    double extent = 0.0;
+    for (int k = 0; k < 3; ++k) extent += fabs((double)ra.boundsMax[k] - ra.boundsMin[k]);
+    double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
+    for (int corner = 0; corner < 8; ++corner)
+    {
+        double p[3] = {corner & 1 ? ra.boundsMax[0] : ra.boundsMin[0], corner & 2 ? ra.boundsMax[1] : ra.boundsMin[1],
+                       corner & 4 ? ra.boundsMax[2] : ra.boundsMin[2]};
+        double v[3] = {p[0] - c.position.x, p[1] - c.position.y, p[2] - c.position.z};
+        double depth = v[0] * fwd[0] + v[1] * fwd[1] + v[2] * fwd[2];
+        if (!(depth > 1e-3 * extent + 1e-6 * dist)) return false; // at or behind the camera plane
+        double lambda = depth / dist; // v = lambda * (filmPoint - position)
+        double a = (v[0] * c.right.x + v[1] * c.right.y + v[2] * c.right.z) / lambda;
+        double b = (v[0] * c.up.x + v[1] * c.up.y + v[2] * c.up.z) / lambda;
+        double fx = a / c.halfFilmWidth, fy = b / c.halfFilmHeight; // [-1, 1] across the film
+        double px = (fx + 1.0) * 0.5 * c.width;
+        double py = (1.0 - (fy + 1.0) * 0.5) * c.height;
+        if (!(px == px) || !(py == py)) return false;
+        if (px < minX) minX = px;
+        if (px > maxX) maxX = px;
+        if (py < minY) minY = py;
+        if (py > maxY) maxY = py;
+    }
+    double padX = 4.0 + 0.01 * (maxX - minX), padY = 4.0 + 0.01 * (maxY - minY);
+    minX = floor(minX - padX); maxX = ceil(maxX + padX);
+    minY = floor(minY - padY); maxY = ceil(maxY + padY);
+    auto clampu = [](double v, uint32_t hi) { return v < 0.0 ? 0u : (v > (double)hi ? hi : (uint32_t)v); };
+    rect->x0 = clampu(minX, c.width); rect->x1 = clampu(maxX, c.width);
+    rect->y0 = clampu(minY, c.height); rect->y1 = clampu(maxY, c.height);
+    return true;
+}
+
+// Wavefront render of args' rectangle.  Pixels outside the scene's screen rectangle go to the sky
+// kernel (one thread per pixel, no queues).  The rest is cut into bands of whole 4-pixel block
 // rows; a band is rendered in passes of S samples per pixel (all of them when they fit), each pass
 // a fixed sequence of kernels over device queues (spb_wavefront.cu).  Nothing is read back between
 // kernels.  Band height and S are chosen so that one pass keeps about 32 Mi paths in flight.
-void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
+// `traced` receives the rectangle that went through the queues (the rest are sky pixels: spp rays,
+// spp misses each).
+void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut, PixelRect *traced)
 {
     Library &L = lib();
-    const uint32_t width = ra.x1 - ra.x0, height = ra.y1 - ra.y0;
-    const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
     const uint32_t spp = ra.spp, bounces = ra.bounces;
+    KernelConfig cfg = kernel_config();
 
+    WaveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.scene = ra.scene;
+    a.materials = ra.materials;
+    a.camera = ra.camera;
+    a.spp = spp;
+    a.bounces = bounces;
+    a.frame = ra.frame;
+    a.clampValue = ra.clampValue;
+    a.out = ra.out;
+    a.stats = L.statsEnabled ? ra.counters : nullptr;
+    a.tileRowCost = ra.tileRowCost;
+    a.tileHeight = ra.tileHeight;
+    a.costRow0 = ra.y0 / (ra.tileHeight ? ra.tileHeight : 1);
+
+    // the part of the strip whose rays can reach the scene, grown to whole 8x4 pixel blocks
+    PixelRect w = {ra.x0, ra.y0, ra.x1, ra.y1};
+    PixelRect r;
+    if (L.skyCulling && scene_screen_rect(ra, &r))
+    {
+        uint32_t x0 = r.x0 > ra.x0 ? ra.x0 + (r.x0 - ra.x0) / 8 * 8 : ra.x0;
+        uint32_t y0 = r.y0 > ra.y0 ? ra.y0 + (r.y0 - ra.y0) / 4 * 4 : ra.y0;
+        uint32_t x1 = r.x1 < ra.x1 ? r.x1 : ra.x1, y1 = r.y1 < ra.y1 ? r.y1 : ra.y1;
+        if (x1 <= x0 || y1 <= y0) x0 = x1 = ra.x0, y0 = y1 = ra.y0; // nothing to trace
+        w.x0 = x0; w.y0 = y0; w.x1 = x1; w.y1 = y1;
+        if (!(w.x0 == ra.x0 && w.y0 == ra.y0 && w.x1 == ra.x1 && w.y1 == ra.y1))
+        {
+            a.x0 = ra.x0; a.y0 = ra.y0; a.x1 = ra.x1; a.y1 = ra.y1;
+            a.stripPixels = (ra.x1 - ra.x0) * (ra.y1 - ra.y0);
+            launch_sky(cfg, a, w.x0, w.y0, w.x1, w.y1, L.stream);
+        }
+    }
+    *traced = w;
+    countersOut.clear();
+    if (w.x1 <= w.x0 || w.y1 <= w.y0) return;
+
+    const uint32_t width = w.x1 - w.x0, height = w.y1 - w.y0;
+    const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
     const uint64_t targetItems = L.pathsPerPass ? L.pathsPerPass : (32u << 20);
     const uint64_t rowItems = (uint64_t)blocksX * 32; // items of one block row, one sample
     uint32_t S = L.params.samplesPerPass ? L.params.samplesPerPass : spp;
@@ -379,7 +472,9 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     uint32_t bandBlocksY = (uint32_t)(targetItems / (rowItems * S));
     if (bandBlocksY < 1) bandBlocksY = 1;
     if (bandBlocksY > blocksY) bandBlocksY = blocksY;
-    const uint32_t bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
+    uint32_t bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
+    bandBlocksY = (blocksY + bands - 1) / bands; // bands of equal height
+    bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
     const uint32_t passes = (spp + S - 1) / S;
     SPB_ASSERT(rowItems * bandBlocksY * S < 0xFFFFFFFFull);
     const uint32_t capacity = (uint32_t)(rowItems * bandBlocksY * S); // ray slots and path ids both fit
@@ -395,17 +490,9 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     L.wCtr.ensure(ctrWords * 4);
     SPB_CUDA(cudaMemsetAsync(L.wCtr.ptr, 0, ctrWords * 4, L.stream));
 
-    WaveArgs a;
-    a.scene = ra.scene;
-    a.materials = ra.materials;
-    a.camera = ra.camera;
-    a.x0 = ra.x0; a.x1 = ra.x1;
+    a.x0 = w.x0; a.x1 = w.x1;
     a.blocksX = blocksX;
-    a.spp = spp;
-    a.bounces = bounces;
-    a.frame = ra.frame;
     a.pathCapacity = capacity;
-    a.clampValue = ra.clampValue;
     a.rays[0] = (v4f *)L.wRays[0].ptr;
     a.rays[1] = (v4f *)L.wRays[1].ptr;
     a.hitRec = (v4f *)L.wHitRec.ptr;
@@ -413,20 +500,14 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut)
     a.missQ = (uint32_t *)L.wMissQ.ptr;
     a.pathTerms = (v4f *)L.wTerms.ptr;
     a.rad = (v4f *)L.wRad.ptr;
-    a.out = ra.out;
-    a.stats = L.statsEnabled ? ra.counters : nullptr;
-    a.tileRowCost = ra.tileRowCost;
-    a.tileHeight = ra.tileHeight;
-    a.costRow0 = ra.y0 / (ra.tileHeight ? ra.tileHeight : 1);
 
-    KernelConfig cfg = kernel_config();
     uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
     for (uint32_t band = 0; band < bands; ++band)
     {
         const uint32_t by0 = band * bandBlocksY;
         const uint32_t by1 = by0 + bandBlocksY < blocksY ? by0 + bandBlocksY : blocksY;
-        a.y0 = ra.y0 + by0 * 4;
-        a.y1 = ra.y0 + by1 * 4 < ra.y1 ? ra.y0 + by1 * 4 : ra.y1;
+        a.y0 = w.y0 + by0 * 4;
+        a.y1 = w.y0 + by1 * 4 < w.y1 ? w.y0 + by1 * 4 : w.y1;
         a.stripPixels = width * (a.y1 - a.y0);
         a.itemsPerSample = blocksX * (by1 - by0) * 32;
         for (uint32_t pass = 0; pass < passes; ++pass)
@@ -521,6 +602,7 @@ extern "C" void sp_b200_FlushTextureCache(void)
 }
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
+extern "C" void sp_b200_SetSkyCulling(int enable) { lib().skyCulling = enable != 0; }
 
 extern "C" u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame)
 {
@@ -1133,17 +1215,21 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     args.counters = ctr;
     args.tileRowCost = tileRowCost ? ctr + CTR_COUNT : nullptr;
     args.tileHeight = tileH;
+    for (int k = 0; k < 3; ++k) { args.boundsMin[k] = ds->worldMin[k]; args.boundsMax[k] = ds->worldMax[k]; }
+    args.hasBounds = ds->hasBounds ? 1 : 0;
     // the kernel tiles the rectangle from y0 in 16-row CTAs; keep CTA rows inside one tile row
     // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
     SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);
 
     std::vector<unsigned long long> c(CTR_COUNT + tileRows);
     std::vector<uint32_t> waveCounters;
+    PixelRect traced = {0, 0, 0, 0};
+    const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL;
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
-    if (L.params.renderMode == SP_B200_RENDER_PER_PIXEL)
+    if (!wavefront)
         launch_render(kernel_config(), args, L.stream);
     else
-        render_wavefront(args, waveCounters);
+        render_wavefront(args, waveCounters, &traced);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
 
@@ -1163,16 +1249,25 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     float kernelMs = 0, totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
     SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
-    if (!waveCounters.empty())
+    if (wavefront)
     {
         // queue lengths are the path counters: rays = rays entering each traversal, and every
-        // ray ends in exactly one of the hit / miss queues
+        // ray ends in exactly one of the hit / miss queues; a sky pixel is spp rays, spp misses
         unsigned long long rays = 0, hits = 0, misses = 0;
         for (size_t i = 0; i + WCTR_STRIDE <= waveCounters.size(); i += WCTR_STRIDE)
         {
             hits += waveCounters[i + WCTR_HITS];
             misses += waveCounters[i + WCTR_MISSES];
         }
+        const unsigned long long spp = L.params.samplesPerPixel;
+        const unsigned long long tracedW = traced.x1 - traced.x0;
+        misses += ((unsigned long long)(rowEnd - rowBegin) * cam.width - tracedW * (traced.y1 - traced.y0)) * spp;
+        if (tileRowCost)
+            for (u32 y = rowBegin; y < rowEnd; ++y)
+            {
+                unsigned long long sky = cam.width - (y >= traced.y0 && y < traced.y1 ? tracedW : 0);
+                c[CTR_COUNT + y / tileH - firstTileRow] += sky * spp * SPB_COST_MISS;
+            }
         rays = hits + misses;
         c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * L.params.samplesPerPixel;
         c[CTR_RAYS] = rays;

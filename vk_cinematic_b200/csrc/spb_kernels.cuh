@@ -35,6 +35,9 @@ struct RenderArgs
     unsigned long long *counters;     // CTR_COUNT slots
     unsigned long long *tileRowCost;  // may be null; rays per tile row, row 0 = y0 / tileHeight
     uint32_t tileHeight;
+    // host only: world bounds of everything in the scene (valid if hasBounds)
+    float boundsMin[3], boundsMax[3];
+    int hasBounds;
 };
 
 // number of kernels this library has launched since load (bench.py's gpu_launches)
@@ -144,5 +147,10 @@ void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t b
                        cudaStream_t stream);
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
 void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
+// Pixels of [x0,x1) x [y0,y1) OUTSIDE the rectangle [rx0,rx1) x [ry0,ry1): every sample's camera ray
+// leaves the scene untouched (the caller guarantees it), so the whole pixel is evaluated in one
+// thread: ray generation, background material, accumulation in sample order.
+void launch_sky(const KernelConfig &cfg, const WaveArgs &args, uint32_t rx0, uint32_t ry0, uint32_t rx1,
+                uint32_t ry1, cudaStream_t stream);
 
 } // namespace spb

@@ -416,6 +416,46 @@ k_accumulate(WaveArgs a)
     }
 }
 
+// Pixels whose camera rays cannot reach anything (outside the padded screen rectangle of the
+// scene's bounds, computed by the host): the sample loop of sp_PathTraceTile
+// (simd_path_tracer.cpp:216-321) with the miss branch only -- same functions, same order of
+// operations as k_trace<PRIMARY> + k_shade_miss + k_accumulate, without the queues in between.
+template <int MATH, int ENVFILTER>
+__global__ void __launch_bounds__(256)
+k_sky(WaveArgs a, uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1)
+{
+    const unsigned width = a.x1 - a.x0;
+    const float weight = 1.0f / (float)a.spp;
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.stripPixels; p += gridDim.x * blockDim.x)
+    {
+        unsigned ly = p / width, lx = p - ly * width;
+        unsigned x = a.x0 + lx, y = a.y0 + ly;
+        if (x >= rx0 && x < rx1 && y >= ry0 && y < ry1) continue;
+        uint32_t pixelIndex = x + y * a.camera.width;
+        f3 total = mk3(0.0f, 0.0f, 0.0f);
+        for (unsigned s = 0; s < a.spp; ++s)
+        {
+            uint32_t rng = stream_seed(pixelIndex, s, a.frame);
+            f3 o, d;
+            primary_ray(a.camera, x, y, rng, o, d);
+            f3 zero = mk3(0.0f, 0.0f, 0.0f);
+            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, neg3(d), 0.0f, 0.0f, &cnt);
+            f3 radiance = fold_radiance(vt, zero, a.clampValue);
+            total = add3(total, mul3(radiance, weight));
+        }
+        v4f out;
+        out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
+        a.out[(size_t)pixelIndex] = out;
+    }
+    if (a.stats)
+    {
+        unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
+        if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <bool CULL, bool STATS, bool PRIMARY>
 static void launch_trace_t(const WaveArgs &a, uint32_t bounce, unsigned grid, cudaStream_t stream)
@@ -487,6 +527,21 @@ void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t boun
     case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
     case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
     default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    }
+}
+
+void launch_sky(const KernelConfig &cfg, const WaveArgs &a, uint32_t rx0, uint32_t ry0, uint32_t rx1,
+                uint32_t ry1, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    unsigned grid = shade_grid();
+    int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
+    switch (key)
+    {
+    case 0: k_sky<0, 0><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
+    case 1: k_sky<0, 1><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
+    case 2: k_sky<1, 0><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
+    default: k_sky<1, 1><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
     }
 }
 
