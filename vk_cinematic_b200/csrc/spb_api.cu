@@ -479,11 +479,13 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut, 
     SPB_ASSERT(rowItems * bandBlocksY * S < 0xFFFFFFFFull);
     const uint32_t capacity = (uint32_t)(rowItems * bandBlocksY * S); // ray slots and path ids both fit
 
-    L.wRays[0].ensure((size_t)capacity * 32);
-    L.wRays[1].ensure((size_t)capacity * 32);
-    L.wHitRec.ensure((size_t)capacity * 16);
-    L.wHitQ.ensure((size_t)capacity * 4);
-    L.wMissQ.ensure((size_t)capacity * 4);
+    // queues and ray arrays carry slack for the partly filled chunks of the warps in flight
+    const size_t slots = (size_t)capacity + SPB_QUEUE_SLACK;
+    L.wRays[0].ensure(slots * 32);
+    L.wRays[1].ensure(slots * 32);
+    L.wHitRec.ensure(slots * 16);
+    L.wHitQ.ensure(slots * 4);
+    L.wMissQ.ensure(slots * 4);
     L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
     L.wRad.ensure((size_t)capacity * 16);
     const size_t ctrWords = (size_t)bands * passes * bounces * WCTR_STRIDE;
@@ -1256,8 +1258,8 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
         unsigned long long rays = 0, hits = 0, misses = 0;
         for (size_t i = 0; i + WCTR_STRIDE <= waveCounters.size(); i += WCTR_STRIDE)
         {
-            hits += waveCounters[i + WCTR_HITS];
-            misses += waveCounters[i + WCTR_MISSES];
+            hits += waveCounters[i + WCTR_NHITS];
+            misses += waveCounters[i + WCTR_NMISSES];
         }
         const unsigned long long spp = L.params.samplesPerPixel;
         const unsigned long long tracedW = traced.x1 - traced.x0;

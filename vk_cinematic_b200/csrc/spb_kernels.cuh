@@ -113,9 +113,18 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
 #endif
 
 // per-(pass, bounce) device counters
-// RAYS: rays queued for this bounce; HITS / MISSES: lengths of the hit / miss queues;
-// CURSOR: work hand-out position of the trace kernel
-enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_STRIDE };
+// RAYS: length of this bounce's ray queue (slots handed to the trace kernel; may contain holes);
+// HITS / MISSES: ALLOCATED lengths of the hit / miss queues -- warps reserve chunks of slots, so a
+// queue ends with up to one partly filled chunk per warp whose tail is holes (SPB_QUEUE_HOLE);
+// CURSOR: work hand-out position of the trace kernel; NHITS / NMISSES: exact counts.
+enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_NHITS, WCTR_NMISSES, WCTR_PAD0, WCTR_PAD1, WCTR_STRIDE };
+#define SPB_QUEUE_HOLE 0xFFFFFFFFu
+// largest chunk a warp reserves from a queue counter with one atomic
+#ifndef SPB_CHUNK_MAX
+#define SPB_CHUNK_MAX 128u
+#endif
+// extra slots every queue / ray array carries for partly filled chunks: warps in flight x chunk
+#define SPB_QUEUE_SLACK (8192u * SPB_CHUNK_MAX)
 
 struct WaveArgs
 {

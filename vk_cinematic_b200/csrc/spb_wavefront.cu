@@ -39,17 +39,43 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
-// Warp-aggregated queue append: one atomic per warp, returns this lane's slot (valid if `want`).
-__device__ __forceinline__ unsigned warp_append(uint32_t *counter, bool want)
+// Chunked reservation from a device counter.  Every warp keeps a private range [next, end) of the
+// counter's index space in shared memory (`ws`) and hands indices out of it; only when the range
+// runs dry does one lane reserve the next `chunk` indices with an atomic.  All warps of the grid
+// used to add to the same address once per retire / refill event (about 2 M same-address atomics
+// per 33 M-ray launch, serialised in L2); now it is one atomic per `chunk` indices.
+// `mask`: lanes that want an index (warp-uniform value); returns this lane's index if it is in mask.
+__device__ __forceinline__ unsigned chunk_take(uint32_t *counter, volatile unsigned *ws, unsigned mask,
+                                               unsigned chunk)
 {
-    unsigned mask = __ballot_sync(SPB_FULL, want);
-    if (!mask) return 0;
-    unsigned leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane_id() == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(SPB_FULL, base, leader);
-    return base + __popc(mask & lanemask_lt());
+    const unsigned n = __popc(mask), rank = __popc(mask & lanemask_lt());
+    const unsigned next = ws[0], end = ws[1];
+    const unsigned avail = end - next;
+    unsigned idx;
+    __syncwarp();
+    if (n <= avail)
+    {
+        idx = next + rank;
+        if (lane_id() == 0) ws[0] = next + n;
+    }
+    else
+    {
+        unsigned base = 0;
+        if (lane_id() == 0) base = atomicAdd(counter, chunk);
+        base = __shfl_sync(SPB_FULL, base, 0);
+        idx = rank < avail ? next + rank : base + (rank - avail);
+        if (lane_id() == 0)
+        {
+            ws[0] = base + (n - avail);
+            ws[1] = base + chunk;
+        }
+    }
+    __syncwarp();
+    return idx;
 }
+
+// slots of a warp's private state in shared memory
+enum { WS_CUR_NEXT = 0, WS_CUR_END, WS_HIT_NEXT, WS_HIT_END, WS_MISS_NEXT, WS_MISS_END, WS_NHITS, WS_NMISSES, WS_COUNT };
 
 __device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, uint32_t rng, uint32_t path)
 {
@@ -108,13 +134,20 @@ k_trace(WaveArgs a, uint32_t bounce)
     __shared__ unsigned slotAll[SPB_TRACE_THREADS];
     TravCold &cold = coldAll[threadIdx.x];
     unsigned &slot = slotAll[threadIdx.x];
+    __shared__ unsigned warpStateAll[SPB_TRACE_THREADS / 32][WS_COUNT];
+    volatile unsigned *ws = warpStateAll[threadIdx.x >> 5];
+    if (lane < WS_COUNT) ws[lane] = 0;
+    __syncwarp();
+    // chunk size: a quarter of an even share per warp, so small queues still spread over the GPU
+    unsigned chunk = (total / (gridDim.x * (SPB_TRACE_THREADS / 32)) / 4 + 31u) & ~31u;
+    chunk = chunk < 32u ? 32u : (chunk > SPB_CHUNK_MAX ? SPB_CHUNK_MAX : chunk);
     Counters cnt = {0, 0, 0, 0};
     Trav st;
     st.cur = SPB_NODE_DONE;
     cold.slow = 0;
     slot = 0;
     bool have = false;
-    bool exhausted = false; // warp-uniform: the queue has been handed out completely
+    bool exhausted = total == 0; // warp-uniform: this warp can get no more work from the queue
 
     for (;;)
     {
@@ -138,8 +171,15 @@ k_trace(WaveArgs a, uint32_t bounce)
             }
             const bool isHit = finished && h.t > 0.0f;
             const bool isMiss = finished && !isHit;
-            unsigned hs = warp_append(&ctr[WCTR_HITS], isHit);
-            unsigned ms = warp_append(&ctr[WCTR_MISSES], isMiss);
+            const unsigned hitMask = __ballot_sync(SPB_FULL, isHit), missMask = __ballot_sync(SPB_FULL, isMiss);
+            unsigned hs = 0, ms = 0;
+            if (hitMask) hs = chunk_take(&ctr[WCTR_HITS], ws + WS_HIT_NEXT, hitMask, chunk);
+            if (missMask) ms = chunk_take(&ctr[WCTR_MISSES], ws + WS_MISS_NEXT, missMask, chunk);
+            if (lane == 0)
+            {
+                ws[WS_NHITS] += __popc(hitMask);
+                ws[WS_NMISSES] += __popc(missMask);
+            }
             if (isHit)
             {
                 unsigned mySlot = slot;
@@ -158,11 +198,8 @@ k_trace(WaveArgs a, uint32_t bounce)
             unsigned need = __ballot_sync(SPB_FULL, !have);
             if (need)
             {
-                unsigned n = __popc(need), leader = __ffs(need) - 1, base = 0;
-                if (lane == leader) base = atomicAdd(cursor, n);
-                base = __shfl_sync(SPB_FULL, base, leader);
-                if (base + n >= total) exhausted = true;
-                unsigned idx = base + __popc(need & lanemask_lt());
+                unsigned idx = chunk_take(cursor, ws + WS_CUR_NEXT, need, chunk);
+                if (ws[WS_CUR_NEXT] >= total) exhausted = true; // chunks are handed out in order
                 if (!have && idx < total)
                 {
                     f3 o, d;
@@ -187,7 +224,9 @@ k_trace(WaveArgs a, uint32_t bounce)
                     }
                     else
                     {
-                        trav_world_ray(rays + (size_t)idx * 2, o, d);
+                        // a slot that stands for a hole of the hit queue it was made from
+                        valid = f2u(rays[(size_t)idx * 2 + 1].w) != SPB_QUEUE_HOLE;
+                        if (valid) trav_world_ray(rays + (size_t)idx * 2, o, d);
                     }
                     if (valid)
                     {
@@ -230,6 +269,16 @@ k_trace(WaveArgs a, uint32_t bounce)
         } while (walking && ((unsigned)__popc(walking) >= SPB_REFILL_THRESHOLD || exhausted));
     }
 
+
+    // holes: the unused tail of this warp's last chunk of either queue; exact counts
+    __syncwarp();
+    for (unsigned i = ws[WS_HIT_NEXT] + lane; i < ws[WS_HIT_END]; i += 32) a.hitQ[i] = SPB_QUEUE_HOLE;
+    for (unsigned i = ws[WS_MISS_NEXT] + lane; i < ws[WS_MISS_END]; i += 32) a.missQ[i] = SPB_QUEUE_HOLE;
+    if (lane == 0)
+    {
+        if (ws[WS_NHITS]) atomicAdd(&ctr[WCTR_NHITS], ws[WS_NHITS]);
+        if (ws[WS_NMISSES]) atomicAdd(&ctr[WCTR_NMISSES], ws[WS_NMISSES]);
+    }
 
     if (STATS)
     {
@@ -306,9 +355,10 @@ k_shade_miss(WaveArgs a, uint32_t bounce)
         unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
         bool active = i < total;
         uint32_t path = 0;
+        unsigned slot = active ? a.missQ[i] : SPB_QUEUE_HOLE;
+        active = slot != SPB_QUEUE_HOLE;
         if (active)
         {
-            unsigned slot = a.missQ[i];
             v4f rb = rays[(size_t)slot * 2 + 1];
             path = f2u(rb.w);
             f3 V = neg3(mk3(rb.x, rb.y, rb.z));
@@ -341,12 +391,13 @@ k_shade_hit(WaveArgs a, uint32_t bounce)
     for (unsigned k = 0; k < rounds; ++k)
     {
         unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool active = i < total;
+        const bool inQueue = i < total;
+        unsigned slot = inQueue ? a.hitQ[i] : SPB_QUEUE_HOLE;
+        bool active = slot != SPB_QUEUE_HOLE;
         f3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0);
-        uint32_t rng = 0, path = 0;
+        uint32_t rng = 0, path = SPB_QUEUE_HOLE;
         if (active)
         {
-            unsigned slot = a.hitQ[i];
             v4f ra = rays[(size_t)slot * 2 + 0], rb = rays[(size_t)slot * 2 + 1];
             v4f hr = a.hitRec[slot];
             f3 o = mk3(ra.x, ra.y, ra.z), d = mk3(rb.x, rb.y, rb.z);
@@ -372,13 +423,12 @@ k_shade_hit(WaveArgs a, uint32_t bounce)
                 nd = L;
             }
         }
-        if (!last)
-        {
-            unsigned dst = warp_append(&ctr[WCTR_STRIDE + WCTR_RAYS], active);
-            if (active) store_ray(nextRays, dst, no, nd, rng, path);
-        }
+        // the next bounce's ray queue is the hit queue, slot for slot (holes stay holes: path id
+        // SPB_QUEUE_HOLE), so no counter is touched here
+        if (!last && inQueue) store_ray(nextRays, i, no, nd, rng, path);
         count_row(a, path, active, SPB_COST_HIT);
     }
+    if (!last && blockIdx.x == 0 && threadIdx.x == 0) ctr[WCTR_STRIDE + WCTR_RAYS] = total;
     if (a.stats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
