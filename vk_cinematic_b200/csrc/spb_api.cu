@@ -207,6 +207,12 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     ds->triangleCount = fs.triangleCount;
     ds->nodeCount = (uint32_t)(fs.nodes.size() / 8);
     ds->maxDepth = fs.maxDepth;
+    // the trace kernel pushes without a bound check (spb_core.cuh trav_push)
+    if (fs.stackNeed + 2 > SPB_STACK_SIZE)
+    {
+        log_message("scene needs %u traversal stack entries, the kernels provide %u", fs.stackNeed + 2, SPB_STACK_SIZE);
+        abort();
+    }
     for (int k = 0; k < 3; ++k) { ds->worldMin[k] = fs.worldMin[k]; ds->worldMax[k] = fs.worldMax[k]; }
     ds->hasBounds = fs.objectCount > 0;
     ds->deviceBytes = (fs.nodes.size() + fs.tris.size() + fs.shade.size() + fs.objInv.size() +

@@ -268,7 +268,10 @@ uint32_t collapse(const Builder &b, Bvh4 &out)
         }
         node.meta[0] = n;
         node.meta[1] = it.depth;
-        uint32_t stackHere = it.stackBefore + (internalKids > 0 ? internalKids - 1 : 0);
+        // the resumable traversal (spb_core.cuh trav_node) pushes every child it does not continue
+        // with, primitives included: up to n - 1 entries per level
+        (void)internalKids;
+        uint32_t stackHere = it.stackBefore + (n > 0 ? n - 1 : 0);
         if (stackHere > worstStack) worstStack = stackHere;
         for (uint32_t k = 0; k < n; ++k)
         {
@@ -304,8 +307,9 @@ Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count)
     {
         b.balancedOnly = true;
         b.build(count);
-        collapse(b, out);
+        need = collapse(b, out);
     }
+    out.stackNeed = need;
     for (int a = 0; a < 3; ++a)
     {
         out.rootMin[a] = b.nodes[0].mn[a];

@@ -27,6 +27,7 @@ struct Bvh4
     std::vector<Node4> nodes;       // breadth-first order: the first nodes are the top levels
     std::vector<uint32_t> slotPrim; // leaf slot -> primitive index (slots in breadth-first order)
     uint32_t maxDepth = 0;
+    uint32_t stackNeed = 0; // worst-case traversal stack entries inside this tree
     float rootMin[3] = {0, 0, 0};
     float rootMax[3] = {0, 0, 0};
 };

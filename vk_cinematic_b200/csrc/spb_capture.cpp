@@ -104,6 +104,7 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
     FlatScene fs;
     struct Placed { uint32_t root, shadeBase; };
     std::map<const MeshAccel *, Placed> placed;
+    uint32_t meshStackNeed = 0;
 
     for (const ObjectInstance &ob : objects)
     {
@@ -136,6 +137,7 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
             fs.shade.push_back(mk4(v1.textureCoord.y, v2.textureCoord.x, v2.textureCoord.y, 0.0f));
         }
         p.root = append_tree(fs, mesh->bvh, triBase);
+        if (mesh->bvh.stackNeed > meshStackNeed) meshStackNeed = mesh->bvh.stackNeed;
         fs.triangleCount += mesh->triangleCount;
         placed[mesh] = p;
     }
@@ -177,6 +179,7 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
                 if (n.ref[k] != SPB_REF_EMPTY && (n.ref[k] & SPB_REF_LEAF))
                     n.ref[k] = SPB_REF_LEAF | tlas.slotPrim[n.ref[k] & ~SPB_REF_LEAF];
         fs.tlasRoot = append_tree(fs, tlas, 0);
+        fs.stackNeed = tlas.stackNeed + meshStackNeed;
     }
     // never hand the device a null array
     if (fs.nodes.empty()) fs.nodes.resize(8, mk4(0, 0, 0, 0));

@@ -16,9 +16,11 @@
 #if defined(__CUDACC__)
 #define SPB_HD __host__ __device__ __forceinline__
 #define SPB_ALIGN16 __align__(16)
+#define SPB_ALIGN8 __align__(8)
 #else
 #define SPB_HD inline
 #define SPB_ALIGN16 alignas(16)
+#define SPB_ALIGN8 alignas(8)
 #endif
 
 namespace spb {
@@ -601,7 +603,21 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
 #define SPB_NODE_EXIT 0xFFFFFFFDu
 
 // One stack entry: reference and entry distance together (one 8-byte local load per pop).
-struct TravEntry { uint32_t ref; float tnear; };
+struct SPB_ALIGN8 TravEntry { uint32_t ref; float tnear; };
+SPB_HD TravEntry load_entry(const TravEntry *p)
+{
+#if defined(__CUDA_ARCH__)
+    // both words at once, whether or not the entry turns out to be culled (volatile keeps the
+    // compiler from splitting it into a load of tnear and a dependent load of ref)
+    unsigned long long raw = *reinterpret_cast<const volatile unsigned long long *>(p);
+    TravEntry e;
+    e.ref = (uint32_t)raw;
+    e.tnear = __uint_as_float((uint32_t)(raw >> 32));
+    return e;
+#else
+    return *p;
+#endif
+}
 
 // Hot state: what every NODE / LEAF step touches.
 struct Trav
@@ -674,7 +690,7 @@ SPB_HD void trav_pop(Trav &st, const TravEntry *stack)
             return;
         }
         st.sp--;
-        TravEntry e = stack[st.sp];
+        TravEntry e = load_entry(stack + st.sp);
         if (CULL && !(e.tnear <= st.tcull)) continue;
         st.cur = e.ref;
         return;
@@ -713,16 +729,24 @@ SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, co
     trav_pop<CULL>(st, stack);
 }
 
+// No bound check: flatten_scene() refuses scenes whose worst-case stack use (three entries per
+// level of the TLAS plus three per level of the deepest mesh tree) exceeds SPB_STACK_SIZE.
 SPB_HD void trav_push(Trav &st, TravEntry *stack, uint32_t ref, float tnear)
 {
-    if (ref != SPB_REF_EMPTY && st.sp < SPB_STACK_SIZE)
-    {
-        TravEntry e;
-        e.ref = ref;
-        e.tnear = tnear;
-        stack[st.sp] = e;
-        st.sp++;
-    }
+    TravEntry e;
+    e.ref = ref;
+    e.tnear = tnear;
+    stack[st.sp] = e;
+    st.sp++;
+}
+
+// compare-exchange on (key, ref) with min/max on the keys (keys are never NaN)
+SPB_HD void sortx(float &ka, uint32_t &ra, float &kb, uint32_t &rb)
+{
+    bool swap = kb < ka;
+    float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
+    uint32_t rlo = swap ? rb : ra, rhi = swap ? ra : rb;
+    ka = lo; kb = hi; ra = rlo; rb = rhi;
 }
 
 // NODE step: st.cur is a node index.
@@ -745,10 +769,7 @@ SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *cou
     bool h1 = slab_fast(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, st.o, st.inv, tn1);
     bool h2 = slab_fast(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, st.o, st.inv, tn2);
     bool h3 = slab_fast(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, st.o, st.inv, tn3);
-    h0 = h0 && refs.x != SPB_REF_EMPTY;
-    h1 = h1 && refs.y != SPB_REF_EMPTY;
-    h2 = h2 && refs.z != SPB_REF_EMPTY;
-    h3 = h3 && refs.w != SPB_REF_EMPTY;
+    // an empty child slot carries a NaN box (spb_bvh.cpp collapse): tfar is NaN, the test fails
     if (CULL)
     {
         h0 = h0 && tn0 <= st.tcull;
@@ -756,31 +777,42 @@ SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *cou
         h2 = h2 && tn2 <= st.tcull;
         h3 = h3 && tn3 <= st.tcull;
     }
+    // a child that is not entered gets the key +inf (an entry distance of +inf cannot lead to a
+    // hit either); validity travels with the key, the refs are never rewritten
     float k0 = h0 ? tn0 : inf, k1 = h1 ? tn1 : inf, k2 = h2 ? tn2 : inf, k3 = h3 ? tn3 : inf;
-    uint32_t r0 = h0 ? refs.x : SPB_REF_EMPTY, r1 = h1 ? refs.y : SPB_REF_EMPTY;
-    uint32_t r2 = h2 ? refs.z : SPB_REF_EMPTY, r3 = h3 ? refs.w : SPB_REF_EMPTY;
+    uint32_t r0 = refs.x, r1 = refs.y, r2 = refs.z, r3 = refs.w;
     if (CULL)
     {
-        sort2(k0, r0, k1, r1);
-        sort2(k2, r2, k3, r3);
-        sort2(k0, r0, k2, r2);
-        sort2(k1, r1, k3, r3);
-        sort2(k1, r1, k2, r2);
+        // 5-exchange network, ascending by entry distance; +inf sinks
+        sortx(k0, r0, k1, r1);
+        sortx(k2, r2, k3, r3);
+        sortx(k0, r0, k2, r2);
+#if !defined(SPB_SORT_NEAREST_ONLY)
+        sortx(k1, r1, k3, r3);
+        sortx(k1, r1, k2, r2);
+#endif
     }
     else
     {
         // no distance order: keep child order, valid entries first
-        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
-        if (r1 == SPB_REF_EMPTY) { r1 = r2; r2 = SPB_REF_EMPTY; }
-        if (r2 == SPB_REF_EMPTY) { r2 = r3; r3 = SPB_REF_EMPTY; }
-        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
-        if (r1 == SPB_REF_EMPTY) { r1 = r2; r2 = SPB_REF_EMPTY; }
-        if (r0 == SPB_REF_EMPTY) { r0 = r1; r1 = SPB_REF_EMPTY; }
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
+        if (!(k1 < inf)) { k1 = k2; r1 = r2; k2 = inf; }
+        if (!(k2 < inf)) { k2 = k3; r2 = r3; k3 = inf; }
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
+        if (!(k1 < inf)) { k1 = k2; r1 = r2; k2 = inf; }
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
     }
-    trav_push(st, stack, r3, k3);
-    trav_push(st, stack, r2, k2);
-    trav_push(st, stack, r1, k1);
-    if (r0 != SPB_REF_EMPTY)
+#if defined(SPB_SORT_NEAREST_ONLY)
+    // (A/B knob) only the nearest child is exact; k2 is the nearer of the two pair minima
+    if (k3 < inf) trav_push(st, stack, r3, k3);
+    if (k1 < inf) trav_push(st, stack, r1, k1);
+    if (k2 < inf) trav_push(st, stack, r2, k2);
+#else
+    if (k3 < inf) trav_push(st, stack, r3, k3);
+    if (k2 < inf) trav_push(st, stack, r2, k2);
+    if (k1 < inf) trav_push(st, stack, r1, k1);
+#endif
+    if (k0 < inf)
     {
         st.cur = r0;
         return;

@@ -118,7 +118,7 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 // retired (hit record, hit/miss queue) and refilled from the ray queue.
 template <bool CULL, bool STATS, bool PRIMARY>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
-k_trace(WaveArgs a, uint32_t bounce)
+k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
     const unsigned lane = lane_id();
     uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
@@ -341,7 +341,7 @@ __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool
 
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
-k_shade_miss(WaveArgs a, uint32_t bounce)
+k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
     const uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
     const unsigned total = ctr[WCTR_MISSES];
@@ -377,7 +377,7 @@ k_shade_miss(WaveArgs a, uint32_t bounce)
 
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
-k_shade_hit(WaveArgs a, uint32_t bounce)
+k_shade_hit(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
     uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
     const unsigned total = ctr[WCTR_HITS];
@@ -438,7 +438,7 @@ k_shade_hit(WaveArgs a, uint32_t bounce)
 
 // total += radiance_s * (1 / spp), s in order (simd_path_tracer.cpp:216-321, 335-339)
 __global__ void __launch_bounds__(256)
-k_accumulate(WaveArgs a)
+k_accumulate(const __grid_constant__ WaveArgs a)
 {
     const unsigned width = a.x1 - a.x0;
     const float weight = 1.0f / (float)a.spp;
@@ -472,7 +472,7 @@ k_accumulate(WaveArgs a)
 // operations as k_trace<PRIMARY> + k_shade_miss + k_accumulate, without the queues in between.
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
-k_sky(WaveArgs a, uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1)
+k_sky(const __grid_constant__ WaveArgs a, uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1)
 {
     const unsigned width = a.x1 - a.x0;
     const float weight = 1.0f / (float)a.spp;
