@@ -42,6 +42,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RESULT_OUT = sys.stdout
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md "FALLBACK"
 
 
@@ -252,13 +253,25 @@ def run_reference_arm(args):
         r.close()
         out["reference_verbatim_3_bounces"] = {"value": int(m[2]) / t / 1e6, "unit": "Mrays/s",
                                                "kind": "reference", "cores": cores}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 
+def claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries print there too (NCCL's version
+    banner ignores NCCL_DEBUG_FILE).  Keep the real stdout for the result and point fd 1 at
+    stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse_args()
+    global RESULT_OUT
+    RESULT_OUT = claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -275,7 +288,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
+        # stdout carries exactly one JSON line: whatever NCCL_DEBUG asks for goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert sp.lib.sp_b200_Init(local) == 0
     stream = torch.cuda.current_stream()
@@ -307,6 +321,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    gather_ev = []
+
     def render_step(frame, bounds, want_cost=False):
         b, e = bounds[rank]
         m, cost = np.zeros(12, np.uint64), None
@@ -315,7 +331,11 @@ def main():
                                     want_cost=want_cost)
         st = sp.last_stats()
         if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
             strips.gather_strips(image, bounds, dist)
+            g1.record()
+            gather_ev.append((g0, g1))
         return m, cost, (st.kernelMs if e > b else 0.0)
 
     # ---- warm-up (also measures per-tile-row cost and re-cuts the strips)
@@ -323,20 +343,19 @@ def main():
     frame = 0
     for w in range(max(args.warmup, 3)):
         barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        m, cost, _ = render_step(frame, bounds, want_cost=True)
-        t1.record()
+        m, cost, kms = render_step(frame, bounds, want_cost=True)
         torch.cuda.synchronize()
         frame += 1
         if world > 1:
+            # seconds = this rank's own render time (CUDA events around its kernels), NOT the step
+            # time: the gather waits for the slowest rank and would hide the imbalance
             row_cost, _secs = strips.gather_row_costs(
-                cost if cost is not None else np.zeros(0), t0.elapsed_time(t1) * 1e-3, bounds, H, TH, dist, dev)
+                cost if cost is not None else np.zeros(0), kms * 1e-3, bounds, H, TH, dist, dev)
             bounds = strips.partition_rows(H, TH, world, row_cost)
 
     # ---- timed region: exactly K steps
     launches0 = sp.lib.sp_b200_KernelLaunchCount()
+    gather_ev.clear()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -358,7 +377,13 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     stat = torch.tensor([elapsed_ms, float(rays), float(launches), float(np.sum(kernel_ms))],
                         dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev])) if gather_ev else 0.0
+        mine = torch.tensor([float(np.mean(kernel_ms)), gather_ms, float(rays) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"kernel_ms": float(t[0]), "gather_ms": float(t[1]), "rays_per_step": float(t[2])} for t in allr]
         mx = stat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stat.clone()
@@ -385,7 +410,8 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": float(np.mean(kernel_ms)),
-                              "rays_per_step": rays / args.steps, "launches": int(launches), "strips": [list(map(int, b)) for b in bounds]}), flush=True)
+                              "rays_per_step": rays / args.steps, "launches": int(launches), "strips": [list(map(int, b)) for b in bounds],
+                              "ranks": per_rank}), file=RESULT_OUT, flush=True)
         r.close()
         if world > 1:
             dist.barrier()
@@ -463,9 +489,11 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "strips": [list(map(int, b)) for b in bounds],
         }
+        if per_rank is not None:
+            out["ranks"] = per_rank
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=RESULT_OUT, flush=True)
     r.close()
     if world > 1:
         dist.barrier()

@@ -1274,7 +1274,7 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
             for (u32 y = rowBegin; y < rowEnd; ++y)
             {
                 unsigned long long sky = cam.width - (y >= traced.y0 && y < traced.y1 ? tracedW : 0);
-                c[CTR_COUNT + y / tileH - firstTileRow] += sky * spp * SPB_COST_MISS;
+                c[CTR_COUNT + y / tileH - firstTileRow] += sky * spp * SPB_COST_SKY;
             }
         rays = hits + misses;
         c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * L.params.samplesPerPixel;

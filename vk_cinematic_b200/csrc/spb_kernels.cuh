@@ -103,9 +103,12 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
 #ifndef SPB_TRACE_MIN_BLOCKS
 #define SPB_TRACE_MIN_BLOCKS 5
 #endif
-// tile-row cost units (sp_b200_RenderRows tileRowCost): per escaped ray / per surface hit
-#define SPB_COST_MISS 1u
-#define SPB_COST_HIT 6u
+// tile-row cost units (sp_b200_RenderRows tileRowCost): per sky-kernel sample / escaped ray / surface hit
+// (measured on C3: a sky-kernel sample ~23 ps, an escaped ray through the queues ~85 ps, a surface
+// hit with everything it triggers ~450 ps)
+#define SPB_COST_SKY 1u
+#define SPB_COST_MISS 4u
+#define SPB_COST_HIT 20u
 // a warp keeps walking until fewer than this many of its lanes still have a node to visit,
 // then retires the finished lanes and refills them from the queue
 #ifndef SPB_REFILL_THRESHOLD
