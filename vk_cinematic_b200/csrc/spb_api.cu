@@ -99,6 +99,7 @@ struct TextureEntry
 {
     DeviceBuffer buffer;
     uint32_t width = 0, height = 0;
+    ~TextureEntry() { buffer.release(); }
 };
 
 struct Library
@@ -118,6 +119,9 @@ struct Library
     struct ExtraObject { sp_Mesh mesh; u32 material; spbh::M4 model, invModel; float mn[3], mx[3]; };
     std::map<sp_Scene *, std::vector<ExtraObject>> extraObjects;
     std::map<const float *, std::unique_ptr<TextureEntry>> textures;
+    // device allocations of flushed textures, reused by the next upload of the same size (a
+    // flush forgets contents, not memory: cudaMalloc/cudaFree of 128 MiB per frame is slow)
+    std::vector<std::unique_ptr<TextureEntry>> texturePool;
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
@@ -265,8 +269,16 @@ const v4f *device_texture(const HdrImage &image)
     auto it = L.textures.find(image.pixels);
     if (it != L.textures.end() && it->second->width == image.width && it->second->height == image.height)
         return (const v4f *)it->second->buffer.ptr;
-    auto entry = std::make_unique<TextureEntry>();
     size_t bytes = (size_t)image.width * image.height * 16;
+    std::unique_ptr<TextureEntry> entry;
+    for (size_t i = 0; i < L.texturePool.size(); ++i)
+        if (L.texturePool[i]->buffer.bytes >= bytes && L.texturePool[i]->buffer.bytes <= bytes + bytes / 2)
+        {
+            entry = std::move(L.texturePool[i]);
+            L.texturePool.erase(L.texturePool.begin() + i);
+            break;
+        }
+    if (!entry) entry = std::make_unique<TextureEntry>();
     entry->buffer.ensure(bytes);
     entry->width = image.width;
     entry->height = image.height;
@@ -570,6 +582,7 @@ extern "C" void sp_b200_Shutdown(void)
     L.meshes.clear();
     L.scenes.clear();
     L.textures.clear();
+    L.texturePool.clear();
     L.emptyScene.reset();
     L.image.release(); L.counters.release(); L.materials.release();
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
@@ -606,7 +619,9 @@ extern "C" void sp_b200_FlushTextureCache(void)
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     if (L.initialized) cudaDeviceSynchronize();
+    for (auto &t : L.textures) L.texturePool.push_back(std::move(t.second));
     L.textures.clear();
+    while (L.texturePool.size() > SPB_MAX_IMAGES) L.texturePool.erase(L.texturePool.begin());
 }
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
