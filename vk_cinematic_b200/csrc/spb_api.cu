@@ -80,9 +80,10 @@ struct DeviceBuffer
 struct DeviceScene
 {
     uint32_t magic = 0x4E435353u; // "SSCN"
-    DeviceBuffer nodes, tris, shade, objInv, objModel, objInfo;
+    DeviceBuffer nodes, tris, shade, objInv, objModel, objInfo, objTris;
     DScene d;
     uint64_t triangleCount = 0;
+    uint64_t instancedTriangles = 0;
     uint32_t nodeCount = 0;
     uint32_t maxDepth = 0;
     size_t deviceBytes = 0;
@@ -91,7 +92,7 @@ struct DeviceScene
     ~DeviceScene()
     {
         nodes.release(); tris.release(); shade.release();
-        objInv.release(); objModel.release(); objInfo.release();
+        objInv.release(); objModel.release(); objInfo.release(); objTris.release();
     }
 };
 
@@ -125,7 +126,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -199,6 +200,9 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     upload(ds->objInv, fs.objInv, L.stream);
     upload(ds->objModel, fs.objModel, L.stream);
     upload(ds->objInfo, fs.objInfo, L.stream);
+    std::vector<uint32_t> objTris = fs.objTris;
+    if (objTris.empty()) objTris.push_back(0);
+    upload(ds->objTris, objTris, L.stream);
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     ds->d.nodes = (const v4f *)ds->nodes.ptr;
     ds->d.tris = (const v4f *)ds->tris.ptr;
@@ -206,6 +210,8 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     ds->d.objInv = (const v4f *)ds->objInv.ptr;
     ds->d.objModel = (const v4f *)ds->objModel.ptr;
     ds->d.objInfo = (const v4u *)ds->objInfo.ptr;
+    ds->d.objTris = (const uint32_t *)ds->objTris.ptr;
+    ds->instancedTriangles = fs.instancedTriangles;
     ds->d.tlasRoot = fs.tlasRoot;
     ds->d.objectCount = fs.objectCount;
     ds->triangleCount = fs.triangleCount;
@@ -382,120 +388,69 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
     return (DeviceScene *)accel->deviceScene;
 }
 
-// Screen rectangle (pixels, half-open) outside which no camera ray of the frame can touch the
-// scene: the projection of the world bounds' corners through the camera of sp_ConfigureCamera /
-// sp_CalculateFilmPositions (simd_path_tracer.cpp:1-63), evaluated in double and padded by 4 pixels
-// + 1 % of its size -- three orders of magnitude more than the +-0.5/width-pixel jitter and any
-// float rounding of ray generation or intersection.  A ray outside it misses every triangle by that
-// margin, so its closest hit is "none" whatever the box tests say.  Returns false when the bounds
-// are not safely in front of the camera (then nothing is culled).
-struct PixelRect { uint32_t x0, y0, x1, y1; };
-bool scene_screen_rect(const RenderArgs &ra, PixelRect *rect)
-{
-    const DCamera &c = ra.camera;
-    if (!ra.hasBounds) { rect->x0 = rect->y0 = rect->x1 = rect->y1 = 0; return true; } // empty scene
-    double F[3] = {(double)c.filmCenter.x - c.position.x, (double)c.filmCenter.y - c.position.y,
-                   (double)c.filmCenter.z - c.position.z};
-    double dist = sqrt(F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
-    if (!(dist > 0.0) || !(c.halfFilmWidth > 0.0f) || !(c.halfFilmHeight > 0.0f)) return false;
-    double fwd[3] = {F[0] / dist, F[1] / dist, F[2] / dist};
-    double extent = 0.0;
-    for (int k = 0; k < 3; ++k) extent += fabs((double)ra.boundsMax[k] - ra.boundsMin[k]);
-    double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
-    for (int corner = 0; corner < 8; ++corner)
-    {
-        double p[3] = {corner & 1 ? ra.boundsMax[0] : ra.boundsMin[0], corner & 2 ? ra.boundsMax[1] : ra.boundsMin[1],
-                       corner & 4 ? ra.boundsMax[2] : ra.boundsMin[2]};
-        double v[3] = {p[0] - c.position.x, p[1] - c.position.y, p[2] - c.position.z};
-        double depth = v[0] * fwd[0] + v[1] * fwd[1] + v[2] * fwd[2];
-        if (!(depth > 1e-3 * extent + 1e-6 * dist)) return false; // at or behind the camera plane
-        double lambda = depth / dist; // v = lambda * (filmPoint - position)
-        double a = (v[0] * c.right.x + v[1] * c.right.y + v[2] * c.right.z) / lambda;
-        double b = (v[0] * c.up.x + v[1] * c.up.y + v[2] * c.up.z) / lambda;
-        double fx = a / c.halfFilmWidth, fy = b / c.halfFilmHeight; // [-1, 1] across the film
-        double px = (fx + 1.0) * 0.5 * c.width;
-        double py = (1.0 - (fy + 1.0) * 0.5) * c.height;
-        if (!(px == px) || !(py == py)) return false;
-        if (px < minX) minX = px;
-        if (px > maxX) maxX = px;
-        if (py < minY) minY = py;
-        if (py > maxY) maxY = py;
-    }
-    double padX = 4.0 + 0.01 * (maxX - minX), padY = 4.0 + 0.01 * (maxY - minY);
-    minX = floor(minX - padX); maxX = ceil(maxX + padX);
-    minY = floor(minY - padY); maxY = ceil(maxY + padY);
-    auto clampu = [](double v, uint32_t hi) { return v < 0.0 ? 0u : (v > (double)hi ? hi : (uint32_t)v); };
-    rect->x0 = clampu(minX, c.width); rect->x1 = clampu(maxX, c.width);
-    rect->y0 = clampu(minY, c.height); rect->y1 = clampu(maxY, c.height);
-    return true;
-}
-
-// Wavefront render of args' rectangle.  Pixels outside the scene's screen rectangle go to the sky
-// kernel (one thread per pixel, no queues).  The rest is cut into bands of whole 4-pixel block
-// rows; a band is rendered in passes of S samples per pixel (all of them when they fit), each pass
-// a fixed sequence of kernels over device queues (spb_wavefront.cu).  Nothing is read back between
-// kernels.  Band height and S are chosen so that one pass keeps about 32 Mi paths in flight.
-// `traced` receives the rectangle that went through the queues (the rest are sky pixels: spp rays,
-// spp misses each).
-void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut, PixelRect *traced)
+// Wavefront render of args' rectangle (the strip).  A coverage pass marks the 8x4 pixel blocks some
+// triangle may project into; the pixels of all other blocks go to the sky kernel (one thread per
+// pixel, no queues).  The covered blocks are rendered in bands of consecutive list entries, a band
+// in passes of S samples per pixel (all of them when they fit), each pass a fixed sequence of
+// kernels over device queues (spb_wavefront.cu).  One 4-byte read-back (the number of covered
+// blocks) sizes the bands; nothing else returns to the host between kernels.  Band size and S are
+// chosen so that one pass keeps about 32 Mi paths in flight.
+void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::vector<uint32_t> &countersOut)
 {
     Library &L = lib();
     const uint32_t spp = ra.spp, bounces = ra.bounces;
     KernelConfig cfg = kernel_config();
+    const uint32_t width = ra.x1 - ra.x0, height = ra.y1 - ra.y0;
+    const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
+    const uint32_t blocks = blocksX * blocksY;
 
     WaveArgs a;
     memset(&a, 0, sizeof(a));
     a.scene = ra.scene;
     a.materials = ra.materials;
     a.camera = ra.camera;
+    a.x0 = ra.x0; a.y0 = ra.y0; a.x1 = ra.x1; a.y1 = ra.y1;
+    a.blocksX = blocksX; a.blocksY = blocksY;
     a.spp = spp;
     a.bounces = bounces;
     a.frame = ra.frame;
     a.clampValue = ra.clampValue;
     a.out = ra.out;
-    a.stats = L.statsEnabled ? ra.counters : nullptr;
+    a.stats = ra.counters;
+    a.countStats = L.statsEnabled ? 1 : 0;
     a.tileRowCost = ra.tileRowCost;
     a.tileHeight = ra.tileHeight;
     a.costRow0 = ra.y0 / (ra.tileHeight ? ra.tileHeight : 1);
 
-    // the part of the strip whose rays can reach the scene, grown to whole 8x4 pixel blocks
-    PixelRect w = {ra.x0, ra.y0, ra.x1, ra.y1};
-    PixelRect r;
-    if (L.skyCulling && scene_screen_rect(ra, &r))
-    {
-        uint32_t x0 = r.x0 > ra.x0 ? ra.x0 + (r.x0 - ra.x0) / 8 * 8 : ra.x0;
-        uint32_t y0 = r.y0 > ra.y0 ? ra.y0 + (r.y0 - ra.y0) / 4 * 4 : ra.y0;
-        uint32_t x1 = r.x1 < ra.x1 ? r.x1 : ra.x1, y1 = r.y1 < ra.y1 ? r.y1 : ra.y1;
-        if (x1 <= x0 || y1 <= y0) x0 = x1 = ra.x0, y0 = y1 = ra.y0; // nothing to trace
-        w.x0 = x0; w.y0 = y0; w.x1 = x1; w.y1 = y1;
-        if (!(w.x0 == ra.x0 && w.y0 == ra.y0 && w.x1 == ra.x1 && w.y1 == ra.y1))
-        {
-            a.x0 = ra.x0; a.y0 = ra.y0; a.x1 = ra.x1; a.y1 = ra.y1;
-            a.stripPixels = (ra.x1 - ra.x0) * (ra.y1 - ra.y0);
-            launch_sky(cfg, a, w.x0, w.y0, w.x1, w.y1, L.stream);
-        }
-    }
-    *traced = w;
+    // coverage -> block mask + list (sky culling off: no triangle marks anything and the
+    // "everything" flag is raised instead)
+    L.wMask.ensure((size_t)blocks + 1);
+    L.wBlockList.ensure((size_t)blocks * 4 + 4);
+    uint32_t *listCount = (uint32_t *)L.wBlockList.ptr + blocks;
+    a.blockMask = (const uint8_t *)L.wMask.ptr;
+    launch_coverage(a, instancedTriangles, !L.skyCulling, (uint8_t *)L.wMask.ptr, (uint32_t *)L.wBlockList.ptr,
+                    listCount, L.stream);
+    launch_sky(cfg, a, L.stream);
+    uint32_t covered = 0;
+    SPB_CUDA(cudaMemcpyAsync(&covered, listCount, 4, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
     countersOut.clear();
-    if (w.x1 <= w.x0 || w.y1 <= w.y0) return;
+    if (covered == 0) return;
 
-    const uint32_t width = w.x1 - w.x0, height = w.y1 - w.y0;
-    const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
     const uint64_t targetItems = L.pathsPerPass ? L.pathsPerPass : (32u << 20);
-    const uint64_t rowItems = (uint64_t)blocksX * 32; // items of one block row, one sample
     uint32_t S = L.params.samplesPerPass ? L.params.samplesPerPass : spp;
     if (S > spp) S = spp;
-    if (rowItems * S > targetItems) S = (uint32_t)(targetItems / rowItems);
+    if (32ull * S > targetItems) S = (uint32_t)(targetItems / 32);
     if (S < 1) S = 1;
-    uint32_t bandBlocksY = (uint32_t)(targetItems / (rowItems * S));
-    if (bandBlocksY < 1) bandBlocksY = 1;
-    if (bandBlocksY > blocksY) bandBlocksY = blocksY;
-    uint32_t bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
-    bandBlocksY = (blocksY + bands - 1) / bands; // bands of equal height
-    bands = (blocksY + bandBlocksY - 1) / bandBlocksY;
+    uint32_t bandBlocks = (uint32_t)(targetItems / (32ull * S));
+    if (bandBlocks < 1) bandBlocks = 1;
+    if (bandBlocks > covered) bandBlocks = covered;
+    uint32_t bands = (covered + bandBlocks - 1) / bandBlocks;
+    bandBlocks = (covered + bands - 1) / bands; // bands of equal size
+    bands = (covered + bandBlocks - 1) / bandBlocks;
     const uint32_t passes = (spp + S - 1) / S;
-    SPB_ASSERT(rowItems * bandBlocksY * S < 0xFFFFFFFFull);
-    const uint32_t capacity = (uint32_t)(rowItems * bandBlocksY * S); // ray slots and path ids both fit
+    SPB_ASSERT(32ull * bandBlocks * S < 0xFFFFFFFFull - SPB_QUEUE_SLACK);
+    const uint32_t capacity = 32u * bandBlocks * S; // ray slots and path ids both fit
 
     // queues and ray arrays carry slack for the partly filled chunks of the warps in flight
     const size_t slots = (size_t)capacity + SPB_QUEUE_SLACK;
@@ -510,8 +465,6 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut, 
     L.wCtr.ensure(ctrWords * 4);
     SPB_CUDA(cudaMemsetAsync(L.wCtr.ptr, 0, ctrWords * 4, L.stream));
 
-    a.x0 = w.x0; a.x1 = w.x1;
-    a.blocksX = blocksX;
     a.pathCapacity = capacity;
     a.rays[0] = (v4f *)L.wRays[0].ptr;
     a.rays[1] = (v4f *)L.wRays[1].ptr;
@@ -524,17 +477,14 @@ void render_wavefront(const RenderArgs &ra, std::vector<uint32_t> &countersOut, 
     uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
     for (uint32_t band = 0; band < bands; ++band)
     {
-        const uint32_t by0 = band * bandBlocksY;
-        const uint32_t by1 = by0 + bandBlocksY < blocksY ? by0 + bandBlocksY : blocksY;
-        a.y0 = w.y0 + by0 * 4;
-        a.y1 = w.y0 + by1 * 4 < w.y1 ? w.y0 + by1 * 4 : w.y1;
-        a.stripPixels = width * (a.y1 - a.y0);
-        a.itemsPerSample = blocksX * (by1 - by0) * 32;
+        const uint32_t first = band * bandBlocks;
+        a.blockList = (const uint32_t *)L.wBlockList.ptr + first;
+        a.bandBlocks = first + bandBlocks <= covered ? bandBlocks : covered - first;
         for (uint32_t pass = 0; pass < passes; ++pass)
         {
             a.firstSample = pass * S;
             a.samplesThisPass = spp - a.firstSample < S ? spp - a.firstSample : S;
-            a.workItems = a.itemsPerSample * a.samplesThisPass;
+            a.workItems = a.bandBlocks * 32u * a.samplesThisPass;
             a.ctr = ctr;
             ctr += (size_t)bounces * WCTR_STRIDE;
             launch_wave_trace(cfg, a, 0, true, L.stream);
@@ -588,6 +538,7 @@ extern "C" void sp_b200_Shutdown(void)
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
+    L.wMask.release(); L.wBlockList.release();
     if (L.initialized)
     {
         cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
@@ -1246,13 +1197,12 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
 
     std::vector<unsigned long long> c(CTR_COUNT + tileRows);
     std::vector<uint32_t> waveCounters;
-    PixelRect traced = {0, 0, 0, 0};
     const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL;
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
     if (!wavefront)
         launch_render(kernel_config(), args, L.stream);
     else
-        render_wavefront(args, waveCounters, &traced);
+        render_wavefront(args, ds->instancedTriangles, waveCounters);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
 
@@ -1282,15 +1232,8 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
             hits += waveCounters[i + WCTR_NHITS];
             misses += waveCounters[i + WCTR_NMISSES];
         }
-        const unsigned long long spp = L.params.samplesPerPixel;
-        const unsigned long long tracedW = traced.x1 - traced.x0;
-        misses += ((unsigned long long)(rowEnd - rowBegin) * cam.width - tracedW * (traced.y1 - traced.y0)) * spp;
-        if (tileRowCost)
-            for (u32 y = rowBegin; y < rowEnd; ++y)
-            {
-                unsigned long long sky = cam.width - (y >= traced.y0 && y < traced.y1 ? tracedW : 0);
-                c[CTR_COUNT + y / tileH - firstTileRow] += sky * spp * SPB_COST_SKY;
-            }
+        // a sky-kernel pixel is spp rays, spp misses (its row cost was added on the device)
+        misses += c[CTR_SKY_PIXELS] * L.params.samplesPerPixel;
         rays = hits + misses;
         c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * L.params.samplesPerPixel;
         c[CTR_RAYS] = rays;

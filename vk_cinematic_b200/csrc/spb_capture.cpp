@@ -1,8 +1,12 @@
 // spb_capture.cpp -- see spb_capture.h
 #include "spb_capture.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+
+#define SPB_CAPTURE_ASSERT(c) do { if (!(c)) { fprintf(stderr, "spb_capture: assertion failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); abort(); } } while (0)
 
 namespace spb {
 
@@ -102,7 +106,7 @@ static uint32_t append_tree(FlatScene &fs, const Bvh4 &bvh, uint32_t leafBase)
 FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
 {
     FlatScene fs;
-    struct Placed { uint32_t root, shadeBase; };
+    struct Placed { uint32_t root, shadeBase, triBase, triCount; };
     std::map<const MeshAccel *, Placed> placed;
     uint32_t meshStackNeed = 0;
 
@@ -113,6 +117,8 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
         Placed p;
         uint32_t triBase = (uint32_t)(fs.tris.size() / 3);
         p.shadeBase = (uint32_t)(fs.shade.size() / 4);
+        p.triBase = triBase;
+        p.triCount = (uint32_t)mesh->bvh.slotPrim.size();
         // triangles in leaf-slot order (breadth-first, so neighbours in the tree are neighbours
         // in memory); w of the first vertex carries the triangle's index within its mesh
         for (uint32_t slot = 0; slot < mesh->bvh.slotPrim.size(); ++slot)
@@ -144,6 +150,21 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
 
     uint32_t count = (uint32_t)objects.size();
     fs.objectCount = count;
+    fs.objTris.assign((size_t)count * 2 + 1, 0u);
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        uint32_t n = 0;
+        if (objects[i].mesh)
+        {
+            const Placed &p = placed[objects[i].mesh.get()];
+            fs.objTris[i] = p.triBase;
+            n = p.triCount;
+        }
+        SPB_CAPTURE_ASSERT(fs.instancedTriangles + n < 0xFFFFFFFFull);
+        fs.objTris[count + i] = (uint32_t)fs.instancedTriangles;
+        fs.instancedTriangles += n;
+    }
+    fs.objTris[(size_t)count * 2] = (uint32_t)fs.instancedTriangles;
     std::vector<float> mn((size_t)count * 3), mx((size_t)count * 3);
     for (uint32_t i = 0; i < count; ++i)
     {

@@ -42,6 +42,10 @@ struct FlatScene
 {
     std::vector<v4f> nodes, tris, shade, objInv, objModel;
     std::vector<v4u> objInfo;
+    // per object: first triangle slot of its mesh, then objectCount + 1 prefix sums of the
+    // objects' triangle counts (DScene::objTris)
+    std::vector<uint32_t> objTris;
+    uint64_t instancedTriangles = 0;
     uint32_t tlasRoot = SPB_REF_EMPTY;
     uint32_t objectCount = 0;
     uint64_t triangleCount = 0;

@@ -242,6 +242,8 @@ struct DScene
     const v4f *objInv;     // 4 per object: inverse model matrix columns
     const v4f *objModel;   // 4 per object: model matrix columns
     const v4u *objInfo;    // x = mesh root node (or EMPTY), y = shade base, z = smooth flag, w = material
+    const uint32_t *objTris; // per object: first triangle slot of its mesh; then objectCount + 1 prefix
+                             // sums of the objects' triangle counts (coverage pass)
     uint32_t tlasRoot;     // node index or SPB_REF_EMPTY
     uint32_t objectCount;
 };

@@ -12,7 +12,7 @@ namespace spb {
 enum
 {
     CTR_PATHS = 0, CTR_RAYS, CTR_HITS, CTR_MISSES, CTR_NODE_VISITS, CTR_TRIANGLE_TESTS,
-    CTR_OBJECT_TESTS, CTR_ENV_CLAMPED, CTR_CLOCK_SUM, CTR_COUNT
+    CTR_OBJECT_TESTS, CTR_ENV_CLAMPED, CTR_CLOCK_SUM, CTR_SKY_PIXELS, CTR_COUNT
 };
 
 struct KernelConfig
@@ -134,11 +134,15 @@ struct WaveArgs
     DScene scene;
     const DMaterials *materials;
     DCamera camera;
-    uint32_t x0, y0, x1, y1;   // pixel rectangle of the band this pass renders
-    uint32_t stripPixels;      // (x1 - x0) * (y1 - y0)
-    uint32_t blocksX;          // 8x4 pixel blocks per row of the band
-    uint32_t itemsPerSample;   // blocksX * blocksY * 32 (pixels of the band incl. block padding)
-    uint32_t workItems;        // itemsPerSample * samplesThisPass; item = pixel * samplesThisPass + sample
+    uint32_t x0, y0, x1, y1;   // pixel rectangle of the strip being rendered
+    uint32_t blocksX, blocksY; // 8x4 pixel blocks of the strip
+    // Blocks that some triangle may project into (coverage pass), in row-major order; the pass at
+    // hand renders bandBlocks of them starting at blockList[0].  Pixels of the other blocks are
+    // the sky kernel's.
+    const uint32_t *blockList;
+    const uint8_t *blockMask;  // per block of the strip: 1 = in the list
+    uint32_t bandBlocks;
+    uint32_t workItems;        // bandBlocks * 32 * samplesThisPass; item = (block, pixel in block, sample)
     uint32_t samplesThisPass, firstSample, spp, bounces, frame;
     uint32_t pathCapacity;     // paths per pass the per-path arrays are sized for
     float clampValue;
@@ -146,23 +150,29 @@ struct WaveArgs
     v4f *hitRec;               // per ray slot: t, triangle slot bits, object index bits, -
     uint32_t *hitQ, *missQ;    // compact lists of ray slots
     v4f *pathTerms;            // [bounce][path] two float4: (E, cosine) (W, -)
-    v4f *rad;                  // [path]: pixel-major (8x4-block order), samplesThisPass per pixel
+    v4f *rad;                  // [path]: block-major, pixel in block, samplesThisPass per pixel
     v4f *out;                  // full image
     uint32_t *ctr;             // this pass's counters: bounces x WCTR_STRIDE
-    unsigned long long *stats; // CTR_* slots, may be null
+    unsigned long long *stats; // CTR_* slots (always valid; node/triangle counts only in stats launches)
     unsigned long long *tileRowCost; // may be null
     uint32_t tileHeight;
     uint32_t costRow0;         // tile row that tileRowCost[0] stands for
+    int countStats;            // 1: stats launch
 };
 
+// Coverage pass: marks every 8x4 pixel block of the strip that the (2-pixel padded) screen bounding
+// box of some triangle touches; coverage[blocks] = 1 flags "everything" (a triangle straddles the
+// camera plane).  Then the marked blocks are listed in row-major order; listCount[0] = how many.
+void launch_coverage(const WaveArgs &args, uint64_t instancedTriangles, bool everything, uint8_t *coverage,
+                     uint32_t *blockList, uint32_t *listCount, cudaStream_t stream);
 void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,
                        cudaStream_t stream);
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
 void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
-// Pixels of [x0,x1) x [y0,y1) OUTSIDE the rectangle [rx0,rx1) x [ry0,ry1): every sample's camera ray
-// leaves the scene untouched (the caller guarantees it), so the whole pixel is evaluated in one
-// thread: ray generation, background material, accumulation in sample order.
-void launch_sky(const KernelConfig &cfg, const WaveArgs &args, uint32_t rx0, uint32_t ry0, uint32_t rx1,
-                uint32_t ry1, cudaStream_t stream);
+// Pixels of the strip whose block is not in the list: every sample's camera ray leaves the scene
+// untouched, so the whole pixel is evaluated in one thread: ray generation, background material,
+// accumulation in sample order.  Adds the pixels it shaded to stats[CTR_SKY_PIXELS] and their cost
+// to tileRowCost.
+void launch_sky(const KernelConfig &cfg, const WaveArgs &args, cudaStream_t stream);
 
 } // namespace spb

@@ -86,15 +86,15 @@ __device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, 
     rays[(size_t)slot * 2 + 1] = b;
 }
 
-// Primary work item / path id -> pixel and sample-in-pass.  Items enumerate the band's pixels in
-// 8x4-block order (block row-major, then row-major inside the block), samplesThisPass consecutive
-// items per pixel.  Pixels past the band's edge (block padding) are holes.
+// Primary work item / path id -> pixel and sample-in-pass.  Items enumerate the pass's blocks (a
+// slice of the strip's covered-block list), the 32 pixels of a block row-major, samplesThisPass
+// consecutive items per pixel.  Pixels past the strip's edge (block padding) are holes.
 __device__ __forceinline__ void item_pixel(const WaveArgs &a, unsigned item, unsigned &x, unsigned &y,
                                            unsigned &sLocal)
 {
     unsigned pi = item / a.samplesThisPass;
     sLocal = item - pi * a.samplesThisPass;
-    unsigned block = pi >> 5, l = pi & 31u;
+    unsigned block = __ldg(a.blockList + (pi >> 5)), l = pi & 31u;
     unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
     x = a.x0 + bx * 8 + (l & 7u);
     y = a.y0 + by * 4 + (l >> 3);
@@ -331,9 +331,13 @@ __device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms
 __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active, unsigned weight)
 {
     if (!a.tileRowCost) return;
-    unsigned x, y, sLocal;
-    item_pixel(a, path, x, y, sLocal);
-    unsigned row = active ? (y / a.tileHeight - a.costRow0) : 0xFFFFFFFFu;
+    unsigned row = 0xFFFFFFFFu;
+    if (active) // (an inactive lane's path id may be a hole: not a valid index into the block list)
+    {
+        unsigned x, y, sLocal;
+        item_pixel(a, path, x, y, sLocal);
+        row = y / a.tileHeight - a.costRow0;
+    }
     unsigned peers = __match_any_sync(SPB_FULL, row);
     if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
         atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
@@ -368,7 +372,7 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
         }
         count_row(a, path, active, SPB_COST_MISS);
     }
-    if (a.stats)
+    if (a.countStats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
         if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
@@ -429,7 +433,7 @@ k_shade_hit(const __grid_constant__ WaveArgs a, uint32_t bounce)
         count_row(a, path, active, SPB_COST_HIT);
     }
     if (!last && blockIdx.x == 0 && threadIdx.x == 0) ctr[WCTR_STRIDE + WCTR_RAYS] = total;
-    if (a.stats)
+    if (a.countStats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
         if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
@@ -440,14 +444,15 @@ k_shade_hit(const __grid_constant__ WaveArgs a, uint32_t bounce)
 __global__ void __launch_bounds__(256)
 k_accumulate(const __grid_constant__ WaveArgs a)
 {
-    const unsigned width = a.x1 - a.x0;
     const float weight = 1.0f / (float)a.spp;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.stripPixels; p += gridDim.x * blockDim.x)
+    const unsigned pixels = a.bandBlocks * 32u;
+    for (unsigned pi = blockIdx.x * blockDim.x + threadIdx.x; pi < pixels; pi += gridDim.x * blockDim.x)
     {
-        unsigned ly = p / width, lx = p - ly * width;
-        size_t pixel = (size_t)(a.x0 + lx) + (size_t)(a.y0 + ly) * a.camera.width;
-        // position of the pixel in 8x4-block order (item_pixel's inverse)
-        unsigned pi = ((ly >> 2) * a.blocksX + (lx >> 3)) * 32u + (ly & 3u) * 8u + (lx & 7u);
+        unsigned block = __ldg(a.blockList + (pi >> 5)), l = pi & 31u;
+        unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
+        unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
+        if (x >= a.x1 || y >= a.y1) continue;
+        size_t pixel = (size_t)x + (size_t)y * a.camera.width;
         const v4f *rad = a.rad + (size_t)pi * a.samplesThisPass;
         f3 total = mk3(0.0f, 0.0f, 0.0f);
         if (a.firstSample != 0)
@@ -466,40 +471,155 @@ k_accumulate(const __grid_constant__ WaveArgs a)
     }
 }
 
-// Pixels whose camera rays cannot reach anything (outside the padded screen rectangle of the
-// scene's bounds, computed by the host): the sample loop of sp_PathTraceTile
+// ---------------------------------------------------------------------------------------------
+// Coverage pass.  One thread per instanced triangle: object-space vertices -> world (model
+// matrix) -> film (sp_CalculateFilmPositions inverted, simd_path_tracer.cpp:38-63) in double; the
+// pixel bounding box of the three projections, padded by 2 pixels, marks the 8x4 blocks it touches.
+// The padding is four orders of magnitude above the jitter (+-0.5/width of a pixel,
+// simd_path_tracer.cpp:222-226) and any rounding of ray generation, so a camera ray through an
+// unmarked block misses every triangle with a margin no float intersection test can bridge: its
+// closest hit is "none", whatever the box tests on the way would have said.
+__global__ void __launch_bounds__(256)
+k_cover(const __grid_constant__ WaveArgs a, unsigned long long triangles, uint8_t *coverage)
+{
+    const DCamera &c = a.camera;
+    const double Fx = (double)c.filmCenter.x - c.position.x, Fy = (double)c.filmCenter.y - c.position.y,
+                 Fz = (double)c.filmCenter.z - c.position.z;
+    const double dist = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+    const uint32_t *first = a.scene.objTris, *prefix = a.scene.objTris + a.scene.objectCount;
+    const unsigned blocks = a.blocksX * a.blocksY;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < triangles;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        // object of this instanced triangle: last prefix entry <= i
+        unsigned lo = 0, hi = a.scene.objectCount;
+        while (hi - lo > 1)
+        {
+            unsigned mid = (lo + hi) >> 1;
+            if (prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const unsigned object = lo;
+        const size_t slot = (size_t)first[object] + (size_t)(i - prefix[object]);
+        const v4f *tp = a.scene.tris + slot * 3;
+        const v4f *mp = a.scene.objModel + (size_t)object * 4;
+        const v4f m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+        double px[3], py[3], depthMin = 1e300, depthMax = -1e300, scale = 0.0;
+        for (int k = 0; k < 3; ++k)
+        {
+            v4f v = tp[k];
+            double wx = (double)m0.x * v.x + (double)m1.x * v.y + (double)m2.x * v.z + m3.x - c.position.x;
+            double wy = (double)m0.y * v.x + (double)m1.y * v.y + (double)m2.y * v.z + m3.y - c.position.y;
+            double wz = (double)m0.z * v.x + (double)m1.z * v.y + (double)m2.z * v.z + m3.z - c.position.z;
+            double depth = (wx * Fx + wy * Fy + wz * Fz) / dist;
+            double lambda = depth / dist; // w = lambda * (film point - camera position)
+            double fa = (wx * c.right.x + wy * c.right.y + wz * c.right.z) / lambda / c.halfFilmWidth;
+            double fb = (wx * c.up.x + wy * c.up.y + wz * c.up.z) / lambda / c.halfFilmHeight;
+            px[k] = (fa + 1.0) * 0.5 * c.width;
+            py[k] = (1.0 - (fb + 1.0) * 0.5) * c.height;
+            depthMin = fmin(depthMin, depth);
+            depthMax = fmax(depthMax, depth);
+            scale = fmax(scale, fabs(wx) + fabs(wy) + fabs(wz));
+        }
+        if (!(depthMax > 0.0)) continue; // entirely behind the camera plane: no camera ray goes there
+        if (!(depthMin > 1e-6 * scale) || !(dist > 0.0))
+        {
+            coverage[blocks] = 1; // reaches the camera plane: its projection is unbounded
+            continue;
+        }
+        double xlo = fmin(px[0], fmin(px[1], px[2])) - 2.0, xhi = fmax(px[0], fmax(px[1], px[2])) + 2.0;
+        double ylo = fmin(py[0], fmin(py[1], py[2])) - 2.0, yhi = fmax(py[0], fmax(py[1], py[2])) + 2.0;
+        if (!(xlo == xlo) || !(xhi == xhi) || !(ylo == ylo) || !(yhi == yhi)) { coverage[blocks] = 1; continue; }
+        if (xhi < (double)a.x0 || yhi < (double)a.y0 || xlo >= (double)a.x1 || ylo >= (double)a.y1) continue;
+        unsigned bx0 = xlo <= (double)a.x0 ? 0u : ((unsigned)xlo - a.x0) >> 3;
+        unsigned by0 = ylo <= (double)a.y0 ? 0u : ((unsigned)ylo - a.y0) >> 2;
+        unsigned bx1 = xhi >= (double)(a.x1 - 1) ? a.blocksX - 1 : ((unsigned)xhi - a.x0) >> 3;
+        unsigned by1 = yhi >= (double)(a.y1 - 1) ? a.blocksY - 1 : ((unsigned)yhi - a.y0) >> 2;
+        for (unsigned by = by0; by <= by1; ++by)
+            for (unsigned bx = bx0; bx <= bx1; ++bx) coverage[by * a.blocksX + bx] = 1;
+    }
+}
+
+// Row-major list of the marked blocks (one CTA: a chunked prefix sum); coverage[] becomes the
+// final mask (the "everything" flag folded in).
+__global__ void __launch_bounds__(1024)
+k_list_blocks(unsigned blocks, uint8_t *coverage, uint32_t *blockList, uint32_t *listCount)
+{
+    __shared__ unsigned sums[1024];
+    const bool all = coverage[blocks] != 0;
+    const unsigned per = (blocks + 1023u) / 1024u;
+    const unsigned b0 = threadIdx.x * per, b1 = b0 + per < blocks ? b0 + per : blocks;
+    unsigned n = 0;
+    for (unsigned b = b0; b < b1; ++b)
+    {
+        if (all) coverage[b] = 1;
+        n += coverage[b] != 0;
+    }
+    sums[threadIdx.x] = n;
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1)
+    {
+        unsigned v = threadIdx.x >= d ? sums[threadIdx.x - d] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned at = sums[threadIdx.x] - n;
+    for (unsigned b = b0; b < b1; ++b)
+        if (coverage[b]) blockList[at++] = b;
+    if (threadIdx.x == 1023) listCount[0] = sums[1023];
+}
+
+// Pixels whose block is not covered: the sample loop of sp_PathTraceTile
 // (simd_path_tracer.cpp:216-321) with the miss branch only -- same functions, same order of
 // operations as k_trace<PRIMARY> + k_shade_miss + k_accumulate, without the queues in between.
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
-k_sky(const __grid_constant__ WaveArgs a, uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1)
+k_sky(const __grid_constant__ WaveArgs a)
 {
-    const unsigned width = a.x1 - a.x0;
     const float weight = 1.0f / (float)a.spp;
     const DMaterials &M = *a.materials;
     Counters cnt = {0, 0, 0, 0};
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.stripPixels; p += gridDim.x * blockDim.x)
+    unsigned shaded = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned rounds = (a.blocksX * a.blocksY * 32u + stride - 1) / stride;
+    for (unsigned k = 0; k < rounds; ++k)
     {
-        unsigned ly = p / width, lx = p - ly * width;
-        unsigned x = a.x0 + lx, y = a.y0 + ly;
-        if (x >= rx0 && x < rx1 && y >= ry0 && y < ry1) continue;
-        uint32_t pixelIndex = x + y * a.camera.width;
-        f3 total = mk3(0.0f, 0.0f, 0.0f);
-        for (unsigned s = 0; s < a.spp; ++s)
+        // 8 x 4 pixel blocks per warp, like the block mask
+        unsigned p = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned blk = p >> 5, l = p & 31u;
+        unsigned by = blk / a.blocksX, bx = blk - by * a.blocksX;
+        unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
+        bool active = blk < a.blocksX * a.blocksY && x < a.x1 && y < a.y1 && a.blockMask[blk] == 0;
+        if (active)
         {
-            uint32_t rng = stream_seed(pixelIndex, s, a.frame);
-            f3 o, d;
-            primary_ray(a.camera, x, y, rng, o, d);
-            f3 zero = mk3(0.0f, 0.0f, 0.0f);
-            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, neg3(d), 0.0f, 0.0f, &cnt);
-            f3 radiance = fold_radiance(vt, zero, a.clampValue);
-            total = add3(total, mul3(radiance, weight));
+            uint32_t pixelIndex = x + y * a.camera.width;
+            f3 total = mk3(0.0f, 0.0f, 0.0f);
+            for (unsigned s = 0; s < a.spp; ++s)
+            {
+                uint32_t rng = stream_seed(pixelIndex, s, a.frame);
+                f3 o, d;
+                primary_ray(a.camera, x, y, rng, o, d);
+                f3 zero = mk3(0.0f, 0.0f, 0.0f);
+                VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, neg3(d), 0.0f, 0.0f, &cnt);
+                f3 radiance = fold_radiance(vt, zero, a.clampValue);
+                total = add3(total, mul3(radiance, weight));
+            }
+            v4f out;
+            out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
+            a.out[(size_t)pixelIndex] = out;
+            shaded++;
         }
-        v4f out;
-        out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
-        a.out[(size_t)pixelIndex] = out;
+        if (a.tileRowCost)
+        {
+            unsigned row = active ? (y / a.tileHeight - a.costRow0) : 0xFFFFFFFFu;
+            unsigned peers = __match_any_sync(SPB_FULL, row);
+            if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * a.spp * SPB_COST_SKY);
+        }
     }
-    if (a.stats)
+    shaded = __reduce_add_sync(SPB_FULL, shaded);
+    if (lane_id() == 0 && shaded) atomicAdd(&a.stats[CTR_SKY_PIXELS], (unsigned long long)shaded);
+    if (a.countStats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
         if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
@@ -580,19 +700,34 @@ void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t boun
     }
 }
 
-void launch_sky(const KernelConfig &cfg, const WaveArgs &a, uint32_t rx0, uint32_t ry0, uint32_t rx1,
-                uint32_t ry1, cudaStream_t stream)
+void launch_sky(const KernelConfig &cfg, const WaveArgs &a, cudaStream_t stream)
 {
     g_kernelLaunches++;
     unsigned grid = shade_grid();
     int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
     switch (key)
     {
-    case 0: k_sky<0, 0><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
-    case 1: k_sky<0, 1><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
-    case 2: k_sky<1, 0><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
-    default: k_sky<1, 1><<<grid, 256, 0, stream>>>(a, rx0, ry0, rx1, ry1); break;
+    case 0: k_sky<0, 0><<<grid, 256, 0, stream>>>(a); break;
+    case 1: k_sky<0, 1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: k_sky<1, 0><<<grid, 256, 0, stream>>>(a); break;
+    default: k_sky<1, 1><<<grid, 256, 0, stream>>>(a); break;
     }
+}
+
+void launch_coverage(const WaveArgs &a, uint64_t instancedTriangles, bool everything, uint8_t *coverage,
+                     uint32_t *blockList, uint32_t *listCount, cudaStream_t stream)
+{
+    g_kernelLaunches += everything ? 1 : 2;
+    const unsigned blocks = a.blocksX * a.blocksY;
+    cudaMemsetAsync(coverage, 0, (size_t)blocks + 1, stream);
+    if (everything) cudaMemsetAsync(coverage + blocks, 1, 1, stream);
+    else if (instancedTriangles)
+    {
+        unsigned long long want = (instancedTriangles + 255) / 256;
+        unsigned grid = (unsigned)(want < (unsigned long long)shade_grid() * 4 ? want : (unsigned long long)shade_grid() * 4);
+        k_cover<<<grid, 256, 0, stream>>>(a, instancedTriangles, coverage);
+    }
+    k_list_blocks<<<1, 1024, 0, stream>>>(blocks, coverage, blockList, listCount);
 }
 
 void launch_wave_accumulate(const WaveArgs &a, cudaStream_t stream)
