@@ -9,6 +9,10 @@
 
 #include "spb_core.cuh"
 
+#ifndef SPB_SWEEP_LIMIT
+#define SPB_SWEEP_LIMIT 8192u
+#endif
+
 namespace spb {
 
 namespace {
@@ -51,10 +55,64 @@ struct Builder
         }
     }
 
+    // Exact SAH for small ranges: sort by centroid on each axis and sweep every split position.
+    // Returns the split position or 0 when no axis separates the centroids.
+    uint32_t sweep_split(uint32_t first, uint32_t count)
+    {
+        std::vector<uint32_t> best, cur(order.begin() + first, order.begin() + first + count);
+        std::vector<float> rightArea(count);
+        float bestCost = INFINITY;
+        uint32_t bestPos = 0;
+        for (int axis = 0; axis < 3; ++axis)
+        {
+            std::sort(cur.begin(), cur.end(), [&](uint32_t a, uint32_t b) {
+                float ca = centroid[(size_t)a * 3 + axis], cb = centroid[(size_t)b * 3 + axis];
+                return ca < cb || (ca == cb && a < b);
+            });
+            if (!(centroid[(size_t)cur.front() * 3 + axis] < centroid[(size_t)cur.back() * 3 + axis])) continue;
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (uint32_t i = count - 1; i > 0; --i)
+            {
+                for (int a = 0; a < 3; ++a)
+                {
+                    mn[a] = std::min(mn[a], aabbMin[(size_t)cur[i] * 3 + a]);
+                    mx[a] = std::max(mx[a], aabbMax[(size_t)cur[i] * 3 + a]);
+                }
+                rightArea[i] = half_area(mn, mx);
+            }
+            for (int a = 0; a < 3; ++a) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+            bool improved = false;
+            for (uint32_t i = 1; i < count; ++i)
+            {
+                for (int a = 0; a < 3; ++a)
+                {
+                    mn[a] = std::min(mn[a], aabbMin[(size_t)cur[i - 1] * 3 + a]);
+                    mx[a] = std::max(mx[a], aabbMax[(size_t)cur[i - 1] * 3 + a]);
+                }
+                float cost = half_area(mn, mx) * (float)i + rightArea[i] * (float)(count - i);
+                if (cost < bestCost)
+                {
+                    bestCost = cost;
+                    bestPos = i;
+                    improved = true;
+                }
+            }
+            if (improved) best = cur;
+        }
+        if (bestPos == 0) return 0;
+        std::copy(best.begin(), best.end(), order.begin() + first);
+        return first + bestPos;
+    }
+
     // Returns the split position (first index of the right half) after partitioning `order`.
     uint32_t split(uint32_t first, uint32_t count, const float *nodeMin, const float *nodeMax)
     {
         const int BINS = 16;
+        if (!balancedOnly && count > 2 && count <= SPB_SWEEP_LIMIT)
+        {
+            uint32_t pos = sweep_split(first, count);
+            if (pos) return pos;
+        }
         uint32_t mid = first + count / 2;
         float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (uint32_t i = first; i < first + count; ++i)
@@ -197,9 +255,74 @@ struct Builder
     }
 };
 
-// Greedy collapse in breadth-first order.  Returns the worst-case traversal stack depth.
+// Which binary subtrees become the (up to four) children of each 4-wide node, chosen to minimise
+// the summed surface area of the 4-wide nodes (the expected number of node visits of a random
+// ray) by dynamic programming over the binary tree -- the construction of Ylitie, Karras and
+// Laine, "Efficient incoherent ray traversal on GPUs through compressed wide BVHs" (HPG 2017),
+// section 4.1, for width 4 and single-primitive leaves:
+//   C(n, 1) = area(n) + min over k of C(left, k) + C(right, 4 - k)      n roots a 4-wide node
+//   C(n, i) = min(C(n, i - 1), min over k of C(left, k) + C(right, i - k))   n is dissolved into i roots
+//   C(leaf, i) = 0
+struct WideDp
+{
+    const Builder &b;
+    std::vector<float> cost;    // [node][i - 1], i = 1..3
+    std::vector<uint8_t> pick;  // [node][j - 2], j = 2..4: k of the best distribution for j roots
+    explicit WideDp(const Builder &builder) : b(builder)
+    {
+        size_t n = b.nodes.size();
+        cost.assign(n * 3, 0.0f);
+        pick.assign(n * 3, 1);
+        // children are created after their parent (nodes.push_back in build()): reverse index
+        // order is a post-order
+        for (size_t idx = n; idx-- > 0;)
+        {
+            const BNode &nd = b.nodes[idx];
+            if (nd.count <= 1) continue;
+            const float *cl = &cost[(size_t)nd.left * 3], *cr = &cost[(size_t)nd.right * 3];
+            float dist[5];
+            for (int j = 2; j <= 4; ++j)
+            {
+                float best = INFINITY;
+                int bestK = 1;
+                for (int k = 1; k < j; ++k)
+                {
+                    if (k > 3 || j - k > 3) continue;
+                    float c = cl[k - 1] + cr[j - k - 1];
+                    if (c < best) { best = c; bestK = k; }
+                }
+                dist[j] = best;
+                pick[idx * 3 + (j - 2)] = (uint8_t)bestK;
+            }
+            float a = half_area(nd.mn, nd.mx);
+            if (!(a >= 0.0f)) a = 0.0f;
+            cost[idx * 3 + 0] = a + dist[4];
+            cost[idx * 3 + 1] = std::min(dist[2], cost[idx * 3 + 0]);
+            cost[idx * 3 + 2] = std::min(dist[3], cost[idx * 3 + 1]);
+        }
+    }
+    // the roots that represent subtree `n` when it may use up to `j` child slots
+    void gather(uint32_t n, int j, uint32_t *kids, uint32_t &count) const
+    {
+        const BNode &nd = b.nodes[n];
+        if (nd.count <= 1 || j <= 1) { kids[count++] = n; return; }
+        if (j <= 3)
+        {
+            // C(n, j) = min(dist[j], C(n, j - 1)): prefer fewer roots on ties
+            float distJ = cost[(size_t)nd.left * 3 + pick[(size_t)n * 3 + (j - 2)] - 1] +
+                          cost[(size_t)nd.right * 3 + (j - pick[(size_t)n * 3 + (j - 2)]) - 1];
+            if (!(distJ < cost[(size_t)n * 3 + (j - 2)])) { gather(n, j - 1, kids, count); return; }
+        }
+        int k = pick[(size_t)n * 3 + (j - 2)];
+        gather(nd.left, k, kids, count);
+        gather(nd.right, j - k, kids, count);
+    }
+};
+
+// Collapse in breadth-first order.  Returns the worst-case traversal stack depth.
 uint32_t collapse(const Builder &b, Bvh4 &out)
 {
+    WideDp dp(b);
     out.nodes.clear();
     out.slotPrim.clear();
     out.maxDepth = 0;
@@ -221,6 +344,7 @@ uint32_t collapse(const Builder &b, Bvh4 &out)
         }
         else
         {
+#if defined(SPB_GREEDY_COLLAPSE)
             kids[n++] = bn.left;
             kids[n++] = bn.right;
             while (n < 4)
@@ -240,6 +364,11 @@ uint32_t collapse(const Builder &b, Bvh4 &out)
                 kids[pick] = b.nodes[expand].left;
                 kids[n++] = b.nodes[expand].right;
             }
+#else
+            int k = dp.pick[(size_t)it.bnode * 3 + 2];
+            dp.gather(bn.left, k, kids, n);
+            dp.gather(bn.right, 4 - k, kids, n);
+#endif
         }
         Node4 node;
         memset(&node, 0, sizeof(node));
