@@ -63,6 +63,8 @@ def parse_args():
                          "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
+    ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
+    ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
     ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -312,6 +314,10 @@ def main():
                   renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
     if args.paths_per_pass:
         sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
+    if args.no_ray_sorting:
+        sp.lib.sp_b200_SetRaySorting(0)
+    if args.refill:
+        sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
     TH = 64
     image = torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev)
 

@@ -261,6 +261,14 @@ void sp_b200_SetPathsPerPass(u32 paths);
  * evaluated by a queue-less kernel (their rays cannot hit anything).  On by default; results do
  * not depend on it. */
 void sp_b200_SetSkyCulling(int enable);
+/* Wavefront mode: the rays leaving the primary hits of a tile of 2048 paths are written in
+ * direction order, so a warp of the trace kernel walks rays with neighbouring origins and similar
+ * directions.  On by default; results do not depend on it. */
+void sp_b200_SetRaySorting(int enable);
+/* Wavefront mode tuning: a warp of the trace kernel retires and refills its lanes when fewer than
+ * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
+ * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */
+void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
 /* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
 u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
 

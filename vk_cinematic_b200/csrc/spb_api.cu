@@ -113,6 +113,24 @@ struct Library
     bool statsEnabled = false;
     uint32_t pathsPerPass = 0; // 0: default (render_wavefront)
     bool skyCulling = true;    // sp_b200_SetSkyCulling
+    bool sortBounceRays = true; // sp_b200_SetRaySorting
+    // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
+    // 0 for the sorted class = measured choice between packet mode (1) and SPB_REFILL_THRESHOLD:
+    // packets win when a tile's sorted rays are coherent (C3: one 8x4 block, 64 spp: -6 % frame
+    // time), and lose on scenes of sub-pixel triangles (C5: +11 %).
+    uint32_t refillThreshold[3] = {1, 0, SPB_REFILL_THRESHOLD};
+    struct SortedTuner
+    {
+        unsigned long long signature = 0;
+        double ms[2] = {0, 0}, rays[2] = {0, 0};
+        int samples[2] = {0, 0};
+        int choice = -1;       // index into candidates, -1 while measuring
+        unsigned frames = 0;
+        // this frame's measurements: candidate, pass (index into the wave counters), events
+        struct Probe { int candidate; size_t ctrIndex; cudaEvent_t e0, e1; };
+        std::vector<Probe> probes;
+        std::vector<cudaEvent_t> pool;
+    } tuner;
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
@@ -126,7 +144,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -461,6 +479,9 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     L.wMissQ.ensure(slots * 4);
     L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
     L.wRad.ensure((size_t)capacity * 16);
+    a.sortPrimaryHits = (bounces > 1 && L.sortBounceRays) ? 1 : 0;
+    if (a.sortPrimaryHits) L.wStage.ensure(slots * 32);
+    a.stage = (v4f *)L.wStage.ptr;
     const size_t ctrWords = (size_t)bands * passes * bounces * WCTR_STRIDE;
     L.wCtr.ensure(ctrWords * 4);
     SPB_CUDA(cudaMemsetAsync(L.wCtr.ptr, 0, ctrWords * 4, L.stream));
@@ -474,7 +495,25 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.pathTerms = (v4f *)L.wTerms.ptr;
     a.rad = (v4f *)L.wRad.ptr;
 
+    // sorted-class refill threshold: fixed, chosen earlier, or being measured (alternating
+    // candidates over the passes of the first frames, timed with events around the bounce-1 trace)
+    static const uint32_t kCandidates[2] = {1u, SPB_REFILL_THRESHOLD};
+    Library::SortedTuner &tn = L.tuner;
+    const unsigned long long signature = instancedTriangles * 1000003ull + ra.scene.objectCount * 10007ull +
+                                         (unsigned long long)spp * 101ull + S * 7ull + bounces + ((unsigned long long)width << 40);
+    if (signature != tn.signature)
+    {
+        tn.signature = signature;
+        tn.ms[0] = tn.ms[1] = tn.rays[0] = tn.rays[1] = 0.0;
+        tn.samples[0] = tn.samples[1] = 0;
+        tn.choice = -1;
+        tn.frames = 0;
+    }
+    tn.probes.clear();
+    const bool tuning = a.sortPrimaryHits && L.refillThreshold[1] == 0 && tn.choice < 0;
+
     uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
+    uint32_t passIndex = 0;
     for (uint32_t band = 0; band < bands; ++band)
     {
         const uint32_t first = band * bandBlocks;
@@ -486,13 +525,42 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             a.samplesThisPass = spp - a.firstSample < S ? spp - a.firstSample : S;
             a.workItems = a.bandBlocks * 32u * a.samplesThisPass;
             a.ctr = ctr;
+            const size_t ctrIndex = (size_t)(ctr - (uint32_t *)L.wCtr.ptr);
             ctr += (size_t)bounces * WCTR_STRIDE;
+            a.refillThreshold = L.refillThreshold[0];
             launch_wave_trace(cfg, a, 0, true, L.stream);
             for (uint32_t b = 0; b < bounces; ++b)
             {
-                launch_wave_shade(cfg, a, b, L.stream);
-                if (b + 1 < bounces) launch_wave_trace(cfg, a, b + 1, false, L.stream);
+                const bool sortedNext = b == 0 && a.sortPrimaryHits;
+                if (sortedNext) launch_wave_shade_primary_sorted(cfg, a, L.stream);
+                else launch_wave_shade(cfg, a, b, L.stream);
+                if (b + 1 >= bounces) break;
+                int probe = -1;
+                if (!sortedNext) a.refillThreshold = L.refillThreshold[2];
+                else if (L.refillThreshold[1]) a.refillThreshold = L.refillThreshold[1];
+                else if (tn.choice >= 0) a.refillThreshold = kCandidates[tn.choice];
+                else
+                {
+                    probe = (int)((passIndex + tn.frames) & 1u);
+                    a.refillThreshold = kCandidates[probe];
+                }
+                if (probe >= 0 && tuning && tn.probes.size() < 8)
+                {
+                    while (tn.pool.size() < 16)
+                    {
+                        cudaEvent_t e;
+                        SPB_CUDA(cudaEventCreate(&e));
+                        tn.pool.push_back(e);
+                    }
+                    Library::SortedTuner::Probe pr = {probe, ctrIndex, tn.pool[tn.probes.size() * 2], tn.pool[tn.probes.size() * 2 + 1]};
+                    SPB_CUDA(cudaEventRecord(pr.e0, L.stream));
+                    launch_wave_trace(cfg, a, b + 1, false, L.stream);
+                    SPB_CUDA(cudaEventRecord(pr.e1, L.stream));
+                    tn.probes.push_back(pr);
+                }
+                else launch_wave_trace(cfg, a, b + 1, false, L.stream);
             }
+            passIndex++;
             launch_wave_accumulate(a, L.stream);
         }
     }
@@ -538,7 +606,11 @@ extern "C" void sp_b200_Shutdown(void)
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
-    L.wMask.release(); L.wBlockList.release();
+    L.wMask.release(); L.wBlockList.release(); L.wStage.release();
+    for (cudaEvent_t e : L.tuner.pool) cudaEventDestroy(e);
+    L.tuner.pool.clear();
+    L.tuner.probes.clear();
+    L.tuner.signature = 0;
     if (L.initialized)
     {
         cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
@@ -577,6 +649,14 @@ extern "C" void sp_b200_FlushTextureCache(void)
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
 extern "C" void sp_b200_SetSkyCulling(int enable) { lib().skyCulling = enable != 0; }
+extern "C" void sp_b200_SetRaySorting(int enable) { lib().sortBounceRays = enable != 0; }
+extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
+{
+    Library &L = lib();
+    L.refillThreshold[0] = primary ? primary : 1;
+    L.refillThreshold[1] = sorted; // 0: measured
+    L.refillThreshold[2] = other ? other : SPB_REFILL_THRESHOLD;
+}
 
 extern "C" u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame)
 {
@@ -1222,6 +1302,26 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     float kernelMs = 0, totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
     SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    if (wavefront && !L.tuner.probes.empty())
+    {
+        // measurements of the sorted-class refill threshold (render_wavefront): ms per ray of the
+        // bounce-1 trace launches that were timed; decide once both candidates have been seen
+        Library::SortedTuner &tn = L.tuner;
+        for (const Library::SortedTuner::Probe &pr : tn.probes)
+        {
+            float ms = 0.0f;
+            SPB_CUDA(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
+            double rays = pr.ctrIndex + WCTR_NHITS < waveCounters.size() ? (double)waveCounters[pr.ctrIndex + WCTR_NHITS] : 0.0;
+            if (rays < 1.0) continue;
+            tn.ms[pr.candidate] += ms;
+            tn.rays[pr.candidate] += rays;
+            tn.samples[pr.candidate]++;
+        }
+        tn.probes.clear();
+        tn.frames++;
+        if (tn.samples[0] >= 2 && tn.samples[1] >= 2)
+            tn.choice = tn.ms[0] / tn.rays[0] <= tn.ms[1] / tn.rays[1] ? 0 : 1;
+    }
     if (wavefront)
     {
         // queue lengths are the path counters: rays = rays entering each traversal, and every

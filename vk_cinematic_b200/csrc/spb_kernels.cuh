@@ -124,7 +124,7 @@ enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_NHITS, WCTR_NMIS
 #define SPB_QUEUE_HOLE 0xFFFFFFFFu
 // largest chunk a warp reserves from a queue counter with one atomic
 #ifndef SPB_CHUNK_MAX
-#define SPB_CHUNK_MAX 128u
+#define SPB_CHUNK_MAX 64u
 #endif
 // extra slots every queue / ray array carries for partly filled chunks: warps in flight x chunk
 #define SPB_QUEUE_SLACK (8192u * SPB_CHUNK_MAX)
@@ -158,7 +158,18 @@ struct WaveArgs
     uint32_t tileHeight;
     uint32_t costRow0;         // tile row that tileRowCost[0] stands for
     int countStats;            // 1: stats launch
+    // Primary hits shaded tile by tile (SPB_SORT_TILE items) with the bounce rays of a tile written
+    // in direction order: the primary trace kernel leaves its results in hitRec by item instead of
+    // a hit queue, `stage` holds the unsorted rays of a tile between the two phases.
+    int sortPrimaryHits;
+    v4f *stage;
+    // a warp of the trace kernel retires and refills its lanes when fewer than this many are still
+    // walking: 1 = packet mode (the whole warp starts and ends together; best when its rays are
+    // coherent), SPB_REFILL_THRESHOLD otherwise.  Set per launch by the host.
+    uint32_t refillThreshold;
 };
+// items (pixel x sample, block-major) whose bounce rays are ordered together
+#define SPB_SORT_TILE 2048u
 
 // Coverage pass: marks every 8x4 pixel block of the strip that the (2-pixel padded) screen bounding
 // box of some triangle touches; coverage[blocks] = 1 flags "everything" (a triangle straddles the
@@ -168,6 +179,8 @@ void launch_coverage(const WaveArgs &args, uint64_t instancedTriangles, bool eve
 void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,
                        cudaStream_t stream);
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
+// bounce 0 with sortPrimaryHits: k_shade_miss + the tile kernel
+void launch_wave_shade_primary_sorted(const KernelConfig &cfg, const WaveArgs &args, cudaStream_t stream);
 void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
 // Pixels of the strip whose block is not in the list: every sample's camera ray leaves the scene
 // untouched, so the whole pixel is evaluated in one thread: ray generation, background material,

@@ -77,6 +77,13 @@ __device__ __forceinline__ unsigned chunk_take(uint32_t *counter, volatile unsig
 // slots of a warp's private state in shared memory
 enum { WS_CUR_NEXT = 0, WS_CUR_END, WS_HIT_NEXT, WS_HIT_END, WS_MISS_NEXT, WS_MISS_END, WS_NHITS, WS_NMISSES, WS_COUNT };
 
+__device__ __forceinline__ v4f mk4f(float x, float y, float z, float w)
+{
+    v4f r;
+    r.x = x; r.y = y; r.z = z; r.w = w;
+    return r;
+}
+
 __device__ __forceinline__ void store_ray(v4f *rays, unsigned slot, f3 o, f3 d, uint32_t rng, uint32_t path)
 {
     v4f a, b;
@@ -172,8 +179,10 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             const bool isHit = finished && h.t > 0.0f;
             const bool isMiss = finished && !isHit;
             const unsigned hitMask = __ballot_sync(SPB_FULL, isHit), missMask = __ballot_sync(SPB_FULL, isMiss);
+            // primary hits of a sorted pass are found through hitRec[item], not through a queue
+            const bool queueHits = !(PRIMARY && a.sortPrimaryHits);
             unsigned hs = 0, ms = 0;
-            if (hitMask) hs = chunk_take(&ctr[WCTR_HITS], ws + WS_HIT_NEXT, hitMask, chunk);
+            if (hitMask && queueHits) hs = chunk_take(&ctr[WCTR_HITS], ws + WS_HIT_NEXT, hitMask, chunk);
             if (missMask) ms = chunk_take(&ctr[WCTR_MISSES], ws + WS_MISS_NEXT, missMask, chunk);
             if (lane == 0)
             {
@@ -186,9 +195,13 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                 v4f r;
                 r.x = h.t; r.y = u2f(h.slot); r.z = u2f((uint32_t)h.object); r.w = 0.0f;
                 a.hitRec[mySlot] = r;
-                a.hitQ[hs] = mySlot;
+                if (queueHits) a.hitQ[hs] = mySlot;
             }
-            if (isMiss) a.missQ[ms] = slot;
+            if (isMiss)
+            {
+                a.missQ[ms] = slot;
+                if (!queueHits) a.hitRec[slot] = mk4f(-1.0f, 0.0f, 0.0f, 0.0f);
+            }
             if (finished) have = false;
         }
 
@@ -221,6 +234,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                             primary_ray(a.camera, x, y, rng, o, d);
                             store_ray(rays, idx, o, d, rng, idx); // path id == primary item
                         }
+                        else if (a.sortPrimaryHits) a.hitRec[idx] = mk4f(-1.0f, 0.0f, 0.0f, 0.0f);
                     }
                     else
                     {
@@ -266,7 +280,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                     trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
-        } while (walking && ((unsigned)__popc(walking) >= SPB_REFILL_THRESHOLD || exhausted));
+        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || exhausted));
     }
 
 
@@ -379,6 +393,40 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
     }
 }
 
+// One surface hit (simd_path_tracer.cpp:262-300): barycentrics, surface attributes, hemisphere
+// sample and BSDF terms; on the last bounce the path is folded back, otherwise its vertex terms
+// are stored and the next ray returned.
+template <int MATH, int ENVFILTER>
+__device__ __forceinline__ void shade_hit_one(const WaveArgs &a, const DMaterials &M, const v4f *rays, uint32_t bounce,
+                                              unsigned slot, bool last, Counters &cnt, f3 &no, f3 &nd,
+                                              uint32_t &rng, uint32_t &path)
+{
+    v4f ra = rays[(size_t)slot * 2 + 0], rb = rays[(size_t)slot * 2 + 1];
+    v4f hr = a.hitRec[slot];
+    f3 o = mk3(ra.x, ra.y, ra.z), d = mk3(rb.x, rb.y, rb.z);
+    rng = f2u(ra.w);
+    path = f2u(rb.w);
+    Hit hit;
+    hit.t = hr.x; hit.slot = f2u(hr.y); hit.object = (int32_t)f2u(hr.z);
+    hit_barycentrics(a.scene, o, d, hit);
+    // simd_path_tracer.cpp:268-289
+    Surface sf = resolve_hit(a.scene, hit);
+    f3 V = neg3(d);
+    f3 P = add3(o, mul3(d, hit.t));
+    f3 L = random_hemisphere<MATH>(sf.normal, rng);
+    VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, sf.material, L, sf.normal, V, sf.uvx, sf.uvy, &cnt);
+    if (last)
+    {
+        finish_path(a, vt, bounce, path);
+    }
+    else
+    {
+        store_terms(a.pathTerms, (size_t)bounce * a.pathCapacity + path, vt);
+        no = add3(P, mul3(sf.normal, 0.0001f));
+        nd = L;
+    }
+}
+
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_shade_hit(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -400,39 +448,127 @@ k_shade_hit(const __grid_constant__ WaveArgs a, uint32_t bounce)
         bool active = slot != SPB_QUEUE_HOLE;
         f3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0);
         uint32_t rng = 0, path = SPB_QUEUE_HOLE;
-        if (active)
-        {
-            v4f ra = rays[(size_t)slot * 2 + 0], rb = rays[(size_t)slot * 2 + 1];
-            v4f hr = a.hitRec[slot];
-            f3 o = mk3(ra.x, ra.y, ra.z), d = mk3(rb.x, rb.y, rb.z);
-            rng = f2u(ra.w);
-            path = f2u(rb.w);
-            Hit hit;
-            hit.t = hr.x; hit.slot = f2u(hr.y); hit.object = (int32_t)f2u(hr.z);
-            hit_barycentrics(a.scene, o, d, hit);
-            // simd_path_tracer.cpp:268-289
-            Surface sf = resolve_hit(a.scene, hit);
-            f3 V = neg3(d);
-            f3 P = add3(o, mul3(d, hit.t));
-            f3 L = random_hemisphere<MATH>(sf.normal, rng);
-            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, sf.material, L, sf.normal, V, sf.uvx, sf.uvy, &cnt);
-            if (last)
-            {
-                finish_path(a, vt, bounce, path);
-            }
-            else
-            {
-                store_terms(a.pathTerms, (size_t)bounce * a.pathCapacity + path, vt);
-                no = add3(P, mul3(sf.normal, 0.0001f));
-                nd = L;
-            }
-        }
+        if (active) shade_hit_one<MATH, ENVFILTER>(a, M, rays, bounce, slot, last, cnt, no, nd, rng, path);
         // the next bounce's ray queue is the hit queue, slot for slot (holes stay holes: path id
         // SPB_QUEUE_HOLE), so no counter is touched here
         if (!last && inQueue) store_ray(nextRays, i, no, nd, rng, path);
         count_row(a, path, active, SPB_COST_HIT);
     }
     if (!last && blockIdx.x == 0 && threadIdx.x == 0) ctr[WCTR_STRIDE + WCTR_RAYS] = total;
+    if (a.countStats)
+    {
+        unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
+        if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
+    }
+}
+
+// Direction bin of a bounce ray: the octahedral map of the direction, 4 bits per coordinate,
+// interleaved (Morton order), so that consecutive bins are neighbouring cones.
+#ifndef SPB_DIR_BINS
+#define SPB_DIR_BINS 256u
+#endif
+__device__ __forceinline__ unsigned direction_bin(f3 d)
+{
+#if SPB_DIR_BINS == 64u
+    unsigned octant = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    const float c = 0.57735f;
+    unsigned shape = (fabsf(d.x) > c ? 1u : 0u) | (fabsf(d.y) > c ? 2u : 0u) | (fabsf(d.z) > c ? 4u : 0u);
+    return octant * 8u + shape;
+#else
+    float n = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+    float inv = n > 0.0f ? __fdividef(1.0f, n) : 0.0f;
+    float u = d.x * inv, v = d.y * inv;
+    if (d.z < 0.0f)
+    {
+        float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f);
+        float fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = fu; v = fv;
+    }
+    int iu = (int)((u * 0.5f + 0.5f) * 16.0f), iv = (int)((v * 0.5f + 0.5f) * 16.0f);
+    unsigned qu = (unsigned)(iu < 0 ? 0 : (iu > 15 ? 15 : iu)), qv = (unsigned)(iv < 0 ? 0 : (iv > 15 ? 15 : iv));
+    // interleave the two 4-bit coordinates
+    qu = (qu | (qu << 2)) & 0x33u; qu = (qu | (qu << 1)) & 0x55u;
+    qv = (qv | (qv << 2)) & 0x33u; qv = (qv | (qv << 1)) & 0x55u;
+    return qu | (qv << 1);
+#endif
+}
+
+// Primary hits, tile by tile.  A tile is SPB_SORT_TILE consecutive primary items -- the samples of
+// the pixels of one 8x4 block when samplesThisPass = 64 -- so its bounce rays leave (almost) one
+// surface point per pixel and differ in direction only.  The CTA shades the tile's hits, bins the
+// new rays by direction and writes them bin by bin into the tile's slots of the next ray queue:
+// the trace kernel then hands a warp 32 rays with neighbouring origins AND similar directions,
+// which walk the same nodes (coalesced node fetches, lanes that finish together).  Slots the tile
+// does not fill are holes.  The order of rays in a queue has no influence on any result.
+template <int MATH, int ENVFILTER>
+__global__ void __launch_bounds__(256)
+k_shade_hit_tiles(const __grid_constant__ WaveArgs a)
+{
+    __shared__ unsigned binCount[SPB_DIR_BINS], binStart[SPB_DIR_BINS];
+    __shared__ unsigned meta[SPB_SORT_TILE];
+    uint32_t *ctr = a.ctr;
+    const v4f *rays = a.rays[0];
+    v4f *nextRays = a.rays[1];
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    const unsigned tiles = (a.workItems + SPB_SORT_TILE - 1) / SPB_SORT_TILE;
+    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        const unsigned base = tile * SPB_SORT_TILE;
+        for (unsigned b = threadIdx.x; b < SPB_DIR_BINS; b += 256) binCount[b] = 0;
+        __syncthreads();
+        for (unsigned k = 0; k < SPB_SORT_TILE / 256; ++k)
+        {
+            const unsigned local = k * 256 + threadIdx.x, item = base + local;
+            bool active = item < a.workItems && a.hitRec[item].x > 0.0f;
+            f3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0);
+            uint32_t rng = 0, path = SPB_QUEUE_HOLE;
+            unsigned m = 0xFFFFFFFFu;
+            if (active)
+            {
+                shade_hit_one<MATH, ENVFILTER>(a, M, rays, 0, item, false, cnt, no, nd, rng, path);
+                unsigned bin = direction_bin(nd);
+                m = (bin << 16) | atomicAdd(&binCount[bin], 1u);
+                store_ray(a.stage, item, no, nd, rng, path);
+            }
+            meta[local] = m;
+            count_row(a, path, active, SPB_COST_HIT);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            // exclusive prefix sum over the bins: SPB_DIR_BINS / 32 consecutive bins per lane
+            const unsigned per = SPB_DIR_BINS / 32u, b0 = threadIdx.x * per;
+            unsigned mine = 0;
+            for (unsigned b = 0; b < per; ++b) mine += binCount[b0 + b];
+            unsigned incl = mine;
+            for (unsigned dlt = 1; dlt < 32; dlt <<= 1)
+            {
+                unsigned v = __shfl_up_sync(SPB_FULL, incl, dlt);
+                if (threadIdx.x >= dlt) incl += v;
+            }
+            unsigned at = incl - mine;
+            for (unsigned b = 0; b < per; ++b) { binStart[b0 + b] = at; at += binCount[b0 + b]; }
+            __syncwarp();
+            if (threadIdx.x == 31) binCount[0] = incl; // rays of the tile
+        }
+        __syncthreads();
+        const unsigned filled = binCount[0];
+        for (unsigned k = 0; k < SPB_SORT_TILE / 256; ++k)
+        {
+            const unsigned local = k * 256 + threadIdx.x;
+            const unsigned m = meta[local];
+            if (m != 0xFFFFFFFFu)
+            {
+                const unsigned dst = base + binStart[m >> 16] + (m & 0xFFFFu);
+                nextRays[(size_t)dst * 2 + 0] = a.stage[(size_t)(base + local) * 2 + 0];
+                nextRays[(size_t)dst * 2 + 1] = a.stage[(size_t)(base + local) * 2 + 1];
+            }
+            if (local >= filled) nextRays[(size_t)(base + local) * 2 + 1] = mk4f(0.0f, 0.0f, 0.0f, u2f(SPB_QUEUE_HOLE));
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr[WCTR_STRIDE + WCTR_RAYS] = tiles * SPB_SORT_TILE;
     if (a.countStats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
@@ -697,6 +833,20 @@ void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t boun
     case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
     case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
     default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    }
+}
+
+void launch_wave_shade_primary_sorted(const KernelConfig &cfg, const WaveArgs &a, cudaStream_t stream)
+{
+    g_kernelLaunches += 2;
+    unsigned grid = shade_grid();
+    int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
+    switch (key)
+    {
+    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<0, 0><<<grid, 256, 0, stream>>>(a); break;
+    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<0, 1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<1, 0><<<grid, 256, 0, stream>>>(a); break;
+    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<1, 1><<<grid, 256, 0, stream>>>(a); break;
     }
 }
 
