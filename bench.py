@@ -63,6 +63,7 @@ def parse_args():
                          "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
+    ap.add_argument("--sort-bounces", type=int, default=0, help="development: direction-sort the rays leaving this many bounces")
     ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
     ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
     ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
@@ -316,6 +317,8 @@ def main():
         sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
     if args.no_ray_sorting:
         sp.lib.sp_b200_SetRaySorting(0)
+    if args.sort_bounces:
+        sp.lib.sp_b200_SetRaySorting(args.sort_bounces)
     if args.refill:
         sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
     TH = 64
@@ -328,6 +331,7 @@ def main():
             torch.cuda.synchronize()
 
     gather_ev = []
+    trace_log = []
 
     def render_step(frame, bounds, want_cost=False):
         b, e = bounds[rank]
@@ -342,6 +346,7 @@ def main():
             strips.gather_strips(image, bounds, dist)
             g1.record()
             gather_ev.append((g0, g1))
+        trace_log.append((st.traceMs, st.traceLaunches, int(st.tracedRays)) if e > b else (0.0, 0, 0))
         return m, cost, (st.kernelMs if e > b else 0.0)
 
     # ---- warm-up (also measures per-tile-row cost and re-cuts the strips)
@@ -362,6 +367,7 @@ def main():
     # ---- timed region: exactly K steps
     launches0 = sp.lib.sp_b200_KernelLaunchCount()
     gather_ev.clear()
+    trace_log.clear()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -445,36 +451,50 @@ def main():
         e2e_secs, e2e_rays = float(a[0]), float(b_[1])
     e2e_value = e2e_rays / e2e_secs / 1e6
 
-    # ---- roofline of the dominant kernel: a stats launch of one frame counts I and L
+    # ---- roofline of the dominant kernel (k_trace, the traversal kernel; all its launches of a
+    # step are timed with CUDA events inside the library): a stats launch of one frame counts I, L
     roofline = None
     cpu = None
     if rank == 0:
+        timed_trace = trace_log[:args.steps]
+        trace_ms = float(np.mean([t[0] for t in timed_trace])) if timed_trace else 0.0
+        trace_launches = int(np.mean([t[1] for t in timed_trace])) if timed_trace else 0
+        traced_rays = float(np.mean([t[2] for t in timed_trace])) if timed_trace else 0.0
         sp.lib.sp_b200_EnableStats(1)
         b, e = bounds[rank]
         m, _ = r.render_rows(b, e, frame=frame - 1, host=False, device_ptr=image.data_ptr())
         st = sp.last_stats()
         sp.lib.sp_b200_EnableStats(0)
-        srays = max(1, int(st.rays))
+        srays = max(1, int(st.tracedRays))
         I, L = st.nodeVisits / srays, st.triangleTests / srays
-        hits = int(m[sp.sp_Metric_RayHitCount])
-        misses = int(m[sp.sp_Metric_RayMissCount])
-        pixels = (e - b) * Wd
-        # per ray 128 I + 48 L + 64; per hit 48 B of normals (smooth shading); per miss one 16-B
-        # env texel; framebuffer 16 B/pixel
-        per_launch_bytes = srays * (128.0 * I + 48.0 * L + 64.0) + 48.0 * hits + 16.0 * misses + 16.0 * pixels
-        per_ray = per_launch_bytes / srays
-        my_rays = float(stat[1])  # this rank's rays over the K timed launches
-        avg_ms = float(np.mean(kernel_ms)) if kernel_ms else 0.0
-        achieved = (per_ray * my_rays / max(1, args.steps)) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        # traversal: per traced ray 128 I + 48 L + 64; sky-kernel samples never
+        # enter the traversal kernel and are not counted
+        per_ray = 128.0 * I + 48.0 * L + 64.0
+        bytes_per_step = per_ray * traced_rays
+        achieved = bytes_per_step / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
         peak, which = measured_peak()
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "trace_traffic.json")))
+            if tr.get("workload") == args.workload and tr.get("spp") == args.spp and tr.get("width") == args.width \
+                    and world == 1 and tr.get("launches"):
+                traffic = float(tr["dram_bytes_per_step"]) / float(tr["launches"])
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": which,
-                    "kernel": "k_trace + k_shade_* (one frame)" if args.render_mode == 0 else "k_render_pixels",
-                    "kernel_ms": avg_ms,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                    "kernel": "k_trace (BVH traversal + triangle tests)",
+                    "launches_per_step": trace_launches,
+                    "kernel_ms_per_step": trace_ms, "step_kernels_ms": float(np.mean(kernel_ms)) if kernel_ms else 0.0,
+                    "avg_launch_ms": trace_ms / max(1, trace_launches),
+                    "algorithmic_bytes_per_launch": bytes_per_step / max(1, trace_launches),
+                    "traced_rays_per_step": traced_rays,
                     "node_visits_per_ray": I, "triangle_tests_per_ray": L,
                     "algorithmic_bytes_per_ray": per_ray,
-                    "note": "BVH (1.3 MB) is L1/L2-resident: the fraction is of the HBM copy peak, "
-                            "the served bytes come mostly from L1/L2 (profiles/)"}
+                    "note": "achieved = algorithmic bytes of the step's k_trace launches / their summed CUDA-event time; "
+                            "traffic = DRAM bytes per launch from the ncu capture under profiles/ (the 1.3 MB BVH is "
+                            "L1/L2-resident, so DRAM traffic is the ray and hit-record queues); the fraction is of the "
+                            "HBM copy peak although the bytes are served from L1/L2"}
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_time_sample(args, wl, args.cpu_seconds, "port")
             cpu.pop("tiles", None)

@@ -236,8 +236,12 @@ typedef struct sp_b200_Stats {
     u64 triangleTests;  /* leaf triangles fetched and tested (48 B each) */
     u64 objectTests;    /* instances entered (ray transformed to object space) */
     u64 envClampedLookups; /* env texel indices past the image end (unclamped in image.h:3-18) */
-    f32 kernelMs;       /* CUDA-event time of the dominant kernel of the last call */
+    f32 kernelMs;       /* CUDA-event time of all kernels of the last call */
     f32 totalMs;        /* CUDA-event time of the whole call on the device (copies included) */
+    f32 traceMs;        /* wavefront mode: summed CUDA-event time of the traversal kernel's launches
+                           (the dominant kernel); otherwise = kernelMs */
+    u32 traceLaunches;  /* how many launches traceMs covers */
+    u64 tracedRays;     /* rays that went through the traversal kernel (rays minus sky-kernel samples) */
 } sp_b200_Stats;
 
 int sp_b200_Init(int device);            /* selects the device; 0 on success */

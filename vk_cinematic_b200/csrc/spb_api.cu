@@ -114,6 +114,7 @@ struct Library
     uint32_t pathsPerPass = 0; // 0: default (render_wavefront)
     bool skyCulling = true;    // sp_b200_SetSkyCulling
     bool sortBounceRays = true; // sp_b200_SetRaySorting
+    uint32_t sortBounces = 1;   // bounces whose outgoing rays are direction-sorted (A/B knob)
     // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
     // 0 for the sorted class = measured choice between packet mode (1) and SPB_REFILL_THRESHOLD:
     // packets win when a tile's sorted rays are coherent (C3: one 8x4 block, 64 spp: -6 % frame
@@ -131,6 +132,9 @@ struct Library
         std::vector<Probe> probes;
         std::vector<cudaEvent_t> pool;
     } tuner;
+    // CUDA events around every k_trace launch of the last wavefront frame (sp_b200_Stats::traceMs)
+    std::vector<cudaEvent_t> traceEvents;
+    size_t traceEventsUsed = 0;
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
@@ -369,6 +373,9 @@ void record_stats(const unsigned long long *c, float kernelMs, float totalMs)
     L.lastStats.envClampedLookups = c[CTR_ENV_CLAMPED];
     L.lastStats.kernelMs = kernelMs;
     L.lastStats.totalMs = totalMs;
+    L.lastStats.traceMs = kernelMs;
+    L.lastStats.traceLaunches = 1;
+    L.lastStats.tracedRays = c[CTR_RAYS];
 }
 
 spbh::M4 to_m4(const mat4 &m)
@@ -512,6 +519,20 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     tn.probes.clear();
     const bool tuning = a.sortPrimaryHits && L.refillThreshold[1] == 0 && tn.choice < 0;
 
+    L.traceEventsUsed = 0;
+    auto timed_trace = [&](uint32_t bounce, bool primary) {
+        if (L.traceEventsUsed + 2 > L.traceEvents.size())
+            for (int k = 0; k < 64; ++k)
+            {
+                cudaEvent_t e;
+                SPB_CUDA(cudaEventCreate(&e));
+                L.traceEvents.push_back(e);
+            }
+        SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
+        launch_wave_trace(cfg, a, bounce, primary, L.stream);
+        SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
+    };
+
     uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
     uint32_t passIndex = 0;
     for (uint32_t band = 0; band < bands; ++band)
@@ -528,11 +549,11 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             const size_t ctrIndex = (size_t)(ctr - (uint32_t *)L.wCtr.ptr);
             ctr += (size_t)bounces * WCTR_STRIDE;
             a.refillThreshold = L.refillThreshold[0];
-            launch_wave_trace(cfg, a, 0, true, L.stream);
+            timed_trace(0, true);
             for (uint32_t b = 0; b < bounces; ++b)
             {
                 const bool sortedNext = b == 0 && a.sortPrimaryHits;
-                if (sortedNext) launch_wave_shade_primary_sorted(cfg, a, L.stream);
+                if (a.sortPrimaryHits && b + 1 < bounces && b < L.sortBounces) launch_wave_shade_sorted(cfg, a, b, L.stream);
                 else launch_wave_shade(cfg, a, b, L.stream);
                 if (b + 1 >= bounces) break;
                 int probe = -1;
@@ -554,11 +575,11 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
                     }
                     Library::SortedTuner::Probe pr = {probe, ctrIndex, tn.pool[tn.probes.size() * 2], tn.pool[tn.probes.size() * 2 + 1]};
                     SPB_CUDA(cudaEventRecord(pr.e0, L.stream));
-                    launch_wave_trace(cfg, a, b + 1, false, L.stream);
+                    timed_trace(b + 1, false);
                     SPB_CUDA(cudaEventRecord(pr.e1, L.stream));
                     tn.probes.push_back(pr);
                 }
-                else launch_wave_trace(cfg, a, b + 1, false, L.stream);
+                else timed_trace(b + 1, false);
             }
             passIndex++;
             launch_wave_accumulate(a, L.stream);
@@ -607,6 +628,9 @@ extern "C" void sp_b200_Shutdown(void)
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
     L.wMask.release(); L.wBlockList.release(); L.wStage.release();
+    for (cudaEvent_t e : L.traceEvents) cudaEventDestroy(e);
+    L.traceEvents.clear();
+    L.traceEventsUsed = 0;
     for (cudaEvent_t e : L.tuner.pool) cudaEventDestroy(e);
     L.tuner.pool.clear();
     L.tuner.probes.clear();
@@ -649,7 +673,11 @@ extern "C" void sp_b200_FlushTextureCache(void)
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
 extern "C" void sp_b200_SetSkyCulling(int enable) { lib().skyCulling = enable != 0; }
-extern "C" void sp_b200_SetRaySorting(int enable) { lib().sortBounceRays = enable != 0; }
+extern "C" void sp_b200_SetRaySorting(int enable)
+{
+    lib().sortBounceRays = enable != 0;
+    lib().sortBounces = enable > 1 ? (uint32_t)enable : 1u;
+}
 extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
 {
     Library &L = lib();
@@ -1302,6 +1330,14 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     float kernelMs = 0, totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
     SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    float traceMs = 0.0f;
+    if (wavefront)
+        for (size_t i = 0; i + 1 < L.traceEventsUsed; i += 2)
+        {
+            float ms = 0.0f;
+            SPB_CUDA(cudaEventElapsedTime(&ms, L.traceEvents[i], L.traceEvents[i + 1]));
+            traceMs += ms;
+        }
     if (wavefront && !L.tuner.probes.empty())
     {
         // measurements of the sorted-class refill threshold (render_wavefront): ms per ray of the
@@ -1342,6 +1378,9 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     }
     add_metrics(metrics, c.data(), kernelMs);
     record_stats(c.data(), kernelMs, totalMs);
+    L.lastStats.traceMs = wavefront ? traceMs : kernelMs;
+    L.lastStats.traceLaunches = wavefront ? (u32)(L.traceEventsUsed / 2) : 1u;
+    L.lastStats.tracedRays = c[CTR_RAYS] - (wavefront ? c[CTR_SKY_PIXELS] * L.params.samplesPerPixel : 0);
     if (tileRowCost)
         for (u32 i = 0; i < tileRows; ++i) tileRowCost[i] = c[CTR_COUNT + i];
     return 0;

@@ -179,8 +179,9 @@ void launch_coverage(const WaveArgs &args, uint64_t instancedTriangles, bool eve
 void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,
                        cudaStream_t stream);
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
-// bounce 0 with sortPrimaryHits: k_shade_miss + the tile kernel
-void launch_wave_shade_primary_sorted(const KernelConfig &cfg, const WaveArgs &args, cudaStream_t stream);
+// k_shade_miss + the tile kernel, which writes the next bounce's rays in direction order per tile
+// (bounce 0 needs sortPrimaryHits: primary results by item; not for the last bounce)
+void launch_wave_shade_sorted(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
 void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
 // Pixels of the strip whose block is not in the list: every sample's camera ray leaves the scene
 // untouched, so the whole pixel is evaluated in one thread: ray generation, background material,

@@ -502,16 +502,20 @@ __device__ __forceinline__ unsigned direction_bin(f3 d)
 // does not fill are holes.  The order of rays in a queue has no influence on any result.
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
-k_shade_hit_tiles(const __grid_constant__ WaveArgs a)
+k_shade_hit_tiles(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
     __shared__ unsigned binCount[SPB_DIR_BINS], binStart[SPB_DIR_BINS];
     __shared__ unsigned meta[SPB_SORT_TILE];
-    uint32_t *ctr = a.ctr;
-    const v4f *rays = a.rays[0];
-    v4f *nextRays = a.rays[1];
+    // bounce 0: the tile's items are primary items (results in hitRec by item); later bounces:
+    // consecutive entries of the hit queue
+    uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
+    const v4f *rays = a.rays[bounce & 1u];
+    v4f *nextRays = a.rays[(bounce + 1u) & 1u];
     const DMaterials &M = *a.materials;
     Counters cnt = {0, 0, 0, 0};
-    const unsigned tiles = (a.workItems + SPB_SORT_TILE - 1) / SPB_SORT_TILE;
+    const bool byItem = bounce == 0;
+    const unsigned entries = byItem ? a.workItems : ctr[WCTR_HITS];
+    const unsigned tiles = (entries + SPB_SORT_TILE - 1) / SPB_SORT_TILE;
     for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x)
     {
         const unsigned base = tile * SPB_SORT_TILE;
@@ -520,13 +524,15 @@ k_shade_hit_tiles(const __grid_constant__ WaveArgs a)
         for (unsigned k = 0; k < SPB_SORT_TILE / 256; ++k)
         {
             const unsigned local = k * 256 + threadIdx.x, item = base + local;
-            bool active = item < a.workItems && a.hitRec[item].x > 0.0f;
+            unsigned slot = SPB_QUEUE_HOLE;
+            if (item < entries) slot = byItem ? (a.hitRec[item].x > 0.0f ? item : SPB_QUEUE_HOLE) : a.hitQ[item];
+            bool active = slot != SPB_QUEUE_HOLE;
             f3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0);
             uint32_t rng = 0, path = SPB_QUEUE_HOLE;
             unsigned m = 0xFFFFFFFFu;
             if (active)
             {
-                shade_hit_one<MATH, ENVFILTER>(a, M, rays, 0, item, false, cnt, no, nd, rng, path);
+                shade_hit_one<MATH, ENVFILTER>(a, M, rays, bounce, slot, false, cnt, no, nd, rng, path);
                 unsigned bin = direction_bin(nd);
                 m = (bin << 16) | atomicAdd(&binCount[bin], 1u);
                 store_ray(a.stage, item, no, nd, rng, path);
@@ -569,7 +575,7 @@ k_shade_hit_tiles(const __grid_constant__ WaveArgs a)
         __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr[WCTR_STRIDE + WCTR_RAYS] = tiles * SPB_SORT_TILE;
-    if (a.countStats)
+    if (a.countStats) // (k_shade_hit_tiles)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
         if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
@@ -836,17 +842,17 @@ void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t boun
     }
 }
 
-void launch_wave_shade_primary_sorted(const KernelConfig &cfg, const WaveArgs &a, cudaStream_t stream)
+void launch_wave_shade_sorted(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, cudaStream_t stream)
 {
     g_kernelLaunches += 2;
     unsigned grid = shade_grid();
     int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
     switch (key)
     {
-    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<0, 0><<<grid, 256, 0, stream>>>(a); break;
-    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<0, 1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<1, 0><<<grid, 256, 0, stream>>>(a); break;
-    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, 0); k_shade_hit_tiles<1, 1><<<grid, 256, 0, stream>>>(a); break;
+    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<0, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
+    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
     }
 }
 

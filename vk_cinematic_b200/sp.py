@@ -187,7 +187,8 @@ class sp_b200_Params(C.Structure):
 
 class sp_b200_Stats(C.Structure):
     _fields_ = [("rays", u64), ("nodeVisits", u64), ("triangleTests", u64), ("objectTests", u64),
-                ("envClampedLookups", u64), ("kernelMs", f32), ("totalMs", f32)]
+                ("envClampedLookups", u64), ("kernelMs", f32), ("totalMs", f32), ("traceMs", f32),
+                ("traceLaunches", u32), ("tracedRays", u64)]
 
 
 class sp_b200_TreeInfo(C.Structure):
