@@ -63,6 +63,7 @@ def parse_args():
                          "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
+    ap.add_argument("--strip-rows", type=int, default=16, help="granularity of strip boundaries in pixel rows (multiple of 4)")
     ap.add_argument("--sort-bounces", type=int, default=0, help="development: direction-sort the rays leaving this many bounces")
     ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
     ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
@@ -88,7 +89,7 @@ def workload_config(args):
         "env_filter": "nearest (reference image.h:3-18)",
         "l2": "env map 134 MB + framebuffer 133 MB touched per step exceed the 126 MB L2; the "
               "1.3 MB BVH is re-read by every ray inside a step by design; frame index advances per step",
-        "partition": "tile-row strips (64-row tiles), rebalanced from measured per-tile-row cost",
+        "partition": "strips of whole 16-pixel rows (quarter tiles), rebalanced from measured per-row cost",
         "scheduler": "wavefront (trace / shade-miss / shade-hit / accumulate kernels over device queues)"
                      if args.render_mode == 0 else "per-pixel kernel",
     }
@@ -311,7 +312,7 @@ def main():
     host_image = torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory()
     r = sp.Renderer(local).load_workload(wl, pixels=host_image.numpy())
     sp.set_params(samplesPerPixel=args.spp, bounceCount=args.bounces, cullByDistance=1,
-                  mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=64,
+                  mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=args.strip_rows,
                   renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
     if args.paths_per_pass:
         sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
@@ -321,7 +322,7 @@ def main():
         sp.lib.sp_b200_SetRaySorting(args.sort_bounces)
     if args.refill:
         sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
-    TH = 64
+    TH = args.strip_rows   # strip boundaries and cost accounting: rows of 16 pixels (a quarter tile)
     image = torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev)
 
     def barrier():
