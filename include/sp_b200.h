@@ -286,6 +286,13 @@ int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32
                        void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);
 /* All rows into ctx->camera->imagePlane->pixels (host). */
 int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics);
+/* Output stage (the step after the path, src/shaders/post_processing.frag.glsl:19-26
+ * PerformToneMapping): color *= exposure; color = color / (1 + color); pow(color, 1/2.2); then the
+ * 8-bit UNORM store of the colour attachment, alpha 255, r in the low byte (the layout of ToColor,
+ * src/math_lib.h:523-532).  pixelCount RGBA f32 pixels from devicePixels if non-NULL, else from
+ * hostPixels; RGBA8 result to hostRGBA8 and/or deviceRGBA8 (either may be NULL, not both). */
+int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, u32 pixelCount, f32 exposure,
+                    u32 *hostRGBA8, void *deviceRGBA8);
 /* Primary-ray closest hits of (sample, frame): per pixel triangle index (-1 = miss), object
  * index and world t.  Output arrays are host memory, any may be NULL. */
 int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *triangleIndex,

@@ -140,6 +140,12 @@ void ora_radiance_for_path(ora_Scene *s, const float *path15, uint32_t n, float 
 /* SampleImageNearest / SampleImageBilinear (image.h:3-18,34-73) */
 void ora_sample_nearest(const float *pixels, uint32_t w, uint32_t h, float u, float v, float *out4);
 void ora_sample_bilinear(const float *pixels, uint32_t w, uint32_t h, float u, float v, float *out4);
+/* Output stage (port only): PerformToneMapping of src/shaders/post_processing.frag.glsl:19-26 --
+ * color *= exposure; color = color / (1 + color); pow(color, 1/2.2) -- on the RGB of `count` RGBA
+ * f32 pixels, then the 8-bit UNORM store a colour attachment performs (round(clamp(c,0,1) * 255)),
+ * alpha 255; out = count x RGBA8 (r in the low byte, like ToColor, src/math_lib.h:523-532).  The
+ * shader is not CPU code, so this function is pinned by known-answer values only. */
+void ora_tone_map(const float *rgba, uint32_t count, float exposure, uint32_t *out);
 /* ComputeTiles (tile.h:11-42): tiles = maxTiles x 4 u32; returns count */
 uint32_t ora_compute_tiles(uint32_t w, uint32_t h, uint32_t tw, uint32_t th, uint32_t *tiles,
                            uint32_t maxTiles);

@@ -1283,6 +1283,31 @@ extern "C" void ora_radiance_for_path(ora_Scene *s, const float *path15, uint32_
     out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 
+// post_processing.frag.glsl:19-26 (PerformToneMapping) + UNORM8 store; pow follows the libm switch
+// of this file (powf, or pow in double rounded once under ORA_DETERMINISTIC_MATH)
+extern "C" void ora_tone_map(const float *rgba, uint32_t count, float exposure, uint32_t *out)
+{
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        uint32_t packed = 0xFF000000u;
+        for (int ch = 0; ch < 3; ++ch)
+        {
+            float c = rgba[(size_t)i * 4 + ch];
+            c = c * exposure;
+            c = c / (1.0f + c);
+#ifdef ORA_DETERMINISTIC_MATH
+            c = (float)pow((double)c, 1.0 / 2.2);
+#else
+            c = powf(c, 1.0f / 2.2f);
+#endif
+            float q = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f; // NaN -> 0
+            uint32_t byte = (uint32_t)floorf(q * 255.0f + 0.5f);
+            packed |= byte << (8 * ch);
+        }
+        out[i] = packed;
+    }
+}
+
 extern "C" void ora_sample_nearest(const float *pixels, uint32_t w, uint32_t h, float u, float v, float *out4)
 {
     Image img;

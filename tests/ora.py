@@ -130,6 +130,8 @@ class OracleLib:
         lib.ora_film_positions.argtypes = [C.c_void_p, C.c_uint32, _f, _f]
         lib.ora_transform_aabb.argtypes = [_f] * 6
         lib.ora_radiance_for_path.argtypes = [C.c_void_p, _f, C.c_uint32, _f]
+        if hasattr(lib, "ora_tone_map"):
+            lib.ora_tone_map.argtypes = [_f, C.c_uint32, C.c_float, _u]
         lib.ora_sample_nearest.argtypes = [_f, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f]
         lib.ora_sample_bilinear.argtypes = [_f, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f]
         lib.ora_compute_tiles.argtypes = [C.c_uint32] * 4 + [_u, C.c_uint32]
@@ -213,6 +215,13 @@ class OracleLib:
         out = np.zeros(4, np.float32)
         self.lib.ora_sample_nearest(_fp(img), img.shape[1], img.shape[0], u, v, _fp(out))
         return out
+
+    def tone_map(self, rgba, exposure=1.0):
+        """(..., 4) float32 -> (...,) uint32 RGBA8 (port only)."""
+        img = np.ascontiguousarray(rgba, dtype=np.float32)
+        out = np.zeros(img.size // 4, np.uint32)
+        self.lib.ora_tone_map(_fp(img), out.size, exposure, _up(out))
+        return out.reshape(img.shape[:-1])
 
     def sample_bilinear(self, image, u, v):
         img = _f32(image)

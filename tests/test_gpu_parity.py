@@ -553,3 +553,23 @@ def test_wavefront_pass_split_and_stats(gpu_sp):
     assert same_bits(r.image, ref_img)
     sp.set_params(samplesPerPixel=1, bounceCount=3, samplesPerPass=0)
     r.close()
+
+
+def test_tone_map_matches_oracle(gpu_sp):
+    """sp_b200_ToneMap (output stage, post_processing.frag.glsl:19-26) against the port's restatement:
+    identical bytes on a rendered frame, on a radiance ramp and on special values, in both math
+    modes' own pairing (mathMode 0 <-> deterministic-math port)."""
+    sp = gpu_sp
+    wl = W.config1(160, 120, env_size=(256, 128))
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=2, bounceCount=3, mathMode=0, renderMode=0)
+    img, _ = r.render_frame(frame=1)
+    rng = np.random.RandomState(3)
+    ramp = np.concatenate([np.linspace(0, 20, 20000), rng.lognormal(0, 2, 20000), [0, -1, np.nan, np.inf, 1e30]]).astype(np.float32)
+    synth = np.stack([ramp, ramp[::-1], ramp * 0.25, np.ones_like(ramp)], axis=-1)
+    port = ora.load_port_dm()
+    for exposure in (1.0, 0.37):
+        assert np.array_equal(sp.tone_map(img, exposure), port.tone_map(img, exposure))
+        assert np.array_equal(sp.tone_map(synth, exposure), port.tone_map(synth, exposure))
+    r.close()
+    sp.set_params(samplesPerPixel=1, bounceCount=3)

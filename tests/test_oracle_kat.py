@@ -412,3 +412,28 @@ def test_port_five_bounces_extends_three(port):
     assert same.mean() > 0.8  # background + short paths
     assert np.all(np.isfinite(i5))
     s.close()
+
+
+def test_tone_map_known_answers():
+    """Output stage, post_processing.frag.glsl:19-26: color / (1 + color), then
+    pow(color, 1/2.2), stored as 8-bit UNORM (round(c * 255)), alpha 255, r in the low byte.  The
+    shader cannot run here, so the restatement is pinned by values worked out by hand / in numpy
+    float64: 0 -> 0; 1 -> (1/2)^(1/2.2) = 0.72974 -> 186; 3 -> 0.75^(1/2.2) = 0.87742 -> 224;
+    exposure 2 on 0.5 equals exposure 1 on 1; negative and NaN radiance -> 0; huge -> 255."""
+    for lib in (ora.load_port(), ora.load_port_dm()):
+        px = np.array([[0, 1, 3, 1], [0.5, 1e30, -0.5, 0], [np.nan, 0.18, 10.0, 1]], np.float32)
+        out = lib.tone_map(px)
+        assert [int(out[0]) & 0xFF, (int(out[0]) >> 8) & 0xFF, (int(out[0]) >> 16) & 0xFF, int(out[0]) >> 24] == [0, 186, 224, 255]
+        assert [int(out[1]) & 0xFF, (int(out[1]) >> 8) & 0xFF, (int(out[1]) >> 16) & 0xFF] == [155, 255, 0]
+        assert int(out[2]) & 0xFF == 0
+        # against numpy float64 on a ramp (bytes can differ only where the value sits on a rounding boundary)
+        ramp = np.linspace(0, 12, 4097, dtype=np.float32)
+        img = np.stack([ramp, ramp * 0.5, ramp * 2, np.ones_like(ramp)], axis=-1)
+        got = lib.tone_map(img)
+        for ch, k in ((0, 1.0), (1, 0.5), (2, 2.0)):
+            c = (ramp.astype(np.float64) * k)
+            want = np.floor(np.clip((c / (1 + c)) ** (1 / 2.2), 0, 1) * 255 + 0.5).astype(np.int64)
+            diff = np.abs(((got >> (8 * ch)) & 0xFF).astype(np.int64) - want)
+            assert diff.max() <= 1 and (diff != 0).mean() < 2e-3
+        assert np.array_equal(lib.tone_map(px[:, :] * np.float32(1.0), exposure=2.0)[1] & 0xFF,
+                              lib.tone_map(np.array([[1.0, 0, 0, 1]], np.float32))[0] & 0xFF)

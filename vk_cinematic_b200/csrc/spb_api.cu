@@ -1388,6 +1388,38 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     return 0;
 }
 
+// Output stage: tone mapping + 8-bit store (post_processing.frag.glsl:19-26).  Source: device
+// pixels if given, else host pixels (uploaded); result to hostRGBA8 and/or deviceRGBA8.
+extern "C" int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, u32 pixelCount, f32 exposure,
+                               u32 *hostRGBA8, void *deviceRGBA8)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    if (pixelCount == 0) return 0;
+    SPB_ASSERT(hostPixels || devicePixels);
+    SPB_ASSERT(hostRGBA8 || deviceRGBA8);
+    const v4f *src = (const v4f *)devicePixels;
+    if (!src)
+    {
+        L.scratchA.ensure((size_t)pixelCount * 16);
+        SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, hostPixels, (size_t)pixelCount * 16, cudaMemcpyHostToDevice, L.stream));
+        src = (const v4f *)L.scratchA.ptr;
+    }
+    uint32_t *dst = (uint32_t *)deviceRGBA8;
+    if (!dst)
+    {
+        L.scratchB.ensure((size_t)pixelCount * 4);
+        dst = (uint32_t *)L.scratchB.ptr;
+    }
+    launch_tone_map(kernel_config(), src, pixelCount, exposure, dst, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    if (hostRGBA8)
+        SPB_CUDA(cudaMemcpyAsync(hostRGBA8, dst, (size_t)pixelCount * 4, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    return 0;
+}
+
 extern "C" int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics)
 {
     SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);

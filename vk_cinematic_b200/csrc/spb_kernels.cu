@@ -374,4 +374,45 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
     SPB_DISPATCH(launch_evalmat_t, c, materials, materialSlot, vertex15, out7, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Output stage: the tone mapping the reference applies when it shows the
+// path tracer's image (post_processing.frag.glsl:19-26: color *= exposure; color /= 1 + color;
+// pow(color, 1/2.2)) and the 8-bit UNORM store of the colour attachment, r in the low byte like
+// ToColor (math_lib.h:523-532).  MATH == 0: pow evaluated in double and rounded once (what the
+// oracle's deterministic-math build computes); MATH == 1: powf.
+template <int MATH>
+__global__ void __launch_bounds__(256)
+k_tone_map(const v4f *pixels, uint32_t count, float exposure, uint32_t *out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        v4f p = pixels[i];
+        float c[3] = {p.x, p.y, p.z};
+        uint32_t packed = 0xFF000000u;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+        {
+            float v = c[ch] * exposure;
+            v = v / (1.0f + v);
+            v = MATH == 0 ? (float)pow((double)v, 1.0 / 2.2) : powf(v, 1.0f / 2.2f);
+            float q = v > 0.0f ? (v < 1.0f ? v : 1.0f) : 0.0f; // NaN -> 0
+            packed |= (uint32_t)floorf(q * 255.0f + 0.5f) << (8 * ch);
+        }
+        out[i] = packed;
+    }
+}
+
+void launch_tone_map(const KernelConfig &cfg, const v4f *pixels, uint32_t count, float exposure, uint32_t *out,
+                     cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    int device = 0, sms = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    unsigned want = (count + 255u) / 256u, grid = (unsigned)sms * 8u;
+    if (want < grid) grid = want ? want : 1u;
+    if (cfg.math) k_tone_map<1><<<grid, 256, 0, stream>>>(pixels, count, exposure, out);
+    else k_tone_map<0><<<grid, 256, 0, stream>>>(pixels, count, exposure, out);
+}
+
 } // namespace spb

@@ -94,6 +94,11 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
                               uint32_t materialSlot, const float *vertex15, float *out7,
                               cudaStream_t stream);
 
+// Output stage: PerformToneMapping (post_processing.frag.glsl:19-26) on RGBA f32 pixels and the
+// 8-bit UNORM store; out = count x RGBA8
+void launch_tone_map(const KernelConfig &cfg, const v4f *pixels, uint32_t count, float exposure, uint32_t *out,
+                     cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // wavefront renderer (spb_wavefront.cu)
 

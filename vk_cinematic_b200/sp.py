@@ -249,6 +249,7 @@ _SIGNATURES = {
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
                                      _P(sp_Metrics), C.c_void_p]),
     "sp_b200_RenderFrame": (C.c_int, [_P(sp_Context), u32, _P(sp_Metrics)]),
+    "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
     "sp_b200_PrimaryHits": (C.c_int, [_P(sp_Context), u32, u32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_RayIntersectSceneBatch": (C.c_int, [_P(sp_Scene), u32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, _P(sp_Metrics)]),
@@ -318,6 +319,25 @@ def set_params(**kw):
         setattr(p, k, v)
     lib.sp_b200_SetParams(C.byref(p))
     return p
+
+
+def tone_map(rgba, exposure=1.0):
+    """(..., 4) float32 host array -> (...,) uint32 RGBA8 through sp_b200_ToneMap."""
+    img = np.ascontiguousarray(rgba, dtype=np.float32)
+    out = np.zeros(img.size // 4, np.uint32)
+    if lib.sp_b200_ToneMap(img.ctypes.data, None, out.size, exposure, out.ctypes.data, None) != 0:
+        raise RuntimeError("sp_b200_ToneMap failed")
+    return out.reshape(img.shape[:-1])
+
+
+def write_ppm(path, rgba8):
+    """RGBA8 (H, W) uint32 image -> binary PPM (the reference has no image writer; this is the
+    harness's way to look at a frame)."""
+    h, w = rgba8.shape
+    rgb = np.stack([(rgba8 >> s) & 0xFF for s in (0, 8, 16)], axis=-1).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(rgb.tobytes())
 
 
 def last_stats():
