@@ -286,6 +286,22 @@ int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32
                        void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);
 /* All rows into ctx->camera->imagePlane->pixels (host). */
 int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics);
+/* Asset input (the step before the path; replaces LoadMesh, src/mesh.cpp:5-62, whose assimp
+ * import is not available): Wavefront OBJ -> the VertexPNT[] / u32[] pair sp_CreateMesh takes.
+ * One vertex per distinct (v, vt, vn) corner in first-seen order, polygons fan-triangulated in
+ * file order (triangle i of the result is the i-th triangle of the file).  Same fields as the
+ * reference's MeshData (src/mesh.h:24-30).  Returns 1 on success, 0 on a missing / malformed
+ * file (house convention of LoadExrImage, src/asset_loader/asset_loader.h:11-22); the arrays are
+ * malloc'ed: release with sp_b200_FreeMeshData. */
+typedef struct sp_b200_MeshData {
+    VertexPNT *vertices;
+    u32 *indices;
+    u32 vertexCount;
+    u32 indexCount;
+} sp_b200_MeshData;
+int sp_b200_LoadObj(const char *path, sp_b200_MeshData *out);
+void sp_b200_FreeMeshData(sp_b200_MeshData *mesh);
+
 /* Output stage (the step after the path, src/shaders/post_processing.frag.glsl:19-26
  * PerformToneMapping): color *= exposure; color = color / (1 + color); pow(color, 1/2.2); then the
  * 8-bit UNORM store of the colour attachment, alpha 255, r in the low byte (the layout of ToColor,

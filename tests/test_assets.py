@@ -1,0 +1,97 @@
+"""Asset input: sp_b200_LoadObj against a pure-Python restatement of its
+loader rules (the rules of tools/make_mesh_fixtures.py, which made assets/*.npz) and, where the
+reference checkout is mounted, against those fixtures on the reference's own OBJ files.  Host
+code only: no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from vk_cinematic_b200 import sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def load_obj_python(path):
+    """One vertex per distinct (v, vt, vn) corner in first-seen order; polygons fan-triangulated in
+    file order; numbers through float() -> float32 (reference src/mesh.cpp:5-62 delegates all of
+    this to assimp, which is absent: see vk_cinematic_b200/csrc/spb_assets.cpp)."""
+    pos, tex, nrm, verts, index_of, indices = [], [], [], [], {}, []
+    for line in open(path):
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "v":
+            pos.append([float(x) for x in t[1:4]])
+        elif t[0] == "vt":
+            tex.append([float(t[1]), float(t[2]) if len(t) > 2 else 0.0])
+        elif t[0] == "vn":
+            nrm.append([float(x) for x in t[1:4]])
+        elif t[0] == "f":
+            corners = []
+            for tok in t[1:]:
+                parts = (tok.split("/") + ["", ""])[:3]
+                key = []
+                for k, n in zip(parts, (len(pos), len(tex), len(nrm))):
+                    if k == "":
+                        key.append(-1)
+                    else:
+                        i = int(k)
+                        key.append(i - 1 if i > 0 else n + i)
+                key = tuple(key)
+                if key not in index_of:
+                    index_of[key] = len(verts)
+                    verts.append(key)
+                corners.append(index_of[key])
+            for k in range(1, len(corners) - 1):
+                indices.extend([corners[0], corners[k], corners[k + 1]])
+    out = np.zeros((len(verts), 8), np.float32)
+    for i, (vi, ti, ni) in enumerate(verts):
+        out[i, 0:3] = np.asarray(pos[vi], np.float32)
+        if ni >= 0:
+            out[i, 3:6] = np.asarray(nrm[ni], np.float32)
+        if ti >= 0:
+            out[i, 6:8] = np.asarray(tex[ti], np.float32)
+    return out, np.asarray(indices, np.uint32)
+
+
+def test_load_obj_fixture():
+    path = os.path.join(HERE, "golden", "quad_mix.obj")
+    v, i = sp.load_obj(path)
+    ev, ei = load_obj_python(path)
+    assert v.shape == ev.shape and np.array_equal(v.view(np.uint32), ev.view(np.uint32))
+    assert np.array_equal(i, ei)
+    # a quad, three triangles, a pentagon and a triangle: 2 + 3 + 3 + 1 = 9 triangles
+    assert len(i) == 27 and i.max() == len(v) - 1
+    # corner 1/1/1 is shared by the quad and the pentagon; "1", "1//2", "1/1" are distinct vertices
+    assert len(v) == 4 + 3 + 3 + 3 + 2 + 3
+    assert np.array_equal(v[0], np.array([0, 0, 0, 0, 0, 1, 0, 0], np.float32))
+    # first corner of the pentagon: "-1" = the last v record so far, no vt, no vn
+    assert np.array_equal(v[13], np.array([-1e-3, 25.0, -0.333333343, 0, 0, 0, 0, 0], np.float32))
+    # last corner of the file: "4//-2" = v 4 with the first vn
+    assert np.array_equal(v[17], np.array([0, 1, 0, 0, 0, 1, 0, 0], np.float32))
+
+
+def test_load_obj_errors(tmp_path):
+    assert sp.load_obj(os.path.join(HERE, "golden", "does_not_exist.obj")) is None
+    for name, text in (("zero_index", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 0 1 2\n"),
+                       ("out_of_range", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4\n"),
+                       ("two_corners", "v 0 0 0\nv 1 0 0\nf 1 2\n"),
+                       ("no_faces", "v 0 0 0\nv 1 0 0\nv 0 1 0\n"),
+                       ("bad_number", "v 0 zero 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")):
+        p = tmp_path / (name + ".obj")
+        p.write_text(text)
+        assert sp.load_obj(str(p)) is None, name
+
+
+@pytest.mark.parametrize("name", ["bunny", "monkey"])
+def test_load_obj_reference_assets(name):
+    """The reference's own meshes (BASELINE.json configs) load to exactly the committed fixtures
+    every parity test renders."""
+    src = os.path.join("/root/reference/assets", name + ".obj")
+    if not os.path.exists(src):
+        pytest.skip("reference checkout not mounted")
+    v, i = sp.load_obj(src)
+    d = np.load(os.path.join(ROOT, "assets", name + ".npz"))
+    assert np.array_equal(v.view(np.uint32), d["vertices"].view(np.uint32)) and np.array_equal(i, d["indices"])

@@ -191,6 +191,11 @@ class sp_b200_Stats(C.Structure):
                 ("traceLaunches", u32), ("tracedRays", u64)]
 
 
+class sp_b200_MeshData(C.Structure):
+    _fields_ = [("vertices", C.POINTER(VertexPNT)), ("indices", C.POINTER(u32)), ("vertexCount", u32),
+                ("indexCount", u32)]
+
+
 class sp_b200_TreeInfo(C.Structure):
     _fields_ = [("leafCount", u32), ("nodeCount", u32), ("maxDepth", u32),
                 ("allLeavesReachable", u32), ("parentsContainChildren", u32), ("rootMin", vec3),
@@ -249,6 +254,8 @@ _SIGNATURES = {
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
                                      _P(sp_Metrics), C.c_void_p]),
     "sp_b200_RenderFrame": (C.c_int, [_P(sp_Context), u32, _P(sp_Metrics)]),
+    "sp_b200_LoadObj": (C.c_int, [C.c_char_p, _P(sp_b200_MeshData)]),
+    "sp_b200_FreeMeshData": (None, [_P(sp_b200_MeshData)]),
     "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
     "sp_b200_PrimaryHits": (C.c_int, [_P(sp_Context), u32, u32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_RayIntersectSceneBatch": (C.c_int, [_P(sp_Scene), u32, C.c_void_p, C.c_void_p,
@@ -319,6 +326,18 @@ def set_params(**kw):
         setattr(p, k, v)
     lib.sp_b200_SetParams(C.byref(p))
     return p
+
+
+def load_obj(path):
+    """Wavefront OBJ -> (vertices (n, 8) float32: position, normal, uv; indices uint32) through
+    sp_b200_LoadObj.  Returns None if the file is missing or malformed."""
+    md = sp_b200_MeshData()
+    if lib.sp_b200_LoadObj(os.fsencode(path), C.byref(md)) != 1:
+        return None
+    vertices = np.ctypeslib.as_array(C.cast(md.vertices, _P(f32)), shape=(md.vertexCount, 8)).copy()
+    indices = np.ctypeslib.as_array(md.indices, shape=(md.indexCount,)).copy()
+    lib.sp_b200_FreeMeshData(C.byref(md))
+    return vertices, indices
 
 
 def tone_map(rgba, exposure=1.0):
