@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--strip-rows", type=int, default=16, help="granularity of strip boundaries in pixel rows (multiple of 4)")
     ap.add_argument("--sort-bounces", type=int, default=0, help="development: direction-sort the rays leaving this many bounces")
     ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
+    ap.add_argument("--no-candidates", action="store_true", help="development: every primary ray walks the tree")
     ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
     ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
@@ -318,6 +319,8 @@ def main():
         sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
     if args.no_ray_sorting:
         sp.lib.sp_b200_SetRaySorting(0)
+    if args.no_candidates:
+        sp.lib.sp_b200_SetPrimaryCandidates(0)
     if args.sort_bounces:
         sp.lib.sp_b200_SetRaySorting(args.sort_bounces)
     if args.refill:

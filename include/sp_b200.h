@@ -269,6 +269,10 @@ void sp_b200_SetSkyCulling(int enable);
  * direction order, so a warp of the trace kernel walks rays with neighbouring origins and similar
  * directions.  On by default; results do not depend on it. */
 void sp_b200_SetRaySorting(int enable);
+/* Wavefront mode, single-object scenes: the tree is walked once per pixel (padded centre ray, no
+ * culling) to list the triangles any of the pixel's camera rays can meet; every sample then
+ * evaluates only those, with the walk's own tests.  On by default; results do not depend on it. */
+void sp_b200_SetPrimaryCandidates(int enable);
 /* Wavefront mode tuning: a warp of the trace kernel retires and refills its lanes when fewer than
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */

@@ -488,11 +488,13 @@ def test_coverage_mask_and_ray_sorting_edge_cases(gpu_sp, case):
     # the same frame with every scheduling feature off, small passes, and through the per-pixel kernel
     sp.lib.sp_b200_SetSkyCulling(0)
     sp.lib.sp_b200_SetRaySorting(0)
+    sp.lib.sp_b200_SetPrimaryCandidates(0)
     sp.lib.sp_b200_SetPathsPerPass(50000)
     img2, m2 = r.render_frame(frame=5)
     assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5])
     sp.lib.sp_b200_SetSkyCulling(1)
     sp.lib.sp_b200_SetRaySorting(1)
+    sp.lib.sp_b200_SetPrimaryCandidates(1)
     for thresholds in ((1, 1, 1), (12, 12, 12), (1, 0, 12)):
         sp.lib.sp_b200_SetRefillThresholds(*thresholds)
         img2, m2 = r.render_frame(frame=5)

@@ -114,6 +114,7 @@ struct Library
     uint32_t pathsPerPass = 0; // 0: default (render_wavefront)
     bool skyCulling = true;    // sp_b200_SetSkyCulling
     bool sortBounceRays = true; // sp_b200_SetRaySorting
+    bool primaryCandidates = true; // sp_b200_SetPrimaryCandidates
     uint32_t sortBounces = 1;   // bounces whose outgoing rays are direction-sorted (A/B knob)
     // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
     // 0 for the sorted class = measured choice between packet mode (1) and SPB_REFILL_THRESHOLD:
@@ -148,7 +149,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -486,6 +487,13 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     L.wMissQ.ensure(slots * 4);
     L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
     L.wRad.ensure((size_t)capacity * 16);
+    // single-object scenes: per-pixel candidate triangles for the primary rays
+    // (the padding of k_candidates covers a jitter of up to 1/100 pixel; sp_ConfigureCamera's is
+    // 0.5 / width of a pixel, simd_path_tracer.cpp:17-18)
+    const bool useCandidates = L.primaryCandidates && ra.scene.objectCount == 1 && ra.scene.tlasRoot != SPB_REF_EMPTY &&
+                               ra.camera.halfPixelWidth <= 0.01f && ra.camera.halfPixelHeight <= 0.01f &&
+                               ra.camera.halfPixelWidth >= 0.0f && ra.camera.halfPixelHeight >= 0.0f;
+    if (useCandidates) L.wCand.ensure((size_t)bandBlocks * 32 * SPB_CAND_STRIDE * 4);
     a.sortPrimaryHits = (bounces > 1 && L.sortBounceRays) ? 1 : 0;
     if (a.sortPrimaryHits) L.wStage.ensure(slots * 32);
     a.stage = (v4f *)L.wStage.ptr;
@@ -540,6 +548,12 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
         const uint32_t first = band * bandBlocks;
         a.blockList = (const uint32_t *)L.wBlockList.ptr + first;
         a.bandBlocks = first + bandBlocks <= covered ? bandBlocks : covered - first;
+        a.candidates = nullptr;
+        if (useCandidates)
+        {
+            launch_candidates(a, (uint32_t *)L.wCand.ptr, L.stream);
+            a.candidates = (const uint32_t *)L.wCand.ptr;
+        }
         for (uint32_t pass = 0; pass < passes; ++pass)
         {
             a.firstSample = pass * S;
@@ -627,7 +641,7 @@ extern "C" void sp_b200_Shutdown(void)
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
-    L.wMask.release(); L.wBlockList.release(); L.wStage.release();
+    L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release();
     for (cudaEvent_t e : L.traceEvents) cudaEventDestroy(e);
     L.traceEvents.clear();
     L.traceEventsUsed = 0;
@@ -673,6 +687,7 @@ extern "C" void sp_b200_FlushTextureCache(void)
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
 extern "C" void sp_b200_SetSkyCulling(int enable) { lib().skyCulling = enable != 0; }
+extern "C" void sp_b200_SetPrimaryCandidates(int enable) { lib().primaryCandidates = enable != 0; }
 extern "C" void sp_b200_SetRaySorting(int enable)
 {
     lib().sortBounceRays = enable != 0;

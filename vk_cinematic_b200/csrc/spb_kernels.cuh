@@ -172,7 +172,15 @@ struct WaveArgs
     // walking: 1 = packet mode (the whole warp starts and ends together; best when its rays are
     // coherent), SPB_REFILL_THRESHOLD otherwise.  Set per launch by the host.
     uint32_t refillThreshold;
+    // Per pixel of the pass (block-major, like the items): candidate triangles of its camera rays
+    // (k_candidates): SPB_CAND_STRIDE words per pixel, [0] = count or SPB_CAND_FALLBACK, then the
+    // triangle slots.  Null: every primary ray walks the tree.
+    const uint32_t *candidates;
 };
+// triangle slots kept per pixel; a pixel whose padded centre ray enters more leaf boxes falls back
+#define SPB_CAND_MAX 23u
+#define SPB_CAND_STRIDE (SPB_CAND_MAX + 1u)
+#define SPB_CAND_FALLBACK 0xFFFFFFFFu
 // items (pixel x sample, block-major) whose bounce rays are ordered together
 #define SPB_SORT_TILE 2048u
 
@@ -188,6 +196,8 @@ void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t b
 // (bounce 0 needs sortPrimaryHits: primary results by item; not for the last bounce)
 void launch_wave_shade_sorted(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
 void launch_wave_accumulate(const WaveArgs &args, cudaStream_t stream);
+// single-object scenes: candidate triangles per pixel of the pass (see k_candidates)
+void launch_candidates(const WaveArgs &args, uint32_t *candidates, cudaStream_t stream);
 // Pixels of the strip whose block is not in the list: every sample's camera ray leaves the scene
 // untouched, so the whole pixel is evaluated in one thread: ray generation, background material,
 // accumulation in sample order.  Adds the pixels it shaded to stats[CTR_SKY_PIXELS] and their cost

@@ -249,6 +249,7 @@ _SIGNATURES = {
     "sp_b200_SetPathsPerPass": (None, [u32]),
     "sp_b200_SetSkyCulling": (None, [C.c_int]),
     "sp_b200_SetRaySorting": (None, [C.c_int]),
+    "sp_b200_SetPrimaryCandidates": (None, [C.c_int]),
     "sp_b200_SetRefillThresholds": (None, [u32, u32, u32]),
     "sp_b200_Seed": (u32, [u32, u32, u32]),
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
