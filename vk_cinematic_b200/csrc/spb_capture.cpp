@@ -1,6 +1,7 @@
 // spb_capture.cpp -- see spb_capture.h
 #include "spb_capture.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -231,6 +232,19 @@ void convert_materials(const sp_MaterialSystem *ms, const v4f *const *imagePixel
         out->roughness[i] = m.roughness;
         out->albedoImage[i] = find_image(m.albedoTexture);
         out->emissionImage[i] = find_image(m.emissionTexture);
+    }
+    // see miss_radiance() in spb_core.cuh; an unknown background id shades as albedo 0, roughness 0
+    {
+        int slot = -1;
+        for (uint32_t i = 0; i < out->count; ++i)
+            if (out->keys[i] == out->backgroundId) { slot = (int)i; break; }
+        out->simpleBackground = 1;
+        if (slot >= 0)
+        {
+            bool ok = out->albedoImage[slot] < 0 && std::isfinite(out->roughness[slot]) && out->roughness[slot] >= 0.0f;
+            for (int k = 0; k < 3; ++k) ok = ok && std::isfinite(out->albedo[slot][k]) && out->albedo[slot][k] >= 0.0f;
+            out->simpleBackground = ok ? 1u : 0u;
+        }
     }
     for (uint32_t i = 0; i < out->imageCount; ++i)
     {

@@ -220,7 +220,9 @@ struct DMaterials
     uint32_t count;
     uint32_t backgroundId;
     uint32_t imageCount;
-    uint32_t pad;
+    // 1 when the vertex terms of an escaped ray cannot influence its radiance (see
+    // miss_radiance()): set by convert_materials()
+    uint32_t simpleBackground;
     uint32_t keys[SPB_MAX_MATERIALS];
     float albedo[SPB_MAX_MATERIALS][3];
     float emission[SPB_MAX_MATERIALS][3];
@@ -1138,6 +1140,28 @@ SPB_HD f3 fold_radiance(const VertexTerms &vt, f3 incoming, float clampValue)
         incoming.z = rmin(rmax(incoming.z, 0.0f), clampValue);
     }
     return add3(vt.E, mul3(had3(vt.W, incoming), vt.cosine));
+}
+
+// Radiance of the vertex where a ray escapes (simd_path_tracer.cpp:290-300 creates it with
+// incomingDir = normal = 0; ComputeRadianceForPath folds it first, with zero incoming radiance):
+//   L = E + (W (.) clamp(0)) * cosine,  cosine = Max(0, Dot(0, 0)) = +0.
+// When the background material has a constant, finite, non-negative albedo and a finite
+// non-negative roughness, W is finite and non-negative for every direction (F in [0.04, 1],
+// D = a2 / pi, G = 0 / k with k = (r + 1)^2 / 8 > 0), so W * 0 * 0 = +0 and L = E + (+0) in every
+// component: exactly E, with a -0 turned into +0 -- which is what `E + 0.0f` computes, NaN and inf
+// included.  The Fresnel / GGX / Smith terms (a pow and a dozen divisions per escaped ray) are then
+// dead arithmetic.  Any other background material takes the full evaluation.
+template <int MATH, int ENVFILTER>
+SPB_HD f3 miss_radiance(const DMaterials &M, f3 V, float clampValue, Counters *counters)
+{
+    f3 zero = mk3(0.0f, 0.0f, 0.0f);
+    if (M.simpleBackground)
+    {
+        MaterialOut mo = evaluate_material<MATH, ENVFILTER>(M, M.backgroundId, V, 0.0f, 0.0f, counters);
+        return mk3(mo.emission.x + 0.0f, mo.emission.y + 0.0f, mo.emission.z + 0.0f);
+    }
+    VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, V, 0.0f, 0.0f, counters);
+    return fold_radiance(vt, zero, clampValue);
 }
 
 // RandomDirectionOnHemisphere (math_lib.h:932-946)

@@ -499,7 +499,17 @@ __device__ __forceinline__ VertexTerms load_terms(const v4f *pathTerms, size_t i
     return vt;
 }
 
-// radiance of the finished path: fold the last vertex, then the stored ones back to the eye
+// radiance of the finished path: the last vertex's radiance, then the stored vertices folded back
+// to the eye
+__device__ __forceinline__ void finish_path_from(const WaveArgs &a, f3 radiance, uint32_t bounce, uint32_t path)
+{
+    for (int i = (int)bounce - 1; i >= 0; --i)
+        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
+    v4f r;
+    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
+    a.rad[path] = r;
+}
+
 __device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms &last, uint32_t bounce,
                                             uint32_t path)
 {
@@ -552,9 +562,7 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
             v4f rb = rays[(size_t)slot * 2 + 1];
             path = f2u(rb.w);
             f3 V = neg3(mk3(rb.x, rb.y, rb.z));
-            f3 zero = mk3(0.0f, 0.0f, 0.0f);
-            VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, V, 0.0f, 0.0f, &cnt);
-            finish_path(a, vt, bounce, path);
+            finish_path_from(a, miss_radiance<MATH, ENVFILTER>(M, V, a.clampValue, &cnt), bounce, path);
         }
         count_row(a, path, active, SPB_COST_MISS);
     }
@@ -913,9 +921,7 @@ k_sky(const __grid_constant__ WaveArgs a)
                 uint32_t rng = stream_seed(pixelIndex, s, a.frame);
                 f3 o, d;
                 primary_ray(a.camera, x, y, rng, o, d);
-                f3 zero = mk3(0.0f, 0.0f, 0.0f);
-                VertexTerms vt = vertex_terms<MATH, ENVFILTER>(M, M.backgroundId, zero, zero, neg3(d), 0.0f, 0.0f, &cnt);
-                f3 radiance = fold_radiance(vt, zero, a.clampValue);
+                f3 radiance = miss_radiance<MATH, ENVFILTER>(M, neg3(d), a.clampValue, &cnt);
                 total = add3(total, mul3(radiance, weight));
             }
             v4f out;
