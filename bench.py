@@ -513,6 +513,10 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
             "rays_per_step": rays / args.steps,
+            "rays_accounting": "rays = the reference's sp_Metric_RaysTraced for the same frame (one per "
+                               "sp_RayIntersectScene call it would make, simd_path_tracer.cpp:242); camera rays of "
+                               "pixels the coverage pass proves empty are counted but never traced (sky kernel); "
+                               "roofline.traced_rays_per_step is what went through the traversal kernel",
             "e2e": {"value": e2e_value, "unit": "Mrays/s",
                     "h2d_bytes_per_step": scene_bytes * world,
                     "d2h_bytes_per_step": H * Wd * 16, "ms_per_step": e2e_secs / args.steps * 1e3},

@@ -264,7 +264,8 @@ void sp_b200_SetPathsPerPass(u32 paths);
 /* Wavefront mode: pixels outside the padded screen rectangle of the scene's world bounds are
  * evaluated by a queue-less kernel (their rays cannot hit anything).  On by default; results do
  * not depend on it. */
-void sp_b200_SetSkyCulling(int enable);
+void sp_b200_SetSkyCulling(int enable); /* 0 off; 1 on, per-sample loop for every sky pixel; 2 (default) on,
+                                           sky pixels whose samples provably read one texel settled by one lookup */
 /* Wavefront mode: the rays leaving the primary hits of a tile of 2048 paths are written in
  * direction order, so a warp of the trace kernel walks rays with neighbouring origins and similar
  * directions.  On by default; results do not depend on it. */

@@ -492,9 +492,12 @@ def test_coverage_mask_and_ray_sorting_edge_cases(gpu_sp, case):
     sp.lib.sp_b200_SetPathsPerPass(50000)
     img2, m2 = r.render_frame(frame=5)
     assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5])
-    sp.lib.sp_b200_SetSkyCulling(1)
+    sp.lib.sp_b200_SetSkyCulling(1)     # sky kernel with the per-sample loop for every pixel
     sp.lib.sp_b200_SetRaySorting(1)
     sp.lib.sp_b200_SetPrimaryCandidates(1)
+    img2, m2 = r.render_frame(frame=5)
+    assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5])
+    sp.lib.sp_b200_SetSkyCulling(2)     # default: one lookup where provably enough
     for thresholds in ((1, 1, 1), (12, 12, 12), (1, 0, 12)):
         sp.lib.sp_b200_SetRefillThresholds(*thresholds)
         img2, m2 = r.render_frame(frame=5)
@@ -538,7 +541,7 @@ def test_wavefront_pass_split_and_stats(gpu_sp):
     _, cost_all = r.render_rows(0, 150, frame=3, want_cost=True)
     # cost units: 4 per escaped ray, 20 per surface hit; a sky-kernel sample counts 1
     assert int(cost_all.sum()) == 4 * int(ref_m[4]) + 20 * int(ref_m[3]) and len(cost_all) == 3
-    sp.lib.sp_b200_SetSkyCulling(1)
+    sp.lib.sp_b200_SetSkyCulling(2)
     _, cost_sky = r.render_rows(0, 150, frame=3, want_cost=True)
     saved = int(cost_all.sum()) - int(cost_sky.sum())
     assert saved > 0 and saved % (3 * 7) == 0 and np.all(cost_sky <= cost_all)   # 3 units x 7 spp per sky pixel

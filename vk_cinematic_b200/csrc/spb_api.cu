@@ -115,6 +115,7 @@ struct Library
     bool skyCulling = true;    // sp_b200_SetSkyCulling
     bool sortBounceRays = true; // sp_b200_SetRaySorting
     bool primaryCandidates = true; // sp_b200_SetPrimaryCandidates
+    bool skyOneLookup = true;      // sp_b200_SetSkyCulling(2 = on with, 1 = on without the one-lookup path)
     uint32_t sortBounces = 1;   // bounces whose outgoing rays are direction-sorted (A/B knob)
     // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
     // 0 for the sorted class = measured choice between packet mode (1) and SPB_REFILL_THRESHOLD:
@@ -149,7 +150,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand, wSkyList;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
 
     Library()
@@ -456,7 +457,32 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.blockMask = (const uint8_t *)L.wMask.ptr;
     launch_coverage(a, instancedTriangles, !L.skyCulling, (uint8_t *)L.wMask.ptr, (uint32_t *)L.wBlockList.ptr,
                     listCount, L.stream);
+    // Sky pixels whose samples provably read one environment texel are settled with one lookup
+    // (k_sky, spb_wavefront.cu); `spread` bounds how far a sample's direction can be from the
+    // pixel centre's: (jitter + one rounding step of the pixel coordinate) x the angle of a pixel,
+    // times 4, plus 1e-6 for the rounding of the normalisation.
+    a.skyList = nullptr;
+    a.skyDirectionSpread = 0.0f;
+    if (L.skyOneLookup && ra.camera.width <= 65535u && ra.camera.height <= 65535u)
+    {
+        const DCamera &c = ra.camera;
+        double fx = (double)c.filmCenter.x - c.position.x, fy = (double)c.filmCenter.y - c.position.y,
+               fz = (double)c.filmCenter.z - c.position.z;
+        double dist = sqrt(fx * fx + fy * fy + fz * fz);
+        double jitter = fmax(fabs((double)c.halfPixelWidth), fabs((double)c.halfPixelHeight)) +
+                        1.2e-7 * (double)(c.width > c.height ? c.width : c.height);
+        double pixelAngle = dist > 0.0 ? 2.0 * fmax((double)c.halfFilmWidth / c.width, (double)c.halfFilmHeight / c.height) / dist : 1.0;
+        double spread = 4.0 * jitter * pixelAngle + 1.0e-6;
+        if (spread < 1.0e-4 && c.halfPixelWidth >= 0.0f && c.halfPixelHeight >= 0.0f)
+        {
+            L.wSkyList.ensure(((size_t)width * height + 1) * 4);
+            SPB_CUDA(cudaMemsetAsync(L.wSkyList.ptr, 0, 4, L.stream));
+            a.skyList = (uint32_t *)L.wSkyList.ptr;
+            a.skyDirectionSpread = (float)spread;
+        }
+    }
     launch_sky(cfg, a, L.stream);
+    if (a.skyList) launch_sky_listed(cfg, a, L.stream);
     uint32_t covered = 0;
     SPB_CUDA(cudaMemcpyAsync(&covered, listCount, 4, cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
@@ -641,7 +667,7 @@ extern "C" void sp_b200_Shutdown(void)
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
-    L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release();
+    L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release(); L.wSkyList.release();
     for (cudaEvent_t e : L.traceEvents) cudaEventDestroy(e);
     L.traceEvents.clear();
     L.traceEventsUsed = 0;
@@ -686,7 +712,11 @@ extern "C" void sp_b200_FlushTextureCache(void)
 }
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
-extern "C" void sp_b200_SetSkyCulling(int enable) { lib().skyCulling = enable != 0; }
+extern "C" void sp_b200_SetSkyCulling(int enable)
+{
+    lib().skyCulling = enable != 0;
+    lib().skyOneLookup = enable != 1; // 1: coverage + sky kernel with the per-sample loop only
+}
 extern "C" void sp_b200_SetPrimaryCandidates(int enable) { lib().primaryCandidates = enable != 0; }
 extern "C" void sp_b200_SetRaySorting(int enable)
 {

@@ -1030,6 +1030,19 @@ SPB_HD f3 sample_bilinear(const DImage &img, float u, float v)
 
 struct MaterialOut { f3 albedo, emission; float roughness; };
 
+// ToSphericalCoordinates (math_lib.h:849-860), MapToEquirectangular (math_lib.h:873-884), then
+// uv.y = 1 - uv.y (sp_material_system.cpp:88-93)
+template <int MATH>
+SPB_HD void equirect_uv(f3 dir, float &eu, float &ev)
+{
+    float inc = m_atan2<MATH>(sqrtf(dir.x * dir.x + dir.z * dir.z), dir.y);
+    float az = m_atan2<MATH>(dir.z, dir.x);
+    if (az < 0.0f) az += 2.0f * SPB_PI;
+    eu = az / (2.0f * SPB_PI);
+    ev = m_cos<MATH>(inc) * 0.5f + 0.5f;
+    ev = 1.0f - ev;
+}
+
 // sp_FindMaterialById + sp_EvaluateMaterial (sp_material_system.cpp:15-29, 59-105) and the
 // missing-material fallback of ComputeRadianceForPath (simd_path_tracer.cpp:122-133)
 template <int MATH, int ENVFILTER>
@@ -1065,13 +1078,8 @@ SPB_HD MaterialOut evaluate_material(const DMaterials &M, uint32_t materialId, f
     {
         // ToSphericalCoordinates(-outgoingDir) (math_lib.h:849-860), MapToEquirectangular
         // (math_lib.h:873-884), then uv.y = 1 - uv.y (sp_material_system.cpp:88-93)
-        f3 dir = neg3(outgoingDir);
-        float inc = m_atan2<MATH>(sqrtf(dir.x * dir.x + dir.z * dir.z), dir.y);
-        float az = m_atan2<MATH>(dir.z, dir.x);
-        if (az < 0.0f) az += 2.0f * SPB_PI;
-        float eu = az / (2.0f * SPB_PI);
-        float ev = m_cos<MATH>(inc) * 0.5f + 0.5f;
-        ev = 1.0f - ev;
+        float eu, ev;
+        equirect_uv<MATH>(neg3(outgoingDir), eu, ev);
         if (ENVFILTER == 0)
             out.emission = sample_nearest(M.images[ei], eu, ev, counters);
         else

@@ -176,6 +176,11 @@ struct WaveArgs
     // (k_candidates): SPB_CAND_STRIDE words per pixel, [0] = count or SPB_CAND_FALLBACK, then the
     // triangle slots.  Null: every primary ray walks the tree.
     const uint32_t *candidates;
+    // k_sky: > 0 enables the one-lookup path for pixels whose samples provably read one texel;
+    // the value bounds |direction of any sample - direction of the pixel centre| (host: jitter
+    // and pixel angle of the camera).  skyList[0] counts, skyList[1..] lists the other pixels.
+    float skyDirectionSpread;
+    uint32_t *skyList;
 };
 // triangle slots kept per pixel; a pixel whose padded centre ray enters more leaf boxes falls back
 #define SPB_CAND_MAX 23u
@@ -203,5 +208,7 @@ void launch_candidates(const WaveArgs &args, uint32_t *candidates, cudaStream_t 
 // accumulation in sample order.  Adds the pixels it shaded to stats[CTR_SKY_PIXELS] and their cost
 // to tileRowCost.
 void launch_sky(const KernelConfig &cfg, const WaveArgs &args, cudaStream_t stream);
+// the pixels k_sky listed in skyList (full sample loop); reads the count from the device
+void launch_sky_listed(const KernelConfig &cfg, const WaveArgs &args, cudaStream_t stream);
 
 } // namespace spb

@@ -895,10 +895,85 @@ k_list_blocks(unsigned blocks, uint8_t *coverage, uint32_t *blockList, uint32_t 
 // (simd_path_tracer.cpp:216-321) with the miss branch only -- same functions, same order of
 // operations as k_trace<PRIMARY> + k_shade_miss + k_accumulate, without the queues in between.
 template <int MATH, int ENVFILTER>
+__device__ __forceinline__ void sky_pixel_samples(const WaveArgs &a, const DMaterials &M, unsigned x, unsigned y,
+                                                  Counters &cnt)
+{
+    const float weight = 1.0f / (float)a.spp;
+    uint32_t pixelIndex = x + y * a.camera.width;
+    f3 total = mk3(0.0f, 0.0f, 0.0f);
+    for (unsigned s = 0; s < a.spp; ++s)
+    {
+        uint32_t rng = stream_seed(pixelIndex, s, a.frame);
+        f3 o, d;
+        primary_ray(a.camera, x, y, rng, o, d);
+        f3 radiance = miss_radiance<MATH, ENVFILTER>(M, neg3(d), a.clampValue, &cnt);
+        total = add3(total, mul3(radiance, weight));
+    }
+    v4f out;
+    out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
+    a.out[(size_t)pixelIndex] = out;
+}
+
+// One-lookup path.  With a simple background (miss_radiance) a sky sample's radiance is the texel
+// its direction selects, E + 0.0f.  The samples of a pixel differ from the jitter-free centre
+// direction c by at most `spread` (a.skyDirectionSpread: jitter x pixel angle plus the rounding of
+// ray generation, with a factor 4 -- host).  Along the reference's chain (equirect_uv, nearest
+// sampling: image.h:3-18) that moves the image coordinates by at most
+//   |d fx| <= W * ((1.5 spread / r + 4e-7) / (2 pi) + 6e-8),  r = sqrt(cx^2 + cz^2)   (atan2(z, x), +2 pi, / 2 pi)
+//   |d fy| <= H * (spread + 4e-7)                                                     (atan2(r, y), cos, * 0.5 + 0.5, 1 -)
+// roundings of the single-precision steps included (the transcendental steps are correctly rounded
+// in deterministic-math mode, the only mode this path is used in).  If the centre's coordinates are
+// further than TWICE those bounds from the next texel boundary, every sample reads the centre's
+// texel, and the pixel is spp times the same addition: total += E * (1 / spp), no per-sample ray at
+// all.  The az = 0 seam, the poles (r < 1e-3) and the image edges sit on boundaries or are excluded
+// explicitly; such pixels, about 4 %, are listed for k_sky_listed, which runs the sample loop.
+template <int MATH, int ENVFILTER>
+__device__ __forceinline__ bool sky_pixel_one_lookup(const WaveArgs &a, const DMaterials &M, unsigned x, unsigned y)
+{
+    if (!(a.skyDirectionSpread > 0.0f) || MATH != 0 || ENVFILTER != 0 || !M.simpleBackground) return false;
+    int slot = -1;
+    for (uint32_t i = 0; i < M.count; ++i)
+        if (M.keys[i] == M.backgroundId) { slot = (int)i; break; }
+    f3 E;
+    if (slot < 0) E = mk3(1.0f, 0.0f, 1.0f);
+    else if (M.emissionImage[slot] < 0) E = mk3(M.emission[slot][0], M.emission[slot][1], M.emission[slot][2]);
+    else
+    {
+        const DCamera &cam = a.camera;
+        float fx = ((float)x + 0.5f) / (float)cam.width, fy = 1.0f - ((float)y + 0.5f) / (float)cam.height;
+        fx = fx * 2.0f - 1.0f;
+        fy = fy * 2.0f - 1.0f;
+        f3 filmP = add3(add3(mul3(cam.right, cam.halfFilmWidth * fx), mul3(cam.up, cam.halfFilmHeight * fy)), cam.filmCenter);
+        f3 c = normalize3(sub3(filmP, cam.position));
+        const DImage &img = M.images[M.emissionImage[slot]];
+        float eu, ev;
+        equirect_uv<MATH>(c, eu, ev);
+        const float W = (float)img.width, H = (float)img.height, spread = a.skyDirectionSpread;
+        float r = sqrtf(c.x * c.x + c.z * c.z);
+        float u = eu * W, v = ev * H;
+        float flu = floorf(u), flv = floorf(v);
+        float mx = 2.0f * W * ((1.5f * spread / r + 4.0e-7f) * 0.15915494f + 6.0e-8f);
+        float my = 2.0f * H * (spread + 4.0e-7f);
+        bool stable = r >= 1.0e-3f && u - flu > mx && u - flu < 1.0f - mx && v - flv > my && v - flv < 1.0f - my &&
+                      flu >= 0.0f && flv >= 0.0f && flu < W && flv < H && mx < 0.25f && my < 0.25f;
+        if (!stable) return false; // NaN coordinates end here as well
+        v4f p = ld4(img.pixels + (size_t)flv * img.width + (size_t)flu);
+        E = mk3(p.x, p.y, p.z);
+    }
+    const float weight = 1.0f / (float)a.spp;
+    const f3 term = mul3(mk3(E.x + 0.0f, E.y + 0.0f, E.z + 0.0f), weight);
+    f3 total = mk3(0.0f, 0.0f, 0.0f);
+    for (unsigned s = 0; s < a.spp; ++s) total = add3(total, term);
+    v4f out;
+    out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
+    a.out[(size_t)x + (size_t)y * a.camera.width] = out;
+    return true;
+}
+
+template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_sky(const __grid_constant__ WaveArgs a)
 {
-    const float weight = 1.0f / (float)a.spp;
     const DMaterials &M = *a.materials;
     Counters cnt = {0, 0, 0, 0};
     unsigned shaded = 0;
@@ -912,22 +987,24 @@ k_sky(const __grid_constant__ WaveArgs a)
         unsigned by = blk / a.blocksX, bx = blk - by * a.blocksX;
         unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
         bool active = blk < a.blocksX * a.blocksY && x < a.x1 && y < a.y1 && a.blockMask[blk] == 0;
+        bool listed = false;
         if (active)
         {
-            uint32_t pixelIndex = x + y * a.camera.width;
-            f3 total = mk3(0.0f, 0.0f, 0.0f);
-            for (unsigned s = 0; s < a.spp; ++s)
-            {
-                uint32_t rng = stream_seed(pixelIndex, s, a.frame);
-                f3 o, d;
-                primary_ray(a.camera, x, y, rng, o, d);
-                f3 radiance = miss_radiance<MATH, ENVFILTER>(M, neg3(d), a.clampValue, &cnt);
-                total = add3(total, mul3(radiance, weight));
-            }
-            v4f out;
-            out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
-            a.out[(size_t)pixelIndex] = out;
+            if (a.skyList) listed = !sky_pixel_one_lookup<MATH, ENVFILTER>(a, M, x, y);
+            else sky_pixel_samples<MATH, ENVFILTER>(a, M, x, y, cnt);
             shaded++;
+        }
+        if (a.skyList)
+        {
+            // warp-aggregated append of the pixels that need the sample loop
+            unsigned mask = __ballot_sync(SPB_FULL, listed);
+            if (mask)
+            {
+                unsigned base = 0;
+                if (lane_id() == (unsigned)(__ffs(mask) - 1)) base = atomicAdd(&a.skyList[0], (unsigned)__popc(mask));
+                base = __shfl_sync(SPB_FULL, base, __ffs(mask) - 1);
+                if (listed) a.skyList[1 + base + __popc(mask & lanemask_lt())] = x | (y << 16);
+            }
         }
         if (a.tileRowCost)
         {
@@ -939,6 +1016,26 @@ k_sky(const __grid_constant__ WaveArgs a)
     }
     shaded = __reduce_add_sync(SPB_FULL, shaded);
     if (lane_id() == 0 && shaded) atomicAdd(&a.stats[CTR_SKY_PIXELS], (unsigned long long)shaded);
+    if (a.countStats)
+    {
+        unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
+        if (lane_id() == 0 && e) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)e);
+    }
+}
+
+// the sky pixels k_sky could not settle with one lookup: the sample loop, every lane busy
+template <int MATH, int ENVFILTER>
+__global__ void __launch_bounds__(256)
+k_sky_listed(const __grid_constant__ WaveArgs a)
+{
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    const unsigned count = a.skyList[0];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        unsigned packed = a.skyList[1 + i];
+        sky_pixel_samples<MATH, ENVFILTER>(a, M, packed & 0xFFFFu, packed >> 16, cnt);
+    }
     if (a.countStats)
     {
         unsigned e = __reduce_add_sync(SPB_FULL, cnt.envClamped);
@@ -1045,6 +1142,20 @@ void launch_sky(const KernelConfig &cfg, const WaveArgs &a, cudaStream_t stream)
     case 1: k_sky<0, 1><<<grid, 256, 0, stream>>>(a); break;
     case 2: k_sky<1, 0><<<grid, 256, 0, stream>>>(a); break;
     default: k_sky<1, 1><<<grid, 256, 0, stream>>>(a); break;
+    }
+}
+
+void launch_sky_listed(const KernelConfig &cfg, const WaveArgs &a, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    unsigned grid = shade_grid();
+    int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
+    switch (key)
+    {
+    case 0: k_sky_listed<0, 0><<<grid, 256, 0, stream>>>(a); break;
+    case 1: k_sky_listed<0, 1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: k_sky_listed<1, 0><<<grid, 256, 0, stream>>>(a); break;
+    default: k_sky_listed<1, 1><<<grid, 256, 0, stream>>>(a); break;
     }
 }
 
