@@ -919,8 +919,8 @@ __device__ __forceinline__ void sky_pixel_samples(const WaveArgs &a, const DMate
 // direction c by at most `spread` (a.skyDirectionSpread: jitter x pixel angle plus the rounding of
 // ray generation, with a factor 4 -- host).  Along the reference's chain (equirect_uv, nearest
 // sampling: image.h:3-18) that moves the image coordinates by at most
-//   |d fx| <= W * ((1.5 spread / r + 4e-7) / (2 pi) + 6e-8),  r = sqrt(cx^2 + cz^2)   (atan2(z, x), +2 pi, / 2 pi)
-//   |d fy| <= H * (spread + 4e-7)                                                     (atan2(r, y), cos, * 0.5 + 0.5, 1 -)
+//   |d fx| <= W * ((1.5 spread / r + 4e-7) / (2 pi) + 1.8e-7),  r = sqrt(cx^2 + cz^2)  (atan2(z, x), +2 pi, / 2 pi, * W)
+//   |d fy| <= H * (spread + 5.2e-7)                                                    (atan2(r, y), cos, * 0.5 + 0.5, 1 -, * H)
 // roundings of the single-precision steps included (the transcendental steps are correctly rounded
 // in deterministic-math mode, the only mode this path is used in).  If the centre's coordinates are
 // further than TWICE those bounds from the next texel boundary, every sample reads the centre's
@@ -952,8 +952,9 @@ __device__ __forceinline__ bool sky_pixel_one_lookup(const WaveArgs &a, const DM
         float r = sqrtf(c.x * c.x + c.z * c.z);
         float u = eu * W, v = ev * H;
         float flu = floorf(u), flv = floorf(v);
-        float mx = 2.0f * W * ((1.5f * spread / r + 4.0e-7f) * 0.15915494f + 6.0e-8f);
-        float my = 2.0f * H * (spread + 4.0e-7f);
+        // (+ 1.2e-7: the rounding of the products eu * W, ev * H when the size is not a power of two)
+        float mx = 2.0f * W * ((1.5f * spread / r + 4.0e-7f) * 0.15915494f + 6.0e-8f + 1.2e-7f);
+        float my = 2.0f * H * (spread + 4.0e-7f + 1.2e-7f);
         bool stable = r >= 1.0e-3f && u - flu > mx && u - flu < 1.0f - mx && v - flv > my && v - flv < 1.0f - my &&
                       flu >= 0.0f && flv >= 0.0f && flu < W && flv < H && mx < 0.25f && my < 0.25f;
         if (!stable) return false; // NaN coordinates end here as well
