@@ -187,7 +187,9 @@ struct WaveArgs
 #define SPB_CAND_STRIDE (SPB_CAND_MAX + 1u)
 #define SPB_CAND_FALLBACK 0xFFFFFFFFu
 // items (pixel x sample, block-major) whose bounce rays are ordered together
+#ifndef SPB_SORT_TILE
 #define SPB_SORT_TILE 2048u
+#endif
 
 // Coverage pass: marks every 8x4 pixel block of the strip that the (2-pixel padded) screen bounding
 // box of some triangle touches; coverage[blocks] = 1 flags "everything" (a triangle straddles the
