@@ -285,7 +285,7 @@ u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
  * hostPixels (RGBA f32, full-image indexing, may be NULL) receives the rows by D2H copy;
  * devicePixels (device pointer to a full image, may be NULL) receives them in place.
  * tileRowCost (may be NULL): per tile-row device cost in cost units (wavefront mode: 1 per sample
- * of a sky-kernel pixel, 4 per escaped ray traced through the queues, 20 per surface hit; per-pixel
+ * of a sky-kernel pixel, 16 per escaped ray traced through the queues, 80 per surface hit; per-pixel
  * mode: rays traced), rowEnd-rowBegin rounded up to tiles.  Returns 0 on success. */
 int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels,
                        void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);

@@ -109,11 +109,11 @@ void launch_tone_map(const KernelConfig &cfg, const v4f *pixels, uint32_t count,
 #define SPB_TRACE_MIN_BLOCKS 5
 #endif
 // tile-row cost units (sp_b200_RenderRows tileRowCost): per sky-kernel sample / escaped ray / surface hit
-// (measured on C3: a sky-kernel sample ~23 ps, an escaped ray through the queues ~85 ps, a surface
-// hit with everything it triggers ~450 ps)
+// (measured on C3: a sky-kernel sample ~5 ps since most sky pixels take one lookup, an escaped ray
+// through the queues ~85 ps, a surface hit with everything it triggers ~400 ps)
 #define SPB_COST_SKY 1u
-#define SPB_COST_MISS 4u
-#define SPB_COST_HIT 20u
+#define SPB_COST_MISS 16u
+#define SPB_COST_HIT 80u
 // a warp keeps walking until fewer than this many of its lanes still have a node to visit,
 // then retires the finished lanes and refills them from the queue
 #ifndef SPB_REFILL_THRESHOLD
