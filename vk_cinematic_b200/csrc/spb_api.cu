@@ -87,8 +87,6 @@ struct DeviceScene
     uint32_t nodeCount = 0;
     uint32_t maxDepth = 0;
     size_t deviceBytes = 0;
-    float worldMin[3] = {0, 0, 0}, worldMax[3] = {0, 0, 0}; // union of the objects' world AABBs
-    bool hasBounds = false;
     ~DeviceScene()
     {
         nodes.release(); tris.release(); shade.release();
@@ -247,8 +245,6 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
         log_message("scene needs %u traversal stack entries, the kernels provide %u", fs.stackNeed + 2, SPB_STACK_SIZE);
         abort();
     }
-    for (int k = 0; k < 3; ++k) { ds->worldMin[k] = fs.worldMin[k]; ds->worldMax[k] = fs.worldMax[k]; }
-    ds->hasBounds = fs.objectCount > 0;
     ds->deviceBytes = (fs.nodes.size() + fs.tris.size() + fs.shade.size() + fs.objInv.size() +
                        fs.objModel.size()) * sizeof(v4f) + fs.objInfo.size() * sizeof(v4u);
     return ds;
@@ -1342,8 +1338,6 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     args.counters = ctr;
     args.tileRowCost = tileRowCost ? ctr + CTR_COUNT : nullptr;
     args.tileHeight = tileH;
-    for (int k = 0; k < 3; ++k) { args.boundsMin[k] = ds->worldMin[k]; args.boundsMax[k] = ds->worldMax[k]; }
-    args.hasBounds = ds->hasBounds ? 1 : 0;
     // the kernel tiles the rectangle from y0 in 16-row CTAs; keep CTA rows inside one tile row
     // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
     SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);

@@ -188,8 +188,6 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
         {
             mn[(size_t)i * 3 + k] = ob.aabbMin[k];
             mx[(size_t)i * 3 + k] = ob.aabbMax[k];
-            if (i == 0 || ob.aabbMin[k] < fs.worldMin[k]) fs.worldMin[k] = ob.aabbMin[k];
-            if (i == 0 || ob.aabbMax[k] > fs.worldMax[k]) fs.worldMax[k] = ob.aabbMax[k];
         }
     }
     if (count > 0)

@@ -51,8 +51,6 @@ struct FlatScene
     uint64_t triangleCount = 0;
     uint32_t maxDepth = 0;
     uint32_t stackNeed = 0; // worst-case traversal stack entries: TLAS + deepest mesh tree
-    // union of the objects' world AABBs (sp_scene.cpp:98-113); valid when objectCount > 0
-    float worldMin[3] = {0, 0, 0}, worldMax[3] = {0, 0, 0};
 };
 
 std::shared_ptr<MeshAccel> build_mesh_accel(const VertexPNT *vertices, uint32_t vertexCount,

@@ -35,9 +35,6 @@ struct RenderArgs
     unsigned long long *counters;     // CTR_COUNT slots
     unsigned long long *tileRowCost;  // may be null; rays per tile row, row 0 = y0 / tileHeight
     uint32_t tileHeight;
-    // host only: world bounds of everything in the scene (valid if hasBounds)
-    float boundsMin[3], boundsMax[3];
-    int hasBounds;
 };
 
 // number of kernels this library has launched since load (bench.py's gpu_launches)
