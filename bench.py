@@ -127,7 +127,7 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
