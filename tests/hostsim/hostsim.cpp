@@ -315,3 +315,85 @@ extern "C" void ora_intersect_rays(ora_Scene *s, uint32_t n, const float *origin
     }
     (void)metrics;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Shortcuts of the wavefront renderer (spb_core.cuh collect_candidates / resolve_from_candidates /
+// sky_one_lookup) against the plain evaluation, pixel by pixel, on the host.
+//   out[0] pixels, [1] camera rays, [2] pixels whose candidate list fell back, [3] rays whose
+//   shortcut result differs from the walk's (t bits, triangle slot or object), [4] of those, rays
+//   where only the slot differs at bit-equal t (ties), [5] pixels all of whose samples escape,
+//   [6] of those, pixels the one-lookup path settles, [7] of those, pixels whose value differs
+//   from the sample loop's, [8] sum of candidate counts.
+extern "C" void hostsim_check_shortcuts(ora_Scene *s, uint32_t spp, uint32_t frame, uint32_t threads, uint64_t *out9)
+{
+    refresh(s);
+    if (threads == 0) threads = 1;
+    const DCamera &c = s->dc;
+    // spread: the host formula of render_wavefront (spb_api.cu)
+    double fx = (double)c.filmCenter.x - c.position.x, fy = (double)c.filmCenter.y - c.position.y,
+           fz = (double)c.filmCenter.z - c.position.z;
+    double dist = sqrt(fx * fx + fy * fy + fz * fz);
+    double jitter = fmax(fabs((double)c.halfPixelWidth), fabs((double)c.halfPixelHeight)) +
+                    1.2e-7 * (double)(c.width > c.height ? c.width : c.height);
+    double pixelAngle = dist > 0.0 ? 2.0 * fmax((double)c.halfFilmWidth / c.width, (double)c.halfFilmHeight / c.height) / dist : 1.0;
+    const float spread = (float)(4.0 * jitter * pixelAngle + 1.0e-6);
+    const bool single = s->d.objectCount == 1 && s->d.tlasRoot != SPB_REF_EMPTY;
+    std::vector<std::vector<uint64_t>> per(threads, std::vector<uint64_t>(9, 0));
+    auto worker = [&](uint32_t tid) {
+        uint64_t *o9 = per[tid].data();
+        uint32_t stack[SPB_STACK_SIZE];
+        float stackT[SPB_STACK_SIZE];
+        uint32_t list[SPB_CAND_STRIDE];
+        const float weight = 1.0f / (float)spp;
+        for (uint32_t y = tid; y < c.height; y += threads)
+            for (uint32_t x = 0; x < c.width; ++x)
+            {
+                o9[0]++;
+                list[0] = SPB_CAND_FALLBACK;
+                if (single) collect_candidates(s->d, c, x, y, list);
+                if (list[0] == SPB_CAND_FALLBACK) o9[2]++;
+                else o9[8] += list[0];
+                bool allMiss = true;
+                f3 total = mk3(0, 0, 0);
+                for (uint32_t sample = 0; sample < spp; ++sample)
+                {
+                    uint32_t rng = stream_seed(x + y * c.width, sample, frame);
+                    f3 o, d;
+                    primary_ray(c, x, y, rng, o, d);
+                    Hit walk = intersect_scene_stepped<true>(s->d, o, d, stack, stackT, nullptr);
+                    o9[1]++;
+                    if (walk.t > 0.0f) allMiss = false;
+                    total = add3(total, mul3(miss_radiance<0, 0>(s->dm, neg3(d), 10.0f, nullptr), weight));
+                    if (list[0] == SPB_CAND_FALLBACK) continue;
+                    Trav st;
+                    TravCold cold;
+                    trav_begin(s->d, o, d, st, cold);
+                    resolve_from_candidates(s->d, list, o, d, st, cold, nullptr);
+                    if (st.cur != SPB_NODE_DONE || cold.slow) continue; // the walk takes over
+                    Hit fast = trav_result(cold);
+                    bool same = f2u(fast.t) == f2u(walk.t) && fast.object == walk.object && (fast.object < 0 || fast.slot == walk.slot);
+                    if (!same)
+                    {
+                        o9[3]++;
+                        if (f2u(fast.t) == f2u(walk.t) && fast.object == walk.object) o9[4]++;
+                    }
+                }
+                if (allMiss)
+                {
+                    o9[5]++;
+                    f3 one;
+                    if (sky_one_lookup<0, 0>(s->dm, c, x, y, spread, spp, one))
+                    {
+                        o9[6]++;
+                        if (f2u(one.x) != f2u(total.x) || f2u(one.y) != f2u(total.y) || f2u(one.z) != f2u(total.z)) o9[7]++;
+                    }
+                }
+            }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : pool) t.join();
+    for (uint32_t t = 0; t < threads; ++t)
+        for (int i = 0; i < 9; ++i) out9[i] += per[t][i];
+}

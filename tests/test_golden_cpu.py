@@ -2,6 +2,8 @@
 fixtures, which tools/make_golden.py produced from the UNMODIFIED reference (CPU only)."""
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -125,3 +127,36 @@ def test_c5_instanced_scene_hostsim_vs_port(hostsim, port_dm):
     hostsim.lib.hostsim_set_stepped(0)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("case", ["framed", "close_up", "off_centre", "big_env"])
+def test_hostsim_shortcuts_equal_plain_evaluation(hostsim, case):
+    """The two shortcuts of the wavefront renderer that rest on the size of the reference's jitter
+    (spb_core.cuh): per-pixel candidate triangles for camera rays, and sky pixels settled by one
+    environment lookup.  Every camera ray's shortcut result must equal its walk's (t bits, triangle,
+    object; equal-t ties aside) and every one-lookup pixel must equal the sample loop's bits.
+    Host build of the device arithmetic: a logic check, no GPU claim."""
+    spp = 8
+    size, env = (224, 160), (512, 256)
+    if case == "big_env":
+        # the bench's environment size; a large image, because the jitter in DIRECTION shrinks with
+        # the square of the resolution and a 4096-texel map needs it small
+        size, env, spp = (1600, 400), (4096, 2048), 4
+    wl = W.config1(size[0], size[1], env_size=env)
+    px, py, pz = wl.camera_position
+    if case == "close_up":
+        wl.camera_position = (px, py + 0.02, pz * 0.45)
+    elif case == "off_centre":
+        wl.camera_position = (px + 0.07, py - 0.04, pz * 0.8)
+        wl.camera_rotation = W.quat_axis_angle((0.3, 1.0, 0.1), 0.35)
+    s = hostsim.scene().load_workload(wl)
+    out = np.zeros(9, np.uint64)
+    hostsim.lib.hostsim_check_shortcuts(s.h, spp, 3, os.cpu_count() or 1, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    pixels, rays, fallback, mismatch, ties, sky, settled, sky_bad, sum_k = (int(v) for v in out)
+    assert pixels == size[0] * size[1] and rays == pixels * spp
+    assert mismatch == ties and ties <= 1e-4 * rays, (mismatch, ties)   # only equal-t ties may differ
+    assert fallback <= 0.02 * pixels                                    # the list almost never overflows
+    assert sky_bad == 0
+    assert sky > 0.2 * pixels and settled >= 0.8 * sky                  # the shortcut actually applies
+    assert sum_k > 0
+    s.close()

@@ -1187,6 +1187,223 @@ SPB_HD f3 random_hemisphere(f3 normal, uint32_t &rng)
     return dir;
 }
 
+// ------------------------------------------------------------------------------------------
+// Shortcuts of the wavefront renderer that rest on the size of the reference's jitter
+// (+-0.5/width of a PIXEL, simd_path_tracer.cpp:222-226): written here, for host and device, so
+// that tests/hostsim can check them against the plain evaluation without a GPU.
+
+// jitter-free camera ray through the centre of pixel (x, y): sp_CalculateFilmPositions
+// (simd_path_tracer.cpp:38-63) on (x + 0.5, y + 0.5)
+SPB_HD f3 centre_direction(const DCamera &cam, uint32_t x, uint32_t y)
+{
+    float fx = ((float)x + 0.5f) / (float)cam.width, fy = 1.0f - ((float)y + 0.5f) / (float)cam.height;
+    fx = fx * 2.0f - 1.0f;
+    fy = fy * 2.0f - 1.0f;
+    f3 filmP = add3(add3(mul3(cam.right, cam.halfFilmWidth * fx), mul3(cam.up, cam.halfFilmHeight * fy)), cam.filmCenter);
+    return normalize3(sub3(filmP, cam.position));
+}
+
+// Min(v0, Min(v1, v2)) / Max(v0, Max(v1, v2)) with the ternaries of build_mesh_accel(): the box
+// of a leaf, bit for bit
+SPB_HD void triangle_box(const v4f &a, const v4f &b, const v4f &c, f3 &lo, f3 &hi)
+{
+    float l, h;
+    l = b.x < c.x ? b.x : c.x; lo.x = a.x < l ? a.x : l;
+    l = b.y < c.y ? b.y : c.y; lo.y = a.y < l ? a.y : l;
+    l = b.z < c.z ? b.z : c.z; lo.z = a.z < l ? a.z : l;
+    h = b.x > c.x ? b.x : c.x; hi.x = a.x > h ? a.x : h;
+    h = b.y > c.y ? b.y : c.y; hi.y = a.y > h ? a.y : h;
+    h = b.z > c.z ? b.z : c.z; hi.z = a.z > h ? a.z : h;
+}
+
+// triangle slots kept per pixel; a pixel whose padded centre ray enters more leaf boxes falls back
+#define SPB_CAND_MAX 23u
+#define SPB_CAND_STRIDE (SPB_CAND_MAX + 1u)
+#define SPB_CAND_FALLBACK 0xFFFFFFFFu
+
+// Candidate triangles of a pixel (single-object scenes).  The 64 camera rays of a pixel differ by
+// about 1e-7 rad; walking the tree once per SAMPLE repeats the same box tests 64 times.  This
+// walks it once per PIXEL with the jitter-free centre ray against boxes padded by
+// delta = 1e-4 x (mesh extent + |origin|) -- a thousand times the separation of the pixel's rays
+// inside the scene plus every rounding of the transforms and slab products -- and lists every
+// triangle whose padded box the centre ray enters, without any distance culling.  Whatever sample
+// ray passes the exact slab test of a triangle's own box (the reference's per-leaf test,
+// bvh.cpp:236-255) therefore finds that triangle in the list.  out[0] = count or
+// SPB_CAND_FALLBACK (list overflow, non-finite reciprocal direction), out[1..] = triangle slots.
+SPB_HD void collect_candidates(const DScene &S, const DCamera &cam, uint32_t x, uint32_t y, uint32_t *out)
+{
+    f3 o = cam.position, d = centre_direction(cam, x, y);
+    v4u info = ld4u(S.objInfo);
+    m4 invModel = load_m4(S.objInv);
+    f3 lo = xform(invModel, o, 1.0f);
+    f3 ld = normalize3(xform(invModel, d, 0.0f));
+    if (info.x == SPB_REF_EMPTY) { out[0] = 0; return; }
+    if (any_nonfinite_inv(d) || any_nonfinite_inv(ld)) { out[0] = SPB_CAND_FALLBACK; return; }
+    f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+    // padding from the mesh's extent (its root node's child boxes) and the origin
+    float delta;
+    {
+        const v4f *n = S.nodes + (size_t)info.x * 8;
+        float big = 0.0f;
+        for (int k = 0; k < 6; ++k)
+        {
+            v4f v = ld4(n + k);
+            // fmaxf skips the NaN of empty slots
+            big = fmaxf(big, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        delta = 1.0e-4f * (6.0f * big + fabsf(lo.x) + fabsf(lo.y) + fabsf(lo.z));
+    }
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t node = info.x, count = 0;
+    bool overflow = false;
+    for (;;)
+    {
+        const v4f *n = S.nodes + (size_t)node * 8;
+        v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
+        v4u refs = ld4u((const v4u *)(n + 6));
+        const float bmn[4][3] = {{mnx.x, mny.x, mnz.x}, {mnx.y, mny.y, mnz.y}, {mnx.z, mny.z, mnz.z}, {mnx.w, mny.w, mnz.w}};
+        const float bmx[4][3] = {{mxx.x, mxy.x, mxz.x}, {mxx.y, mxy.y, mxz.y}, {mxx.z, mxy.z, mxz.z}, {mxx.w, mxy.w, mxz.w}};
+        const uint32_t ref[4] = {refs.x, refs.y, refs.z, refs.w};
+        for (int k = 0; k < 4; ++k)
+        {
+            float tn;
+            if (ref[k] == SPB_REF_EMPTY) continue;
+            if (!slab_fast(bmn[k][0] - delta, bmn[k][1] - delta, bmn[k][2] - delta, bmx[k][0] + delta,
+                           bmx[k][1] + delta, bmx[k][2] + delta, lo, inv, tn))
+                continue;
+            if (ref[k] & SPB_REF_LEAF)
+            {
+                if (count < SPB_CAND_MAX) out[1 + count] = ref[k] & ~SPB_REF_LEAF;
+                else overflow = true;
+                count++;
+            }
+            else if (sp < 64) stack[sp++] = ref[k];
+            else overflow = true;
+        }
+        if (sp == 0 || overflow) break;
+        node = stack[--sp];
+    }
+    out[0] = overflow ? SPB_CAND_FALLBACK : count;
+}
+
+// A camera ray (world o, d; st / cold fresh from trav_begin) resolved from its pixel's candidate
+// list: exactly what its walk would have evaluated -- the slab test of the object's world box,
+// the ray in object space, for each listed triangle the slab test of its own box (recomputed from
+// the vertices) and Moller-Trumbore, the closest hit carried back to world space -- with the
+// walk's functions, so the same bits; only the winner among exactly equal t may differ, as with
+// any visit order.  Leaves st.cur = DONE with the result in `cold`, or everything untouched when
+// the pixel falls back to the walk.
+SPB_HD void resolve_from_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d, Trav &st, TravCold &cold,
+                                    Counters *counters)
+{
+    if (cold.slow || st.cur == SPB_NODE_DONE) return; // non-finite reciprocal direction / empty scene
+    const uint32_t count = list[0];
+    if (count == SPB_CAND_FALLBACK) return;
+    // the TLAS root's test of the object's world box (what trav_node would run; the other three
+    // slots of the root are empty in a single-object scene)
+    {
+        const v4f *n = S.nodes + (size_t)S.tlasRoot * 8;
+        v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
+        float tn;
+        if (counters) counters->nodeVisits++;
+        st.cur = SPB_NODE_DONE;
+        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, st.o, st.inv, tn)) return; // miss: cold.bT = -1
+    }
+    // object entry (trav_leaf, sp_scene.cpp:274-276)
+    v4u info = ld4u(S.objInfo);
+    if (counters) counters->objectTests++;
+    if (info.x == SPB_REF_EMPTY) return;
+    m4 invModel = load_m4(S.objInv);
+    f3 lo = xform(invModel, o, 1.0f);
+    f3 ld = normalize3(xform(invModel, d, 0.0f));
+    if (any_nonfinite_inv(ld))
+    {
+        cold.slow = 1;
+        return;
+    }
+    f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+    float lT = -1.0f;
+    uint32_t lSlot = 0;
+    for (uint32_t k = 0; k < count; ++k)
+    {
+        const uint32_t tri = list[1 + k];
+        const v4f *tp = S.tris + (size_t)tri * 3;
+        v4f va = ld4(tp + 0), vb = ld4(tp + 1), vc = ld4(tp + 2);
+        f3 bmn, bmx;
+        triangle_box(va, vb, vc, bmn, bmx);
+        float tn;
+        if (!slab_fast(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, lo, inv, tn)) continue; // the leaf's own box
+        if (counters) counters->triangleTests++;
+        float t, u, v;
+        if (ray_triangle_mt(lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
+            if (t > 0.0f && (t < lT || lT < 0.0f))
+            {
+                lT = t;
+                lSlot = tri;
+            }
+    }
+    // leaving the object (trav_exit, sp_scene.cpp:296-322)
+    if (lT >= 0.0f)
+    {
+        m4 model = load_m4(S.objModel);
+        f3 localHit = add3(lo, mul3(ld, lT));
+        f3 worldHit = xform(model, localHit, 1.0f);
+        cold.bT = dot3(sub3(worldHit, o), d);
+        cold.bObject = 0;
+        cold.bSlot = lSlot;
+    }
+}
+
+// One-lookup sky pixels.  With a simple background (miss_radiance) a sky sample's radiance is the
+// texel its direction selects, E + 0.0f.  The samples of a pixel differ from the jitter-free centre
+// direction c by at most `spread` (jitter x pixel angle plus the rounding of ray generation, with
+// a factor 4 -- computed by the host from the camera).  Along the reference's chain (equirect_uv,
+// nearest sampling: image.h:3-18) that moves the image coordinates by at most
+//   |d fx| <= W * ((1.5 spread / r + 4e-7) / (2 pi) + 1.8e-7),  r = sqrt(cx^2 + cz^2)  (atan2(z, x), +2 pi, / 2 pi, * W)
+//   |d fy| <= H * (spread + 5.2e-7)                                                    (atan2(r, y), cos, * 0.5 + 0.5, 1 -, * H)
+// roundings of the single-precision steps included (the transcendental steps are correctly rounded
+// in deterministic-math mode, the only mode this path is used in).  If the centre's coordinates are
+// further than TWICE those bounds from the next texel boundary, every sample reads the centre's
+// texel, and the pixel is spp times the same addition: total += E * (1 / spp), no per-sample ray at
+// all.  The az = 0 seam, the poles (r < 1e-3) and the image edges sit on boundaries or are excluded
+// explicitly.  Returns false when the pixel needs the sample loop.
+template <int MATH, int ENVFILTER>
+SPB_HD bool sky_one_lookup(const DMaterials &M, const DCamera &cam, uint32_t x, uint32_t y, float spread, uint32_t spp,
+                           f3 &total)
+{
+    if (!(spread > 0.0f) || MATH != 0 || ENVFILTER != 0 || !M.simpleBackground) return false;
+    int slot = -1;
+    for (uint32_t i = 0; i < M.count; ++i)
+        if (M.keys[i] == M.backgroundId) { slot = (int)i; break; }
+    f3 E;
+    if (slot < 0) E = mk3(1.0f, 0.0f, 1.0f);
+    else if (M.emissionImage[slot] < 0) E = mk3(M.emission[slot][0], M.emission[slot][1], M.emission[slot][2]);
+    else
+    {
+        f3 c = centre_direction(cam, x, y);
+        const DImage &img = M.images[M.emissionImage[slot]];
+        float eu, ev;
+        equirect_uv<MATH>(c, eu, ev);
+        const float W = (float)img.width, H = (float)img.height;
+        float r = sqrtf(c.x * c.x + c.z * c.z);
+        float u = eu * W, v = ev * H;
+        float flu = floorf(u), flv = floorf(v);
+        float mx = 2.0f * W * ((1.5f * spread / r + 4.0e-7f) * 0.15915494f + 6.0e-8f + 1.2e-7f);
+        float my = 2.0f * H * (spread + 4.0e-7f + 1.2e-7f);
+        bool stable = r >= 1.0e-3f && u - flu > mx && u - flu < 1.0f - mx && v - flv > my && v - flv < 1.0f - my &&
+                      flu >= 0.0f && flv >= 0.0f && flu < W && flv < H && mx < 0.25f && my < 0.25f;
+        if (!stable) return false; // NaN coordinates end here as well
+        v4f p = ld4(img.pixels + (size_t)flv * img.width + (size_t)flu);
+        E = mk3(p.x, p.y, p.z);
+    }
+    const float weight = 1.0f / (float)spp;
+    const f3 term = mul3(mk3(E.x + 0.0f, E.y + 0.0f, E.z + 0.0f), weight);
+    total = mk3(0.0f, 0.0f, 0.0f);
+    for (uint32_t s = 0; s < spp; ++s) total = add3(total, term);
+    return true;
+}
+
 struct PathCounters { uint32_t rays, hits, misses; };
 
 // One light path = one iteration of the sample loop of sp_PathTraceTile

@@ -179,10 +179,7 @@ struct WaveArgs
     float skyDirectionSpread;
     uint32_t *skyList;
 };
-// triangle slots kept per pixel; a pixel whose padded centre ray enters more leaf boxes falls back
-#define SPB_CAND_MAX 23u
-#define SPB_CAND_STRIDE (SPB_CAND_MAX + 1u)
-#define SPB_CAND_FALLBACK 0xFFFFFFFFu
+// (SPB_CAND_MAX / SPB_CAND_STRIDE / SPB_CAND_FALLBACK: spb_core.cuh)
 // items (pixel x sample, block-major) whose bounce rays are ordered together
 #ifndef SPB_SORT_TILE
 #define SPB_SORT_TILE 2048u

@@ -108,40 +108,12 @@ __device__ __forceinline__ void item_pixel(const WaveArgs &a, unsigned item, uns
 }
 
 // ---------------------------------------------------------------------------------------------
-// Candidate triangles of a pixel (single-object scenes).
-//
-// The 64 camera rays of a pixel differ by +-0.5/width of a pixel in jitter
-// (simd_path_tracer.cpp:222-226): about 1e-7 rad.  Walking the tree once per SAMPLE repeats the
-// same box tests 64 times.  k_candidates walks it once per PIXEL with the jitter-free centre ray
-// against boxes padded by delta = 1e-4 x (scene extent + |origin|) -- a thousand times the
-// separation of the pixel's rays inside the scene plus every rounding of the transforms and slab
-// products -- and lists every triangle whose padded box the centre ray enters, without any
-// distance culling.  Whatever sample ray passes the exact slab test of a triangle's own box (the
-// reference's per-leaf test, bvh.cpp:236-255) therefore finds that triangle in the list.
-// k_trace<PRIMARY> then evaluates, per sample, exactly what its walk would have evaluated --
-// the slab test of the object's world box, the ray in object space, for each listed triangle the
-// slab test of its own box (recomputed from the vertices with the builder's min/max) and
-// Moller-Trumbore, the closest hit carried back to world space -- with the same functions, so
-// the same bits; only the winner among exactly equal t may differ, as with any visit order.
-// Pixels whose list would overflow, or whose rays have a non-finite reciprocal direction, fall
-// back to the walk.
-__device__ __forceinline__ void triangle_box(const v4f &a, const v4f &b, const v4f &c, f3 &lo, f3 &hi)
-{
-    // Min(v0, Min(v1, v2)) / Max(v0, Max(v1, v2)) with the ternaries of build_mesh_accel()
-    float l, h;
-    l = b.x < c.x ? b.x : c.x; lo.x = a.x < l ? a.x : l;
-    l = b.y < c.y ? b.y : c.y; lo.y = a.y < l ? a.y : l;
-    l = b.z < c.z ? b.z : c.z; lo.z = a.z < l ? a.z : l;
-    h = b.x > c.x ? b.x : c.x; hi.x = a.x > h ? a.x : h;
-    h = b.y > c.y ? b.y : c.y; hi.y = a.y > h ? a.y : h;
-    h = b.z > c.z ? b.z : c.z; hi.z = a.z > h ? a.z : h;
-}
-
+// Candidate triangles of a pixel (single-object scenes): spb_core.cuh collect_candidates() /
+// resolve_from_candidates().
 __global__ void __launch_bounds__(128)
 k_candidates(const __grid_constant__ WaveArgs a, uint32_t *candidates)
 {
     const unsigned pixels = a.bandBlocks * 32u;
-    const DScene &S = a.scene;
     for (unsigned pi = blockIdx.x * blockDim.x + threadIdx.x; pi < pixels; pi += gridDim.x * blockDim.x)
     {
         uint32_t *out = candidates + (size_t)pi * SPB_CAND_STRIDE;
@@ -149,132 +121,18 @@ k_candidates(const __grid_constant__ WaveArgs a, uint32_t *candidates)
         unsigned by = block / a.blocksX, bx = block - by * a.blocksX;
         unsigned x = a.x0 + bx * 8 + (l & 7u), y = a.y0 + by * 4 + (l >> 3);
         if (x >= a.x1 || y >= a.y1) { out[0] = 0; continue; }
-        // centre ray: sp_CalculateFilmPositions (simd_path_tracer.cpp:38-63) without jitter
-        const DCamera &cam = a.camera;
-        float fx = ((float)x + 0.5f) / (float)cam.width, fy = 1.0f - ((float)y + 0.5f) / (float)cam.height;
-        fx = fx * 2.0f - 1.0f;
-        fy = fy * 2.0f - 1.0f;
-        f3 filmP = add3(add3(mul3(cam.right, cam.halfFilmWidth * fx), mul3(cam.up, cam.halfFilmHeight * fy)), cam.filmCenter);
-        f3 o = cam.position, d = normalize3(sub3(filmP, cam.position));
-        v4u info = ld4u(S.objInfo);
-        m4 invModel = load_m4(S.objInv);
-        f3 lo = xform(invModel, o, 1.0f);
-        f3 ld = normalize3(xform(invModel, d, 0.0f));
-        if (info.x == SPB_REF_EMPTY) { out[0] = 0; continue; }
-        if (any_nonfinite_inv(d) || any_nonfinite_inv(ld)) { out[0] = SPB_CAND_FALLBACK; continue; }
-        f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-        // padding from the mesh's extent (its root node's child boxes) and the origin
-        float delta;
-        {
-            const v4f *n = S.nodes + (size_t)info.x * 8;
-            v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
-            float big = 0.0f;
-            const float vals[24] = {mnx.x, mnx.y, mnx.z, mnx.w, mny.x, mny.y, mny.z, mny.w, mnz.x, mnz.y, mnz.z, mnz.w,
-                                    mxx.x, mxx.y, mxx.z, mxx.w, mxy.x, mxy.y, mxy.z, mxy.w, mxz.x, mxz.y, mxz.z, mxz.w};
-#pragma unroll
-            for (int k = 0; k < 24; ++k) big = fmaxf(big, fabsf(vals[k])); // fmaxf skips the NaN of empty slots
-            delta = 1.0e-4f * (6.0f * big + fabsf(lo.x) + fabsf(lo.y) + fabsf(lo.z));
-        }
-        uint32_t stack[64];
-        int sp = 0;
-        uint32_t node = info.x, count = 0;
-        bool overflow = false;
-        for (;;)
-        {
-            const v4f *n = S.nodes + (size_t)node * 8;
-            v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
-            v4u refs = ld4u((const v4u *)(n + 6));
-            const float bmn[4][3] = {{mnx.x, mny.x, mnz.x}, {mnx.y, mny.y, mnz.y}, {mnx.z, mny.z, mnz.z}, {mnx.w, mny.w, mnz.w}};
-            const float bmx[4][3] = {{mxx.x, mxy.x, mxz.x}, {mxx.y, mxy.y, mxz.y}, {mxx.z, mxy.z, mxz.z}, {mxx.w, mxy.w, mxz.w}};
-            const uint32_t ref[4] = {refs.x, refs.y, refs.z, refs.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                float tn;
-                if (ref[k] == SPB_REF_EMPTY) continue;
-                if (!slab_fast(bmn[k][0] - delta, bmn[k][1] - delta, bmn[k][2] - delta, bmx[k][0] + delta,
-                               bmx[k][1] + delta, bmx[k][2] + delta, lo, inv, tn))
-                    continue;
-                if (ref[k] & SPB_REF_LEAF)
-                {
-                    if (count < SPB_CAND_MAX) out[1 + count] = ref[k] & ~SPB_REF_LEAF;
-                    else overflow = true;
-                    count++;
-                }
-                else if (sp < 64) stack[sp++] = ref[k];
-                else overflow = true;
-            }
-            if (sp == 0 || overflow) break;
-            node = stack[--sp];
-        }
-        out[0] = overflow ? SPB_CAND_FALLBACK : count;
+        collect_candidates(a.scene, a.camera, x, y, out);
     }
 }
 
-// Primary ray of item `idx` resolved from its pixel's candidate list (see above); leaves the
-// lane finished (st.cur = DONE with the result in `cold`), or untouched when the pixel falls back.
+// Primary ray of item `idx` resolved from its pixel's candidate list (spb_core.cuh
+// resolve_from_candidates); leaves the lane finished, or untouched when the pixel falls back.
 template <bool CULL>
 __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsigned idx, f3 o, f3 d, Trav &st,
                                                         TravCold &cold, Counters *counters)
 {
-    if (cold.slow || st.cur == SPB_NODE_DONE) return; // non-finite reciprocal direction / empty scene
-    const uint32_t *list = a.candidates + (size_t)(idx / a.samplesThisPass) * SPB_CAND_STRIDE;
-    const uint32_t count = __ldg(list);
-    if (count == SPB_CAND_FALLBACK) return;
-    const DScene &S = a.scene;
-    // the TLAS root's test of the object's world box (what trav_node would run; the other three
-    // slots of the root are empty in a single-object scene)
-    {
-        const v4f *n = S.nodes + (size_t)S.tlasRoot * 8;
-        v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
-        float tn;
-        if (counters) counters->nodeVisits++;
-        st.cur = SPB_NODE_DONE;
-        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, st.o, st.inv, tn)) return; // miss: cold.bT = -1
-    }
-    // object entry (trav_leaf, sp_scene.cpp:274-276)
-    v4u info = ld4u(S.objInfo);
-    if (counters) counters->objectTests++;
-    if (info.x == SPB_REF_EMPTY) return;
-    m4 invModel = load_m4(S.objInv);
-    f3 lo = xform(invModel, o, 1.0f);
-    f3 ld = normalize3(xform(invModel, d, 0.0f));
-    if (any_nonfinite_inv(ld))
-    {
-        cold.slow = 1;
-        return;
-    }
-    f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-    float lT = -1.0f;
-    uint32_t lSlot = 0;
-    for (uint32_t k = 0; k < count; ++k)
-    {
-        const uint32_t tri = __ldg(list + 1 + k);
-        const v4f *tp = S.tris + (size_t)tri * 3;
-        v4f va = ld4(tp + 0), vb = ld4(tp + 1), vc = ld4(tp + 2);
-        f3 bmn, bmx;
-        triangle_box(va, vb, vc, bmn, bmx);
-        float tn;
-        if (!slab_fast(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, lo, inv, tn)) continue; // the leaf's own box
-        if (counters) counters->triangleTests++;
-        float t, u, v;
-        if (ray_triangle_mt(lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
-            if (t > 0.0f && (t < lT || lT < 0.0f))
-            {
-                lT = t;
-                lSlot = tri;
-            }
-    }
-    // leaving the object (trav_exit, sp_scene.cpp:296-322)
-    if (lT >= 0.0f)
-    {
-        m4 model = load_m4(S.objModel);
-        f3 localHit = add3(lo, mul3(ld, lT));
-        f3 worldHit = xform(model, localHit, 1.0f);
-        cold.bT = dot3(sub3(worldHit, o), d);
-        cold.bObject = 0;
-        cold.bSlot = lSlot;
-    }
+    resolve_from_candidates(a.scene, a.candidates + (size_t)(idx / a.samplesThisPass) * SPB_CAND_STRIDE, o, d, st, cold,
+                            counters);
 }
 
 // The rare ray whose reciprocal direction is not finite (axis-parallel): exact slab form.
@@ -914,57 +772,13 @@ __device__ __forceinline__ void sky_pixel_samples(const WaveArgs &a, const DMate
     a.out[(size_t)pixelIndex] = out;
 }
 
-// One-lookup path.  With a simple background (miss_radiance) a sky sample's radiance is the texel
-// its direction selects, E + 0.0f.  The samples of a pixel differ from the jitter-free centre
-// direction c by at most `spread` (a.skyDirectionSpread: jitter x pixel angle plus the rounding of
-// ray generation, with a factor 4 -- host).  Along the reference's chain (equirect_uv, nearest
-// sampling: image.h:3-18) that moves the image coordinates by at most
-//   |d fx| <= W * ((1.5 spread / r + 4e-7) / (2 pi) + 1.8e-7),  r = sqrt(cx^2 + cz^2)  (atan2(z, x), +2 pi, / 2 pi, * W)
-//   |d fy| <= H * (spread + 5.2e-7)                                                    (atan2(r, y), cos, * 0.5 + 0.5, 1 -, * H)
-// roundings of the single-precision steps included (the transcendental steps are correctly rounded
-// in deterministic-math mode, the only mode this path is used in).  If the centre's coordinates are
-// further than TWICE those bounds from the next texel boundary, every sample reads the centre's
-// texel, and the pixel is spp times the same addition: total += E * (1 / spp), no per-sample ray at
-// all.  The az = 0 seam, the poles (r < 1e-3) and the image edges sit on boundaries or are excluded
-// explicitly; such pixels, about 4 %, are listed for k_sky_listed, which runs the sample loop.
+// One-lookup path: spb_core.cuh sky_one_lookup(); pixels it cannot settle (about 4 %) are listed for
+// k_sky_listed, which runs the sample loop.
 template <int MATH, int ENVFILTER>
 __device__ __forceinline__ bool sky_pixel_one_lookup(const WaveArgs &a, const DMaterials &M, unsigned x, unsigned y)
 {
-    if (!(a.skyDirectionSpread > 0.0f) || MATH != 0 || ENVFILTER != 0 || !M.simpleBackground) return false;
-    int slot = -1;
-    for (uint32_t i = 0; i < M.count; ++i)
-        if (M.keys[i] == M.backgroundId) { slot = (int)i; break; }
-    f3 E;
-    if (slot < 0) E = mk3(1.0f, 0.0f, 1.0f);
-    else if (M.emissionImage[slot] < 0) E = mk3(M.emission[slot][0], M.emission[slot][1], M.emission[slot][2]);
-    else
-    {
-        const DCamera &cam = a.camera;
-        float fx = ((float)x + 0.5f) / (float)cam.width, fy = 1.0f - ((float)y + 0.5f) / (float)cam.height;
-        fx = fx * 2.0f - 1.0f;
-        fy = fy * 2.0f - 1.0f;
-        f3 filmP = add3(add3(mul3(cam.right, cam.halfFilmWidth * fx), mul3(cam.up, cam.halfFilmHeight * fy)), cam.filmCenter);
-        f3 c = normalize3(sub3(filmP, cam.position));
-        const DImage &img = M.images[M.emissionImage[slot]];
-        float eu, ev;
-        equirect_uv<MATH>(c, eu, ev);
-        const float W = (float)img.width, H = (float)img.height, spread = a.skyDirectionSpread;
-        float r = sqrtf(c.x * c.x + c.z * c.z);
-        float u = eu * W, v = ev * H;
-        float flu = floorf(u), flv = floorf(v);
-        // (+ 1.2e-7: the rounding of the products eu * W, ev * H when the size is not a power of two)
-        float mx = 2.0f * W * ((1.5f * spread / r + 4.0e-7f) * 0.15915494f + 6.0e-8f + 1.2e-7f);
-        float my = 2.0f * H * (spread + 4.0e-7f + 1.2e-7f);
-        bool stable = r >= 1.0e-3f && u - flu > mx && u - flu < 1.0f - mx && v - flv > my && v - flv < 1.0f - my &&
-                      flu >= 0.0f && flv >= 0.0f && flu < W && flv < H && mx < 0.25f && my < 0.25f;
-        if (!stable) return false; // NaN coordinates end here as well
-        v4f p = ld4(img.pixels + (size_t)flv * img.width + (size_t)flu);
-        E = mk3(p.x, p.y, p.z);
-    }
-    const float weight = 1.0f / (float)a.spp;
-    const f3 term = mul3(mk3(E.x + 0.0f, E.y + 0.0f, E.z + 0.0f), weight);
-    f3 total = mk3(0.0f, 0.0f, 0.0f);
-    for (unsigned s = 0; s < a.spp; ++s) total = add3(total, term);
+    f3 total;
+    if (!sky_one_lookup<MATH, ENVFILTER>(M, a.camera, x, y, a.skyDirectionSpread, a.spp, total)) return false;
     v4f out;
     out.x = total.x; out.y = total.y; out.z = total.z; out.w = 1.0f;
     a.out[(size_t)x + (size_t)y * a.camera.width] = out;
