@@ -397,3 +397,57 @@ extern "C" void hostsim_check_shortcuts(ora_Scene *s, uint32_t spp, uint32_t fra
     for (uint32_t t = 0; t < threads; ++t)
         for (int i = 0; i < 9; ++i) out9[i] += per[t][i];
 }
+
+// Coverage pass (spb_core.cuh cover_triangle) on the host: out[0] blocks, [1] blocks left
+// unmarked, [2] "everything" flag, [3] camera rays (all samples) of pixels in unmarked blocks,
+// [4] of those, rays whose walk HITS something (must be 0).
+extern "C" void hostsim_check_coverage(ora_Scene *s, uint32_t spp, uint32_t frame, uint32_t threads, uint64_t *out5)
+{
+    refresh(s);
+    if (threads == 0) threads = 1;
+    const DCamera &c = s->dc;
+    const uint32_t blocksX = (c.width + 7) / 8, blocksY = (c.height + 3) / 4, blocks = blocksX * blocksY;
+    std::vector<uint8_t> coverage((size_t)blocks + 1, 0);
+    std::vector<uint32_t> objTris = s->flat.objTris;
+    if (objTris.empty()) objTris.push_back(0);
+    DScene d = s->d;
+    d.objTris = objTris.data();
+    for (uint64_t i = 0; i < s->flat.instancedTriangles; ++i)
+        cover_triangle(d, c, i, 0, 0, c.width, c.height, blocksX, blocksY, coverage.data());
+    out5[0] = blocks;
+    out5[2] = coverage[blocks];
+    std::vector<std::vector<uint64_t>> per(threads, std::vector<uint64_t>(3, 0));
+    auto worker = [&](uint32_t tid) {
+        uint32_t stack[SPB_STACK_SIZE];
+        float stackT[SPB_STACK_SIZE];
+        for (uint32_t b = tid; b < blocks; b += threads)
+        {
+            if (coverage[b] || coverage[blocks]) continue;
+            per[tid][0]++;
+            for (uint32_t l = 0; l < 32; ++l)
+            {
+                uint32_t x = (b % blocksX) * 8 + (l & 7u), y = (b / blocksX) * 4 + (l >> 3);
+                if (x >= c.width || y >= c.height) continue;
+                for (uint32_t sample = 0; sample < spp; ++sample)
+                {
+                    uint32_t rng = stream_seed(x + y * c.width, sample, frame);
+                    f3 o, dir;
+                    primary_ray(c, x, y, rng, o, dir);
+                    Hit walk = intersect_scene<true>(d, o, dir, stack, stackT, nullptr);
+                    per[tid][1]++;
+                    if (walk.t > 0.0f) per[tid][2]++;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : pool) t.join();
+    for (uint32_t t = 0; t < threads; ++t)
+    {
+        out5[1] += per[t][0];
+        out5[3] += per[t][1];
+        out5[4] += per[t][2];
+    }
+}

@@ -430,6 +430,7 @@ def load_hostsim():
     o = OracleLib(HOSTSIM_LIB)
     o.lib.hostsim_set_cull.argtypes = [C.c_int]
     o.lib.hostsim_check_shortcuts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64]
+    o.lib.hostsim_check_coverage.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64]
     o.lib.hostsim_set_stepped.argtypes = [C.c_int]
     return o
 

@@ -160,3 +160,35 @@ def test_hostsim_shortcuts_equal_plain_evaluation(hostsim, case):
     assert sky > 0.2 * pixels and settled >= 0.8 * sky                  # the shortcut actually applies
     assert sum_k > 0
     s.close()
+
+
+@pytest.mark.parametrize("case", ["bunny", "bunny_edge", "multi_object", "instanced"])
+def test_hostsim_coverage_is_conservative(hostsim, case):
+    """Coverage pass (spb_core.cuh cover_triangle, what k_cover runs per instanced triangle): no camera
+    ray of any pixel in an unmarked 8x4 block may hit anything.  The multi-object scene has a ground
+    plane that passes under the camera (the "everything" flag); the instanced one is the C5 layout at
+    reduced size.  Host build of the device arithmetic: a logic check, no GPU claim."""
+    spp = 4
+    if case == "bunny":
+        wl = W.config1(320, 200, env_size=(256, 128))
+    elif case == "bunny_edge":
+        wl = W.config1(333, 187, env_size=(256, 128))
+        px, py, pz = wl.camera_position
+        wl.camera_rotation = W.quat_axis_angle((0, 1, 0), np.pi * 0.15)
+        wl.camera_position = (px + 0.05, py, pz * 0.35)
+    elif case == "multi_object":
+        wl = W.multi_object_workload(width=200, height=150, spp=1, env_size=(256, 128))
+    else:
+        wl = W.config5(240, 136, spp=1, bounces=2, env_size=(256, 128), sphere_level=3)
+    s = hostsim.scene().load_workload(wl)
+    out = np.zeros(5, np.uint64)
+    hostsim.lib.hostsim_check_coverage(s.h, spp, 2, os.cpu_count() or 1, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    blocks, unmarked, everything, rays, hits = (int(v) for v in out)
+    assert hits == 0
+    if case == "multi_object":
+        assert everything == 1
+    else:
+        # (the instanced field fills most of the view; the single mesh leaves most of it empty)
+        floor = 0.02 if case == "instanced" else 0.3
+        assert everything == 0 and floor * blocks < unmarked < blocks and rays > 0
+    s.close()

@@ -1192,6 +1192,67 @@ SPB_HD f3 random_hemisphere(f3 normal, uint32_t &rng)
 // (+-0.5/width of a PIXEL, simd_path_tracer.cpp:222-226): written here, for host and device, so
 // that tests/hostsim can check them against the plain evaluation without a GPU.
 
+// Coverage of one instanced triangle (index i over all objects' triangles, DScene::objTris):
+// object-space vertices -> world (model matrix) -> film (sp_CalculateFilmPositions inverted,
+// simd_path_tracer.cpp:38-63) in double; the pixel bounding box of the three projections, padded
+// by 2 pixels, marks the 8x4 pixel blocks of the strip [x0,x1) x [y0,y1) it touches in
+// coverage[blocksX * blocksY]; coverage[blocksX * blocksY] is the "everything" flag, raised when
+// the triangle reaches the camera plane (its projection is unbounded).
+SPB_HD void cover_triangle(const DScene &S, const DCamera &c, unsigned long long i, uint32_t x0, uint32_t y0,
+                           uint32_t x1, uint32_t y1, uint32_t blocksX, uint32_t blocksY, uint8_t *coverage)
+{
+    const double Fx = (double)c.filmCenter.x - c.position.x, Fy = (double)c.filmCenter.y - c.position.y,
+                 Fz = (double)c.filmCenter.z - c.position.z;
+    const double dist = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+    const uint32_t *first = S.objTris, *prefix = S.objTris + S.objectCount;
+    const uint32_t blocks = blocksX * blocksY;
+    // object of this instanced triangle: last prefix entry <= i
+    uint32_t lo = 0, hi = S.objectCount;
+    while (hi - lo > 1)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t object = lo;
+    const size_t slot = (size_t)first[object] + (size_t)(i - prefix[object]);
+    const v4f *tp = S.tris + slot * 3;
+    const v4f *mp = S.objModel + (size_t)object * 4;
+    const v4f m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+    double px[3], py[3], depthMin = 1e300, depthMax = -1e300, scale = 0.0;
+    for (int k = 0; k < 3; ++k)
+    {
+        v4f v = tp[k];
+        double wx = (double)m0.x * v.x + (double)m1.x * v.y + (double)m2.x * v.z + m3.x - c.position.x;
+        double wy = (double)m0.y * v.x + (double)m1.y * v.y + (double)m2.y * v.z + m3.y - c.position.y;
+        double wz = (double)m0.z * v.x + (double)m1.z * v.y + (double)m2.z * v.z + m3.z - c.position.z;
+        double depth = (wx * Fx + wy * Fy + wz * Fz) / dist;
+        double lambda = depth / dist; // w = lambda * (film point - camera position)
+        double fa = (wx * c.right.x + wy * c.right.y + wz * c.right.z) / lambda / c.halfFilmWidth;
+        double fb = (wx * c.up.x + wy * c.up.y + wz * c.up.z) / lambda / c.halfFilmHeight;
+        px[k] = (fa + 1.0) * 0.5 * c.width;
+        py[k] = (1.0 - (fb + 1.0) * 0.5) * c.height;
+        depthMin = fmin(depthMin, depth);
+        depthMax = fmax(depthMax, depth);
+        scale = fmax(scale, fabs(wx) + fabs(wy) + fabs(wz));
+    }
+    if (!(depthMax > 0.0)) return; // entirely behind the camera plane: no camera ray goes there
+    if (!(depthMin > 1e-6 * scale) || !(dist > 0.0))
+    {
+        coverage[blocks] = 1; // reaches the camera plane: its projection is unbounded
+        return;
+    }
+    double xlo = fmin(px[0], fmin(px[1], px[2])) - 2.0, xhi = fmax(px[0], fmax(px[1], px[2])) + 2.0;
+    double ylo = fmin(py[0], fmin(py[1], py[2])) - 2.0, yhi = fmax(py[0], fmax(py[1], py[2])) + 2.0;
+    if (!(xlo == xlo) || !(xhi == xhi) || !(ylo == ylo) || !(yhi == yhi)) { coverage[blocks] = 1; return; }
+    if (xhi < (double)x0 || yhi < (double)y0 || xlo >= (double)x1 || ylo >= (double)y1) return;
+    uint32_t bx0 = xlo <= (double)x0 ? 0u : ((uint32_t)xlo - x0) >> 3;
+    uint32_t by0 = ylo <= (double)y0 ? 0u : ((uint32_t)ylo - y0) >> 2;
+    uint32_t bx1 = xhi >= (double)(x1 - 1) ? blocksX - 1 : ((uint32_t)xhi - x0) >> 3;
+    uint32_t by1 = yhi >= (double)(y1 - 1) ? blocksY - 1 : ((uint32_t)yhi - y0) >> 2;
+    for (uint32_t by = by0; by <= by1; ++by)
+        for (uint32_t bx = bx0; bx <= bx1; ++bx) coverage[by * blocksX + bx] = 1;
+}
+
 // jitter-free camera ray through the centre of pixel (x, y): sp_CalculateFilmPositions
 // (simd_path_tracer.cpp:38-63) on (x + 0.5, y + 0.5)
 SPB_HD f3 centre_direction(const DCamera &cam, uint32_t x, uint32_t y)

@@ -662,61 +662,9 @@ k_accumulate(const __grid_constant__ WaveArgs a)
 __global__ void __launch_bounds__(256)
 k_cover(const __grid_constant__ WaveArgs a, unsigned long long triangles, uint8_t *coverage)
 {
-    const DCamera &c = a.camera;
-    const double Fx = (double)c.filmCenter.x - c.position.x, Fy = (double)c.filmCenter.y - c.position.y,
-                 Fz = (double)c.filmCenter.z - c.position.z;
-    const double dist = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
-    const uint32_t *first = a.scene.objTris, *prefix = a.scene.objTris + a.scene.objectCount;
-    const unsigned blocks = a.blocksX * a.blocksY;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < triangles;
          i += (unsigned long long)gridDim.x * blockDim.x)
-    {
-        // object of this instanced triangle: last prefix entry <= i
-        unsigned lo = 0, hi = a.scene.objectCount;
-        while (hi - lo > 1)
-        {
-            unsigned mid = (lo + hi) >> 1;
-            if (prefix[mid] <= i) lo = mid; else hi = mid;
-        }
-        const unsigned object = lo;
-        const size_t slot = (size_t)first[object] + (size_t)(i - prefix[object]);
-        const v4f *tp = a.scene.tris + slot * 3;
-        const v4f *mp = a.scene.objModel + (size_t)object * 4;
-        const v4f m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
-        double px[3], py[3], depthMin = 1e300, depthMax = -1e300, scale = 0.0;
-        for (int k = 0; k < 3; ++k)
-        {
-            v4f v = tp[k];
-            double wx = (double)m0.x * v.x + (double)m1.x * v.y + (double)m2.x * v.z + m3.x - c.position.x;
-            double wy = (double)m0.y * v.x + (double)m1.y * v.y + (double)m2.y * v.z + m3.y - c.position.y;
-            double wz = (double)m0.z * v.x + (double)m1.z * v.y + (double)m2.z * v.z + m3.z - c.position.z;
-            double depth = (wx * Fx + wy * Fy + wz * Fz) / dist;
-            double lambda = depth / dist; // w = lambda * (film point - camera position)
-            double fa = (wx * c.right.x + wy * c.right.y + wz * c.right.z) / lambda / c.halfFilmWidth;
-            double fb = (wx * c.up.x + wy * c.up.y + wz * c.up.z) / lambda / c.halfFilmHeight;
-            px[k] = (fa + 1.0) * 0.5 * c.width;
-            py[k] = (1.0 - (fb + 1.0) * 0.5) * c.height;
-            depthMin = fmin(depthMin, depth);
-            depthMax = fmax(depthMax, depth);
-            scale = fmax(scale, fabs(wx) + fabs(wy) + fabs(wz));
-        }
-        if (!(depthMax > 0.0)) continue; // entirely behind the camera plane: no camera ray goes there
-        if (!(depthMin > 1e-6 * scale) || !(dist > 0.0))
-        {
-            coverage[blocks] = 1; // reaches the camera plane: its projection is unbounded
-            continue;
-        }
-        double xlo = fmin(px[0], fmin(px[1], px[2])) - 2.0, xhi = fmax(px[0], fmax(px[1], px[2])) + 2.0;
-        double ylo = fmin(py[0], fmin(py[1], py[2])) - 2.0, yhi = fmax(py[0], fmax(py[1], py[2])) + 2.0;
-        if (!(xlo == xlo) || !(xhi == xhi) || !(ylo == ylo) || !(yhi == yhi)) { coverage[blocks] = 1; continue; }
-        if (xhi < (double)a.x0 || yhi < (double)a.y0 || xlo >= (double)a.x1 || ylo >= (double)a.y1) continue;
-        unsigned bx0 = xlo <= (double)a.x0 ? 0u : ((unsigned)xlo - a.x0) >> 3;
-        unsigned by0 = ylo <= (double)a.y0 ? 0u : ((unsigned)ylo - a.y0) >> 2;
-        unsigned bx1 = xhi >= (double)(a.x1 - 1) ? a.blocksX - 1 : ((unsigned)xhi - a.x0) >> 3;
-        unsigned by1 = yhi >= (double)(a.y1 - 1) ? a.blocksY - 1 : ((unsigned)yhi - a.y0) >> 2;
-        for (unsigned by = by0; by <= by1; ++by)
-            for (unsigned bx = bx0; bx <= bx1; ++bx) coverage[by * a.blocksX + bx] = 1;
-    }
+        cover_triangle(a.scene, a.camera, i, a.x0, a.y0, a.x1, a.y1, a.blocksX, a.blocksY, coverage);
 }
 
 // Row-major list of the marked blocks (one CTA: a chunked prefix sum); coverage[] becomes the
