@@ -307,6 +307,13 @@ typedef struct sp_b200_MeshData {
 int sp_b200_LoadObj(const char *path, sp_b200_MeshData *out);
 void sp_b200_FreeMeshData(sp_b200_MeshData *mesh);
 
+/* OpenEXR input behind the reference's own loader ABI (src/asset_loader/asset_loader.h:11-22; there
+ * implemented with the vendored tinyexr): 0 on success, 1 on failure; pixels = malloc'ed RGBA f32,
+ * rows top to bottom, alpha 1 when the file has none, a single channel replicated; the caller
+ * free()s them.  Single-part scanline files, HALF / FLOAT channels, compression NONE / RLE / ZIPS /
+ * ZIP; anything else (tiled, multi-part, PIZ ...) is refused with 1. */
+int LoadExrImage(HdrImage *image, const char *path);
+
 /* Output stage (the step after the path, src/shaders/post_processing.frag.glsl:19-26
  * PerformToneMapping): color *= exposure; color = color / (1 + color); pow(color, 1/2.2); then the
  * 8-bit UNORM store of the colour attachment, alpha 255, r in the low byte (the layout of ToColor,

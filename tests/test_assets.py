@@ -95,3 +95,78 @@ def test_load_obj_reference_assets(name):
     v, i = sp.load_obj(src)
     d = np.load(os.path.join(ROOT, "assets", name + ".npz"))
     assert np.array_equal(v.view(np.uint32), d["vertices"].view(np.uint32)) and np.array_equal(i, d["indices"])
+
+
+# ---------------------------------------------------------------------------------------------
+# OpenEXR input: the library's LoadExrImage (same C ABI as the reference's asset_loader.h:11-22)
+# against (a) the arrays the fixtures were written from (tools/make_exr_fixtures.py, OpenCV's
+# encoder) and (b) the reference's own loader -- its asset_loader.cpp over the vendored tinyexr,
+# compiled unmodified by `make -C oracle exrref` -- where that library is present.
+
+EXR_DIR = os.path.join(HERE, "golden", "exr")
+EXR_CASES = ["none_f32_rgb_13x9", "zip_f32_rgb_70x45", "zip_half_rgba_33x20", "zips_half_rgb_21x7",
+             "rle_f32_rgb_40x11", "zip_f32_grey_17x5", "piz_half_rgb_16x8", "piz_half_rgb_70x45",
+             "piz_f32_rgba_37x33"]
+
+
+def _reference_exr_loader():
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libexrref.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.LoadExrImage.argtypes = [C.POINTER(sp.HdrImage), C.c_char_p]
+    lib.LoadExrImage.restype = C.c_int
+
+    def load(p):
+        img = sp.HdrImage()
+        if lib.LoadExrImage(C.byref(img), os.fsencode(p)) != 0:
+            return None
+        out = np.ctypeslib.as_array(img.pixels, shape=(img.height, img.width, 4)).copy()
+        sp._libc_free(img.pixels)
+        return out
+    return load
+
+
+@pytest.mark.parametrize("name", EXR_CASES)
+def test_load_exr_fixture(name):
+    got = sp.load_exr(os.path.join(EXR_DIR, name + ".exr"))
+    want = np.load(os.path.join(EXR_DIR, name + ".npy"))
+    assert got is not None and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    ref = _reference_exr_loader()
+    if ref is not None:
+        r = ref(os.path.join(EXR_DIR, name + ".exr"))
+        assert r is not None and np.array_equal(got.view(np.uint32), r.view(np.uint32))
+
+
+def test_load_exr_refuses_what_it_cannot_read(tmp_path):
+    """Return value 1 (the reference's failure code), image untouched: unsupported compression
+    (PXR24: this reader says no rather than guess), missing file, truncated files, garbage."""
+    assert sp.load_exr(os.path.join(EXR_DIR, "pxr24_f32_rgb_16x8.exr")) is None
+    assert sp.load_exr(os.path.join(EXR_DIR, "nope.exr")) is None
+    data = open(os.path.join(EXR_DIR, "zip_f32_rgb_70x45.exr"), "rb").read()
+    for cut in (3, 40, 400, len(data) // 2, len(data) - 7):
+        p = tmp_path / f"cut{cut}.exr"
+        p.write_bytes(data[:cut])
+        assert sp.load_exr(str(p)) is None
+    piz = open(os.path.join(EXR_DIR, "piz_half_rgb_70x45.exr"), "rb").read()
+    for cut in (len(piz) // 3, len(piz) - 5):
+        p = tmp_path / f"pizcut{cut}.exr"
+        p.write_bytes(piz[:cut])
+        assert sp.load_exr(str(p)) is None
+    for k in range(0, len(piz), 97):          # corrupted PIZ streams must not crash
+        broken = bytearray(piz)
+        broken[k] ^= 0xA5
+        p = tmp_path / "pizflip.exr"
+        p.write_bytes(bytes(broken))
+        sp.load_exr(str(p))
+    p = tmp_path / "garbage.exr"
+    p.write_bytes(bytes(range(256)) * 8)
+    assert sp.load_exr(str(p)) is None
+    # a flipped byte inside a compressed chunk must not crash (it may or may not be detected)
+    broken = bytearray(data)
+    broken[len(broken) // 2] ^= 0x5A
+    p = tmp_path / "flipped.exr"
+    p.write_bytes(bytes(broken))
+    sp.load_exr(str(p))

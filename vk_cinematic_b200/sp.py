@@ -255,6 +255,7 @@ _SIGNATURES = {
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
                                      _P(sp_Metrics), C.c_void_p]),
     "sp_b200_RenderFrame": (C.c_int, [_P(sp_Context), u32, _P(sp_Metrics)]),
+    "LoadExrImage": (C.c_int, [_P(HdrImage), C.c_char_p]),
     "sp_b200_LoadObj": (C.c_int, [C.c_char_p, _P(sp_b200_MeshData)]),
     "sp_b200_FreeMeshData": (None, [_P(sp_b200_MeshData)]),
     "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
@@ -339,6 +340,22 @@ def load_obj(path):
     indices = np.ctypeslib.as_array(md.indices, shape=(md.indexCount,)).copy()
     lib.sp_b200_FreeMeshData(C.byref(md))
     return vertices, indices
+
+
+def load_exr(path):
+    """OpenEXR file -> (H, W, 4) float32 through the library's LoadExrImage; None on failure."""
+    img = HdrImage()
+    if lib.LoadExrImage(C.byref(img), os.fsencode(path)) != 0:
+        return None
+    out = np.ctypeslib.as_array(img.pixels, shape=(img.height, img.width, 4)).copy()
+    _libc_free(img.pixels)
+    return out
+
+
+def _libc_free(ptr):
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(ptr, C.c_void_p))
 
 
 def tone_map(rgba, exposure=1.0):
