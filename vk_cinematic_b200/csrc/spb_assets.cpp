@@ -20,7 +20,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -734,18 +736,18 @@ static int load_exr_image(HdrImage *image, const char *path)
     if (!b.ok) return 1;
     float *out = (float *)malloc((size_t)width * (size_t)height * 4 * sizeof(float));
     if (!out) return 1;
-    std::vector<uint8_t> raw, tmp;
-    bool ok = true;
-    for (size_t i = 0; i < chunks && ok; ++i)
+    // chunks are independent (own rows of the output): decoded by up to 8 threads
+    auto decode_chunk = [&](size_t i, std::vector<uint8_t> &raw, std::vector<uint8_t> &tmp) -> bool
     {
+        bool ok = true;
         Bytes c;
         c.p = file.data();
         c.n = file.size();
         c.at = (size_t)offsets[i];
-        if (offsets[i] >= file.size()) { ok = false; break; }
+        if (offsets[i] >= file.size()) return false;
         int32_t y = (int32_t)c.u32();
         uint32_t dataSize = c.u32();
-        if (!c.ok || c.at + dataSize > c.n || y < dw[1] || y > dw[3]) { ok = false; break; }
+        if (!c.ok || c.at + dataSize > c.n || y < dw[1] || y > dw[3]) return false;
         const int64_t lines = std::min<int64_t>(linesPerBlock, (int64_t)dw[3] - y + 1);
         const size_t rawSize = bytesPerPixelRow * (size_t)lines;
         raw.resize(rawSize);
@@ -753,7 +755,7 @@ static int load_exr_image(HdrImage *image, const char *path)
         if (compression == 0 || dataSize >= rawSize)
         {
             // stored: NONE, or a chunk the writer could not shrink
-            if (dataSize != rawSize) { ok = false; break; }
+            if (dataSize != rawSize) return false;
             memcpy(raw.data(), src, rawSize);
         }
         else if (compression == 1)
@@ -767,31 +769,31 @@ static int load_exr_image(HdrImage *image, const char *path)
                 if (n < 0)
                 {
                     size_t len = (size_t)(-n);
-                    if (at + len > dataSize) { ok = false; break; }
+                    if (at + len > dataSize) return false;
                     tmp.insert(tmp.end(), src + at, src + at + len);
                     at += len;
                 }
                 else
                 {
-                    if (at >= dataSize) { ok = false; break; }
+                    if (at >= dataSize) return false;
                     tmp.insert(tmp.end(), (size_t)n + 1, src[at++]);
                 }
             }
-            if (!ok || tmp.size() != rawSize) { ok = false; break; }
+            if (!ok || tmp.size() != rawSize) return false;
             exr_unfilter(tmp, raw.data());
         }
         else if (compression == 4)
         {
             std::vector<int> sizes;
             for (const Channel &ch : channels) sizes.push_back(ch.type == 1 ? 1 : 2);
-            if (!piz_decode(src, dataSize, raw.data(), (int)width, (int)lines, sizes)) { ok = false; break; }
+            if (!piz_decode(src, dataSize, raw.data(), (int)width, (int)lines, sizes)) return false;
         }
         else
         {
             Inflate z;
             z.in = src;
             z.inLen = dataSize;
-            if (!z.run(tmp, rawSize) || tmp.size() != rawSize) { ok = false; break; }
+            if (!z.run(tmp, rawSize) || tmp.size() != rawSize) return false;
             exr_unfilter(tmp, raw.data());
         }
         for (int64_t l = 0; l < lines; ++l)
@@ -826,7 +828,29 @@ static int load_exr_image(HdrImage *image, const char *path)
                 }
             }
         }
-    }
+        return ok;
+    };
+    std::atomic<size_t> next(0);
+    std::atomic<bool> failed(false);
+    auto worker = [&]() {
+        std::vector<uint8_t> raw, tmp;
+        for (;;)
+        {
+            size_t i = next.fetch_add(1);
+            if (i >= chunks || failed.load()) break;
+            bool good = false;
+            try { good = decode_chunk(i, raw, tmp); } catch (...) { good = false; }
+            if (!good) failed.store(true);
+        }
+    };
+    unsigned threads = std::thread::hardware_concurrency();
+    threads = threads < 1 ? 1 : (threads > 8 ? 8 : threads);
+    if (chunks < 8) threads = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread &t : pool) t.join();
+    const bool ok = !failed.load();
     if (!ok)
     {
         free(out);
