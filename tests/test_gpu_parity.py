@@ -578,3 +578,42 @@ def test_tone_map_matches_oracle(gpu_sp):
         assert np.array_equal(sp.tone_map(synth, exposure), port.tone_map(synth, exposure))
     r.close()
     sp.set_params(samplesPerPixel=1, bounceCount=3)
+
+
+def test_assets_to_pixels_end_to_end(gpu_sp, tmp_path):
+    """The rows either side of the path plugged together through the C ABI only: a mesh read by
+    sp_b200_LoadObj and an environment map read by LoadExrImage (fixture files) are rendered, tone
+    mapped and written as PPM.  The oracle port gets the same arrays: the image must be bit-identical
+    (deterministic math) and the RGBA8 bytes equal."""
+    sp = gpu_sp
+    here = os.path.dirname(os.path.abspath(__file__))
+    vertices, indices = sp.load_obj(os.path.join(here, "golden", "quad_mix.obj"))
+    env = sp.load_exr(os.path.join(here, "golden", "exr", "zip_f32_rgb_70x45.exr"))
+    assert vertices is not None and env is not None and env.shape == (45, 70, 4)
+    mesh = W.Mesh(vertices, indices, smooth=False)
+    lo, hi = mesh.bounds()
+    wl = W.Workload(
+        name="assets_end_to_end", meshes=[mesh],
+        objects=[W.SceneObject(0, W.MATERIAL_SURFACE, rotation=W.quat_axis_angle((0.2, 1.0, 0.0), 0.6))],
+        materials=[W.Material(W.MATERIAL_BACKGROUND, emission_texture=W.IMAGE_ENV),
+                   W.Material(W.MATERIAL_SURFACE, albedo=(0.6, 0.5, 0.4), roughness=0.5)],
+        textures={W.IMAGE_ENV: env}, background=W.MATERIAL_BACKGROUND,
+        camera_position=W.frame_camera(lo, hi, 1.6), camera_rotation=(0.0, 0.0, 0.0, 1.0), film_distance=0.8,
+        width=96, height=72, spp=4, bounces=4)
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=4, bounceCount=4, radianceClamp=10.0, envFilter=0, mathMode=0, cullByDistance=1,
+                  tileWidth=64, tileHeight=64, renderMode=0, samplesPerPass=0)
+    img, m = r.render_frame(frame=9)
+    chk = ora.load_port_dm().scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=4, bounces=4, frame=9)
+    ntie = assert_same_image_up_to_ties(img, cimg, chk, 4, 4, 9)
+    assert m[3] > 0 and m[4] > 0 and (ntie > 0 or np.array_equal(m[1:5], cm[1:5]))
+    rgba8 = sp.tone_map(img)
+    if ntie == 0:
+        assert np.array_equal(rgba8, ora.load_port_dm().tone_map(cimg))
+    out = tmp_path / "frame.ppm"
+    sp.write_ppm(str(out), rgba8)
+    assert out.stat().st_size == len(b"P6\n96 72\n255\n") + 96 * 72 * 3
+    chk.close()
+    r.close()
+    sp.set_params(samplesPerPixel=1, bounceCount=3)
