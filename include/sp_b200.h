@@ -321,6 +321,33 @@ int LoadExrImage(HdrImage *image, const char *path);
  * hostPixels; RGBA8 result to hostRGBA8 and/or deviceRGBA8 (either may be NULL, not both). */
 int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, u32 pixelCount, f32 exposure,
                     u32 *hostRGBA8, void *deviceRGBA8);
+
+/* Environment pre-processing on the GPU (src/cubemap.cpp; the reference bakes both maps on the CPU
+ * at start-up, main.cpp:1307-1315).  Faces are written layer-major in the reference's order
+ * (+X -X +Y -Y +Z -Z, cubemap.cpp:13-21, basis vectors :54-104), each width x height RGBA f32, rows
+ * top to bottom: 6 * width * height * 4 floats, to hostFaces and/or deviceFaces (either may be
+ * NULL, not both).  The source goes through the same device texture cache as registered textures.
+ *
+ * sp_b200_CreateCubeMap replaces CreateCubeMap(HdrImage, MemoryArena*, u32, u32)
+ * (cubemap.cpp:237-291): per texel Normalize(forward + right*fx + up*fy) -> ToSphericalCoordinates
+ * -> MapToEquirectangular -> v flipped -> SampleImageBilinear (image.h:34-73), all four channels.
+ *
+ * sp_b200_CreateIrradianceCubeMap replaces CreateIrradianceCubeMap(HdrImage, MemoryArena*, u32,
+ * u32, u32 samplesPerPixel = 32) (cubemap.cpp:108-233).  The reference picks its sampling at
+ * compile time (IRRADIANCE_CUBEMAP_USE_UNIFORM_SAMPLING, config.h:47, = 1); here it is an argument:
+ *   SP_B200_IRRADIANCE_UNIFORM  the (phi, theta) grid of cubemap.cpp:152-198; sampleDelta is the
+ *       loop step (0.1f in the reference, "TODO: Parameterize"); samplesPerPixel is ignored, as there;
+ *   SP_B200_IRRADIANCE_RANDOM   cubemap.cpp:200-224: samplesPerPixel jittered directions per texel
+ *       drawn from ONE serial XorShift32 stream over all texels (state 0x45BA12F3, :122-123); every
+ *       texel's place in that stream is reached by a GF(2) jump, so the result equals the serial loop's.
+ * Each texel's terms are summed in the reference's order; radiance clamp = RADIANCE_CLAMP (config.h:36).
+ * Both return 0 (asserts abort through LogMessage like the rest of the library). */
+#define SP_B200_IRRADIANCE_UNIFORM 0u
+#define SP_B200_IRRADIANCE_RANDOM 1u
+int sp_b200_CreateCubeMap(const HdrImage *equirect, u32 width, u32 height, f32 *hostFaces,
+                          void *deviceFaces);
+int sp_b200_CreateIrradianceCubeMap(const HdrImage *equirect, u32 width, u32 height, u32 samplesPerPixel,
+                                    u32 sampling, f32 sampleDelta, f32 *hostFaces, void *deviceFaces);
 /* Primary-ray closest hits of (sample, frame): per pixel triangle index (-1 = miss), object
  * index and world t.  Output arrays are host memory, any may be NULL. */
 int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *triangleIndex,

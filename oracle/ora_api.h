@@ -146,6 +146,18 @@ void ora_sample_bilinear(const float *pixels, uint32_t w, uint32_t h, float u, f
  * alpha 255; out = count x RGBA8 (r in the low byte, like ToColor, src/math_lib.h:523-532).  The
  * shader is not CPU code, so this function is pinned by known-answer values only. */
 void ora_tone_map(const float *rgba, uint32_t count, float exposure, uint32_t *out);
+/* Environment pre-processing (src/cubemap.cpp).  pixels = w x h RGBA f32 equirectangular map; out =
+ * 6 faces (+X -X +Y -Y +Z -Z) of faceW x faceH RGBA f32, layer-major.
+ * ora_create_cube_map: CreateCubeMap (cubemap.cpp:237-291).
+ * ora_create_irradiance_cube_map: CreateIrradianceCubeMap (cubemap.cpp:108-233); sampling 0 = the
+ * uniform grid the reference's config.h:47 selects, 1 = the random branch.  The reference build
+ * compiles both branches (the file is included twice) but its sampleDelta is the literal 0.1f:
+ * any other value is refused there (returns 0; 1 on success).  The port takes any step. */
+void ora_create_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW, uint32_t faceH,
+                         float *out);
+int ora_create_irradiance_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                   uint32_t faceH, uint32_t samplesPerPixel, uint32_t sampling,
+                                   float sampleDelta, float *out);
 /* ComputeTiles (tile.h:11-42): tiles = maxTiles x 4 u32; returns count */
 uint32_t ora_compute_tiles(uint32_t w, uint32_t h, uint32_t tw, uint32_t th, uint32_t *tiles,
                            uint32_t maxTiles);

@@ -82,6 +82,19 @@ static u32 g_oraSamplesPerPixel = 1;
 #include "sp_scene.cpp"
 #include "sp_material_system.cpp"
 #include "simd_path_tracer.cpp"
+// src/cubemap.cpp twice: once as config.h:47 configures it (uniform irradiance sampling) and once
+// with the switch flipped, so the random branch (cubemap.cpp:200-224) is the reference's code too.
+// The file defines only `internal` functions and its own small types; a namespace per copy.
+namespace ora_cubemap_uniform {
+#include "cubemap.cpp"
+}
+#undef IRRADIANCE_CUBEMAP_USE_UNIFORM_SAMPLING
+#define IRRADIANCE_CUBEMAP_USE_UNIFORM_SAMPLING 0
+namespace ora_cubemap_random {
+#include "cubemap.cpp"
+}
+#undef IRRADIANCE_CUBEMAP_USE_UNIFORM_SAMPLING
+#define IRRADIANCE_CUBEMAP_USE_UNIFORM_SAMPLING 1
 // -----------------------------------------------------------------------------------------
 
 #include "ora_api.h"
@@ -879,4 +892,55 @@ extern "C" void ora_mesh_tree_stats(ora_Scene *s, uint32_t mesh, uint32_t *out6)
     out6[3] = maxDepth;
     out6[4] = reachable;
     out6[5] = contained;
+}
+
+// ---- environment pre-processing: the reference's bakers over a caller-supplied image --------
+template <class CubeMap>
+static void OraCopyFaces(const CubeMap &cube, uint32_t faceW, uint32_t faceH, float *out)
+{
+    for (uint32_t layer = 0; layer < 6; ++layer)
+        memcpy(out + (size_t)layer * faceW * faceH * 4, cube.images[layer].pixels, (size_t)faceW * faceH * 16);
+}
+
+struct OraFaceArena
+{
+    MemoryArena arena;
+    void *memory;
+    OraFaceArena(uint32_t faceW, uint32_t faceH)
+    {
+        size_t bytes = (size_t)6 * faceW * faceH * 16 + 4096;
+        memory = calloc(1, bytes);
+        InitializeMemoryArena(&arena, memory, bytes);
+    }
+    ~OraFaceArena() { free(memory); }
+};
+
+extern "C" void ora_create_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                    uint32_t faceH, float *out)
+{
+    HdrImage env = {};
+    env.pixels = (f32 *)pixels;
+    env.width = w;
+    env.height = h;
+    OraFaceArena a(faceW, faceH);
+    OraCopyFaces(ora_cubemap_uniform::CreateCubeMap(env, &a.arena, faceW, faceH), faceW, faceH, out);
+}
+
+extern "C" int ora_create_irradiance_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                              uint32_t faceH, uint32_t samplesPerPixel, uint32_t sampling,
+                                              float sampleDelta, float *out)
+{
+    if (sampling == 0 && sampleDelta != 0.1f) return 0; // literal in cubemap.cpp:160
+    HdrImage env = {};
+    env.pixels = (f32 *)pixels;
+    env.width = w;
+    env.height = h;
+    OraFaceArena a(faceW, faceH);
+    if (sampling == 0)
+        OraCopyFaces(ora_cubemap_uniform::CreateIrradianceCubeMap(env, &a.arena, faceW, faceH, samplesPerPixel),
+                     faceW, faceH, out);
+    else
+        OraCopyFaces(ora_cubemap_random::CreateIrradianceCubeMap(env, &a.arena, faceW, faceH, samplesPerPixel),
+                     faceW, faceH, out);
+    return 1;
 }

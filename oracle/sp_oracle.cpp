@@ -1326,6 +1326,133 @@ extern "C" void ora_sample_bilinear(const float *pixels, uint32_t w, uint32_t h,
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Environment pre-processing (src/cubemap.cpp), restated.  Faces +X -X +Y -Y +Z -Z.
+
+// MapCubeMapLayerIndexToBasisVectors, cubemap.cpp:54-104: {forward, up, right} per layer
+static void face_axes(uint32_t layer, V3 *fwd, V3 *up, V3 *right)
+{
+    static const float table[6][9] = {
+        {1, 0, 0, 0, 1, 0, 0, 0, -1},  {-1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 1, 0, 0, 0, -1, 1, 0, 0},
+        {0, -1, 0, 0, 0, 1, 1, 0, 0},  {0, 0, 1, 0, 1, 0, 1, 0, 0},  {0, 0, -1, 0, 1, 0, -1, 0, 0}};
+    const float *t = table[layer];
+    *fwd = P3(t[0], t[1], t[2]);
+    *up = P3(t[3], t[4], t[5]);
+    *right = P3(t[6], t[7], t[8]);
+}
+
+// cubemap.cpp:263-275 (and :139-150)
+static V3 face_direction(V3 fwd, V3 up, V3 right, uint32_t x, uint32_t y, uint32_t w, uint32_t h)
+{
+    float fx = (float)x / (float)w, fy = (float)y / (float)h;
+    fy = 1.0f - fy;
+    fx = fx * 2.0f - 1.0f;
+    fy = fy * 2.0f - 1.0f;
+    return unit(plus(plus(fwd, times(right, fx)), times(up, fy)));
+}
+
+// cubemap.cpp:277-281: direction -> spherical -> equirect uv, v flipped -> bilinear
+static V4 env_bilinear(const Image &env, V3 d)
+{
+    V2 uv = to_equirect(to_sphere(d));
+    uv.y = 1.0f - uv.y;
+    return bilinear(env, uv);
+}
+
+static inline float clamp_to(float v, float c) { return lo2(hi2(v, 0.0f), c); } // Clamp, math_utils.h:135-139
+
+static Image wrap_image(const float *pixels, uint32_t w, uint32_t h)
+{
+    Image img;
+    img.w = w;
+    img.h = h;
+    img.px.assign(pixels, pixels + (size_t)w * h * 4);
+    return img;
+}
+
+// CreateCubeMap, cubemap.cpp:237-291
+extern "C" void ora_create_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                    uint32_t faceH, float *out)
+{
+    Image env = wrap_image(pixels, w, h);
+    for (uint32_t layer = 0; layer < 6; ++layer)
+    {
+        V3 fwd, up, right;
+        face_axes(layer, &fwd, &up, &right);
+        for (uint32_t y = 0; y < faceH; ++y)
+            for (uint32_t x = 0; x < faceW; ++x)
+            {
+                V4 s = env_bilinear(env, face_direction(fwd, up, right, x, y, faceW, faceH));
+                float *dst = out + (((size_t)layer * faceH + y) * faceW + x) * 4;
+                dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = s.w;
+            }
+    }
+}
+
+// CreateIrradianceCubeMap, cubemap.cpp:108-233.  sampling 0: the uniform (phi, theta) grid
+// (:152-198, the branch config.h:47 compiles); sampling 1: random offsets from one serial stream
+// (:200-224).  sampleDelta is the 0.1f of :160.
+extern "C" int ora_create_irradiance_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                               uint32_t faceH, uint32_t samplesPerPixel, uint32_t sampling,
+                                               float sampleDelta, float *out)
+{
+    Image env = wrap_image(pixels, w, h);
+    const float clampValue = 10.0f; // RADIANCE_CLAMP, config.h:36
+    float contribution = 1.0f / (float)samplesPerPixel;
+    uint32_t rng = 0x45BA12F3u; // :123, never reseeded
+    for (uint32_t layer = 0; layer < 6; ++layer)
+    {
+        V3 fwd, up, right;
+        face_axes(layer, &fwd, &up, &right);
+        for (uint32_t y = 0; y < faceH; ++y)
+            for (uint32_t x = 0; x < faceW; ++x)
+            {
+                V3 dir = face_direction(fwd, up, right, x, y, faceW, faceH);
+                V3 sum = P3(0, 0, 0);
+                if (sampling == 0)
+                {
+                    V3 tangent = unit(outer(up, dir));
+                    V3 bitangent = unit(outer(dir, tangent));
+                    uint32_t count = 0;
+                    for (float phi = 0.0f; phi < 2.0f * kPi; phi += sampleDelta)
+                        for (float theta = 0.0f; theta < 0.5f * kPi; theta += sampleDelta)
+                        {
+                            V3 local = from_sphere(V2{phi, theta});
+                            V3 world = plus(plus(times(dir, local.y), times(tangent, local.x)),
+                                            times(bitangent, local.z));
+                            V4 s = env_bilinear(env, world);
+                            V3 radiance = P3(clamp_to(s.x, clampValue), clamp_to(s.y, clampValue),
+                                             clamp_to(s.z, clampValue));
+                            sum = plus(sum, times(times(radiance, lm_cos(theta)), lm_sin(theta)));
+                            count++;
+                        }
+                    sum = times(times(sum, kPi), 1.0f / (float)count);
+                }
+                else
+                {
+                    for (uint32_t i = 0; i < samplesPerPixel; ++i)
+                    {
+                        // Vec3(RandomBilateral, RandomBilateral, RandomBilateral): g++ evaluates
+                        // call arguments right to left, so z is drawn first
+                        float oz = rnd11(&rng);
+                        float oy = rnd11(&rng);
+                        float ox = rnd11(&rng);
+                        V3 sd = unit(plus(dir, P3(ox, oy, oz)));
+                        if (inner(sd, dir) < 0.0f) sd = flip(sd);
+                        float cosine = hi2(inner(dir, sd), 0.0f);
+                        V4 s = env_bilinear(env, sd);
+                        V3 radiance = P3(clamp_to(s.x * cosine, clampValue), clamp_to(s.y * cosine, clampValue),
+                                         clamp_to(s.z * cosine, clampValue));
+                        sum = plus(sum, times(radiance, contribution));
+                    }
+                }
+                float *dst = out + (((size_t)layer * faceH + y) * faceW + x) * 4;
+                dst[0] = sum.x; dst[1] = sum.y; dst[2] = sum.z; dst[3] = 1.0f;
+            }
+    }
+    return 1;
+}
+
 // ComputeTiles, tile.h:11-42
 extern "C" uint32_t ora_compute_tiles(uint32_t w, uint32_t h, uint32_t tw, uint32_t th,
                                       uint32_t *tiles, uint32_t maxTiles)

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../vk_cinematic_b200/csrc/spb_capture.h"
+#include "../../vk_cinematic_b200/csrc/spb_cubemap.cuh"
 #include "../../oracle/ora_api.h"
 
 using namespace spb;
@@ -449,5 +450,73 @@ extern "C" void hostsim_check_coverage(ora_Scene *s, uint32_t spp, uint32_t fram
         out5[1] += per[t][0];
         out5[3] += per[t][1];
         out5[4] += per[t][2];
+    }
+}
+
+// ---- environment pre-processing (spb_cubemap.cuh on the host) ---------------------------------
+// Same decomposition as the kernels in spb_cubemap.cu: per-texel state found by the GF(2) jump,
+// per-sample terms evaluated independently, folded front to back.
+extern "C" void hostsim_create_cube_map(const float *pixels, uint32_t w, uint32_t h, uint32_t faceW,
+                                        uint32_t faceH, float *out)
+{
+    DImage env;
+    env.pixels = (const v4f *)pixels;
+    env.width = w; env.height = h; env.pad = 0;
+    for (uint32_t layer = 0; layer < 6; ++layer)
+        for (uint32_t y = 0; y < faceH; ++y)
+            for (uint32_t x = 0; x < faceW; ++x)
+            {
+                v4f t = cube_map_texel<0>(env, layer, x, y, faceW, faceH);
+                float *dst = out + (((size_t)layer * faceH + y) * faceW + x) * 4;
+                dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+            }
+}
+
+extern "C" void hostsim_create_irradiance_cube_map(const float *pixels, uint32_t w, uint32_t h,
+                                                   uint32_t faceW, uint32_t faceH, uint32_t spp,
+                                                   uint32_t sampling, float sampleDelta, float *out)
+{
+    DImage env;
+    env.pixels = (const v4f *)pixels;
+    env.width = w; env.height = h; env.pad = 0;
+    std::vector<float> phis(irradiance_loop_values(2.0f * SPB_PI, sampleDelta, nullptr, 0));
+    std::vector<float> thetas(irradiance_loop_values(0.5f * SPB_PI, sampleDelta, nullptr, 0));
+    irradiance_loop_values(2.0f * SPB_PI, sampleDelta, phis.data(), (uint32_t)phis.size());
+    irradiance_loop_values(0.5f * SPB_PI, sampleDelta, thetas.data(), (uint32_t)thetas.size());
+    std::vector<uint32_t> jumpTexel(32 * 32), jumpSample(32 * 32);
+    if (sampling)
+    {
+        xorshift_build_jump_table(3 * spp, jumpTexel.data());
+        xorshift_build_jump_table(3, jumpSample.data());
+    }
+    const uint32_t sampleCount = sampling ? spp : (uint32_t)(phis.size() * thetas.size());
+    std::vector<f3> terms(sampleCount);
+    for (uint32_t texel = 0; texel < 6 * faceW * faceH; ++texel)
+    {
+        uint32_t layer = texel / (faceW * faceH), r = texel % (faceW * faceH);
+        uint32_t y = r / faceW, x = r % faceW;
+        f3 forward, up, right, tangent, bitangent;
+        cube_face_basis(layer, forward, up, right);
+        f3 dir = cube_texel_direction(forward, up, right, x, y, faceW, faceH);
+        irradiance_frame(up, dir, tangent, bitangent);
+        uint32_t texelState = sampling ? xorshift_jump(jumpTexel.data(), texel, 0x45BA12F3u) : 0u;
+        for (uint32_t s = sampleCount; s-- > 0;) // any order: the terms are independent
+        {
+            if (sampling)
+            {
+                uint32_t rng = xorshift_jump(jumpSample.data(), s, texelState);
+                terms[s] = irradiance_random_term<0>(env, dir, rng, 10.0f, 1.0f / (float)spp);
+            }
+            else
+            {
+                uint32_t iphi = s / (uint32_t)thetas.size(), itheta = s % (uint32_t)thetas.size();
+                terms[s] = irradiance_uniform_term<0>(env, dir, tangent, bitangent, phis[iphi], thetas[itheta], 10.0f);
+            }
+        }
+        f3 sum = mk3(0, 0, 0);
+        for (uint32_t s = 0; s < sampleCount; ++s) sum = add3(sum, terms[s]);
+        if (!sampling) sum = irradiance_uniform_finish(sum, sampleCount);
+        float *dst = out + (size_t)texel * 4;
+        dst[0] = sum.x; dst[1] = sum.y; dst[2] = sum.z; dst[3] = 1.0f;
     }
 }

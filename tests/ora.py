@@ -132,6 +132,11 @@ class OracleLib:
         lib.ora_radiance_for_path.argtypes = [C.c_void_p, _f, C.c_uint32, _f]
         if hasattr(lib, "ora_tone_map"):
             lib.ora_tone_map.argtypes = [_f, C.c_uint32, C.c_float, _u]
+        lib.ora_create_cube_map.argtypes = [_f] + [C.c_uint32] * 4 + [_f]
+        lib.ora_create_irradiance_cube_map.argtypes = [_f] + [C.c_uint32] * 6 + [C.c_float, _f]
+        lib.ora_create_irradiance_cube_map.restype = C.c_int
+        lib.hostsim_create_cube_map.argtypes = [_f] + [C.c_uint32] * 4 + [_f]
+        lib.hostsim_create_irradiance_cube_map.argtypes = [_f] + [C.c_uint32] * 6 + [C.c_float, _f]
         lib.ora_sample_nearest.argtypes = [_f, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f]
         lib.ora_sample_bilinear.argtypes = [_f, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f]
         lib.ora_compute_tiles.argtypes = [C.c_uint32] * 4 + [_u, C.c_uint32]
@@ -174,6 +179,26 @@ class OracleLib:
     def ray_aabb_scalar(self, mn, mx, o, d):
         return np.float32(self.lib.ora_ray_aabb_scalar(_fp(_f32(mn)), _fp(_f32(mx)), _fp(_f32(o)),
                                                        _fp(_f32(d))))
+
+    # ---- environment pre-processing (src/cubemap.cpp) ----
+    def create_cube_map(self, env, face_w, face_h):
+        """env: (H, W, 4) float32 equirect map -> (6, face_h, face_w, 4)"""
+        env = _f32(env)
+        out = np.zeros((6, face_h, face_w, 4), np.float32)
+        fn = self.lib.hostsim_create_cube_map if self.name == "hostsim" else self.lib.ora_create_cube_map
+        fn(_fp(env), env.shape[1], env.shape[0], face_w, face_h, _fp(out))
+        return out
+
+    def create_irradiance_cube_map(self, env, face_w, face_h, spp=32, sampling=0, sample_delta=0.1):
+        env = _f32(env)
+        out = np.zeros((6, face_h, face_w, 4), np.float32)
+        if self.name == "hostsim":
+            self.lib.hostsim_create_irradiance_cube_map(_fp(env), env.shape[1], env.shape[0], face_w, face_h,
+                                                        spp, sampling, sample_delta, _fp(out))
+        elif not self.lib.ora_create_irradiance_cube_map(_fp(env), env.shape[1], env.shape[0], face_w, face_h,
+                                                         spp, sampling, sample_delta, _fp(out)):
+            raise ValueError("%s cannot bake with sample_delta %r" % (self.name, sample_delta))
+        return out
 
     def hemisphere(self, state, normal):
         s = C.c_uint32(state)

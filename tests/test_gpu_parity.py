@@ -617,3 +617,100 @@ def test_assets_to_pixels_end_to_end(gpu_sp, tmp_path):
     chk.close()
     r.close()
     sp.set_params(samplesPerPixel=1, bounceCount=3)
+
+
+# ---- environment pre-processing (src/cubemap.cpp) --------------------------
+
+def test_cube_map_and_irradiance_match_oracle(gpu_sp):
+    """sp_b200_CreateCubeMap / sp_b200_CreateIrradianceCubeMap (k_cube_map, k_irradiance) against the
+    reference's CreateCubeMap / CreateIrradianceCubeMap (cubemap.cpp:108-291, compiled unmodified in
+    oracle/_ref; both sampling branches) in deterministic-math mode: every float of every face bit
+    for bit.  Ragged and 1x1 faces, sample counts that are not powers of two (the random branch's
+    serial XorShift32 stream is reached per texel by a GF(2) jump on the device), the committed
+    fixture made from the reference, and other sampleDelta values against the port."""
+    sp = gpu_sp
+    sp.set_params(mathMode=0)
+    chk = best(dm=True)
+    env = W.make_env_map(256, 128)
+    for (w, h, spp) in ((7, 9, 13), (1, 1, 1), (16, 16, 32), (33, 5, 100)):
+        assert same_bits(sp.create_cube_map(env, 3 * w, 2 * h), chk.create_cube_map(env, 3 * w, 2 * h)), (w, h)
+        for sampling in (sp.IRRADIANCE_UNIFORM, sp.IRRADIANCE_RANDOM):
+            got = sp.create_irradiance_cube_map(env, w, h, spp=spp, sampling=sampling)
+            want = chk.create_irradiance_cube_map(env, w, h, spp=spp, sampling=sampling)
+            assert same_bits(got, want), (w, h, spp, sampling)
+    # more than one shared-memory chunk of terms per texel (SPB_IRR_CHUNK = 1024): 2500 random
+    # samples, and a finer uniform grid (sampleDelta 0.05: 126 x 32 = 4032 terms) against the port
+    port = ora.load_port_dm()
+    assert same_bits(sp.create_irradiance_cube_map(env, 3, 2, spp=2500, sampling=sp.IRRADIANCE_RANDOM),
+                     chk.create_irradiance_cube_map(env, 3, 2, spp=2500, sampling=1))
+    for delta in (0.05, 0.25, 3.0):
+        assert same_bits(sp.create_irradiance_cube_map(env, 3, 2, sample_delta=delta),
+                         port.create_irradiance_cube_map(env, 3, 2, sample_delta=delta)), delta
+    g = np.load(os.path.join(GOLD, "g4_cubemap.npz"))
+    genv = W.make_env_map(int(g["env_params"][0]), int(g["env_params"][1]), str(g["env_variant"]))
+    cw, ch = (int(v) for v in g["cube_size"])
+    iw, ih = (int(v) for v in g["irradiance_size"])
+    assert same_bits(sp.create_cube_map(genv, cw, ch), g["cube_dm"])
+    assert same_bits(sp.create_irradiance_cube_map(genv, iw, ih), g["irradiance_uniform_dm"])
+    assert same_bits(sp.create_irradiance_cube_map(genv, iw, ih, spp=int(g["spp"]), sampling=sp.IRRADIANCE_RANDOM),
+                     g["irradiance_random_dm"])
+
+
+def _time_bakers(sp, env):
+    """With SPB_TIMING_OUT set: wall time of the two bakers at the reference's sizes with the map
+    already resident on the device and the faces left there (launch + kernel + synchronize; best
+    of 5), appended to that file for profiles/.  Not a test."""
+    path = os.environ.get("SPB_TIMING_OUT")
+    if not path:
+        return
+    import time
+    import torch
+    img = np.ascontiguousarray(env, dtype=np.float32)
+    hdr = sp.HdrImage(img.ctypes.data_as(C.POINTER(C.c_float)), img.shape[1], img.shape[0])
+    faces = torch.empty(6 * 1024 * 1024 * 4, dtype=torch.float32, device="cuda")
+    lines = []
+    for name, call in (
+            ("cube_map 4096x2048 -> 6x1024x1024", lambda: sp.lib.sp_b200_CreateCubeMap(C.byref(hdr), 1024, 1024, None, faces.data_ptr())),
+            ("irradiance uniform 6x32x32 (1008 terms/texel)", lambda: sp.lib.sp_b200_CreateIrradianceCubeMap(C.byref(hdr), 32, 32, 32, 0, 0.1, None, faces.data_ptr())),
+            ("irradiance random 6x32x32 spp 32", lambda: sp.lib.sp_b200_CreateIrradianceCubeMap(C.byref(hdr), 32, 32, 32, 1, 0.1, None, faces.data_ptr()))):
+        call()  # uploads the map on first use
+        best_s = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            call()
+            best_s = min(best_s, time.perf_counter() - t0)
+        lines.append("%s: %.3f ms" % (name, best_s * 1e3))
+    sp.lib.sp_b200_FlushTextureCache()
+    with open(path, "a") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def test_cube_map_reference_sizes(gpu_sp):
+    """The sizes the reference bakes at start-up (main.cpp:1307-1315): a 4096x2048 map to 6 x 1024^2
+    faces and to a 6 x 32^2 irradiance map on the uniform grid (1008 terms per texel) -- bit-exact in
+    deterministic-math mode; with CUDA's float libm (mathMode 1) against the plain reference within
+    a stated tolerance: cube map texels differ by more than 1e-3 relative on at most 2 % of the
+    texels (a 1-ulp change of u or v moves the bilinear weights by 4096 ulp), irradiance texels by
+    at most 1e-3 relative."""
+    sp = gpu_sp
+    env = W.make_env_map(4096, 2048)
+    sp.set_params(mathMode=0)
+    chk = best(dm=True)
+    want_cube = chk.create_cube_map(env, 1024, 1024)
+    got_cube = sp.create_cube_map(env, 1024, 1024)
+    assert same_bits(got_cube, want_cube)
+    want_irr = chk.create_irradiance_cube_map(env, 32, 32)
+    assert same_bits(sp.create_irradiance_cube_map(env, 32, 32), want_irr)
+    _time_bakers(sp, env)
+    sp.set_params(mathMode=1)
+    try:
+        plain = best(dm=False)
+        fast_cube = sp.create_cube_map(env, 256, 256)
+        ref_cube = plain.create_cube_map(env, 256, 256)
+        rel = np.abs(fast_cube - ref_cube) / np.maximum(np.abs(ref_cube), 1e-3)
+        assert (rel.max(axis=-1) > 1e-3).mean() <= 0.02
+        fast_irr = sp.create_irradiance_cube_map(env, 32, 32)
+        ref_irr = plain.create_irradiance_cube_map(env, 32, 32)
+        assert np.allclose(fast_irr, ref_irr, rtol=1e-3, atol=0)
+    finally:
+        sp.set_params(mathMode=0)

@@ -16,6 +16,7 @@
 
 #include "spb_capture.h"
 #include "spb_kernels.cuh"
+#include "spb_cubemap.cuh"
 
 using namespace spb;
 
@@ -1456,6 +1457,119 @@ extern "C" int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, 
     if (hostRGBA8)
         SPB_CUDA(cudaMemcpyAsync(hostRGBA8, dst, (size_t)pixelCount * 4, cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
+    return 0;
+}
+
+// Environment pre-processing (src/cubemap.cpp): the equirectangular map the path samples, turned
+// into the cube map / irradiance cube map the reference bakes at start-up (main.cpp:1307-1315).
+// The source image goes through the same device texture cache as the path tracer's textures.
+static DImage device_image(const HdrImage *equirect)
+{
+    SPB_ASSERT(equirect && equirect->pixels && equirect->width > 0 && equirect->height > 0);
+    DImage env;
+    env.pixels = device_texture(*equirect);
+    env.width = equirect->width;
+    env.height = equirect->height;
+    env.pad = 0;
+    return env;
+}
+
+static void finish_faces(const v4f *faces, size_t texels, f32 *hostFaces, void *deviceFaces)
+{
+    Library &L = lib();
+    if (hostFaces)
+        SPB_CUDA(cudaMemcpyAsync(hostFaces, faces, texels * 16, cudaMemcpyDeviceToHost, L.stream));
+    (void)deviceFaces;
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+}
+
+extern "C" int sp_b200_CreateCubeMap(const HdrImage *equirect, u32 width, u32 height, f32 *hostFaces,
+                                     void *deviceFaces)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(hostFaces || deviceFaces);
+    size_t texels = (size_t)6 * width * height;
+    if (texels == 0) return 0;
+    DImage env = device_image(equirect);
+    v4f *faces = (v4f *)deviceFaces;
+    if (!faces)
+    {
+        L.scratchB.ensure(texels * 16);
+        faces = (v4f *)L.scratchB.ptr;
+    }
+    launch_cube_map(kernel_config(), env, faces, width, height, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    finish_faces(faces, texels, hostFaces, deviceFaces);
+    return 0;
+}
+
+extern "C" int sp_b200_CreateIrradianceCubeMap(const HdrImage *equirect, u32 width, u32 height,
+                                               u32 samplesPerPixel, u32 sampling, f32 sampleDelta,
+                                               f32 *hostFaces, void *deviceFaces)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(hostFaces || deviceFaces);
+    SPB_ASSERT(sampling == SP_B200_IRRADIANCE_UNIFORM || sampling == SP_B200_IRRADIANCE_RANDOM);
+    size_t texels = (size_t)6 * width * height;
+    if (texels == 0) return 0;
+    SPB_ASSERT(texels < 0xFFFFFFFFull);
+    IrradianceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.env = device_image(equirect);
+    a.width = width;
+    a.height = height;
+    a.clampValue = (f32)10; // RADIANCE_CLAMP, config.h:36 (compile-time in the reference's baker)
+    std::vector<uint32_t> staging;
+    if (sampling == SP_B200_IRRADIANCE_UNIFORM)
+    {
+        // the reference's loop variables (cubemap.cpp:162-164): phi and theta grow by repeated
+        // float addition of sampleDelta (0.1f there), bounds 2*PI and 0.5*PI in float
+        SPB_ASSERT(sampleDelta > 1e-3f);
+        std::vector<float> phis(irradiance_loop_values(2.0f * SPB_PI, sampleDelta, nullptr, 0));
+        std::vector<float> thetas(irradiance_loop_values(0.5f * SPB_PI, sampleDelta, nullptr, 0));
+        irradiance_loop_values(2.0f * SPB_PI, sampleDelta, phis.data(), (uint32_t)phis.size());
+        irradiance_loop_values(0.5f * SPB_PI, sampleDelta, thetas.data(), (uint32_t)thetas.size());
+        a.phiCount = (uint32_t)phis.size();
+        a.thetaCount = (uint32_t)thetas.size();
+        staging.resize(phis.size() + thetas.size());
+        memcpy(staging.data(), phis.data(), phis.size() * 4);
+        memcpy(staging.data() + phis.size(), thetas.data(), thetas.size() * 4);
+    }
+    else
+    {
+        SPB_ASSERT(samplesPerPixel > 0 && samplesPerPixel < (1u << 28));
+        a.samplesPerPixel = samplesPerPixel;
+        a.sampleContribution = 1.0f / (f32)samplesPerPixel; // cubemap.cpp:115
+        a.seed = 0x45BA12F3u;                               // cubemap.cpp:123
+        staging.resize(2 * 32 * 32);
+        xorshift_build_jump_table(3 * samplesPerPixel, staging.data());
+        xorshift_build_jump_table(3, staging.data() + 32 * 32);
+    }
+    L.scratchA.ensure(staging.size() * 4);
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, L.stream));
+    if (sampling == SP_B200_IRRADIANCE_UNIFORM)
+    {
+        a.phis = (const float *)L.scratchA.ptr;
+        a.thetas = a.phis + a.phiCount;
+    }
+    else
+    {
+        a.jumpTexel = (const uint32_t *)L.scratchA.ptr;
+        a.jumpSample = a.jumpTexel + 32 * 32;
+    }
+    a.out = (v4f *)deviceFaces;
+    if (!a.out)
+    {
+        L.scratchB.ensure(texels * 16);
+        a.out = (v4f *)L.scratchB.ptr;
+    }
+    launch_irradiance(kernel_config(), a, sampling == SP_B200_IRRADIANCE_RANDOM ? 1 : 0, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    finish_faces(a.out, texels, hostFaces, deviceFaces);
     return 0;
 }
 

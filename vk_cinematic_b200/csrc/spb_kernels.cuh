@@ -96,6 +96,27 @@ void launch_evaluate_material(const KernelConfig &cfg, const DMaterials *materia
 void launch_tone_map(const KernelConfig &cfg, const v4f *pixels, uint32_t count, float exposure, uint32_t *out,
                      cudaStream_t stream);
 
+// Environment pre-processing (spb_cubemap.cu; src/cubemap.cpp:108-291).  out = 6 faces of
+// width x height RGBA f32, layer-major (+X -X +Y -Y +Z -Z), rows top to bottom.
+void launch_cube_map(const KernelConfig &cfg, const DImage &env, v4f *out, uint32_t width, uint32_t height,
+                     cudaStream_t stream);
+struct IrradianceArgs
+{
+    DImage env;
+    v4f *out;
+    uint32_t width, height;
+    float clampValue;
+    // uniform mode: the phi / theta values of the reference's float-accumulating loops
+    const float *phis, *thetas;
+    uint32_t phiCount, thetaCount;
+    // random mode: serial XorShift32 stream, three draws per sample; jump tables (32 x 32 words,
+    // see xorshift_jump) for strides of 3 * samplesPerPixel draws (texel) and 3 draws (sample)
+    uint32_t samplesPerPixel, seed;
+    float sampleContribution;
+    const uint32_t *jumpTexel, *jumpSample;
+};
+void launch_irradiance(const KernelConfig &cfg, const IrradianceArgs &args, int mode, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // wavefront renderer (spb_wavefront.cu)
 

@@ -259,6 +259,9 @@ _SIGNATURES = {
     "sp_b200_LoadObj": (C.c_int, [C.c_char_p, _P(sp_b200_MeshData)]),
     "sp_b200_FreeMeshData": (None, [_P(sp_b200_MeshData)]),
     "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
+    "sp_b200_CreateCubeMap": (C.c_int, [C.c_void_p, u32, u32, C.c_void_p, C.c_void_p]),
+    "sp_b200_CreateIrradianceCubeMap": (C.c_int, [C.c_void_p, u32, u32, u32, u32, f32, C.c_void_p,
+                                                  C.c_void_p]),
     "sp_b200_PrimaryHits": (C.c_int, [_P(sp_Context), u32, u32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_RayIntersectSceneBatch": (C.c_int, [_P(sp_Scene), u32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, _P(sp_Metrics)]),
@@ -365,6 +368,38 @@ def tone_map(rgba, exposure=1.0):
     if lib.sp_b200_ToneMap(img.ctypes.data, None, out.size, exposure, out.ctypes.data, None) != 0:
         raise RuntimeError("sp_b200_ToneMap failed")
     return out.reshape(img.shape[:-1])
+
+
+IRRADIANCE_UNIFORM, IRRADIANCE_RANDOM = 0, 1
+
+
+def _equirect(env):
+    img = np.ascontiguousarray(env, dtype=np.float32)
+    assert img.ndim == 3 and img.shape[2] == 4
+    hdr = HdrImage(img.ctypes.data_as(C.POINTER(C.c_float)), img.shape[1], img.shape[0])
+    return img, hdr
+
+
+def create_cube_map(env, face_w, face_h):
+    """CreateCubeMap (cubemap.cpp:237-291) through sp_b200_CreateCubeMap: (H, W, 4) float32
+    equirectangular map -> (6, face_h, face_w, 4) faces (+X -X +Y -Y +Z -Z)."""
+    img, hdr = _equirect(env)
+    out = np.zeros((6, face_h, face_w, 4), np.float32)
+    if lib.sp_b200_CreateCubeMap(C.byref(hdr), face_w, face_h, out.ctypes.data, None) != 0:
+        raise RuntimeError("sp_b200_CreateCubeMap failed")
+    lib.sp_b200_FlushTextureCache()  # `img` may be a temporary: forget its device copy
+    return out
+
+
+def create_irradiance_cube_map(env, face_w, face_h, spp=32, sampling=IRRADIANCE_UNIFORM, sample_delta=0.1):
+    """CreateIrradianceCubeMap (cubemap.cpp:108-233) through sp_b200_CreateIrradianceCubeMap."""
+    img, hdr = _equirect(env)
+    out = np.zeros((6, face_h, face_w, 4), np.float32)
+    if lib.sp_b200_CreateIrradianceCubeMap(C.byref(hdr), face_w, face_h, spp, sampling, sample_delta,
+                                           out.ctypes.data, None) != 0:
+        raise RuntimeError("sp_b200_CreateIrradianceCubeMap failed")
+    lib.sp_b200_FlushTextureCache()
+    return out
 
 
 def write_ppm(path, rgba8):
