@@ -322,6 +322,20 @@ int LoadExrImage(HdrImage *image, const char *path);
 int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, u32 pixelCount, f32 exposure,
                     u32 *hostRGBA8, void *deviceRGBA8);
 
+/* Image files out of the path (the reference has no writer; its frames go to the swap chain,
+ * main.cpp:1607).  House convention of LoadExrImage: 0 on success, 1 on failure.
+ * sp_b200_SaveExrImage: RGBA f32 image -> single-part scanline OpenEXR file, channels A B G R,
+ *   pixelType HALF (round to nearest even) or FLOAT, compression NONE / ZIPS / ZIP; what LoadExrImage
+ *   (this library's and the reference's tinyexr-based one) reads back bit for bit.
+ * sp_b200_SavePpm: RGBA8 pixels as sp_b200_ToneMap stores them (r in the low byte) -> binary PPM. */
+#define SP_B200_EXR_HALF 1u
+#define SP_B200_EXR_FLOAT 2u
+#define SP_B200_EXR_NONE 0u
+#define SP_B200_EXR_ZIPS 2u
+#define SP_B200_EXR_ZIP 3u
+int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32 pixelType, u32 compression);
+int sp_b200_SavePpm(const u32 *rgba8, u32 width, u32 height, const char *path);
+
 /* Environment pre-processing on the GPU (src/cubemap.cpp; the reference bakes both maps on the CPU
  * at start-up, main.cpp:1307-1315).  Faces are written layer-major in the reference's order
  * (+X -X +Y -Y +Z -Z, cubemap.cpp:13-21, basis vectors :54-104), each width x height RGBA f32, rows

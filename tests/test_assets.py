@@ -170,3 +170,75 @@ def test_load_exr_refuses_what_it_cannot_read(tmp_path):
     p = tmp_path / "flipped.exr"
     p.write_bytes(bytes(broken))
     sp.load_exr(str(p))
+
+
+# ---------------------------------------------------------------------------------------------
+# Image output: sp_b200_SaveExrImage / sp_b200_SavePpm.  Three independent
+# readers check every file: the library's own LoadExrImage, the reference's loader (tinyexr,
+# compiled unmodified) where present, and OpenCV's OpenEXR decoder.
+
+def _test_image(h, w, seed):
+    rng = np.random.RandomState(seed)
+    img = (rng.rand(h, w, 4) ** 3 * 60).astype(np.float32)
+    img[h // 3: h // 2] = np.linspace(0, 3, w, dtype=np.float32)[None, :, None]  # smooth rows: matches to find
+    img[0, 0] = (0.0, -0.0, 1e-8, 65519.0)       # zero, negative zero, a half subnormal's neighbourhood, just below overflow
+    img[0, 1 % w] = (6.1e-5, 5.9e-8, 2.98e-8, 1.0)
+    return img
+
+
+@pytest.mark.parametrize("pixel_type", ["half", "float"])
+@pytest.mark.parametrize("compression", ["none", "zips", "zip"])
+@pytest.mark.parametrize("shape", [(45, 70), (1, 1), (16, 3), (33, 129)])
+def test_save_exr_round_trip(tmp_path, pixel_type, compression, shape):
+    img = _test_image(shape[0], shape[1], seed=shape[0] * 131 + shape[1])
+    want = img.astype(np.float16).astype(np.float32) if pixel_type == "half" else img
+    path = str(tmp_path / "out.exr")
+    assert sp.save_exr(path, img, {"half": sp.EXR_HALF, "float": sp.EXR_FLOAT}[pixel_type],
+                       {"none": sp.EXR_NONE, "zips": sp.EXR_ZIPS, "zip": sp.EXR_ZIP}[compression])
+    got = sp.load_exr(path)
+    assert got is not None and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    ref = _reference_exr_loader()
+    if ref is not None:
+        r = ref(path)
+        assert r is not None and np.array_equal(r.view(np.uint32), want.view(np.uint32))
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    bgra = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert bgra is not None and bgra.shape == want.shape
+    assert np.array_equal(np.ascontiguousarray(bgra[..., [2, 1, 0, 3]]).view(np.uint32), want.view(np.uint32))
+
+
+def test_save_exr_compresses_and_refuses(tmp_path):
+    """ZIP must actually shrink a smooth image (the match search and the fixed Huffman code work),
+    noise falls back to stored chunks without growing by more than the chunk headers, and bad
+    arguments return 1 without writing."""
+    smooth = np.zeros((64, 256, 4), np.float32)
+    smooth[..., :3] = np.linspace(0, 1, 256, dtype=np.float32)[None, :, None]
+    smooth[..., 3] = 1.0
+    p = str(tmp_path / "smooth.exr")
+    assert sp.save_exr(p, smooth, sp.EXR_FLOAT, sp.EXR_ZIP)
+    assert os.path.getsize(p) < smooth.nbytes // 8
+    assert np.array_equal(sp.load_exr(p), smooth)
+    noise = np.random.RandomState(1).rand(32, 64, 4).astype(np.float32).view(np.uint32)
+    noise = (noise ^ np.random.RandomState(2).randint(0, 2 ** 23, noise.shape).astype(np.uint32)).view(np.float32)
+    p = str(tmp_path / "noise.exr")
+    assert sp.save_exr(p, noise, sp.EXR_FLOAT, sp.EXR_ZIPS)
+    assert os.path.getsize(p) <= noise.nbytes + 32 * 16 + 512
+    assert np.array_equal(sp.load_exr(p).view(np.uint32), noise.view(np.uint32))
+    assert not sp.save_exr(str(tmp_path / "no" / "dir.exr"), smooth)
+    assert not sp.save_exr(p, smooth, 0, sp.EXR_ZIP)
+    assert not sp.save_exr(p, smooth, sp.EXR_FLOAT, 4)          # PIZ: not written
+
+
+def test_save_ppm(tmp_path):
+    rgba8 = (np.arange(7 * 5, dtype=np.uint32).reshape(5, 7) * 0x01030507 + 0xFF000000) & 0xFFFFFFFF
+    p = str(tmp_path / "out.ppm")
+    sp.write_ppm(p, rgba8)
+    data = open(p, "rb").read()
+    assert data.startswith(b"P6\n7 5\n255\n")
+    body = np.frombuffer(data[len(b"P6\n7 5\n255\n"):], np.uint8).reshape(5, 7, 3)
+    for ch in range(3):
+        assert np.array_equal(body[..., ch], (rgba8 >> (8 * ch)) & 0xFF)
+    with pytest.raises(OSError):
+        sp.write_ppm(str(tmp_path / "no" / "dir.ppm"), rgba8)

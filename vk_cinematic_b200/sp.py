@@ -259,6 +259,8 @@ _SIGNATURES = {
     "sp_b200_LoadObj": (C.c_int, [C.c_char_p, _P(sp_b200_MeshData)]),
     "sp_b200_FreeMeshData": (None, [_P(sp_b200_MeshData)]),
     "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
+    "sp_b200_SaveExrImage": (C.c_int, [C.c_void_p, C.c_char_p, u32, u32]),
+    "sp_b200_SavePpm": (C.c_int, [C.c_void_p, u32, u32, C.c_char_p]),
     "sp_b200_CreateCubeMap": (C.c_int, [C.c_void_p, u32, u32, C.c_void_p, C.c_void_p]),
     "sp_b200_CreateIrradianceCubeMap": (C.c_int, [C.c_void_p, u32, u32, u32, u32, f32, C.c_void_p,
                                                   C.c_void_p]),
@@ -403,13 +405,21 @@ def create_irradiance_cube_map(env, face_w, face_h, spp=32, sampling=IRRADIANCE_
 
 
 def write_ppm(path, rgba8):
-    """RGBA8 (H, W) uint32 image -> binary PPM (the reference has no image writer; this is the
-    harness's way to look at a frame)."""
-    h, w = rgba8.shape
-    rgb = np.stack([(rgba8 >> s) & 0xFF for s in (0, 8, 16)], axis=-1).astype(np.uint8)
-    with open(path, "wb") as f:
-        f.write(b"P6\n%d %d\n255\n" % (w, h))
-        f.write(rgb.tobytes())
+    """RGBA8 (H, W) uint32 image -> binary PPM through sp_b200_SavePpm."""
+    img = np.ascontiguousarray(rgba8, dtype=np.uint32)
+    h, w = img.shape
+    if lib.sp_b200_SavePpm(img.ctypes.data, w, h, os.fsencode(path)) != 0:
+        raise OSError("sp_b200_SavePpm failed: %s" % path)
+
+
+EXR_HALF, EXR_FLOAT = 1, 2
+EXR_NONE, EXR_ZIPS, EXR_ZIP = 0, 2, 3
+
+
+def save_exr(path, rgba, pixel_type=EXR_FLOAT, compression=EXR_ZIP):
+    """(H, W, 4) float32 image -> OpenEXR file through sp_b200_SaveExrImage; False on failure."""
+    img, hdr = _equirect(rgba)
+    return lib.sp_b200_SaveExrImage(C.byref(hdr), os.fsencode(path), pixel_type, compression) == 0
 
 
 def last_stats():
