@@ -202,6 +202,21 @@ WorkQueue CreateWorkQueue(MemoryArena *arena, u32 objectSize, u32 maxObjects);
 b32 WorkQueuePush(WorkQueue *queue, void *object, u32 objectSize);
 void *WorkQueuePop(WorkQueue *queue, u32 objectSize);
 
+/* The tile scheduler on top of the queue (main.cpp:246-250 sp_Task; :819-844 AddRayTracingWorkQueue;
+ * :728-759 WorkerThread + g_metricsBuffer).  `internal` in the reference, so they carry the library
+ * prefix here.  sp_b200_AddRayTracingWorkQueue: asserts the queue is empty, resets tail/head and
+ * pushes one sp_Task per tile of ctx's image plane (tile size from sp_b200_Params, default 64x64 =
+ * TILE_WIDTH/HEIGHT; at most queue->maxObjects tiles where the reference has MAX_TILES); returns the
+ * tile count.  sp_b200_DrainRayTracingWorkQueue: what the worker threads do until the queue is empty
+ * -- pop a task, RandomNumberGenerator{0xF51C0E49}, sp_PathTraceTile, append the tile's sp_Metrics --
+ * with every popped tile of a context rendered in one launch; pixels equal the reference's, metrics
+ * are appended in pop order (at most maxMetrics; metricsBuffer may be NULL); returns tasks rendered. */
+#ifndef SP_B200_USE_REFERENCE_TYPES /* main.cpp defines its own sp_Task (same layout, 24 bytes) */
+typedef struct sp_Task { sp_Context *context; Tile tile; } sp_Task;
+#endif
+u32 sp_b200_AddRayTracingWorkQueue(WorkQueue *workQueue, sp_Context *ctx);
+u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *metricsBuffer, u32 maxMetrics);
+
 /* =============================== additions (sp_b200_*) =============================== */
 
 typedef void (*sp_b200_LogFn)(const char *message);

@@ -714,3 +714,40 @@ def test_cube_map_reference_sizes(gpu_sp):
         assert np.allclose(fast_irr, ref_irr, rtol=1e-3, atol=0)
     finally:
         sp.set_params(mathMode=0)
+
+
+def test_work_queue_driver_matches_reference_scheduling(gpu_sp):
+    """the reference's own frame loop -- AddRayTracingWorkQueue pushes one
+    sp_Task per 64x64 tile, the workers pop, reseed 0xF51C0E49 and call sp_PathTraceTile
+    (main.cpp:728-759, 819-844) -- through sp_b200_AddRayTracingWorkQueue /
+    sp_b200_DrainRayTracingWorkQueue, against the checker's restatement of that pool over the
+    reference's sp_PathTraceTile (ora_render_tiles): image bit-exact (deterministic math), summed
+    counters equal, one sp_Metrics per tile, ragged right/bottom tiles, 2 spp; a queue too small for
+    the frame takes the first `capacity` tiles only (the reference would trip its Assert at
+    work_queue.h:27 instead)."""
+    sp = gpu_sp
+    wl = W.config1(200, 150, env_size=(256, 128))      # 4 x 3 tiles, the last column / row ragged
+    r = sp.Renderer().load_workload(wl)
+    chk = best(True).scene().load_workload(wl)
+    for spp in (1, 2):
+        sp.set_params(samplesPerPixel=spp, bounceCount=3, mathMode=0, tileWidth=64, tileHeight=64)
+        r.image[:] = 0
+        tiles, per_tile = r.render_work_queue()
+        cimg, cm, _ = chk.render_tiles(64, 64, spp=spp, bounces=3, threads=4)
+        assert tiles == 12 and per_tile.shape == (12, 12)
+        assert same_bits(r.image, cimg)
+        assert np.array_equal(per_tile[:, 1:5].sum(axis=0), cm[1:5])
+        # per tile: paths = pixels x spp, in ComputeTiles (row-major) order
+        assert per_tile[0, 1] == 64 * 64 * spp and per_tile[3, 1] == 8 * 64 * spp and per_tile[11, 1] == 8 * 22 * spp
+        assert np.all(per_tile[:, 0] > 0)
+    # the tile equals what one sp_PathTraceTile call gives
+    one = r.image.copy()
+    r.image[:] = 0
+    r.path_trace_tile((64, 64, 128, 128), 0xF51C0E49)
+    assert same_bits(r.image[64:128, 64:128], one[64:128, 64:128]) and not r.image[:64].any()
+    r.image[:] = 0
+    tiles, per_tile = r.render_work_queue(capacity=5)
+    assert tiles == 5 and not r.image[64:, 64:].any() and same_bits(r.image[:64], one[:64])
+    sp.set_params(samplesPerPixel=1)
+    chk.close()
+    r.close()

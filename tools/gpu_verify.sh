@@ -3,7 +3,7 @@
 # kernels, then a bench line.  Usage (under gpurun): bash tools/gpu_verify.sh <tag>
 TAG=${1:-r03}
 mkdir -p gpurun_out
-SPB_TIMING_OUT=gpurun_out/cubemap_timing_${TAG}.txt timeout 100 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${TAG}.log 2>&1
+SPB_TIMING_OUT=gpurun_out/cubemap_timing_${TAG}.txt timeout 110 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_${TAG}.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_${TAG}.log
 timeout 40 python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke_${TAG}.log

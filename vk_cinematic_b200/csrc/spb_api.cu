@@ -1642,6 +1642,147 @@ extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerat
     record_stats(c, kernelMs, totalMs);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The reference's tile scheduler (main.cpp:246-250 sp_Task, :728-759 WorkerThread + g_metricsBuffer,
+// :819-844 AddRayTracingWorkQueue) on top of the WorkQueue above.  The reference's 16 worker
+// threads each pop a task, reseed (0xF51C0E49) and render its tile; here the drain pops every task
+// and renders all tiles of one context in ONE launch of the serial-stream tile kernel (one thread
+// of control per tile, as the per-tile RNG stream demands), so the pixels are the reference's.
+
+extern "C" u32 sp_b200_AddRayTracingWorkQueue(WorkQueue *workQueue, sp_Context *ctx)
+{
+    Library &L = lib();
+    SPB_ASSERT(workQueue && ctx && ctx->camera && ctx->camera->imagePlane);
+    SPB_ASSERT(workQueue->head == workQueue->tail);      // main.cpp:821
+    SPB_ASSERT(workQueue->objectSize == sizeof(sp_Task));
+    ImagePlane *plane = ctx->camera->imagePlane;
+    u32 tileWidth, tileHeight;
+    {
+        std::lock_guard<std::recursive_mutex> lock(L.mutex);
+        tileWidth = L.params.tileWidth ? L.params.tileWidth : 64;    // TILE_WIDTH, config.h:15-16
+        tileHeight = L.params.tileHeight ? L.params.tileHeight : 64;
+    }
+    // MAX_TILES (config.h:19) bounds the reference's stack array; the queue's capacity bounds ours
+    std::vector<Tile> tiles(workQueue->maxObjects);
+    u32 tileCount = ComputeTiles(plane->width, plane->height, tileWidth, tileHeight, tiles.data(),
+                                 workQueue->maxObjects);
+    workQueue->tail = 0; // main.cpp:833
+    for (u32 i = 0; i < tileCount; ++i)
+    {
+        sp_Task task;
+        memset(&task, 0, sizeof(task));
+        task.context = ctx;
+        task.tile = tiles[i];
+        WorkQueuePush(workQueue, &task, sizeof(task));
+    }
+    workQueue->head = 0; // main.cpp:843
+    return tileCount;
+}
+
+extern "C" u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *metricsBuffer, u32 maxMetrics)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(queue && queue->objectSize == sizeof(sp_Task));
+    std::vector<sp_Task> tasks;
+    while (queue->head != queue->tail) // WorkerThread's test, main.cpp:736
+        tasks.push_back(*(sp_Task *)WorkQueuePop(queue, sizeof(sp_Task)));
+    u32 done = 0;
+    // tasks of one context are rendered together; contexts in first-seen order
+    std::vector<bool> taken(tasks.size(), false);
+    for (size_t first = 0; first < tasks.size(); ++first)
+    {
+        if (taken[first]) continue;
+        sp_Context *ctx = tasks[first].context;
+        SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+        ImagePlane *plane = ctx->camera->imagePlane;
+        std::vector<uint32_t> staging; // per tile: minX minY maxX maxY, then one rng state per tile
+        std::vector<size_t> members;
+        for (size_t i = first; i < tasks.size(); ++i)
+            if (!taken[i] && tasks[i].context == ctx)
+            {
+                taken[i] = true;
+                members.push_back(i);
+                const Tile &t = tasks[i].tile;
+                staging.push_back(t.minX);
+                staging.push_back(t.minY);
+                staging.push_back(t.maxX < plane->width ? t.maxX : plane->width);   // simd_path_tracer.cpp:188-191
+                staging.push_back(t.maxY < plane->height ? t.maxY : plane->height);
+            }
+        const u32 count = (u32)members.size();
+        staging.resize((size_t)count * 5, 0xF51C0E49u); // rng.state per task, main.cpp:738-739
+
+        DCamera cam;
+        convert_camera(ctx->camera, &cam);
+        DeviceScene *ds = find_scene(ctx->scene);
+        size_t imageBytes = (size_t)cam.width * cam.height * 16;
+        L.image.ensure(imageBytes ? imageBytes : 16);
+        SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+        const DMaterials *dm = upload_materials(ctx->materialSystem);
+        unsigned long long *ctr = reset_counters((size_t)(count - 1) * CTR_COUNT);
+        L.scratchA.ensure(staging.size() * 4);
+        SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, L.stream));
+
+        TileArgs args;
+        args.scene = ds->d;
+        args.materials = dm;
+        args.camera = cam;
+        args.tiles = (const uint32_t *)L.scratchA.ptr;
+        args.rngStates = (uint32_t *)L.scratchA.ptr + (size_t)count * 4;
+        args.count = count;
+        args.spp = L.params.samplesPerPixel;
+        args.bounces = L.params.bounceCount;
+        args.clampValue = L.params.radianceClamp;
+        args.out = (v4f *)L.image.ptr;
+        args.counters = ctr;
+        SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+        launch_tiles_serial(kernel_config(), args, L.stream);
+        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+
+        std::vector<unsigned long long> c((size_t)count * CTR_COUNT);
+        SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
+        if (plane->pixels)
+            for (u32 k = 0; k < count; ++k)
+            {
+                const uint32_t *t = staging.data() + (size_t)k * 4;
+                if (t[2] <= t[0] || t[3] <= t[1]) continue;
+                size_t pitch = (size_t)cam.width * 16;
+                size_t offset = (size_t)t[1] * cam.width + t[0];
+                SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
+                                           pitch, (size_t)(t[2] - t[0]) * 16, t[3] - t[1],
+                                           cudaMemcpyDeviceToHost, L.stream));
+            }
+        SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+        SPB_CUDA(cudaStreamSynchronize(L.stream));
+        float kernelMs = 0, totalMs = 0;
+        SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
+        SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+        int clockKHz = 0;
+        cudaDeviceGetAttribute(&clockKHz, cudaDevAttrClockRate, L.device);
+        std::vector<unsigned long long> total(CTR_COUNT, 0);
+        for (u32 k = 0; k < count; ++k)
+        {
+            const unsigned long long *ck = c.data() + (size_t)k * CTR_COUNT;
+            for (int j = 0; j < CTR_COUNT; ++j) total[j] += ck[j];
+            if (metricsBuffer && done + k < maxMetrics)
+            {
+                // one sp_Metrics per task, in pop order (the reference appends in completion order,
+                // main.cpp:746-747); CyclesElapsed = this tile's own device time in nanoseconds
+                sp_Metrics m;
+                memset(&m, 0, sizeof(m));
+                float tileMs = clockKHz > 0 ? (float)((double)ck[CTR_CLOCK_SUM] / (double)clockKHz) : kernelMs;
+                add_metrics(&m, ck, tileMs);
+                metricsBuffer[done + k] = m;
+            }
+        }
+        record_stats(total.data(), kernelMs, totalMs);
+        done += count;
+    }
+    return done;
+}
+
 extern "C" int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *triangleIndex,
                                    i32 *objectIndex, f32 *t)
 {

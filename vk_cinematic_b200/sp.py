@@ -96,6 +96,11 @@ SP_MAX_METRICS = 12
  sp_Metric_RayIntersectMesh_TestsPerformed) = range(SP_MAX_METRICS)
 
 
+class sp_Task(C.Structure):
+    """main.cpp:246-250"""
+    _fields_ = [("context", C.c_void_p), ("tile", Tile)]
+
+
 class sp_Metrics(C.Structure):
     _fields_ = [("values", u64 * SP_MAX_METRICS)]
 
@@ -235,6 +240,8 @@ _SIGNATURES = {
     "CreateWorkQueue": (WorkQueue, [_P(MemoryArena), u32, u32]),
     "WorkQueuePush": (u32, [_P(WorkQueue), C.c_void_p, u32]),
     "WorkQueuePop": (C.c_void_p, [_P(WorkQueue), u32]),
+    "sp_b200_AddRayTracingWorkQueue": (u32, [_P(WorkQueue), C.c_void_p]),
+    "sp_b200_DrainRayTracingWorkQueue": (u32, [_P(WorkQueue), C.c_void_p, u32]),
     "sp_b200_Init": (C.c_int, [C.c_int]),
     "sp_b200_Shutdown": (None, []),
     "sp_b200_SetLogCallback": (None, [C.c_void_p]),
@@ -533,6 +540,21 @@ class Renderer:
         rng = RandomNumberGenerator(rng_state)
         lib.sp_PathTraceTile(C.byref(self.ctx), Tile(*tile), C.byref(rng), C.byref(m))
         return rng.state, np.array(list(m.values), dtype=np.uint64)
+
+    def render_work_queue(self, capacity=1024):
+        """The reference's own frame loop (main.cpp:1380-1381, 1545-1557, 728-759): a WorkQueue of
+        `capacity` sp_Tasks (1024 in the app), one task per tile pushed by AddRayTracingWorkQueue,
+        drained the way the worker threads drain it.  Returns (tile count, per-tile metrics
+        (n, 12) uint64 in pop order); pixels land in the image plane."""
+        storage = np.zeros(capacity * C.sizeof(sp_Task), np.uint8)
+        arena = MemoryArena(storage.ctypes.data, 0, storage.nbytes)
+        queue = lib.CreateWorkQueue(C.byref(arena), C.sizeof(sp_Task), capacity)
+        pushed = lib.sp_b200_AddRayTracingWorkQueue(C.byref(queue), C.addressof(self.ctx))
+        metrics = (sp_Metrics * max(pushed, 1))()
+        done = lib.sp_b200_DrainRayTracingWorkQueue(C.byref(queue), C.addressof(metrics), pushed)
+        assert done == pushed and queue.head == queue.tail
+        per_tile = np.array([list(metrics[i].values) for i in range(done)], dtype=np.uint64).reshape(done, -1)
+        return pushed, per_tile
 
     def primary_hits(self, sample=0, frame=0):
         n = self.plane.width * self.plane.height
