@@ -485,7 +485,19 @@ def main():
                 traffic = float(tr["dram_bytes_per_step"]) / float(tr["launches"])
         except Exception:
             pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        # on-chip read peaks of this pool's B200 (tools/l2_peak.cu, committed result): the levels the
+        # resident BVH is actually served from
+        onchip = {}
+        try:
+            lp = json.load(open(os.path.join(ROOT, "profiles", "r03b_l2_peak.json")))
+            l2_peak = max(float(lp["l2_16MiB_GBs"]), float(lp["l2_48MiB_GBs"]))
+            onchip = {"l2_read_peak": l2_peak, "frac_of_l2_read_peak": achieved / l2_peak,
+                      "l1_read_peak": float(lp["l1_64KiB_per_cta_GBs"]),
+                      "frac_of_l1_read_peak": achieved / float(lp["l1_64KiB_per_cta_GBs"]),
+                      "source": "profiles/r03b_l2_peak.json (tools/l2_peak.cu: 16-byte read sweeps, measured)"}
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "on_chip": onchip,
                     "frac": achieved / peak, "traffic": traffic, "peak_source": which,
                     "kernel": "k_trace (BVH traversal + triangle tests)",
                     "launches_per_step": trace_launches,
