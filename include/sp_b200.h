@@ -326,7 +326,8 @@ void sp_b200_FreeMeshData(sp_b200_MeshData *mesh);
  * implemented with the vendored tinyexr): 0 on success, 1 on failure; pixels = malloc'ed RGBA f32,
  * rows top to bottom, alpha 1 when the file has none, a single channel replicated; the caller
  * free()s them.  Single-part scanline files, HALF / FLOAT channels, compression NONE / RLE / ZIPS /
- * ZIP; anything else (tiled, multi-part, PIZ ...) is refused with 1. */
+ * ZIP / PIZ, scanline or single-part tiled (level 0); anything else (multi-part, deep, PXR24, B44,
+ * DWA -- which the reference's tinyexr refuses too) is refused with 1. */
 int LoadExrImage(HdrImage *image, const char *path);
 
 /* Output stage (the step after the path, src/shaders/post_processing.frag.glsl:19-26
@@ -349,6 +350,9 @@ int sp_b200_ToneMap(const f32 *hostPixels, const void *devicePixels, u32 pixelCo
 #define SP_B200_EXR_ZIPS 2u
 #define SP_B200_EXR_ZIP 3u
 int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32 pixelType, u32 compression);
+/* the same as a single-part tiled file (one level, tileWidth x tileHeight tiles, a chunk per tile) */
+int sp_b200_SaveExrImageTiled(const HdrImage *image, const char *path, u32 pixelType, u32 compression,
+                              u32 tileWidth, u32 tileHeight);
 int sp_b200_SavePpm(const u32 *rgba8, u32 width, u32 height, const char *path);
 
 /* Environment pre-processing on the GPU (src/cubemap.cpp; the reference bakes both maps on the CPU

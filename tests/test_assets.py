@@ -242,3 +242,58 @@ def test_save_ppm(tmp_path):
         assert np.array_equal(body[..., ch], (rgba8 >> (8 * ch)) & 0xFF)
     with pytest.raises(OSError):
         sp.write_ppm(str(tmp_path / "no" / "dir.ppm"), rgba8)
+
+
+@pytest.mark.parametrize("pixel_type", ["half", "float"])
+@pytest.mark.parametrize("compression", ["none", "zips", "zip"])
+@pytest.mark.parametrize("shape,tile", [((45, 70), (32, 32)), ((45, 70), (16, 8)), ((1, 1), (64, 64)),
+                                        ((33, 129), (128, 16)), ((64, 64), (64, 64))])
+def test_tiled_exr_round_trip(tmp_path, pixel_type, compression, shape, tile):
+    """Single-part tiled files (what LoadEXR also reads, tinyexr.h:5905-5990): written by
+    sp_b200_SaveExrImageTiled, read back by the library's LoadExrImage, by the reference's loader and
+    by OpenCV; ragged right / bottom tiles, tiles larger than the image."""
+    img = _test_image(shape[0], shape[1], seed=shape[0] * 17 + tile[0])
+    want = img.astype(np.float16).astype(np.float32) if pixel_type == "half" else img
+    path = str(tmp_path / "tiled.exr")
+    assert sp.save_exr(path, img, {"half": sp.EXR_HALF, "float": sp.EXR_FLOAT}[pixel_type],
+                       {"none": sp.EXR_NONE, "zips": sp.EXR_ZIPS, "zip": sp.EXR_ZIP}[compression], tile=tile)
+    got = sp.load_exr(path)
+    assert got is not None and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    ref = _reference_exr_loader()
+    if ref is not None:
+        r = ref(path)
+        assert r is not None and np.array_equal(r.view(np.uint32), want.view(np.uint32))
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    bgra = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert bgra is not None and bgra.shape == want.shape
+    assert np.array_equal(np.ascontiguousarray(bgra[..., [2, 1, 0, 3]]).view(np.uint32), want.view(np.uint32))
+
+
+def test_tiled_exr_damaged_files(tmp_path):
+    """Truncated and corrupted tiled files return 1 or decode without a fault; a tile header that
+    points outside the image or at another level is refused."""
+    img = _test_image(40, 50, seed=5)
+    path = str(tmp_path / "t.exr")
+    assert sp.save_exr(path, img, sp.EXR_FLOAT, sp.EXR_ZIP, tile=(16, 16))
+    data = open(path, "rb").read()
+    for cut in (10, 200, len(data) // 2, len(data) - 3):
+        p = tmp_path / "cut.exr"
+        p.write_bytes(data[:cut])
+        assert sp.load_exr(str(p)) is None
+    for k in range(0, len(data), 53):
+        broken = bytearray(data)
+        broken[k] ^= 0xFF
+        p = tmp_path / "flip.exr"
+        p.write_bytes(bytes(broken))
+        sp.load_exr(str(p))
+    # first chunk's tile x -> 1000, then its level -> 1
+    first = int.from_bytes(data[data.index(b"tiledesc\0") + 9 + 4 + 9 + 1:][:8], "little")
+    for field, value in ((0, 1000), (8, 1)):
+        broken = bytearray(data)
+        broken[first + field:first + field + 4] = value.to_bytes(4, "little")
+        p = tmp_path / "hdr.exr"
+        p.write_bytes(bytes(broken))
+        assert sp.load_exr(str(p)) is None
+    assert not sp.save_exr(path, img, sp.EXR_FLOAT, sp.EXR_ZIP, tile=(0, 16))

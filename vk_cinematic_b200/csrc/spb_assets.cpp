@@ -171,8 +171,9 @@ extern "C" void sp_b200_FreeMeshData(sp_b200_MeshData *mesh)
 // single-part scanline images, channels R, G, B (+ A) or one luminance channel, HALF or FLOAT
 // pixels, compression NONE / RLE / ZIPS / ZIP / PIZ, any line order, data window != display window.
 // Output convention of LoadEXR: rows top to bottom over the data window, RGBA, alpha 1 when the
-// file has none, a single channel replicated into all four.  Tiled, multi-part, deep, UINT and
-// PXR24 / B44 / DWA files are refused (return 1), never misread.
+// file has none, a single channel replicated into all four.  Single-part tiled files are read too
+// (level 0 of any level mode, like LoadEXR).  Multi-part, deep, UINT and PXR24 / B44 / DWA files
+// are refused (return 1) -- tinyexr refuses those compressions as well -- never misread.
 namespace {
 
 struct Bytes
@@ -662,11 +663,13 @@ static int load_exr_image(HdrImage *image, const char *path)
     b.n = file.size();
     if (b.u32() != 20000630u) return 1;           // magic 76 2f 31 01
     uint32_t version = b.u32();
-    if ((version & 0xFFu) != 2 || (version & 0x1A00u)) return 1; // tiled / deep / multi-part: refused
+    if ((version & 0xFFu) != 2 || (version & 0x1800u)) return 1; // deep / multi-part: refused
+    const bool tiled = (version & 0x200u) != 0;                  // single-part tiled file
 
     struct Channel { char name[64]; uint32_t type; };
     std::vector<Channel> channels;
     int compression = -1, lineOrder = 0;
+    uint32_t tileW = 0, tileH = 0, tileMode = 0;
     int32_t dw[4] = {0, 0, -1, -1};
     for (;;)
     {
@@ -698,6 +701,12 @@ static int load_exr_image(HdrImage *image, const char *path)
         else if (!strcmp(name, "dataWindow"))
             for (int k = 0; k < 4; ++k) dw[k] = (int32_t)a.u32();
         else if (!strcmp(name, "lineOrder")) lineOrder = a.u8();
+        else if (!strcmp(name, "tiles") && !strcmp(type, "tiledesc"))
+        {
+            tileW = a.u32();
+            tileH = a.u32();
+            tileMode = a.u8();
+        }
         if (!a.ok) return 1;
     }
     (void)lineOrder; // chunks carry their own y
@@ -714,13 +723,11 @@ static int load_exr_image(HdrImage *image, const char *path)
     }
     // channel roles (LoadEXR: one channel -> grey; else R, G, B required, A optional)
     int idx[4] = {-1, -1, -1, -1};
-    size_t bytesPerPixelRow = 0;
-    std::vector<size_t> chOffset(channels.size());
+    size_t bytesPerPixel = 0;            // all channels of one pixel
     for (size_t c = 0; c < channels.size(); ++c)
     {
         if (channels[c].type != 1 && channels[c].type != 2) return 1; // UINT: refused
-        chOffset[c] = bytesPerPixelRow;
-        bytesPerPixelRow += (size_t)width * (channels[c].type == 1 ? 2 : 4);
+        bytesPerPixel += channels[c].type == 1 ? 2 : 4;
         const char *n = channels[c].name;
         if (!strcmp(n, "R")) idx[0] = (int)c;
         else if (!strcmp(n, "G")) idx[1] = (int)c;
@@ -730,13 +737,25 @@ static int load_exr_image(HdrImage *image, const char *path)
     const bool grey = channels.size() == 1;
     if (!grey && (idx[0] < 0 || idx[1] < 0 || idx[2] < 0)) return 1;
 
-    const size_t chunks = (size_t)((height + linesPerBlock - 1) / linesPerBlock);
+    // Blocks.  Scanline files: `linesPerBlock` full-width rows per chunk, chunk = {y, size, data}.
+    // Tiled files: tileW x tileH rectangles (clipped at the right / bottom edge), chunk = {tileX,
+    // tileY, levelX, levelY, size, data}; only level (0, 0) is the image (LoadEXR reads nothing
+    // else), and its tiles are the first nx * ny entries of the offset table in every level mode.
+    size_t tilesX = 0, tilesY = 0;
+    if (tiled)
+    {
+        if (tileW == 0 || tileH == 0 || tileW > 65536 || tileH > 65536) return 1;
+        if ((tileMode & 0xFu) > 2) return 1;
+        tilesX = (size_t)((width + tileW - 1) / tileW);
+        tilesY = (size_t)((height + tileH - 1) / tileH);
+    }
+    const size_t chunks = tiled ? tilesX * tilesY : (size_t)((height + linesPerBlock - 1) / linesPerBlock);
     std::vector<uint64_t> offsets(chunks);
     for (size_t i = 0; i < chunks; ++i) offsets[i] = b.u64();
     if (!b.ok) return 1;
-    float *out = (float *)malloc((size_t)width * (size_t)height * 4 * sizeof(float));
+    float *out = (float *)calloc((size_t)width * (size_t)height * 4, sizeof(float)); // free()d by the caller
     if (!out) return 1;
-    // chunks are independent (own rows of the output): decoded by up to 8 threads
+    // chunks are independent (own pixels of the output): decoded by up to 8 threads
     auto decode_chunk = [&](size_t i, std::vector<uint8_t> &raw, std::vector<uint8_t> &tmp) -> bool
     {
         bool ok = true;
@@ -745,10 +764,27 @@ static int load_exr_image(HdrImage *image, const char *path)
         c.n = file.size();
         c.at = (size_t)offsets[i];
         if (offsets[i] >= file.size()) return false;
-        int32_t y = (int32_t)c.u32();
+        // the block's rectangle inside the data window: columns [bx, bx + bw), rows [by, by + lines)
+        int64_t bx = 0, by, bw = width, lines;
+        if (tiled)
+        {
+            uint32_t tx = c.u32(), ty = c.u32(), lx = c.u32(), ly = c.u32();
+            if (!c.ok || lx != 0 || ly != 0 || tx >= tilesX || ty >= tilesY) return false;
+            bx = (int64_t)tx * tileW;
+            by = (int64_t)ty * tileH;
+            bw = std::min<int64_t>(tileW, width - bx);
+            lines = std::min<int64_t>(tileH, height - by);
+        }
+        else
+        {
+            int32_t y = (int32_t)c.u32();
+            if (!c.ok || y < dw[1] || y > dw[3]) return false;
+            by = (int64_t)y - dw[1];
+            lines = std::min<int64_t>(linesPerBlock, height - by);
+        }
         uint32_t dataSize = c.u32();
-        if (!c.ok || c.at + dataSize > c.n || y < dw[1] || y > dw[3]) return false;
-        const int64_t lines = std::min<int64_t>(linesPerBlock, (int64_t)dw[3] - y + 1);
+        if (!c.ok || c.at + dataSize > c.n) return false;
+        const size_t bytesPerPixelRow = bytesPerPixel * (size_t)bw;
         const size_t rawSize = bytesPerPixelRow * (size_t)lines;
         raw.resize(rawSize);
         const uint8_t *src = c.p + c.at;
@@ -778,6 +814,7 @@ static int load_exr_image(HdrImage *image, const char *path)
                     if (at >= dataSize) return false;
                     tmp.insert(tmp.end(), (size_t)n + 1, src[at++]);
                 }
+                if (tmp.size() > rawSize) return false;
             }
             if (!ok || tmp.size() != rawSize) return false;
             exr_unfilter(tmp, raw.data());
@@ -786,7 +823,7 @@ static int load_exr_image(HdrImage *image, const char *path)
         {
             std::vector<int> sizes;
             for (const Channel &ch : channels) sizes.push_back(ch.type == 1 ? 1 : 2);
-            if (!piz_decode(src, dataSize, raw.data(), (int)width, (int)lines, sizes)) return false;
+            if (!piz_decode(src, dataSize, raw.data(), (int)bw, (int)lines, sizes)) return false;
         }
         else
         {
@@ -796,10 +833,20 @@ static int load_exr_image(HdrImage *image, const char *path)
             if (!z.run(tmp, rawSize) || tmp.size() != rawSize) return false;
             exr_unfilter(tmp, raw.data());
         }
+        // within a row the channels follow each other (file order), bw samples each
+        std::vector<size_t> chOffset(channels.size());
+        {
+            size_t at = 0;
+            for (size_t k = 0; k < channels.size(); ++k)
+            {
+                chOffset[k] = at;
+                at += (size_t)bw * (channels[k].type == 1 ? 2 : 4);
+            }
+        }
         for (int64_t l = 0; l < lines; ++l)
         {
             const uint8_t *row = raw.data() + bytesPerPixelRow * (size_t)l;
-            float *dst = out + ((size_t)(y - dw[1] + l) * (size_t)width) * 4;
+            float *dst = out + ((size_t)(by + l) * (size_t)width + (size_t)bx) * 4;
             auto sample = [&](int ch, int64_t x) -> float {
                 const uint8_t *p = row + chOffset[(size_t)ch];
                 if (channels[(size_t)ch].type == 1)
@@ -812,7 +859,7 @@ static int load_exr_image(HdrImage *image, const char *path)
                 memcpy(&v, &u, 4);
                 return v;
             };
-            for (int64_t x = 0; x < width; ++x)
+            for (int64_t x = 0; x < bw; ++x)
             {
                 if (grey)
                 {

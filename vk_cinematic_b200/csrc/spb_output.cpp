@@ -8,7 +8,8 @@
 //
 // Written from the OpenEXR file-layout description: single-part scanline file, channels A B G R
 // (alphabetical, as the format requires), HALF or FLOAT, compression NONE, ZIPS (one line per
-// chunk) or ZIP (16 lines per chunk).  ZIP chunks: bytes split into even / odd halves, delta
+// chunk) or ZIP (16 lines per chunk); sp_b200_SaveExrImageTiled writes the single-part tiled layout
+// (one level, a chunk per tile) instead.  ZIP chunks: bytes split into even / odd halves, delta
 // predictor, then a zlib stream (RFC 1950) holding one DEFLATE block with the fixed Huffman code
 // (RFC 1951 §3.2.6) over a hash-chain LZ77 match search; a chunk that does not shrink is stored raw,
 // which every reader takes by its size.  Host code only.
@@ -194,7 +195,22 @@ struct Header
 
 } // namespace
 
+static int save_exr(const HdrImage *image, const char *path, u32 pixelType, u32 compression, u32 tileW, u32 tileH);
+
 extern "C" int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32 pixelType, u32 compression)
+{
+    return save_exr(image, path, pixelType, compression, 0, 0);
+}
+
+extern "C" int sp_b200_SaveExrImageTiled(const HdrImage *image, const char *path, u32 pixelType, u32 compression,
+                                         u32 tileWidth, u32 tileHeight)
+{
+    if (tileWidth == 0 || tileHeight == 0 || tileWidth > 65536 || tileHeight > 65536) return 1;
+    return save_exr(image, path, pixelType, compression, tileWidth, tileHeight);
+}
+
+// tileW == 0: scanline file; else single-part tiled file, one level, tiles in row-major order
+static int save_exr(const HdrImage *image, const char *path, u32 pixelType, u32 compression, u32 tileW, u32 tileH)
 {
     if (!image || !image->pixels || !path || image->width == 0 || image->height == 0) return 1;
     if (image->width > 65536 || image->height > 65536) return 1;
@@ -203,14 +219,17 @@ extern "C" int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32
     try
     {
         const uint32_t width = image->width, height = image->height;
-        const uint32_t linesPerBlock = compression == SP_B200_EXR_ZIP ? 16u : 1u;
+        const bool tiled = tileW != 0;
+        const uint32_t linesPerBlock = tiled ? tileH : (compression == SP_B200_EXR_ZIP ? 16u : 1u);
+        const uint32_t blockWidth = tiled ? tileW : width;
         const size_t sampleBytes = pixelType == SP_B200_EXR_HALF ? 2 : 4;
-        const size_t rowBytes = (size_t)width * sampleBytes * 4;
-        const uint32_t chunks = (height + linesPerBlock - 1) / linesPerBlock;
+        const uint32_t blocksX = (width + blockWidth - 1) / blockWidth;
+        const uint32_t blocksY = (height + linesPerBlock - 1) / linesPerBlock;
+        const uint32_t chunks = blocksX * blocksY;
 
         Header h;
         h.i32(20000630); // magic
-        h.i32(2);        // version 2, single-part scanline
+        h.i32(tiled ? 2 | 0x200 : 2); // version 2, single part; bit 9: tiled
         {
             Header v;
             const char *names[4] = {"A", "B", "G", "R"};
@@ -231,6 +250,14 @@ extern "C" int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32
         { Header v; v.f32(1.0f); h.attr("pixelAspectRatio", "float", v.b); }
         { Header v; v.f32(0.0f); v.f32(0.0f); h.attr("screenWindowCenter", "v2f", v.b); }
         { Header v; v.f32(1.0f); h.attr("screenWindowWidth", "float", v.b); }
+        if (tiled)
+        {
+            Header v;
+            v.i32((int32_t)tileW);
+            v.i32((int32_t)tileH);
+            v.b.push_back(0); // ONE_LEVEL, ROUND_DOWN
+            h.attr("tiles", "tiledesc", v.b);
+        }
         h.b.push_back(0);
 
         std::vector<uint8_t> file(h.b);
@@ -241,15 +268,18 @@ extern "C" int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32
         std::vector<uint8_t> raw, filtered, packed;
         for (uint32_t chunk = 0; chunk < chunks; ++chunk)
         {
-            const uint32_t y0 = chunk * linesPerBlock;
+            const uint32_t blockX = chunk % blocksX, blockY = chunk / blocksX;
+            const uint32_t x0 = blockX * blockWidth, y0 = blockY * linesPerBlock;
+            const uint32_t cols = width - x0 < blockWidth ? width - x0 : blockWidth;
             const uint32_t lines = height - y0 < linesPerBlock ? height - y0 : linesPerBlock;
+            const size_t rowBytes = (size_t)cols * sampleBytes * 4;
             raw.resize(rowBytes * lines);
             for (uint32_t l = 0; l < lines; ++l)
             {
-                const float *src = image->pixels + (size_t)(y0 + l) * width * 4;
+                const float *src = image->pixels + ((size_t)(y0 + l) * width + x0) * 4;
                 uint8_t *dst = raw.data() + rowBytes * l;
                 for (int c = 0; c < 4; ++c)
-                    for (uint32_t x = 0; x < width; ++x)
+                    for (uint32_t x = 0; x < cols; ++x)
                     {
                         float f = src[(size_t)x * 4 + kSource[c]];
                         if (pixelType == SP_B200_EXR_HALF)
@@ -282,7 +312,14 @@ extern "C" int sp_b200_SaveExrImage(const HdrImage *image, const char *path, u32
             const uint64_t at = file.size();
             for (int k = 0; k < 8; ++k) file[tableAt + (size_t)chunk * 8 + k] = (uint8_t)(at >> (8 * k));
             Header c;
-            c.i32((int32_t)y0);
+            if (tiled)
+            {
+                c.i32((int32_t)blockX);
+                c.i32((int32_t)blockY);
+                c.i32(0); // level x
+                c.i32(0); // level y
+            }
+            else c.i32((int32_t)y0);
             c.i32((int32_t)payload->size());
             file.insert(file.end(), c.b.begin(), c.b.end());
             file.insert(file.end(), payload->begin(), payload->end());

@@ -268,6 +268,7 @@ _SIGNATURES = {
     "sp_b200_ToneMap": (C.c_int, [C.c_void_p, C.c_void_p, u32, f32, C.c_void_p, C.c_void_p]),
     "sp_b200_SaveExrImage": (C.c_int, [C.c_void_p, C.c_char_p, u32, u32]),
     "sp_b200_SavePpm": (C.c_int, [C.c_void_p, u32, u32, C.c_char_p]),
+    "sp_b200_SaveExrImageTiled": (C.c_int, [C.c_void_p, C.c_char_p, u32, u32, u32, u32]),
     "sp_b200_CreateCubeMap": (C.c_int, [C.c_void_p, u32, u32, C.c_void_p, C.c_void_p]),
     "sp_b200_CreateIrradianceCubeMap": (C.c_int, [C.c_void_p, u32, u32, u32, u32, f32, C.c_void_p,
                                                   C.c_void_p]),
@@ -423,9 +424,13 @@ EXR_HALF, EXR_FLOAT = 1, 2
 EXR_NONE, EXR_ZIPS, EXR_ZIP = 0, 2, 3
 
 
-def save_exr(path, rgba, pixel_type=EXR_FLOAT, compression=EXR_ZIP):
-    """(H, W, 4) float32 image -> OpenEXR file through sp_b200_SaveExrImage; False on failure."""
+def save_exr(path, rgba, pixel_type=EXR_FLOAT, compression=EXR_ZIP, tile=None):
+    """(H, W, 4) float32 image -> OpenEXR file through sp_b200_SaveExrImage (scanline) or, with
+    tile=(w, h), sp_b200_SaveExrImageTiled; False on failure."""
     img, hdr = _equirect(rgba)
+    if tile is not None:
+        return lib.sp_b200_SaveExrImageTiled(C.byref(hdr), os.fsencode(path), pixel_type, compression,
+                                             tile[0], tile[1]) == 0
     return lib.sp_b200_SaveExrImage(C.byref(hdr), os.fsencode(path), pixel_type, compression) == 0
 
 
