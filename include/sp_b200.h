@@ -394,6 +394,23 @@ int sp_b200_RayIntersectSceneBatch(sp_Scene *scene, u32 count, const vec3 *rayOr
  * more than maxIntersections leaves are hit. */
 u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 rayDirection,
                                   u32 *leafIndices, u32 maxIntersections, b32 *errorOccurred);
+/* Which builder sp_BuildMeshMidphase uses (replaces bvh_CreateTree, bvh.cpp:51-200).  HOST_SAH
+ * (default): binned / swept SAH on the host.  DEVICE_LBVH: Morton keys, radix sort, binary radix
+ * tree and bottom-up boxes on the GPU (Karras 2012), then the same 4-wide collapse on the host; it
+ * falls back to HOST_SAH for meshes of fewer than 8 triangles, for trees deeper than the traversal
+ * stack and on CUDA errors.  Results of ray queries and renders do not depend on the builder (every
+ * triangle sits alone in a child slot with its own AABB either way); traversal cost does. */
+#define SP_B200_BUILDER_HOST_SAH 0u
+#define SP_B200_BUILDER_DEVICE_LBVH 1u
+typedef struct sp_b200_BuildInfo {
+    u32 builder;       /* builder selected for the last sp_BuildMeshMidphase */
+    u32 fellBack;      /* 1 if DEVICE_LBVH was selected but the host builder made the tree */
+    u32 triangleCount; u32 nodeCount; u32 maxDepth; u32 stackNeed;
+    f32 deviceMs;      /* CUDA-event time of the four device passes */
+    f32 wallMs;        /* whole call: snapshot, boxes, build, collapse */
+} sp_b200_BuildInfo;
+void sp_b200_SetMeshBuilder(u32 builder);
+void sp_b200_GetLastBuildInfo(sp_b200_BuildInfo *info);
 /* Host-side structure queries on the midphase tree (test hooks, cf. unit_tests/test_bvh.cpp). */
 typedef struct sp_b200_TreeInfo {
     u32 leafCount; u32 nodeCount; u32 maxDepth; b32 allLeavesReachable;

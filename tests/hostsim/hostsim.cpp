@@ -57,10 +57,47 @@ extern "C" ora_Scene *ora_create(void)
 }
 extern "C" void ora_destroy(ora_Scene *s) { delete s; }
 
+// 1: mesh trees come from the host emulation of the device LBVH builder (spb_lbvh.cuh functions in a
+// loop + bvh4_from_binary), 0: the host SAH builder
+static int g_hostsimBuilder = 0;
+extern "C" void hostsim_set_builder(int builder) { g_hostsimBuilder = builder; }
+
+// out8: nodeCount, maxDepth, stackNeed, leafCount, fellBack (1 if the LBVH path refused and the SAH
+// builder made the tree), summed node half-area x 1e3 (a cost proxy), 0, 0
+extern "C" void hostsim_build_info(const float *vertices, uint32_t vertexCount, const uint32_t *indices,
+                                   uint32_t indexCount, int builder, uint32_t *out8)
+{
+    auto accel = build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount,
+                                  builder ? &build_bvh4_lbvh_host : nullptr);
+    const Bvh4 &b = accel->bvh;
+    out8[0] = (uint32_t)b.nodes.size();
+    out8[1] = b.maxDepth;
+    out8[2] = b.stackNeed;
+    out8[3] = (uint32_t)b.slotPrim.size();
+    out8[4] = 0;
+    if (builder)
+    {
+        auto sah = build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount, nullptr);
+        out8[4] = sah->bvh.nodes.size() == b.nodes.size() && sah->bvh.maxDepth == b.maxDepth &&
+                  memcmp(sah->bvh.nodes.data(), b.nodes.data(), b.nodes.size() * sizeof(Node4)) == 0;
+    }
+    double area = 0.0;
+    for (const Node4 &n : b.nodes)
+        for (int k = 0; k < 4; ++k)
+        {
+            if (n.ref[k] == SPB_REF_EMPTY || (n.ref[k] & SPB_REF_LEAF)) continue;
+            double dx = n.bmax[0][k] - n.bmin[0][k], dy = n.bmax[1][k] - n.bmin[1][k], dz = n.bmax[2][k] - n.bmin[2][k];
+            area += dx * dy + dy * dz + dz * dx;
+        }
+    out8[5] = (uint32_t)(area * 1e3);
+    out8[6] = out8[7] = 0;
+}
+
 extern "C" int ora_add_mesh(ora_Scene *s, const float *vertices, uint32_t vertexCount,
                             const uint32_t *indices, uint32_t indexCount, uint32_t smooth)
 {
-    s->meshes.push_back(build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount));
+    s->meshes.push_back(build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount,
+                                         g_hostsimBuilder ? &build_bvh4_lbvh_host : nullptr));
     s->meshSmooth.push_back(smooth);
     return (int)s->meshes.size() - 1;
 }

@@ -135,6 +135,8 @@ class OracleLib:
         lib.ora_create_cube_map.argtypes = [_f] + [C.c_uint32] * 4 + [_f]
         lib.ora_create_irradiance_cube_map.argtypes = [_f] + [C.c_uint32] * 6 + [C.c_float, _f]
         lib.ora_create_irradiance_cube_map.restype = C.c_int
+        lib.hostsim_set_builder.argtypes = [C.c_int]
+        lib.hostsim_build_info.argtypes = [_f, C.c_uint32, _u, C.c_uint32, C.c_int, _u]
         lib.hostsim_create_cube_map.argtypes = [_f] + [C.c_uint32] * 4 + [_f]
         lib.hostsim_create_irradiance_cube_map.argtypes = [_f] + [C.c_uint32] * 6 + [C.c_float, _f]
         lib.ora_sample_nearest.argtypes = [_f, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f]
@@ -179,6 +181,19 @@ class OracleLib:
     def ray_aabb_scalar(self, mn, mx, o, d):
         return np.float32(self.lib.ora_ray_aabb_scalar(_fp(_f32(mn)), _fp(_f32(mx)), _fp(_f32(o)),
                                                        _fp(_f32(d))))
+
+    # ---- hostsim only: which builder makes the mesh trees ----
+    def set_builder(self, builder):
+        self.lib.hostsim_set_builder(int(builder))
+
+    def build_info(self, vertices, indices, builder):
+        """nodeCount, maxDepth, stackNeed, leafCount, fellBack, area proxy of the tree `builder`
+        (0 host SAH, 1 host emulation of the device LBVH) makes for this mesh."""
+        v = _f32(vertices)
+        i = np.ascontiguousarray(indices, dtype=np.uint32)
+        out = np.zeros(8, np.uint32)
+        self.lib.hostsim_build_info(_fp(v), len(v), _up(i), len(i), int(builder), _up(out))
+        return dict(zip(["nodeCount", "maxDepth", "stackNeed", "leafCount", "fellBack", "area"], (int(x) for x in out[:6])))
 
     # ---- environment pre-processing (src/cubemap.cpp) ----
     def create_cube_map(self, env, face_w, face_h):

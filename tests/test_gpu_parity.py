@@ -751,3 +751,78 @@ def test_work_queue_driver_matches_reference_scheduling(gpu_sp):
     sp.set_params(samplesPerPixel=1)
     chk.close()
     r.close()
+
+
+def test_device_lbvh_builder(gpu_sp):
+    """sp_BuildMeshMidphase with SP_B200_BUILDER_DEVICE_LBVH (k_lbvh_keys, radix
+    sort, k_lbvh_nodes, k_lbvh_fit on the GPU, collapse on the host).  (1) The tree has the shape the
+    host emulation of the same per-element functions gives (node count, depth, stack need) -- the
+    device passes computed the same binary tree; (2) results do not depend on the builder: the
+    fixtures made by the unmodified reference (image, hit ids, ray queries, serial tile stream) are
+    reproduced bit for bit on device-built trees, wavefront and per-pixel kernels, with the
+    candidate lists and the coverage pass on; (3) a 2-triangle mesh falls back to the host builder
+    and says so."""
+    sp = gpu_sp
+    hs = ora.load_hostsim()
+    sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_DEVICE_LBVH)
+    try:
+        for mesh in (W.load_mesh("bunny"), W.load_mesh("monkey"), W.icosphere_mesh(6)):
+            r = sp.Renderer()
+            r.add_mesh(mesh.vertices, mesh.indices)
+            info = sp.last_build_info()
+            want = hs.build_info(mesh.vertices, mesh.indices, 1)
+            assert info.builder == sp.BUILDER_DEVICE_LBVH and info.fellBack == 0 and info.deviceMs > 0
+            assert info.triangleCount == len(mesh.indices) // 3
+            assert (info.nodeCount, info.maxDepth, info.stackNeed) == (want["nodeCount"], want["maxDepth"], want["stackNeed"])
+            r.close()
+        g = np.load(os.path.join(GOLD, "g1_bunny_96x64.npz"))
+        for mode in (0, 1):
+            sp.set_params(samplesPerPixel=2, bounceCount=3, mathMode=0, renderMode=mode, cullByDistance=1)
+            r = sp.Renderer().load_workload(W.config1(96, 64, env_size=(512, 256)))
+            assert sp.last_build_info().fellBack == 0
+            img, m = r.render_frame(frame=1)
+            assert same_bits(img, g["image_ref_dm"]) and np.array_equal(m[1:5], g["metrics_ref_dm"])
+            ph = r.primary_hits(sample=0, frame=1)
+            assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+            r.image[:] = 0
+            state, tm = r.path_trace_tile((16, 8, 48, 40), 0xF51C0E49)
+            assert state == int(g["tile_state_ref_dm"]) and same_bits(r.image, g["tile_image_ref_dm"])
+            r.close()
+        sp.set_params(samplesPerPixel=1, renderMode=0)
+        g = np.load(os.path.join(GOLD, "g2_monkey_160x90_primary.npz"))
+        r = sp.Renderer().load_workload(W.config2(160, 90, env_size=(64, 32)))
+        ph = r.primary_hits()
+        assert np.array_equal(ph["tri"], g["tri"]) and same_bits(ph["t"], g["t"])
+        r.close()
+        g = np.load(os.path.join(GOLD, "g3_multi_80x60.npz"))
+        r = sp.Renderer().load_workload(W.multi_object_workload(width=80, height=60, spp=2, env_size=(256, 128)))
+        q = r.intersect_rays(g["origins"], g["dirs"])
+        assert same_bits(q["t"], g["rays_t"]) and np.array_equal(q["tri"], g["rays_tri"])
+        assert np.array_equal(q["obj"], g["rays_obj"]) and same_bits(q["normal"], g["rays_normal"])
+        r.close()
+        tiny = W.plane_mesh()
+        r = sp.Renderer()
+        r.add_mesh(tiny.vertices, tiny.indices)
+        assert sp.last_build_info().fellBack == 1 and sp.last_build_info().deviceMs == 0
+        r.close()
+    finally:
+        sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_HOST_SAH)
+        sp.set_params(samplesPerPixel=1, renderMode=0)
+    if os.environ.get("SPB_TIMING_OUT"):
+        sphere = W.icosphere_mesh(6)
+        lines = []
+        for builder in (sp.BUILDER_HOST_SAH, sp.BUILDER_DEVICE_LBVH):
+            sp.lib.sp_b200_SetMeshBuilder(builder)
+            for name, mesh in (("bunny 4968", W.load_mesh("bunny")), ("monkey 15744", W.load_mesh("monkey")), ("icosphere 81920", sphere)):
+                best_wall, best_dev = 1e9, 1e9
+                for _ in range(3):
+                    r = sp.Renderer()
+                    r.add_mesh(mesh.vertices, mesh.indices)
+                    info = sp.last_build_info()
+                    best_wall, best_dev = min(best_wall, info.wallMs), min(best_dev, info.deviceMs)
+                    r.close()
+                lines.append("builder %d %s triangles: sp_BuildMeshMidphase %.2f ms wall, device passes %.3f ms, %d nodes"
+                             % (builder, name, best_wall, best_dev, info.nodeCount))
+        sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_HOST_SAH)
+        with open(os.environ["SPB_TIMING_OUT"], "a") as f:
+            f.write("\n".join(lines) + "\n")

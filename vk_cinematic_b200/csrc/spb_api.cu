@@ -4,6 +4,7 @@
 // compute entry point in this library: without a usable CUDA device they abort.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -114,6 +115,7 @@ struct Library
     bool skyCulling = true;    // sp_b200_SetSkyCulling
     bool sortBounceRays = true; // sp_b200_SetRaySorting
     bool primaryCandidates = true; // sp_b200_SetPrimaryCandidates
+    uint32_t meshBuilder = 0;      // sp_b200_SetMeshBuilder
     bool skyOneLookup = true;      // sp_b200_SetSkyCulling(2 = on with, 1 = on without the one-lookup path)
     uint32_t sortBounces = 1;   // bounces whose outgoing rays are direction-sorted (A/B knob)
     // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
@@ -759,6 +761,48 @@ extern "C" sp_Mesh sp_CreateMesh(VertexPNT *vertices, u32 vertexCount, u32 *indi
     return result;
 }
 
+// sp_b200_SetMeshBuilder(SP_B200_BUILDER_DEVICE_LBVH): the tree of the next sp_BuildMeshMidphase
+// calls comes from the device builder (spb_lbvh.cu) + the host collapse; anything it cannot do
+// (fewer than 8 triangles, a tree deeper than the traversal stack, a CUDA error) falls back to the
+// host SAH builder and says so in sp_b200_BuildInfo.
+static sp_b200_BuildInfo g_lastBuild;
+static Bvh4 device_tree_builder(const float *aabbMin, const float *aabbMax, uint32_t count)
+{
+    Library &L = lib();
+    g_lastBuild.builder = SP_B200_BUILDER_DEVICE_LBVH;
+    g_lastBuild.fellBack = 1;
+    g_lastBuild.deviceMs = 0.0f;
+    Bvh4 out;
+    if (count >= 8)
+    {
+        BinaryTree tree;
+        float ms = 0.0f;
+        if (lbvh_build_binary_device(aabbMin, aabbMax, count, &tree, &ms, L.stream) &&
+            bvh4_from_binary(aabbMin, aabbMax, count, tree, &out))
+        {
+            g_lastBuild.fellBack = 0;
+            g_lastBuild.deviceMs = ms;
+            return out;
+        }
+    }
+    return build_bvh4(aabbMin, aabbMax, count);
+}
+
+extern "C" void sp_b200_SetMeshBuilder(u32 builder)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    SPB_ASSERT(builder == SP_B200_BUILDER_HOST_SAH || builder == SP_B200_BUILDER_DEVICE_LBVH);
+    L.meshBuilder = builder;
+}
+
+extern "C" void sp_b200_GetLastBuildInfo(sp_b200_BuildInfo *info)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (info) *info = g_lastBuild;
+}
+
 extern "C" void sp_BuildMeshMidphase(sp_Mesh *mesh, MemoryArena *arena, MemoryArena *tempArena)
 {
     (void)arena;
@@ -767,8 +811,18 @@ extern "C" void sp_BuildMeshMidphase(sp_Mesh *mesh, MemoryArena *arena, MemoryAr
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     SPB_ASSERT(mesh->indexCount % 3 == 0);
     for (u32 i = 0; i < mesh->indexCount; ++i) SPB_ASSERT(mesh->indices[i] < mesh->vertexCount);
+    const bool onDevice = L.meshBuilder == SP_B200_BUILDER_DEVICE_LBVH;
+    if (onDevice) ensure_init();
+    memset(&g_lastBuild, 0, sizeof(g_lastBuild));
+    auto t0 = std::chrono::steady_clock::now();
     std::shared_ptr<MeshAccel> accel =
-        build_mesh_accel(mesh->vertices, mesh->vertexCount, mesh->indices, mesh->indexCount);
+        build_mesh_accel(mesh->vertices, mesh->vertexCount, mesh->indices, mesh->indexCount,
+                         onDevice ? &device_tree_builder : nullptr);
+    g_lastBuild.wallMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    g_lastBuild.triangleCount = mesh->indexCount / 3;
+    g_lastBuild.nodeCount = (u32)accel->bvh.nodes.size();
+    g_lastBuild.stackNeed = accel->bvh.stackNeed;
+    g_lastBuild.maxDepth = accel->bvh.maxDepth;
     void *handle = accel.get();
     L.meshes[handle] = accel;
     mesh->midphaseTree.root = handle;

@@ -8,6 +8,7 @@
 #include <queue>
 
 #include "spb_core.cuh"
+#include "spb_lbvh.cuh"
 
 #ifndef SPB_SWEEP_LIMIT
 #define SPB_SWEEP_LIMIT 8192u
@@ -418,6 +419,178 @@ uint32_t collapse(const Builder &b, Bvh4 &out)
 }
 
 } // namespace
+
+void lbvh_root_bounds(const float *aabbMin, const float *aabbMax, uint32_t count, float *rootMin, float *rootMax)
+{
+    for (int a = 0; a < 3; ++a) { rootMin[a] = INFINITY; rootMax[a] = -INFINITY; }
+    for (uint32_t i = 0; i < count; ++i)
+        for (int a = 0; a < 3; ++a)
+        {
+            float lo = aabbMin[(size_t)i * 3 + a], hi = aabbMax[(size_t)i * 3 + a];
+            if (std::isfinite(lo) && lo < rootMin[a]) rootMin[a] = lo;
+            if (std::isfinite(hi) && hi > rootMax[a]) rootMax[a] = hi;
+        }
+}
+
+BinaryTree lbvh_build_binary_host(const float *aabbMin, const float *aabbMax, uint32_t count)
+{
+    BinaryTree t;
+    if (count < 2) return t;
+    float rootMin[3], rootMax[3];
+    lbvh_root_bounds(aabbMin, aabbMax, count, rootMin, rootMax);
+    std::vector<uint64_t> keys(count);
+    t.sortedPrim.resize(count);
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        keys[i] = lbvh_key(aabbMin + (size_t)i * 3, aabbMax + (size_t)i * 3, rootMin, rootMax);
+        t.sortedPrim[i] = i;
+    }
+    // a radix sort is stable: equal keys keep their input (= primitive index) order
+    std::stable_sort(t.sortedPrim.begin(), t.sortedPrim.end(),
+                     [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> sortedKeys(count);
+    for (uint32_t i = 0; i < count; ++i) sortedKeys[i] = keys[t.sortedPrim[i]];
+    const uint32_t internal = count - 1;
+    t.children.resize((size_t)internal * 2);
+    for (uint32_t i = 0; i < internal; ++i)
+        lbvh_node(sortedKeys.data(), count, i, t.children[(size_t)i * 2], t.children[(size_t)i * 2 + 1]);
+    // boxes bottom-up: the kernels do this with one atomic counter per node, here a post-order walk
+    t.boxes.assign((size_t)internal * 6, 0.0f);
+    std::vector<uint8_t> state(internal, 0);
+    std::vector<uint32_t> stack;
+    stack.push_back(0);
+    auto child_box = [&](uint32_t ref, float *mn, float *mx) {
+        if (ref & SPB_REF_LEAF)
+        {
+            uint32_t prim = t.sortedPrim[ref & ~SPB_REF_LEAF];
+            for (int a = 0; a < 3; ++a) { mn[a] = aabbMin[(size_t)prim * 3 + a]; mx[a] = aabbMax[(size_t)prim * 3 + a]; }
+        }
+        else
+            for (int a = 0; a < 3; ++a) { mn[a] = t.boxes[(size_t)ref * 6 + a]; mx[a] = t.boxes[(size_t)ref * 6 + 3 + a]; }
+    };
+    while (!stack.empty())
+    {
+        uint32_t n = stack.back();
+        if (n >= internal) { t.children.clear(); return t; } // malformed: caught by the caller
+        if (state[n] == 0)
+        {
+            state[n] = 1;
+            for (int k = 0; k < 2; ++k)
+            {
+                uint32_t ref = t.children[(size_t)n * 2 + k];
+                if (!(ref & SPB_REF_LEAF) && ref < internal && state[ref] == 0) stack.push_back(ref);
+            }
+            continue;
+        }
+        stack.pop_back();
+        if (state[n] == 2) continue;
+        state[n] = 2;
+        float lmn[3], lmx[3], rmn[3], rmx[3];
+        child_box(t.children[(size_t)n * 2], lmn, lmx);
+        child_box(t.children[(size_t)n * 2 + 1], rmn, rmx);
+        for (int a = 0; a < 3; ++a)
+        {
+            // fminf / fmaxf: a NaN operand is ignored, like the `<` / `>` tests of bounds_of
+            t.boxes[(size_t)n * 6 + a] = fminf(lmn[a], rmn[a]);
+            t.boxes[(size_t)n * 6 + 3 + a] = fmaxf(lmx[a], rmx[a]);
+        }
+    }
+    return t;
+}
+
+bool bvh4_from_binary(const float *aabbMin, const float *aabbMax, uint32_t count, const BinaryTree &tree,
+                      Bvh4 *out)
+{
+    if (count < 2) return false;
+    const uint32_t internal = count - 1;
+    if (tree.sortedPrim.size() != count || tree.children.size() != (size_t)internal * 2 ||
+        tree.boxes.size() != (size_t)internal * 6)
+        return false;
+    // sortedPrim must be a permutation
+    {
+        std::vector<uint8_t> seen(count, 0);
+        for (uint32_t p : tree.sortedPrim)
+        {
+            if (p >= count || seen[p]) return false;
+            seen[p] = 1;
+        }
+    }
+    Builder b;
+    b.aabbMin = aabbMin;
+    b.aabbMax = aabbMax;
+    b.balancedOnly = false;
+    b.order = tree.sortedPrim;
+    b.nodes.reserve((size_t)count * 2);
+    // breadth-first renumbering from internal node 0: parents before children, which is what the
+    // collapse's dynamic programme (reverse index order = post-order) relies on
+    std::vector<uint8_t> visitedInternal(internal, 0), visitedLeaf(count, 0);
+    std::vector<uint32_t> source; // b.nodes index -> tree reference
+    auto make = [&](uint32_t ref) -> bool {
+        BNode n = {};
+        if (ref & SPB_REF_LEAF)
+        {
+            uint32_t pos = ref & ~SPB_REF_LEAF;
+            if (pos >= count || visitedLeaf[pos]) return false;
+            visitedLeaf[pos] = 1;
+            uint32_t prim = tree.sortedPrim[pos];
+            n.first = pos;
+            n.count = 1;
+            // a leaf's box is the primitive's own AABB, taken from the caller's arrays: the parity
+            // contract rests on this, not on anything the device computed
+            for (int a = 0; a < 3; ++a) { n.mn[a] = aabbMin[(size_t)prim * 3 + a]; n.mx[a] = aabbMax[(size_t)prim * 3 + a]; }
+        }
+        else
+        {
+            if (ref >= internal || visitedInternal[ref]) return false;
+            visitedInternal[ref] = 1;
+            n.count = 2; // "more than one": the collapse only tests count <= 1
+            for (int a = 0; a < 3; ++a) { n.mn[a] = tree.boxes[(size_t)ref * 6 + a]; n.mx[a] = tree.boxes[(size_t)ref * 6 + 3 + a]; }
+        }
+        b.nodes.push_back(n);
+        source.push_back(ref);
+        return true;
+    };
+    if (!make(0)) return false;
+    for (size_t at = 0; at < b.nodes.size(); ++at)
+    {
+        if (b.nodes[at].count <= 1) continue;
+        uint32_t ref = source[at];
+        uint32_t li = (uint32_t)b.nodes.size();
+        if (!make(tree.children[(size_t)ref * 2]) || !make(tree.children[(size_t)ref * 2 + 1])) return false;
+        b.nodes[at].left = li;
+        b.nodes[at].right = li + 1;
+    }
+    if (b.nodes.size() != (size_t)count * 2 - 1) return false; // something was never reached
+    // every internal box must contain its children's (NaN boxes aside): a cheap check of the fit pass
+    for (const BNode &n : b.nodes)
+    {
+        if (n.count <= 1) continue;
+        for (uint32_t child : {n.left, n.right})
+            for (int a = 0; a < 3; ++a)
+            {
+                if (b.nodes[child].mn[a] < n.mn[a] || b.nodes[child].mx[a] > n.mx[a]) return false;
+            }
+    }
+    Bvh4 result;
+    uint32_t need = collapse(b, result);
+    if (need + 4 > (SPB_STACK_SIZE * 2) / 3) return false; // deeper than the traversal stack allows
+    result.stackNeed = need;
+    for (int a = 0; a < 3; ++a)
+    {
+        result.rootMin[a] = b.nodes[0].mn[a];
+        result.rootMax[a] = b.nodes[0].mx[a];
+    }
+    *out = std::move(result);
+    return true;
+}
+
+Bvh4 build_bvh4_lbvh_host(const float *aabbMin, const float *aabbMax, uint32_t count)
+{
+    Bvh4 out;
+    if (count >= 2 && bvh4_from_binary(aabbMin, aabbMax, count, lbvh_build_binary_host(aabbMin, aabbMax, count), &out))
+        return out;
+    return build_bvh4(aabbMin, aabbMax, count);
+}
 
 Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count)
 {

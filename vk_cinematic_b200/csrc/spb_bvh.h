@@ -35,4 +35,26 @@ struct Bvh4
 // aabbMin/aabbMax: count x 3 floats.  count == 0 gives an empty tree (no nodes).
 Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count);
 
+// ---- device builder (LBVH, spb_lbvh.cu) --------------------------------------------------------
+// The O(n log n) part -- Morton keys, sort, binary radix tree, bottom-up boxes -- runs on the GPU;
+// what comes back is the binary tree below.  bvh4_from_binary validates it (every primitive and
+// every internal node reached exactly once from node 0), renumbers it parent-before-child and
+// runs the same 4-wide collapse as the host builder.  It returns false -- the caller falls back
+// to build_bvh4 -- when the tree is malformed or deeper than the traversal stack allows.
+struct BinaryTree
+{
+    std::vector<uint32_t> sortedPrim; // n: primitive index at each sorted position
+    std::vector<uint32_t> children;   // 2 x (n - 1): internal node index, or SPB_REF_LEAF | sorted position
+    std::vector<float> boxes;         // 6 x (n - 1): min xyz, max xyz of each internal node
+};
+bool bvh4_from_binary(const float *aabbMin, const float *aabbMax, uint32_t count, const BinaryTree &tree,
+                      Bvh4 *out);
+// The same binary tree computed on the host with the per-element functions the kernels run
+// (spb_lbvh.cuh): the reference the device result is compared with, and what tests/hostsim uses.
+BinaryTree lbvh_build_binary_host(const float *aabbMin, const float *aabbMax, uint32_t count);
+// bounds of all finite box corners (the Morton grid); false if there is no finite extent at all
+void lbvh_root_bounds(const float *aabbMin, const float *aabbMax, uint32_t count, float *rootMin, float *rootMax);
+// host emulation end to end: LBVH binary tree -> 4-wide, falling back to build_bvh4 like the device path
+Bvh4 build_bvh4_lbvh_host(const float *aabbMin, const float *aabbMax, uint32_t count);
+
 } // namespace spb

@@ -19,7 +19,8 @@ static inline v4f mk4(float x, float y, float z, float w)
 }
 
 std::shared_ptr<MeshAccel> build_mesh_accel(const VertexPNT *vertices, uint32_t vertexCount,
-                                            const uint32_t *indices, uint32_t indexCount)
+                                            const uint32_t *indices, uint32_t indexCount,
+                                            TreeBuilderFn treeBuilder)
 {
     auto accel = std::make_shared<MeshAccel>();
     accel->vertices.assign(vertices, vertices + vertexCount);
@@ -46,7 +47,8 @@ std::shared_ptr<MeshAccel> build_mesh_accel(const VertexPNT *vertices, uint32_t 
             mx[(size_t)i * 3 + k] = hi;
         }
     }
-    accel->bvh = build_bvh4(mn.data(), mx.data(), triangleCount);
+    accel->bvh = treeBuilder ? treeBuilder(mn.data(), mx.data(), triangleCount)
+                             : build_bvh4(mn.data(), mx.data(), triangleCount);
     return accel;
 }
 

@@ -53,8 +53,11 @@ struct FlatScene
     uint32_t stackNeed = 0; // worst-case traversal stack entries: TLAS + deepest mesh tree
 };
 
+// treeBuilder: how the per-triangle boxes become a Bvh4 (default: build_bvh4, the host SAH builder)
+typedef Bvh4 (*TreeBuilderFn)(const float *aabbMin, const float *aabbMax, uint32_t count);
 std::shared_ptr<MeshAccel> build_mesh_accel(const VertexPNT *vertices, uint32_t vertexCount,
-                                            const uint32_t *indices, uint32_t indexCount);
+                                            const uint32_t *indices, uint32_t indexCount,
+                                            TreeBuilderFn treeBuilder = nullptr);
 
 // sp_AddObjectToScene's arithmetic (sp_scene.cpp:77-117) for one object.
 void compute_object_transform(const MeshAccel *mesh, const VertexPNT *vertices,

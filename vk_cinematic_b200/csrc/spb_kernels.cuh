@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "spb_bvh.h"
 #include "spb_core.cuh"
 
 namespace spb {
@@ -116,6 +117,11 @@ struct IrradianceArgs
     const uint32_t *jumpTexel, *jumpSample;
 };
 void launch_irradiance(const KernelConfig &cfg, const IrradianceArgs &args, int mode, cudaStream_t stream);
+
+// Device BVH builder (spb_lbvh.cu): Morton keys, radix sort, binary radix tree, bottom-up boxes.
+// false on a CUDA error; the tree is validated and collapsed by bvh4_from_binary (spb_bvh.h).
+bool lbvh_build_binary_device(const float *aabbMin, const float *aabbMax, uint32_t count, BinaryTree *tree,
+                              float *kernelMs, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // wavefront renderer (spb_wavefront.cu)

@@ -96,6 +96,20 @@ SP_MAX_METRICS = 12
  sp_Metric_RayIntersectMesh_TestsPerformed) = range(SP_MAX_METRICS)
 
 
+class sp_b200_BuildInfo(C.Structure):
+    _fields_ = [("builder", u32), ("fellBack", u32), ("triangleCount", u32), ("nodeCount", u32),
+                ("maxDepth", u32), ("stackNeed", u32), ("deviceMs", f32), ("wallMs", f32)]
+
+
+BUILDER_HOST_SAH, BUILDER_DEVICE_LBVH = 0, 1
+
+
+def last_build_info():
+    info = sp_b200_BuildInfo()
+    lib.sp_b200_GetLastBuildInfo(C.addressof(info))
+    return info
+
+
 class sp_Task(C.Structure):
     """main.cpp:246-250"""
     _fields_ = [("context", C.c_void_p), ("tile", Tile)]
@@ -277,6 +291,8 @@ _SIGNATURES = {
                                                  C.c_void_p, C.c_void_p, C.c_void_p, _P(sp_Metrics)]),
     "sp_b200_MeshIntersectedLeaves": (u32, [sp_Mesh, vec3, vec3, C.c_void_p, u32, _P(u32)]),
     "sp_b200_MeshTreeInfo": (None, [sp_Mesh, _P(sp_b200_TreeInfo)]),
+    "sp_b200_SetMeshBuilder": (None, [u32]),
+    "sp_b200_GetLastBuildInfo": (None, [C.c_void_p]),
     "sp_b200_SceneDeviceBytes": (u64, [_P(sp_Scene)]),
     "sp_b200_ReleaseMesh": (None, [_P(sp_Mesh)]),
     "sp_b200_ReleaseScene": (None, [_P(sp_Scene)]),
