@@ -114,3 +114,51 @@ def test_serial_stream_is_shared_across_texels(port):
     again = port.create_irradiance_cube_map(env, 2, 1, spp=8, sampling=1)
     assert same_bits(both, again)
     assert not same_bits(both[0, 0, 0], both[0, 0, 1])
+
+
+def _direction_image(width, height):
+    """An equirectangular map whose texel holds the direction it represents (the construction of
+    the reference's TestCreateCubeMap, unit_tests.cpp:283-346, at texel centres): az = 2 pi u,
+    cos(inc) = 1 - 2 v (MapToEquirectangular, math_lib.h:873-884, with the v flip of the bakers)."""
+    u = (np.arange(width) + 0.5) / width
+    v = (np.arange(height) + 0.5) / height
+    az = 2 * np.pi * u[None, :]
+    cos_inc = 1 - 2 * v[:, None]
+    sin_inc = np.sqrt(np.maximum(0, 1 - cos_inc ** 2))
+    img = np.ones((height, width, 4), np.float32)
+    img[..., 0] = sin_inc * np.cos(az)
+    img[..., 1] = cos_inc * np.ones_like(az)
+    img[..., 2] = sin_inc * np.sin(az)
+    return img
+
+
+@pytest.mark.parametrize("which", ["port", "hostsim", "ref"])
+def test_reference_cube_map_unit_tests(which, request):
+    """unit_tests.cpp:480-538 (TestMapCubeMapFaceToVector, TestMapCubeMapFaceToBasisVectors) and
+    :283-346 (TestCreateCubeMap, the test the reference keeps disabled: "our terrible sampling is
+    struggling at such a low res" -- restated at a resolution where it holds), through the baker's
+    output: on a map of directions, texel (1, 1) of a 2x2 face looks exactly along the face's forward
+    axis (fx = fy = 0), texel (1, 0) along forward + up, texel (0, 1) along forward - right."""
+    lib = request.getfixturevalue(which)
+    faces = lib.create_cube_map(_direction_image(512, 256), 2, 2)[..., :3].astype(np.float64)
+    forward = np.array([(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)], np.float64)
+    up = np.array([(0, 1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1), (0, 1, 0), (0, 1, 0)], np.float64)
+    right = np.array([(0, 0, -1), (0, 0, 1), (1, 0, 0), (1, 0, 0), (1, 0, 0), (-1, 0, 0)], np.float64)
+    for layer in range(6):
+        # bilinear blend of unit vectors 0.7 degrees apart; straight up / down the lookup lands on the
+        # centre of the first / last row (v clamps to the edge), sin(inc) = 0.088 away from the pole
+        tol = 0.1 if layer in (2, 3) else 2e-2
+        assert np.allclose(faces[layer, 1, 1], forward[layer], atol=tol), layer
+        assert np.allclose(faces[layer, 0, 1] * np.sqrt(2), forward[layer] + up[layer], atol=2 * tol), layer
+        assert np.allclose(faces[layer, 1, 0] * np.sqrt(2), forward[layer] - right[layer], atol=2 * tol), layer
+
+
+def test_sphere_coords_sample(port):
+    """unit_tests.cpp:540-558 (TestSphereCoordsSample): (phi, theta) = (0, 0) is the tangent-space
+    pole (0, 1, 0), which the uniform branch maps onto the texel's own direction -- so the first
+    term of every texel's sum is a lookup straight along the normal."""
+    assert np.allclose(port.spherical_to_cartesian((0.0, 0.0)), (0, 1, 0), atol=1.2e-7)
+    env = _direction_image(256, 128)
+    # with a step that leaves one sample (phi = theta = 0 only): irradiance = PI * L(normal) * cos0 * sin0 = 0
+    one = port.create_irradiance_cube_map(env, 2, 2, sampling=0, sample_delta=7.0)
+    assert np.all(one[..., :3] == 0) and np.all(one[..., 3] == 1)
