@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--no-candidates", action="store_true", help="development: every primary ray walks the tree")
     ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
     ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
+    ap.add_argument("--device-builder", action="store_true",
+                    help="development: mesh trees from the device LBVH builder (sp_b200_SetMeshBuilder); default: host SAH")
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -311,7 +313,10 @@ def main():
     env_pinned = torch.from_numpy(wl.textures[env_key]).pin_memory()
     wl.textures[env_key] = env_pinned.numpy()
     host_image = torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory()
+    if args.device_builder:
+        sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_DEVICE_LBVH)
     r = sp.Renderer(local).load_workload(wl, pixels=host_image.numpy())
+    sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_HOST_SAH)
     sp.set_params(samplesPerPixel=args.spp, bounceCount=args.bounces, cullByDistance=1,
                   mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=args.strip_rows,
                   renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
