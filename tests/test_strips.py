@@ -71,3 +71,52 @@ def test_gather_two_ranks_gloo():
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert p.returncode == 0 and "STRIPS_OK" in p.stdout, p.stdout + p.stderr
+
+
+def test_partition_is_minmax_optimal():
+    """With a cost array the cut is the contiguous partition whose largest strip sum is minimal
+    (checked against brute force on small cases) -- the step time is the slowest rank's."""
+    import itertools
+    rng = np.random.RandomState(11)
+    for _ in range(40):
+        rows = int(rng.randint(3, 11))
+        world = int(rng.randint(2, min(rows, 4) + 1))
+        if rows <= world:
+            continue
+        cost = rng.uniform(0.05, 5.0, rows) ** 2
+        b = strips.partition_rows(rows * 16, 16, world, cost)
+        check_cover(b, rows * 16, 16)
+        assert all(e > s for s, e in b)
+        got = max(cost[s // 16:e // 16].sum() for s, e in b)
+        brute = min(max(cost[a:c].sum() for a, c in zip((0,) + cuts, cuts + (rows,)))
+                    for cuts in itertools.combinations(range(1, rows), world - 1))
+        assert got <= brute * (1 + 1e-12)
+
+
+def test_rebalancing_converges_at_eight_ranks():
+    """The bench's loop in miniature: per-row cost units with a model error (cheap sky rows
+    overrated), scaled per rank by its measured seconds (strips.gather_row_costs), re-cut every
+    frame.  C3-like profile (expensive rows in the middle of 2160 / 16 = 135 rows), 8 ranks, fixed
+    per-rank overhead: after the bench's 8 warm-up frames the slowest rank is within 8 % of the
+    mean, and never worse than the even split it started from."""
+    H, TH, world = 2160, 16, 8
+    rows = H // TH
+    y = (np.arange(rows) + 0.5) / rows
+    obj = np.exp(-((y - 0.5) / 0.18) ** 2)
+    true_ms = 0.08 + obj
+    for overrate in (1.0, 1.3, 5.0):
+        units = true_ms * np.where(obj < 0.3, overrate, 1.0)
+        bounds = strips.partition_rows(H, TH, world)
+        history = []
+        for _ in range(8):
+            secs = [true_ms[b // TH:e // TH].sum() + 0.15 for b, e in bounds]
+            history.append(max(secs) / np.mean(secs))
+            cost = np.zeros(rows)
+            for (b, e), s in zip(bounds, secs):
+                seg = units[b // TH:e // TH]
+                cost[b // TH:e // TH] = seg * (s / seg.sum())
+            bounds = strips.partition_rows(H, TH, world, cost)
+            check_cover(bounds, H, TH)
+        secs = [true_ms[b // TH:e // TH].sum() + 0.15 for b, e in bounds]
+        final = max(secs) / np.mean(secs)
+        assert final <= 1.08 and final <= history[0], (overrate, history, final)

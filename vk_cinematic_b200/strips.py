@@ -26,6 +26,9 @@ def partition_rows(height, tile_h, world, cost=None):
     Returns a list of (row_begin, row_end) pixel rows, one per rank; trailing ranks may be empty
     when there are fewer tile rows than ranks."""
     rows = tile_row_count(height, tile_h)
+    if cost is not None and rows > world > 1:
+        cuts = _minmax_cuts(np.asarray(cost, dtype=np.float64), world)
+        return [(min(cuts[i] * tile_h, height), min(cuts[i + 1] * tile_h, height)) for i in range(world)]
     if cost is None:
         cost = np.ones(rows, dtype=np.float64)
     cost = np.asarray(cost, dtype=np.float64)
@@ -45,6 +48,34 @@ def partition_rows(height, tile_h, world, cost=None):
         cuts.append(int(min(max(k, lo), hi)))
     cuts.append(rows)
     return [(min(cuts[i] * tile_h, height), min(cuts[i + 1] * tile_h, height)) for i in range(world)]
+
+
+def _minmax_cuts(cost, world):
+    """Contiguous partition of `cost` into `world` non-empty strips with the smallest possible
+    largest strip sum (the step time is the slowest rank's): dynamic programme over (strips used,
+    rows covered), vectorised over the position of the last cut.  The prefix-closest-to-target
+    cuts used before sit up to half a row off per boundary, which at 8 strips of ~17 rows each was
+    a 10 % imbalance on a centre-heavy frame; this is the optimum for the given granularity."""
+    rows = len(cost)
+    assert rows >= world
+    cost = np.maximum(cost, 1e-9 * max(1.0, float(cost.max())))
+    prefix = np.concatenate([[0.0], np.cumsum(cost)])
+    best = np.full((world + 1, rows + 1), np.inf)
+    arg = np.zeros((world + 1, rows + 1), dtype=np.int64)
+    best[0, 0] = 0.0
+    for k in range(1, world + 1):
+        for i in range(k, rows - (world - k) + 1):
+            j = np.arange(k - 1, i)
+            v = np.maximum(best[k - 1, k - 1:i], prefix[i] - prefix[j])
+            m = int(np.argmin(v))
+            best[k, i] = v[m]
+            arg[k, i] = j[m]
+    cuts = [rows]
+    i = rows
+    for k in range(world, 0, -1):
+        i = int(arg[k, i])
+        cuts.append(i)
+    return cuts[::-1]
 
 
 def strip_cost_to_row_cost(bounds, strip_costs, height, tile_h):
