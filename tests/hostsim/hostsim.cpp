@@ -126,8 +126,22 @@ extern "C" void ora_build(ora_Scene *s)
     s->d.objInv = s->flat.objInv.data();
     s->d.objModel = s->flat.objModel.data();
     s->d.objInfo = s->flat.objInfo.data();
+    s->d.objBox = s->flat.objBox.data();
+    s->d.objTris = s->flat.objTris.data();
     s->d.tlasRoot = s->flat.tlasRoot;
     s->d.objectCount = s->flat.objectCount;
+    s->d.tlasExtent = s->flat.tlasExtent;
+    s->d.tlasNodeCount = s->flat.tlasNodeCount;
+}
+
+// what flatten_scene() made of the scene: [0] worst-case traversal stack entries (TLAS + deepest
+// mesh tree), [1] TLAS nodes, [2] deepest tree level, [3] objects
+extern "C" void hostsim_flat_info(ora_Scene *s, uint32_t *out4)
+{
+    out4[0] = s->flat.stackNeed;
+    out4[1] = s->flat.tlasNodeCount;
+    out4[2] = s->flat.maxDepth;
+    out4[3] = s->flat.objectCount;
 }
 
 extern "C" int ora_register_material(ora_Scene *s, uint32_t id, const float *albedo,
@@ -184,7 +198,7 @@ extern "C" void hostsim_set_stepped(int stepped) { g_hostsimStepped = stepped; }
 template <bool CULL>
 static Hit hs_intersect(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT)
 {
-    return g_hostsimStepped ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, nullptr)
+    return g_hostsimStepped ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, nullptr)
                             : intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
 }
 
@@ -355,6 +369,61 @@ extern "C" void ora_intersect_rays(ora_Scene *s, uint32_t n, const float *origin
 }
 
 // ---------------------------------------------------------------------------------------------
+// The conservative box test of the resumable machine (spb_core.cuh slab_wide / trav2_constants)
+// against the reference's predicate (slab_fast) on seeded adversarial pairs: flat and point boxes,
+// origins on box faces and far outside, directions with components down to 1e-28, grazing rays aimed
+// at box corners and edges.  out[0] = pairs, out[1] = pairs the exact test passes, out[2] = pairs the
+// wide test passes, out[3] = pairs the exact test passes and the wide one does NOT (must be 0).
+extern "C" void hostsim_check_wide_slab(uint32_t seed, uint32_t count, uint64_t *out4)
+{
+    uint32_t rng = seed | 1u;
+    auto uni = [&]() { return rand_unilateral(rng); };
+    auto bi = [&]() { return rand_bilateral(rng); };
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        const float extent = powf(10.0f, floorf(bi() * 4.0f));           // 1e-4 .. 1e3
+        float mn[3], mx[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            float c = bi() * extent * 0.9f, h = uni() * extent * 0.1f;
+            uint32_t kind = xorshift32(rng) & 7u;
+            if (kind == 0) h = 0.0f;                                       // flat on this axis
+            if (kind == 1) h = extent * 1.0e-7f;
+            mn[a] = c - h;
+            mx[a] = c + h;
+            if (mn[a] > mx[a]) { float t = mn[a]; mn[a] = mx[a]; mx[a] = t; }
+        }
+        f3 o, d;
+        uint32_t mode = xorshift32(rng) % 6u;
+        float far = (mode == 1) ? 1000.0f : ((mode == 2) ? 30.0f : 2.0f);
+        o = mk3(bi() * extent * far, bi() * extent * far, bi() * extent * far);
+        if (mode == 3) { o.x = (xorshift32(rng) & 1u) ? mn[0] : mx[0]; }   // on a face
+        // aim at a point of the box: a corner, an edge point or an interior point, then perturb by ulps
+        float tx = mn[0] + (mx[0] - mn[0]) * (float)(xorshift32(rng) % 3u) * 0.5f;
+        float ty = mn[1] + (mx[1] - mn[1]) * (float)(xorshift32(rng) % 3u) * 0.5f;
+        float tz = mn[2] + (mx[2] - mn[2]) * (float)(xorshift32(rng) % 3u) * 0.5f;
+        d = mk3(tx - o.x, ty - o.y, tz - o.z);
+        if (mode == 4) d = mk3(bi(), bi(), bi());
+        if (mode == 5) { d.x = bi() * 1.0e-20f; if ((xorshift32(rng) & 3u) == 0) d.y = bi() * 1.0e-28f; }
+        d = normalize3(d);
+        uint32_t nudge = xorshift32(rng) & 3u;
+        if (nudge == 1) d.x = u2f(f2u(d.x) + 1u);
+        if (nudge == 2) d.y = u2f(f2u(d.y) - 1u);
+        if (!trav2_ray_ok(o, d, extent)) continue;
+        f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float tn;
+        bool exact = slab_fast(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], o, inv, tn);
+        Trav2 st;
+        trav2_constants(o, inv, extent, st);
+        bool wide = slab_wide(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], st, u2f(0x7F800000u)) < u2f(0x7F800000u);
+        out4[0]++;
+        out4[1] += exact;
+        out4[2] += wide;
+        out4[3] += (exact && !wide);
+    }
+}
+
 // Shortcuts of the wavefront renderer (spb_core.cuh collect_candidates / resolve_from_candidates /
 // sky_one_lookup) against the plain evaluation, pixel by pixel, on the host.
 //   out[0] pixels, [1] camera rays, [2] pixels whose candidate list fell back, [3] rays whose
@@ -398,17 +467,23 @@ extern "C" void hostsim_check_shortcuts(ora_Scene *s, uint32_t spp, uint32_t fra
                     uint32_t rng = stream_seed(x + y * c.width, sample, frame);
                     f3 o, d;
                     primary_ray(c, x, y, rng, o, d);
-                    Hit walk = intersect_scene_stepped<true>(s->d, o, d, stack, stackT, nullptr);
+                    Hit walk = intersect_scene_stepped2<true>(s->d, o, d, stack, stackT, nullptr);
                     o9[1]++;
                     if (walk.t > 0.0f) allMiss = false;
                     total = add3(total, mul3(miss_radiance<0, 0>(s->dm, neg3(d), 10.0f, nullptr), weight));
                     if (list[0] == SPB_CAND_FALLBACK) continue;
-                    Trav st;
-                    TravCold cold;
-                    trav_begin(s->d, o, d, st, cold);
-                    resolve_from_candidates(s->d, list, o, d, st, cold, nullptr);
-                    if (st.cur != SPB_NODE_DONE || cold.slow) continue; // the walk takes over
-                    Hit fast = trav_result(cold);
+                    // what k_trace<PRIMARY> does with the list (second machine)
+                    Trav2 st;
+                    float record[T2_WORDS];
+                    T2View<1> view;
+                    view.base = record;
+                    v4f ray[2];
+                    ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
+                    ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
+                    if (!trav2_start(s->d, o, d, st, view)) continue;      // empty scene / exact walk
+                    if (!resolve_from_candidates2(s->d, list, o, d, st, view, nullptr)) continue; // the walk takes over
+                    if (view.u(T2_SLOW)) continue;
+                    Hit fast = trav2_finish(s->d, ray, view, true);
                     bool same = f2u(fast.t) == f2u(walk.t) && fast.object == walk.object && (fast.object < 0 || fast.slot == walk.slot);
                     if (!same)
                     {

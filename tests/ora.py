@@ -472,6 +472,8 @@ def load_hostsim():
     o.lib.hostsim_check_shortcuts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64]
     o.lib.hostsim_check_coverage.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64]
     o.lib.hostsim_set_stepped.argtypes = [C.c_int]
+    o.lib.hostsim_check_wide_slab.argtypes = [C.c_uint32, C.c_uint32, _u64]
+    o.lib.hostsim_flat_info.argtypes = [C.c_void_p, _u]
     return o
 
 

@@ -193,3 +193,52 @@ def test_hostsim_coverage_is_conservative(hostsim, case):
         floor = 0.3 if case == "bunny" else 0.02
         assert everything == 0 and floor * blocks < unmarked < blocks and rays > 0
     s.close()
+
+
+def test_hostsim_wide_slab_is_conservative(hostsim):
+    """The resumable machine opens subtrees with a padded four-FFMA box test (spb_core.cuh
+    slab_wide) and applies the reference's predicate (simd.h:198-271, here slab_fast) only to the
+    leaves that come off the stack.  That is only sound if the padded test passes WHENEVER the
+    reference's does.  4 M seeded adversarial (box, ray) pairs -- flat and point boxes, origins on
+    faces and 1000 extents away, direction components down to 1e-28, rays aimed at corners and
+    edges and nudged by one ulp -- must show no pair that the exact test passes and the wide one
+    rejects.  (Every ray here is aimed AT its box, so the pairs the exact test rejects are grazing
+    misses by a few ulps: the wide test is expected to accept a good part of those, not all.)"""
+    total = np.zeros(4, np.uint64)
+    for seed in (0x1A34C249, 0x45BA12F3, 77, 123456789):
+        out = np.zeros(4, np.uint64)
+        hostsim.lib.hostsim_check_wide_slab(seed, 1_000_000, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        total += out
+    pairs, exact, wide, violations = (int(x) for x in total)
+    assert pairs > 3_500_000 and exact > pairs // 10
+    assert violations == 0
+    assert exact <= wide < pairs - pairs // 4, (pairs, exact, wide)
+
+
+def test_nested_objects_tlas_stays_inside_its_stack_share(hostsim, port_dm):
+    """intersect_scene() gives the TLAS walk a third of the traversal stack and
+    used to drop children silently beyond it, while nothing limited the TLAS depth once
+    sp_b200_AddObjectToScene lifted the 32-object cap.  48 nested quads, each 2.25x the area of the
+    one before, are an input a surface-area split peels one at a time: the SAH tree of these boxes
+    needs 37 stack entries (12 four-wide levels) against a share of 30; rebuilt with median splits it
+    needs 14.  The builder
+    must keep the TLAS inside SPB_TLAS_STACK_LIMIT (median-split rebuild), and all three walks --
+    the exact non-resumable one, the resumable machine, the port's -- must then see every object."""
+    wl = W.nested_objects_workload(48)
+    a = port_dm.scene().load_workload(wl)
+    ia, ma = a.render_seeded(spp=1, bounces=3, frame=1)
+    pa = a.primary_hits()
+    assert len(np.unique(pa["obj"])) > 8            # rings of ever larger quads, seen through each other
+    for stepped in (0, 1):
+        hostsim.lib.hostsim_set_stepped(stepped)
+        b = hostsim.scene().load_workload(wl)
+        info = np.zeros(4, np.uint32)
+        hostsim.lib.hostsim_flat_info(b.h, info.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert info[3] == 48 and info[0] <= 30 + 2    # TLAS share (30) + the two-triangle mesh tree
+        ib, mb = b.render_seeded(spp=1, bounces=3, frame=1)
+        pb = b.primary_hits()
+        assert same_bits(ia, ib) and np.array_equal(ma[1:5], mb[1:5])
+        assert np.array_equal(pa["obj"], pb["obj"]) and same_bits(pa["t"], pb["t"])
+        b.close()
+    hostsim.lib.hostsim_set_stepped(0)
+    a.close()

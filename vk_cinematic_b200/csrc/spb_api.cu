@@ -82,7 +82,7 @@ struct DeviceBuffer
 struct DeviceScene
 {
     uint32_t magic = 0x4E435353u; // "SSCN"
-    DeviceBuffer nodes, tris, shade, objInv, objModel, objInfo, objTris;
+    DeviceBuffer nodes, tris, shade, objInv, objModel, objInfo, objTris, objBox;
     DScene d;
     uint64_t triangleCount = 0;
     uint64_t instancedTriangles = 0;
@@ -92,7 +92,7 @@ struct DeviceScene
     ~DeviceScene()
     {
         nodes.release(); tris.release(); shade.release();
-        objInv.release(); objModel.release(); objInfo.release(); objTris.release();
+        objInv.release(); objModel.release(); objInfo.release(); objTris.release(); objBox.release();
     }
 };
 
@@ -228,6 +228,7 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     std::vector<uint32_t> objTris = fs.objTris;
     if (objTris.empty()) objTris.push_back(0);
     upload(ds->objTris, objTris, L.stream);
+    upload(ds->objBox, fs.objBox, L.stream);
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     ds->d.nodes = (const v4f *)ds->nodes.ptr;
     ds->d.tris = (const v4f *)ds->tris.ptr;
@@ -236,16 +237,21 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     ds->d.objModel = (const v4f *)ds->objModel.ptr;
     ds->d.objInfo = (const v4u *)ds->objInfo.ptr;
     ds->d.objTris = (const uint32_t *)ds->objTris.ptr;
+    ds->d.objBox = (const v4f *)ds->objBox.ptr;
+    ds->d.tlasExtent = fs.tlasExtent;
+    ds->d.tlasNodeCount = fs.tlasNodeCount;
     ds->instancedTriangles = fs.instancedTriangles;
     ds->d.tlasRoot = fs.tlasRoot;
     ds->d.objectCount = fs.objectCount;
     ds->triangleCount = fs.triangleCount;
     ds->nodeCount = (uint32_t)(fs.nodes.size() / 8);
     ds->maxDepth = fs.maxDepth;
-    // the trace kernel pushes without a bound check (spb_core.cuh trav_push)
-    if (fs.stackNeed + 2 > SPB_STACK_SIZE)
+    // the trace kernel pushes without a bound check (spb_core.cuh trav_push); two more entries are
+    // its sentinels.  flatten_scene() has already kept the TLAS and every mesh tree inside their
+    // shares (SPB_TLAS_STACK_LIMIT / SPB_MESH_STACK_LIMIT, which intersect_scene() relies on).
+    if (fs.stackNeed + 4 > SPB_STACK_SIZE)
     {
-        log_message("scene needs %u traversal stack entries, the kernels provide %u", fs.stackNeed + 2, SPB_STACK_SIZE);
+        log_message("scene needs %u traversal stack entries, the kernels provide %u", fs.stackNeed + 4, SPB_STACK_SIZE);
         abort();
     }
     ds->deviceBytes = (fs.nodes.size() + fs.tris.size() + fs.shade.size() + fs.objInv.size() +

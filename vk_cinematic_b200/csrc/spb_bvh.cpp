@@ -573,7 +573,7 @@ bool bvh4_from_binary(const float *aabbMin, const float *aabbMax, uint32_t count
     }
     Bvh4 result;
     uint32_t need = collapse(b, result);
-    if (need + 4 > (SPB_STACK_SIZE * 2) / 3) return false; // deeper than the traversal stack allows
+    if (need > SPB_MESH_STACK_LIMIT) return false; // deeper than the traversal stack allows
     result.stackNeed = need;
     for (int a = 0; a < 3; ++a)
     {
@@ -592,20 +592,39 @@ Bvh4 build_bvh4_lbvh_host(const float *aabbMin, const float *aabbMax, uint32_t c
     return build_bvh4(aabbMin, aabbMax, count);
 }
 
-Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count)
+float bvh4_extent(const Bvh4 &bvh)
+{
+    float big = 0.0f;
+    if (bvh.nodes.empty()) return big;
+    const Node4 &n = bvh.nodes[0];
+    for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 4; ++k)
+        {
+            // NaN: an empty slot or a leaf with a NaN vertex (kept out of its ancestors); an infinite
+            // corner makes the extent infinite, which sends every ray of the tree to the exact walk
+            float lo = std::fabs(n.bmin[a][k]), hi = std::fabs(n.bmax[a][k]);
+            if (lo > big) big = lo;
+            if (hi > big) big = hi;
+        }
+    return big;
+}
+
+Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count, uint32_t stackLimit)
 {
     Bvh4 out;
     if (count == 0) return out;
+    if (stackLimit == 0) stackLimit = SPB_MESH_STACK_LIMIT;
     Builder b;
     b.aabbMin = aabbMin;
     b.aabbMax = aabbMax;
     b.balancedOnly = false;
     b.build(count);
     uint32_t need = collapse(b, out);
-    // The traversal stack gives each tree 2/3 of SPB_STACK_SIZE entries.  A SAH tree that could
-    // exceed it (pathological inputs only) is rebuilt with median splits, whose depth is
-    // ceil(log2 n).
-    if (need + 4 > (SPB_STACK_SIZE * 2) / 3)
+    // The traversal stack gives a mesh tree SPB_MESH_STACK_LIMIT entries and the TLAS
+    // SPB_TLAS_STACK_LIMIT (spb_core.cuh).  A SAH tree that could exceed its share (pathological
+    // inputs: e.g. thousands of objects along a line) is rebuilt with median splits, whose depth
+    // is ceil(log2 n).
+    if (need > stackLimit)
     {
         b.balancedOnly = true;
         b.build(count);

@@ -33,7 +33,12 @@ struct Bvh4
 };
 
 // aabbMin/aabbMax: count x 3 floats.  count == 0 gives an empty tree (no nodes).
-Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count);
+// stackLimit: the traversal stack entries this tree may need (0: the share of a mesh tree,
+// SPB_MESH_STACK_LIMIT); a SAH tree that would need more is rebuilt with median splits.
+Bvh4 build_bvh4(const float *aabbMin, const float *aabbMax, uint32_t count, uint32_t stackLimit = 0);
+// Largest |coordinate| of the finite corners of a tree's child boxes (every box of the tree lies
+// inside its root's child boxes); 0 for an empty tree.
+float bvh4_extent(const Bvh4 &bvh);
 
 // ---- device builder (LBVH, spb_lbvh.cu) --------------------------------------------------------
 // The O(n log n) part -- Morton keys, sort, binary radix tree, bottom-up boxes -- runs on the GPU;

@@ -109,7 +109,7 @@ static uint32_t append_tree(FlatScene &fs, const Bvh4 &bvh, uint32_t leafBase)
 FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
 {
     FlatScene fs;
-    struct Placed { uint32_t root, shadeBase, triBase, triCount; };
+    struct Placed { uint32_t root, shadeBase, triBase, triCount; float extent; };
     std::map<const MeshAccel *, Placed> placed;
     uint32_t meshStackNeed = 0;
 
@@ -146,6 +146,8 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
             fs.shade.push_back(mk4(v1.textureCoord.y, v2.textureCoord.x, v2.textureCoord.y, 0.0f));
         }
         p.root = append_tree(fs, mesh->bvh, triBase);
+        p.extent = bvh4_extent(mesh->bvh);
+        SPB_CAPTURE_ASSERT(mesh->bvh.stackNeed <= SPB_MESH_STACK_LIMIT);
         if (mesh->bvh.stackNeed > meshStackNeed) meshStackNeed = mesh->bvh.stackNeed;
         fs.triangleCount += mesh->triangleCount;
         placed[mesh] = p;
@@ -190,17 +192,26 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
         {
             mn[(size_t)i * 3 + k] = ob.aabbMin[k];
             mx[(size_t)i * 3 + k] = ob.aabbMax[k];
+            float lo = std::fabs(ob.aabbMin[k]), hi = std::fabs(ob.aabbMax[k]);
+            if (lo > fs.tlasExtent) fs.tlasExtent = lo; // (NaN compares false; inf: every ray takes the exact walk)
+            if (hi > fs.tlasExtent) fs.tlasExtent = hi;
         }
+        fs.objBox.push_back(mk4(ob.aabbMin[0], ob.aabbMin[1], ob.aabbMin[2], ob.mesh ? placed[ob.mesh.get()].extent : 0.0f));
+        fs.objBox.push_back(mk4(ob.aabbMax[0], ob.aabbMax[1], ob.aabbMax[2], 0.0f));
     }
     if (count > 0)
     {
-        Bvh4 tlas = build_bvh4(mn.data(), mx.data(), count);
+        // (a TLAS deeper than its share of the stack -- thousands of objects in a row -- comes back
+        // rebuilt with median splits)
+        Bvh4 tlas = build_bvh4(mn.data(), mx.data(), count, SPB_TLAS_STACK_LIMIT);
+        SPB_CAPTURE_ASSERT(tlas.stackNeed <= SPB_TLAS_STACK_LIMIT);
         // leaf slots of the TLAS refer to object indices
         for (Node4 &n : tlas.nodes)
             for (int k = 0; k < 4; ++k)
                 if (n.ref[k] != SPB_REF_EMPTY && (n.ref[k] & SPB_REF_LEAF))
                     n.ref[k] = SPB_REF_LEAF | tlas.slotPrim[n.ref[k] & ~SPB_REF_LEAF];
         fs.tlasRoot = append_tree(fs, tlas, 0);
+        fs.tlasNodeCount = (uint32_t)tlas.nodes.size();
         fs.stackNeed = tlas.stackNeed + meshStackNeed;
     }
     // never hand the device a null array
@@ -209,6 +220,7 @@ FlatScene flatten_scene(const std::vector<ObjectInstance> &objects)
     if (fs.shade.empty()) fs.shade.resize(4, mk4(0, 0, 0, 0));
     if (fs.objInv.empty()) { fs.objInv.resize(4, mk4(0, 0, 0, 0)); fs.objModel.resize(4, mk4(0, 0, 0, 0)); }
     if (fs.objInfo.empty()) { v4u z; z.x = SPB_REF_EMPTY; z.y = z.z = z.w = 0; fs.objInfo.push_back(z); }
+    if (fs.objBox.empty()) fs.objBox.resize(2, mk4(0, 0, 0, 0));
     return fs;
 }
 

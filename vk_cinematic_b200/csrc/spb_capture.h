@@ -45,6 +45,10 @@ struct FlatScene
     // per object: first triangle slot of its mesh, then objectCount + 1 prefix sums of the
     // objects' triangle counts (DScene::objTris)
     std::vector<uint32_t> objTris;
+    // per object: (world AABB min, extent of its mesh tree) (world AABB max, -)   (DScene::objBox)
+    std::vector<v4f> objBox;
+    float tlasExtent = 0.0f;     // largest |coordinate| of the object boxes
+    uint32_t tlasNodeCount = 0;
     uint64_t instancedTriangles = 0;
     uint32_t tlasRoot = SPB_REF_EMPTY;
     uint32_t objectCount = 0;

@@ -101,6 +101,12 @@ SPB_HD float u2f(uint32_t u)
 #define SPB_REF_EMPTY 0xFFFFFFFFu
 #define SPB_REF_LEAF 0x80000000u
 #define SPB_STACK_SIZE 96
+// Shares of the traversal stack: intersect_scene() gives the TLAS walk the first third and the
+// mesh walk the rest; the resumable machine uses one stack for both plus two sentinel entries.
+// build_bvh4() keeps every tree inside its share (median-split rebuild), flatten_scene() and
+// upload_scene() check it.
+#define SPB_TLAS_STACK_LIMIT (SPB_STACK_SIZE / 3 - 2)
+#define SPB_MESH_STACK_LIMIT ((SPB_STACK_SIZE * 2) / 3 - 4)
 #define SPB_MAX_BOUNCES 8
 #define SPB_MAX_MATERIALS 32
 #define SPB_MAX_IMAGES 16
@@ -246,8 +252,14 @@ struct DScene
     const v4u *objInfo;    // x = mesh root node (or EMPTY), y = shade base, z = smooth flag, w = material
     const uint32_t *objTris; // per object: first triangle slot of its mesh; then objectCount + 1 prefix
                              // sums of the objects' triangle counts (coverage pass)
+    const v4f *objBox;     // 2 per object: (world AABB min, largest |coordinate| of its mesh tree's boxes)
+                           // (world AABB max, -): the box the TLAS leaf carries (sp_scene.cpp:98-116), kept
+                           // apart so that a traversal that reaches the object through a CONSERVATIVE
+                           // inner test can still apply the reference's exact test to the object's own box
     uint32_t tlasRoot;     // node index or SPB_REF_EMPTY
     uint32_t objectCount;
+    float tlasExtent;      // largest |coordinate| of the TLAS boxes (world space)
+    uint32_t tlasNodeCount; // TLAS nodes are [tlasRoot, tlasRoot + tlasNodeCount), breadth-first
 };
 
 struct Counters
@@ -649,6 +661,7 @@ struct TravCold
 
 SPB_HD bool trav_is_node(const Trav &st) { return (st.cur & SPB_REF_LEAF) == 0; } // DONE / EXIT have the bit set
 SPB_HD bool trav_is_walking(const Trav &st) { return st.cur < SPB_NODE_EXIT; }
+SPB_HD bool trav_is_walking_ref(uint32_t cur) { return cur < SPB_NODE_EXIT; }
 
 SPB_HD void trav_begin(const DScene &S, f3 o, f3 d, Trav &st, TravCold &c)
 {
@@ -932,6 +945,439 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
     }
     if (cold.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
     Hit h = trav_result(cold);
+    if (h.object >= 0) hit_barycentrics(S, o, d, h);
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// Resumable traversal, second form (round 2; what k_trace runs).  Same query, same result set as
+// intersect_scene() -- the minimum over {triangles whose OWN box passes the reference's slab
+// predicate, Moller-Trumbore accepts, t > 0} over {objects whose OWN world box passes it} -- but
+// the reference's predicate is evaluated only where the result depends on it:
+//
+//   * inner boxes (and the first look at a leaf's box, inside its parent's node step) get a
+//     CONSERVATIVE test that costs half the instructions and none of the min/max pairs: per axis
+//         tnear = bmin * p + bmax * q + cn,   tfar = bmin * q + bmax * p + cf      (four FFMA)
+//     with (p, q) = (1/d, 0) or (0, 1/d) by the sign of d -- the multiply by zero selects the near
+//     and the far plane without a compare -- and cn / cf = -(o -+ delta) / d, the box grown by
+//     delta = 2^-21 (|o|_1 + extent of the tree) on every side.  Both forms round (b - o) / d a few
+//     ulps of (|b| + |o|) / |d| away from its value (the reference: sub, mul; this one: mul, fma);
+//     delta is eight times the sum of the two bounds, so the padded interval of every axis
+//     contains the reference's and whatever passes the reference's test passes this one.
+//   * a leaf that comes off the stack is tested AGAIN, exactly: a triangle's own box is rebuilt
+//     from its three vertices (min / max are exact, so these are the builder's bits up to the sign
+//     of a zero, which no comparison of the slab test can see) and an object's own world box is
+//     read from DScene::objBox; slab_fast() on it is the reference's test (all reciprocals finite).
+//     Only then Moller-Trumbore / the object entry runs.
+//
+// The set of leaves that reach Moller-Trumbore is therefore exactly the reference's; the
+// conservative test only decides which subtrees are opened on the way.  Rays with a reciprocal
+// direction beyond 1e30 (|d| < 1e-30 on some axis, where b * (1/d) could overflow) or coordinates
+// beyond 1e8 take the exact non-resumable walk, like rays with a non-finite reciprocal before.
+//
+// State.  Registers ("hot", Trav2): the twelve test constants, the cull distance, the current
+// entry and the stack pointer.  Everything a NODE step does not touch lives in a per-lane record
+// reached through a strided view (shared memory in the kernel, a plain array on the host): the
+// object-space ray and its reciprocal for the exact leaf tests, the closest hit inside the object,
+// the closest hit overall, and the world-space constants parked while inside an object.  The
+// stack carries sentinel entries instead of a base pointer: {DONE} at the bottom, {EXIT} under
+// the entries of an object.
+struct Trav2
+{
+    f3 p, q, cn, cf;
+    float tcull;
+    uint32_t cur;
+    int sp;
+};
+
+enum
+{
+    T2_OX = 0, T2_OY, T2_OZ, T2_DX, T2_DY, T2_DZ, T2_IX, T2_IY, T2_IZ, // ray of the current space, reciprocal
+    T2_LT, T2_LSLOT,                                                   // closest hit inside the object
+    T2_WORLDCULL, T2_OBJECT, T2_BT, T2_BSLOT, T2_BOBJECT, T2_SLOW,     // TravCold's fields (object = NONE in the TLAS)
+    T2_WP, T2_WQ = T2_WP + 3, T2_WCN = T2_WQ + 3, T2_WCF = T2_WCN + 3, // parked world-space constants
+    T2_WORDS = T2_WCF + 3
+};
+#define SPB_T2_NO_OBJECT 0xFFFFFFFFu
+
+// one lane's record: word k at base[k * STRIDE]
+template <int STRIDE>
+struct T2View
+{
+    float *base;
+    SPB_HD float &f(int k) const { return base[k * STRIDE]; }
+    SPB_HD uint32_t &u(int k) const { return reinterpret_cast<uint32_t *>(base)[k * STRIDE]; }
+    SPB_HD f3 f3at(int k) const { return mk3(base[k * STRIDE], base[(k + 1) * STRIDE], base[(k + 2) * STRIDE]); }
+    SPB_HD void set3(int k, f3 v) const { base[k * STRIDE] = v.x; base[(k + 1) * STRIDE] = v.y; base[(k + 2) * STRIDE] = v.z; }
+};
+
+SPB_HD float fma_rn(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+// |d| >= 1e-30 on every axis and every coordinate below 1e8: b * (1/d) and o * (1/d) stay finite
+SPB_HD bool trav2_ray_ok(f3 o, f3 d, float extent)
+{
+    const float tiny = 1.0e-30f;
+    const float big = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + extent;
+    return fabsf(d.x) >= tiny && fabsf(d.y) >= tiny && fabsf(d.z) >= tiny && big < 1.0e8f;
+}
+
+// test constants of the ray (o, d) against a tree whose boxes lie within +-extent
+SPB_HD void trav2_constants(f3 o, f3 inv, float extent, Trav2 &st)
+{
+    const float delta = 4.76837158203125e-07f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + extent); // 2^-21
+    const float kminx = -(o.x + delta) * inv.x, kmaxx = -(o.x - delta) * inv.x; // pairs with bmin / bmax
+    const float kminy = -(o.y + delta) * inv.y, kmaxy = -(o.y - delta) * inv.y;
+    const float kminz = -(o.z + delta) * inv.z, kmaxz = -(o.z - delta) * inv.z;
+    const bool px = inv.x >= 0.0f, py = inv.y >= 0.0f, pz = inv.z >= 0.0f;
+    st.p = mk3(px ? inv.x : 0.0f, py ? inv.y : 0.0f, pz ? inv.z : 0.0f);
+    st.q = mk3(px ? 0.0f : inv.x, py ? 0.0f : inv.y, pz ? 0.0f : inv.z);
+    st.cn = mk3(px ? kminx : kmaxx, py ? kminy : kmaxy, pz ? kminz : kmaxz);
+    st.cf = mk3(px ? kmaxx : kminx, py ? kmaxy : kminy, pz ? kmaxz : kminz);
+}
+
+// conservative slab test of one child (see above).  Returns the key the children are ordered by:
+// the entry distance if the padded box is entered before `tlimit` (the cull distance), else +inf.
+SPB_HD float slab_wide(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, const Trav2 &st,
+                       float tlimit)
+{
+    const float tnx = fma_rn(bminx, st.p.x, fma_rn(bmaxx, st.q.x, st.cn.x));
+    const float tny = fma_rn(bminy, st.p.y, fma_rn(bmaxy, st.q.y, st.cn.y));
+    const float tnz = fma_rn(bminz, st.p.z, fma_rn(bmaxz, st.q.z, st.cn.z));
+    const float tfx = fma_rn(bminx, st.q.x, fma_rn(bmaxx, st.p.x, st.cf.x));
+    const float tfy = fma_rn(bminy, st.q.y, fma_rn(bmaxy, st.p.y, st.cf.y));
+    const float tfz = fma_rn(bminz, st.q.z, fma_rn(bmaxz, st.p.z, st.cf.z));
+    // The entry distance is NOT clamped at 0 (a box around the origin gets a negative key and goes
+    // first); boxes behind the origin are rejected by tfar >= 0 instead.  An empty slot's NaN box
+    // gives NaN on every axis: fmaxf / fminf drop NaN operands, so tnear = NaN (compares false)
+    // while tfar = tlimit.
+    const float tnear = fmaxf(fmaxf(tnx, tny), tnz);
+    const float tfar = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+    return (tnear <= tfar && tfar >= 0.0f) ? tnear : u2f(0x7F800000u);
+}
+
+SPB_HD void trav2_push(Trav2 &st, TravEntry *stack, uint32_t ref, float tnear)
+{
+    TravEntry e;
+    e.ref = ref;
+    e.tnear = tnear;
+    stack[st.sp] = e;
+    st.sp++;
+}
+
+// pops until an entry passes the cull distance; the sentinels (tnear = -inf) always do
+template <bool CULL>
+SPB_HD void trav2_pop(Trav2 &st, const TravEntry *stack)
+{
+    for (;;)
+    {
+        st.sp--;
+        TravEntry e = load_entry(stack + st.sp);
+        if (CULL && !(e.tnear <= st.tcull)) continue;
+        st.cur = e.ref;
+        return;
+    }
+}
+
+// Start of a query: world ray (o, d).  Initialises the lane's record; returns false when there is
+// nothing to walk: st.cur = DONE, with T2_SLOW set if the caller must finish the ray with
+// intersect_scene().  On true the record holds the world ray and its reciprocal.
+template <int STRIDE>
+SPB_HD bool trav2_start(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STRIDE> &v)
+{
+    st.sp = 0;
+    st.tcull = u2f(0x7F800000u);
+    st.cur = SPB_NODE_DONE;
+    v.u(T2_OBJECT) = SPB_T2_NO_OBJECT;
+    v.f(T2_BT) = -1.0f;
+    v.u(T2_BSLOT) = 0;
+    v.u(T2_BOBJECT) = 0xFFFFFFFFu;
+    v.u(T2_SLOW) = 0;
+    if (S.tlasRoot == SPB_REF_EMPTY) return false;
+    if (!trav2_ray_ok(o, d, S.tlasExtent))
+    {
+        v.u(T2_SLOW) = 1;
+        return false;
+    }
+    v.set3(T2_OX, o);
+    v.set3(T2_DX, d);
+    v.set3(T2_IX, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z));
+    return true;
+}
+
+// General scenes: the walk starts at the TLAS root.
+template <int STRIDE>
+SPB_HD void trav2_begin(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STRIDE> &v, TravEntry *stack)
+{
+    if (!trav2_start(S, o, d, st, v)) return;
+    trav2_constants(o, v.f3at(T2_IX), S.tlasExtent, st);
+    trav2_push(st, stack, SPB_NODE_DONE, u2f(0xFF800000u));
+    st.cur = S.tlasRoot;
+}
+
+// NODE step: st.cur is a node index.
+template <bool CULL>
+SPB_HD void trav2_node(const DScene &S, Trav2 &st, TravEntry *stack, Counters *counters)
+{
+    const float inf = u2f(0x7F800000u);
+    const v4f *n = S.nodes + (size_t)st.cur * 8;
+    v4f minx, miny, minz, maxx, maxy, maxz, refsf, meta;
+    ld8(n + 0, minx, miny);
+    ld8(n + 2, minz, maxx);
+    ld8(n + 4, maxy, maxz);
+    ld8(n + 6, refsf, meta);
+    if (counters) counters->nodeVisits++;
+
+    const float tlimit = CULL ? st.tcull : inf;
+    float k0 = slab_wide(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st, tlimit);
+    float k1 = slab_wide(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, st, tlimit);
+    float k2 = slab_wide(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, st, tlimit);
+    float k3 = slab_wide(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, st, tlimit);
+    uint32_t r0 = f2u(refsf.x), r1 = f2u(refsf.y), r2 = f2u(refsf.z), r3 = f2u(refsf.w);
+    if (CULL)
+    {
+        sortx(k0, r0, k1, r1);
+        sortx(k2, r2, k3, r3);
+        sortx(k0, r0, k2, r2);
+        sortx(k1, r1, k3, r3);
+        sortx(k1, r1, k2, r2);
+    }
+    else
+    {
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
+        if (!(k1 < inf)) { k1 = k2; r1 = r2; k2 = inf; }
+        if (!(k2 < inf)) { k2 = k3; r2 = r3; k3 = inf; }
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
+        if (!(k1 < inf)) { k1 = k2; r1 = r2; k2 = inf; }
+        if (!(k0 < inf)) { k0 = k1; r0 = r1; k1 = inf; }
+    }
+    if (k3 < inf) trav2_push(st, stack, r3, k3);
+    if (k2 < inf) trav2_push(st, stack, r2, k2);
+    if (k1 < inf) trav2_push(st, stack, r1, k1);
+    if (k0 < inf)
+    {
+        st.cur = r0;
+        return;
+    }
+    trav2_pop<CULL>(st, stack);
+}
+
+// Object entry (sp_scene.cpp:274-276) for object `index` whose own world box passed the exact
+// test.  World ray (wo, wd) and its constants are parked; the walk continues in object space.
+// Returns false (T2_SLOW set, st.cur = DONE) when the object-space ray needs the exact walk.
+template <bool CULL, bool PARK, int STRIDE>
+SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, f3 wo, f3 wd, Trav2 &st,
+                        const T2View<STRIDE> &v, TravEntry *stack, uint32_t sentinel)
+{
+    const float inf = u2f(0x7F800000u), ninf = u2f(0xFF800000u);
+    m4 invModel = load_m4(S.objInv + (size_t)index * 4);
+    f3 lo = xform(invModel, wo, 1.0f);
+    float scaleLen;
+    f3 ld = normalize3(xform(invModel, wd, 0.0f), &scaleLen);
+    const float extent = ld4(S.objBox + (size_t)index * 2).w;
+    if (!trav2_ray_ok(lo, ld, extent))
+    {
+        v.u(T2_SLOW) = 1;
+        st.cur = SPB_NODE_DONE;
+        return false;
+    }
+    if (PARK)
+    {
+        v.f(T2_WORLDCULL) = st.tcull;
+        v.set3(T2_WP, st.p);
+        v.set3(T2_WQ, st.q);
+        v.set3(T2_WCN, st.cn);
+        v.set3(T2_WCF, st.cf);
+    }
+    st.tcull = inf;
+    const float bT = v.f(T2_BT);
+    if (CULL && bT >= 0.0f) st.tcull = (bT + cull_pad(wo, bT)) * scaleLen * SPB_CULL_SLACK;
+    const f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+    v.set3(T2_OX, lo);
+    v.set3(T2_DX, ld);
+    v.set3(T2_IX, inv);
+    v.f(T2_LT) = -1.0f;
+    v.u(T2_LSLOT) = 0;
+    v.u(T2_OBJECT) = index;
+    trav2_constants(lo, inv, extent, st);
+    trav2_push(st, stack, sentinel, ninf);
+    st.cur = meshRoot;
+    return true;
+}
+
+// The object's closest hit carried back to world space (sp_scene.cpp:296-322); updates the closest
+// hit overall and returns the world cull distance that follows from it.
+template <int STRIDE>
+SPB_HD float trav2_leave(const DScene &S, f3 wo, f3 wd, float worldCull, const T2View<STRIDE> &v)
+{
+    const float lT = v.f(T2_LT);
+    if (lT >= 0.0f)
+    {
+        const uint32_t object = v.u(T2_OBJECT);
+        m4 model = load_m4(S.objModel + (size_t)object * 4);
+        f3 localHit = add3(v.f3at(T2_OX), mul3(v.f3at(T2_DX), lT));
+        f3 worldHit = xform(model, localHit, 1.0f);
+        float t = dot3(sub3(worldHit, wo), wd);
+        float bT = v.f(T2_BT);
+        if (t < bT || bT < 0.0f)
+        {
+            v.f(T2_BT) = t;
+            v.u(T2_BOBJECT) = object;
+            v.u(T2_BSLOT) = v.u(T2_LSLOT);
+            float c2 = (t + cull_pad(wo, t)) * SPB_CULL_SLACK;
+            if (t > 0.0f && c2 < worldCull) worldCull = c2;
+        }
+    }
+    return worldCull;
+}
+
+// EXIT step (st.cur == SPB_NODE_EXIT): leave the object and go on with the TLAS entries below.
+template <bool CULL, int STRIDE>
+SPB_HD void trav2_exit(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, const v4f *ray, const TravEntry *stack)
+{
+    f3 wo, wd;
+    trav_world_ray(ray, wo, wd);
+    st.tcull = trav2_leave(S, wo, wd, v.f(T2_WORLDCULL), v);
+    st.p = v.f3at(T2_WP);
+    st.q = v.f3at(T2_WQ);
+    st.cn = v.f3at(T2_WCN);
+    st.cf = v.f3at(T2_WCF);
+    v.u(T2_OBJECT) = SPB_T2_NO_OBJECT;
+    // the world ray's reciprocal is p + q (one of them is zero); the exact test of the next object
+    // box needs it again
+    v.set3(T2_OX, wo);
+    v.set3(T2_DX, wd);
+    v.set3(T2_IX, mk3(st.p.x + st.q.x, st.p.y + st.q.y, st.p.z + st.q.z));
+    trav2_pop<CULL>(st, stack);
+}
+
+// LEAF step: st.cur is SPB_REF_LEAF | slot -- a triangle (inside an object) or an object (TLAS)
+// whose box passed the conservative test of its parent's node step.
+template <bool CULL, int STRIDE>
+SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, const v4f *ray, TravEntry *stack,
+                       Counters *counters)
+{
+    (void)ray;
+    const uint32_t index = st.cur & ~SPB_REF_LEAF;
+    const f3 o = v.f3at(T2_OX), inv = v.f3at(T2_IX);
+    if (v.u(T2_OBJECT) != SPB_T2_NO_OBJECT)
+    {
+        const v4f *tp = S.tris + (size_t)index * 3;
+        v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
+        // the triangle's own box (sp_scene.cpp:35-50) and the reference's test of it (bvh.cpp:236-255)
+        float tn;
+        const bool own = slab_fast(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)),
+                                   fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)),
+                                   o, inv, tn);
+        if (own && (!CULL || tn <= st.tcull))
+        {
+            if (counters) counters->triangleTests++;
+            const f3 d = v.f3at(T2_DX);
+            float t, uu, vv;
+            if (ray_triangle_mt(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, uu, vv))
+            {
+                const float lT = v.f(T2_LT);
+                if (t > 0.0f && (t < lT || lT < 0.0f))
+                {
+                    v.f(T2_LT) = t;
+                    v.u(T2_LSLOT) = index;
+                    float c2 = t * SPB_CULL_SLACK;
+                    if (c2 < st.tcull) st.tcull = c2;
+                }
+            }
+        }
+    }
+    else
+    {
+        // the object's own world box, exactly (the TLAS leaf's box: sp_scene.cpp:98-116, bvh.cpp:236-255)
+        v4f bmin = ld4(S.objBox + (size_t)index * 2), bmax = ld4(S.objBox + (size_t)index * 2 + 1);
+        float tn;
+        const bool own = slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, inv, tn);
+        if (own && (!CULL || tn <= st.tcull))
+        {
+            v4u info = ld4u(S.objInfo + index);
+            if (counters) counters->objectTests++;
+            if (info.x != SPB_REF_EMPTY)
+            {
+                // (in the TLAS the record holds the world ray)
+                trav2_enter<CULL, true>(S, index, info.x, o, v.f3at(T2_DX), st, v, stack, SPB_NODE_EXIT);
+                return;
+            }
+        }
+    }
+    trav2_pop<CULL>(st, stack);
+}
+
+// Single-object scenes (C1-C4): what the walk would do before it reaches the mesh tree -- the TLAS
+// root's one child is the object: its own box, exactly; then the object entry -- done at once when
+// the ray starts (every lane of a refilling warp is busy here, and two rounds of the step loop are
+// saved).  Leaves st.cur = the mesh root, or DONE.  The sentinel under the object's entries is DONE
+// rather than EXIT: the walk ends inside the object, and trav2_finish() carries the hit out.
+template <bool CULL, int STRIDE>
+SPB_HD void trav2_begin_single(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STRIDE> &v, TravEntry *stack,
+                               Counters *counters)
+{
+    if (!trav2_start(S, o, d, st, v)) return;
+    if (counters) counters->nodeVisits++;
+    v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
+    float tn;
+    if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, v.f3at(T2_IX), tn)) return;
+    v4u info = ld4u(S.objInfo);
+    if (counters) counters->objectTests++;
+    if (info.x == SPB_REF_EMPTY) return;
+    trav2_enter<CULL, false>(S, 0, info.x, o, d, st, v, stack, SPB_NODE_DONE);
+}
+
+// End of a query: the closest hit.  `single`: the walk ended inside the one object.
+template <int STRIDE>
+SPB_HD Hit trav2_finish(const DScene &S, const v4f *ray, const T2View<STRIDE> &v, bool single)
+{
+    if (single && v.u(T2_OBJECT) != SPB_T2_NO_OBJECT && v.f(T2_LT) >= 0.0f)
+    {
+        f3 wo, wd;
+        trav_world_ray(ray, wo, wd);
+        trav2_leave(S, wo, wd, 0.0f, v);
+    }
+    Hit h;
+    h.t = v.f(T2_BT);
+    h.object = (int32_t)v.u(T2_BOBJECT);
+    h.slot = v.u(T2_BSLOT);
+    h.u = h.v = 0.0f;
+    h.localOrigin = h.localDirection = mk3(0, 0, 0);
+    h.localT = -1.0f;
+    return h;
+}
+
+// The second machine run to completion for one ray (what each lane of k_trace does); hostsim
+// checks it against intersect_scene() and the oracle.
+template <bool CULL>
+SPB_HD Hit intersect_scene_stepped2(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT, Counters *counters)
+{
+    Trav2 st;
+    float record[T2_WORDS];
+    T2View<1> v;
+    v.base = record;
+    TravEntry entries[SPB_STACK_SIZE];
+    v4f ray[2];
+    ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
+    ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
+    const bool single = S.objectCount == 1;
+    if (single) trav2_begin_single<CULL>(S, o, d, st, v, entries, counters);
+    else trav2_begin(S, o, d, st, v, entries);
+    while (st.cur != SPB_NODE_DONE)
+    {
+        if (st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(S, st, v, ray, entries);
+        else if ((st.cur & SPB_REF_LEAF) == 0) trav2_node<CULL>(S, st, entries, counters);
+        else trav2_leaf<CULL>(S, st, v, ray, entries, counters);
+    }
+    if (v.u(T2_SLOW)) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+    Hit h = trav2_finish(S, ray, v, single);
     if (h.object >= 0) hit_barycentrics(S, o, d, h);
     return h;
 }
@@ -1355,34 +1801,33 @@ SPB_HD void collect_candidates(const DScene &S, const DCamera &cam, uint32_t x, 
 // walk's functions, so the same bits; only the winner among exactly equal t may differ, as with
 // any visit order.  Leaves st.cur = DONE with the result in `cold`, or everything untouched when
 // the pixel falls back to the walk.
-SPB_HD void resolve_from_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d, Trav &st, TravCold &cold,
-                                    Counters *counters)
+// Returns 0: resolved (bT >= 0: closest hit, world distance bT in triangle slot bSlot of object 0;
+// bT < 0: no hit), 1: the pixel falls back to the walk (nothing counted), 2: the object-space ray
+// needs the exact walk.  `o, d, inv`: world ray and its (finite) reciprocal.
+SPB_HD int resolve_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d, f3 winv, Counters *counters, float &bT,
+                              uint32_t &bSlot)
 {
-    if (cold.slow || st.cur == SPB_NODE_DONE) return; // non-finite reciprocal direction / empty scene
+    bT = -1.0f;
+    bSlot = 0;
     const uint32_t count = list[0];
-    if (count == SPB_CAND_FALLBACK) return;
-    // the TLAS root's test of the object's world box (what trav_node would run; the other three
+    if (count == SPB_CAND_FALLBACK) return 1;
+    // the TLAS root's test of the object's world box (what the walk would run; the other three
     // slots of the root are empty in a single-object scene)
     {
         const v4f *n = S.nodes + (size_t)S.tlasRoot * 8;
         v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
         float tn;
         if (counters) counters->nodeVisits++;
-        st.cur = SPB_NODE_DONE;
-        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, st.o, st.inv, tn)) return; // miss: cold.bT = -1
+        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, winv, tn)) return 0; // miss
     }
-    // object entry (trav_leaf, sp_scene.cpp:274-276)
+    // object entry (sp_scene.cpp:274-276)
     v4u info = ld4u(S.objInfo);
     if (counters) counters->objectTests++;
-    if (info.x == SPB_REF_EMPTY) return;
+    if (info.x == SPB_REF_EMPTY) return 0;
     m4 invModel = load_m4(S.objInv);
     f3 lo = xform(invModel, o, 1.0f);
     f3 ld = normalize3(xform(invModel, d, 0.0f));
-    if (any_nonfinite_inv(ld))
-    {
-        cold.slow = 1;
-        return;
-    }
+    if (any_nonfinite_inv(ld)) return 2;
     f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
     float lT = -1.0f;
     uint32_t lSlot = 0;
@@ -1404,16 +1849,56 @@ SPB_HD void resolve_from_candidates(const DScene &S, const uint32_t *list, f3 o,
                 lSlot = tri;
             }
     }
-    // leaving the object (trav_exit, sp_scene.cpp:296-322)
+    // leaving the object (sp_scene.cpp:296-322)
     if (lT >= 0.0f)
     {
         m4 model = load_m4(S.objModel);
         f3 localHit = add3(lo, mul3(ld, lT));
         f3 worldHit = xform(model, localHit, 1.0f);
-        cold.bT = dot3(sub3(worldHit, o), d);
-        cold.bObject = 0;
-        cold.bSlot = lSlot;
+        bT = dot3(sub3(worldHit, o), d);
+        bSlot = lSlot;
     }
+    return 0;
+}
+
+// (first machine: kept for A/B builds, -DSPB_TRAV_OLD)
+SPB_HD void resolve_from_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d, Trav &st, TravCold &cold,
+                                    Counters *counters)
+{
+    if (cold.slow || st.cur == SPB_NODE_DONE) return; // non-finite reciprocal direction / empty scene
+    float bT;
+    uint32_t bSlot;
+    const int status = resolve_candidates(S, list, o, d, st.inv, counters, bT, bSlot);
+    if (status == 1) return;
+    st.cur = SPB_NODE_DONE;
+    if (status == 2) { cold.slow = 1; return; }
+    if (bT >= 0.0f)
+    {
+        cold.bT = bT;
+        cold.bObject = 0;
+        cold.bSlot = bSlot;
+    }
+}
+
+// second machine: the lane's record was initialised by trav2_start() (which returned true);
+// returns false when the pixel falls back to the walk
+template <int STRIDE>
+SPB_HD bool resolve_from_candidates2(const DScene &S, const uint32_t *list, f3 o, f3 d, Trav2 &st, const T2View<STRIDE> &v,
+                                     Counters *counters)
+{
+    float bT;
+    uint32_t bSlot;
+    const int status = resolve_candidates(S, list, o, d, v.f3at(T2_IX), counters, bT, bSlot);
+    if (status == 1) return false;
+    st.cur = SPB_NODE_DONE;
+    if (status == 2) { v.u(T2_SLOW) = 1; return true; }
+    if (bT >= 0.0f)
+    {
+        v.f(T2_BT) = bT;
+        v.u(T2_BOBJECT) = 0;
+        v.u(T2_BSLOT) = bSlot;
+    }
+    return true;
 }
 
 // One-lookup sky pixels.  With a simple background (miss_radiance) a sky sample's radiance is the
@@ -1481,7 +1966,7 @@ SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, u
     uint32_t pathLength = 0;
     for (uint32_t bounce = 0; bounce < bounceCount; ++bounce)
     {
-        Hit hit = STEPPED ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, counters)
+        Hit hit = STEPPED ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, counters)
                           : intersect_scene<CULL>(S, o, d, stack, stackT, counters);
         pc.rays++;
         f3 V = neg3(d);

@@ -125,6 +125,229 @@ k_candidates(const __grid_constant__ WaveArgs a, uint32_t *candidates)
     }
 }
 
+// The rare ray the resumable machine hands back (a reciprocal direction beyond 1e30 or not finite,
+// coordinates beyond 1e8): the exact, non-resumable walk.
+template <bool CULL>
+__device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
+{
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    Hit h = intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+    return h;
+}
+
+#if !defined(SPB_TRAV_OLD)
+// ---------------------------------------------------------------------------------------------
+// Traversal kernel.  Persistent warps; every lane owns one ray at a time and advances it with the
+// resumable machine of spb_core.cuh (Trav2: conservative four-FFMA box tests on the way down, the
+// reference's exact test on every leaf that comes off the stack).  Each iteration of the inner
+// loop the warp runs ONE kind of step -- node visits or leaf work (triangle tests / object entry)
+// -- whichever more of its lanes are waiting for, so both code paths execute with most lanes
+// active.  When fewer than refillThreshold lanes still have work, finished lanes are retired (hit
+// record, hit/miss queue) and refilled from the ray queue.  In single-object scenes the object is
+// entered when the ray starts and left when it retires: both with every lane of the warp busy.
+// Registers hold what a node step touches (12 test constants, cull distance, current entry, stack
+// pointer); the rest of a lane's state is a 29-word record in shared memory, word-major so that
+// the lanes of a warp hit 32 different banks.
+template <bool CULL, bool STATS, bool PRIMARY>
+__global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
+k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
+{
+    const unsigned lane = lane_id();
+    uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
+    const unsigned total = PRIMARY ? a.workItems : ctr[WCTR_RAYS];
+    uint32_t *cursor = &ctr[WCTR_CURSOR];
+    v4f *rays = a.rays[bounce & 1u];
+    const bool single = a.scene.objectCount == 1;
+
+    TravEntry stack[SPB_STACK_SIZE];
+    __shared__ float recordAll[T2_WORDS][SPB_TRACE_THREADS];
+    __shared__ unsigned slotAll[SPB_TRACE_THREADS];
+    T2View<SPB_TRACE_THREADS> rec;
+    rec.base = &recordAll[0][threadIdx.x];
+    unsigned &slot = slotAll[threadIdx.x];
+    __shared__ unsigned warpStateAll[SPB_TRACE_THREADS / 32][WS_COUNT];
+    volatile unsigned *ws = warpStateAll[threadIdx.x >> 5];
+    if (lane < WS_COUNT) ws[lane] = 0;
+    __syncwarp();
+    // chunk size: a quarter of an even share per warp, so small queues still spread over the GPU
+    unsigned chunk = (total / (gridDim.x * (SPB_TRACE_THREADS / 32)) / 4 + 31u) & ~31u;
+    chunk = chunk < 32u ? 32u : (chunk > SPB_CHUNK_MAX ? SPB_CHUNK_MAX : chunk);
+    Counters cnt = {0, 0, 0, 0};
+    Trav2 st;
+    st.cur = SPB_NODE_DONE;
+    st.sp = 0;
+    st.tcull = 0.0f;
+    st.p = st.q = st.cn = st.cf = mk3(0.0f, 0.0f, 0.0f);
+    rec.u(T2_SLOW) = 0;
+    slot = 0;
+    bool have = false;
+    bool exhausted = total == 0; // warp-uniform: this warp can get no more work from the queue
+
+    for (;;)
+    {
+        // ---- retire finished lanes: hit record + queue entry
+        const bool finished = have && st.cur == SPB_NODE_DONE;
+        if (__any_sync(SPB_FULL, finished))
+        {
+            Hit h;
+            h.t = -1.0f;
+            h.slot = 0;
+            h.object = -1;
+            if (finished)
+            {
+                const v4f *ray = rays + (size_t)slot * 2;
+                if (rec.u(T2_SLOW))
+                {
+                    f3 wo, wd;
+                    trav_world_ray(ray, wo, wd);
+                    h = slow_intersect<CULL>(a.scene, wo, wd);
+                }
+                else h = trav2_finish(a.scene, ray, rec, single);
+            }
+            const bool isHit = finished && h.t > 0.0f;
+            const bool isMiss = finished && !isHit;
+            const unsigned hitMask = __ballot_sync(SPB_FULL, isHit), missMask = __ballot_sync(SPB_FULL, isMiss);
+            // primary hits of a sorted pass are found through hitRec[item], not through a queue
+            const bool queueHits = !(PRIMARY && a.sortPrimaryHits);
+            unsigned hs = 0, ms = 0;
+            if (hitMask && queueHits) hs = chunk_take(&ctr[WCTR_HITS], ws + WS_HIT_NEXT, hitMask, chunk);
+            if (missMask) ms = chunk_take(&ctr[WCTR_MISSES], ws + WS_MISS_NEXT, missMask, chunk);
+            if (lane == 0)
+            {
+                ws[WS_NHITS] += __popc(hitMask);
+                ws[WS_NMISSES] += __popc(missMask);
+            }
+            if (isHit)
+            {
+                unsigned mySlot = slot;
+                v4f r;
+                r.x = h.t; r.y = u2f(h.slot); r.z = u2f((uint32_t)h.object); r.w = 0.0f;
+                a.hitRec[mySlot] = r;
+                if (queueHits) a.hitQ[hs] = mySlot;
+            }
+            if (isMiss)
+            {
+                a.missQ[ms] = slot;
+                if (!queueHits) a.hitRec[slot] = mk4f(-1.0f, 0.0f, 0.0f, 0.0f);
+            }
+            if (finished) have = false;
+        }
+
+        // ---- refill idle lanes from the queue (regeneration)
+        if (!exhausted)
+        {
+            unsigned need = __ballot_sync(SPB_FULL, !have);
+            if (need)
+            {
+                unsigned idx = chunk_take(cursor, ws + WS_CUR_NEXT, need, chunk);
+                if (ws[WS_CUR_NEXT] >= total) exhausted = true; // chunks are handed out in order
+                if (!have && idx < total)
+                {
+                    f3 o, d;
+                    bool valid = true;
+                    if (PRIMARY)
+                    {
+                        // item -> (pixel in 8x4-block order, sample): neighbouring lanes trace
+                        // the samples of one pixel, then the neighbouring pixel.  The reference's
+                        // jitter is +-0.5/width of a PIXEL (simd_path_tracer.cpp:222-226), so the
+                        // samples of a pixel walk the same nodes: node fetches of a warp coalesce
+                        // into one L1 wavefront and its lanes stay together.
+                        unsigned x, y, sLocal;
+                        item_pixel(a, idx, x, y, sLocal);
+                        valid = x < a.x1 && y < a.y1;
+                        if (valid)
+                        {
+                            uint32_t pixelIndex = x + y * a.camera.width;
+                            uint32_t rng = stream_seed(pixelIndex, a.firstSample + sLocal, a.frame);
+                            primary_ray(a.camera, x, y, rng, o, d);
+                            store_ray(rays, idx, o, d, rng, idx); // path id == primary item
+                        }
+                        else if (a.sortPrimaryHits) a.hitRec[idx] = mk4f(-1.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                    else
+                    {
+                        // a slot that stands for a hole of the hit queue it was made from
+                        valid = f2u(rays[(size_t)idx * 2 + 1].w) != SPB_QUEUE_HOLE;
+                        if (valid) trav_world_ray(rays + (size_t)idx * 2, o, d);
+                    }
+                    if (valid)
+                    {
+                        have = true;
+                        slot = idx;
+                        Counters *c = STATS ? &cnt : nullptr;
+                        bool resolved = false;
+                        if (PRIMARY && a.candidates)
+                        {
+                            // camera ray resolved from its pixel's candidate list (spb_core.cuh
+                            // resolve_candidates); pixels that fall back walk the tree below
+                            if (!trav2_start(a.scene, o, d, st, rec)) resolved = true;
+                            else
+                                resolved = resolve_from_candidates2(
+                                    a.scene, a.candidates + (size_t)(idx / a.samplesThisPass) * SPB_CAND_STRIDE, o, d, st, rec, c);
+                        }
+                        if (!resolved)
+                        {
+                            if (single) trav2_begin_single<CULL>(a.scene, o, d, st, rec, stack, c);
+                            else trav2_begin(a.scene, o, d, st, rec, stack);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- walk
+        // lanes whose walk inside an object has ended leave it together (the exit arithmetic
+        // would otherwise run for one or two lanes at a time); single-object scenes never get here
+        if (have && st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(a.scene, st, rec, rays + (size_t)slot * 2, stack);
+        unsigned walking = __ballot_sync(SPB_FULL, have && trav_is_walking_ref(st.cur));
+        if (!walking)
+        {
+            if (!__any_sync(SPB_FULL, have) && exhausted) break;
+            continue; // everything in flight finished at once
+        }
+        do
+        {
+            const bool live = have && trav_is_walking_ref(st.cur);
+            const bool wantNode = live && (st.cur & SPB_REF_LEAF) == 0;
+            const bool wantLeaf = live && !wantNode;
+            unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
+            unsigned leafMask = walking & ~nodeMask;
+            if (__popc(nodeMask) >= __popc(leafMask))
+            {
+                if (wantNode) trav2_node<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr);
+            }
+            else
+            {
+                if (wantLeaf) trav2_leaf<CULL>(a.scene, st, rec, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+            }
+            walking = __ballot_sync(SPB_FULL, have && trav_is_walking_ref(st.cur));
+        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || exhausted));
+    }
+
+    // holes: the unused tail of this warp's last chunk of either queue; exact counts
+    __syncwarp();
+    for (unsigned i = ws[WS_HIT_NEXT] + lane; i < ws[WS_HIT_END]; i += 32) a.hitQ[i] = SPB_QUEUE_HOLE;
+    for (unsigned i = ws[WS_MISS_NEXT] + lane; i < ws[WS_MISS_END]; i += 32) a.missQ[i] = SPB_QUEUE_HOLE;
+    if (lane == 0)
+    {
+        if (ws[WS_NHITS]) atomicAdd(&ctr[WCTR_NHITS], ws[WS_NHITS]);
+        if (ws[WS_NMISSES]) atomicAdd(&ctr[WCTR_NMISSES], ws[WS_NMISSES]);
+    }
+
+    if (STATS)
+    {
+        unsigned n = __reduce_add_sync(SPB_FULL, cnt.nodeVisits), t = __reduce_add_sync(SPB_FULL, cnt.triangleTests),
+                 ob = __reduce_add_sync(SPB_FULL, cnt.objectTests);
+        if (lane == 0)
+        {
+            atomicAdd(&a.stats[CTR_NODE_VISITS], (unsigned long long)n);
+            atomicAdd(&a.stats[CTR_TRIANGLE_TESTS], (unsigned long long)t);
+            atomicAdd(&a.stats[CTR_OBJECT_TESTS], (unsigned long long)ob);
+        }
+    }
+}
+#else // SPB_TRAV_OLD: round 1's kernel over the first machine, kept for A/B builds
 // Primary ray of item `idx` resolved from its pixel's candidate list (spb_core.cuh
 // resolve_from_candidates); leaves the lane finished, or untouched when the pixel falls back.
 template <bool CULL>
@@ -133,16 +356,6 @@ __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsig
 {
     resolve_from_candidates(a.scene, a.candidates + (size_t)(idx / a.samplesThisPass) * SPB_CAND_STRIDE, o, d, st, cold,
                             counters);
-}
-
-// The rare ray whose reciprocal direction is not finite (axis-parallel): exact slab form.
-template <bool CULL>
-__device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
-{
-    uint32_t stack[SPB_STACK_SIZE];
-    float stackT[SPB_STACK_SIZE];
-    Hit h = intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
-    return h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -336,6 +549,8 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
         }
     }
 }
+
+#endif // SPB_TRAV_OLD
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_terms(v4f *pathTerms, size_t index, const VertexTerms &vt)

@@ -303,6 +303,27 @@ def multi_object_workload(width=320, height=240, spp=1, bounces=3, count=12, see
         notes={"objects": len(objects)})
 
 
+def nested_objects_workload(count=48, width=96, height=64, spp=1, bounces=3, env_size=(128, 64)):
+    """Pathological TLAS input: `count` quads, each 1.5x the size of the one in front
+    of it, so every object's box contains all the smaller ones' in x and y and has 2.25x their
+    area.  A surface-area split peels such boxes off one at a time -- cost 1 + (n - 1) / 2.25
+    against n / 2 for the middle split -- giving a tree as deep as the object count: more than the
+    traversal stack's TLAS share holds.  The builder must notice and rebuild balanced."""
+    plane = plane_mesh()
+    objects = []
+    for i in range(count):
+        s = 1.0e-3 * (1.5 ** i)
+        objects.append(SceneObject(0, MATERIAL_SURFACE if i % 2 else MATERIAL_CHECKER,
+                                   position=(0.0, 0.0, -0.01 * i), scale=(s, s, s)))
+    materials = _standard_materials() + [Material(MATERIAL_CHECKER, albedo=(0.6, 0.3, 0.2), roughness=0.35)]
+    return Workload(
+        name=f"nested_{count}obj_{width}x{height}", meshes=[plane], objects=objects, materials=materials,
+        textures={IMAGE_ENV: make_env_map(env_size[0], env_size[1], "studio_garden")},
+        background=MATERIAL_BACKGROUND, camera_position=(0.0, 0.0, 3.0),
+        camera_rotation=(0.0, 0.0, 0.0, 1.0), film_distance=0.8, width=width, height=height,
+        spp=spp, bounces=bounces, notes={"objects": count})
+
+
 def config5(width=3840, height=2160, spp=16, bounces=5, bunnies=64, spheres=118, sphere_level=6,
             unique_spheres=False, seed=0x1A34C249, env_size=(4096, 2048)):
     """BASELINE configs[4]: procedural instanced scene, ~10 M triangles at the defaults
