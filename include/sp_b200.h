@@ -30,6 +30,7 @@ typedef int32_t i32;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef float f32;
+typedef double f64;
 typedef u32 b32;
 
 /* math_lib.h:12-92 (unions there; plain structs with the same layout here) */
@@ -260,6 +261,36 @@ typedef struct sp_b200_Stats {
 } sp_b200_Stats;
 
 int sp_b200_Init(int device);            /* selects the device; 0 on success */
+/* Several GPUs of the box in ONE process (SURVEY.md §8b "sp_b200_Init(deviceMask)", §8e): bit i of
+ * the mask selects CUDA device i; the lowest one becomes the primary (every entry point keeps
+ * running there), each further one gets its own worker thread, stream set and working buffers.
+ * From then on sp_b200_RenderFrame / sp_b200_RenderFrameToDevice split the frame into strips of rows
+ * cut at multiples of sp_b200_Params::tileHeight, one per device, all rendered concurrently; strip
+ * boundaries are re-cut after every frame from the measured per-row cost (sp_b200_PartitionRows).
+ * Scenes must be built (sp_BuildSceneBroadphase) AFTER this call: the further devices upload the
+ * host copy it keeps, on first use.  Returns the number of devices in use, or -1. */
+int sp_b200_InitDevices(u32 deviceMask);
+/* The same with an explicit list (first entry = primary).  An ordinal may appear more than once:
+ * every entry gets its own worker, streams and buffers, which exercises the whole multi-device path
+ * -- strips, concurrent renders, gather, re-cut -- on a box with a single GPU. */
+int sp_b200_InitDeviceList(const i32 *devices, u32 count);
+u32 sp_b200_DeviceCount(void);
+/* The frame gathered on the primary device: every other device sends its strip with a peer copy
+ * (NVLink where the topology has it) into devicePixels, width x height RGBA f32 on the primary.
+ * sp_b200_RenderFrame is the host-memory form: each device copies its own rows to the image plane's
+ * (pinned) pixels over its own PCIe link. */
+int sp_b200_RenderFrameToDevice(sp_Context *ctx, u32 frame, void *devicePixels, sp_Metrics *metrics);
+/* Figures of device `index` (0 = primary) for the last multi-device frame and the rows it rendered;
+ * 0 on success.  sp_b200_GetLastStats holds the frame's totals (times: the slowest device's). */
+int sp_b200_GetDeviceStats(u32 index, sp_b200_Stats *stats, u32 *rowBegin, u32 *rowEnd);
+/* The cut itself (host arithmetic; also what a multi-process host uses between its ranks): `parts`
+ * contiguous strips of `height` rows with boundaries at multiples of `quantum`, minimising the
+ * largest strip's summed cost (rowCost: one value per quantum row; NULL = even split).
+ * bounds: parts + 1 ascending rows.  sp_b200_RowSeconds turns what the parts measured -- cost units
+ * per quantum row (sp_b200_RenderRows tileRowCost) and seconds per part -- into seconds per row. */
+void sp_b200_PartitionRows(u32 height, u32 quantum, u32 parts, const f64 *rowCost, u32 *bounds);
+void sp_b200_RowSeconds(u32 height, u32 quantum, u32 parts, const u32 *bounds, const f64 *units,
+                        const f64 *seconds, f64 *rowSeconds);
 void sp_b200_Shutdown(void);             /* frees every device and host object */
 void sp_b200_SetLogCallback(sp_b200_LogFn fn);
 void sp_b200_SetStream(void *cudaStream);/* stream all later launches use (0 = default) */
@@ -289,6 +320,13 @@ void sp_b200_SetRaySorting(int enable);
  * culling) to list the triangles any of the pixel's camera rays can meet; every sample then
  * evaluates only those, with the walk's own tests.  On by default; results do not depend on it. */
 void sp_b200_SetPrimaryCandidates(int enable);
+/* Copy-engine overlap (on by default; results do not depend on it).  HdrImage pixels (pinned host
+ * memory) are uploaded on a second stream and the render stream waits for them only where the first
+ * kernel that samples a texture starts -- behind the coverage pass, the candidate lists and the first
+ * primary trace -- and sp_b200_RenderFrame / sp_b200_RenderRows copy finished rows to a pinned host
+ * image band by band while later bands render.  0: one upload in front of the frame and one copy
+ * behind it, both on the render stream (round 1's behaviour). */
+void sp_b200_SetCopyOverlap(int enable);
 /* Wavefront mode tuning: a warp of the trace kernel retires and refills its lanes when fewer than
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */

@@ -9,11 +9,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import importlib.util  # noqa: E402
-
-spec = importlib.util.spec_from_file_location("strips", os.path.join(ROOT, "vk_cinematic_b200", "strips.py"))
-strips = importlib.util.module_from_spec(spec)
-spec.loader.exec_module(strips)
+from vk_cinematic_b200 import strips  # noqa: E402  (loads libspb200.so for the cut; no compute call, no GPU)
 
 
 def main():

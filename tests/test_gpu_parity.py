@@ -17,6 +17,7 @@ import pytest
 
 import ora
 from vk_cinematic_b200 import workloads as W
+from vk_cinematic_b200.fixtures import lattice, relative_error_report, tile_crcs
 
 pytestmark = pytest.mark.gpu
 
@@ -46,6 +47,24 @@ def assert_same_image_up_to_ties(img, cimg, chk, spp, bounces, frame, bound=1e-4
                                   f"{list(zip(*np.nonzero(unexplained)))[:8]}"
     assert diff.sum() <= max(1, int(bound * diff.size)), f"{int(diff.sum())} tie pixels differ (bound {bound})"
     return int(diff.sum())
+
+
+def assert_tiles_match(image, metrics, gold, key, ties_key, bound=1e-4):
+    """Whole-frame comparison against per-tile CRC-32s of a checker's render (fixtures.tile_crcs):
+    every 64x64 tile must hash to the checker's value, except tiles holding a pixel the checker
+    recorded an exact-t tie for; ray / hit / miss counters equal up to those ties."""
+    crc = tile_crcs(image)
+    want = gold["tile_crc_" + key]
+    assert crc.shape == want.shape
+    bad = set(np.nonzero(crc != want)[0].tolist())
+    tx = (image.shape[1] + 63) // 64
+    tie_tiles = set(int(y // 64) * tx + int(x // 64) for x, y in gold[ties_key])
+    assert bad <= tie_tiles, f"tiles differing without a tie pixel: {sorted(bad - tie_tiles)[:8]}"
+    assert len(bad) <= max(1, int(bound * image.shape[0] * image.shape[1]))
+    gm = gold["metrics_" + key].astype(np.int64)
+    slack = 8 * len(gold[ties_key]) * 64
+    assert int(metrics[1]) == int(gm[0]) and np.all(np.abs(metrics[2:5].astype(np.int64) - gm[1:4]) <= slack)
+    return len(bad)
 
 
 def best(dm):
@@ -395,6 +414,10 @@ def test_c3_full_size_properties(params):
     full = full.copy()
     assert np.isfinite(full).all() and (full[..., 3] == 1.0).all()
     assert m[sp.sp_Metric_PathsTraced] == 3840 * 2160 * 64
+    # (e) EVERY pixel of the bench frame: the 2040 tile CRCs of the port's deterministic-math render
+    # (tests/golden/g5_c3_full_frame.npz, tools/make_full_frame_golden.py).  A tile may differ only
+    # if it holds one of the pixels where the port itself met an exact-t tie.
+    assert_tiles_match(full, m, np.load(os.path.join(GOLD, "g5_c3_full_frame.npz")), "port_dm_5b", "ties_5b")
     assert m[sp.sp_Metric_RaysTraced] == m[sp.sp_Metric_RayHitCount] + m[sp.sp_Metric_RayMissCount]
     r.image[:] = 0
     total = np.zeros(12, np.uint64)
@@ -418,6 +441,75 @@ def test_c3_full_size_properties(params):
         assert same_bits(full[y0:y1, x0:x1], cimg[y0:y1, x0:x1]), rect
     chk.close()
     r.close()
+
+
+def test_c3_full_frame_vs_the_reference_at_its_three_bounces(gpu_sp):
+    """The bench frame against the UNMODIFIED reference (fixed at 3 bounces,
+    simd_path_tracer.cpp:195), every pixel: (a) deterministic-math mode vs libspref_dm: the 2040 tile
+    CRCs of tests/golden/g5_c3_full_frame.npz, bit for bit (ties aside); (b) both math modes vs the
+    plain reference (glibc libm) on the fixture's lattice of 32 400 pixels spread over the frame:
+    stated tolerance -- at most 2 % of pixels off by more than 1e-3 relative, RMSE <= 2 % of the mean
+    radiance (a last-ulp difference in a bounce direction can move a path to another texel of the
+    noisy environment map); per-tile means of the whole frame within 1e-3 relative."""
+    sp = gpu_sp
+    gold = np.load(os.path.join(GOLD, "g5_c3_full_frame.npz"))
+    wl = W.config3()
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=64, bounceCount=3, mathMode=0, renderMode=0)
+    img, m = r.render_frame(frame=0)
+    assert_tiles_match(img, m, gold, "ref_dm_3b", "ties_3b")
+    for math_mode in (0, 1):
+        sp.set_params(samplesPerPixel=64, bounceCount=3, mathMode=math_mode, renderMode=0)
+        img, m = r.render_frame(frame=0)
+        rep = relative_error_report(lattice(img), gold["lattice_ref_3b"])
+        assert rep["fraction_above"]["0.001"] <= 0.02 and rep["rmse_over_mean"] <= 0.02, rep
+        sums = img[:33 * 64, :, 0:3].astype(np.float64).reshape(33, 64, 60, 64, 3).sum(axis=(1, 3)).reshape(-1, 3)
+        want = gold["tile_sum_ref_3b"][:33 * 60]
+        assert np.all(np.abs(sums - want) <= 1e-3 * np.abs(want) + 1e-6), float(np.abs(sums / want - 1).max())
+        assert abs(int(m[2]) - int(gold["metrics_ref_3b"][1])) <= 1e-3 * int(m[2])
+    sp.set_params(samplesPerPixel=1, bounceCount=3, mathMode=0)
+    r.close()
+
+
+def test_c2_full_frame_fixture(gpu_sp):
+    """BASELINE configs[1] against the committed fingerprint of the unmodified reference's closest
+    hits (tests/golden/g6_c2_full_frame.npz: per-tile CRCs of triangle ids, distances, object ids):
+    the comparison bench.py's `parity` block makes without a checker at hand."""
+    sp = gpu_sp
+    gold = np.load(os.path.join(GOLD, "g6_c2_full_frame.npz"))
+    wl = W.config2()
+    r = sp.Renderer().load_workload(wl)
+    g = r.primary_hits(sample=0, frame=0)
+    assert np.array_equal(tile_crcs(g["t"]), gold["tile_crc_t"]) and np.array_equal(tile_crcs(g["obj"]), gold["tile_crc_obj"])
+    tiles_off = int((tile_crcs(g["tri"]) != gold["tile_crc_tri"]).sum())
+    assert tiles_off <= 2 and int((g["tri"] >= 0).sum()) == int(gold["hit_pixels"])
+    r.close()
+
+
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_multi_device_frame(gpu_sp, mode):
+    """Several devices behind the C ABI: sp_b200_InitDeviceList, then
+    sp_b200_RenderFrame (every device copies its rows to the host image) or
+    sp_b200_RenderFrameToDevice (strips gathered on the primary with peer copies).  The frame must be
+    bit-identical to the one-device frame and the counters equal, for every frame while the strip
+    boundaries are re-cut from the measured cost.  Uses every GPU of the box; on a one-GPU box the
+    same device is listed three times, which exercises the same code (own worker, streams and buffers
+    per entry).  Own process: the device set of a process is chosen once."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    devices = list(range(min(n, 4))) if n > 1 else [0, 0, 0]
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_multi_device_worker.py")
+    p = subprocess.run([sys.executable, worker, ",".join(map(str, devices)), mode], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert all(out["identical"]) and all(out["metrics_equal"]), out
+    first, last = out["strips"][0], out["strips"][-1]
+    assert first[0][0] == 0 and first[-1][1] == 368 and all(a[1] == b[0] for a, b in zip(first, first[1:]))
+    assert last[0][0] == 0 and last[-1][1] == 368 and all(a[1] == b[0] for a, b in zip(last, last[1:]))
+    assert first != last                       # the cut moved: this camera makes an even split uneven
 
 
 def test_c5_instanced_scene(params):

@@ -53,6 +53,20 @@ def test_partition_by_cost_balances():
     assert (b[1][1] - b[1][0]) < (b[0][1] - b[0][0])
 
 
+def test_partition_is_the_minmax_optimum():
+    """sp_b200_PartitionRows against brute force over every cut position (small cases)."""
+    import itertools
+    rng = np.random.RandomState(11)
+    for _ in range(40):
+        rows, world = int(rng.randint(4, 11)), int(rng.choice([2, 3, 4]))
+        cost = rng.uniform(0.0, 5.0, rows) ** 3
+        b = strips.partition_rows(rows * 16, 16, world, cost)
+        got = max(cost[s // 16:e // 16].sum() for s, e in b)
+        best = min(max(cost[a:c].sum() for a, c in zip((0,) + cuts, cuts + (rows,)))
+                   for cuts in itertools.combinations(range(1, rows), world - 1))
+        assert got <= best * (1 + 1e-12) + 1e-12
+
+
 def test_strip_cost_roundtrip():
     bounds = strips.partition_rows(2160, 64, 4)
     per = [np.arange((e - 1) // 64 - s // 64 + 1) + 10 * r for r, (s, e) in enumerate(bounds)]

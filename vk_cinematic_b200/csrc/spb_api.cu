@@ -6,6 +6,9 @@
 
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +21,7 @@
 #include "spb_capture.h"
 #include "spb_kernels.cuh"
 #include "spb_cubemap.cuh"
+#include "spb_strips.h"
 
 using namespace spb;
 
@@ -153,6 +157,14 @@ struct Library
     // wavefront working set (DESIGN.md "Data layout")
     DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand, wSkyList;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
+    // Copy engine side of a frame (DESIGN.md "End to end"): texture uploads run on copyStream and
+    // the render stream waits for them only where the first kernel that reads a texture is
+    // launched; finished rows go back to a pinned host image band by band on the same stream
+    // while later bands render.
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evTextures = nullptr, evRowsReady = nullptr, evCopyDone = nullptr, evOrder = nullptr;
+    bool texturesPending = false; // an upload was issued on copyStream and nobody waited for it yet
+    bool overlapCopies = true;    // sp_b200_SetCopyOverlap
 
     Library()
     {
@@ -170,16 +182,112 @@ struct Library
     }
 };
 
-Library &lib()
+// One Library per device.  The primary one serves every call made on the host's own threads (what
+// round 1 had: a process-wide singleton); sp_b200_InitDevices adds one per further GPU, each owned
+// by a worker thread that points `t_current` at it, so that the same entry points -- which all go
+// through lib() -- render a strip on that device when the worker calls them.
+thread_local Library *t_current = nullptr;
+
+Library &primary_lib()
 {
     static Library *instance = new Library(); // never destroyed: safe at process exit
+    return *instance;
+}
+
+Library &lib() { return t_current ? *t_current : primary_lib(); }
+
+// A further device of the process: its Library and the thread that owns it.  Jobs are run one at
+// a time; run() returns when the job is done.
+struct DeviceWorker
+{
+    Library *L = nullptr;
+    std::thread thread;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool hasJob = false, done = true, quit = false;
+
+    void start()
+    {
+        thread = std::thread([this] {
+            t_current = L;
+            for (;;)
+            {
+                std::function<void()> f;
+                {
+                    std::unique_lock<std::mutex> lock(m);
+                    cv.wait(lock, [this] { return hasJob || quit; });
+                    if (quit) return;
+                    f = std::move(job);
+                    hasJob = false;
+                }
+                f();
+                {
+                    std::lock_guard<std::mutex> lock(m);
+                    done = true;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    void post(std::function<void()> f)
+    {
+        std::lock_guard<std::mutex> lock(m);
+        job = std::move(f);
+        hasJob = true;
+        done = false;
+        cv.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [this] { return done; });
+    }
+    void run(std::function<void()> f) { post(std::move(f)); wait(); }
+    void stop()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            quit = true;
+        }
+        cv.notify_all();
+        if (thread.joinable()) thread.join();
+    }
+};
+
+struct MultiDevice
+{
+    std::mutex mutex;                       // one multi-device frame at a time
+    std::vector<int> devices;               // CUDA ordinals; [0] is the primary's
+    std::vector<std::unique_ptr<DeviceWorker>> workers; // devices[1..]
+    // host copies of the built scenes, for the further devices to upload from (keyed like
+    // Library::scenes: sp_Scene::broadphaseTree.root)
+    std::map<void *, std::shared_ptr<FlatScene>> flats;
+    // strips of the last frame and what they cost (sp_b200_RenderFrame re-cuts from it)
+    std::vector<uint32_t> bounds, nextBounds; // the cut of the last frame / the one the next frame will use
+    uint32_t height = 0, quantum = 0;
+    std::vector<sp_b200_Stats> stats;
+    std::vector<double> seconds;
+    bool active() const { return devices.size() > 1; }
+};
+
+MultiDevice &multi()
+{
+    static MultiDevice *instance = new MultiDevice();
     return *instance;
 }
 
 void ensure_init()
 {
     Library &L = lib();
-    if (L.initialized) return;
+    if (L.initialized)
+    {
+        // the device is per-thread state of the CUDA runtime: a host thread that has not called
+        // in before would otherwise launch on device 0
+        int current = -1;
+        if (cudaGetDevice(&current) == cudaSuccess && current != L.device) SPB_CUDA(cudaSetDevice(L.device));
+        return;
+    }
     int count = 0;
     cudaError_t err = cudaGetDeviceCount(&count);
     if (err != cudaSuccess || count == 0)
@@ -193,6 +301,11 @@ void ensure_init()
     SPB_CUDA(cudaEventCreate(&L.evKernel0));
     SPB_CUDA(cudaEventCreate(&L.evKernel1));
     SPB_CUDA(cudaEventCreate(&L.evEnd));
+    SPB_CUDA(cudaStreamCreateWithFlags(&L.copyStream, cudaStreamNonBlocking));
+    SPB_CUDA(cudaEventCreateWithFlags(&L.evTextures, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&L.evRowsReady, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&L.evCopyDone, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&L.evOrder, cudaEventDisableTiming));
     L.initialized = true;
 }
 
@@ -280,8 +393,22 @@ DeviceScene *find_scene(sp_Scene *scene)
         auto it = L.scenes.find(scene->broadphaseTree.root);
         if (it == L.scenes.end())
         {
-            log_message("sp_Scene::broadphaseTree was not built by sp_BuildSceneBroadphase of libspb200");
-            abort();
+            // a further device (sp_b200_InitDevices) meets the scene for the first time: upload the
+            // host copy sp_BuildSceneBroadphase kept
+            std::shared_ptr<FlatScene> flat;
+            if (t_current)
+            {
+                MultiDevice &M = multi();
+                auto f = M.flats.find(scene->broadphaseTree.root);
+                if (f != M.flats.end()) flat = f->second;
+            }
+            if (!flat)
+            {
+                log_message(t_current ? "sp_Scene was built before sp_b200_InitDevices: call sp_BuildSceneBroadphase again"
+                                      : "sp_Scene::broadphaseTree was not built by sp_BuildSceneBroadphase of libspb200");
+                abort();
+            }
+            it = L.scenes.emplace(scene->broadphaseTree.root, upload_scene(*flat)).first;
         }
         return it->second.get();
     }
@@ -317,15 +444,39 @@ const v4f *device_texture(const HdrImage &image)
     entry->buffer.ensure(bytes);
     entry->width = image.width;
     entry->height = image.height;
-    SPB_CUDA(cudaMemcpyAsync(entry->buffer.ptr, image.pixels, bytes, cudaMemcpyHostToDevice, L.stream));
-    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    if (L.overlapCopies)
+    {
+        // no host wait: whoever launches the first kernel that reads a texture makes the render
+        // stream wait for evTextures (wait_textures).  The buffer may have been read by kernels of
+        // an earlier frame still in flight on the render stream: order the copy after them.
+        SPB_CUDA(cudaEventRecord(L.evOrder, L.stream));
+        SPB_CUDA(cudaStreamWaitEvent(L.copyStream, L.evOrder, 0));
+        SPB_CUDA(cudaMemcpyAsync(entry->buffer.ptr, image.pixels, bytes, cudaMemcpyHostToDevice, L.copyStream));
+        SPB_CUDA(cudaEventRecord(L.evTextures, L.copyStream));
+        L.texturesPending = true;
+    }
+    else
+    {
+        SPB_CUDA(cudaMemcpyAsync(entry->buffer.ptr, image.pixels, bytes, cudaMemcpyHostToDevice, L.stream));
+        SPB_CUDA(cudaStreamSynchronize(L.stream));
+    }
     const v4f *p = (const v4f *)entry->buffer.ptr;
     L.textures[image.pixels] = std::move(entry);
     return p;
 }
 
-// Uploads the material system (textures resolved) and returns the device pointer.
-const DMaterials *upload_materials(const sp_MaterialSystem *ms, size_t *bytesOut = nullptr)
+// The render stream goes on only after every texture upload issued so far has landed.
+void wait_textures()
+{
+    Library &L = lib();
+    if (!L.texturesPending) return;
+    SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evTextures, 0));
+    L.texturesPending = false;
+}
+
+// Uploads the material system (textures resolved) and returns the device pointer.  deferWait: the
+// caller launches kernels that do not read textures first and calls wait_textures() itself.
+const DMaterials *upload_materials(const sp_MaterialSystem *ms, size_t *bytesOut = nullptr, bool deferWait = false)
 {
     Library &L = lib();
     static sp_MaterialSystem emptySystem; // zero-initialised
@@ -344,6 +495,7 @@ const DMaterials *upload_materials(const sp_MaterialSystem *ms, size_t *bytesOut
     L.materials.ensure(sizeof(DMaterials));
     SPB_CUDA(cudaMemcpyAsync(L.materials.ptr, &dm, sizeof(dm), cudaMemcpyHostToDevice, L.stream));
     if (bytesOut) *bytesOut = sizeof(dm);
+    if (!deferWait) wait_textures();
     return (const DMaterials *)L.materials.ptr;
 }
 
@@ -427,7 +579,10 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
 // kernels over device queues (spb_wavefront.cu).  One 4-byte read-back (the number of covered
 // blocks) sizes the bands; nothing else returns to the host between kernels.  Band size and S are
 // chosen so that one pass keeps about 32 Mi paths in flight.
-void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::vector<uint32_t> &countersOut)
+// hostOut: pinned host image (full frame, same layout as ra.out) that finished rows are copied to on
+// the copy stream while later bands render, or null (the caller copies).  Returns true when the rows
+// [ra.y0, ra.y1) have been (asynchronously) copied to hostOut; evCopyDone then marks the last copy.
+bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::vector<uint32_t> &countersOut, f32 *hostOut)
 {
     Library &L = lib();
     const uint32_t spp = ra.spp, bounces = ra.bounces;
@@ -435,6 +590,10 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     const uint32_t width = ra.x1 - ra.x0, height = ra.y1 - ra.y0;
     const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
     const uint32_t blocks = blocksX * blocksY;
+    // (statistics of this frame only, whatever path it takes below)
+    L.traceEventsUsed = 0;
+    L.tuner.probes.clear();
+    countersOut.clear();
 
     WaveArgs a;
     memset(&a, 0, sizeof(a));
@@ -486,13 +645,45 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             a.skyDirectionSpread = (float)spread;
         }
     }
-    launch_sky(cfg, a, L.stream);
-    if (a.skyList) launch_sky_listed(cfg, a, L.stream);
+    // The one read-back of the frame: the number of covered blocks (it sizes the bands).  Only the
+    // coverage pass is in front of it; the sky kernels -- the first to read the environment map --
+    // are launched behind the first primary trace, which does not, so a texture upload in flight
+    // on the copy stream has that long to land before anything waits for it.
     uint32_t covered = 0;
     SPB_CUDA(cudaMemcpyAsync(&covered, listCount, 4, cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
-    countersOut.clear();
-    if (covered == 0) return;
+
+    // rows -> host, band by band, on the copy stream (pinned destinations only: a pageable one
+    // would block this thread inside cudaMemcpyAsync and stall the launches behind it)
+    bool streamRows = false;
+    if (hostOut && L.overlapCopies)
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, hostOut) == cudaSuccess && attr.type == cudaMemoryTypeHost) streamRows = true;
+        else cudaGetLastError();
+    }
+    // rows [rowBegin, rowEnd) are final once everything launched on the render stream so far is done
+    auto copy_rows = [&](uint32_t rowBegin, uint32_t rowEnd) {
+        if (!streamRows || rowEnd <= rowBegin) return;
+        SPB_CUDA(cudaEventRecord(L.evRowsReady, L.stream));
+        SPB_CUDA(cudaStreamWaitEvent(L.copyStream, L.evRowsReady, 0));
+        const size_t offset = (size_t)rowBegin * ra.camera.width;
+        SPB_CUDA(cudaMemcpyAsync(hostOut + offset * 4, ra.out + offset, (size_t)(rowEnd - rowBegin) * ra.camera.width * 16,
+                                 cudaMemcpyDeviceToHost, L.copyStream));
+        SPB_CUDA(cudaEventRecord(L.evCopyDone, L.copyStream));
+    };
+    uint32_t rowsCopied = ra.y0, rowsBottom = ra.y1; // rows outside [rowsCopied, rowsBottom) are on their way
+    auto launch_sky_kernels = [&]() {
+        wait_textures();
+        launch_sky(cfg, a, L.stream);
+        if (a.skyList) launch_sky_listed(cfg, a, L.stream);
+    };
+    if (covered == 0)
+    {
+        launch_sky_kernels();
+        copy_rows(ra.y0, ra.y1);
+        return streamRows;
+    }
 
     const uint64_t targetItems = L.pathsPerPass ? L.pathsPerPass : (32u << 20);
     uint32_t S = L.params.samplesPerPass ? L.params.samplesPerPass : spp;
@@ -506,6 +697,21 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     bandBlocks = (covered + bands - 1) / bands; // bands of equal size
     bands = (covered + bandBlocks - 1) / bandBlocks;
     const uint32_t passes = (spp + S - 1) / S;
+    // last block of every band (the list is row-major): rows above the block row it lies in are
+    // final once the band is done.  One more small read-back, the stream is idle anyway.
+    std::vector<uint32_t> bandLast(bands, 0);
+    uint32_t firstBlock = 0;
+    if (streamRows)
+    {
+        const uint32_t *list = (const uint32_t *)L.wBlockList.ptr;
+        SPB_CUDA(cudaMemcpyAsync(&firstBlock, list, 4, cudaMemcpyDeviceToHost, L.stream));
+        for (uint32_t b = 0; b < bands; ++b)
+        {
+            uint32_t last = (b + 1) * bandBlocks < covered ? (b + 1) * bandBlocks - 1 : covered - 1;
+            SPB_CUDA(cudaMemcpyAsync(&bandLast[b], list + last, 4, cudaMemcpyDeviceToHost, L.stream));
+        }
+        SPB_CUDA(cudaStreamSynchronize(L.stream));
+    }
     SPB_ASSERT(32ull * bandBlocks * S < 0xFFFFFFFFull - SPB_QUEUE_SLACK);
     const uint32_t capacity = 32u * bandBlocks * S; // ray slots and path ids both fit
 
@@ -555,10 +761,8 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
         tn.choice = -1;
         tn.frames = 0;
     }
-    tn.probes.clear();
     const bool tuning = a.sortPrimaryHits && L.refillThreshold[1] == 0 && tn.choice < 0;
 
-    L.traceEventsUsed = 0;
     auto timed_trace = [&](uint32_t bounce, bool primary) {
         if (L.traceEventsUsed + 2 > L.traceEvents.size())
             for (int k = 0; k < 64; ++k)
@@ -595,6 +799,23 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             ctr += (size_t)bounces * WCTR_STRIDE;
             a.refillThreshold = L.refillThreshold[0];
             timed_trace(0, true);
+            if (band == 0 && pass == 0)
+            {
+                // sky pixels, behind the first primary trace (see above); the rows above the
+                // first and below the last covered block row are sky only: off to the host
+                launch_sky_kernels();
+                if (streamRows)
+                {
+                    uint32_t top = ra.y0 + 4u * (firstBlock / blocksX);
+                    uint32_t bottom = ra.y0 + 4u * (bandLast[bands - 1] / blocksX + 1u);
+                    if (top > ra.y1) top = ra.y1;
+                    if (bottom > ra.y1) bottom = ra.y1;
+                    copy_rows(ra.y0, top);
+                    copy_rows(bottom, ra.y1);
+                    rowsCopied = top;
+                    rowsBottom = bottom;
+                }
+            }
             for (uint32_t b = 0; b < bounces; ++b)
             {
                 const bool sortedNext = b == 0 && a.sortPrimaryHits;
@@ -629,32 +850,40 @@ void render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             passIndex++;
             launch_wave_accumulate(a, L.stream);
         }
+        if (streamRows)
+        {
+            // the band's last block row may continue in the next band: stop above it
+            uint32_t end = band + 1 < bands ? ra.y0 + 4u * (bandLast[band] / blocksX) : rowsBottom;
+            if (end > rowsBottom) end = rowsBottom;
+            if (end > rowsCopied)
+            {
+                copy_rows(rowsCopied, end);
+                rowsCopied = end;
+            }
+        }
     }
     countersOut.resize(ctrWords);
+    return streamRows;
 }
 
-} // namespace
-
-// =============================================================================================
-// library control
-
-extern "C" int sp_b200_Init(int device)
+// A scene handle is the address of the primary's DeviceScene, which the allocator may hand out
+// again: the further devices must forget their copy the moment the primary's dies.
+void forget_scene_on_devices(void *handle)
 {
-    Library &L = lib();
-    std::lock_guard<std::recursive_mutex> lock(L.mutex);
-    if (L.initialized && device != L.device)
-    {
-        log_message("sp_b200_Init: already initialised on device %d", L.device);
-        return 1;
-    }
-    L.device = device;
-    ensure_init();
-    return 0;
+    MultiDevice &M = multi();
+    M.flats.erase(handle);
+    for (auto &w : M.workers)
+        w->run([handle] {
+            Library &L = lib();
+            std::lock_guard<std::recursive_mutex> lock(L.mutex);
+            if (L.initialized) cudaDeviceSynchronize();
+            L.scenes.erase(handle);
+        });
 }
 
-extern "C" void sp_b200_Shutdown(void)
+// everything one Library owns on its device (called on the thread that owns it)
+void shutdown_library(Library &L)
 {
-    Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     if (L.initialized) cudaDeviceSynchronize();
     for (auto &m : L.meshes)
@@ -684,8 +913,157 @@ extern "C" void sp_b200_Shutdown(void)
     {
         cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
         cudaEventDestroy(L.evKernel1); cudaEventDestroy(L.evEnd);
+        cudaEventDestroy(L.evTextures); cudaEventDestroy(L.evRowsReady); cudaEventDestroy(L.evCopyDone); cudaEventDestroy(L.evOrder);
+        cudaStreamDestroy(L.copyStream);
+        L.copyStream = nullptr;
     }
+    L.texturesPending = false;
     L.initialized = false;
+}
+
+void stop_devices()
+{
+    MultiDevice &M = multi();
+    for (auto &w : M.workers)
+    {
+        w->run([] { shutdown_library(lib()); });
+        w->stop();
+        delete w->L;
+    }
+    M.workers.clear();
+    M.devices.clear();
+    M.flats.clear();
+    M.bounds.clear();
+    M.nextBounds.clear();
+    M.stats.clear();
+    M.seconds.clear();
+}
+
+} // namespace
+
+// =============================================================================================
+// library control
+
+extern "C" int sp_b200_Init(int device)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (L.initialized && device != L.device)
+    {
+        log_message("sp_b200_Init: already initialised on device %d", L.device);
+        return 1;
+    }
+    L.device = device;
+    ensure_init();
+    return 0;
+}
+
+extern "C" void sp_b200_Shutdown(void)
+{
+    stop_devices();
+    shutdown_library(primary_lib());
+}
+
+extern "C" int sp_b200_InitDeviceList(const i32 *deviceList, u32 listCount)
+{
+    MultiDevice &M = multi();
+    std::lock_guard<std::mutex> lock(M.mutex);
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+    {
+        log_message("sp_b200_InitDevices: no usable CUDA device (%s); libspb200 has no CPU path",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "0 devices");
+        abort();
+    }
+    std::vector<int> wanted;
+    for (u32 i = 0; i < listCount; ++i)
+    {
+        if (deviceList[i] < 0 || deviceList[i] >= count)
+        {
+            log_message("sp_b200_InitDevices: device %d of %d does not exist", deviceList[i], count);
+            return -1;
+        }
+        wanted.push_back(deviceList[i]);
+    }
+    if (wanted.empty()) return -1;
+    Library &P = primary_lib();
+    if (M.active() || (P.initialized && P.device != wanted[0]))
+    {
+        log_message("sp_b200_InitDevices: devices were already chosen (call sp_b200_Shutdown first)");
+        return -1;
+    }
+    if (sp_b200_Init(wanted[0]) != 0) return -1;
+    M.devices = wanted;
+    for (size_t i = 1; i < wanted.size(); ++i)
+    {
+        auto w = std::make_unique<DeviceWorker>();
+        w->L = new Library();
+        w->L->device = wanted[i];
+        w->start();
+        const int mine = wanted[i], first = wanted[0];
+        w->run([mine, first] {
+            ensure_init();
+            // strips go to the primary's image with direct peer copies over NVLink where the
+            // topology allows it (otherwise cudaMemcpyPeerAsync stages through the host)
+            int can = 0;
+            if (mine != first && cudaDeviceCanAccessPeer(&can, mine, first) == cudaSuccess && can)
+                if (cudaDeviceEnablePeerAccess(first, 0) != cudaSuccess) cudaGetLastError();
+        });
+        M.workers.push_back(std::move(w));
+    }
+    for (size_t i = 1; i < wanted.size(); ++i)
+    {
+        int can = 0;
+        if (wanted[i] != wanted[0] && cudaDeviceCanAccessPeer(&can, wanted[0], wanted[i]) == cudaSuccess && can)
+            if (cudaDeviceEnablePeerAccess(wanted[i], 0) != cudaSuccess) cudaGetLastError();
+    }
+    M.bounds.clear();
+    M.nextBounds.clear();
+    return (int)wanted.size();
+}
+
+extern "C" int sp_b200_InitDevices(u32 deviceMask)
+{
+    i32 list[32];
+    u32 n = 0;
+    for (i32 d = 0; d < 32; ++d)
+        if (deviceMask & (1u << d)) list[n++] = d;
+    if (n == 0)
+    {
+        log_message("sp_b200_InitDevices: empty device mask");
+        return -1;
+    }
+    return sp_b200_InitDeviceList(list, n);
+}
+
+extern "C" u32 sp_b200_DeviceCount(void)
+{
+    MultiDevice &M = multi();
+    return M.active() ? (u32)M.devices.size() : 1u;
+}
+
+extern "C" void sp_b200_PartitionRows(u32 height, u32 quantum, u32 parts, const f64 *rowCost, u32 *bounds)
+{
+    partition_rows(height, quantum, parts, rowCost, bounds);
+}
+
+extern "C" void sp_b200_RowSeconds(u32 height, u32 quantum, u32 parts, const u32 *bounds, const f64 *units,
+                                   const f64 *seconds, f64 *rowSeconds)
+{
+    std::vector<double> r = row_seconds(height, quantum, parts, bounds, units, seconds);
+    for (size_t i = 0; i < r.size(); ++i) rowSeconds[i] = r[i];
+}
+
+extern "C" int sp_b200_GetDeviceStats(u32 index, sp_b200_Stats *stats, u32 *rowBegin, u32 *rowEnd)
+{
+    MultiDevice &M = multi();
+    std::lock_guard<std::mutex> lock(M.mutex);
+    if (index >= M.stats.size() || (size_t)index + 1 >= M.bounds.size()) return 1;
+    if (stats) *stats = M.stats[index];
+    if (rowBegin) *rowBegin = M.bounds[index];
+    if (rowEnd) *rowEnd = M.bounds[index + 1];
+    return 0;
 }
 
 extern "C" void sp_b200_SetLogCallback(sp_b200_LogFn fn) { g_log = fn; }
@@ -723,6 +1101,7 @@ extern "C" void sp_b200_SetSkyCulling(int enable)
     lib().skyOneLookup = enable != 1; // 1: coverage + sky kernel with the per-sample loop only
 }
 extern "C" void sp_b200_SetPrimaryCandidates(int enable) { lib().primaryCandidates = enable != 0; }
+extern "C" void sp_b200_SetCopyOverlap(int enable) { lib().overlapCopies = enable != 0; }
 extern "C" void sp_b200_SetRaySorting(int enable)
 {
     lib().sortBounceRays = enable != 0;
@@ -899,6 +1278,7 @@ extern "C" void sp_b200_ReleaseScene(sp_Scene *scene)
     {
         if (L.initialized) cudaDeviceSynchronize();
         L.scenes.erase(scene->broadphaseTree.root);
+        forget_scene_on_devices(scene->broadphaseTree.root);
         scene->broadphaseTree.root = nullptr;
     }
 }
@@ -941,6 +1321,7 @@ extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
     {
         if (L.initialized) cudaDeviceSynchronize();
         L.scenes.erase(scene->broadphaseTree.root);
+        forget_scene_on_devices(scene->broadphaseTree.root);
     }
     scene->broadphaseTree.root = nullptr;
 
@@ -974,6 +1355,7 @@ extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
     FlatScene fs = flatten_scene(objects);
     std::unique_ptr<DeviceScene> ds = upload_scene(fs);
     void *handle = ds.get();
+    if (multi().active()) multi().flats[handle] = std::make_shared<FlatScene>(std::move(fs));
     scene->broadphaseTree.root = handle;
     scene->broadphaseTree.memoryPool.storage = nullptr;
     scene->broadphaseTree.memoryPool.objectSize = (u32)sizeof(Node4);
@@ -1379,8 +1761,10 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     u32 firstTileRow = rowBegin / tileH;
     u32 tileRows = (rowEnd - 1) / tileH - firstTileRow + 1;
 
+    const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL;
     SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
-    const DMaterials *dm = upload_materials(ctx->materialSystem);
+    // (the wavefront path waits for texture uploads where its first texture-reading kernel starts)
+    const DMaterials *dm = upload_materials(ctx->materialSystem, nullptr, wavefront);
     unsigned long long *ctr = reset_counters(tileRows);
 
     RenderArgs args;
@@ -1405,12 +1789,12 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
 
     std::vector<unsigned long long> c(CTR_COUNT + tileRows);
     std::vector<uint32_t> waveCounters;
-    const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL;
+    bool rowsStreamed = false;
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
     if (!wavefront)
         launch_render(kernel_config(), args, L.stream);
     else
-        render_wavefront(args, ds->instancedTriangles, waveCounters);
+        rowsStreamed = render_wavefront(args, ds->instancedTriangles, waveCounters, hostPixels);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
 
@@ -1418,13 +1802,15 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     if (!waveCounters.empty())
         SPB_CUDA(cudaMemcpyAsync(waveCounters.data(), L.wCtr.ptr, waveCounters.size() * 4,
                                  cudaMemcpyDeviceToHost, L.stream));
-    if (hostPixels)
+    if (hostPixels && !rowsStreamed)
     {
         size_t offset = (size_t)rowBegin * cam.width;
         SPB_CUDA(cudaMemcpyAsync(hostPixels + offset * 4, image + offset,
                                  (size_t)(rowEnd - rowBegin) * cam.width * 16,
                                  cudaMemcpyDeviceToHost, L.stream));
     }
+    // (rows that went out on the copy stream: the frame ends when the last of them has landed)
+    if (rowsStreamed) SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evCopyDone, 0));
     SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float kernelMs = 0, totalMs = 0;
@@ -1528,6 +1914,7 @@ static DImage device_image(const HdrImage *equirect)
     SPB_ASSERT(equirect && equirect->pixels && equirect->width > 0 && equirect->height > 0);
     DImage env;
     env.pixels = device_texture(*equirect);
+    wait_textures();
     env.width = equirect->width;
     env.height = equirect->height;
     env.pad = 0;
@@ -1633,11 +2020,122 @@ extern "C" int sp_b200_CreateIrradianceCubeMap(const HdrImage *equirect, u32 wid
     return 0;
 }
 
+// One frame over every device of sp_b200_InitDevices.  Each device renders a strip of rows cut at
+// multiples of tileHeight: the primary on the calling thread, the others on their worker threads,
+// all through sp_b200_RenderRows.  Output: hostPixels (each device copies its rows there itself,
+// over its own PCIe link) and / or primaryDevicePixels (the other devices send their strips with
+// peer copies: the gather of SURVEY.md §8e).  The cut of the NEXT frame is made from what this one
+// cost: per-row cost units scaled by each device's kernel time (spb_strips.h).
+static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, void *primaryDevicePixels, sp_Metrics *metrics)
+{
+    MultiDevice &M = multi();
+    std::lock_guard<std::mutex> lock(M.mutex);
+    Library &P = primary_lib();
+    const u32 parts = (u32)M.devices.size();
+    const u32 height = ctx->camera->imagePlane->height, width = ctx->camera->imagePlane->width;
+    const u32 quantum = P.params.tileHeight;
+    const u32 rows = (height + quantum - 1) / quantum;
+    if (M.nextBounds.size() == parts + 1 && M.height == height && M.quantum == quantum) M.bounds = M.nextBounds;
+    else
+    {
+        M.bounds.assign(parts + 1, 0);
+        partition_rows(height, quantum, parts, nullptr, M.bounds.data());
+        M.height = height;
+        M.quantum = quantum;
+    }
+    M.stats.assign(parts, sp_b200_Stats());
+    M.seconds.assign(parts, 0.0);
+    std::vector<sp_Metrics> partMetrics(parts);
+    std::vector<std::vector<u64>> partCost(parts);
+    std::vector<double> units(rows, 0.0);
+    memset(partMetrics.data(), 0, sizeof(sp_Metrics) * parts);
+    // what the host set on the primary holds for every device
+    struct Settings
+    {
+        sp_b200_Params params; bool stats, sky, sort, cand, one, overlap; uint32_t paths, sortBounces, refill[3];
+    } set = {P.params, P.statsEnabled, P.skyCulling, P.sortBounceRays, P.primaryCandidates, P.skyOneLookup, P.overlapCopies,
+             P.pathsPerPass, P.sortBounces, {P.refillThreshold[0], P.refillThreshold[1], P.refillThreshold[2]}};
+    const int primaryDevice = M.devices[0];
+    auto render_part = [&](u32 p) {
+        const u32 b = M.bounds[p], e = M.bounds[p + 1];
+        if (e <= b) return;
+        Library &L = lib();
+        if (p > 0)
+        {
+            L.params = set.params; L.statsEnabled = set.stats; L.skyCulling = set.sky; L.sortBounceRays = set.sort;
+            L.primaryCandidates = set.cand; L.skyOneLookup = set.one; L.overlapCopies = set.overlap;
+            L.pathsPerPass = set.paths; L.sortBounces = set.sortBounces;
+            for (int k = 0; k < 3; ++k) L.refillThreshold[k] = set.refill[k];
+        }
+        partCost[p].assign((e - 1) / quantum - b / quantum + 1, 0);
+        // the primary renders straight into the gathered image; the others into their own
+        void *device = p == 0 ? primaryDevicePixels : nullptr;
+        sp_b200_RenderRows(ctx, b, e, frame, hostPixels, device, &partMetrics[p], partCost[p].data());
+        if (p > 0 && primaryDevicePixels)
+        {
+            const size_t offset = (size_t)b * width * 16, bytes = (size_t)(e - b) * width * 16;
+            SPB_CUDA(cudaMemcpyPeerAsync((char *)primaryDevicePixels + offset, primaryDevice, (const char *)L.image.ptr + offset,
+                                         L.device, bytes, L.stream));
+            SPB_CUDA(cudaStreamSynchronize(L.stream));
+        }
+        M.stats[p] = L.lastStats;
+        M.seconds[p] = (double)L.lastStats.kernelMs * 1e-3;
+    };
+    for (u32 p = 1; p < parts; ++p) M.workers[p - 1]->post([&render_part, p] { render_part(p); });
+    render_part(0);
+    for (u32 p = 1; p < parts; ++p) M.workers[p - 1]->wait();
+
+    // metrics: counters add up, "cycles" (device nanoseconds) are the slowest device's
+    u64 slowest = 0;
+    for (u32 p = 0; p < parts; ++p)
+    {
+        if (metrics)
+            for (int k = 0; k < 12; ++k)
+                if (k != sp_Metric_CyclesElapsed) metrics->values[k] += partMetrics[p].values[k];
+        if (partMetrics[p].values[sp_Metric_CyclesElapsed] > slowest) slowest = partMetrics[p].values[sp_Metric_CyclesElapsed];
+        const u32 b = M.bounds[p], e = M.bounds[p + 1];
+        if (e <= b) continue;
+        const u32 first = b / quantum;
+        for (size_t i = 0; i < partCost[p].size() && first + i < rows; ++i) units[first + i] += (double)partCost[p][i];
+    }
+    if (metrics) metrics->values[sp_Metric_CyclesElapsed] = slowest;
+    // the whole frame's figures on the primary (sp_b200_GetLastStats); per device: sp_b200_GetDeviceStats
+    sp_b200_Stats total = M.stats[0];
+    for (u32 p = 1; p < parts; ++p)
+    {
+        const sp_b200_Stats &s = M.stats[p];
+        total.rays += s.rays; total.nodeVisits += s.nodeVisits; total.triangleTests += s.triangleTests;
+        total.objectTests += s.objectTests; total.envClampedLookups += s.envClampedLookups;
+        total.tracedRays += s.tracedRays; total.traceLaunches += s.traceLaunches;
+        if (s.kernelMs > total.kernelMs) total.kernelMs = s.kernelMs;
+        if (s.totalMs > total.totalMs) total.totalMs = s.totalMs;
+        if (s.traceMs > total.traceMs) total.traceMs = s.traceMs;
+    }
+    P.lastStats = total;
+    // next frame's cut
+    std::vector<double> cost = row_seconds(height, quantum, parts, M.bounds.data(), units.data(), M.seconds.data());
+    double sum = 0.0;
+    for (double c : cost) sum += c;
+    // (M.bounds / M.stats keep describing the frame just rendered: sp_b200_GetDeviceStats)
+    M.nextBounds = M.bounds;
+    if (sum > 0.0 && rows > parts) partition_rows(height, quantum, parts, cost.data(), M.nextBounds.data());
+    return 0;
+}
+
 extern "C" int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics)
 {
     SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
     ImagePlane *plane = ctx->camera->imagePlane;
+    if (multi().active() && !t_current) return render_frame_devices(ctx, frame, (f32 *)plane->pixels, nullptr, metrics);
     return sp_b200_RenderRows(ctx, 0, plane->height, frame, (f32 *)plane->pixels, nullptr, metrics, nullptr);
+}
+
+extern "C" int sp_b200_RenderFrameToDevice(sp_Context *ctx, u32 frame, void *devicePixels, sp_Metrics *metrics)
+{
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane && devicePixels);
+    ImagePlane *plane = ctx->camera->imagePlane;
+    if (multi().active() && !t_current) return render_frame_devices(ctx, frame, nullptr, devicePixels, metrics);
+    return sp_b200_RenderRows(ctx, 0, plane->height, frame, nullptr, devicePixels, metrics, nullptr);
 }
 
 extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng,

@@ -12,7 +12,7 @@
 
 namespace spb {
 
-unsigned long long g_kernelLaunches = 0;
+std::atomic<unsigned long long> g_kernelLaunches{0};
 
 __device__ __forceinline__ unsigned warp_sum(unsigned v)
 {

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "spb_bvh.h"
 #include "spb_core.cuh"
 
@@ -39,7 +41,7 @@ struct RenderArgs
 };
 
 // number of kernels this library has launched since load (bench.py's gpu_launches)
-extern unsigned long long g_kernelLaunches;
+extern std::atomic<unsigned long long> g_kernelLaunches; // (several host threads launch in multi-device mode)
 
 void launch_render(const KernelConfig &cfg, const RenderArgs &args, cudaStream_t stream);
 

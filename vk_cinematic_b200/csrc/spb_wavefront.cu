@@ -25,6 +25,9 @@
 // the per-pixel kernel and to the oracle in deterministic-math mode.
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
+#include <cstdio>
+#include <cstdlib>
+
 #include "spb_kernels.cuh"
 
 namespace spb {
@@ -1040,6 +1043,13 @@ static unsigned trace_grid_t()
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, PRIMARY>, SPB_TRACE_THREADS, 0);
         if (perSm < 1) perSm = 1;
         cached = (unsigned)(sms * perSm); // persistent: every CTA resident, a multiple of the SM count
+        // every warp in flight may leave one partly filled chunk in each queue: the slack the queues
+        // and ray arrays carry (spb_api.cu render_wavefront) must cover them all
+        if ((unsigned long long)cached * (SPB_TRACE_THREADS / 32) * SPB_CHUNK_MAX > SPB_QUEUE_SLACK)
+        {
+            fprintf(stderr, "[sp_b200] trace grid of %u CTAs needs more queue slack than SPB_QUEUE_SLACK provides\n", cached);
+            abort();
+        }
     }
     return cached;
 }

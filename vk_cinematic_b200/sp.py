@@ -14,7 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libspb200.so")
+# (development: SPB_B200_LIB points at another build of the same library, e.g. an A/B variant made
+# by tools/build_variants.sh; the product path is always the in-tree libspb200.so)
+LIB_PATH = os.environ.get("SPB_B200_LIB") or os.path.join(_HERE, "libspb200.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "sp_b200.h")
 
 U32_MAX = 0xFFFFFFFF
@@ -257,6 +259,13 @@ _SIGNATURES = {
     "sp_b200_AddRayTracingWorkQueue": (u32, [_P(WorkQueue), C.c_void_p]),
     "sp_b200_DrainRayTracingWorkQueue": (u32, [_P(WorkQueue), C.c_void_p, u32]),
     "sp_b200_Init": (C.c_int, [C.c_int]),
+    "sp_b200_InitDevices": (C.c_int, [u32]),
+    "sp_b200_InitDeviceList": (C.c_int, [C.c_void_p, u32]),
+    "sp_b200_DeviceCount": (u32, []),
+    "sp_b200_RenderFrameToDevice": (C.c_int, [C.c_void_p, u32, C.c_void_p, C.c_void_p]),
+    "sp_b200_GetDeviceStats": (C.c_int, [u32, C.c_void_p, _P(u32), _P(u32)]),
+    "sp_b200_PartitionRows": (None, [u32, u32, u32, C.c_void_p, C.c_void_p]),
+    "sp_b200_RowSeconds": (None, [u32, u32, u32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_Shutdown": (None, []),
     "sp_b200_SetLogCallback": (None, [C.c_void_p]),
     "sp_b200_SetStream": (None, [C.c_void_p]),
@@ -271,6 +280,7 @@ _SIGNATURES = {
     "sp_b200_SetSkyCulling": (None, [C.c_int]),
     "sp_b200_SetRaySorting": (None, [C.c_int]),
     "sp_b200_SetPrimaryCandidates": (None, [C.c_int]),
+    "sp_b200_SetCopyOverlap": (None, [C.c_int]),
     "sp_b200_SetRefillThresholds": (None, [u32, u32, u32]),
     "sp_b200_Seed": (u32, [u32, u32, u32]),
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,

@@ -8,8 +8,8 @@ of whole tile rows into its own image buffer and the finished strips are gathere
 the only exchange step of the path.  Strip boundaries are re-cut between frames from the
 measured per-tile-row cost.
 
-Host logic only; the transport is torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU
-tests).
+Host logic only: the cut is made by the library (sp_b200_PartitionRows); the transport is
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 import numpy as np
 
@@ -21,61 +21,20 @@ def tile_row_count(height, tile_h):
 def partition_rows(height, tile_h, world, cost=None):
     """Cut `height` pixel rows into `world` contiguous strips of whole tile rows.
 
-    cost: optional per-tile-row cost (length tile_row_count); strips get near-equal cost sums
-    (prefix-sum cuts), every strip keeps at least one tile row while rows last.
+    cost: optional per-tile-row cost (length tile_row_count): the cut then minimises the largest
+    strip's summed cost (the step takes as long as the slowest rank); every strip keeps at least
+    one tile row while rows last.  The arithmetic is the library's (sp_b200_PartitionRows,
+    csrc/spb_strips.cpp): the same cut the single-process multi-device path of libspb200 makes.
     Returns a list of (row_begin, row_end) pixel rows, one per rank; trailing ranks may be empty
     when there are fewer tile rows than ranks."""
-    rows = tile_row_count(height, tile_h)
-    if cost is not None and rows > world > 1:
-        cuts = _minmax_cuts(np.asarray(cost, dtype=np.float64), world)
-        return [(min(cuts[i] * tile_h, height), min(cuts[i + 1] * tile_h, height)) for i in range(world)]
-    if cost is None:
-        cost = np.ones(rows, dtype=np.float64)
-    cost = np.asarray(cost, dtype=np.float64)
-    assert len(cost) == rows
-    cost = np.maximum(cost, 1e-9 * max(1.0, float(cost.max()) if rows else 1.0))
-    prefix = np.concatenate([[0.0], np.cumsum(cost)])
-    total = prefix[-1]
-    cuts = [0]
-    for r in range(1, world):
-        target = total * r / world
-        # first boundary whose prefix is closest to the target
-        k = int(np.searchsorted(prefix, target))
-        if k > 0 and abs(prefix[k - 1] - target) <= abs(prefix[min(k, rows)] - target):
-            k -= 1
-        lo = min(cuts[-1] + 1, rows)              # at least one tile row per strip ...
-        hi = max(lo, rows - (world - r))          # ... and leave one for each later strip
-        cuts.append(int(min(max(k, lo), hi)))
-    cuts.append(rows)
-    return [(min(cuts[i] * tile_h, height), min(cuts[i + 1] * tile_h, height)) for i in range(world)]
-
-
-def _minmax_cuts(cost, world):
-    """Contiguous partition of `cost` into `world` non-empty strips with the smallest possible
-    largest strip sum (the step time is the slowest rank's): dynamic programme over (strips used,
-    rows covered), vectorised over the position of the last cut.  The prefix-closest-to-target
-    cuts used before sit up to half a row off per boundary, which at 8 strips of ~17 rows each was
-    a 10 % imbalance on a centre-heavy frame; this is the optimum for the given granularity."""
-    rows = len(cost)
-    assert rows >= world
-    cost = np.maximum(cost, 1e-9 * max(1.0, float(cost.max())))
-    prefix = np.concatenate([[0.0], np.cumsum(cost)])
-    best = np.full((world + 1, rows + 1), np.inf)
-    arg = np.zeros((world + 1, rows + 1), dtype=np.int64)
-    best[0, 0] = 0.0
-    for k in range(1, world + 1):
-        for i in range(k, rows - (world - k) + 1):
-            j = np.arange(k - 1, i)
-            v = np.maximum(best[k - 1, k - 1:i], prefix[i] - prefix[j])
-            m = int(np.argmin(v))
-            best[k, i] = v[m]
-            arg[k, i] = j[m]
-    cuts = [rows]
-    i = rows
-    for k in range(world, 0, -1):
-        i = int(arg[k, i])
-        cuts.append(i)
-    return cuts[::-1]
+    from . import sp
+    bounds = np.zeros(world + 1, np.uint32)
+    c = None
+    if cost is not None:
+        c = np.ascontiguousarray(cost, dtype=np.float64)
+        assert len(c) == tile_row_count(height, tile_h)
+    sp.lib.sp_b200_PartitionRows(height, tile_h, world, c.ctypes.data if c is not None else None, bounds.ctypes.data)
+    return [(int(bounds[i]), int(bounds[i + 1])) for i in range(world)]
 
 
 def strip_cost_to_row_cost(bounds, strip_costs, height, tile_h):
