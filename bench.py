@@ -73,6 +73,9 @@ def parse_args():
                     help="development: mesh trees from the device LBVH builder (sp_b200_SetMeshBuilder); default: host SAH")
     ap.add_argument("--quick", action="store_true", help="development: value only (no e2e, roofline, cpu baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity block")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C5 secondary block")
+    ap.add_argument("--no-copy-overlap", action="store_true", help="development: sp_b200_SetCopyOverlap(0)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -218,7 +221,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from vk_cinematic_b200 import workloads as W
+    # workloads.py alone, by path: importing the package would map libspb200.so into a process that
+    # must not contain any of the product (the driver records the .so files each arm loaded)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spb_workloads", os.path.join(ROOT, "vk_cinematic_b200", "workloads.py"))
+    W = importlib.util.module_from_spec(spec)
+    sys.modules["spb_workloads"] = W
+    spec.loader.exec_module(W)
     wl = W.config3(args.width, args.height, spp=args.spp, bounces=args.bounces)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import ora
@@ -275,6 +284,144 @@ def claim_stdout():
     return real
 
 
+def load_json(*parts):
+    try:
+        return json.load(open(os.path.join(ROOT, *parts)))
+    except Exception:
+        return None
+
+
+def on_chip_peaks(bvh_bytes):
+    """L2 / L1 read peaks of this pool's B200 measured by tools/l2_peak.cu (committed sweep,
+    profiles/r2/l2_peak_sweep.json): the L2 figure for the smallest swept working set that holds the
+    scene's BVH (what the traversal re-reads), the plateau over the large sets, the L1 figure."""
+    lp = load_json("profiles", "r2", "l2_peak_sweep.json")
+    if not lp:
+        return None
+    sweep = {int(k.replace("MiB", "")): float(v) for k, v in lp["l2_cg_16B_GBs"].items()}
+    sizes = sorted(sweep)
+    fit = next((m for m in sizes if m * (1 << 20) >= bvh_bytes), sizes[-1])
+    plateau = min(sweep[m] for m in sizes if m >= 16)
+    return {"l2_read_peak": sweep[fit], "l2_working_set_mib": fit, "l2_sweep_GBs": sweep, "l2_plateau_16_to_96_mib": plateau,
+            "l1_read_peak": float(lp["l1_64KiB_per_cta_GBs"]), "hbm_read_peak": float(lp["hbm_1GiB_GBs"]),
+            "source": "profiles/r2/l2_peak_sweep.json (tools/l2_peak.cu: ld.global.cg read sweeps, 2-96 MiB working sets, measured)"}
+
+
+def roofline_block(sp, args, r, bounds, rank, image_ptr, frame, timed_trace, world, kernel_ms, workload, scene_bytes):
+    """Roofline of the dominant kernel (k_trace: BVH traversal + triangle tests; every launch of a step is
+    timed with CUDA events inside the library).  A stats launch of one frame counts I and L."""
+    trace_ms = float(np.mean([t[0] for t in timed_trace])) if timed_trace else 0.0
+    trace_launches = int(np.mean([t[1] for t in timed_trace])) if timed_trace else 0
+    traced_rays = float(np.mean([t[2] for t in timed_trace])) if timed_trace else 0.0
+    sp.lib.sp_b200_EnableStats(1)
+    b, e = bounds[rank]
+    st = None
+    if e > b:
+        r.render_rows(b, e, frame=frame, host=False, device_ptr=image_ptr)
+        st = sp.last_stats()
+    sp.lib.sp_b200_EnableStats(0)
+    if st is None or trace_ms <= 0:
+        return None
+    srays = max(1, int(st.tracedRays))
+    I, L = st.nodeVisits / srays, st.triangleTests / srays
+    # traversal: per traced ray 128 I + 48 L + 64 (SURVEY.md §8d); sky-kernel samples never enter the
+    # traversal kernel and are not counted
+    per_ray = 128.0 * I + 48.0 * L + 64.0
+    bytes_per_step = per_ray * traced_rays
+    achieved = bytes_per_step / (trace_ms * 1e-3) / 1e9
+    hbm_peak, which = measured_peak()
+    chip = on_chip_peaks(scene_bytes)
+    # DRAM traffic per launch from the committed ncu capture of this workload (1 GPU, whole frame);
+    # with several ranks a launch covers a strip: scaled by traced rays (per-ray DRAM bytes are a
+    # property of the kernel and the queues, not of the strip)
+    traffic, traffic_how = None, None
+    tr = load_json("profiles", "r2", f"trace_traffic_{workload}.json")
+    if tr and tr.get("spp") == args.spp and tr.get("width") == args.width and tr.get("launches") and tr.get("traced_rays_per_step"):
+        per_traced_ray = float(tr["dram_bytes_per_step"]) / float(tr["traced_rays_per_step"])
+        traffic = per_traced_ray * traced_rays / max(1, trace_launches)
+        traffic_how = ("ncu dram__bytes_read+write of every k_trace launch of one frame (profiles/r2/trace_traffic_%s.json), "
+                       "per launch%s" % (workload, "" if world == 1 else "; scaled to this rank's traced rays"))
+    out = {"bound": "l2", "achieved": achieved, "unit": "GB/s",
+           "peak": chip["l2_read_peak"] if chip else None,
+           "frac": achieved / chip["l2_read_peak"] if chip else None,
+           "peak_source": ("measured L2 read peak (tools/l2_peak.cu) for a %d MiB working set, the smallest swept set that holds "
+                           "the scene's %.1f MB of nodes and triangles" % (chip["l2_working_set_mib"], scene_bytes / 1e6)) if chip else "unavailable",
+           "traffic": traffic, "traffic_source": traffic_how,
+           "kernel": "k_trace (BVH traversal + triangle tests)",
+           "launches_per_step": trace_launches, "kernel_ms_per_step": trace_ms,
+           "step_kernels_ms": float(np.mean(kernel_ms)) if kernel_ms else 0.0,
+           "avg_launch_ms": trace_ms / max(1, trace_launches),
+           "algorithmic_bytes_per_launch": bytes_per_step / max(1, trace_launches),
+           "traced_rays_per_step": traced_rays, "traversal_grays_per_s": traced_rays / (trace_ms * 1e-3) / 1e9,
+           "node_visits_per_ray": I, "triangle_tests_per_ray": L, "algorithmic_bytes_per_ray": per_ray,
+           "hbm": {"peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": which,
+                   "note": "context only: the BVH is served from L1/L2; DRAM sees the ray and hit-record queues (traffic)"},
+           "on_chip": chip,
+           "note": "achieved = algorithmic bytes (128 I + 48 L + 64 per traced ray, I and L counted by the kernel) of the step's "
+                   "k_trace launches / their summed CUDA-event time.  The kernel is bound by instruction issue, not by a memory "
+                   "level (profiles/r2/README.md: lanes per instruction x issue-slot utilisation); the L2 fraction is what "
+                   "SURVEY.md §8d asks to be reported"}
+    if chip:
+        out["frac_of_l2_plateau"] = achieved / chip["l2_plateau_16_to_96_mib"]
+        out["frac_of_l1_read_peak"] = achieved / chip["l1_read_peak"]
+    return out
+
+
+def parity_block(sp, W, args, render_full_frame, rank):
+    """Whole-frame parity of what this run's library renders, against the committed fingerprints of the CPU
+    checkers (tests/golden/g5, g6: made by tools/make_full_frame_golden.py from the unmodified reference
+    and the restatement; no checker is called here).  Every rank renders its strip; rank 0 compares."""
+    from vk_cinematic_b200.fixtures import lattice, relative_error_report, tile_crcs
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "g5_c3_full_frame.npz"))
+    out = {}
+
+    def compare(image, key, ties):
+        crc = tile_crcs(image)
+        want = gold["tile_crc_" + key]
+        bad = np.nonzero(crc != want)[0]
+        tx = (image.shape[1] + 63) // 64
+        tie_tiles = set(int(y // 64) * tx + int(x // 64) for x, y in gold[ties])
+        return {"tiles": int(len(want)), "tiles_differing": int(len(bad)),
+                "tiles_differing_without_a_tie_pixel": int(sum(1 for t in bad if int(t) not in tie_tiles)),
+                "tie_pixels_in_frame": int(len(gold[ties])), "pixels": int(image.shape[0] * image.shape[1])}
+
+    img5, m5 = render_full_frame(5, 0)
+    if rank == 0:
+        out["c3_5_bounces_vs_port_dm"] = compare(img5, "port_dm_5b", "ties_5b")
+        out["c3_5_bounces_vs_port_dm"]["rays"] = [int(m5), int(gold["metrics_port_dm_5b"][1])]
+    img3, m3 = render_full_frame(3, 0)
+    if rank == 0:
+        out["c3_3_bounces_vs_reference_dm"] = compare(img3, "ref_dm_3b", "ties_3b")
+        out["c3_3_bounces_vs_reference_dm"]["rays"] = [int(m3), int(gold["metrics_ref_dm_3b"][1])]
+        rep = relative_error_report(lattice(img3), gold["lattice_ref_3b"])
+        rep["what"] = ("deterministic-math render vs the unmodified reference with glibc libm, 3 bounces, on the fixture's lattice "
+                       "of every 16th pixel; stated tolerance: <= 2 % of pixels off by > 1e-3 relative, RMSE <= 2 % of mean radiance")
+        out["c3_3_bounces_vs_plain_reference"] = rep
+    return out
+
+
+def c2_parity(sp, W, local):
+    """BASELINE configs[1] (monkey, 1920x1080, primary rays): closest-hit triangle ids, distances and object
+    ids against the fingerprint of the unmodified reference's (tests/golden/g6_c2_full_frame.npz)."""
+    from vk_cinematic_b200.fixtures import tile_crcs
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "g6_c2_full_frame.npz"))
+    wl = W.config2()
+    r = sp.Renderer(local).load_workload(wl)
+    t0 = time.perf_counter()
+    g = r.primary_hits(sample=0, frame=0)
+    secs = time.perf_counter() - t0
+    st = sp.last_stats()
+    r.close()
+    tri_off = int((tile_crcs(g["tri"]) != gold["tile_crc_tri"]).sum())
+    return {"rays": int(g["tri"].size), "hit_pixels": [int((g["tri"] >= 0).sum()), int(gold["hit_pixels"])],
+            "tiles": int(len(gold["tile_crc_tri"])), "tiles_with_differing_triangle_ids": tri_off,
+            "tiles_with_differing_t_bits": int((tile_crcs(g["t"]) != gold["tile_crc_t"]).sum()),
+            "tiles_with_differing_object_ids": int((tile_crcs(g["obj"]) != gold["tile_crc_obj"]).sum()),
+            "triangle_id_mismatch_rate_bound": tri_off * 4096 / g["tri"].size,
+            "stated_bound": 1e-4, "kernel_ms": st.kernelMs, "primary_mrays_per_s": g["tri"].size / max(st.kernelMs, 1e-9) / 1e3,
+            "call_seconds": secs}
+
+
 def main():
     args = parse_args()
     global RESULT_OUT
@@ -302,24 +449,44 @@ def main():
     stream = torch.cuda.current_stream()
     sp.lib.sp_b200_SetStream(stream.cuda_stream)
 
-    if args.workload == "c3":
-        wl = W.config3(args.width, args.height, spp=args.spp, bounces=args.bounces)
-    else:
-        wl = W.config5(args.width, args.height, spp=args.spp, bounces=args.bounces,
-                       unique_spheres=args.workload == "c5u")
+    def make_workload(name, width, height, spp, bounces):
+        if name == "c3":
+            return W.config3(width, height, spp=spp, bounces=bounces)
+        return W.config5(width, height, spp=spp, bounces=bounces, unique_spheres=name == "c5u")
+
+    wl = make_workload(args.workload, args.width, args.height, args.spp, args.bounces)
     H, Wd = wl.height, wl.width
-    # pinned host buffers: environment map (input) and the image plane (output)
+    # pinned host buffers: environment map (input) and the image plane (output).  With several ranks the
+    # image plane is ONE pinned buffer shared by all processes (a file in /dev/shm mapped by every rank
+    # and registered with cudaHostRegister): each GPU copies its own rows there over its own PCIe link.
     env_key = W.IMAGE_ENV
     env_pinned = torch.from_numpy(wl.textures[env_key]).pin_memory()
     wl.textures[env_key] = env_pinned.numpy()
-    host_image = torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory()
+    shared_path = None
+    if world > 1:
+        name = [f"/dev/shm/spb200_frame_{os.getpid()}"] if rank == 0 else [None]
+        dist.broadcast_object_list(name, src=0)
+        shared_path = name[0]
+        if rank == 0:
+            with open(shared_path, "wb") as f:
+                f.truncate(H * Wd * 16)
+        dist.barrier()
+        host_np = np.memmap(shared_path, dtype=np.float32, mode="r+", shape=(H, Wd, 4))
+        host_image = torch.from_numpy(host_np)
+        rc = torch.cuda.cudart().cudaHostRegister(host_image.data_ptr(), host_image.numel() * 4, 0)
+        assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
+    else:
+        host_image = torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory()
     if args.device_builder:
         sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_DEVICE_LBVH)
     r = sp.Renderer(local).load_workload(wl, pixels=host_image.numpy())
     sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_HOST_SAH)
-    sp.set_params(samplesPerPixel=args.spp, bounceCount=args.bounces, cullByDistance=1,
-                  mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=args.strip_rows,
-                  renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
+
+    def set_render_params(spp, bounces):
+        sp.set_params(samplesPerPixel=spp, bounceCount=bounces, cullByDistance=1,
+                      mathMode=args.math, envFilter=0, radianceClamp=10.0, tileWidth=64, tileHeight=args.strip_rows,
+                      renderMode=args.render_mode, samplesPerPass=args.samples_per_pass)
+    set_render_params(args.spp, args.bounces)
     if args.paths_per_pass:
         sp.lib.sp_b200_SetPathsPerPass(args.paths_per_pass)
     if args.no_ray_sorting:
@@ -330,8 +497,14 @@ def main():
         sp.lib.sp_b200_SetRaySorting(args.sort_bounces)
     if args.refill:
         sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
-    TH = args.strip_rows   # strip boundaries and cost accounting: rows of 16 pixels (a quarter tile)
-    image = torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev)
+    if args.no_copy_overlap:
+        sp.lib.sp_b200_SetCopyOverlap(0)
+    TH = args.strip_rows   # strip boundaries and cost accounting: rows of TH pixels
+    # Two device images, used alternately: the strips of frame k are on their way to rank 0 (NCCL, on
+    # its own stream) while frame k + 1 renders into the other one.
+    images = [torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    gathered = [torch.cuda.Event() for _ in images]
 
     def barrier():
         torch.cuda.synchronize()
@@ -341,8 +514,25 @@ def main():
 
     gather_ev = []
     trace_log = []
+    step_counter = [0]
 
-    def render_step(frame, bounds, want_cost=False):
+    def gather_async(image, bounds, slot):
+        """The one exchange step: strips to rank 0, one batched send/recv group on the
+        communication stream; the render stream goes on with the next frame."""
+        comm.wait_stream(stream)
+        with torch.cuda.stream(comm):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(comm)
+            strips.gather_strips(image, bounds, dist)
+            g1.record(comm)
+            gathered[slot].record(comm)
+        gather_ev.append((g0, g1))
+
+    def render_step(frame, bounds, want_cost=False, wait_gather=False):
+        slot = step_counter[0] % len(images)
+        step_counter[0] += 1
+        image = images[slot]
+        stream.wait_event(gathered[slot])        # this buffer's previous strips have left
         b, e = bounds[rank]
         m, cost = np.zeros(12, np.uint64), None
         if e > b:
@@ -350,24 +540,20 @@ def main():
                                     want_cost=want_cost)
         st = sp.last_stats()
         if world > 1:
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            strips.gather_strips(image, bounds, dist)
-            g1.record()
-            gather_ev.append((g0, g1))
+            gather_async(image, bounds, slot)
+            if wait_gather:
+                stream.wait_stream(comm)
         trace_log.append((st.traceMs, st.traceLaunches, int(st.tracedRays)) if e > b else (0.0, 0, 0))
-        return m, cost, (st.kernelMs if e > b else 0.0)
+        return m, cost, (st.kernelMs if e > b else 0.0), image
 
-    # ---- warm-up (also measures per-tile-row cost and re-cuts the strips)
+    # ---- warm-up (also measures per-row cost and re-cuts the strips: every warm-up frame is one
+    # iteration of the rebalancing)
     bounds = strips.partition_rows(H, TH, world)
     frame = 0
-    # with several ranks every warm-up frame is also one iteration of the strip rebalancing (re-cut
-    # from measured cost); 3 iterations from an even split did not converge at N = 8 (ranks at
-    # 3.7-11.0 ms, profiles/r02r_bench_n8.json), so multi-rank runs take at least 8
-    warmups = max(args.warmup, 3) if world == 1 else max(args.warmup, 8)
+    warmups = max(args.warmup, 3)
     for w in range(warmups):
         barrier()
-        m, cost, kms = render_step(frame, bounds, want_cost=True)
+        m, cost, kms, _ = render_step(frame, bounds, want_cost=True, wait_gather=True)
         torch.cuda.synchronize()
         frame += 1
         if world > 1:
@@ -391,20 +577,24 @@ def main():
     ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
     for k in range(args.steps):
-        m, _, kms = render_step(frame, bounds)
+        m, _, kms, _ = render_step(frame, bounds)
         rays += int(m[sp.sp_Metric_RaysTraced])
         kernel_ms.append(kms)
         frame += 1
+    if world > 1:
+        stream.wait_stream(comm)                 # the last strips have arrived
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = sp.lib.sp_b200_KernelLaunchCount() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
-    stat = torch.tensor([elapsed_ms, float(rays), float(launches), float(np.sum(kernel_ms))],
+    timed_trace = list(trace_log[:args.steps])
+    traced = float(np.sum([t[2] for t in timed_trace]))
+    stat = torch.tensor([elapsed_ms, float(rays), float(launches), float(np.sum(kernel_ms)), traced],
                         dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
-        gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev])) if gather_ev else 0.0
+        gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev[:args.steps]])) if gather_ev else 0.0
         mine = torch.tensor([float(np.mean(kernel_ms)), gather_ms, float(rays) / args.steps], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
@@ -413,25 +603,9 @@ def main():
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stat.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed_ms, rays, launches = float(mx[0]), float(sm[1]), float(sm[2])
+        elapsed_ms, rays, launches, traced = float(mx[0]), float(sm[1]), float(sm[2]), float(sm[4])
     value = rays / (elapsed_ms * 1e-3) / 1e6
 
-    # ---- e2e: host buffers, copies inside the timed region
-    def e2e_step(frame):
-        b, e = bounds[rank]
-        sp.lib.sp_b200_FlushTextureCache()           # env map + materials re-uploaded
-        r.build()                                     # scene flattened and re-uploaded
-        m = np.zeros(12, np.uint64)
-        if world == 1:
-            _, m = r.render_frame(frame=frame)        # D2H of the finished frame into pinned host
-        else:
-            if e > b:
-                m, _ = r.render_rows(b, e, frame=frame, host=False, device_ptr=image.data_ptr())
-            strips.gather_strips(image, bounds, dist)
-            if rank == 0:
-                host_image.copy_(image, non_blocking=True)
-                torch.cuda.synchronize()
-        return m
     if args.quick:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": float(np.mean(kernel_ms)),
@@ -441,8 +615,43 @@ def main():
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+            if rank == 0:
+                os.unlink(shared_path)
         return
-    scene_bytes = int(env_pinned.numel() * 4) + int(sp.lib.sp_b200_SceneDeviceBytes(r.scene)) + 2048
+
+    # ---- e2e: host buffers, copies inside the timed region.  Every step: the scene is flattened and
+    # uploaded again (sp_BuildSceneBroadphase), the environment map and the material table go to the
+    # device again (texture cache flushed), the strip is rendered, and its rows are copied to the pinned
+    # host image (band by band on the copy stream while later bands render).  With several ranks every
+    # rank uploads one slice of the environment map and an NCCL all-gather over NVLink assembles the
+    # copies (sp_b200_SetDeviceTexture), and every rank writes its rows into the shared host image.
+    env_flat = env_pinned.view(-1)
+    env_dev = torch.empty_like(env_flat, device=dev) if world > 1 else None
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    env_ready = torch.cuda.Event() if world > 1 else None
+    eh, ew = wl.textures[env_key].shape[0], wl.textures[env_key].shape[1]
+
+    def e2e_step(frame):
+        b, e = bounds[rank]
+        sp.lib.sp_b200_FlushTextureCache()           # env map + materials re-uploaded
+        if world > 1:
+            n = env_flat.numel() // world
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                lo, hi = rank * n, (rank + 1) * n
+                env_dev[lo:hi].copy_(env_flat[lo:hi], non_blocking=True)
+                dist.all_gather_into_tensor(env_dev[:n * world], env_dev[lo:hi])
+                if n * world < env_flat.numel():
+                    env_dev[n * world:].copy_(env_flat[n * world:], non_blocking=True)
+                env_ready.record(side)
+            sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), env_dev.data_ptr(), ew, eh, env_ready.cuda_event)
+        r.build()                                     # scene flattened and re-uploaded
+        m = np.zeros(12, np.uint64)
+        if e > b:
+            m, _ = r.render_rows(b, e, frame=frame, host=True)   # rows -> pinned host image
+        if world > 1:
+            dist.barrier()                            # the frame is complete in host memory
+        return m
     for _ in range(2):
         e2e_step(frame)
         frame += 1
@@ -455,6 +664,9 @@ def main():
         frame += 1
     barrier()
     e2e_secs = time.perf_counter() - t0
+    if world > 1:
+        sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), None, 0, 0, None)
+        sp.lib.sp_b200_FlushTextureCache()
     est = torch.tensor([e2e_secs, float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         a = est.clone()
@@ -463,89 +675,83 @@ def main():
         dist.all_reduce(b_, op=dist.ReduceOp.SUM)
         e2e_secs, e2e_rays = float(a[0]), float(b_[1])
     e2e_value = e2e_rays / e2e_secs / 1e6
+    scene_bytes = int(sp.lib.sp_b200_SceneDeviceBytes(r.scene))
+    env_bytes = int(env_pinned.numel() * 4)
+    h2d = (scene_bytes + 2048) * world + env_bytes * (1 if world > 1 else 1)
 
-    # ---- roofline of the dominant kernel (k_trace, the traversal kernel; all its launches of a
-    # step are timed with CUDA events inside the library): a stats launch of one frame counts I, L
-    roofline = None
+    # ---- roofline of the dominant kernel
+    roofline = roofline_block(sp, args, r, bounds, rank, images[0].data_ptr(), frame - 1, timed_trace, world, kernel_ms,
+                              args.workload, scene_bytes) if rank == 0 else None
+    if world > 1 and rank != 0:
+        # (the stats frame above is rank 0's alone; nothing to do here)
+        pass
+
+    # ---- parity of this run's frames against the committed fingerprints (untimed)
+    parity = None
+    if not args.no_parity and args.workload == "c3" and (args.width, args.height, args.spp, args.math) == (3840, 2160, 64, 0):
+        def render_full_frame(bounces, fr):
+            set_render_params(args.spp, bounces)
+            m, _, _, image = render_step(fr, bounds, wait_gather=True)
+            torch.cuda.synchronize()
+            total = torch.tensor([float(m[sp.sp_Metric_RaysTraced])], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(total)
+            return (image.cpu().numpy() if rank == 0 else None), float(total[0])
+        try:
+            parity = parity_block(sp, W, args, render_full_frame, rank)
+            set_render_params(args.spp, args.bounces)
+            if rank == 0:
+                parity["c2_primary_rays_vs_reference"] = c2_parity(sp, W, local)
+        except Exception as ex:   # a missing fixture must not cost the bench line
+            parity = {"error": repr(ex)}
+        set_render_params(args.spp, args.bounces)
+
+    # ---- secondary: BASELINE configs[4] (C5), time-bounded, same strips machinery
+    secondary = {}
+    if not args.no_secondary and args.workload == "c3":
+        try:
+            secondary["c5"] = secondary_c5(sp, W, strips, args, rank, world, local, dev, dist if world > 1 else None, torch)
+        except Exception as ex:
+            secondary["c5"] = {"error": repr(ex)}
     cpu = None
-    if rank == 0:
-        timed_trace = trace_log[:args.steps]
-        trace_ms = float(np.mean([t[0] for t in timed_trace])) if timed_trace else 0.0
-        trace_launches = int(np.mean([t[1] for t in timed_trace])) if timed_trace else 0
-        traced_rays = float(np.mean([t[2] for t in timed_trace])) if timed_trace else 0.0
-        sp.lib.sp_b200_EnableStats(1)
-        b, e = bounds[rank]
-        m, _ = r.render_rows(b, e, frame=frame - 1, host=False, device_ptr=image.data_ptr())
-        st = sp.last_stats()
-        sp.lib.sp_b200_EnableStats(0)
-        srays = max(1, int(st.tracedRays))
-        I, L = st.nodeVisits / srays, st.triangleTests / srays
-        # traversal: per traced ray 128 I + 48 L + 64; sky-kernel samples never
-        # enter the traversal kernel and are not counted
-        per_ray = 128.0 * I + 48.0 * L + 64.0
-        bytes_per_step = per_ray * traced_rays
-        achieved = bytes_per_step / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-        peak, which = measured_peak()
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "trace_traffic.json")))
-            if tr.get("workload") == args.workload and tr.get("spp") == args.spp and tr.get("width") == args.width \
-                    and world == 1 and tr.get("launches"):
-                traffic = float(tr["dram_bytes_per_step"]) / float(tr["launches"])
-        except Exception:
-            pass
-        # on-chip read peaks of this pool's B200 (tools/l2_peak.cu, committed result): the levels the
-        # resident BVH is actually served from
-        onchip = {}
-        try:
-            lp = json.load(open(os.path.join(ROOT, "profiles", "r03b_l2_peak.json")))
-            l2_peak = max(float(lp["l2_16MiB_GBs"]), float(lp["l2_48MiB_GBs"]))
-            onchip = {"l2_read_peak": l2_peak, "frac_of_l2_read_peak": achieved / l2_peak,
-                      "l1_read_peak": float(lp["l1_64KiB_per_cta_GBs"]),
-                      "frac_of_l1_read_peak": achieved / float(lp["l1_64KiB_per_cta_GBs"]),
-                      "source": "profiles/r03b_l2_peak.json (tools/l2_peak.cu: 16-byte read sweeps, measured)"}
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "on_chip": onchip,
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": which,
-                    "kernel": "k_trace (BVH traversal + triangle tests)",
-                    "launches_per_step": trace_launches,
-                    "kernel_ms_per_step": trace_ms, "step_kernels_ms": float(np.mean(kernel_ms)) if kernel_ms else 0.0,
-                    "avg_launch_ms": trace_ms / max(1, trace_launches),
-                    "algorithmic_bytes_per_launch": bytes_per_step / max(1, trace_launches),
-                    "traced_rays_per_step": traced_rays,
-                    "node_visits_per_ray": I, "triangle_tests_per_ray": L,
-                    "algorithmic_bytes_per_ray": per_ray,
-                    "note": "achieved = algorithmic bytes of the step's k_trace launches / their summed CUDA-event time; "
-                            "traffic = DRAM bytes per launch from the ncu capture under profiles/ (the 1.3 MB BVH is "
-                            "L1/L2-resident, so DRAM traffic is the ray and hit-record queues); the fraction is of the "
-                            "HBM copy peak although the bytes are served from L1/L2"}
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_time_sample(args, wl, args.cpu_seconds, "port")
-            cpu.pop("tiles", None)
-            cpu.pop("rays", None)
-            cpu.pop("seconds", None)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_time_sample(args, wl, args.cpu_seconds, "port")
+        cpu.pop("tiles", None)
+        cpu.pop("rays", None)
+        cpu.pop("seconds", None)
 
     if rank == 0:
+        ms = elapsed_ms / args.steps
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmups, "ms_per_step": elapsed_ms / args.steps,
-            "s_per_frame": elapsed_ms / args.steps * 1e-3,
+            "steps": args.steps, "warmup": warmups, "ms_per_step": ms,
+            "s_per_frame": ms * 1e-3,
+            "value_traced_only": traced / (elapsed_ms * 1e-3) / 1e6,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
-            "rays_per_step": rays / args.steps,
-            "rays_accounting": "rays = the reference's sp_Metric_RaysTraced for the same frame (one per "
-                               "sp_RayIntersectScene call it would make, simd_path_tracer.cpp:242); camera rays of "
-                               "pixels the coverage pass proves empty are counted but never traced (sky kernel); "
-                               "roofline.traced_rays_per_step is what went through the traversal kernel",
+            "rays_per_step": rays / args.steps, "traced_rays_per_step": traced / args.steps,
+            "rays_accounting": "value counts the reference's rays for the same frame (sp_Metric_RaysTraced: one per "
+                               "sp_RayIntersectScene call it makes, simd_path_tracer.cpp:242), which is what makes it comparable "
+                               "with the CPU arm: both divide the same count by their own time.  Camera rays of pixels the "
+                               "coverage pass proves empty are settled by the sky kernel (bit-identical result) and never "
+                               "enter the traversal kernel: value_traced_only counts only rays that did; s_per_frame does not "
+                               "depend on the accounting",
             "e2e": {"value": e2e_value, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": scene_bytes * world,
-                    "d2h_bytes_per_step": H * Wd * 16, "ms_per_step": e2e_secs / args.steps * 1e3},
+                    "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": H * Wd * 16, "ms_per_step": e2e_secs / args.steps * 1e3,
+                    "how": "per step: texture cache flushed, scene re-built and re-uploaded, environment map re-uploaded "
+                           + ("(one slice per rank + NCCL all-gather), rows copied by every rank into one shared pinned host image, barrier"
+                              if world > 1 else "(copy stream, overlapped with coverage / candidates / first primary trace), "
+                              "rows copied to the pinned host image band by band while later bands render")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "strips": [list(map(int, b)) for b in bounds],
         }
         if per_rank is not None:
             out["ranks"] = per_rank
+        if parity is not None:
+            out["parity"] = parity
+        if secondary:
+            out["secondary"] = secondary
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), file=RESULT_OUT, flush=True)
@@ -553,6 +759,106 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            try:
+                os.unlink(shared_path)
+            except OSError:
+                pass
+
+
+def secondary_c5(sp, W, strips, args, rank, world, local, dev, dist, torch):
+    """BASELINE configs[4]: 64 bunnies + 118 level-6 icospheres (9.98 M instanced triangles), 3840x2160,
+    16 spp, 5 bounces -- the configuration the reference cannot hold (32-object table, sp_scene.h:15).
+    Same strips, same kernels; 2 warm-up + 3 timed frames per rank, device time, max over ranks."""
+    wl = W.config5(3840, 2160, spp=16, bounces=5)
+    H, Wd, TH = wl.height, wl.width, args.strip_rows
+    t0 = time.perf_counter()
+    r = sp.Renderer(local).load_workload(wl)
+    build_s = time.perf_counter() - t0
+    sp.set_params(samplesPerPixel=16, bounceCount=5, cullByDistance=1, mathMode=args.math, envFilter=0, radianceClamp=10.0,
+                  tileWidth=64, tileHeight=TH, renderMode=0, samplesPerPass=0)
+    image = torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev)
+    bounds = strips.partition_rows(H, TH, world)
+    frame = 100
+
+    def step(want_cost):
+        b, e = bounds[rank]
+        m, cost, kms, st = np.zeros(12, np.uint64), None, 0.0, None
+        if e > b:
+            m, cost = r.render_rows(b, e, frame=frame, host=False, device_ptr=image.data_ptr(), want_cost=want_cost)
+            st = sp.last_stats()
+            kms = st.kernelMs
+        return m, cost, kms, st
+    for _ in range(2):
+        m, cost, kms, _ = step(True)
+        frame += 1
+        if world > 1:
+            row_cost, _ = strips.gather_row_costs(cost if cost is not None else np.zeros(0), kms * 1e-3, bounds, H, TH, dist, dev)
+            bounds = strips.partition_rows(H, TH, world, row_cost)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    rays, kms_all, trace_ms, traced, launches = 0, [], [], 0, []
+    for _ in range(3):
+        m, _, kms, st = step(False)
+        rays += int(m[sp.sp_Metric_RaysTraced])
+        kms_all.append(kms)
+        if st is not None:
+            trace_ms.append(st.traceMs)
+            traced += int(st.tracedRays)
+            launches.append(st.traceLaunches)
+        frame += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    elapsed = ev0.elapsed_time(ev1)
+    stat = torch.tensor([elapsed, float(rays), float(np.mean(kms_all))], dtype=torch.float64, device=dev)
+    per_rank = None
+    if world > 1:
+        allr = [torch.zeros_like(stat) for _ in range(world)]
+        dist.all_gather(allr, stat)
+        per_rank = [float(t[2]) for t in allr]
+        elapsed = max(float(t[0]) for t in allr)
+        rays = sum(float(t[1]) for t in allr)
+    out = None
+    if rank == 0:
+        scene_bytes = int(sp.lib.sp_b200_SceneDeviceBytes(r.scene))
+        sp.lib.sp_b200_EnableStats(1)
+        b, e = bounds[rank]
+        r.render_rows(b, e, frame=frame - 1, host=False, device_ptr=image.data_ptr())
+        st = sp.last_stats()
+        sp.lib.sp_b200_EnableStats(0)
+        srays = max(1, int(st.tracedRays))
+        I, L = st.nodeVisits / srays, st.triangleTests / srays
+        per_ray = 128.0 * I + 48.0 * L + 64.0
+        tms = float(np.mean(trace_ms)) if trace_ms else 0.0
+        tr = traced / 3.0
+        achieved = per_ray * tr / (tms * 1e-3) / 1e9 if tms > 0 else 0.0
+        chip = on_chip_peaks(scene_bytes)
+        hbm, which = measured_peak()
+        traffic = None
+        tj = load_json("profiles", "r2", "trace_traffic_c5.json")
+        if tj and tj.get("traced_rays_per_step"):
+            traffic = float(tj["dram_bytes_per_step"]) / float(tj["traced_rays_per_step"]) * tr / max(1, int(np.mean(launches)))
+        out = {"workload": "C5: 64 bunnies + 118 level-6 icospheres (9.98 M instanced triangles, 182 objects), 3840x2160, 16 spp, "
+                           "5 bounces (BASELINE.json configs[4])",
+               "value": rays / (elapsed * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": elapsed / 3.0, "steps": 3, "warmup": 2,
+               "n_gpus": world, "rank_kernel_ms": per_rank, "strips": [list(map(int, b)) for b in bounds],
+               "scene_build_seconds": build_s, "scene_device_bytes": scene_bytes,
+               "what": "device time of 3 frames (CUDA events, max over ranks); strips rendered, not gathered",
+               "roofline": {"bound": "l2", "achieved": achieved, "unit": "GB/s",
+                            "peak": chip["l2_read_peak"] if chip else None,
+                            "frac": achieved / chip["l2_read_peak"] if chip else None,
+                            "l2_working_set_mib": chip["l2_working_set_mib"] if chip else None,
+                            "hbm": {"peak": hbm, "frac": achieved / hbm, "peak_source": which},
+                            "traffic": traffic, "kernel": "k_trace", "kernel_ms_per_step": tms,
+                            "launches_per_step": int(np.mean(launches)) if launches else 0,
+                            "traced_rays_per_step": tr, "traversal_grays_per_s": tr / (tms * 1e-3) / 1e9 if tms > 0 else 0.0,
+                            "node_visits_per_ray": I, "triangle_tests_per_ray": L, "object_entries_per_ray": st.objectTests / srays,
+                            "algorithmic_bytes_per_ray": per_ray}}
+    r.close()
+    return out
 
 
 if __name__ == "__main__":

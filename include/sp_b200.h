@@ -192,16 +192,24 @@ vec3 ComputeRadianceForPath(sp_PathVertex *path, u32 pathLength, sp_MaterialSyst
  * pixels exactly as the reference (one GPU thread per tile: drop-in fidelity, not speed);
  * overwrites metrics[CyclesElapsed] with device nanoseconds, increments the counters. */
 void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng, sp_Metrics *metrics);
+/* sp_PathTraceTile may be called from many host threads at once, like WorkerThread does
+ * (main.cpp:728-759): concurrent calls are combined -- every request that queues up while a launch is
+ * running goes into the next launch, one GPU thread per tile -- instead of taking turns on a mutex.
+ * Counts so far: launches made and tiles rendered by them. */
+void sp_b200_TileCombinerStats(u64 *launches, u64 *tiles);
 
-/* aabb.h:29-58 */
+/* The reference DEFINES the next five `inline` in its headers (aabb.h:29-58, tile.h:11-42,
+ * work_queue.h:13-44), so a reference-side translation unit already has them -- with C++ linkage --
+ * and keeps using them; the library exports C versions of the same arithmetic for every other host
+ * (tests/dropin compiles the reference-side case, tests/test_abi.py the plain C one). */
+#ifndef SP_B200_USE_REFERENCE_TYPES
 Aabb TransformAabb(vec3 boxMin, vec3 boxMax, vec3 position, quat orientation, vec3 scale);
-/* tile.h:11-42 */
 u32 ComputeTiles(u32 totalWidth, u32 totalHeight, u32 tileWidth, u32 tileHeight, Tile *tiles,
                  u32 maxTiles);
-/* work_queue.h:13-44 */
 WorkQueue CreateWorkQueue(MemoryArena *arena, u32 objectSize, u32 maxObjects);
 b32 WorkQueuePush(WorkQueue *queue, void *object, u32 objectSize);
 void *WorkQueuePop(WorkQueue *queue, u32 objectSize);
+#endif
 
 /* The tile scheduler on top of the queue (main.cpp:246-250 sp_Task; :819-844 AddRayTracingWorkQueue;
  * :728-759 WorkerThread + g_metricsBuffer).  `internal` in the reference, so they carry the library
@@ -215,8 +223,9 @@ void *WorkQueuePop(WorkQueue *queue, u32 objectSize);
 #ifndef SP_B200_USE_REFERENCE_TYPES /* main.cpp defines its own sp_Task (same layout, 24 bytes) */
 typedef struct sp_Task { sp_Context *context; Tile tile; } sp_Task;
 #endif
-u32 sp_b200_AddRayTracingWorkQueue(WorkQueue *workQueue, sp_Context *ctx);
-u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *metricsBuffer, u32 maxMetrics);
+/* (`struct WorkQueue`: a reference-side unit may include this header before work_queue.h) */
+u32 sp_b200_AddRayTracingWorkQueue(struct WorkQueue *workQueue, sp_Context *ctx);
+u32 sp_b200_DrainRayTracingWorkQueue(struct WorkQueue *queue, sp_Metrics *metricsBuffer, u32 maxMetrics);
 
 /* =============================== additions (sp_b200_*) =============================== */
 
@@ -327,6 +336,13 @@ void sp_b200_SetPrimaryCandidates(int enable);
  * image band by band while later bands render.  0: one upload in front of the frame and one copy
  * behind it, both on the render stream (round 1's behaviour). */
 void sp_b200_SetCopyOverlap(int enable);
+/* The device already holds a copy of the HdrImage whose pixels == hostPixels (width x height RGBA
+ * f32 at devicePixels, owned by the caller): use it instead of uploading.  readyEvent (a cudaEvent_t,
+ * or NULL) is what the render stream waits for before the first kernel that samples a texture -- the
+ * copy may still be in flight, e.g. an environment map of which every rank of a multi-process host
+ * uploaded one slice and an NCCL all-gather over NVLink is assembling the rest.  devicePixels = NULL
+ * forgets the association; sp_b200_FlushTextureCache forgets all of them. */
+void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u32 width, u32 height, void *readyEvent);
 /* Wavefront mode tuning: a warp of the trace kernel retires and refills its lanes when fewer than
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */

@@ -158,6 +158,20 @@ def test_midphase_tree_structure_host(sp):
         sp.lib.sp_b200_ReleaseMesh(C.byref(m))
 
 
+def test_reference_unit_tests_against_the_reference_itself():
+    """The bar for tests/dropin: the reference's own test file, unmodified, against the reference's own
+    sources (tests/dropin/_build/reference_unit_tests, built where the checkout is mounted).  15 of its 16
+    tests pass; TestEvaluateLightPath fails THERE too (GGX at roughness 0 is 0/0), which is why
+    the drop-in run leaves it out."""
+    exe = os.path.join(ROOT, "tests", "dropin", "_build", "reference_unit_tests")
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("tests/dropin/_build not built (the reference checkout was never mounted here)")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "16 Tests 1 Failures 0 Ignored" in p.stdout
+    assert "TestEvaluateLightPath:FAIL" in p.stdout
+
+
 def test_product_never_touches_the_oracle():
     """The product path must not import, link or call anything under oracle/ (or hostsim)."""
     pkg = os.path.join(ROOT, "vk_cinematic_b200")

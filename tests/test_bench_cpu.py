@@ -31,6 +31,22 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_does_not_map_the_product_library():
+    """The driver records which .so files each arm loaded: the reference arm is the CPU checker alone and
+    must not even map libspb200.so ("it dirties the record")."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--width', '96', '--height', '64', "
+            "'--spp', '1']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "sys.stderr.write('MAPPED_PRODUCT=%%d MAPPED_CHECKER=%%d\\n' %% ('libspb200' in maps, 'libsporacle' in maps or 'libspref' in maps))\n"
+            % os.path.join(ROOT, "bench.py"))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "MAPPED_PRODUCT=0 MAPPED_CHECKER=1" in p.stderr, p.stderr[-500:]
+
+
 def test_b200_arm_refuses_to_run_without_a_gpu():
     p = run_bench("--steps", "1", "--warmup", "1", "--width", "64", "--height", "48", "--spp", "1", "--quick",
                   timeout=120)

@@ -486,6 +486,34 @@ def test_c2_full_frame_fixture(gpu_sp):
     r.close()
 
 
+def test_reference_unit_tests_against_the_library(gpu_sp):
+    """INTEGRATION.md §1 exercised: tests/dropin/_build/dropin_unit_tests is ONE translation unit that
+    includes the reference's own headers (all types), include/sp_b200.h with
+    SP_B200_USE_REFERENCE_TYPES, and the reference's own Unity test functions -- extracted unmodified
+    from unit_tests/test_simd_path_tracer.cpp:49-395 at build time -- and links libspb200.so where the
+    reference's test links bvh.cpp / sp_scene.cpp / sp_material_system.cpp / simd_path_tracer.cpp.  Every
+    test that passes against the reference's sources (tests/test_abi.py runs that binary) must pass here
+    on the GPU; plus the reference's frame loop -- its inline WorkQueue, 16 WorkerThreads calling
+    sp_PathTraceTile (main.cpp:728-759) -- whose image must equal the one-thread image while the
+    concurrent callers share launches.  Built where the reference is mounted; the binary travels."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin", "_build", "dropin_unit_tests")
+    if not os.path.exists(exe):
+        pytest.skip("tests/dropin/_build not built (the reference checkout was never mounted here)")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    assert "9 Tests 0 Failures 0 Ignored" in out, out[-3000:]
+    for name in ("TestPathTraceSingleColor", "TestPathTraceTile", "TestConfigureCamera", "TestCalculateFilmP",
+                 "TestRayIntersectScene", "TestMaterialAlbedoTexture", "TestMetrics", "TestRayIntersectMesh",
+                 "TestWorkerThreadsThroughTheLibrary"):
+        assert f"{name}:PASS" in out, name
+    timing = os.environ.get("SPB_TIMING_OUT")
+    if timing:
+        with open(timing, "a") as f:
+            f.write([l for l in out.splitlines() if l.startswith("WORKER_THREADS")][0] + "\n")
+
+
 @pytest.mark.parametrize("mode", ["host", "device"])
 def test_multi_device_frame(gpu_sp, mode):
     """Several devices behind the C ABI: sp_b200_InitDeviceList, then

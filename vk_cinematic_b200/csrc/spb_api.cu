@@ -103,6 +103,7 @@ struct DeviceScene
 struct TextureEntry
 {
     DeviceBuffer buffer;
+    const void *external = nullptr; // sp_b200_SetDeviceTexture: the caller's device copy (never freed here)
     uint32_t width = 0, height = 0;
     ~TextureEntry() { buffer.release(); }
 };
@@ -164,6 +165,7 @@ struct Library
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evTextures = nullptr, evRowsReady = nullptr, evCopyDone = nullptr, evOrder = nullptr;
     bool texturesPending = false; // an upload was issued on copyStream and nobody waited for it yet
+    std::vector<cudaEvent_t> externalReady; // events of sp_b200_SetDeviceTexture copies nobody waited for yet
     bool overlapCopies = true;    // sp_b200_SetCopyOverlap
 
     Library()
@@ -430,7 +432,7 @@ const v4f *device_texture(const HdrImage &image)
     if (!image.pixels || image.width == 0 || image.height == 0) return nullptr;
     auto it = L.textures.find(image.pixels);
     if (it != L.textures.end() && it->second->width == image.width && it->second->height == image.height)
-        return (const v4f *)it->second->buffer.ptr;
+        return (const v4f *)(it->second->external ? it->second->external : it->second->buffer.ptr);
     size_t bytes = (size_t)image.width * image.height * 16;
     std::unique_ptr<TextureEntry> entry;
     for (size_t i = 0; i < L.texturePool.size(); ++i)
@@ -469,6 +471,8 @@ const v4f *device_texture(const HdrImage &image)
 void wait_textures()
 {
     Library &L = lib();
+    for (cudaEvent_t e : L.externalReady) SPB_CUDA(cudaStreamWaitEvent(L.stream, e, 0));
+    L.externalReady.clear();
     if (!L.texturesPending) return;
     SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evTextures, 0));
     L.texturesPending = false;
@@ -1089,9 +1093,32 @@ extern "C" void sp_b200_FlushTextureCache(void)
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     if (L.initialized) cudaDeviceSynchronize();
-    for (auto &t : L.textures) L.texturePool.push_back(std::move(t.second));
+    for (auto &t : L.textures)
+        if (!t.second->external) L.texturePool.push_back(std::move(t.second));
     L.textures.clear();
+    L.externalReady.clear();
     while (L.texturePool.size() > SPB_MAX_IMAGES) L.texturePool.erase(L.texturePool.begin());
+}
+
+extern "C" void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u32 width, u32 height, void *readyEvent)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(hostPixels != nullptr);
+    auto it = L.textures.find(hostPixels);
+    if (it != L.textures.end())
+    {
+        if (!it->second->external) L.texturePool.push_back(std::move(it->second));
+        L.textures.erase(it);
+    }
+    if (!devicePixels) return; // forget the association
+    auto entry = std::make_unique<TextureEntry>();
+    entry->external = devicePixels;
+    entry->width = width;
+    entry->height = height;
+    L.textures[hostPixels] = std::move(entry);
+    if (readyEvent) L.externalReady.push_back((cudaEvent_t)readyEvent);
 }
 
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
@@ -2138,38 +2165,77 @@ extern "C" int sp_b200_RenderFrameToDevice(sp_Context *ctx, u32 frame, void *dev
     return sp_b200_RenderRows(ctx, 0, plane->height, frame, nullptr, devicePixels, metrics, nullptr);
 }
 
-extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng,
-                                 sp_Metrics *metrics)
+// sp_PathTraceTile is re-entrant in the reference: WorkerThread (main.cpp:728-759) calls it from 16
+// host threads at once, one tile each.  A tile is one GPU thread of control by definition (its pixels
+// share one serial XorShift32 stream), so a launch per call would keep one lane of the whole GPU busy
+// and 15 host threads waiting on the library mutex.  Concurrent callers are COMBINED instead: a caller
+// that finds nobody rendering becomes the leader and renders every request that has queued up behind
+// it -- its own first, then, while that launch runs, the requests of the other threads, all of one
+// context in ONE launch of k_tiles_serial -- until the queue is empty; the others sleep until their
+// request is marked done.  Results are per tile (own rng state, own pixels, own metrics), so a caller
+// cannot tell whether it was batched.
+struct TileRequest
+{
+    sp_Context *ctx;
+    Tile tile;
+    RandomNumberGenerator *rng;
+    sp_Metrics *metrics;
+    bool done;
+};
+
+struct TileCombiner
+{
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<TileRequest *> pending;
+    bool leaderActive = false;
+    unsigned long long launches = 0, tiles = 0;
+};
+
+static TileCombiner &tile_combiner()
+{
+    static TileCombiner *instance = new TileCombiner();
+    return *instance;
+}
+
+// every request of `group` has the same context: one launch
+static void render_tile_group(const std::vector<TileRequest *> &group)
 {
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     ensure_init();
+    sp_Context *ctx = group[0]->ctx;
     SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    ImagePlane *plane = ctx->camera->imagePlane;
+    const u32 count = (u32)group.size();
+    std::vector<uint32_t> staging((size_t)count * 5); // per tile: minX minY maxX maxY, then one rng state per tile
+    for (u32 k = 0; k < count; ++k)
+    {
+        const Tile &t = group[k]->tile;
+        staging[(size_t)k * 4 + 0] = t.minX;
+        staging[(size_t)k * 4 + 1] = t.minY;
+        staging[(size_t)k * 4 + 2] = t.maxX < plane->width ? t.maxX : plane->width; // simd_path_tracer.cpp:188-191
+        staging[(size_t)k * 4 + 3] = t.maxY < plane->height ? t.maxY : plane->height;
+        staging[(size_t)count * 4 + k] = group[k]->rng->state;
+    }
     DCamera cam;
     convert_camera(ctx->camera, &cam);
-    ImagePlane *plane = ctx->camera->imagePlane;
-    // simd_path_tracer.cpp:188-191
-    u32 minX = tile.minX, minY = tile.minY;
-    u32 maxX = tile.maxX < plane->width ? tile.maxX : plane->width;
-    u32 maxY = tile.maxY < plane->height ? tile.maxY : plane->height;
     DeviceScene *ds = find_scene(ctx->scene);
-
     size_t imageBytes = (size_t)cam.width * cam.height * 16;
     L.image.ensure(imageBytes ? imageBytes : 16);
     SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
     const DMaterials *dm = upload_materials(ctx->materialSystem);
-    unsigned long long *ctr = reset_counters();
-    uint32_t tileData[5] = {minX, minY, maxX, maxY, rng->state};
-    L.scratchA.ensure(sizeof(tileData));
-    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, tileData, sizeof(tileData), cudaMemcpyHostToDevice, L.stream));
+    unsigned long long *ctr = reset_counters((size_t)(count - 1) * CTR_COUNT);
+    L.scratchA.ensure(staging.size() * 4);
+    SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, L.stream));
 
     TileArgs args;
     args.scene = ds->d;
     args.materials = dm;
     args.camera = cam;
     args.tiles = (const uint32_t *)L.scratchA.ptr;
-    args.rngStates = (uint32_t *)L.scratchA.ptr + 4;
-    args.count = 1;
+    args.rngStates = (uint32_t *)L.scratchA.ptr + (size_t)count * 4;
+    args.count = count;
     args.spp = L.params.samplesPerPixel;
     args.bounces = L.params.bounceCount;
     args.clampValue = L.params.radianceClamp;
@@ -2180,24 +2246,90 @@ extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerat
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
 
-    unsigned long long c[CTR_COUNT];
-    SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
-    SPB_CUDA(cudaMemcpyAsync(&rng->state, (uint32_t *)L.scratchA.ptr + 4, 4, cudaMemcpyDeviceToHost, L.stream));
-    if (maxX > minX && maxY > minY && plane->pixels)
-    {
-        size_t pitch = (size_t)cam.width * 16;
-        size_t offset = (size_t)minY * cam.width + minX;
-        SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
-                                   pitch, (size_t)(maxX - minX) * 16, maxY - minY,
-                                   cudaMemcpyDeviceToHost, L.stream));
-    }
+    std::vector<unsigned long long> c((size_t)count * CTR_COUNT);
+    std::vector<uint32_t> states(count);
+    SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(states.data(), (uint32_t *)L.scratchA.ptr + (size_t)count * 4, (size_t)count * 4,
+                             cudaMemcpyDeviceToHost, L.stream));
+    if (plane->pixels)
+        for (u32 k = 0; k < count; ++k)
+        {
+            const uint32_t *t = staging.data() + (size_t)k * 4;
+            if (t[2] <= t[0] || t[3] <= t[1]) continue;
+            size_t pitch = (size_t)cam.width * 16;
+            size_t offset = (size_t)t[1] * cam.width + t[0];
+            SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
+                                       pitch, (size_t)(t[2] - t[0]) * 16, t[3] - t[1],
+                                       cudaMemcpyDeviceToHost, L.stream));
+        }
     SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float kernelMs = 0, totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
     SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
-    add_metrics(metrics, c, kernelMs);
-    record_stats(c, kernelMs, totalMs);
+    int clockKHz = 0;
+    cudaDeviceGetAttribute(&clockKHz, cudaDevAttrClockRate, L.device);
+    std::vector<unsigned long long> total(CTR_COUNT, 0);
+    for (u32 k = 0; k < count; ++k)
+    {
+        const unsigned long long *ck = c.data() + (size_t)k * CTR_COUNT;
+        for (int j = 0; j < CTR_COUNT; ++j) total[j] += ck[j];
+        group[k]->rng->state = states[k];
+        // CyclesElapsed = this tile's own device time (nanoseconds) when it shared the launch
+        float tileMs = (count > 1 && clockKHz > 0) ? (float)((double)ck[CTR_CLOCK_SUM] / (double)clockKHz) : kernelMs;
+        add_metrics(group[k]->metrics, ck, tileMs);
+    }
+    record_stats(total.data(), kernelMs, totalMs);
+}
+
+extern "C" void sp_PathTraceTile(sp_Context *ctx, Tile tile, RandomNumberGenerator *rng,
+                                 sp_Metrics *metrics)
+{
+    SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane && rng);
+    TileCombiner &C = tile_combiner();
+    TileRequest req = {ctx, tile, rng, metrics, false};
+    std::unique_lock<std::mutex> lock(C.m);
+    C.pending.push_back(&req);
+    if (C.leaderActive)
+    {
+        C.cv.wait(lock, [&] { return req.done; });
+        return;
+    }
+    C.leaderActive = true;
+    while (!C.pending.empty())
+    {
+        std::vector<TileRequest *> batch;
+        batch.swap(C.pending);
+        lock.unlock();
+        // one launch per context, contexts in first-seen order
+        std::vector<bool> taken(batch.size(), false);
+        for (size_t first = 0; first < batch.size(); ++first)
+        {
+            if (taken[first]) continue;
+            std::vector<TileRequest *> group;
+            for (size_t i = first; i < batch.size(); ++i)
+                if (!taken[i] && batch[i]->ctx == batch[first]->ctx)
+                {
+                    taken[i] = true;
+                    group.push_back(batch[i]);
+                }
+            render_tile_group(group);
+        }
+        lock.lock();
+        C.launches++;
+        C.tiles += batch.size();
+        for (TileRequest *r : batch) r->done = true;
+        C.cv.notify_all();
+    }
+    C.leaderActive = false;
+}
+
+extern "C" void sp_b200_TileCombinerStats(u64 *launches, u64 *tiles)
+{
+    TileCombiner &C = tile_combiner();
+    std::lock_guard<std::mutex> lock(C.m);
+    if (launches) *launches = C.launches;
+    if (tiles) *tiles = C.tiles;
 }
 
 // ---------------------------------------------------------------------------------------------
