@@ -63,7 +63,7 @@ def parse_args():
                          "c5u: the same with every sphere its own mesh (BVH larger than L2)")
     ap.add_argument("--render-mode", type=int, default=0, help="0: wavefront kernels (default), 1: per-pixel kernel")
     ap.add_argument("--samples-per-pass", type=int, default=0)
-    ap.add_argument("--strip-rows", type=int, default=16, help="granularity of strip boundaries in pixel rows (multiple of 4)")
+    ap.add_argument("--strip-rows", type=int, default=8, help="granularity of strip boundaries in pixel rows (multiple of 4)")
     ap.add_argument("--sort-bounces", type=int, default=0, help="development: direction-sort the rays leaving this many bounces")
     ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
     ap.add_argument("--no-candidates", action="store_true", help="development: every primary ray walks the tree")
@@ -95,7 +95,7 @@ def workload_config(args):
         "env_filter": "nearest (reference image.h:3-18)",
         "l2": "env map 134 MB + framebuffer 133 MB touched per step exceed the 126 MB L2; the "
               "1.3 MB BVH is re-read by every ray inside a step by design; frame index advances per step",
-        "partition": "strips of whole 16-pixel rows (quarter tiles), rebalanced from measured per-row cost",
+        "partition": f"strips of whole {args.strip_rows}-pixel rows, re-cut every warm-up frame from the measured per-row cost (sp_b200_PartitionRows: min-max optimal contiguous cut)",
         "scheduler": "wavefront (trace / shade-miss / shade-hit / accumulate kernels over device queues)"
                      if args.render_mode == 0 else "per-pixel kernel",
     }
@@ -551,6 +551,7 @@ def main():
     bounds = strips.partition_rows(H, TH, world)
     frame = 0
     warmups = max(args.warmup, 3)
+    history = []
     for w in range(warmups):
         barrier()
         m, cost, kms, _ = render_step(frame, bounds, want_cost=True, wait_gather=True)
@@ -561,6 +562,7 @@ def main():
             # time: the gather waits for the slowest rank and would hide the imbalance
             row_cost, _secs = strips.gather_row_costs(
                 cost if cost is not None else np.zeros(0), kms * 1e-3, bounds, H, TH, dist, dev)
+            history.append({"strips": [int(b[1]) for b in bounds], "kernel_ms": [round(float(x) * 1e3, 3) for x in _secs]})
             bounds = strips.partition_rows(H, TH, world, row_cost)
 
     # ---- timed region: exactly K steps
@@ -610,7 +612,7 @@ def main():
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": float(np.mean(kernel_ms)),
                               "rays_per_step": rays / args.steps, "launches": int(launches), "strips": [list(map(int, b)) for b in bounds],
-                              "ranks": per_rank}), file=RESULT_OUT, flush=True)
+                              "ranks": per_rank, "rebalance_history": history}), file=RESULT_OUT, flush=True)
         r.close()
         if world > 1:
             dist.barrier()
@@ -748,6 +750,7 @@ def main():
         }
         if per_rank is not None:
             out["ranks"] = per_rank
+            out["rebalance_history"] = history
         if parity is not None:
             out["parity"] = parity
         if secondary:

@@ -229,6 +229,17 @@ u32 sp_b200_DrainRayTracingWorkQueue(struct WorkQueue *queue, sp_Metrics *metric
 
 /* =============================== additions (sp_b200_*) =============================== */
 
+/* simd_RayIntersectAabb4 (simd.h:198-271) as the DEVICE evaluates it, for known-answer tests: `count`
+ * queries of four boxes (boxMin / boxMax: count x 4 x 3 floats) against (rayOrigin, invRayDirection)
+ * taken exactly as the reference's function takes them.  masks[q * 3 + 0]: the exact form with the
+ * SSE NaN semantics (second operand of min / max wins), [1]: the hardware min / max form used when no
+ * product can be NaN, [2]: the conservative test of the resumable traversal (must contain [0]), or
+ * 0xFFFFFFFF for a ray that traversal hands to the exact walk; bit k = box k.  tnear (optional):
+ * count x 4 entry distances of the exact form. */
+int sp_b200_RayIntersectAabb4Batch(u32 count, const f32 *boxMin, const f32 *boxMax, const vec3 *rayOrigins,
+                                   const vec3 *invRayDirections, u32 *masks, f32 *tnear);
+
+
 typedef void (*sp_b200_LogFn)(const char *message);
 
 enum { SP_B200_ENV_NEAREST = 0, SP_B200_ENV_BILINEAR = 1 };
@@ -353,9 +364,11 @@ u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
 /* Whole-frame render with per-(pixel,sample) seeding: rows [rowBegin,rowEnd) of the image plane.
  * hostPixels (RGBA f32, full-image indexing, may be NULL) receives the rows by D2H copy;
  * devicePixels (device pointer to a full image, may be NULL) receives them in place.
- * tileRowCost (may be NULL): per tile-row device cost in cost units (wavefront mode: 1 per sample
- * of a sky-kernel pixel, 16 per escaped ray traced through the queues, 80 per surface hit; per-pixel
- * mode: rays traced), rowEnd-rowBegin rounded up to tiles.  Returns 0 on success. */
+ * tileRowCost (may be NULL): cost of every tile row (tileHeight rows; rowEnd-rowBegin rounded up) in
+ * NANOSECONDS of this call's kernels: the work the kernels counted in the row -- wavefront mode: sky-
+ * kernel samples, escaped rays (16 units) and surface hits (80 units) of the queue kernels; per-pixel
+ * mode: rays -- converted class by class with the time that class of kernels took in this call, so the
+ * rows add up to sp_b200_Stats::kernelMs.  What sp_b200_PartitionRows cuts by.  Returns 0 on success. */
 int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels,
                        void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);
 /* All rows into ctx->camera->imagePlane->pixels (host). */

@@ -477,13 +477,10 @@ extern "C" void hostsim_check_shortcuts(ora_Scene *s, uint32_t spp, uint32_t fra
                     float record[T2_WORDS];
                     T2View<1> view;
                     view.base = record;
-                    v4f ray[2];
-                    ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
-                    ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
                     if (!trav2_start(s->d, o, d, st, view)) continue;      // empty scene / exact walk
                     if (!resolve_from_candidates2(s->d, list, o, d, st, view, nullptr)) continue; // the walk takes over
                     if (view.u(T2_SLOW)) continue;
-                    Hit fast = trav2_finish(s->d, ray, view, true);
+                    Hit fast = trav2_finish(s->d, st, view);
                     bool same = f2u(fast.t) == f2u(walk.t) && fast.object == walk.object && (fast.object < 0 || fast.slot == walk.slot);
                     if (!same)
                     {

@@ -164,6 +164,8 @@ struct Library
     // while later bands render.
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evTextures = nullptr, evRowsReady = nullptr, evCopyDone = nullptr, evOrder = nullptr;
+    cudaEvent_t evSky0 = nullptr, evSky1 = nullptr; // around the sky kernels of a wavefront frame
+    bool skyTimed = false;
     bool texturesPending = false; // an upload was issued on copyStream and nobody waited for it yet
     std::vector<cudaEvent_t> externalReady; // events of sp_b200_SetDeviceTexture copies nobody waited for yet
     bool overlapCopies = true;    // sp_b200_SetCopyOverlap
@@ -308,6 +310,8 @@ void ensure_init()
     SPB_CUDA(cudaEventCreateWithFlags(&L.evRowsReady, cudaEventDisableTiming));
     SPB_CUDA(cudaEventCreateWithFlags(&L.evCopyDone, cudaEventDisableTiming));
     SPB_CUDA(cudaEventCreateWithFlags(&L.evOrder, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreate(&L.evSky0));
+    SPB_CUDA(cudaEventCreate(&L.evSky1));
     L.initialized = true;
 }
 
@@ -614,6 +618,8 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.stats = ra.counters;
     a.countStats = L.statsEnabled ? 1 : 0;
     a.tileRowCost = ra.tileRowCost;
+    // (the second half of the caller's cost array: the sky kernels' class, see sp_b200_RenderRows)
+    a.tileRowSky = ra.tileRowCost ? ra.tileRowCost + ((ra.y1 - 1) / ra.tileHeight - ra.y0 / ra.tileHeight + 1) : nullptr;
     a.tileHeight = ra.tileHeight;
     a.costRow0 = ra.y0 / (ra.tileHeight ? ra.tileHeight : 1);
 
@@ -679,8 +685,11 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     uint32_t rowsCopied = ra.y0, rowsBottom = ra.y1; // rows outside [rowsCopied, rowsBottom) are on their way
     auto launch_sky_kernels = [&]() {
         wait_textures();
+        SPB_CUDA(cudaEventRecord(L.evSky0, L.stream));
         launch_sky(cfg, a, L.stream);
         if (a.skyList) launch_sky_listed(cfg, a, L.stream);
+        SPB_CUDA(cudaEventRecord(L.evSky1, L.stream));
+        L.skyTimed = true;
     };
     if (covered == 0)
     {
@@ -918,6 +927,7 @@ void shutdown_library(Library &L)
         cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
         cudaEventDestroy(L.evKernel1); cudaEventDestroy(L.evEnd);
         cudaEventDestroy(L.evTextures); cudaEventDestroy(L.evRowsReady); cudaEventDestroy(L.evCopyDone); cudaEventDestroy(L.evOrder);
+        cudaEventDestroy(L.evSky0); cudaEventDestroy(L.evSky1);
         cudaStreamDestroy(L.copyStream);
         L.copyStream = nullptr;
     }
@@ -1489,6 +1499,32 @@ extern "C" sp_RayIntersectMeshResult sp_RayIntersectMesh(sp_Mesh mesh, vec3 rayO
     return result;
 }
 
+extern "C" int sp_b200_RayIntersectAabb4Batch(u32 count, const f32 *boxMin, const f32 *boxMax, const vec3 *rayOrigins,
+                                              const vec3 *invRayDirections, u32 *masks, f32 *tnear)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    if (count == 0) return 0;
+    const size_t boxBytes = (size_t)count * 12 * 4, vecBytes = (size_t)count * 12;
+    L.scratchA.ensure(boxBytes * 2 + vecBytes * 2);
+    L.scratchB.ensure((size_t)count * (3 + 4) * 4);
+    char *in = (char *)L.scratchA.ptr;
+    SPB_CUDA(cudaMemcpyAsync(in, boxMin, boxBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(in + boxBytes, boxMax, boxBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(in + boxBytes * 2, rayOrigins, vecBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(in + boxBytes * 2 + vecBytes, invRayDirections, vecBytes, cudaMemcpyHostToDevice, L.stream));
+    uint32_t *dMasks = (uint32_t *)L.scratchB.ptr;
+    float *dNear = (float *)(dMasks + (size_t)count * 3);
+    launch_slab_kat(count, (const float *)in, (const float *)(in + boxBytes), (const float *)(in + boxBytes * 2),
+                    (const float *)(in + boxBytes * 2 + vecBytes), dMasks, dNear, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaMemcpyAsync(masks, dMasks, (size_t)count * 3 * 4, cudaMemcpyDeviceToHost, L.stream));
+    if (tnear) SPB_CUDA(cudaMemcpyAsync(tnear, dNear, (size_t)count * 4 * 4, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    return 0;
+}
+
 extern "C" u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 rayDirection,
                                              u32 *leafIndices, u32 maxIntersections,
                                              b32 *errorOccurred)
@@ -1792,7 +1828,9 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
     // (the wavefront path waits for texture uploads where its first texture-reading kernel starts)
     const DMaterials *dm = upload_materials(ctx->materialSystem, nullptr, wavefront);
-    unsigned long long *ctr = reset_counters(tileRows);
+    // two cost classes per tile row (queue kernels, sky kernels): 2 x tileRows slots behind the counters
+    unsigned long long *ctr = reset_counters((size_t)tileRows * 2);
+    L.skyTimed = false;
 
     RenderArgs args;
     args.scene = ds->d;
@@ -1814,7 +1852,7 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
     SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);
 
-    std::vector<unsigned long long> c(CTR_COUNT + tileRows);
+    std::vector<unsigned long long> c(CTR_COUNT + (size_t)tileRows * 2);
     std::vector<uint32_t> waveCounters;
     bool rowsStreamed = false;
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
@@ -1897,7 +1935,28 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     L.lastStats.traceLaunches = wavefront ? (u32)(L.traceEventsUsed / 2) : 1u;
     L.lastStats.tracedRays = c[CTR_RAYS] - (wavefront ? c[CTR_SKY_PIXELS] * L.params.samplesPerPixel : 0);
     if (tileRowCost)
-        for (u32 i = 0; i < tileRows; ++i) tileRowCost[i] = c[CTR_COUNT + i];
+    {
+        // Cost of every tile row in NANOSECONDS of this device: the units the kernels counted,
+        // converted class by class with the time that class took in this very call -- the sky
+        // kernels' units by the sky kernels' time, the queue kernels' (escaped rays, surface hits)
+        // by the rest.  A unit of sky is not a unit of bunny, and how much not depends on the
+        // scene and the strip; measuring the two apart takes that guess out of the re-cut.
+        float skyMs = 0.0f;
+        if (wavefront && L.skyTimed) SPB_CUDA(cudaEventElapsedTime(&skyMs, L.evSky0, L.evSky1));
+        double unitsQueue = 0.0, unitsSky = 0.0;
+        for (u32 i = 0; i < tileRows; ++i)
+        {
+            unitsQueue += (double)c[CTR_COUNT + i];
+            unitsSky += (double)c[CTR_COUNT + tileRows + i];
+        }
+        double nsSky = (double)skyMs * 1e6, nsQueue = (double)kernelMs * 1e6 - nsSky;
+        if (nsQueue < 0.0) nsQueue = 0.0;
+        if (unitsSky <= 0.0) { nsQueue += nsSky; nsSky = 0.0; }
+        if (unitsQueue <= 0.0) { nsSky += nsQueue; nsQueue = 0.0; }
+        const double perQueue = unitsQueue > 0.0 ? nsQueue / unitsQueue : 0.0, perSky = unitsSky > 0.0 ? nsSky / unitsSky : 0.0;
+        for (u32 i = 0; i < tileRows; ++i)
+            tileRowCost[i] = (u64)((double)c[CTR_COUNT + i] * perQueue + (double)c[CTR_COUNT + tileRows + i] * perSky + 0.5);
+    }
     return 0;
 }
 

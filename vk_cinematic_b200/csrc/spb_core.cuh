@@ -953,10 +953,11 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
 // Resumable traversal, second form (round 2; what k_trace runs).  Same query, same result set as
 // intersect_scene() -- the minimum over {triangles whose OWN box passes the reference's slab
 // predicate, Moller-Trumbore accepts, t > 0} over {objects whose OWN world box passes it} -- but
-// the reference's predicate is evaluated only where the result depends on it:
+// inside an object the reference's predicate is evaluated only where the result depends on it:
 //
-//   * inner boxes (and the first look at a leaf's box, inside its parent's node step) get a
-//     CONSERVATIVE test that costs half the instructions and none of the min/max pairs: per axis
+//   * the boxes of a mesh tree (inner boxes, and the first look at a leaf's box inside its
+//     parent's node step) get a CONSERVATIVE test that costs half the instructions and none of the
+//     min/max pairs: per axis
 //         tnear = bmin * p + bmax * q + cn,   tfar = bmin * q + bmax * p + cf      (four FFMA)
 //     with (p, q) = (1/d, 0) or (0, 1/d) by the sign of d -- the multiply by zero selects the near
 //     and the far plane without a compare -- and cn / cf = -(o -+ delta) / d, the box grown by
@@ -964,39 +965,44 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
 //     ulps of (|b| + |o|) / |d| away from its value (the reference: sub, mul; this one: mul, fma);
 //     delta is eight times the sum of the two bounds, so the padded interval of every axis
 //     contains the reference's and whatever passes the reference's test passes this one.
-//   * a leaf that comes off the stack is tested AGAIN, exactly: a triangle's own box is rebuilt
-//     from its three vertices (min / max are exact, so these are the builder's bits up to the sign
-//     of a zero, which no comparison of the slab test can see) and an object's own world box is
-//     read from DScene::objBox; slab_fast() on it is the reference's test (all reciprocals finite).
-//     Only then Moller-Trumbore / the object entry runs.
+//   * a triangle that comes off the stack is tested AGAIN, exactly: its own box is rebuilt from
+//     its three vertices (min / max are exact, so these are the builder's bits up to the sign of
+//     a zero, which no comparison of the slab test can see) and slab_fast() on it is the
+//     reference's test (all reciprocals finite).  Only then Moller-Trumbore runs.
+//   * the TLAS is walked with the exact test throughout (slab_fast on the world ray, which stays
+//     in the lane's record): its leaves are the objects' own boxes, few nodes are visited per
+//     ray, and a world-space set of test constants would have to be parked and restored around
+//     every object (measured on the 182-object scene: 10 % of the frame).
 //
-// The set of leaves that reach Moller-Trumbore is therefore exactly the reference's; the
-// conservative test only decides which subtrees are opened on the way.  Rays with a reciprocal
-// direction beyond 1e30 (|d| < 1e-30 on some axis, where b * (1/d) could overflow) or coordinates
-// beyond 1e8 take the exact non-resumable walk, like rays with a non-finite reciprocal before.
+// The set of leaves that reach Moller-Trumbore / the object entry is therefore exactly the
+// reference's; the conservative test only decides which subtrees of a mesh are opened on the way.
+// Rays with a reciprocal direction beyond 1e30 (|d| < 1e-30 on some axis, where b * (1/d) could
+// overflow) or coordinates beyond 1e8 take the exact non-resumable walk, like rays with a
+// non-finite reciprocal before.
 //
-// State.  Registers ("hot", Trav2): the twelve test constants, the cull distance, the current
-// entry and the stack pointer.  Everything a NODE step does not touch lives in a per-lane record
-// reached through a strided view (shared memory in the kernel, a plain array on the host): the
-// object-space ray and its reciprocal for the exact leaf tests, the closest hit inside the object,
-// the closest hit overall, and the world-space constants parked while inside an object.  The
-// stack carries sentinel entries instead of a base pointer: {DONE} at the bottom, {EXIT} under
-// the entries of an object.
+// State.  Registers ("hot", Trav2): the twelve test constants of the object being walked, the
+// cull distance, the current entry, the stack pointer and the object (NONE in the TLAS).
+// Everything else lives in a per-lane record reached through a strided view (shared memory in the
+// kernel, a plain array on the host): the world ray and its reciprocal, the object-space ray and
+// its reciprocal for the exact triangle tests, the closest hit inside the object and overall.
+// The stack carries sentinel entries instead of a base pointer: {DONE} at the bottom, {EXIT}
+// under the entries of an object.
 struct Trav2
 {
     f3 p, q, cn, cf;
     float tcull;
     uint32_t cur;
     int sp;
+    uint32_t object; // SPB_T2_NO_OBJECT while in the TLAS
 };
 
 enum
 {
-    T2_OX = 0, T2_OY, T2_OZ, T2_DX, T2_DY, T2_DZ, T2_IX, T2_IY, T2_IZ, // ray of the current space, reciprocal
-    T2_LT, T2_LSLOT,                                                   // closest hit inside the object
-    T2_WORLDCULL, T2_OBJECT, T2_BT, T2_BSLOT, T2_BOBJECT, T2_SLOW,     // TravCold's fields (object = NONE in the TLAS)
-    T2_WP, T2_WQ = T2_WP + 3, T2_WCN = T2_WQ + 3, T2_WCF = T2_WCN + 3, // parked world-space constants
-    T2_WORDS = T2_WCF + 3
+    T2_OX = 0, T2_OY, T2_OZ, T2_DX, T2_DY, T2_DZ, T2_IX, T2_IY, T2_IZ,       // object-space ray, reciprocal
+    T2_LT, T2_LSLOT,                                                         // closest hit inside the object
+    T2_WOX, T2_WOY, T2_WOZ, T2_WDX, T2_WDY, T2_WDZ, T2_WIX, T2_WIY, T2_WIZ,  // world ray, reciprocal
+    T2_WORLDCULL, T2_BT, T2_BSLOT, T2_BOBJECT, T2_SLOW,                      // world cull distance while inside an object; closest hit overall
+    T2_WORDS
 };
 #define SPB_T2_NO_OBJECT 0xFFFFFFFFu
 
@@ -1062,6 +1068,14 @@ SPB_HD float slab_wide(float bminx, float bminy, float bminz, float bmaxx, float
     return (tnear <= tfar && tfar >= 0.0f) ? tnear : u2f(0x7F800000u);
 }
 
+// the reference's test of one child (world space: the TLAS), same return convention
+SPB_HD float slab_key(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, f3 o, f3 inv, float tlimit)
+{
+    float tnear;
+    const bool hit = slab_fast(bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, o, inv, tnear);
+    return (hit && tnear <= tlimit) ? tnear : u2f(0x7F800000u);
+}
+
 SPB_HD void trav2_push(Trav2 &st, TravEntry *stack, uint32_t ref, float tnear)
 {
     TravEntry e;
@@ -1094,7 +1108,7 @@ SPB_HD bool trav2_start(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STR
     st.sp = 0;
     st.tcull = u2f(0x7F800000u);
     st.cur = SPB_NODE_DONE;
-    v.u(T2_OBJECT) = SPB_T2_NO_OBJECT;
+    st.object = SPB_T2_NO_OBJECT;
     v.f(T2_BT) = -1.0f;
     v.u(T2_BSLOT) = 0;
     v.u(T2_BOBJECT) = 0xFFFFFFFFu;
@@ -1105,9 +1119,9 @@ SPB_HD bool trav2_start(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STR
         v.u(T2_SLOW) = 1;
         return false;
     }
-    v.set3(T2_OX, o);
-    v.set3(T2_DX, d);
-    v.set3(T2_IX, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z));
+    v.set3(T2_WOX, o);
+    v.set3(T2_WDX, d);
+    v.set3(T2_WIX, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z));
     return true;
 }
 
@@ -1116,29 +1130,52 @@ template <int STRIDE>
 SPB_HD void trav2_begin(const DScene &S, f3 o, f3 d, Trav2 &st, const T2View<STRIDE> &v, TravEntry *stack)
 {
     if (!trav2_start(S, o, d, st, v)) return;
-    trav2_constants(o, v.f3at(T2_IX), S.tlasExtent, st);
     trav2_push(st, stack, SPB_NODE_DONE, u2f(0xFF800000u));
     st.cur = S.tlasRoot;
 }
 
-// NODE step: st.cur is a node index.
-template <bool CULL>
-SPB_HD void trav2_node(const DScene &S, Trav2 &st, TravEntry *stack, Counters *counters)
+// NODE step: st.cur is a node index.  `tlas`: optional copy of the first `tlasCount` TLAS nodes in
+// shared memory (9 float4 per node: 8 + one of padding, so that a quarter-warp reading the same
+// word of eight different nodes hits eight different bank groups); null = read from global memory.
+template <bool CULL, int STRIDE>
+SPB_HD void trav2_node(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, TravEntry *stack, Counters *counters,
+                       const v4f *tlas = nullptr, uint32_t tlasCount = 0)
 {
     const float inf = u2f(0x7F800000u);
-    const v4f *n = S.nodes + (size_t)st.cur * 8;
     v4f minx, miny, minz, maxx, maxy, maxz, refsf, meta;
-    ld8(n + 0, minx, miny);
-    ld8(n + 2, minz, maxx);
-    ld8(n + 4, maxy, maxz);
-    ld8(n + 6, refsf, meta);
+    const uint32_t local = st.cur - S.tlasRoot;
+    if (tlas && st.object == SPB_T2_NO_OBJECT && local < tlasCount)
+    {
+        const v4f *n = tlas + (size_t)local * 9;
+        minx = n[0]; miny = n[1]; minz = n[2]; maxx = n[3]; maxy = n[4]; maxz = n[5]; refsf = n[6];
+    }
+    else
+    {
+        const v4f *n = S.nodes + (size_t)st.cur * 8;
+        ld8(n + 0, minx, miny);
+        ld8(n + 2, minz, maxx);
+        ld8(n + 4, maxy, maxz);
+        ld8(n + 6, refsf, meta);
+    }
     if (counters) counters->nodeVisits++;
 
     const float tlimit = CULL ? st.tcull : inf;
-    float k0 = slab_wide(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st, tlimit);
-    float k1 = slab_wide(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, st, tlimit);
-    float k2 = slab_wide(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, st, tlimit);
-    float k3 = slab_wide(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, st, tlimit);
+    float k0, k1, k2, k3;
+    if (st.object != SPB_T2_NO_OBJECT)
+    {
+        k0 = slab_wide(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st, tlimit);
+        k1 = slab_wide(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, st, tlimit);
+        k2 = slab_wide(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, st, tlimit);
+        k3 = slab_wide(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, st, tlimit);
+    }
+    else
+    {
+        const f3 o = v.f3at(T2_WOX), inv = v.f3at(T2_WIX);
+        k0 = slab_key(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, o, inv, tlimit);
+        k1 = slab_key(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, o, inv, tlimit);
+        k2 = slab_key(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, o, inv, tlimit);
+        k3 = slab_key(minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w, o, inv, tlimit);
+    }
     uint32_t r0 = f2u(refsf.x), r1 = f2u(refsf.y), r2 = f2u(refsf.z), r3 = f2u(refsf.w);
     if (CULL)
     {
@@ -1168,14 +1205,15 @@ SPB_HD void trav2_node(const DScene &S, Trav2 &st, TravEntry *stack, Counters *c
     trav2_pop<CULL>(st, stack);
 }
 
-// Object entry (sp_scene.cpp:274-276) for object `index` whose own world box passed the exact
-// test.  World ray (wo, wd) and its constants are parked; the walk continues in object space.
+// Object entry (sp_scene.cpp:274-276) for object `index`, whose own world box passed the exact
+// test.  The world ray is in the record; the walk continues in object space above `sentinel`.
 // Returns false (T2_SLOW set, st.cur = DONE) when the object-space ray needs the exact walk.
-template <bool CULL, bool PARK, int STRIDE>
-SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, f3 wo, f3 wd, Trav2 &st,
-                        const T2View<STRIDE> &v, TravEntry *stack, uint32_t sentinel)
+template <bool CULL, int STRIDE>
+SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, Trav2 &st, const T2View<STRIDE> &v,
+                        TravEntry *stack, uint32_t sentinel)
 {
     const float inf = u2f(0x7F800000u), ninf = u2f(0xFF800000u);
+    const f3 wo = v.f3at(T2_WOX), wd = v.f3at(T2_WDX);
     m4 invModel = load_m4(S.objInv + (size_t)index * 4);
     f3 lo = xform(invModel, wo, 1.0f);
     float scaleLen;
@@ -1187,14 +1225,7 @@ SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, f3 w
         st.cur = SPB_NODE_DONE;
         return false;
     }
-    if (PARK)
-    {
-        v.f(T2_WORLDCULL) = st.tcull;
-        v.set3(T2_WP, st.p);
-        v.set3(T2_WQ, st.q);
-        v.set3(T2_WCN, st.cn);
-        v.set3(T2_WCF, st.cf);
-    }
+    v.f(T2_WORLDCULL) = st.tcull;
     st.tcull = inf;
     const float bT = v.f(T2_BT);
     if (CULL && bT >= 0.0f) st.tcull = (bT + cull_pad(wo, bT)) * scaleLen * SPB_CULL_SLACK;
@@ -1204,7 +1235,7 @@ SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, f3 w
     v.set3(T2_IX, inv);
     v.f(T2_LT) = -1.0f;
     v.u(T2_LSLOT) = 0;
-    v.u(T2_OBJECT) = index;
+    st.object = index;
     trav2_constants(lo, inv, extent, st);
     trav2_push(st, stack, sentinel, ninf);
     st.cur = meshRoot;
@@ -1214,12 +1245,12 @@ SPB_HD bool trav2_enter(const DScene &S, uint32_t index, uint32_t meshRoot, f3 w
 // The object's closest hit carried back to world space (sp_scene.cpp:296-322); updates the closest
 // hit overall and returns the world cull distance that follows from it.
 template <int STRIDE>
-SPB_HD float trav2_leave(const DScene &S, f3 wo, f3 wd, float worldCull, const T2View<STRIDE> &v)
+SPB_HD float trav2_leave(const DScene &S, uint32_t object, float worldCull, const T2View<STRIDE> &v)
 {
     const float lT = v.f(T2_LT);
     if (lT >= 0.0f)
     {
-        const uint32_t object = v.u(T2_OBJECT);
+        const f3 wo = v.f3at(T2_WOX), wd = v.f3at(T2_WDX);
         m4 model = load_m4(S.objModel + (size_t)object * 4);
         f3 localHit = add3(v.f3at(T2_OX), mul3(v.f3at(T2_DX), lT));
         f3 worldHit = xform(model, localHit, 1.0f);
@@ -1239,35 +1270,23 @@ SPB_HD float trav2_leave(const DScene &S, f3 wo, f3 wd, float worldCull, const T
 
 // EXIT step (st.cur == SPB_NODE_EXIT): leave the object and go on with the TLAS entries below.
 template <bool CULL, int STRIDE>
-SPB_HD void trav2_exit(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, const v4f *ray, const TravEntry *stack)
+SPB_HD void trav2_exit(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, const TravEntry *stack)
 {
-    f3 wo, wd;
-    trav_world_ray(ray, wo, wd);
-    st.tcull = trav2_leave(S, wo, wd, v.f(T2_WORLDCULL), v);
-    st.p = v.f3at(T2_WP);
-    st.q = v.f3at(T2_WQ);
-    st.cn = v.f3at(T2_WCN);
-    st.cf = v.f3at(T2_WCF);
-    v.u(T2_OBJECT) = SPB_T2_NO_OBJECT;
-    // the world ray's reciprocal is p + q (one of them is zero); the exact test of the next object
-    // box needs it again
-    v.set3(T2_OX, wo);
-    v.set3(T2_DX, wd);
-    v.set3(T2_IX, mk3(st.p.x + st.q.x, st.p.y + st.q.y, st.p.z + st.q.z));
+    st.tcull = trav2_leave(S, st.object, v.f(T2_WORLDCULL), v);
+    st.object = SPB_T2_NO_OBJECT;
     trav2_pop<CULL>(st, stack);
 }
 
-// LEAF step: st.cur is SPB_REF_LEAF | slot -- a triangle (inside an object) or an object (TLAS)
-// whose box passed the conservative test of its parent's node step.
+// LEAF step: st.cur is SPB_REF_LEAF | slot -- inside an object a triangle whose box passed the
+// conservative test of its parent's node step; in the TLAS an object whose own box passed the
+// exact one.
 template <bool CULL, int STRIDE>
-SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, const v4f *ray, TravEntry *stack,
-                       Counters *counters)
+SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, TravEntry *stack, Counters *counters)
 {
-    (void)ray;
     const uint32_t index = st.cur & ~SPB_REF_LEAF;
-    const f3 o = v.f3at(T2_OX), inv = v.f3at(T2_IX);
-    if (v.u(T2_OBJECT) != SPB_T2_NO_OBJECT)
+    if (st.object != SPB_T2_NO_OBJECT)
     {
+        const f3 o = v.f3at(T2_OX), inv = v.f3at(T2_IX);
         const v4f *tp = S.tris + (size_t)index * 3;
         v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
         // the triangle's own box (sp_scene.cpp:35-50) and the reference's test of it (bvh.cpp:236-255)
@@ -1295,20 +1314,12 @@ SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, cons
     }
     else
     {
-        // the object's own world box, exactly (the TLAS leaf's box: sp_scene.cpp:98-116, bvh.cpp:236-255)
-        v4f bmin = ld4(S.objBox + (size_t)index * 2), bmax = ld4(S.objBox + (size_t)index * 2 + 1);
-        float tn;
-        const bool own = slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, inv, tn);
-        if (own && (!CULL || tn <= st.tcull))
+        v4u info = ld4u(S.objInfo + index);
+        if (counters) counters->objectTests++;
+        if (info.x != SPB_REF_EMPTY)
         {
-            v4u info = ld4u(S.objInfo + index);
-            if (counters) counters->objectTests++;
-            if (info.x != SPB_REF_EMPTY)
-            {
-                // (in the TLAS the record holds the world ray)
-                trav2_enter<CULL, true>(S, index, info.x, o, v.f3at(T2_DX), st, v, stack, SPB_NODE_EXIT);
-                return;
-            }
+            trav2_enter<CULL>(S, index, info.x, st, v, stack, SPB_NODE_EXIT);
+            return;
         }
     }
     trav2_pop<CULL>(st, stack);
@@ -1327,23 +1338,18 @@ SPB_HD void trav2_begin_single(const DScene &S, f3 o, f3 d, Trav2 &st, const T2V
     if (counters) counters->nodeVisits++;
     v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
     float tn;
-    if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, v.f3at(T2_IX), tn)) return;
+    if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, v.f3at(T2_WIX), tn)) return;
     v4u info = ld4u(S.objInfo);
     if (counters) counters->objectTests++;
     if (info.x == SPB_REF_EMPTY) return;
-    trav2_enter<CULL, false>(S, 0, info.x, o, d, st, v, stack, SPB_NODE_DONE);
+    trav2_enter<CULL>(S, 0, info.x, st, v, stack, SPB_NODE_DONE);
 }
 
-// End of a query: the closest hit.  `single`: the walk ended inside the one object.
+// End of a query: the closest hit.  (A single-object walk ends inside the object.)
 template <int STRIDE>
-SPB_HD Hit trav2_finish(const DScene &S, const v4f *ray, const T2View<STRIDE> &v, bool single)
+SPB_HD Hit trav2_finish(const DScene &S, const Trav2 &st, const T2View<STRIDE> &v)
 {
-    if (single && v.u(T2_OBJECT) != SPB_T2_NO_OBJECT && v.f(T2_LT) >= 0.0f)
-    {
-        f3 wo, wd;
-        trav_world_ray(ray, wo, wd);
-        trav2_leave(S, wo, wd, 0.0f, v);
-    }
+    if (st.object != SPB_T2_NO_OBJECT && !v.u(T2_SLOW)) trav2_leave(S, st.object, 0.0f, v);
     Hit h;
     h.t = v.f(T2_BT);
     h.object = (int32_t)v.u(T2_BOBJECT);
@@ -1364,20 +1370,17 @@ SPB_HD Hit intersect_scene_stepped2(const DScene &S, f3 o, f3 d, uint32_t *stack
     T2View<1> v;
     v.base = record;
     TravEntry entries[SPB_STACK_SIZE];
-    v4f ray[2];
-    ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
-    ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
     const bool single = S.objectCount == 1;
     if (single) trav2_begin_single<CULL>(S, o, d, st, v, entries, counters);
     else trav2_begin(S, o, d, st, v, entries);
     while (st.cur != SPB_NODE_DONE)
     {
-        if (st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(S, st, v, ray, entries);
-        else if ((st.cur & SPB_REF_LEAF) == 0) trav2_node<CULL>(S, st, entries, counters);
-        else trav2_leaf<CULL>(S, st, v, ray, entries, counters);
+        if (st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(S, st, v, entries);
+        else if ((st.cur & SPB_REF_LEAF) == 0) trav2_node<CULL>(S, st, v, entries, counters);
+        else trav2_leaf<CULL>(S, st, v, entries, counters);
     }
     if (v.u(T2_SLOW)) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
-    Hit h = trav2_finish(S, ray, v, single);
+    Hit h = trav2_finish(S, st, v);
     if (h.object >= 0) hit_barycentrics(S, o, d, h);
     return h;
 }
@@ -1888,7 +1891,7 @@ SPB_HD bool resolve_from_candidates2(const DScene &S, const uint32_t *list, f3 o
 {
     float bT;
     uint32_t bSlot;
-    const int status = resolve_candidates(S, list, o, d, v.f3at(T2_IX), counters, bT, bSlot);
+    const int status = resolve_candidates(S, list, o, d, v.f3at(T2_WIX), counters, bT, bSlot);
     if (status == 1) return false;
     st.cur = SPB_NODE_DONE;
     if (status == 2) { v.u(T2_SLOW) = 1; return true; }

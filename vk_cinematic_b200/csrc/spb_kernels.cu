@@ -305,6 +305,51 @@ void launch_collect_leaves(const DScene &scene, const float *origin3, const floa
     k_collect_leaves<<<1, 1, 0, stream>>>(scene, origin3, dir3, leaves, maxLeaves, countAndError);
 }
 
+// simd_RayIntersectAabb4 (simd.h:198-271) on the device, query by query: the three forms of the slab
+// test the kernels use, evaluated on the caller's boxes and (origin, reciprocal direction) exactly as
+// the reference's function takes them.  masks[q * 3 + 0] = slab_exact (the SSE semantics: the second
+// operand of min/max wins on NaN), [1] = slab_fast (hardware min/max; identical when no product is
+// NaN), [2] = the conservative test of the resumable traversal (slab_wide, padded by the query's
+// own extent) or 0xFFFFFFFF when the ray is one that machine hands to the exact walk (non-finite or
+// huge reciprocal).  Bit k = box k.  tnear[q * 4 + k] = entry distance of slab_exact.
+__global__ void k_slab_kat(uint32_t count, const float *boxMin12, const float *boxMax12, const float *origin3,
+                           const float *invDir3, uint32_t *masks, float *tnear)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const float *mn = boxMin12 + (size_t)q * 12, *mx = boxMax12 + (size_t)q * 12;
+    const f3 o = mk3(origin3[q * 3 + 0], origin3[q * 3 + 1], origin3[q * 3 + 2]);
+    const f3 inv = mk3(invDir3[q * 3 + 0], invDir3[q * 3 + 1], invDir3[q * 3 + 2]);
+    uint32_t exact = 0, fast = 0, wide = 0;
+    float extent = 0.0f;
+    for (int k = 0; k < 12; ++k) extent = fmaxf(extent, fmaxf(fabsf(mn[k]), fabsf(mx[k])));
+    const f3 d = mk3(1.0f / inv.x, 1.0f / inv.y, 1.0f / inv.z);
+    const bool machineRay = trav2_ray_ok(o, d, extent) && fabsf(inv.x) <= 1.0e30f && fabsf(inv.y) <= 1.0e30f && fabsf(inv.z) <= 1.0e30f;
+    Trav2 st;
+    st.p = st.q = st.cn = st.cf = mk3(0.0f, 0.0f, 0.0f);
+    if (machineRay) trav2_constants(o, inv, extent, st);
+    for (int k = 0; k < 4; ++k)
+    {
+        float tn = 0.0f, tf = 0.0f;
+        if (slab_exact(mn[k * 3 + 0], mn[k * 3 + 1], mn[k * 3 + 2], mx[k * 3 + 0], mx[k * 3 + 1], mx[k * 3 + 2], o, inv, tn)) exact |= 1u << k;
+        tnear[(size_t)q * 4 + k] = tn;
+        if (slab_fast(mn[k * 3 + 0], mn[k * 3 + 1], mn[k * 3 + 2], mx[k * 3 + 0], mx[k * 3 + 1], mx[k * 3 + 2], o, inv, tf)) fast |= 1u << k;
+        if (machineRay && slab_wide(mn[k * 3 + 0], mn[k * 3 + 1], mn[k * 3 + 2], mx[k * 3 + 0], mx[k * 3 + 1], mx[k * 3 + 2], st,
+                                    u2f(0x7F800000u)) < u2f(0x7F800000u))
+            wide |= 1u << k;
+    }
+    masks[(size_t)q * 3 + 0] = exact;
+    masks[(size_t)q * 3 + 1] = fast;
+    masks[(size_t)q * 3 + 2] = machineRay ? wide : 0xFFFFFFFFu;
+}
+
+void launch_slab_kat(uint32_t count, const float *boxMin12, const float *boxMax12, const float *origin3, const float *invDir3,
+                     uint32_t *masks, float *tnear, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    k_slab_kat<<<(count + 127) / 128, 128, 0, stream>>>(count, boxMin12, boxMax12, origin3, invDir3, masks, tnear);
+}
+
 template <int MATH, int ENVFILTER, bool CULL, bool STATS>
 __global__ void k_radiance_for_path(const DMaterials *materials, const float *path15, uint32_t n,
                                     float clampValue, float *out3)

@@ -85,6 +85,9 @@ void launch_intersect_mesh(const KernelConfig &cfg, const DScene &scene, uint32_
 void launch_collect_leaves(const DScene &scene, const float *origin3, const float *dir3,
                            uint32_t *leaves, uint32_t maxLeaves, uint32_t *countAndError,
                            cudaStream_t stream);
+// the device forms of simd_RayIntersectAabb4 on caller data (k_slab_kat): known-answer tests
+void launch_slab_kat(uint32_t count, const float *boxMin12, const float *boxMax12, const float *origin3, const float *invDir3,
+                     uint32_t *masks, float *tnear, cudaStream_t stream);
 // ComputeRadianceForPath over n vertices of 15 floats (materialId bits, P3, out3, in3, n3, uv2)
 void launch_radiance_for_path(const KernelConfig &cfg, const DMaterials *materials,
                               const float *path15, uint32_t n, float clampValue, float *out3,
@@ -133,6 +136,10 @@ bool lbvh_build_binary_device(const float *aabbMin, const float *aabbMax, uint32
 #endif
 #ifndef SPB_TRACE_MIN_BLOCKS
 #define SPB_TRACE_MIN_BLOCKS 5
+#endif
+// A/B knob: > 0 stages that many top-level TLAS nodes in shared memory (spb_wavefront.cu k_trace)
+#ifndef SPB_TLAS_SMEM_NODES
+#define SPB_TLAS_SMEM_NODES 0
 #endif
 // tile-row cost units (sp_b200_RenderRows tileRowCost): per sky-kernel sample / escaped ray / surface hit
 // (measured on C3: a sky-kernel sample ~5 ps since most sky pixels take one lookup, an escaped ray
@@ -185,7 +192,8 @@ struct WaveArgs
     v4f *out;                  // full image
     uint32_t *ctr;             // this pass's counters: bounces x WCTR_STRIDE
     unsigned long long *stats; // CTR_* slots (always valid; node/triangle counts only in stats launches)
-    unsigned long long *tileRowCost; // may be null
+    unsigned long long *tileRowCost; // may be null: cost units of the queue kernels per tile row (SPB_COST_MISS / _HIT)
+    unsigned long long *tileRowSky;  // may be null: cost units of the sky kernels per tile row (SPB_COST_SKY per sample run)
     uint32_t tileHeight;
     uint32_t costRow0;         // tile row that tileRowCost[0] stands for
     int countStats;            // 1: stats launch

@@ -150,8 +150,8 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 // record, hit/miss queue) and refilled from the ray queue.  In single-object scenes the object is
 // entered when the ray starts and left when it retires: both with every lane of the warp busy.
 // Registers hold what a node step touches (12 test constants, cull distance, current entry, stack
-// pointer); the rest of a lane's state is a 29-word record in shared memory, word-major so that
-// the lanes of a warp hit 32 different banks.
+// pointer, object); the rest of a lane's state is a 25-word record in shared memory, word-major so
+// that the lanes of a warp hit 32 different banks.
 template <bool CULL, bool STATS, bool PRIMARY>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -173,6 +173,20 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     volatile unsigned *ws = warpStateAll[threadIdx.x >> 5];
     if (lane < WS_COUNT) ws[lane] = 0;
     __syncwarp();
+#if SPB_TLAS_SMEM_NODES > 0
+    // north star: "hot top-level nodes staged in shared memory" -- the first SPB_TLAS_SMEM_NODES nodes
+    // of the TLAS (breadth-first: the top levels), 9 float4 each.  An A/B build (off by default: the
+    // counters that decided it are in profiles/r2/README.md).
+    __shared__ v4f tlasNodes[SPB_TLAS_SMEM_NODES * 9];
+    const unsigned tlasCount = single ? 0u : (a.scene.tlasNodeCount < SPB_TLAS_SMEM_NODES ? a.scene.tlasNodeCount : SPB_TLAS_SMEM_NODES);
+    for (unsigned i = threadIdx.x; i < tlasCount * 8u; i += SPB_TRACE_THREADS)
+        tlasNodes[(i >> 3) * 9 + (i & 7u)] = ld4(a.scene.nodes + (size_t)a.scene.tlasRoot * 8 + i);
+    __syncthreads();
+    const v4f *tlas = tlasCount ? tlasNodes : nullptr;
+#else
+    const v4f *tlas = nullptr;
+    const unsigned tlasCount = 0;
+#endif
     // chunk size: a quarter of an even share per warp, so small queues still spread over the GPU
     unsigned chunk = (total / (gridDim.x * (SPB_TRACE_THREADS / 32)) / 4 + 31u) & ~31u;
     chunk = chunk < 32u ? 32u : (chunk > SPB_CHUNK_MAX ? SPB_CHUNK_MAX : chunk);
@@ -181,6 +195,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     st.cur = SPB_NODE_DONE;
     st.sp = 0;
     st.tcull = 0.0f;
+    st.object = SPB_T2_NO_OBJECT;
     st.p = st.q = st.cn = st.cf = mk3(0.0f, 0.0f, 0.0f);
     rec.u(T2_SLOW) = 0;
     slot = 0;
@@ -199,14 +214,13 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             h.object = -1;
             if (finished)
             {
-                const v4f *ray = rays + (size_t)slot * 2;
                 if (rec.u(T2_SLOW))
                 {
                     f3 wo, wd;
-                    trav_world_ray(ray, wo, wd);
+                    trav_world_ray(rays + (size_t)slot * 2, wo, wd);
                     h = slow_intersect<CULL>(a.scene, wo, wd);
                 }
-                else h = trav2_finish(a.scene, ray, rec, single);
+                else h = trav2_finish(a.scene, st, rec);
             }
             const bool isHit = finished && h.t > 0.0f;
             const bool isMiss = finished && !isHit;
@@ -302,7 +316,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
         // ---- walk
         // lanes whose walk inside an object has ended leave it together (the exit arithmetic
         // would otherwise run for one or two lanes at a time); single-object scenes never get here
-        if (have && st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(a.scene, st, rec, rays + (size_t)slot * 2, stack);
+        if (have && st.cur == SPB_NODE_EXIT) trav2_exit<CULL>(a.scene, st, rec, stack);
         unsigned walking = __ballot_sync(SPB_FULL, have && trav_is_walking_ref(st.cur));
         if (!walking)
         {
@@ -318,11 +332,11 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             unsigned leafMask = walking & ~nodeMask;
             if (__popc(nodeMask) >= __popc(leafMask))
             {
-                if (wantNode) trav2_node<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr);
+                if (wantNode) trav2_node<CULL>(a.scene, st, rec, stack, STATS ? &cnt : nullptr, tlas, tlasCount);
             }
             else
             {
-                if (wantLeaf) trav2_leaf<CULL>(a.scene, st, rec, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                if (wantLeaf) trav2_leaf<CULL>(a.scene, st, rec, stack, STATS ? &cnt : nullptr);
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking_ref(st.cur));
         } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || exhausted));
@@ -987,12 +1001,16 @@ k_sky(const __grid_constant__ WaveArgs a)
                 if (listed) a.skyList[1 + base + __popc(mask & lanemask_lt())] = x | (y << 16);
             }
         }
-        if (a.tileRowCost)
+        if (a.tileRowSky)
         {
+            // the sky kernels' own cost class (their time is measured separately: spb_api.cu converts
+            // units to nanoseconds class by class); a pixel settled by one lookup costs a sample's worth
             unsigned row = active ? (y / a.tileHeight - a.costRow0) : 0xFFFFFFFFu;
             unsigned peers = __match_any_sync(SPB_FULL, row);
+            unsigned weight = (a.skyList && !listed) ? 1u : a.spp;
+            unsigned total = __reduce_add_sync(peers, active ? weight : 0u);
             if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
-                atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * a.spp * SPB_COST_SKY);
+                atomicAdd(&a.tileRowSky[row], (unsigned long long)total * SPB_COST_SKY);
         }
     }
     shaded = __reduce_add_sync(SPB_FULL, shaded);

@@ -281,6 +281,7 @@ _SIGNATURES = {
     "sp_b200_SetRaySorting": (None, [C.c_int]),
     "sp_b200_SetPrimaryCandidates": (None, [C.c_int]),
     "sp_b200_SetCopyOverlap": (None, [C.c_int]),
+    "sp_b200_RayIntersectAabb4Batch": (C.c_int, [u32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_TileCombinerStats": (None, [_P(C.c_uint64), _P(C.c_uint64)]),
     "sp_b200_SetDeviceTexture": (None, [C.c_void_p, C.c_void_p, u32, u32, C.c_void_p]),
     "sp_b200_SetRefillThresholds": (None, [u32, u32, u32]),
