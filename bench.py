@@ -546,24 +546,30 @@ def main():
         trace_log.append((st.traceMs, st.traceLaunches, int(st.tracedRays)) if e > b else (0.0, 0, 0))
         return m, cost, (st.kernelMs if e > b else 0.0), image
 
-    # ---- warm-up (also measures per-row cost and re-cuts the strips: every warm-up frame is one
-    # iteration of the rebalancing)
+    # ---- warm-up.  With several ranks every warm-up frame but the first is also one iteration of the
+    # strip rebalancing: the cut of the next frame is made from this frame's per-row cost (nanoseconds,
+    # sp_b200_RenderRows) scaled to what the rank's step took on the host clock -- kernels plus the
+    # rank's own launch and gather bookkeeping, which is what bounds its frame rate (NOT the time to
+    # the end of the gather, which waits for the slowest rank and would hide the imbalance).  The
+    # first frame allocates the working set and is not a measurement.
     bounds = strips.partition_rows(H, TH, world)
     frame = 0
     warmups = max(args.warmup, 3)
     history = []
     for w in range(warmups):
         barrier()
-        m, cost, kms, _ = render_step(frame, bounds, want_cost=True, wait_gather=True)
+        t_step = time.perf_counter()
+        m, cost, kms, _ = render_step(frame, bounds, want_cost=True, wait_gather=False)
+        step_s = time.perf_counter() - t_step
         torch.cuda.synchronize()
         frame += 1
         if world > 1:
-            # seconds = this rank's own render time (CUDA events around its kernels), NOT the step
-            # time: the gather waits for the slowest rank and would hide the imbalance
             row_cost, _secs = strips.gather_row_costs(
-                cost if cost is not None else np.zeros(0), kms * 1e-3, bounds, H, TH, dist, dev)
-            history.append({"strips": [int(b[1]) for b in bounds], "kernel_ms": [round(float(x) * 1e3, 3) for x in _secs]})
-            bounds = strips.partition_rows(H, TH, world, row_cost)
+                cost if cost is not None else np.zeros(0), step_s, bounds, H, TH, dist, dev)
+            history.append({"strips": [int(b[1]) for b in bounds], "step_ms": [round(float(x) * 1e3, 3) for x in _secs],
+                            "kernel_ms_rank0": round(kms, 3)})
+            if w >= 1:
+                bounds = strips.partition_rows(H, TH, world, row_cost)
 
     # ---- timed region: exactly K steps
     launches0 = sp.lib.sp_b200_KernelLaunchCount()
@@ -715,6 +721,11 @@ def main():
             secondary["c5"] = secondary_c5(sp, W, strips, args, rank, world, local, dev, dist if world > 1 else None, torch)
         except Exception as ex:
             secondary["c5"] = {"error": repr(ex)}
+    if rank == 0 and not args.no_secondary:
+        try:
+            secondary["reference_perf_tests"] = secondary_perf_tests(sp, W, local, world == 1 and not args.no_cpu_baseline)
+        except Exception as ex:
+            secondary["reference_perf_tests"] = {"error": repr(ex)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_time_sample(args, wl, args.cpu_seconds, "port")
@@ -767,6 +778,55 @@ def main():
                 os.unlink(shared_path)
             except OSError:
                 pass
+
+
+def secondary_perf_tests(sp, W, local, with_cpu):
+    """The reference's own performance tests (perf_tests/perf_tests.cpp:51-118 TestBvh -- the only
+    performance number the repository states: < 3100 cycles per ray; :212-305 TestMeshMidphase) with the
+    reference's seeded inputs restated draw for draw, as batched queries through the C ABI.  GPU figures:
+    CUDA-event time of the query kernel, best of 5 (rays resident).  with_cpu (N = 1, the cpu_baseline leg):
+    the same loops over the CPU checker, single-threaded as the reference runs them, and the two results
+    compared (leaf sets per ray; t bit for bit)."""
+    out = {}
+    mn, mx, o, d = W.perf_bvh_inputs(sp.xorshift_bilateral_stream(0x1A34C249))
+    r = sp.Renderer(local)
+    boxes = W.boxes_as_triangles(mn, mx)
+    t0 = time.perf_counter()
+    m = r.add_mesh(boxes.vertices, boxes.indices, False)
+    build_s = time.perf_counter() - t0
+    best, got = 1e30, None
+    for _ in range(6):
+        got, ms = sp.mesh_leaves_batch(r.meshes[m], o, d)
+        best = min(best, ms)
+    out["TestBvh"] = {"boxes": int(len(mn)), "rays": int(len(o)), "gpu_kernel_us": best * 1e3, "gpu_ns_per_ray": best * 1e6 / len(o),
+                      "gpu_tree_build_ms": build_s * 1e3, "leaves_per_ray": float(got[:, 0].mean()),
+                      "reference_assert": "cyclesPerRay < 3100 on one CPU core (perf_tests.cpp:115)"}
+    rays = 1024 * 8192
+    mesh, o2, d2 = W.perf_mesh_inputs(sp.xorshift_bilateral_stream(0x1A34C249), rays)
+    m2 = r.add_mesh(mesh.vertices, mesh.indices, False)
+    best2, t_got = 1e30, None
+    for _ in range(4):
+        t_got, tri_got, ms = sp.mesh_intersect_batch(r.meshes[m2], o2, d2)
+        best2 = min(best2, ms)
+    out["TestMeshMidphase"] = {"triangles": int(mesh.triangle_count), "rays": rays, "gpu_kernel_ms": best2,
+                               "gpu_ns_per_ray": best2 * 1e6 / rays, "gpu_mrays_per_s": rays / best2 / 1e3,
+                               "hits": int((t_got >= 0).sum())}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ora
+        lib = ora.load_ref() if ora.have_ref() else ora.load_port()
+        want, cpu_build, cpu_q = lib.perf_bvh(mn, mx, o, d, 2048)
+        out["TestBvh"].update({"cpu_ns_per_ray": cpu_q * 1e9 / len(o), "cpu_tree_build_ms": cpu_build * 1e3, "cpu_kind": lib.name,
+                               "leaf_sets_equal": bool(np.array_equal(want, got))})
+        n = 1 << 20   # bounded sample of the 8.4 M rays (about a second of one core)
+        s = lib.scene()
+        s.add_mesh(mesh.vertices, mesh.indices, False)
+        t_want, _tri, secs = s.perf_mesh(0, o2[:n], d2[:n])
+        s.close()
+        out["TestMeshMidphase"].update({"cpu_ns_per_ray": secs * 1e9 / n, "cpu_sample_rays": n, "cpu_kind": lib.name,
+                                        "t_bit_equal_on_sample": bool(np.array_equal(t_want.view(np.uint32), t_got[:n].view(np.uint32)))})
+    r.close()
+    return out
 
 
 def secondary_c5(sp, W, strips, args, rank, world, local, dev, dist, torch):

@@ -229,6 +229,18 @@ u32 sp_b200_DrainRayTracingWorkQueue(struct WorkQueue *queue, sp_Metrics *metric
 
 /* =============================== additions (sp_b200_*) =============================== */
 
+/* Batched forms of the two queries the reference's own performance tests time
+ * (perf_tests/perf_tests.cpp:51-118 TestBvh: bvh_IntersectRay; :212-305 TestMeshMidphase:
+ * sp_RayIntersectMesh), one ray per GPU thread, object-space rays against `mesh` (built by
+ * sp_BuildMeshMidphase).  Leaves: countXorSum[3 q + 0] = leaves whose own box ray q passes (what
+ * bvh_IntersectRay returns in `count`, without its 2048 cap), [1] = XOR of primitiveIndex * 0x9E3779B1,
+ * [2] = sum of the primitive indices: a fingerprint of the leaf set.  Mesh: t (-1 on a miss) and the
+ * triangle index.  kernelMs (optional): CUDA-event time of the kernel alone.  0 on success. */
+int sp_b200_MeshIntersectedLeavesBatch(sp_Mesh mesh, u32 count, const vec3 *rayOrigins, const vec3 *rayDirections,
+                                       u32 *countXorSum, f32 *kernelMs);
+int sp_b200_RayIntersectMeshBatch(sp_Mesh mesh, u32 count, const vec3 *rayOrigins, const vec3 *rayDirections, f32 *t,
+                                  i32 *triangleIndex, f32 *kernelMs);
+
 /* simd_RayIntersectAabb4 (simd.h:198-271) as the DEVICE evaluates it, for known-answer tests: `count`
  * queries of four boxes (boxMin / boxMax: count x 4 x 3 floats) against (rayOrigin, invRayDirection)
  * taken exactly as the reference's function takes them.  masks[q * 3 + 0]: the exact form with the
@@ -243,6 +255,13 @@ int sp_b200_RayIntersectAabb4Batch(u32 count, const f32 *boxMin, const f32 *boxM
 typedef void (*sp_b200_LogFn)(const char *message);
 
 enum { SP_B200_ENV_NEAREST = 0, SP_B200_ENV_BILINEAR = 1 };
+/* MOLLER_TRUMBORE: the reference's test, operation for operation (ray_intersection.cpp:156-190): the
+ * parity default.  WATERTIGHT: Woop / Benthin / Wald 2013 with the reference's acceptance rules (front
+ * faces, t > 0): no ray through a shared edge or vertex of two triangles can miss both.  It decides
+ * those edge cases differently from the reference BY DESIGN, so images can differ from the
+ * reference's in the pixels such rays belong to; every other guarantee (scheduler independence,
+ * multi-GPU split) holds in both modes. */
+enum { SP_B200_TRIANGLE_MOLLER_TRUMBORE = 0, SP_B200_TRIANGLE_WATERTIGHT = 1 };
 enum { SP_B200_MATH_F64_ROUNDED = 0, SP_B200_MATH_FAST_F32 = 1 };
 /* WAVEFRONT: ray generation / traversal / shading as separate kernels over compact device
  * queues with warp-level lane refill (the default).  PER_PIXEL: one thread walks all samples and
@@ -263,6 +282,7 @@ typedef struct sp_b200_Params {
     u32 renderMode;      /* SP_B200_RENDER_*: how sp_b200_Render* schedules the work on the GPU */
     u32 samplesPerPass;  /* wavefront mode: samples per pixel traced per pass; 0 = automatic (all
                             of them, in bands of rows sized by sp_b200_SetPathsPerPass) */
+    u32 triangleTest;    /* SP_B200_TRIANGLE_*: the ray / triangle test of every traversal */
 } sp_b200_Params;
 
 /* Kernel-side counters of the most recent launch (for the roofline). */
@@ -358,6 +378,17 @@ void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */
 void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
+/* `count` draws of the reference's XorShift32 (math_utils.h:184-196) continuing *state (host side,
+ * integer only): what seeded inputs like the reference's perf tests' are generated from. */
+void sp_b200_XorShift32Stream(u32 *state, u32 count, u32 *values);
+/* Progressive accumulation across frames (the reference's own to-do, main.cpp:75): deviceAccum
+ * (pixelCount RGBA f32 on the device, owned by the caller) becomes the running mean of the frames
+ * folded in so far, accum += (frame - accum) / (framesAccumulated + 1) per colour component in f32
+ * (framesAccumulated = 0 copies the frame).  The new frame comes from deviceFrame or, if that is
+ * NULL, from hostFrame; hostAccumOut (optional) receives the updated mean.  With sp_b200_RenderFrame's
+ * per-(pixel, sample, frame) seeds, N frames of S samples accumulate to N x S independent samples. */
+int sp_b200_AccumulateFrame(void *deviceAccum, const void *deviceFrame, const f32 *hostFrame, u32 pixelCount,
+                            u32 framesAccumulated, f32 *hostAccumOut);
 /* Seed of the per-(pixel, sample, frame) XorShift32 stream used by sp_b200_Render*. */
 u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
 

@@ -167,6 +167,18 @@ uint32_t ora_compute_tiles(uint32_t w, uint32_t h, uint32_t tw, uint32_t th, uin
 uint32_t ora_bvh_query(const float *aabbMin, const float *aabbMax, uint32_t n, const float *o3,
                        const float *d3, uint32_t *leaves, uint32_t maxLeaves, uint32_t *error,
                        uint32_t *aabbTests, float *rootBounds6);
+/* The reference's performance tests as library calls (perf_tests/perf_tests.cpp:51-118 TestBvh,
+ * :212-305 TestMeshMidphase), single-threaded like there.  Both return the wall seconds of the
+ * query loop alone (steady_clock).
+ *   ora_perf_bvh: one tree over `n` boxes (bvh_CreateTree; *buildSeconds if not NULL), then
+ *     bvh_IntersectRay for every ray with a `maxLeaves`-entry result array; countXorSum[3 q + 0] = leaves
+ *     reported for ray q, [1] = XOR of leafIndex * 0x9E3779B1, [2] = sum of the leaf indices.
+ *   ora_perf_mesh: sp_RayIntersectMesh(mesh `mesh` of the scene) for every object-space ray; t[q]
+ *     (-1 = miss), tri[q] (-1 = miss; the port reports the triangle, the reference driver -2 = unknown). */
+double ora_perf_bvh(const float *aabbMin, const float *aabbMax, uint32_t n, uint32_t rays, const float *origins3,
+                    const float *dirs3, uint32_t maxLeaves, uint32_t *countXorSum, double *buildSeconds);
+double ora_perf_mesh(ora_Scene *s, uint32_t mesh, uint32_t rays, const float *origins3, const float *dirs3, float *t,
+                     int32_t *tri);
 /* Tree statistics of mesh `mesh` midphase: out[0]=leafCount out[1]=internalCount
  * out[2]=minDepth out[3]=maxDepth out[4]=allLeavesReachable out[5]=parentsContainChildren */
 void ora_mesh_tree_stats(ora_Scene *s, uint32_t mesh, uint32_t *out6);

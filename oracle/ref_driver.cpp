@@ -869,6 +869,61 @@ extern "C" uint32_t ora_bvh_query(const float *aabbMin, const float *aabbMax, ui
     return r.count;
 }
 
+// perf_tests/perf_tests.cpp:51-118 (TestBvh) and :212-305 (TestMeshMidphase) as calls: the reference's
+// own functions, single-threaded, timed around the query loop only.
+extern "C" double ora_perf_bvh(const float *aabbMin, const float *aabbMax, uint32_t n, uint32_t rays, const float *origins3,
+                               const float *dirs3, uint32_t maxLeaves, uint32_t *countXorSum, double *buildSeconds)
+{
+    bvh_Tree tree = {};
+    std::vector<u8> storage;
+    auto b0 = std::chrono::steady_clock::now();
+    if (n > 0)
+    {
+        size_t bytes = (size_t)n * 10 * sizeof(bvh_Node) + 2 * (size_t)n * sizeof(bvh_NodeDistSqPair) + 4096;
+        storage.resize(bytes);
+        MemoryArena arena;
+        InitializeMemoryArena(&arena, storage.data(), bytes);
+        tree = bvh_CreateTree(&arena, (vec3 *)aabbMin, (vec3 *)aabbMax, n);
+    }
+    if (buildSeconds) *buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+    std::vector<bvh_Node *> nodes(maxLeaves ? maxLeaves : 1);
+    std::vector<uint32_t> counts(rays);
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t q = 0; q < rays; ++q)
+    {
+        bvh_IntersectRayResult r = bvh_IntersectRay(&tree, Vec3(origins3[q * 3], origins3[q * 3 + 1], origins3[q * 3 + 2]),
+            Vec3(dirs3[q * 3], dirs3[q * 3 + 1], dirs3[q * 3 + 2]), nodes.data(), maxLeaves);
+        // (the fingerprint is part of the timed loop on purpose: without a use of the result the
+        // compiler may drop the query, and it is a few integer operations per reported leaf)
+        uint32_t x = 0, sum = 0;
+        for (u32 i = 0; i < r.count; ++i)
+        {
+            x ^= nodes[i]->leafIndex * 0x9E3779B1u;
+            sum += nodes[i]->leafIndex;
+        }
+        countXorSum[q * 3 + 0] = r.count;
+        countXorSum[q * 3 + 1] = x;
+        countXorSum[q * 3 + 2] = sum;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+extern "C" double ora_perf_mesh(ora_Scene *s, uint32_t mesh, uint32_t rays, const float *origins3, const float *dirs3,
+                                float *t, int32_t *tri)
+{
+    sp_Metrics metrics = {};
+    sp_Mesh m = s->meshes[mesh];
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t q = 0; q < rays; ++q)
+    {
+        sp_RayIntersectMeshResult r = sp_RayIntersectMesh(m, Vec3(origins3[q * 3], origins3[q * 3 + 1], origins3[q * 3 + 2]),
+            Vec3(dirs3[q * 3], dirs3[q * 3 + 1], dirs3[q * 3 + 2]), &metrics);
+        t[q] = r.triangleIntersection.t;
+        if (tri) tri[q] = r.triangleIntersection.t >= 0.0f ? -2 : -1;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 extern "C" void ora_mesh_tree_stats(ora_Scene *s, uint32_t mesh, uint32_t *out6)
 {
     sp_Mesh *m = &s->meshes[mesh];

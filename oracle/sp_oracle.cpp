@@ -1502,6 +1502,51 @@ extern "C" uint32_t ora_bvh_query(const float *aabbMin, const float *aabbMax, ui
     return q.count;
 }
 
+// perf_tests/perf_tests.cpp:51-118 (TestBvh) and :212-305 (TestMeshMidphase) as calls, single-threaded
+extern "C" double ora_perf_bvh(const float *aabbMin, const float *aabbMax, uint32_t n, uint32_t rays, const float *origins3,
+                               const float *dirs3, uint32_t maxLeaves, uint32_t *countXorSum, double *buildSeconds)
+{
+    auto b0 = std::chrono::steady_clock::now();
+    Tree tree = grow_tree((const V3 *)aabbMin, (const V3 *)aabbMax, n);
+    if (buildSeconds) *buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+    std::vector<int> out, st[2];
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t q = 0; q < rays; ++q)
+    {
+        Query r = walk_tree(tree, P3(origins3[q * 3], origins3[q * 3 + 1], origins3[q * 3 + 2]),
+                            P3(dirs3[q * 3], dirs3[q * 3 + 1], dirs3[q * 3 + 2]), out, maxLeaves, st);
+        uint32_t x = 0, sum = 0;
+        for (uint32_t i = 0; i < r.count; ++i)
+        {
+            uint32_t leaf = (uint32_t)tree.nodes[out[i]].leaf;
+            x ^= leaf * 0x9E3779B1u;
+            sum += leaf;
+        }
+        countXorSum[q * 3 + 0] = r.count;
+        countXorSum[q * 3 + 1] = x;
+        countXorSum[q * 3 + 2] = sum;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+extern "C" double ora_perf_mesh(ora_Scene *s, uint32_t mesh, uint32_t rays, const float *origins3, const float *dirs3,
+                                float *t, int32_t *tri)
+{
+    Counters64 m;
+    memset(&m, 0, sizeof(m));
+    Scratch sc;
+    const Mesh &me = s->meshes[mesh];
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t q = 0; q < rays; ++q)
+    {
+        MeshHit h = hit_mesh(me, P3(origins3[q * 3], origins3[q * 3 + 1], origins3[q * 3 + 2]),
+                             P3(dirs3[q * 3], dirs3[q * 3 + 1], dirs3[q * 3 + 2]), &m, &sc);
+        t[q] = h.tri.t;
+        if (tri) tri[q] = h.triangle;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 static void tree_stats(const Tree &t, int ni, uint32_t depth, uint32_t *leaves, uint32_t *internal,
                        uint32_t *minDepth, uint32_t *maxDepth, uint32_t *contained, std::vector<uint8_t> *seen)
 {

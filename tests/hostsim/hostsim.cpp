@@ -117,6 +117,10 @@ extern "C" int ora_add_object(ora_Scene *s, uint32_t mesh, uint32_t material, co
     return (int)s->objects.size() - 1;
 }
 
+// 1: the watertight triangle test (sp_b200_Params::triangleTest) in every later ora_build
+static uint32_t g_hostsimTriangleTest = 0;
+extern "C" void hostsim_set_triangle_test(uint32_t test) { g_hostsimTriangleTest = test; }
+
 extern "C" void ora_build(ora_Scene *s)
 {
     s->flat = flatten_scene(s->objects);
@@ -132,6 +136,7 @@ extern "C" void ora_build(ora_Scene *s)
     s->d.objectCount = s->flat.objectCount;
     s->d.tlasExtent = s->flat.tlasExtent;
     s->d.tlasNodeCount = s->flat.tlasNodeCount;
+    s->d.triangleTest = g_hostsimTriangleTest;
 }
 
 // what flatten_scene() made of the scene: [0] worst-case traversal stack entries (TLAS + deepest
@@ -191,18 +196,20 @@ extern "C" uint32_t ora_seed(uint32_t pixelIndex, uint32_t sample, uint32_t fram
 
 static int g_hostsimCull = 1;
 extern "C" void hostsim_set_cull(int cull) { g_hostsimCull = cull; }
-// 1: traverse with the resumable state machine the wavefront kernels use (trav_step)
+// 1: traverse with the resumable state machine the production trace kernel runs (single-object entry
+// at the start included); 2: the second machine (A/B build -DSPB_TRAV2); 0: the non-resumable walk
 static int g_hostsimStepped = 0;
 extern "C" void hostsim_set_stepped(int stepped) { g_hostsimStepped = stepped; }
 
 template <bool CULL>
 static Hit hs_intersect(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT)
 {
-    return g_hostsimStepped ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, nullptr)
-                            : intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+    return g_hostsimStepped == 1 ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, nullptr)
+           : g_hostsimStepped == 2 ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, nullptr)
+                                   : intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
 }
 
-template <bool CULL, bool STEPPED>
+template <bool CULL, int STEPPED>
 static void render_rows(ora_Scene *s, float *rgba, uint32_t x0, uint32_t y0, uint32_t x1,
                         uint32_t y1, uint32_t spp, uint32_t bounces, uint32_t frame,
                         uint32_t tid, uint32_t threads, uint64_t *m)
@@ -242,14 +249,13 @@ extern "C" void ora_render_seeded(ora_Scene *s, float *rgba, uint32_t x0, uint32
     if (threads == 0) threads = 1;
     std::vector<std::vector<uint64_t>> per(threads, std::vector<uint64_t>(ORA_METRIC_COUNT, 0));
     auto worker = [&](uint32_t tid) {
-        if (g_hostsimCull && g_hostsimStepped)
-            render_rows<true, true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
-        else if (g_hostsimCull)
-            render_rows<true, false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
-        else if (g_hostsimStepped)
-            render_rows<false, true>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
-        else
-            render_rows<false, false>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, per[tid].data());
+        uint64_t *out = per[tid].data();
+        if (g_hostsimCull && g_hostsimStepped == 1) render_rows<true, 1>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
+        else if (g_hostsimCull && g_hostsimStepped == 2) render_rows<true, 2>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
+        else if (g_hostsimCull) render_rows<true, 0>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
+        else if (g_hostsimStepped == 1) render_rows<false, 1>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
+        else if (g_hostsimStepped == 2) render_rows<false, 2>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
+        else render_rows<false, 0>(s, rgba, x0, y0, x1, y1, spp, bounces, frame, tid, threads, out);
     };
     std::vector<std::thread> pool;
     for (uint32_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
@@ -467,20 +473,18 @@ extern "C" void hostsim_check_shortcuts(ora_Scene *s, uint32_t spp, uint32_t fra
                     uint32_t rng = stream_seed(x + y * c.width, sample, frame);
                     f3 o, d;
                     primary_ray(c, x, y, rng, o, d);
-                    Hit walk = intersect_scene_stepped2<true>(s->d, o, d, stack, stackT, nullptr);
+                    Hit walk = intersect_scene_stepped<true>(s->d, o, d, stack, stackT, nullptr);
                     o9[1]++;
                     if (walk.t > 0.0f) allMiss = false;
                     total = add3(total, mul3(miss_radiance<0, 0>(s->dm, neg3(d), 10.0f, nullptr), weight));
                     if (list[0] == SPB_CAND_FALLBACK) continue;
-                    // what k_trace<PRIMARY> does with the list (second machine)
-                    Trav2 st;
-                    float record[T2_WORDS];
-                    T2View<1> view;
-                    view.base = record;
-                    if (!trav2_start(s->d, o, d, st, view)) continue;      // empty scene / exact walk
-                    if (!resolve_from_candidates2(s->d, list, o, d, st, view, nullptr)) continue; // the walk takes over
-                    if (view.u(T2_SLOW)) continue;
-                    Hit fast = trav2_finish(s->d, st, view);
+                    // what k_trace<PRIMARY> does with the list
+                    Trav st;
+                    TravCold cold;
+                    trav_begin(s->d, o, d, st, cold);
+                    resolve_from_candidates(s->d, list, o, d, st, cold, nullptr);
+                    if (st.cur != SPB_NODE_DONE || cold.slow) continue; // the walk takes over
+                    Hit fast = trav_result(cold);
                     bool same = f2u(fast.t) == f2u(walk.t) && fast.object == walk.object && (fast.object < 0 || fast.slot == walk.slot);
                     if (!same)
                     {

@@ -145,6 +145,11 @@ class OracleLib:
         lib.ora_compute_tiles.restype = C.c_uint32
         lib.ora_bvh_query.argtypes = [_f, _f, C.c_uint32, _f, _f, _u, C.c_uint32, _u, _u, _f]
         lib.ora_bvh_query.restype = C.c_uint32
+        if hasattr(lib, "ora_perf_bvh"):
+            lib.ora_perf_bvh.argtypes = [_f, _f, C.c_uint32, C.c_uint32, _f, _f, C.c_uint32, _u, C.POINTER(C.c_double)]
+            lib.ora_perf_bvh.restype = C.c_double
+            lib.ora_perf_mesh.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _f, _f, _f, C.POINTER(C.c_int32)]
+            lib.ora_perf_mesh.restype = C.c_double
         lib.ora_mesh_tree_stats.argtypes = [C.c_void_p, C.c_uint32, _u]
         self.name = lib.ora_name().decode()
         self.max_bounces = lib.ora_max_bounces()
@@ -285,6 +290,15 @@ class OracleLib:
         return {"count": n, "leaves": leaves[:n].copy(), "error": bool(err.value),
                 "aabb_tests": tests.value, "root_min": root[0:3], "root_max": root[3:6]}
 
+    def perf_bvh(self, aabb_min, aabb_max, origins, dirs, max_leaves):
+        """TestBvh's loop (perf_tests.cpp:101-108): (count, xor, sum) per ray, build seconds, query seconds."""
+        mn, mx = _f32(aabb_min).reshape(-1, 3), _f32(aabb_max).reshape(-1, 3)
+        o, d = _f32(origins).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        out = np.zeros((len(o), 3), np.uint32)
+        build = C.c_double()
+        secs = self.lib.ora_perf_bvh(_fp(mn), _fp(mx), len(mn), len(o), _fp(o), _fp(d), max_leaves, _up(out), C.byref(build))
+        return out, build.value, secs
+
     def scene(self):
         return OracleScene(self)
 
@@ -317,6 +331,13 @@ class OracleScene:
                    scale=(1, 1, 1)):
         return self.lib.ora_add_object(self.h, mesh, material, _fp(_f32(position)),
                                        _fp(_f32(rotation)), _fp(_f32(scale)))
+
+    def perf_mesh(self, mesh, origins, dirs):
+        """TestMeshMidphase's loop (perf_tests.cpp:240-276): t and triangle per ray, wall seconds."""
+        o, d = _f32(origins).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
+        secs = self.lib.ora_perf_mesh(self.h, mesh, len(o), _fp(o), _fp(d), _fp(t), tri.ctypes.data_as(C.POINTER(C.c_int32)))
+        return t, tri, secs
 
     def build(self):
         self.lib.ora_build(self.h)
@@ -474,6 +495,7 @@ def load_hostsim():
     o.lib.hostsim_set_stepped.argtypes = [C.c_int]
     o.lib.hostsim_check_wide_slab.argtypes = [C.c_uint32, C.c_uint32, _u64]
     o.lib.hostsim_flat_info.argtypes = [C.c_void_p, _u]
+    o.lib.hostsim_set_triangle_test.argtypes = [C.c_uint32]
     return o
 
 

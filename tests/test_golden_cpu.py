@@ -66,11 +66,13 @@ def test_g3_port_rays_and_image(port, port_dm):
 # hostsim = vk_cinematic_b200/csrc/spb_core.cuh + the host builder compiled for the host: the
 # LOGIC of the CUDA path (not the GPU) against the reference's outputs.  No GPU parity claim.
 
-@pytest.mark.parametrize("stepped", [0, 1])
+@pytest.mark.parametrize("stepped", [0, 1, 2])
 @pytest.mark.parametrize("cull", [1, 0])
 def test_hostsim_logic_against_golden(hostsim, cull, stepped):
-    """stepped = 1 traverses with the resumable state machine of the wavefront kernels
-    (spb_core.cuh trav_step), 0 with the recursive-descent form of the per-pixel kernels."""
+    """stepped = 1 traverses with the resumable state machine of the production trace kernel
+    (spb_core.cuh trav_*, single-object entry at ray start included), 2 with the second machine
+    (conservative inner tests, -DSPB_TRAV2 builds), 0 with the non-resumable walk of the per-pixel
+    kernels."""
     hostsim.lib.hostsim_set_cull(cull)
     hostsim.lib.hostsim_set_stepped(stepped)
     g = gold("g1_bunny_96x64.npz")
@@ -229,7 +231,7 @@ def test_nested_objects_tlas_stays_inside_its_stack_share(hostsim, port_dm):
     ia, ma = a.render_seeded(spp=1, bounces=3, frame=1)
     pa = a.primary_hits()
     assert len(np.unique(pa["obj"])) > 8            # rings of ever larger quads, seen through each other
-    for stepped in (0, 1):
+    for stepped in (0, 1, 2):
         hostsim.lib.hostsim_set_stepped(stepped)
         b = hostsim.scene().load_workload(wl)
         info = np.zeros(4, np.uint32)
@@ -242,3 +244,47 @@ def test_nested_objects_tlas_stays_inside_its_stack_share(hostsim, port_dm):
         b.close()
     hostsim.lib.hostsim_set_stepped(0)
     a.close()
+
+
+def _crack_scene(lib_scene, mesh):
+    s = lib_scene
+    s.add_mesh(mesh.vertices, mesh.indices, False)
+    s.add_object(0, W.MATERIAL_SURFACE)
+    s.build()
+    return s
+
+
+def test_hostsim_watertight_option_closes_the_cracks(hostsim, port):
+    """sp_b200_Params::triangleTest = WATERTIGHT (north star: "watertight ray-triangle intersection"; an
+    option, never the parity default -- SURVEY.md §0).  200 000 rays aimed at points lying exactly on
+    shared edges and vertices of a sheet of triangles: the reference's Moller-Trumbore
+    (ray_intersection.cpp:156-190), which tests the two neighbours independently, lets some of them
+    through (and the device restatement of it must leak exactly the rays the port leaks: parity includes
+    the cracks); the watertight test must let none through, and away from those rays it must agree with
+    Moller-Trumbore on what is hit and, to a few ulps, where."""
+    mesh, o, d = W.crack_test_inputs()
+    a = _crack_scene(port.scene(), mesh)
+    ra = a.intersect_rays(o, d)
+    a.close()
+    hostsim.lib.hostsim_set_stepped(1)
+    b = _crack_scene(hostsim.scene(), mesh)
+    rb = b.intersect_rays(o, d)
+    b.close()
+    hostsim.lib.hostsim_set_triangle_test(1)
+    c = _crack_scene(hostsim.scene(), mesh)
+    rc = c.intersect_rays(o, d)
+    for other in (0, 2):                                 # the non-resumable walk; the second machine
+        hostsim.lib.hostsim_set_stepped(other)
+        rco = c.intersect_rays(o, d)
+        assert int((rco["t"] < 0).sum()) == 0 and same_bits(rco["t"], rc["t"])
+    c.close()
+    hostsim.lib.hostsim_set_triangle_test(0)
+    assert same_bits(ra["t"], rb["t"])                    # parity, cracks included
+    differ = ra["tri"] != rb["tri"]                      # rays ON an edge meet both neighbours at bit-equal t:
+    assert np.all(ra["tri"][differ] >= 0) and np.all(rb["tri"][differ] >= 0)   # the winner is the order's
+    leaks_mt, leaks_wt = int((rb["t"] < 0).sum()), int((rc["t"] < 0).sum())
+    assert leaks_wt == 0, leaks_wt
+    assert leaks_mt > 0, "the sheet was meant to show the reference's cracks"
+    both = (rb["t"] > 0) & (rc["t"] > 0)
+    assert both.sum() > 150000
+    assert np.all(np.abs(rb["t"][both] - rc["t"][both]) <= 1e-5 * np.abs(rb["t"][both]))

@@ -525,7 +525,7 @@ def test_device_slab_kats(gpu_sp):
         rng = np.random.RandomState(0x1A34C249 & 0x7FFFFFFF)
         n = 20000
         c = rng.uniform(-2, 2, (n, 4, 3)).astype(np.float32)
-        h = (rng.uniform(0, 1, (n, 4, 3)) ** 3).astype(np.float32)
+        h = (1.5 * rng.uniform(0, 1, (n, 4, 3)) ** 2).astype(np.float32)
         h[rng.rand(n, 4, 3) < 0.1] = 0.0                             # flat boxes
         lo, hi = (c - h).astype(np.float32), (c + h).astype(np.float32)
         o = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
@@ -543,7 +543,7 @@ def test_device_slab_kats(gpu_sp):
     assert finite.sum() > 15000 and np.array_equal(masks[finite, 1], want[finite])
     machine = masks[:, 2] != 0xFFFFFFFF
     assert machine.sum() > 15000 and not np.any(want[machine] & ~masks[machine, 2])
-    assert (want != 0).sum() > 1000
+    assert (want != 0).sum() > 500
 
 
 def test_metrics_mesh_test_counters(gpu_sp):
@@ -576,6 +576,109 @@ def test_metrics_mesh_test_counters(gpu_sp):
     sp.lib.sp_b200_EnableStats(0)
     sp.set_params(samplesPerPixel=1, bounceCount=3, cullByDistance=1, renderMode=0)
     chk.close()
+    r.close()
+
+
+def test_watertight_option(gpu_sp):
+    """sp_b200_Params::triangleTest = WATERTIGHT on the device (per-ray query kernel and both render
+    schedulers).  (a) 200 000 rays aimed exactly at shared edges / vertices of a sheet: with the default
+    test the GPU leaks exactly the rays the checker's Moller-Trumbore leaks (t bit for bit); with the
+    watertight test it leaks none.  (b) an image of the sheet seen from above: no pixel of the sheet's
+    interior may show the sky in watertight mode, in either scheduler, and the two schedulers agree bit
+    for bit in that mode as well."""
+    sp = gpu_sp
+    mesh, o, d = W.crack_test_inputs()
+    chk = best(False).scene()
+    chk.add_mesh(mesh.vertices, mesh.indices, False)
+    chk.add_object(0, W.MATERIAL_SURFACE)
+    chk.build()
+    want = chk.intersect_rays(o, d)
+    chk.close()
+    r = sp.Renderer()
+    r.add_object(r.add_mesh(mesh.vertices, mesh.indices, False), W.MATERIAL_SURFACE)
+    r.build()
+    sp.set_params(triangleTest=sp.TRIANGLE_MOLLER_TRUMBORE)
+    got = r.intersect_rays(o, d)
+    assert same_bits(got["t"], want["t"]) and int((got["t"] < 0).sum()) > 0      # parity includes the cracks
+    sp.set_params(triangleTest=sp.TRIANGLE_WATERTIGHT)
+    wt = r.intersect_rays(o, d)
+    assert int((wt["t"] < 0).sum()) == 0
+    both = got["t"] > 0
+    assert np.all(np.abs(wt["t"][both] - got["t"][both]) <= 1e-5 * np.abs(got["t"][both]))
+    # (b) every pixel whose centre ray points into the sheet's interior must hit it
+    for m_id, kw in ((W.MATERIAL_BACKGROUND, dict(emission=(0.0, 0.0, 0.0))), (W.MATERIAL_SURFACE, dict(albedo=(0, 0, 0), emission=(1.0, 1.0, 1.0), roughness=0.5))):
+        r.register_material(m_id, **kw)
+    r.set_background(W.MATERIAL_BACKGROUND)
+    r.configure_camera((0.0, 0.0, 2.0), (0.0, 0.0, 0.0, 1.0), 0.8, 256, 256)
+    images = []
+    for mode in (0, 1):
+        sp.set_params(samplesPerPixel=4, bounceCount=1, renderMode=mode, triangleTest=sp.TRIANGLE_WATERTIGHT)
+        img, m = r.render_frame(frame=1)
+        images.append(img.copy())
+        inner = img[64:192, 64:192, 0]                 # well inside the sheet's projection
+        assert np.all(inner == 1.0), int((inner != 1.0).sum())
+    assert same_bits(images[0], images[1])
+    sp.set_params(samplesPerPixel=1, bounceCount=3, renderMode=0, triangleTest=sp.TRIANGLE_MOLLER_TRUMBORE)
+    r.close()
+
+
+def test_progressive_accumulation(gpu_sp):
+    """sp_b200_AccumulateFrame: the running mean of frames (the reference's own to-do, main.cpp:75).
+    Six frames of 2 spp folded in on the device equal the same recurrence in numpy float32, bit for bit,
+    and approach the 12-spp-per-pixel mean."""
+    import torch
+    sp = gpu_sp
+    wl = W.config1(160, 120, env_size=(256, 128))
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=2, bounceCount=3)
+    n = wl.width * wl.height
+    accum = torch.zeros((wl.height, wl.width, 4), dtype=torch.float32, device="cuda:0")
+    ref = None
+    out = np.zeros((wl.height, wl.width, 4), np.float32)
+    for f in range(6):
+        img, _ = r.render_frame(frame=f)
+        img = img.copy()
+        assert sp.lib.sp_b200_AccumulateFrame(accum.data_ptr(), None, img.ctypes.data, n, f, out.ctypes.data) == 0
+        if f == 0:
+            ref = img.copy()
+        else:
+            ref[..., 0:3] = ref[..., 0:3] + (img[..., 0:3] - ref[..., 0:3]) / np.float32(f + 1)
+            ref[..., 3] = img[..., 3]
+        assert same_bits(out, ref), f
+    assert same_bits(accum.cpu().numpy(), ref)
+    sp.set_params(samplesPerPixel=1, bounceCount=3)
+    r.close()
+
+
+def test_reference_perf_test_queries(gpu_sp):
+    """The queries of the reference's own performance tests (perf_tests/perf_tests.cpp:51-118 TestBvh,
+    :212-305 TestMeshMidphase) with the reference's seeded inputs restated draw for draw
+    (workloads.perf_bvh_inputs / perf_mesh_inputs), batched on the GPU: per ray the SET of intersected
+    leaves (count, xor and sum of the leaf indices) must equal bvh_IntersectRay's, and sp_RayIntersectMesh's
+    t must match bit for bit, over the reference compiled unmodified."""
+    sp = gpu_sp
+    chk = best(False)
+    mn, mx, o, d = W.perf_bvh_inputs(sp.xorshift_bilateral_stream(0x1A34C249))
+    assert mn.shape == (2048, 3) and o.shape == (8192, 3)
+    want, build_s, query_s = chk.perf_bvh(mn, mx, o, d, 2048)
+    boxes = W.boxes_as_triangles(mn, mx)
+    r = sp.Renderer()
+    m = r.add_mesh(boxes.vertices, boxes.indices, False)
+    got, ms = sp.mesh_leaves_batch(r.meshes[m], o, d)
+    assert np.array_equal(got, want) and want[:, 0].max() > 20
+    mesh, o2, d2 = W.perf_mesh_inputs(sp.xorshift_bilateral_stream(0x1A34C249), 1 << 18)
+    s = chk.scene()
+    s.add_mesh(mesh.vertices, mesh.indices, False)
+    t_want, _tri, secs = s.perf_mesh(0, o2, d2)
+    s.close()
+    m2 = r.add_mesh(mesh.vertices, mesh.indices, False)
+    t_got, tri_got, ms2 = sp.mesh_intersect_batch(r.meshes[m2], o2, d2)
+    assert same_bits(t_got, t_want) and (t_want >= 0).sum() > 10000
+    timing = os.environ.get("SPB_TIMING_OUT")
+    if timing:
+        with open(timing, "a") as f:
+            f.write(f"PERF_TESTS TestBvh 8192 rays x 2048 boxes: GPU kernel {ms * 1e3:.1f} us, {chk.name} query loop {query_s * 1e3:.2f} ms "
+                    f"(tree build {build_s:.2f} s); TestMeshMidphase {len(o2)} rays: GPU kernel {ms2:.3f} ms, {chk.name} {secs * 1e3:.1f} ms\n")
     r.close()
 
 
@@ -655,6 +758,29 @@ def test_c5_instanced_scene(params):
     assert np.array_equal(g["obj"], e["obj"]) and same_bits(g["t"], e["t"])
     assert (g["tri"] != e["tri"]).sum() <= 1e-4 * g["tri"].size
     assert len(np.unique(e["obj"])) > 100
+    chk.close()
+    r.close()
+
+
+def test_c5_instanced_scene_1080p(gpu_sp):
+    """BASELINE configs[4] at 1920x1080, 4 spp, 5 bounces ("C5 parity runs only at 480x270x2"):
+    8.3 M paths through 182 instances / 9.98 M instanced triangles, the production (wavefront) scheduler
+    against the port in deterministic-math mode -- image bit for bit except at the port's own exact-t tie
+    pixels (bounded at 1e-4), object ids and hit distances exact, triangle ids up to ties."""
+    sp = gpu_sp
+    wl = W.config5(1920, 1080, spp=4, bounces=5, env_size=(1024, 512))
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=4, bounceCount=5, renderMode=0)
+    img, m = r.render_frame(frame=2)
+    chk = ora.load_port_dm().scene().load_workload(wl)
+    cimg, cm = chk.render_seeded(spp=4, bounces=5, frame=2)
+    ntie = assert_same_image_up_to_ties(img, cimg, chk, 4, 5, 2)
+    assert m[1] == cm[1] and np.all(np.abs(m[2:5].astype(np.int64) - cm[2:5].astype(np.int64)) <= max(1, ntie) * 4 * 5)
+    g, e = r.primary_hits(), chk.primary_hits()
+    assert np.array_equal(g["obj"], e["obj"]) and same_bits(g["t"], e["t"])
+    assert (g["tri"] != e["tri"]).sum() <= 1e-4 * g["tri"].size
+    assert len(np.unique(e["obj"])) > 120
+    sp.set_params(samplesPerPixel=1, bounceCount=3)
     chk.close()
     r.close()
 

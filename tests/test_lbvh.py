@@ -30,7 +30,7 @@ def lbvh(hostsim):
     hostsim.lib.hostsim_set_stepped(0)
 
 
-@pytest.mark.parametrize("stepped", [0, 1])
+@pytest.mark.parametrize("stepped", [0, 1, 2])
 def test_lbvh_trees_give_the_reference_results(lbvh, stepped):
     lbvh.lib.hostsim_set_stepped(stepped)
     g = np.load(os.path.join(GOLD, "g1_bunny_96x64.npz"))

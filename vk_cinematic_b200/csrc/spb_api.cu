@@ -183,6 +183,7 @@ struct Library
         params.tileHeight = 64;
         params.renderMode = SP_B200_RENDER_WAVEFRONT;
         params.samplesPerPass = 0;
+        params.triangleTest = SP_B200_TRIANGLE_MOLLER_TRUMBORE;
     }
 };
 
@@ -360,6 +361,7 @@ std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
     ds->d.tlasExtent = fs.tlasExtent;
     ds->d.tlasNodeCount = fs.tlasNodeCount;
     ds->instancedTriangles = fs.instancedTriangles;
+    ds->d.triangleTest = 0;
     ds->d.tlasRoot = fs.tlasRoot;
     ds->d.objectCount = fs.objectCount;
     ds->triangleCount = fs.triangleCount;
@@ -426,6 +428,14 @@ DeviceScene *find_scene(sp_Scene *scene)
         L.emptyScene = upload_scene(flatten_scene(none));
     }
     return L.emptyScene.get();
+}
+
+// the scene as a launch sees it: the uploaded arrays plus the per-call choices that live in DScene
+DScene launch_scene(const DeviceScene *ds)
+{
+    DScene d = ds->d;
+    d.triangleTest = lib().params.triangleTest == SP_B200_TRIANGLE_WATERTIGHT ? 1u : 0u;
+    return d;
 }
 
 // Device copies of HdrImage pixel buffers, keyed by the host pointer (the reference aliases the
@@ -625,8 +635,10 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
 
     // coverage -> block mask + list (sky culling off: no triangle marks anything and the
     // "everything" flag is raised instead)
-    L.wMask.ensure((size_t)blocks + 1);
-    L.wBlockList.ensure((size_t)blocks * 4 + 4);
+    // (sized for the whole image: a strip that grows at the next re-cut must not reallocate)
+    const size_t imageBlocks = (size_t)blocksX * ((ra.camera.height + 3) / 4 + 1);
+    L.wMask.ensure((imageBlocks > blocks ? imageBlocks : blocks) + 1);
+    L.wBlockList.ensure((imageBlocks > blocks ? imageBlocks : blocks) * 4 + 4);
     uint32_t *listCount = (uint32_t *)L.wBlockList.ptr + blocks;
     a.blockMask = (const uint8_t *)L.wMask.ptr;
     launch_coverage(a, instancedTriangles, !L.skyCulling, (uint8_t *)L.wMask.ptr, (uint32_t *)L.wBlockList.ptr,
@@ -649,7 +661,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
         double spread = 4.0 * jitter * pixelAngle + 1.0e-6;
         if (spread < 1.0e-4 && c.halfPixelWidth >= 0.0f && c.halfPixelHeight >= 0.0f)
         {
-            L.wSkyList.ensure(((size_t)width * height + 1) * 4);
+            L.wSkyList.ensure(((size_t)width * (ra.camera.height > height ? ra.camera.height : height) + 1) * 4);
             SPB_CUDA(cudaMemsetAsync(L.wSkyList.ptr, 0, 4, L.stream));
             a.skyList = (uint32_t *)L.wSkyList.ptr;
             a.skyDirectionSpread = (float)spread;
@@ -728,22 +740,32 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     SPB_ASSERT(32ull * bandBlocks * S < 0xFFFFFFFFull - SPB_QUEUE_SLACK);
     const uint32_t capacity = 32u * bandBlocks * S; // ray slots and path ids both fit
 
+    // The working set is sized for the largest pass ANY strip of this image can need (the pass size
+    // the whole image would use), not for this strip's: when the strips of a multi-GPU frame are
+    // re-cut, a strip that grew must not stop for cudaFree / cudaMalloc in the middle of a frame
+    // (measured: several ms, and a cost measurement the next cut cannot use).
+    const uint64_t fullBlocks = (uint64_t)((ra.camera.width + 7) / 8) * ((ra.camera.height + 3) / 4);
+    uint64_t allocBlocks = targetItems / (32ull * S);
+    if (allocBlocks < 1) allocBlocks = 1;
+    if (allocBlocks > fullBlocks) allocBlocks = fullBlocks;
+    if (allocBlocks < bandBlocks) allocBlocks = bandBlocks;
+    const size_t allocItems = (size_t)(32ull * S * allocBlocks);
     // queues and ray arrays carry slack for the partly filled chunks of the warps in flight
-    const size_t slots = (size_t)capacity + SPB_QUEUE_SLACK;
+    const size_t slots = allocItems + SPB_QUEUE_SLACK;
     L.wRays[0].ensure(slots * 32);
     L.wRays[1].ensure(slots * 32);
     L.wHitRec.ensure(slots * 16);
     L.wHitQ.ensure(slots * 4);
     L.wMissQ.ensure(slots * 4);
-    L.wTerms.ensure((size_t)capacity * 32 * (bounces > 1 ? bounces - 1 : 1));
-    L.wRad.ensure((size_t)capacity * 16);
+    L.wTerms.ensure(allocItems * 32 * (bounces > 1 ? bounces - 1 : 1));
+    L.wRad.ensure(allocItems * 16);
     // single-object scenes: per-pixel candidate triangles for the primary rays
     // (the padding of k_candidates covers a jitter of up to 1/100 pixel; sp_ConfigureCamera's is
     // 0.5 / width of a pixel, simd_path_tracer.cpp:17-18)
     const bool useCandidates = L.primaryCandidates && ra.scene.objectCount == 1 && ra.scene.tlasRoot != SPB_REF_EMPTY &&
                                ra.camera.halfPixelWidth <= 0.01f && ra.camera.halfPixelHeight <= 0.01f &&
                                ra.camera.halfPixelWidth >= 0.0f && ra.camera.halfPixelHeight >= 0.0f;
-    if (useCandidates) L.wCand.ensure((size_t)bandBlocks * 32 * SPB_CAND_STRIDE * 4);
+    if (useCandidates) L.wCand.ensure((size_t)allocBlocks * 32 * SPB_CAND_STRIDE * 4);
     a.sortPrimaryHits = (bounces > 1 && L.sortBounceRays) ? 1 : 0;
     if (a.sortPrimaryHits) L.wStage.ensure(slots * 32);
     a.stage = (v4f *)L.wStage.ptr;
@@ -1091,6 +1113,7 @@ extern "C" void sp_b200_SetParams(const sp_b200_Params *params)
     SPB_ASSERT(params->bounceCount >= 1 && params->bounceCount <= SPB_MAX_BOUNCES);
     SPB_ASSERT(params->tileWidth >= 1 && params->tileHeight >= 4 && params->tileHeight % 4 == 0);
     SPB_ASSERT(params->renderMode <= SP_B200_RENDER_PER_PIXEL);
+    SPB_ASSERT(params->triangleTest <= SP_B200_TRIANGLE_WATERTIGHT);
     lib().params = *params;
 }
 extern "C" void sp_b200_GetParams(sp_b200_Params *params) { *params = lib().params; }
@@ -1131,6 +1154,29 @@ extern "C" void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devi
     if (readyEvent) L.externalReady.push_back((cudaEvent_t)readyEvent);
 }
 
+extern "C" int sp_b200_AccumulateFrame(void *deviceAccum, const void *deviceFrame, const f32 *hostFrame, u32 pixelCount,
+                                       u32 framesAccumulated, f32 *hostAccumOut)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    SPB_ASSERT(deviceAccum != nullptr && (deviceFrame != nullptr || hostFrame != nullptr));
+    if (pixelCount == 0) return 0;
+    const size_t bytes = (size_t)pixelCount * 16;
+    const v4f *frame = (const v4f *)deviceFrame;
+    if (!frame)
+    {
+        L.scratchC.ensure(bytes);
+        SPB_CUDA(cudaMemcpyAsync(L.scratchC.ptr, hostFrame, bytes, cudaMemcpyHostToDevice, L.stream));
+        frame = (const v4f *)L.scratchC.ptr;
+    }
+    launch_accumulate_frame((v4f *)deviceAccum, frame, pixelCount, framesAccumulated, L.stream);
+    SPB_CUDA(cudaGetLastError());
+    if (hostAccumOut) SPB_CUDA(cudaMemcpyAsync(hostAccumOut, deviceAccum, bytes, cudaMemcpyDeviceToHost, L.stream));
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    return 0;
+}
+
 extern "C" void sp_b200_SetPathsPerPass(u32 paths) { lib().pathsPerPass = paths; }
 extern "C" void sp_b200_SetSkyCulling(int enable)
 {
@@ -1150,6 +1196,20 @@ extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
     L.refillThreshold[0] = primary ? primary : 1;
     L.refillThreshold[1] = sorted; // 0: measured
     L.refillThreshold[2] = other ? other : SPB_REFILL_THRESHOLD;
+}
+
+extern "C" void sp_b200_XorShift32Stream(u32 *state, u32 count, u32 *values)
+{
+    // XorShift32 (math_utils.h:184-196), `count` draws continuing *state: integer-only, host side
+    u32 x = *state;
+    for (u32 i = 0; i < count; ++i)
+    {
+        x ^= x << 13;
+        x ^= x >> 17;
+        x ^= x << 5;
+        values[i] = x;
+    }
+    *state = x;
 }
 
 extern "C" u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame)
@@ -1424,7 +1484,7 @@ extern "C" int sp_b200_RayIntersectSceneBatch(sp_Scene *scene, u32 count, const 
     SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, rayOrigins, rayBytes, cudaMemcpyHostToDevice, L.stream));
     SPB_CUDA(cudaMemcpyAsync(L.scratchB.ptr, rayDirections, rayBytes, cudaMemcpyHostToDevice, L.stream));
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
-    launch_intersect_batch(kernel_config(), ds->d, count, (const float *)L.scratchA.ptr,
+    launch_intersect_batch(kernel_config(), launch_scene(ds), count, (const float *)L.scratchA.ptr,
                            (const float *)L.scratchB.ptr, (HitRecord *)L.scratchC.ptr, ctr, L.stream);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
@@ -1485,7 +1545,7 @@ extern "C" sp_RayIntersectMeshResult sp_RayIntersectMesh(sp_Mesh mesh, vec3 rayO
     L.scratchC.ensure(sizeof(HitRecord));
     float ray[6] = {rayOrigin.x, rayOrigin.y, rayOrigin.z, rayDirection.x, rayDirection.y, rayDirection.z};
     SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, ray, sizeof(ray), cudaMemcpyHostToDevice, L.stream));
-    launch_intersect_mesh(kernel_config(), ds->d, mesh.useSmoothShading ? 1u : 0u,
+    launch_intersect_mesh(kernel_config(), launch_scene(ds), mesh.useSmoothShading ? 1u : 0u,
                           (const float *)L.scratchA.ptr, (const float *)L.scratchA.ptr + 3,
                           (HitRecord *)L.scratchC.ptr, L.stream);
     SPB_CUDA(cudaGetLastError());
@@ -1541,7 +1601,7 @@ extern "C" u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 
     L.scratchC.ensure(16);
     float ray[6] = {rayOrigin.x, rayOrigin.y, rayOrigin.z, rayDirection.x, rayDirection.y, rayDirection.z};
     SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, ray, sizeof(ray), cudaMemcpyHostToDevice, L.stream));
-    launch_collect_leaves(ds->d, (const float *)L.scratchA.ptr, (const float *)L.scratchA.ptr + 3,
+    launch_collect_leaves(launch_scene(ds), (const float *)L.scratchA.ptr, (const float *)L.scratchA.ptr + 3,
                           (uint32_t *)L.scratchB.ptr, maxIntersections, (uint32_t *)L.scratchC.ptr, L.stream);
     SPB_CUDA(cudaGetLastError());
     uint32_t ce[2];
@@ -1551,6 +1611,59 @@ extern "C" u32 sp_b200_MeshIntersectedLeaves(sp_Mesh mesh, vec3 rayOrigin, vec3 
         SPB_CUDA(cudaMemcpy(leafIndices, L.scratchB.ptr, (size_t)ce[0] * 4, cudaMemcpyDeviceToHost));
     if (errorOccurred) *errorOccurred = ce[1];
     return ce[0];
+}
+
+// Rays stay on the device between the two batched queries when the caller passes the same arrays
+// again (perf tests time the query, not the upload): kernelMs is the CUDA-event time of the kernel.
+static int mesh_batch(sp_Mesh mesh, u32 count, const vec3 *origins, const vec3 *dirs, int what, u32 *leafOut3, f32 *tOut,
+                      i32 *triOut, f32 *kernelMs)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    if (kernelMs) *kernelMs = 0.0f;
+    if (count == 0) return 0;
+    std::shared_ptr<MeshAccel> accel = find_mesh(mesh);
+    if (!accel) return 1;
+    DeviceScene *ds = mesh_device_scene(accel, mesh.useSmoothShading);
+    const size_t vecBytes = (size_t)count * 12;
+    L.scratchA.ensure(vecBytes * 2);
+    L.scratchB.ensure((size_t)count * 12);
+    char *in = (char *)L.scratchA.ptr;
+    SPB_CUDA(cudaMemcpyAsync(in, origins, vecBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaMemcpyAsync(in + vecBytes, dirs, vecBytes, cudaMemcpyHostToDevice, L.stream));
+    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    if (what == 0)
+        launch_collect_leaves_batch(launch_scene(ds), count, (const float *)in, (const float *)(in + vecBytes), (uint32_t *)L.scratchB.ptr, L.stream);
+    else
+        launch_intersect_mesh_batch(kernel_config(), launch_scene(ds), count, (const float *)in, (const float *)(in + vecBytes),
+                                    (float *)L.scratchB.ptr, (int32_t *)((float *)L.scratchB.ptr + count), L.stream);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    if (what == 0)
+        SPB_CUDA(cudaMemcpyAsync(leafOut3, L.scratchB.ptr, (size_t)count * 12, cudaMemcpyDeviceToHost, L.stream));
+    else
+    {
+        if (tOut) SPB_CUDA(cudaMemcpyAsync(tOut, L.scratchB.ptr, (size_t)count * 4, cudaMemcpyDeviceToHost, L.stream));
+        if (triOut) SPB_CUDA(cudaMemcpyAsync(triOut, (float *)L.scratchB.ptr + count, (size_t)count * 4, cudaMemcpyDeviceToHost, L.stream));
+    }
+    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    float ms = 0.0f;
+    SPB_CUDA(cudaEventElapsedTime(&ms, L.evKernel0, L.evKernel1));
+    if (kernelMs) *kernelMs = ms;
+    return 0;
+}
+
+extern "C" int sp_b200_MeshIntersectedLeavesBatch(sp_Mesh mesh, u32 count, const vec3 *rayOrigins, const vec3 *rayDirections,
+                                                  u32 *countXorSum, f32 *kernelMs)
+{
+    return mesh_batch(mesh, count, rayOrigins, rayDirections, 0, countXorSum, nullptr, nullptr, kernelMs);
+}
+
+extern "C" int sp_b200_RayIntersectMeshBatch(sp_Mesh mesh, u32 count, const vec3 *rayOrigins, const vec3 *rayDirections, f32 *t,
+                                             i32 *triangleIndex, f32 *kernelMs)
+{
+    return mesh_batch(mesh, count, rayOrigins, rayDirections, 1, nullptr, t, triangleIndex, kernelMs);
 }
 
 extern "C" void sp_b200_MeshTreeInfo(sp_Mesh mesh, sp_b200_TreeInfo *info)
@@ -1833,7 +1946,7 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     L.skyTimed = false;
 
     RenderArgs args;
-    args.scene = ds->d;
+    args.scene = launch_scene(ds);
     args.materials = dm;
     args.camera = cam;
     args.x0 = 0;
@@ -2289,7 +2402,7 @@ static void render_tile_group(const std::vector<TileRequest *> &group)
     SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, L.stream));
 
     TileArgs args;
-    args.scene = ds->d;
+    args.scene = launch_scene(ds);
     args.materials = dm;
     args.camera = cam;
     args.tiles = (const uint32_t *)L.scratchA.ptr;
@@ -2474,7 +2587,7 @@ extern "C" u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *me
         SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, L.stream));
 
         TileArgs args;
-        args.scene = ds->d;
+        args.scene = launch_scene(ds);
         args.materials = dm;
         args.camera = cam;
         args.tiles = (const uint32_t *)L.scratchA.ptr;
@@ -2550,7 +2663,7 @@ extern "C" int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *
     unsigned long long *ctr = reset_counters();
     SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
     SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
-    launch_primary_hits(kernel_config(), ds->d, cam, sample, frame, (int32_t *)L.scratchA.ptr,
+    launch_primary_hits(kernel_config(), launch_scene(ds), cam, sample, frame, (int32_t *)L.scratchA.ptr,
                         (int32_t *)L.scratchB.ptr, (float *)L.scratchC.ptr, ctr, L.stream);
     SPB_CUDA(cudaGetLastError());
     SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));

@@ -14,10 +14,14 @@
 #include <float.h>
 
 #if defined(__CUDACC__)
+// (out of line on purpose: optional paths whose registers and local arrays must not be charged to
+// the kernels' hot loops)
+#define SPB_HD_NOINLINE static __host__ __device__ __noinline__
 #define SPB_HD __host__ __device__ __forceinline__
 #define SPB_ALIGN16 __align__(16)
 #define SPB_ALIGN8 __align__(8)
 #else
+#define SPB_HD_NOINLINE inline
 #define SPB_HD inline
 #define SPB_ALIGN16 alignas(16)
 #define SPB_ALIGN8 alignas(8)
@@ -260,6 +264,7 @@ struct DScene
     uint32_t objectCount;
     float tlasExtent;      // largest |coordinate| of the TLAS boxes (world space)
     uint32_t tlasNodeCount; // TLAS nodes are [tlasRoot, tlasRoot + tlasNodeCount), breadth-first
+    uint32_t triangleTest; // 0: the reference's Moller-Trumbore (parity); 1: watertight (sp_b200_Params::triangleTest)
 };
 
 struct Counters
@@ -322,6 +327,28 @@ SPB_HD bool slab_fast(float bminx, float bminy, float bminz, float bmaxx, float 
     return tnear <= tfar;
 }
 
+// Watertight mode (sp_b200_Params::triangleTest): the box tests must not lose a ray the watertight
+// triangle test would accept -- a ray that grazes the common edge of two triangles also grazes a face
+// of both their boxes, where the slab test's rounding can reject it twice.  Every box is therefore
+// grown, per axis, by 2^-20 of the magnitudes involved before it is tested (Woop et al. 2013 section 4
+// pad their boxes for the same reason).  NaN boxes (empty slots) stay NaN.  Not used in parity mode.
+SPB_HD void grow_box(f3 o, float &bminx, float &bminy, float &bminz, float &bmaxx, float &bmaxy, float &bmaxz)
+{
+    const float e = 9.5367431640625e-07f; // 2^-20
+    const float px = e * (fabsf(o.x) + fmaxf(fabsf(bminx), fabsf(bmaxx)));
+    const float py = e * (fabsf(o.y) + fmaxf(fabsf(bminy), fabsf(bmaxy)));
+    const float pz = e * (fabsf(o.z) + fmaxf(fabsf(bminz), fabsf(bmaxz)));
+    bminx -= px; bminy -= py; bminz -= pz;
+    bmaxx += px; bmaxy += py; bmaxz += pz;
+}
+SPB_HD_NOINLINE void grow_boxes4(f3 o, v4f &minx, v4f &miny, v4f &minz, v4f &maxx, v4f &maxy, v4f &maxz)
+{
+    grow_box(o, minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x);
+    grow_box(o, minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y);
+    grow_box(o, minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z);
+    grow_box(o, minx.w, miny.w, minz.w, maxx.w, maxy.w, maxz.w);
+}
+
 // Moller-Trumbore (ray_intersection.cpp:156-190).  Returns true when the reference would set
 // result.t; the caller applies t > 0 (sp_scene.cpp:189).
 SPB_HD bool ray_triangle_mt(f3 o, f3 d, f3 a, f3 b, f3 c, float &t, float &u, float &v)
@@ -341,6 +368,56 @@ SPB_HD bool ray_triangle_mt(f3 o, f3 d, f3 a, f3 b, f3 c, float &t, float &u, fl
     float f = dot3(d, n);
     return (u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f && w >= 0.0f && w <= 1.0f &&
             f < 0.0f);
+}
+
+// Watertight ray / triangle test (Woop, Benthin, Wald 2013), the north star's option; NEVER the
+// parity default: it decides edge cases differently from the reference's Moller-Trumbore by design.
+// The triangle is translated to the ray origin and sheared so that the ray runs along +z of a
+// permuted frame; the three scaled barycentrics are 2D edge functions of the SAME shared vertices for
+// neighbouring triangles, so a ray through a shared edge or vertex cannot fall between them; a zero
+// edge function is re-evaluated in double precision.  Same interface and the same acceptance rules
+// as ray_triangle_mt(): front faces only (d . (e1 x e2) < 0, ray_intersection.cpp:183-188), (u, v)
+// the weights of b and c, the caller applies t > 0.
+SPB_HD_NOINLINE bool ray_triangle_wt(f3 o, f3 d, f3 a, f3 b, f3 c, float &t, float &u, float &v)
+{
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    const float dv[3] = {d.x, d.y, d.z};
+    if (dv[kz] < 0.0f) { int s = kx; kx = ky; ky = s; }
+    const float Sx = dv[kx] / dv[kz], Sy = dv[ky] / dv[kz], Sz = 1.0f / dv[kz];
+    const float A[3] = {a.x - o.x, a.y - o.y, a.z - o.z}, B[3] = {b.x - o.x, b.y - o.y, b.z - o.z},
+                Cv[3] = {c.x - o.x, c.y - o.y, c.z - o.z};
+    const float Ax = A[kx] - Sx * A[kz], Ay = A[ky] - Sy * A[kz];
+    const float Bx = B[kx] - Sx * B[kz], By = B[ky] - Sy * B[kz];
+    const float Cx = Cv[kx] - Sx * Cv[kz], Cy = Cv[ky] - Sy * Cv[kz];
+    float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f)
+    {
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    t = -1.0f;
+    u = v = 0.0f;
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    // front faces only, like the reference
+    f3 n = cross3(sub3(b, a), sub3(c, a));
+    if (!(dot3(d, n) < 0.0f)) return false;
+    const float T = U * (Sz * A[kz]) + V * (Sz * B[kz]) + W * (Sz * Cv[kz]);
+    const float rcp = 1.0f / det;
+    t = T * rcp;
+    u = V * rcp;
+    v = W * rcp;
+    return true;
+}
+
+// the triangle test of the scene (sp_b200_Params::triangleTest; uniform over a launch)
+SPB_HD bool ray_triangle(uint32_t test, f3 o, f3 d, f3 a, f3 b, f3 c, float &t, float &u, float &v)
+{
+    return test == 0 ? ray_triangle_mt(o, d, a, b, c, t, u, v) : ray_triangle_wt(o, d, a, b, c, t, u, v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -373,7 +450,7 @@ SPB_HD void sort2(float &ta, uint32_t &ra, float &tb, uint32_t &rb)
 template <bool CULL, bool EXACT, class LeafFn>
 SPB_HD void traverse(const v4f *nodes, uint32_t root, f3 o, f3 inv, float tcull, uint32_t *stack,
                      float *stackT, int stackBase, int stackLimit, Counters *counters,
-                     LeafFn &leaf)
+                     LeafFn &leaf, uint32_t watertight = 0)
 {
     int sp = stackBase;
     uint32_t node = root;
@@ -385,6 +462,7 @@ SPB_HD void traverse(const v4f *nodes, uint32_t root, f3 o, f3 inv, float tcull,
         v4f maxx = ld4(n + 3), maxy = ld4(n + 4), maxz = ld4(n + 5);
         v4u refs = ld4u((const v4u *)(n + 6));
         if (counters) counters->nodeVisits++;
+        if (watertight) grow_boxes4(o, minx, miny, minz, maxx, maxy, maxz);
 
         float tn0, tn1, tn2, tn3;
         bool h0, h1, h2, h3;
@@ -491,7 +569,7 @@ SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float
         v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle_mt(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
+        if (ray_triangle(S.triangleTest, o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
         {
             if (t > 0.0f)
             {
@@ -508,7 +586,8 @@ SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float
         }
         return cull;
     };
-    traverse<CULL, EXACT>(S.nodes, meshRoot, o, inv, tcull, stack, stackT, stackBase, SPB_STACK_SIZE, counters, leaf);
+    traverse<CULL, EXACT>(S.nodes, meshRoot, o, inv, tcull, stack, stackT, stackBase, SPB_STACK_SIZE, counters, leaf,
+                          S.triangleTest);
 }
 
 SPB_HD m4 load_m4(const v4f *p)
@@ -594,9 +673,9 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
     };
 
     if (worldExact)
-        traverse<CULL, true>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf);
+        traverse<CULL, true>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, S.triangleTest);
     else
-        traverse<CULL, false>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf);
+        traverse<CULL, false>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, S.triangleTest);
     return best;
 }
 
@@ -746,6 +825,62 @@ SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, co
     trav_pop<CULL>(st, stack);
 }
 
+// The exit arithmetic alone (sp_scene.cpp:296-322): the object's closest hit carried to world space.
+SPB_HD void trav_leave(const DScene &S, const Trav &st, TravCold &c, const v4f *ray)
+{
+    if (!(st.lT >= 0.0f)) return;
+    f3 wo, wd;
+    trav_world_ray(ray, wo, wd);
+    m4 model = load_m4(S.objModel + (size_t)c.object * 4);
+    f3 localHit = add3(st.o, mul3(st.d, st.lT));
+    f3 worldHit = xform(model, localHit, 1.0f);
+    float t = dot3(sub3(worldHit, wo), wd);
+    float bT = c.bT;
+    if (t < bT || bT < 0.0f)
+    {
+        c.bT = t;
+        c.bObject = (int32_t)c.object;
+        c.bSlot = st.lSlot;
+    }
+}
+
+// Single-object scenes: what the walk does before it reaches the mesh tree -- the TLAS root's one
+// child is the object: the exact test of its box, then the object entry of trav_leaf() -- done at
+// once when the ray starts, with every lane of a refilling warp busy; the walk then ends with
+// SPB_NODE_EXIT, which the caller treats as finished (trav_leave() at retire).
+template <bool CULL>
+SPB_HD void trav_begin_single(const DScene &S, f3 o, f3 d, Trav &st, TravCold &c, Counters *counters)
+{
+    trav_begin(S, o, d, st, c);
+    if (st.cur == SPB_NODE_DONE) return;
+    st.cur = SPB_NODE_DONE;
+    if (counters) counters->nodeVisits++;
+    v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
+    if (S.triangleTest) grow_box(st.o, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z);
+    float tn;
+    if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, st.o, st.inv, tn)) return;
+    v4u info = ld4u(S.objInfo);
+    if (counters) counters->objectTests++;
+    if (info.x == SPB_REF_EMPTY) return;
+    m4 invModel = load_m4(S.objInv);
+    f3 lo = xform(invModel, o, 1.0f);
+    f3 ld = normalize3(xform(invModel, d, 0.0f));
+    if (any_nonfinite_inv(ld))
+    {
+        c.slow = 1;
+        return;
+    }
+    c.worldCull = st.tcull;
+    st.o = lo;
+    st.d = ld;
+    st.inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+    c.object = 0;
+    st.blasBase = 0;
+    st.lT = -1.0f;
+    st.lSlot = 0;
+    st.cur = info.x;
+}
+
 // No bound check: flatten_scene() refuses scenes whose worst-case stack use (three entries per
 // level of the TLAS plus three per level of the deepest mesh tree) exceeds SPB_STACK_SIZE.
 SPB_HD void trav_push(Trav &st, TravEntry *stack, uint32_t ref, float tnear)
@@ -780,6 +915,7 @@ SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *cou
     v4u refs;
     refs.x = f2u(refsf.x); refs.y = f2u(refsf.y); refs.z = f2u(refsf.z); refs.w = f2u(refsf.w);
     if (counters) counters->nodeVisits++;
+    if (S.triangleTest) grow_boxes4(st.o, minx, miny, minz, maxx, maxy, maxz);
 
     float tn0, tn1, tn2, tn3;
     bool h0 = slab_fast(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st.o, st.inv, tn0);
@@ -851,7 +987,7 @@ SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, Tr
         v4f a = ld4(tp + 0), b = ld4(tp + 1), cc = ld4(tp + 2);
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle_mt(st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(cc.x, cc.y, cc.z), t, u, v))
+        if (ray_triangle(S.triangleTest, st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(cc.x, cc.y, cc.z), t, u, v))
         {
             if (t > 0.0f && (t < st.lT || st.lT < 0.0f))
             {
@@ -909,7 +1045,7 @@ SPB_HD void hit_barycentrics(const DScene &S, f3 o, f3 d, Hit &hit)
     const v4f *tp = S.tris + (size_t)hit.slot * 3;
     v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
     float t;
-    ray_triangle_mt(lo, ld, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, hit.u, hit.v);
+    ray_triangle(S.triangleTest, lo, ld, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, hit.u, hit.v);
 }
 
 SPB_HD Hit trav_result(const TravCold &c)
@@ -925,7 +1061,8 @@ SPB_HD Hit trav_result(const TravCold &c)
 }
 
 // The state machine run to completion for one ray (what each lane of k_trace does, unrolled in
-// time); hostsim uses it to check the machine against intersect_scene() and the oracle.
+// time, single-object entry at the start included); hostsim uses it to check the machine against
+// intersect_scene() and the oracle.
 template <bool CULL>
 SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT,
                                    Counters *counters)
@@ -933,16 +1070,19 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
     Trav st;
     TravCold cold;
     TravEntry entries[SPB_STACK_SIZE];
-    trav_begin(S, o, d, st, cold);
     v4f ray[2];
     ray[0].x = o.x; ray[0].y = o.y; ray[0].z = o.z; ray[0].w = 0.0f;
     ray[1].x = d.x; ray[1].y = d.y; ray[1].z = d.z; ray[1].w = 0.0f;
-    while (st.cur != SPB_NODE_DONE)
+    const bool single = S.objectCount == 1;
+    if (single) trav_begin_single<CULL>(S, o, d, st, cold, counters);
+    else trav_begin(S, o, d, st, cold);
+    while (st.cur != SPB_NODE_DONE && !(single && st.cur == SPB_NODE_EXIT))
     {
         if (st.cur == SPB_NODE_EXIT) trav_exit<CULL>(S, st, cold, ray, entries);
         else if (trav_is_node(st)) trav_node<CULL>(S, st, entries, counters);
         else trav_leaf<CULL>(S, st, cold, ray, entries, counters);
     }
+    if (single && st.cur == SPB_NODE_EXIT) trav_leave(S, st, cold, ray);
     if (cold.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
     Hit h = trav_result(cold);
     if (h.object >= 0) hit_barycentrics(S, o, d, h);
@@ -1171,6 +1311,7 @@ SPB_HD void trav2_node(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
     else
     {
         const f3 o = v.f3at(T2_WOX), inv = v.f3at(T2_WIX);
+        if (S.triangleTest) grow_boxes4(o, minx, miny, minz, maxx, maxy, maxz);
         k0 = slab_key(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, o, inv, tlimit);
         k1 = slab_key(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, o, inv, tlimit);
         k2 = slab_key(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, o, inv, tlimit);
@@ -1290,8 +1431,11 @@ SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
         const v4f *tp = S.tris + (size_t)index * 3;
         v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
         // the triangle's own box (sp_scene.cpp:35-50) and the reference's test of it (bvh.cpp:236-255)
-        float tn;
-        const bool own = slab_fast(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)),
+        // (watertight mode: the padded test of the parent's node step stands; no exact test may
+        // come between it and the triangle test)
+        float tn = 0.0f;
+        const bool own = S.triangleTest != 0 ||
+                         slab_fast(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)),
                                    fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)),
                                    o, inv, tn);
         if (own && (!CULL || tn <= st.tcull))
@@ -1299,7 +1443,7 @@ SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
             if (counters) counters->triangleTests++;
             const f3 d = v.f3at(T2_DX);
             float t, uu, vv;
-            if (ray_triangle_mt(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, uu, vv))
+            if (ray_triangle(S.triangleTest, o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, uu, vv))
             {
                 const float lT = v.f(T2_LT);
                 if (t > 0.0f && (t < lT || lT < 0.0f))
@@ -1337,6 +1481,7 @@ SPB_HD void trav2_begin_single(const DScene &S, f3 o, f3 d, Trav2 &st, const T2V
     if (!trav2_start(S, o, d, st, v)) return;
     if (counters) counters->nodeVisits++;
     v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
+    if (S.triangleTest) grow_box(o, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z);
     float tn;
     if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, v.f3at(T2_WIX), tn)) return;
     v4u info = ld4u(S.objInfo);
@@ -1821,7 +1966,9 @@ SPB_HD int resolve_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d,
         v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
         float tn;
         if (counters) counters->nodeVisits++;
-        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, winv, tn)) return 0; // miss
+        float b0 = mnx.x, b1 = mny.x, b2 = mnz.x, b3 = mxx.x, b4 = mxy.x, b5 = mxz.x;
+        if (S.triangleTest) grow_box(o, b0, b1, b2, b3, b4, b5);
+        if (!slab_fast(b0, b1, b2, b3, b4, b5, o, winv, tn)) return 0; // miss
     }
     // object entry (sp_scene.cpp:274-276)
     v4u info = ld4u(S.objInfo);
@@ -1842,10 +1989,11 @@ SPB_HD int resolve_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d,
         f3 bmn, bmx;
         triangle_box(va, vb, vc, bmn, bmx);
         float tn;
+        if (S.triangleTest) grow_box(lo, bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z);
         if (!slab_fast(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, lo, inv, tn)) continue; // the leaf's own box
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle_mt(lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
+        if (ray_triangle(S.triangleTest, lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
             if (t > 0.0f && (t < lT || lT < 0.0f))
             {
                 lT = t;
@@ -1957,7 +2105,7 @@ struct PathCounters { uint32_t rays, hits, misses; };
 
 // One light path = one iteration of the sample loop of sp_PathTraceTile
 // (simd_path_tracer.cpp:216-320).  `rng` continues the caller's stream.
-template <int MATH, int ENVFILTER, bool CULL, bool STEPPED = false>
+template <int MATH, int ENVFILTER, bool CULL, int STEPPED = 0>
 SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, uint32_t x,
                      uint32_t y, uint32_t &rng, uint32_t bounceCount, float clampValue,
                      uint32_t *stack, float *stackT, PathCounters &pc, Counters *counters)
@@ -1969,8 +2117,9 @@ SPB_HD f3 trace_path(const DScene &S, const DMaterials &M, const DCamera &cam, u
     uint32_t pathLength = 0;
     for (uint32_t bounce = 0; bounce < bounceCount; ++bounce)
     {
-        Hit hit = STEPPED ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, counters)
-                          : intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+        Hit hit = STEPPED == 1 ? intersect_scene_stepped<CULL>(S, o, d, stack, stackT, counters)
+                  : STEPPED == 2 ? intersect_scene_stepped2<CULL>(S, o, d, stack, stackT, counters)
+                                 : intersect_scene<CULL>(S, o, d, stack, stackT, counters);
         pc.rays++;
         f3 V = neg3(d);
         if (hit.t > 0.0f)

@@ -305,6 +305,113 @@ void launch_collect_leaves(const DScene &scene, const float *origin3, const floa
     k_collect_leaves<<<1, 1, 0, stream>>>(scene, origin3, dir3, leaves, maxLeaves, countAndError);
 }
 
+// Progressive accumulation across frames (the reference lists it as not done: main.cpp:75
+// "Accumulate pixel samples over multiple frames [ ]"): the running mean of the frames rendered
+// so far, accum += (frame - accum) / (n + 1) per component, alpha kept at the frame's.
+__global__ void __launch_bounds__(256) k_accumulate_frame(v4f *accum, const v4f *frame, uint32_t count, uint32_t n)
+{
+    const float denom = (float)(n + 1u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        v4f f = frame[i];
+        if (n == 0)
+        {
+            accum[i] = f;
+            continue;
+        }
+        v4f a = accum[i];
+        a.x = a.x + (f.x - a.x) / denom;
+        a.y = a.y + (f.y - a.y) / denom;
+        a.z = a.z + (f.z - a.z) / denom;
+        a.w = f.w;
+        accum[i] = a;
+    }
+}
+
+void launch_accumulate_frame(v4f *accum, const v4f *frame, uint32_t count, uint32_t framesAccumulated, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    unsigned grid = (count + 255) / 256;
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    k_accumulate_frame<<<grid, 256, 0, stream>>>(accum, frame, count, framesAccumulated);
+}
+
+// Batched forms for the reference's own performance tests (perf_tests/perf_tests.cpp:51-118 TestBvh:
+// bvh_IntersectRay over seeded boxes; :212-305 TestMeshMidphase: sp_RayIntersectMesh over a seeded
+// icosphere): one ray per thread, object-space rays against object 0's mesh.
+// Leaves: per ray the number of leaves whose own box the ray passes and the XOR and the sum of their
+// primitive indices (a fingerprint the checker's leaf list can be compared with).
+__global__ void __launch_bounds__(128)
+k_collect_leaves_batch(DScene scene, uint32_t count, const float *origins3, const float *dirs3, uint32_t *out3)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[1];
+    f3 o = mk3(origins3[q * 3 + 0], origins3[q * 3 + 1], origins3[q * 3 + 2]);
+    f3 d = mk3(dirs3[q * 3 + 0], dirs3[q * 3 + 1], dirs3[q * 3 + 2]);
+    f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    v4u info = ld4u(scene.objInfo);
+    uint32_t n = 0, x = 0, sum = 0;
+    if (info.x != SPB_REF_EMPTY)
+    {
+        auto leaf = [&](uint32_t slot, float cull) -> float {
+            uint32_t prim = f2u(ld4(scene.tris + (size_t)slot * 3).w);
+            n++;
+            x ^= prim * 0x9E3779B1u;
+            sum += prim;
+            return cull;
+        };
+        const float inf = u2f(0x7F800000u);
+        if (any_nonfinite_inv(d))
+            traverse<false, true>(scene.nodes, info.x, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE, nullptr, leaf);
+        else
+            traverse<false, false>(scene.nodes, info.x, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE, nullptr, leaf);
+    }
+    out3[(size_t)q * 3 + 0] = n;
+    out3[(size_t)q * 3 + 1] = x;
+    out3[(size_t)q * 3 + 2] = sum;
+}
+
+void launch_collect_leaves_batch(const DScene &scene, uint32_t count, const float *origins3, const float *dirs3,
+                                 uint32_t *out3, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    k_collect_leaves_batch<<<(count + 127) / 128, 128, 0, stream>>>(scene, count, origins3, dirs3, out3);
+}
+
+// sp_RayIntersectMesh (sp_scene.cpp:127-227) per ray: t (or -1) and the triangle index
+template <bool CULL>
+__global__ void __launch_bounds__(128)
+k_intersect_mesh_batch(DScene scene, uint32_t count, const float *origins3, const float *dirs3, float *tOut, int32_t *triOut)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    uint32_t stack[SPB_STACK_SIZE];
+    float stackT[SPB_STACK_SIZE];
+    f3 o = mk3(origins3[q * 3 + 0], origins3[q * 3 + 1], origins3[q * 3 + 2]);
+    f3 d = mk3(dirs3[q * 3 + 0], dirs3[q * 3 + 1], dirs3[q * 3 + 2]);
+    v4u info = ld4u(scene.objInfo);
+    float t, u, v;
+    uint32_t slot;
+    const float inf = u2f(0x7F800000u);
+    if (any_nonfinite_inv(d))
+        intersect_mesh<CULL, true>(scene, info.x, o, d, inf, stack, stackT, 0, nullptr, t, slot, u, v);
+    else
+        intersect_mesh<CULL, false>(scene, info.x, o, d, inf, stack, stackT, 0, nullptr, t, slot, u, v);
+    tOut[q] = t;
+    triOut[q] = t >= 0.0f ? (int32_t)f2u(ld4(scene.tris + (size_t)slot * 3).w) : -1;
+}
+
+void launch_intersect_mesh_batch(const KernelConfig &cfg, const DScene &scene, uint32_t count, const float *origins3,
+                                 const float *dirs3, float *tOut, int32_t *triOut, cudaStream_t stream)
+{
+    g_kernelLaunches++;
+    const unsigned grid = (count + 127) / 128;
+    if (cfg.cull) k_intersect_mesh_batch<true><<<grid, 128, 0, stream>>>(scene, count, origins3, dirs3, tOut, triOut);
+    else k_intersect_mesh_batch<false><<<grid, 128, 0, stream>>>(scene, count, origins3, dirs3, tOut, triOut);
+}
+
 // simd_RayIntersectAabb4 (simd.h:198-271) on the device, query by query: the three forms of the slab
 // test the kernels use, evaluated on the caller's boxes and (origin, reciprocal direction) exactly as
 // the reference's function takes them.  masks[q * 3 + 0] = slab_exact (the SSE semantics: the second

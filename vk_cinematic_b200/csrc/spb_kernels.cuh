@@ -85,6 +85,13 @@ void launch_intersect_mesh(const KernelConfig &cfg, const DScene &scene, uint32_
 void launch_collect_leaves(const DScene &scene, const float *origin3, const float *dir3,
                            uint32_t *leaves, uint32_t maxLeaves, uint32_t *countAndError,
                            cudaStream_t stream);
+// running mean over frames: accum += (frame - accum) / (framesAccumulated + 1)
+void launch_accumulate_frame(v4f *accum, const v4f *frame, uint32_t count, uint32_t framesAccumulated, cudaStream_t stream);
+// batched forms (the reference's perf tests): per ray leaf count / xor / sum; per ray t and triangle index
+void launch_collect_leaves_batch(const DScene &scene, uint32_t count, const float *origins3, const float *dirs3,
+                                 uint32_t *out3, cudaStream_t stream);
+void launch_intersect_mesh_batch(const KernelConfig &cfg, const DScene &scene, uint32_t count, const float *origins3,
+                                 const float *dirs3, float *tOut, int32_t *triOut, cudaStream_t stream);
 // the device forms of simd_RayIntersectAabb4 on caller data (k_slab_kat): known-answer tests
 void launch_slab_kat(uint32_t count, const float *boxMin12, const float *boxMax12, const float *origin3, const float *invDir3,
                      uint32_t *masks, float *tnear, cudaStream_t stream);

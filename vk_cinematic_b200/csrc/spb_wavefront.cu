@@ -139,8 +139,15 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
     return h;
 }
 
-#if !defined(SPB_TRAV_OLD)
+#if defined(SPB_TRAV2)
 // ---------------------------------------------------------------------------------------------
+// A/B BUILD (-DSPB_TRAV2), not the production kernel: the second traversal machine, built on VERDICT
+// r01's suggestion that the exact slab predicate is only needed on a leaf's own box.  Measured
+// (profiles/r2/README.md): 4.29 G instead of 4.63 G warp instructions per bounce-1 launch of C3, but
+// no faster (6.13 vs 6.23 ms: five of its twelve test constants spill, every leaf pays an exact test
+// of its own) and 10-13 % slower on the 182-object scene, where the extra leaf step runs at 13 of
+// 32 lanes.  What did pay -- entering the object when the ray starts -- was moved into the
+// production kernel below.
 // Traversal kernel.  Persistent warps; every lane owns one ray at a time and advances it with the
 // resumable machine of spb_core.cuh (Trav2: conservative four-FFMA box tests on the way down, the
 // reference's exact test on every leaf that comes off the stack).  Each iteration of the inner
@@ -364,7 +371,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
         }
     }
 }
-#else // SPB_TRAV_OLD: round 1's kernel over the first machine, kept for A/B builds
+#else // the production kernel: the first machine (exact box tests at every node)
 // Primary ray of item `idx` resolved from its pixel's candidate list (spb_core.cuh
 // resolve_from_candidates); leaves the lane finished, or untouched when the pixel falls back.
 template <bool CULL>
@@ -390,7 +397,15 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     const unsigned total = PRIMARY ? a.workItems : ctr[WCTR_RAYS];
     uint32_t *cursor = &ctr[WCTR_CURSOR];
     v4f *rays = a.rays[bounce & 1u];
-
+#if defined(SPB_NO_FUSED_ENTRY)
+    const bool single = false; // (A/B build: round 1's behaviour)
+#else
+    // Single-object scenes (C1-C4): the object is entered when the ray starts and left when it
+    // retires, both with every lane of the warp busy, instead of through three more rounds of the
+    // step loop (TLAS root, object entry, exit) at whatever lane count the votes give them.
+    // Measured on C3: 64.1 ms per frame against 68.2 without (profiles/r2/s6_ab_first_machine_fused_entry.txt).
+    const bool single = a.scene.objectCount == 1;
+#endif
 
     // per-lane stack in local memory; state that is touched only when an object is entered or
     // left, or the ray retired, lives in shared memory (6 + 1 words per lane, conflict-free stride)
@@ -417,7 +432,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     for (;;)
     {
         // ---- retire finished lanes: hit record + queue entry
-        const bool finished = have && st.cur == SPB_NODE_DONE;
+        const bool finished = have && (st.cur == SPB_NODE_DONE || (single && st.cur == SPB_NODE_EXIT));
         if (__any_sync(SPB_FULL, finished))
         {
             Hit h;
@@ -426,6 +441,11 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             h.object = -1;
             if (finished)
             {
+                if (single && st.cur == SPB_NODE_EXIT)
+                {
+                    trav_leave(a.scene, st, cold, rays + (size_t)slot * 2);
+                    st.cur = SPB_NODE_DONE;
+                }
                 if (cold.slow)
                 {
                     f3 wo, wd;
@@ -502,11 +522,21 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                     }
                     if (valid)
                     {
-                        trav_begin(a.scene, o, d, st, cold);
                         have = true;
                         slot = idx;
-                        if (PRIMARY && a.candidates)
-                            primary_from_candidates<CULL>(a, idx, o, d, st, cold, STATS ? &cnt : nullptr);
+                        if (single && !(PRIMARY && a.candidates)) trav_begin_single<CULL>(a.scene, o, d, st, cold, STATS ? &cnt : nullptr);
+                        else
+                        {
+                            trav_begin(a.scene, o, d, st, cold);
+                            if (PRIMARY && a.candidates)
+                            {
+                                uint32_t before = st.cur;
+                                primary_from_candidates<CULL>(a, idx, o, d, st, cold, STATS ? &cnt : nullptr);
+                                // a pixel that falls back to the walk
+                                if (single && st.cur == before && st.cur != SPB_NODE_DONE && !cold.slow)
+                                    trav_begin_single<CULL>(a.scene, o, d, st, cold, STATS ? &cnt : nullptr);
+                            }
+                        }
                     }
                 }
             }
@@ -515,7 +545,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
         // ---- walk
         // lanes whose walk inside an object has ended leave it together (the exit arithmetic
         // would otherwise run for one or two lanes at a time)
-        if (have && st.cur == SPB_NODE_EXIT)
+        if (!single && have && st.cur == SPB_NODE_EXIT)
             trav_exit<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack);
         unsigned walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         if (!walking)
@@ -567,7 +597,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     }
 }
 
-#endif // SPB_TRAV_OLD
+#endif // SPB_TRAV2
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_terms(v4f *pathTerms, size_t index, const VertexTerms &vt)

@@ -104,6 +104,7 @@ class sp_b200_BuildInfo(C.Structure):
 
 
 BUILDER_HOST_SAH, BUILDER_DEVICE_LBVH = 0, 1
+TRIANGLE_MOLLER_TRUMBORE, TRIANGLE_WATERTIGHT = 0, 1
 
 
 def last_build_info():
@@ -203,7 +204,7 @@ class sp_b200_Params(C.Structure):
     _fields_ = [("samplesPerPixel", u32), ("bounceCount", u32), ("radianceClamp", f32),
                 ("envFilter", u32), ("mathMode", u32), ("cullByDistance", u32),
                 ("tileWidth", u32), ("tileHeight", u32), ("renderMode", u32),
-                ("samplesPerPass", u32)]
+                ("samplesPerPass", u32), ("triangleTest", u32)]
 
 
 class sp_b200_Stats(C.Structure):
@@ -281,6 +282,10 @@ _SIGNATURES = {
     "sp_b200_SetRaySorting": (None, [C.c_int]),
     "sp_b200_SetPrimaryCandidates": (None, [C.c_int]),
     "sp_b200_SetCopyOverlap": (None, [C.c_int]),
+    "sp_b200_AccumulateFrame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u32, u32, C.c_void_p]),
+    "sp_b200_XorShift32Stream": (None, [_P(u32), u32, C.c_void_p]),
+    "sp_b200_MeshIntersectedLeavesBatch": (C.c_int, [sp_Mesh, u32, C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_float)]),
+    "sp_b200_RayIntersectMeshBatch": (C.c_int, [sp_Mesh, u32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_float)]),
     "sp_b200_RayIntersectAabb4Batch": (C.c_int, [u32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_b200_TileCombinerStats": (None, [_P(C.c_uint64), _P(C.c_uint64)]),
     "sp_b200_SetDeviceTexture": (None, [C.c_void_p, C.c_void_p, u32, u32, C.c_void_p]),
@@ -461,6 +466,36 @@ def save_exr(path, rgba, pixel_type=EXR_FLOAT, compression=EXR_ZIP, tile=None):
         return lib.sp_b200_SaveExrImageTiled(C.byref(hdr), os.fsencode(path), pixel_type, compression,
                                              tile[0], tile[1]) == 0
     return lib.sp_b200_SaveExrImage(C.byref(hdr), os.fsencode(path), pixel_type, compression) == 0
+
+
+def xorshift_bilateral_stream(seed):
+    """draw(n): the next n values of RandomBilateral (math_utils.h:198-214) over one XorShift32 stream."""
+    state = u32(seed)
+
+    def draw(n):
+        raw = np.zeros(n, np.uint32)
+        lib.sp_b200_XorShift32Stream(C.byref(state), n, raw.ctypes.data)
+        uni = (raw >> np.uint32(1)).astype(np.float32) / np.float32(2147483648.0)
+        return (np.float32(-1.0) + np.float32(2.0) * uni).astype(np.float32)
+    return draw
+
+
+def mesh_leaves_batch(mesh, origins, dirs):
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((len(o), 3), np.uint32)
+    ms = C.c_float()
+    assert lib.sp_b200_MeshIntersectedLeavesBatch(mesh, len(o), o.ctypes.data, d.ctypes.data, out.ctypes.data, C.byref(ms)) == 0
+    return out, ms.value
+
+
+def mesh_intersect_batch(mesh, origins, dirs):
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    t, tri = np.zeros(len(o), np.float32), np.zeros(len(o), np.int32)
+    ms = C.c_float()
+    assert lib.sp_b200_RayIntersectMeshBatch(mesh, len(o), o.ctypes.data, d.ctypes.data, t.ctypes.data, tri.ctypes.data, C.byref(ms)) == 0
+    return t, tri, ms.value
 
 
 def last_stats():

@@ -324,6 +324,108 @@ def nested_objects_workload(count=48, width=96, height=64, spp=1, bounces=3, env
         spp=spp, bounces=bounces, notes={"objects": count})
 
 
+def crack_test_inputs(n=24, rays=200000, seed=0x45BA12F3):
+    """A wavy sheet of 2 n^2 triangles facing +z and `rays` rays from seeded origins above it, each
+    aimed at a point that lies EXACTLY on an interior shared edge or vertex of the sheet (vertices,
+    edge midpoints, random points of edges).  The direction is rounded to f32, so each ray passes within
+    an ulp of the edge: a test that evaluates the two neighbours independently can reject the ray on
+    both sides (a crack); a watertight test cannot.  Returns (mesh, origins, dirs)."""
+    rng = np.random.RandomState(seed & 0x7FFFFFFF)
+    xs = np.linspace(-1.0, 1.0, n + 1).astype(np.float32)
+    gx, gy = np.meshgrid(xs, xs)
+    gz = (0.15 * np.sin(3.0 * gx) * np.cos(3.0 * gy)).astype(np.float32)
+    v = np.zeros(((n + 1) * (n + 1), 8), np.float32)
+    v[:, 0], v[:, 1], v[:, 2] = gx.ravel(), gy.ravel(), gz.ravel()
+    v[:, 5] = 1.0
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a, b = j * (n + 1) + i, j * (n + 1) + i + 1
+            c, d = a + n + 1, b + n + 1
+            idx += [a, b, d, a, d, c]
+    mesh = Mesh(v, np.asarray(idx, np.uint32))
+    pos = v[:, 0:3].reshape(n + 1, n + 1, 3)
+    j = rng.randint(1, n - 1, rays)
+    i = rng.randint(1, n - 1, rays)
+    kind = rng.randint(0, 4, rays)
+    p0 = pos[j, i]
+    # the other end of an edge leaving (i, j): +x, +y or the diagonal of the cell (a -> d)
+    di = np.where(kind == 2, 0, 1)
+    dj = np.where(kind == 1, 0, 1)
+    dj = np.where(kind == 0, 0, dj)
+    di = np.where(kind == 0, 0, di)
+    p1 = pos[j + dj, i + di]
+    w = np.where(kind == 0, 0.0, np.where(rng.rand(rays) < 0.5, 0.5, rng.rand(rays))).astype(np.float32)
+    target = (p0 + (p1 - p0) * w[:, None]).astype(np.float32)
+    origins = np.stack([rng.uniform(-1.5, 1.5, rays), rng.uniform(-1.5, 1.5, rays), rng.uniform(1.0, 4.0, rays)], axis=1).astype(np.float32)
+    d = (target - origins).astype(np.float32)
+    d = (d / np.sqrt((d * d).sum(axis=1, dtype=np.float32))[:, None]).astype(np.float32)
+    return mesh, origins, d
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own performance tests (perf_tests/perf_tests.cpp), inputs restated draw for draw.
+# `draw(n)` returns the next n RandomBilateral values of ONE XorShift32 stream (seed 0x1A34C249,
+# perf_tests.cpp:57,214): sp.xorshift_bilateral_stream on the product side, ora's on the checker's.
+
+def _lerp(a, b, t):
+    return (np.float32(a) * (np.float32(1.0) - t) + np.float32(b) * t).astype(np.float32)
+
+
+def _perf_rays(draw, lo, hi, count):
+    """perf_tests.cpp:80-99 / :243-258: per ray six draws in statement order x0 y0 z0 x1 y1 z1,
+    Lerp(min, max, RandomBilateral) (t in [-1, 1]: points may lie outside the box), Normalize(q - p)."""
+    r = draw(count * 6).reshape(count, 6)
+    p = np.stack([_lerp(lo[k], hi[k], r[:, k]) for k in range(3)], axis=1)
+    q = np.stack([_lerp(lo[k], hi[k], r[:, 3 + k]) for k in range(3)], axis=1)
+    d = (q - p).astype(np.float32)
+    # Normalize (math_lib.h:503-512): sqrt of the dot product in f32, multiply by the reciprocal
+    length = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(np.float32)).astype(np.float32)
+    inv = (np.float32(1.0) / length).astype(np.float32)
+    return p.astype(np.float32), (d * inv[:, None]).astype(np.float32)
+
+
+def perf_bvh_inputs(draw, boxes=2048, rays=8192):
+    """TestBvh (perf_tests.cpp:51-118): 2048 boxes -- centre 2000 * (B, B, B) with the THREE draws of the
+    Vec3(...) call made right to left (g++ evaluates call arguments last to first: z, y, x), then radius
+    500 * B, min = centre - radius, max = centre + radius (a negative radius gives min > max; the slab
+    test orders each axis itself) -- and 8192 rays inside the root's bounds."""
+    r = draw(boxes * 4).reshape(boxes, 4)
+    s = np.float32(2000.0)
+    centre = np.stack([s * r[:, 2], s * r[:, 1], s * r[:, 0]], axis=1).astype(np.float32)
+    radius = (np.float32(500.0) * r[:, 3]).astype(np.float32)
+    mn = (centre - radius[:, None]).astype(np.float32)
+    mx = (centre + radius[:, None]).astype(np.float32)
+    lo, hi = np.minimum(mn, mx).min(axis=0), np.maximum(mn, mx).max(axis=0)   # root of the reference's tree: all boxes
+    lo, hi = mn.min(axis=0), mx.max(axis=0)
+    origins, dirs = _perf_rays(draw, lo, hi, rays)
+    return mn, mx, origins, dirs
+
+
+def boxes_as_triangles(mn, mx):
+    """A mesh whose triangle i has exactly box i as its AABB (vertices at min, max and (min.x, max.y,
+    min.z)): bvh_IntersectRay over boxes becomes the leaf query of a mesh tree.  The per-axis order of
+    min / max does not matter to the slab test (simd.h:226-239 orders t0, t1 itself)."""
+    n = len(mn)
+    v = np.zeros((n * 3, 8), np.float32)
+    v[0::3, 0:3] = mn
+    v[1::3, 0:3] = mx
+    v[2::3, 0] = mn[:, 0]
+    v[2::3, 1] = mx[:, 1]
+    v[2::3, 2] = mn[:, 2]
+    v[:, 5] = 1.0
+    return Mesh(v, np.arange(n * 3, dtype=np.uint32))
+
+
+def perf_mesh_inputs(draw, rays, level=3):
+    """TestMeshMidphase (perf_tests.cpp:212-305): a level-3 icosphere (1280 triangles) and `rays` rays
+    (the reference: 1024 * 8192) between seeded points of its bounding box."""
+    mesh = icosphere_mesh(level, smooth=False)
+    lo, hi = mesh.bounds()
+    origins, dirs = _perf_rays(draw, lo.astype(np.float32), hi.astype(np.float32), rays)
+    return mesh, origins, dirs
+
+
 def config5(width=3840, height=2160, spp=16, bounces=5, bunnies=64, spheres=118, sphere_level=6,
             unique_spheres=False, seed=0x1A34C249, env_size=(4096, 2048)):
     """BASELINE configs[4]: procedural instanced scene, ~10 M triangles at the defaults
