@@ -259,8 +259,10 @@ enum { SP_B200_ENV_NEAREST = 0, SP_B200_ENV_BILINEAR = 1 };
  * parity default.  WATERTIGHT: Woop / Benthin / Wald 2013 with the reference's acceptance rules (front
  * faces, t > 0): no ray through a shared edge or vertex of two triangles can miss both.  It decides
  * those edge cases differently from the reference BY DESIGN, so images can differ from the
- * reference's in the pixels such rays belong to; every other guarantee (scheduler independence,
- * multi-GPU split) holds in both modes. */
+ * reference's in the pixels such rays belong to.  Every box test on the way is padded in this mode
+ * (a ray that grazes a shared edge also grazes a face of both triangles' boxes).  Implemented in the
+ * non-resumable walk: sp_b200_Render* use the per-pixel kernel while it is selected, whatever
+ * renderMode says; ray queries and sp_PathTraceTile honour it directly. */
 enum { SP_B200_TRIANGLE_MOLLER_TRUMBORE = 0, SP_B200_TRIANGLE_WATERTIGHT = 1 };
 enum { SP_B200_MATH_F64_ROUNDED = 0, SP_B200_MATH_FAST_F32 = 1 };
 /* WAVEFRONT: ray generation / traversal / shading as separate kernels over compact device

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """DRAM traffic of the kernels captured in an .ncu-rep (ncu --set full): per launch and summed.
 Writes profiles/trace_traffic.json, which bench.py reports as roofline.traffic.
-usage: python tools/ncu_traffic.py rep.ncu-rep workload spp width [out.json]"""
+usage: python tools/ncu_traffic.py rep.ncu-rep workload spp width [out.json] [traced rays per step]
+(the traced-ray count, printed by `bench.py --quick` as traced_rays_per_step, lets bench.py scale the
+per-launch DRAM bytes to a strip of the frame)"""
 import csv
 import json
 import subprocess
@@ -11,6 +13,7 @@ import sys
 def main():
     rep, workload, spp, width = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
     out = sys.argv[5] if len(sys.argv) > 5 else "profiles/trace_traffic.json"
+    traced = float(sys.argv[6]) if len(sys.argv) > 6 else None
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -28,6 +31,7 @@ def main():
     total = sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in launches)
     doc = {"workload": workload, "spp": spp, "width": width, "launches": len(launches),
            "dram_bytes_per_step": total, "dram_bytes_per_launch": total / max(1, len(launches)),
+           "traced_rays_per_step": traced,
            "source": rep.split("/")[-1] + " (ncu --set full --clock-control none, every k_trace launch of one frame)",
            "per_launch": launches}
     json.dump(doc, open(out, "w"), indent=1)

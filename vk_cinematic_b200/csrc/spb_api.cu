@@ -1937,7 +1937,10 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     u32 firstTileRow = rowBegin / tileH;
     u32 tileRows = (rowEnd - 1) / tileH - firstTileRow + 1;
 
-    const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL;
+    // (the wavefront kernels run the reference's triangle test only: the watertight option renders
+    // with the per-pixel kernel, whose walk carries the padded box tests that option needs)
+    const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL &&
+                           L.params.triangleTest == SP_B200_TRIANGLE_MOLLER_TRUMBORE;
     SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
     // (the wavefront path waits for texture uploads where its first texture-reading kernel starts)
     const DMaterials *dm = upload_materials(ctx->materialSystem, nullptr, wavefront);

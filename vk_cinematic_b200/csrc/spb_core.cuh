@@ -341,7 +341,7 @@ SPB_HD void grow_box(f3 o, float &bminx, float &bminy, float &bminz, float &bmax
     bminx -= px; bminy -= py; bminz -= pz;
     bmaxx += px; bmaxy += py; bmaxz += pz;
 }
-SPB_HD_NOINLINE void grow_boxes4(f3 o, v4f &minx, v4f &miny, v4f &minz, v4f &maxx, v4f &maxy, v4f &maxz)
+SPB_HD void grow_boxes4(f3 o, v4f &minx, v4f &miny, v4f &minz, v4f &maxx, v4f &maxy, v4f &maxz)
 {
     grow_box(o, minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x);
     grow_box(o, minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y);
@@ -554,7 +554,9 @@ SPB_HD float cull_pad(f3 worldOrigin, float t)
 }
 
 // sp_RayIntersectMesh (sp_scene.cpp:127-227) on one object-space ray.
-template <bool CULL, bool EXACT>
+// WT: whether sp_b200_Params::triangleTest may be honoured here (false in the wavefront kernels, which
+// run the reference's test only and must not carry the option's code at all).
+template <bool CULL, bool EXACT, bool WT = true>
 SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float tcull,
                            uint32_t *stack, float *stackT, int stackBase, Counters *counters,
                            float &bestT, uint32_t &bestSlot, float &bestU, float &bestV)
@@ -569,7 +571,7 @@ SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float
         v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle(S.triangleTest, o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
+        if (ray_triangle(WT ? S.triangleTest : 0u, o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, u, v))
         {
             if (t > 0.0f)
             {
@@ -587,7 +589,7 @@ SPB_HD void intersect_mesh(const DScene &S, uint32_t meshRoot, f3 o, f3 d, float
         return cull;
     };
     traverse<CULL, EXACT>(S.nodes, meshRoot, o, inv, tcull, stack, stackT, stackBase, SPB_STACK_SIZE, counters, leaf,
-                          S.triangleTest);
+                          WT ? S.triangleTest : 0u);
 }
 
 SPB_HD m4 load_m4(const v4f *p)
@@ -609,7 +611,7 @@ SPB_HD bool any_nonfinite_inv(f3 d)
 
 // sp_RayIntersectScene (sp_scene.cpp:229-339): closest hit over all objects whose world AABB the
 // ray passes.  The winner's surface attributes are resolved afterwards by resolve_hit().
-template <bool CULL>
+template <bool CULL, bool WT = true>
 SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *stackT,
                            Counters *counters)
 {
@@ -644,9 +646,9 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
         // the object traversal continues on the same stack above the entries of the TLAS
         int base = SPB_STACK_SIZE / 3;
         if (any_nonfinite_inv(ld))
-            intersect_mesh<CULL, true>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
+            intersect_mesh<CULL, true, WT>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
         else
-            intersect_mesh<CULL, false>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
+            intersect_mesh<CULL, false, WT>(S, info.x, lo, ld, localCull, stack, stackT, base, counters, lt, lslot, lu, lv);
 
         if (lt >= 0.0f)
         {
@@ -672,10 +674,11 @@ SPB_HD Hit intersect_scene(const DScene &S, f3 o, f3 d, uint32_t *stack, float *
         return cull;
     };
 
+    const uint32_t watertight = WT ? S.triangleTest : 0u;
     if (worldExact)
-        traverse<CULL, true>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, S.triangleTest);
+        traverse<CULL, true>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, watertight);
     else
-        traverse<CULL, false>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, S.triangleTest);
+        traverse<CULL, false>(S.nodes, S.tlasRoot, o, inv, inf, stack, stackT, 0, SPB_STACK_SIZE / 3, counters, objectLeaf, watertight);
     return best;
 }
 
@@ -856,7 +859,6 @@ SPB_HD void trav_begin_single(const DScene &S, f3 o, f3 d, Trav &st, TravCold &c
     st.cur = SPB_NODE_DONE;
     if (counters) counters->nodeVisits++;
     v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
-    if (S.triangleTest) grow_box(st.o, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z);
     float tn;
     if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, st.o, st.inv, tn)) return;
     v4u info = ld4u(S.objInfo);
@@ -915,7 +917,6 @@ SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *cou
     v4u refs;
     refs.x = f2u(refsf.x); refs.y = f2u(refsf.y); refs.z = f2u(refsf.z); refs.w = f2u(refsf.w);
     if (counters) counters->nodeVisits++;
-    if (S.triangleTest) grow_boxes4(st.o, minx, miny, minz, maxx, maxy, maxz);
 
     float tn0, tn1, tn2, tn3;
     bool h0 = slab_fast(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, st.o, st.inv, tn0);
@@ -987,7 +988,7 @@ SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, Tr
         v4f a = ld4(tp + 0), b = ld4(tp + 1), cc = ld4(tp + 2);
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle(S.triangleTest, st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(cc.x, cc.y, cc.z), t, u, v))
+        if (ray_triangle_mt(st.o, st.d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(cc.x, cc.y, cc.z), t, u, v))
         {
             if (t > 0.0f && (t < st.lT || st.lT < 0.0f))
             {
@@ -1037,7 +1038,9 @@ SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, Tr
 
 // Barycentrics of the winning triangle, recomputed from the same inputs with the same code the
 // traversal ran (so the same bits): the traversal itself carries only (t, slot, object).
-SPB_HD void hit_barycentrics(const DScene &S, f3 o, f3 d, Hit &hit)
+// `watertight`: the triangle test the hit was found with (a compile-time 0 in the wavefront kernels,
+// which only run the reference's test; DScene::triangleTest in the per-pixel and query kernels).
+SPB_HD void hit_barycentrics(const DScene &S, f3 o, f3 d, Hit &hit, uint32_t watertight = 0)
 {
     m4 invModel = load_m4(S.objInv + (size_t)hit.object * 4);
     f3 lo = xform(invModel, o, 1.0f);
@@ -1045,7 +1048,7 @@ SPB_HD void hit_barycentrics(const DScene &S, f3 o, f3 d, Hit &hit)
     const v4f *tp = S.tris + (size_t)hit.slot * 3;
     v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
     float t;
-    ray_triangle(S.triangleTest, lo, ld, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, hit.u, hit.v);
+    ray_triangle(watertight, lo, ld, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, hit.u, hit.v);
 }
 
 SPB_HD Hit trav_result(const TravCold &c)
@@ -1083,7 +1086,7 @@ SPB_HD Hit intersect_scene_stepped(const DScene &S, f3 o, f3 d, uint32_t *stack,
         else trav_leaf<CULL>(S, st, cold, ray, entries, counters);
     }
     if (single && st.cur == SPB_NODE_EXIT) trav_leave(S, st, cold, ray);
-    if (cold.slow) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+    if (cold.slow) return intersect_scene<CULL, false>(S, o, d, stack, stackT, counters);
     Hit h = trav_result(cold);
     if (h.object >= 0) hit_barycentrics(S, o, d, h);
     return h;
@@ -1311,7 +1314,6 @@ SPB_HD void trav2_node(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
     else
     {
         const f3 o = v.f3at(T2_WOX), inv = v.f3at(T2_WIX);
-        if (S.triangleTest) grow_boxes4(o, minx, miny, minz, maxx, maxy, maxz);
         k0 = slab_key(minx.x, miny.x, minz.x, maxx.x, maxy.x, maxz.x, o, inv, tlimit);
         k1 = slab_key(minx.y, miny.y, minz.y, maxx.y, maxy.y, maxz.y, o, inv, tlimit);
         k2 = slab_key(minx.z, miny.z, minz.z, maxx.z, maxy.z, maxz.z, o, inv, tlimit);
@@ -1431,11 +1433,8 @@ SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
         const v4f *tp = S.tris + (size_t)index * 3;
         v4f a = ld4(tp + 0), b = ld4(tp + 1), c = ld4(tp + 2);
         // the triangle's own box (sp_scene.cpp:35-50) and the reference's test of it (bvh.cpp:236-255)
-        // (watertight mode: the padded test of the parent's node step stands; no exact test may
-        // come between it and the triangle test)
-        float tn = 0.0f;
-        const bool own = S.triangleTest != 0 ||
-                         slab_fast(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)),
+        float tn;
+        const bool own = slab_fast(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)),
                                    fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)),
                                    o, inv, tn);
         if (own && (!CULL || tn <= st.tcull))
@@ -1443,7 +1442,7 @@ SPB_HD void trav2_leaf(const DScene &S, Trav2 &st, const T2View<STRIDE> &v, Trav
             if (counters) counters->triangleTests++;
             const f3 d = v.f3at(T2_DX);
             float t, uu, vv;
-            if (ray_triangle(S.triangleTest, o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, uu, vv))
+            if (ray_triangle_mt(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t, uu, vv))
             {
                 const float lT = v.f(T2_LT);
                 if (t > 0.0f && (t < lT || lT < 0.0f))
@@ -1481,7 +1480,6 @@ SPB_HD void trav2_begin_single(const DScene &S, f3 o, f3 d, Trav2 &st, const T2V
     if (!trav2_start(S, o, d, st, v)) return;
     if (counters) counters->nodeVisits++;
     v4f bmin = ld4(S.objBox), bmax = ld4(S.objBox + 1);
-    if (S.triangleTest) grow_box(o, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z);
     float tn;
     if (!slab_fast(bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, o, v.f3at(T2_WIX), tn)) return;
     v4u info = ld4u(S.objInfo);
@@ -1524,7 +1522,7 @@ SPB_HD Hit intersect_scene_stepped2(const DScene &S, f3 o, f3 d, uint32_t *stack
         else if ((st.cur & SPB_REF_LEAF) == 0) trav2_node<CULL>(S, st, v, entries, counters);
         else trav2_leaf<CULL>(S, st, v, entries, counters);
     }
-    if (v.u(T2_SLOW)) return intersect_scene<CULL>(S, o, d, stack, stackT, counters);
+    if (v.u(T2_SLOW)) return intersect_scene<CULL, false>(S, o, d, stack, stackT, counters);
     Hit h = trav2_finish(S, st, v);
     if (h.object >= 0) hit_barycentrics(S, o, d, h);
     return h;
@@ -1966,9 +1964,7 @@ SPB_HD int resolve_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d,
         v4f mnx = ld4(n + 0), mny = ld4(n + 1), mnz = ld4(n + 2), mxx = ld4(n + 3), mxy = ld4(n + 4), mxz = ld4(n + 5);
         float tn;
         if (counters) counters->nodeVisits++;
-        float b0 = mnx.x, b1 = mny.x, b2 = mnz.x, b3 = mxx.x, b4 = mxy.x, b5 = mxz.x;
-        if (S.triangleTest) grow_box(o, b0, b1, b2, b3, b4, b5);
-        if (!slab_fast(b0, b1, b2, b3, b4, b5, o, winv, tn)) return 0; // miss
+        if (!slab_fast(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, winv, tn)) return 0; // miss
     }
     // object entry (sp_scene.cpp:274-276)
     v4u info = ld4u(S.objInfo);
@@ -1989,11 +1985,10 @@ SPB_HD int resolve_candidates(const DScene &S, const uint32_t *list, f3 o, f3 d,
         f3 bmn, bmx;
         triangle_box(va, vb, vc, bmn, bmx);
         float tn;
-        if (S.triangleTest) grow_box(lo, bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z);
         if (!slab_fast(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, lo, inv, tn)) continue; // the leaf's own box
         if (counters) counters->triangleTests++;
         float t, u, v;
-        if (ray_triangle(S.triangleTest, lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
+        if (ray_triangle_mt(lo, ld, mk3(va.x, va.y, va.z), mk3(vb.x, vb.y, vb.z), mk3(vc.x, vc.y, vc.z), t, u, v))
             if (t > 0.0f && (t < lT || lT < 0.0f))
             {
                 lT = t;

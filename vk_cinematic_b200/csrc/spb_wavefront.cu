@@ -135,7 +135,7 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 {
     uint32_t stack[SPB_STACK_SIZE];
     float stackT[SPB_STACK_SIZE];
-    Hit h = intersect_scene<CULL>(S, o, d, stack, stackT, nullptr);
+    Hit h = intersect_scene<CULL, false>(S, o, d, stack, stackT, nullptr);
     return h;
 }
 

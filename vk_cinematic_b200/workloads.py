@@ -385,19 +385,24 @@ def _perf_rays(draw, lo, hi, count):
     return p.astype(np.float32), (d * inv[:, None]).astype(np.float32)
 
 
-def perf_bvh_inputs(draw, boxes=2048, rays=8192):
+def perf_bvh_inputs(draw, boxes=2048, rays=8192, proper=False):
     """TestBvh (perf_tests.cpp:51-118): 2048 boxes -- centre 2000 * (B, B, B) with the THREE draws of the
     Vec3(...) call made right to left (g++ evaluates call arguments last to first: z, y, x), then radius
-    500 * B, min = centre - radius, max = centre + radius (a negative radius gives min > max; the slab
-    test orders each axis itself) -- and 8192 rays inside the root's bounds."""
+    500 * B, min = centre - radius, max = centre + radius -- and 8192 rays inside the root's bounds.
+    Half the radii are NEGATIVE, i.e. half the boxes have min > max.  The slab test orders each axis
+    itself, so such a leaf is tested like its reordered box; but the reference's tree unions boxes with
+    Min(min) / Max(max), which for inverted children is not a union at all, so which of those leaves
+    bvh_IntersectRay reports depends on its tree.  `proper=True` uses |radius| (same draws): the input
+    on which "every leaf whose own box the ray passes" is well defined and tree-independent."""
     r = draw(boxes * 4).reshape(boxes, 4)
     s = np.float32(2000.0)
     centre = np.stack([s * r[:, 2], s * r[:, 1], s * r[:, 0]], axis=1).astype(np.float32)
     radius = (np.float32(500.0) * r[:, 3]).astype(np.float32)
+    if proper:
+        radius = np.abs(radius)
     mn = (centre - radius[:, None]).astype(np.float32)
     mx = (centre + radius[:, None]).astype(np.float32)
-    lo, hi = np.minimum(mn, mx).min(axis=0), np.maximum(mn, mx).max(axis=0)   # root of the reference's tree: all boxes
-    lo, hi = mn.min(axis=0), mx.max(axis=0)
+    lo, hi = mn.min(axis=0), mx.max(axis=0)     # tree.root->min / max: Min over the mins, Max over the maxes
     origins, dirs = _perf_rays(draw, lo, hi, rays)
     return mn, mx, origins, dirs
 
