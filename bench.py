@@ -635,27 +635,46 @@ def main():
     # rank uploads one slice of the environment map and an NCCL all-gather over NVLink assembles the
     # copies (sp_b200_SetDeviceTexture), and every rank writes its rows into the shared host image.
     env_flat = env_pinned.view(-1)
-    env_dev = torch.empty_like(env_flat, device=dev) if world > 1 else None
+    # (several ranks: two device copies of the map, filled alternately -- the slice upload and the
+    # all-gather of step k + 1 run on a side stream while step k renders from the other copy)
+    env_dev = [torch.empty_like(env_flat, device=dev) for _ in range(2)] if world > 1 else None
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    env_ready = torch.cuda.Event() if world > 1 else None
+    env_ready = [torch.cuda.Event() for _ in range(2)] if world > 1 else None
+    env_issued = [-1, -1]
     eh, ew = wl.textures[env_key].shape[0], wl.textures[env_key].shape[1]
+
+    def upload_env(step):
+        """This rank's slice of the environment map to the device and the all-gather of the other ranks'
+        slices over NVLink, for e2e step `step`, on the side stream."""
+        buf = step % 2
+        if env_issued[buf] == step:
+            return
+        n = env_flat.numel() // world
+        side.wait_stream(stream)                      # the render that last read this copy is enqueued before us
+        with torch.cuda.stream(side):
+            lo, hi = rank * n, (rank + 1) * n
+            env_dev[buf][lo:hi].copy_(env_flat[lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(env_dev[buf][:n * world], env_dev[buf][lo:hi])
+            if n * world < env_flat.numel():
+                env_dev[buf][n * world:].copy_(env_flat[n * world:], non_blocking=True)
+            env_ready[buf].record(side)
+        env_issued[buf] = step
+
+    e2e_counter = [0]
 
     def e2e_step(frame):
         b, e = bounds[rank]
-        sp.lib.sp_b200_FlushTextureCache()           # env map + materials re-uploaded
+        k = e2e_counter[0]
+        e2e_counter[0] += 1
         if world > 1:
-            n = env_flat.numel() // world
-            side.wait_stream(stream)
-            with torch.cuda.stream(side):
-                lo, hi = rank * n, (rank + 1) * n
-                env_dev[lo:hi].copy_(env_flat[lo:hi], non_blocking=True)
-                dist.all_gather_into_tensor(env_dev[:n * world], env_dev[lo:hi])
-                if n * world < env_flat.numel():
-                    env_dev[n * world:].copy_(env_flat[n * world:], non_blocking=True)
-                env_ready.record(side)
-            sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), env_dev.data_ptr(), ew, eh, env_ready.cuda_event)
+            upload_env(k)                             # (already in flight since the previous step, except for the first)
+            sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), env_dev[k % 2].data_ptr(), ew, eh, env_ready[k % 2].cuda_event)
+        else:
+            sp.lib.sp_b200_FlushTextureCache()       # env map + materials re-uploaded
         r.build()                                     # scene flattened and re-uploaded
         m = np.zeros(12, np.uint64)
+        if world > 1:
+            upload_env(k + 1)                         # next step's copy goes up under this step's kernels
         if e > b:
             m, _ = r.render_rows(b, e, frame=frame, host=True)   # rows -> pinned host image
         if world > 1:
@@ -674,6 +693,7 @@ def main():
     barrier()
     e2e_secs = time.perf_counter() - t0
     if world > 1:
+        torch.cuda.synchronize()
         sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), None, 0, 0, None)
         sp.lib.sp_b200_FlushTextureCache()
     est = torch.tensor([e2e_secs, float(e2e_rays)], dtype=torch.float64, device=dev)
@@ -754,7 +774,8 @@ def main():
                     "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": H * Wd * 16, "ms_per_step": e2e_secs / args.steps * 1e3,
                     "how": "per step: texture cache flushed, scene re-built and re-uploaded, environment map re-uploaded "
-                           + ("(one slice per rank + NCCL all-gather), rows copied by every rank into one shared pinned host image, barrier"
+                           + ("(one slice per rank + NCCL all-gather over NVLink, double-buffered: step k + 1's copy goes up under step k's "
+                              "kernels), rows copied by every rank into one shared pinned host image, barrier"
                               if world > 1 else "(copy stream, overlapped with coverage / candidates / first primary trace), "
                               "rows copied to the pinned host image band by band while later bands render")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
