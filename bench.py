@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--strip-rows", type=int, default=8, help="granularity of strip boundaries in pixel rows (multiple of 4)")
     ap.add_argument("--sort-bounces", type=int, default=0, help="development: direction-sort the rays leaving this many bounces")
     ap.add_argument("--refill", default="", help="development: refill thresholds primary,sorted,other")
+    ap.add_argument("--evict", default="", help="development: straggler eviction thresholds sorted,other (0 = off)")
     ap.add_argument("--no-candidates", action="store_true", help="development: every primary ray walks the tree")
     ap.add_argument("--no-ray-sorting", action="store_true", help="development: bounce rays in hit-queue order")
     ap.add_argument("--paths-per-pass", type=int, default=0, help="development: paths in flight per pass (0 = library default)")
@@ -497,6 +498,8 @@ def main():
         sp.lib.sp_b200_SetRaySorting(args.sort_bounces)
     if args.refill:
         sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
+    if args.evict:
+        sp.lib.sp_b200_SetStragglerEviction(*[int(x) for x in args.evict.split(",")])
     if args.no_copy_overlap:
         sp.lib.sp_b200_SetCopyOverlap(0)
     TH = args.strip_rows   # strip boundaries and cost accounting: rows of TH pixels

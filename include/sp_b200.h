@@ -380,6 +380,15 @@ void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */
 void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
+/* Wavefront mode tuning: straggler eviction of the bounce traces.  A warp of the trace kernel walks a
+ * packet of 32 rays; the rays of a packet end at different times, and the last few would keep the warp
+ * busy at a fraction of its lanes.  With a threshold > 0, a packet whose walking lanes drop below it
+ * parks them (a 128-byte continuation record each: traversal state and live stack entries) and the warp
+ * starts the next packet; a second launch of the kernel refills its lanes from the parked records, so the
+ * stragglers of many packets walk on together.  Every ray takes the same sequence of traversal steps
+ * either way: results are bit-identical.  `sorted`: threshold for the direction-sorted launch (the first
+ * bounce), `other`: for the later bounces; 0 = off (then sp_b200_SetRefillThresholds applies). */
+void sp_b200_SetStragglerEviction(u32 sorted, u32 other);
 /* `count` draws of the reference's XorShift32 (math_utils.h:184-196) continuing *state (host side,
  * integer only): what seeded inputs like the reference's perf tests' are generated from. */
 void sp_b200_XorShift32Stream(u32 *state, u32 count, u32 *values);

@@ -765,6 +765,13 @@ def test_c5_instanced_scene(params):
     assert np.array_equal(g["obj"], e["obj"]) and same_bits(g["t"], e["t"])
     assert (g["tri"] != e["tri"]).sum() <= 1e-4 * g["tri"].size
     assert len(np.unique(e["obj"])) > 100
+    # straggler eviction in a multi-object scene: continuations parked in the TLAS and inside objects
+    img = img.copy()
+    for evict in ((12, 12), (32, 20)):
+        sp.lib.sp_b200_SetStragglerEviction(*evict)
+        img2, m2 = r.render_frame(frame=4)
+        assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5]), evict
+    sp.lib.sp_b200_SetStragglerEviction(0, 0)
     chk.close()
     r.close()
 
@@ -848,6 +855,12 @@ def test_coverage_mask_and_ray_sorting_edge_cases(gpu_sp, case):
         sp.lib.sp_b200_SetRefillThresholds(*thresholds)
         img2, m2 = r.render_frame(frame=5)
         assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5])
+    # straggler eviction (continuation records + a second launch of the trace kernel): same walk, same bits
+    for evict in ((12, 0), (0, 12), (16, 16), (32, 32), (3, 5)):
+        sp.lib.sp_b200_SetStragglerEviction(*evict)
+        img2, m2 = r.render_frame(frame=5)
+        assert same_bits(img2, img) and np.array_equal(m2[1:5], m[1:5]), evict
+    sp.lib.sp_b200_SetStragglerEviction(0, 0)
     sp.lib.sp_b200_SetPathsPerPass(0)
     sp.set_params(renderMode=1)
     img2, m2 = r.render_frame(frame=5)

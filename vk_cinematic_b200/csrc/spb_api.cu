@@ -128,6 +128,10 @@ struct Library
     // packets win when a tile's sorted rays are coherent (C3: one 8x4 block, 64 spp: -6 % frame
     // time), and lose on scenes of sub-pixel triangles (C5: +11 %).
     uint32_t refillThreshold[3] = {1, 0, SPB_REFILL_THRESHOLD};
+    // straggler eviction of the bounce traces (sp_b200_SetStragglerEviction): a packet of the direction-sorted
+    // launch [0] / of the later launches [1] whose walking lanes drop below this many parks them in the
+    // continuation buffer and a second launch walks the parked rays on, compacted; 0 = off
+    uint32_t evictBelow[2] = {8, 0};
     struct SortedTuner
     {
         unsigned long long signature = 0;
@@ -156,7 +160,7 @@ struct Library
     std::unique_ptr<DeviceScene> emptyScene;
     DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
-    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand, wSkyList;
+    DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand, wSkyList, wCont;
     cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
     // Copy engine side of a frame (DESIGN.md "End to end"): texture uploads run on copyStream and
     // the render stream waits for them only where the first kernel that reads a texture is
@@ -316,6 +320,16 @@ void ensure_init()
         abort();
     }
     SPB_CUDA(cudaSetDevice(L.device));
+    // (A/B knob) L2 fetch granularity: the shading kernels read scattered 16- and 32-byte records
+    if (const char *g = getenv("SPB_B200_L2_FETCH"))
+    {
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        log_message("libspb200: L2 fetch granularity %zu -> %zu (%s)", before, after, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
     SPB_CUDA(cudaEventCreate(&L.evStart));
     SPB_CUDA(cudaEventCreate(&L.evKernel0));
     SPB_CUDA(cudaEventCreate(&L.evKernel1));
@@ -842,7 +856,19 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     }
     const bool tuning = a.sortPrimaryHits && L.refillThreshold[1] == 0 && tn.choice < 0;
 
-    auto timed_trace = [&](uint32_t bounce, bool primary) {
+    // continuation buffer of the evicting launches: half the ray slots (a launch that fills it stops evicting)
+    const bool evicting = L.evictBelow[0] || L.evictBelow[1];
+    a.cont = nullptr;
+    a.contCapacity = 0;
+    if (evicting)
+    {
+        const size_t records = allocItems / 2 + 1024;
+        L.wCont.ensure(records * SPB_CONT_QUADS * 16);
+        a.cont = (v4u *)L.wCont.ptr;
+        a.contCapacity = (uint32_t)records;
+    }
+
+    auto timed_trace = [&](uint32_t bounce, bool primary, uint32_t evictBelow = 0) {
         if (L.traceEventsUsed + 2 > L.traceEvents.size())
             for (int k = 0; k < 64; ++k)
             {
@@ -851,7 +877,17 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
                 L.traceEvents.push_back(e);
             }
         SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
-        launch_wave_trace(cfg, a, bounce, primary, L.stream);
+        if (evictBelow && !primary)
+        {
+            // the packets' stragglers are parked (EVICT), then walked on together (RESUME)
+            const uint32_t keep = a.refillThreshold;
+            a.refillThreshold = evictBelow;
+            launch_wave_trace(cfg, a, bounce, SPB_TRACE_EVICT, L.stream);
+            a.refillThreshold = L.refillThreshold[2];
+            launch_wave_trace(cfg, a, bounce, SPB_TRACE_RESUME, L.stream);
+            a.refillThreshold = keep;
+        }
+        else launch_wave_trace(cfg, a, bounce, primary ? SPB_TRACE_PRIMARY : SPB_TRACE_QUEUE, L.stream);
         SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
     };
 
@@ -902,6 +938,12 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
                 else launch_wave_shade(cfg, a, b, L.stream);
                 if (b + 1 >= bounces) break;
                 int probe = -1;
+                const uint32_t evictBelow = L.evictBelow[sortedNext ? 0 : 1];
+                if (evictBelow)
+                {
+                    timed_trace(b + 1, false, evictBelow);
+                    continue;
+                }
                 if (!sortedNext) a.refillThreshold = L.refillThreshold[2];
                 else if (L.refillThreshold[1]) a.refillThreshold = L.refillThreshold[1];
                 else if (tn.choice >= 0) a.refillThreshold = kCandidates[tn.choice];
@@ -980,7 +1022,7 @@ void shutdown_library(Library &L)
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
-    L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release(); L.wSkyList.release();
+    L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release(); L.wSkyList.release(); L.wCont.release();
     for (cudaEvent_t e : L.traceEvents) cudaEventDestroy(e);
     L.traceEvents.clear();
     L.traceEventsUsed = 0;
@@ -1243,6 +1285,13 @@ extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
     L.refillThreshold[0] = primary ? primary : 1;
     L.refillThreshold[1] = sorted; // 0: measured
     L.refillThreshold[2] = other ? other : SPB_REFILL_THRESHOLD;
+}
+
+extern "C" void sp_b200_SetStragglerEviction(u32 sorted, u32 other)
+{
+    Library &L = lib();
+    L.evictBelow[0] = sorted > 32 ? 32 : sorted;
+    L.evictBelow[1] = other > 32 ? 32 : other;
 }
 
 extern "C" void sp_b200_XorShift32Stream(u32 *state, u32 count, u32 *values)
@@ -2324,9 +2373,9 @@ static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, voi
     // what the host set on the primary holds for every device
     struct Settings
     {
-        sp_b200_Params params; bool stats, sky, sort, cand, one, overlap; uint32_t paths, sortBounces, refill[3];
+        sp_b200_Params params; bool stats, sky, sort, cand, one, overlap; uint32_t paths, sortBounces, refill[3], evict[2];
     } set = {P.params, P.statsEnabled, P.skyCulling, P.sortBounceRays, P.primaryCandidates, P.skyOneLookup, P.overlapCopies,
-             P.pathsPerPass, P.sortBounces, {P.refillThreshold[0], P.refillThreshold[1], P.refillThreshold[2]}};
+             P.pathsPerPass, P.sortBounces, {P.refillThreshold[0], P.refillThreshold[1], P.refillThreshold[2]}, {P.evictBelow[0], P.evictBelow[1]}};
     const int primaryDevice = M.devices[0];
     auto render_part = [&](u32 p) {
         const u32 b = M.bounds[p], e = M.bounds[p + 1];
@@ -2338,6 +2387,7 @@ static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, voi
             L.primaryCandidates = set.cand; L.skyOneLookup = set.one; L.overlapCopies = set.overlap;
             L.pathsPerPass = set.paths; L.sortBounces = set.sortBounces;
             for (int k = 0; k < 3; ++k) L.refillThreshold[k] = set.refill[k];
+            L.evictBelow[0] = set.evict[0]; L.evictBelow[1] = set.evict[1];
         }
         partCost[p].assign((e - 1) / quantum - b / quantum + 1, 0);
         // the primary renders straight into the gathered image; the others into their own

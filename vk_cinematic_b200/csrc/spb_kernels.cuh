@@ -165,7 +165,9 @@ bool lbvh_build_binary_device(const float *aabbMin, const float *aabbMax, uint32
 // HITS / MISSES: ALLOCATED lengths of the hit / miss queues -- warps reserve chunks of slots, so a
 // queue ends with up to one partly filled chunk per warp whose tail is holes (SPB_QUEUE_HOLE);
 // CURSOR: work hand-out position of the trace kernel; NHITS / NMISSES: exact counts.
-enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_NHITS, WCTR_NMISSES, WCTR_PAD0, WCTR_PAD1, WCTR_STRIDE };
+// CONT: continuation records written by an EVICT launch of the trace kernel (may exceed the buffer's capacity:
+// the excess was not written); CONT_CURSOR: hand-out position of the RESUME launch.
+enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_NHITS, WCTR_NMISSES, WCTR_CONT, WCTR_CONT_CURSOR, WCTR_STRIDE };
 #define SPB_QUEUE_HOLE 0xFFFFFFFFu
 // largest chunk a warp reserves from a queue counter with one atomic
 #ifndef SPB_CHUNK_MAX
@@ -173,6 +175,11 @@ enum { WCTR_RAYS = 0, WCTR_HITS, WCTR_MISSES, WCTR_CURSOR, WCTR_NHITS, WCTR_NMIS
 #endif
 // extra slots every queue / ray array carries for partly filled chunks: warps in flight x chunk
 #define SPB_QUEUE_SLACK (8192u * SPB_CHUNK_MAX)
+// modes of the trace kernel (spb_wavefront.cu k_trace)
+enum { SPB_TRACE_QUEUE = 0, SPB_TRACE_PRIMARY = 1, SPB_TRACE_RESUME = 2, SPB_TRACE_EVICT = 3 };
+// continuation record of an evicted straggler: 3 quads of state + SPB_CONT_STACK stack entries, two per quad
+#define SPB_CONT_STACK 10u
+#define SPB_CONT_QUADS (3u + SPB_CONT_STACK / 2u)
 
 struct WaveArgs
 {
@@ -213,6 +220,9 @@ struct WaveArgs
     // walking: 1 = packet mode (the whole warp starts and ends together; best when its rays are
     // coherent), SPB_REFILL_THRESHOLD otherwise.  Set per launch by the host.
     uint32_t refillThreshold;
+    // EVICT / RESUME launches: the continuation buffer (SPB_CONT_QUADS quads per record) and its capacity in records
+    v4u *cont;
+    uint32_t contCapacity;
     // Per pixel of the pass (block-major, like the items): candidate triangles of its camera rays
     // (k_candidates): SPB_CAND_STRIDE words per pixel, [0] = count or SPB_CAND_FALLBACK, then the
     // triangle slots.  Null: every primary ray walks the tree.
@@ -234,8 +244,7 @@ struct WaveArgs
 // camera plane).  Then the marked blocks are listed in row-major order; listCount[0] = how many.
 void launch_coverage(const WaveArgs &args, uint64_t instancedTriangles, bool everything, uint8_t *coverage,
                      uint32_t *blockList, uint32_t *listCount, cudaStream_t stream);
-void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, bool primary,
-                       cudaStream_t stream);
+void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, int mode, cudaStream_t stream);
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &args, uint32_t bounce, cudaStream_t stream);
 // k_shade_miss + the tile kernel, which writes the next bounce's rays in direction order per tile
 // (bounce 0 needs sortPrimaryHits: primary results by item; not for the last bounce)

@@ -159,10 +159,11 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 // Registers hold what a node step touches (12 test constants, cull distance, current entry, stack
 // pointer, object); the rest of a lane's state is a 25-word record in shared memory, word-major so
 // that the lanes of a warp hit 32 different banks.
-template <bool CULL, bool STATS, bool PRIMARY>
+template <bool CULL, bool STATS, int MODE>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
+    constexpr bool PRIMARY = MODE == SPB_TRACE_PRIMARY; // (this A/B machine has no eviction / resume modes)
     const unsigned lane = lane_id();
     uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
     const unsigned total = PRIMARY ? a.workItems : ctr[WCTR_RAYS];
@@ -386,16 +387,26 @@ __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsig
 // Traversal kernel.  Persistent warps; every lane owns one ray at a time.  Each iteration of the
 // inner loop the warp runs ONE kind of step -- node visits or leaf work (triangle tests / object
 // entry) -- whichever more of its lanes are waiting for, so both code paths execute with most
-// lanes active.  When fewer than SPB_REFILL_THRESHOLD lanes still have work, finished lanes are
+// lanes active.  When fewer than refillThreshold lanes still have work, finished lanes are
 // retired (hit record, hit/miss queue) and refilled from the ray queue.
-template <bool CULL, bool STATS, bool PRIMARY>
+//
+// MODE (SPB_TRACE_*): QUEUE -- rays of a bounce queue; PRIMARY -- camera rays generated here; EVICT -- a
+// bounce queue walked in packets whose STRAGGLERS are evicted: when fewer than refillThreshold lanes of a
+// packet are still walking, their state (a 128-byte continuation record: what a lane needs to go on, its
+// few live stack entries included) goes to the continuation buffer and the warp starts a fresh packet
+// with all 32 lanes; RESUME -- the second launch of such a step: lanes are refilled from the continuation
+// buffer, so the stragglers of many packets walk on together instead of alone in their warps.  The walk
+// of a ray is the same sequence of steps either way (spb_core.cuh trav_*), hence the same result.
+template <bool CULL, bool STATS, int MODE>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
+    constexpr bool PRIMARY = MODE == SPB_TRACE_PRIMARY, EVICT = MODE == SPB_TRACE_EVICT, RESUME = MODE == SPB_TRACE_RESUME;
     const unsigned lane = lane_id();
     uint32_t *ctr = a.ctr + bounce * WCTR_STRIDE;
-    const unsigned total = PRIMARY ? a.workItems : ctr[WCTR_RAYS];
-    uint32_t *cursor = &ctr[WCTR_CURSOR];
+    // (RESUME: the continuation count of the launch before, clipped to what was written)
+    const unsigned total = PRIMARY ? a.workItems : RESUME ? (ctr[WCTR_CONT] < a.contCapacity ? ctr[WCTR_CONT] : a.contCapacity) : ctr[WCTR_RAYS];
+    uint32_t *cursor = &ctr[RESUME ? WCTR_CONT_CURSOR : WCTR_CURSOR];
     v4f *rays = a.rays[bounce & 1u];
 #if defined(SPB_NO_FUSED_ENTRY)
     const bool single = false; // (A/B build: round 1's behaviour)
@@ -431,6 +442,47 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 
     for (;;)
     {
+        // ---- evict the stragglers of a packet (the walk below came back with fewer than refillThreshold
+        // lanes still walking): continuation records, one atomic per warp; a lane whose stack is deeper
+        // than a record holds stays and walks on beside the next packet
+        if (EVICT)
+        {
+            const bool straggler = have && trav_is_walking(st);
+            const unsigned stragglers = __ballot_sync(SPB_FULL, straggler);
+            if (stragglers && (unsigned)__popc(stragglers) < a.refillThreshold)
+            {
+                const bool fits = straggler && st.sp <= (int)SPB_CONT_STACK;
+                const unsigned m = __ballot_sync(SPB_FULL, fits);
+                if (m)
+                {
+                    const unsigned leader = (unsigned)__ffs(m) - 1u;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(&ctr[WCTR_CONT], (unsigned)__popc(m));
+                    base = __shfl_sync(SPB_FULL, base, leader);
+                    const unsigned at = base + __popc(m & lanemask_lt());
+                    if (fits && at < a.contCapacity)
+                    {
+                        v4u *rec = a.cont + (size_t)at * SPB_CONT_QUADS;
+                        v4u q;
+                        q.x = slot; q.y = st.cur; q.z = f2u(st.tcull); q.w = f2u(st.lT);
+                        rec[0] = q;
+                        q.x = st.lSlot; q.y = (uint32_t)st.sp | ((uint32_t)(st.blasBase + 1) << 16); q.z = f2u(cold.worldCull); q.w = cold.object;
+                        rec[1] = q;
+                        q.x = f2u(cold.bT); q.y = cold.bSlot; q.z = (uint32_t)cold.bObject; q.w = 0;
+                        rec[2] = q;
+                        for (int k = 0; k < st.sp; k += 2)
+                        {
+                            q.x = stack[k].ref; q.y = f2u(stack[k].tnear);
+                            q.z = k + 1 < st.sp ? stack[k + 1].ref : 0u; q.w = k + 1 < st.sp ? f2u(stack[k + 1].tnear) : 0u;
+                            rec[3 + (k >> 1)] = q;
+                        }
+                        have = false;
+                        st.cur = SPB_NODE_DONE;
+                    }
+                }
+            }
+        }
+
         // ---- retire finished lanes: hit record + queue entry
         const bool finished = have && (st.cur == SPB_NODE_DONE || (single && st.cur == SPB_NODE_EXIT));
         if (__any_sync(SPB_FULL, finished))
@@ -491,7 +543,39 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             {
                 unsigned idx = chunk_take(cursor, ws + WS_CUR_NEXT, need, chunk);
                 if (ws[WS_CUR_NEXT] >= total) exhausted = true; // chunks are handed out in order
-                if (!have && idx < total)
+                if (RESUME)
+                {
+                    if (!have && idx < total)
+                    {
+                        // a continuation: the state the EVICT launch parked; the ray in the space it was
+                        // being walked in is recomputed with the arithmetic that produced it the first time
+                        const v4u *rec = a.cont + (size_t)idx * SPB_CONT_QUADS;
+                        v4u q0 = rec[0], q1 = rec[1], q2 = rec[2];
+                        slot = q0.x;
+                        st.cur = q0.y; st.tcull = u2f(q0.z); st.lT = u2f(q0.w);
+                        st.lSlot = q1.x; st.sp = (int)(q1.y & 0xFFFFu); st.blasBase = (int)(q1.y >> 16) - 1;
+                        cold.worldCull = u2f(q1.z); cold.object = q1.w;
+                        cold.bT = u2f(q2.x); cold.bSlot = q2.y; cold.bObject = (int32_t)q2.z; cold.slow = 0;
+                        for (int k = 0; k < st.sp; k += 2)
+                        {
+                            v4u q = rec[3 + (k >> 1)];
+                            stack[k].ref = q.x; stack[k].tnear = u2f(q.y);
+                            if (k + 1 < st.sp) { stack[k + 1].ref = q.z; stack[k + 1].tnear = u2f(q.w); }
+                        }
+                        f3 wo, wd;
+                        trav_world_ray(rays + (size_t)slot * 2, wo, wd);
+                        if (st.blasBase >= 0)
+                        {
+                            m4 invModel = load_m4(a.scene.objInv + (size_t)cold.object * 4);
+                            st.o = xform(invModel, wo, 1.0f);
+                            st.d = normalize3(xform(invModel, wd, 0.0f));
+                        }
+                        else { st.o = wo; st.d = wd; }
+                        st.inv = mk3(1.0f / st.d.x, 1.0f / st.d.y, 1.0f / st.d.z);
+                        have = true;
+                    }
+                }
+                else if (!have && idx < total)
                 {
                     f3 o, d;
                     bool valid = true;
@@ -570,7 +654,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                     trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
-        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || exhausted));
+        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
     }
 
 
@@ -1073,13 +1157,13 @@ k_sky_listed(const __grid_constant__ WaveArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool CULL, bool STATS, bool PRIMARY>
+template <bool CULL, bool STATS, int MODE>
 static void launch_trace_t(const WaveArgs &a, uint32_t bounce, unsigned grid, cudaStream_t stream)
 {
-    k_trace<CULL, STATS, PRIMARY><<<grid, SPB_TRACE_THREADS, 0, stream>>>(a, bounce);
+    k_trace<CULL, STATS, MODE><<<grid, SPB_TRACE_THREADS, 0, stream>>>(a, bounce);
 }
 
-template <bool CULL, bool STATS, bool PRIMARY>
+template <bool CULL, bool STATS, int MODE>
 static unsigned trace_grid_t()
 {
     static unsigned cached = 0;
@@ -1088,7 +1172,7 @@ static unsigned trace_grid_t()
         int device = 0, sms = 0, perSm = 0;
         cudaGetDevice(&device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, PRIMARY>, SPB_TRACE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, MODE>, SPB_TRACE_THREADS, 0);
         if (perSm < 1) perSm = 1;
         cached = (unsigned)(sms * perSm); // persistent: every CTA resident, a multiple of the SM count
         // every warp in flight may leave one partly filled chunk in each queue: the slack the queues
@@ -1102,26 +1186,40 @@ static unsigned trace_grid_t()
     return cached;
 }
 
+#if defined(SPB_TRAV2)
+#define SPB_TRACE_MODES(CALL, C, S)                                                \
+    switch (mode) {                                                                \
+    case SPB_TRACE_PRIMARY: CALL(C, S, SPB_TRACE_PRIMARY); break;                  \
+    case SPB_TRACE_RESUME: break; /* (the A/B machine never evicts) */             \
+    default: CALL(C, S, SPB_TRACE_QUEUE); break;                                   \
+    }
+#else
+#define SPB_TRACE_MODES(CALL, C, S)                                                \
+    switch (mode) {                                                                \
+    case SPB_TRACE_PRIMARY: CALL(C, S, SPB_TRACE_PRIMARY); break;                  \
+    case SPB_TRACE_EVICT: CALL(C, S, SPB_TRACE_EVICT); break;                      \
+    case SPB_TRACE_RESUME: CALL(C, S, SPB_TRACE_RESUME); break;                    \
+    default: CALL(C, S, SPB_TRACE_QUEUE); break;                                   \
+    }
+#endif
 #define SPB_TRACE_DISPATCH(CALL)                                                   \
     do {                                                                           \
-        int key = (cfg.cull ? 4 : 0) | (cfg.stats ? 2 : 0) | (primary ? 1 : 0);    \
+        int key = (cfg.cull ? 2 : 0) | (cfg.stats ? 1 : 0);                        \
         switch (key) {                                                             \
-        case 0: CALL(false, false, false); break;                                  \
-        case 1: CALL(false, false, true); break;                                   \
-        case 2: CALL(false, true, false); break;                                   \
-        case 3: CALL(false, true, true); break;                                    \
-        case 4: CALL(true, false, false); break;                                   \
-        case 5: CALL(true, false, true); break;                                    \
-        case 6: CALL(true, true, false); break;                                    \
-        default: CALL(true, true, true); break;                                    \
+        case 0: SPB_TRACE_MODES(CALL, false, false); break;                        \
+        case 1: SPB_TRACE_MODES(CALL, false, true); break;                         \
+        case 2: SPB_TRACE_MODES(CALL, true, false); break;                         \
+        default: SPB_TRACE_MODES(CALL, true, true); break;                         \
         }                                                                          \
     } while (0)
 
-void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, bool primary,
-                       cudaStream_t stream)
+void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, int mode, cudaStream_t stream)
 {
+#if defined(SPB_TRAV2)
+    if (mode == SPB_TRACE_RESUME) return;
+#endif
     g_kernelLaunches++;
-#define SPB_CALL(C, S, P) launch_trace_t<C, S, P>(a, bounce, trace_grid_t<C, S, P>(), stream)
+#define SPB_CALL(C, S, M) launch_trace_t<C, S, M>(a, bounce, trace_grid_t<C, S, M>(), stream)
     SPB_TRACE_DISPATCH(SPB_CALL);
 #undef SPB_CALL
 }

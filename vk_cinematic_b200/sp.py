@@ -290,6 +290,7 @@ _SIGNATURES = {
     "sp_b200_TileCombinerStats": (None, [_P(C.c_uint64), _P(C.c_uint64)]),
     "sp_b200_SetDeviceTexture": (None, [C.c_void_p, C.c_void_p, u32, u32, C.c_void_p]),
     "sp_b200_SetRefillThresholds": (None, [u32, u32, u32]),
+    "sp_b200_SetStragglerEviction": (None, [u32, u32]),
     "sp_b200_Seed": (u32, [u32, u32, u32]),
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
                                      _P(sp_Metrics), C.c_void_p]),
