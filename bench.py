@@ -691,29 +691,41 @@ def main():
         env_issued[buf] = step
 
     e2e_counter = [0]
+    e2e_phases = np.zeros(4)                          # host seconds: inputs, scene build, render call, barrier
+    e2e_device = np.zeros(2)                          # device ms inside the render call: kernels, whole call
 
     def e2e_step(frame):
         b, e = bounds[rank]
         k = e2e_counter[0]
         e2e_counter[0] += 1
+        t_a = time.perf_counter()
         if world > 1:
             upload_env(k)                             # (already in flight since the previous step, except for the first)
             sp.lib.sp_b200_SetDeviceTexture(env_pinned.data_ptr(), env_dev[k % 2].data_ptr(), ew, eh, env_ready[k % 2].cuda_event)
         else:
             sp.lib.sp_b200_FlushTextureCache()       # env map + materials re-uploaded
+        t_b = time.perf_counter()
         r.build()                                     # scene flattened and re-uploaded
+        t_c = time.perf_counter()
         m = np.zeros(12, np.uint64)
         if world > 1:
             upload_env(k + 1)                         # next step's copy goes up under this step's kernels
         if e > b:
             m, _ = r.render_rows(b, e, frame=frame, host=True)   # rows -> pinned host image
+            st_ = sp.last_stats()
+            e2e_device[:] += (st_.kernelMs, st_.totalMs)
+        t_d = time.perf_counter()
         if world > 1:
             dist.barrier()                            # the frame is complete in host memory
+        t_e = time.perf_counter()
+        e2e_phases[:] += (t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d)
         return m
     for _ in range(2):
         e2e_step(frame)
         frame += 1
     barrier()
+    e2e_phases[:] = 0
+    e2e_device[:] = 0
     t0 = time.perf_counter()
     e2e_rays = 0
     for k in range(args.steps):
@@ -803,6 +815,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s",
                     "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": H * Wd * 16, "ms_per_step": e2e_secs / args.steps * 1e3,
+                    "rank0_host_phases_ms": dict(zip(("inputs", "scene_build", "render_call", "barrier"),
+                                                     [round(float(x) / args.steps * 1e3, 4) for x in e2e_phases])),
+                    "rank0_render_call_device_ms": {"kernels": round(float(e2e_device[0]) / args.steps, 4), "call": round(float(e2e_device[1]) / args.steps, 4)},
                     "how": "per step: texture cache flushed, scene re-built and re-uploaded, environment map re-uploaded "
                            + ("(one slice per rank + NCCL all-gather over NVLink, double-buffered: step k + 1's copy goes up under step k's "
                               "kernels), rows copied by every rank into one shared pinned host image, barrier"

@@ -413,6 +413,21 @@ u32 sp_b200_Seed(u32 pixelIndex, u32 sample, u32 frame);
  * rows add up to sp_b200_Stats::kernelMs.  What sp_b200_PartitionRows cuts by.  Returns 0 on success. */
 int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels,
                        void *devicePixels, sp_Metrics *metrics, u64 *tileRowCost);
+/* The same call in two halves, so that a host which renders frame after frame (the reference's main
+ * loop, main.cpp:1529-1557) keeps the device busy across the frame boundary.  Begin enqueues the whole
+ * strip -- coverage pass, kernels, read-back of the counters, rows to the (pinned) host image band by
+ * band -- and returns without waiting; End waits for that frame and fills metrics, sp_b200_GetLastStats
+ * and tileRowCost (wantTileRowCost must have been set).  Up to TWO frames may be in flight: begin frame
+ * k + 1, then end frame k -- the host-side epilogue of k and prologue of k + 1 then run under k + 1's
+ * kernels, and the tail of k's row copies under them too.  Frames in flight must not share their
+ * destination: with devicePixels = NULL each has its own device image; a caller that passes devicePixels
+ * or hostPixels alternates between two of each.  The scene, camera and material system of ctx must stay
+ * as they are until End (a scene may be REBUILT with identical content in between: the device copy a frame
+ * in flight uses is kept until it ends).  Begin returns the frame's slot (0 or 1) for End, -1 if two
+ * frames are already in flight.  sp_b200_RenderRows = Begin + End. */
+int sp_b200_RenderRowsBegin(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels,
+                            void *devicePixels, int wantTileRowCost);
+int sp_b200_RenderRowsEnd(int slot, sp_Metrics *metrics, u64 *tileRowCost);
 /* All rows into ctx->camera->imagePlane->pixels (host). */
 int sp_b200_RenderFrame(sp_Context *ctx, u32 frame, sp_Metrics *metrics);
 /* Asset input (the step before the path; replaces LoadMesh, src/mesh.cpp:5-62, whose assimp

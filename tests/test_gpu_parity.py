@@ -650,6 +650,63 @@ def test_progressive_accumulation(gpu_sp):
     r.close()
 
 
+def test_pipelined_frames_begin_end(gpu_sp):
+    """sp_b200_RenderRowsBegin / End: two frames in flight (begin k + 1 before ending k) give the bits, metrics
+    and per-row cost totals of the same frames rendered one call at a time -- into pinned host images (rows
+    streamed band by band), into caller-owned device images, with the strip moved between frames (the cached
+    coverage no longer applies) and with the scene rebuilt in between; a third Begin is refused."""
+    import torch
+    sp = gpu_sp
+    wl = W.config1(320, 200, env_size=(256, 128))
+    r = sp.Renderer().load_workload(wl)
+    sp.set_params(samplesPerPixel=6, bounceCount=4, renderMode=0, tileHeight=8, tileWidth=64)
+    H, Wd = wl.height, wl.width
+    strips = [(0, H), (0, H), (40, 160), (40, 160), (0, 96), (0, H)]
+    want = []
+    for f, (b, e) in enumerate(strips):
+        r.image[...] = 0
+        m, cost = r.render_rows(b, e, frame=f, host=True, want_cost=True)
+        want.append((r.image.copy(), m, cost))
+    hosts = [torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    devs = [torch.zeros((H, Wd, 4), dtype=torch.float32, device="cuda:0") for _ in range(2)]
+    for mode in ("host", "device", "host_rebuild"):
+        got = [None] * len(strips)
+        slots = {}
+        def end(f):
+            m, cost = r.render_rows_end(slots.pop(f))
+            img = hosts[f % 2].numpy().copy() if mode != "device" else devs[f % 2].cpu().numpy()
+            got[f] = (img, m, cost)
+        for f, (b, e) in enumerate(strips):
+            if mode == "device":
+                devs[f % 2].zero_()
+                torch.cuda.synchronize()
+                slots[f] = r.render_rows_begin(b, e, frame=f, host=False, device_ptr=devs[f % 2].data_ptr(), want_cost=True)
+            else:
+                hosts[f % 2].zero_()
+                if mode == "host_rebuild" and f in (2, 5):
+                    r.build()
+                slots[f] = r.render_rows_begin(b, e, frame=f, host_ptr=hosts[f % 2].data_ptr(), want_cost=True)
+            if f == 1:
+                with pytest.raises(RuntimeError):
+                    r.render_rows_begin(b, e, frame=f, host_ptr=hosts[0].data_ptr())
+            if f >= 1:
+                end(f - 1)
+        end(len(strips) - 1)
+        for f, (img, m, cost) in enumerate(got):
+            assert same_bits(img, want[f][0]), (mode, f)
+            assert np.array_equal(m[1:5], want[f][1][1:5]), (mode, f)
+            assert cost.shape == want[f][2].shape and (cost > 0).sum() == (want[f][2] > 0).sum(), (mode, f)
+    # the one-call form still works with a frame in flight, and afterwards
+    s0 = r.render_rows_begin(0, H, frame=1, host_ptr=hosts[0].data_ptr())
+    r.image[...] = 0
+    m, _ = r.render_rows(0, H, frame=0, host=True)
+    assert same_bits(r.image, want[0][0])
+    r.render_rows_end(s0)
+    assert same_bits(hosts[0].numpy(), want[1][0])
+    sp.set_params(samplesPerPixel=1, bounceCount=3, tileHeight=64)
+    r.close()
+
+
 def test_reference_perf_test_queries(gpu_sp):
     """The queries of the reference's own performance tests (perf_tests/perf_tests.cpp:51-118 TestBvh,
     :212-305 TestMeshMidphase) with the reference's seeded inputs restated draw for draw

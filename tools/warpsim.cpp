@@ -36,6 +36,7 @@ struct Policy
     uint32_t earlyMinSteps = 0;   // ... once it has run this many iterations; survivors go to a second launch
     uint32_t secondThreshold = 1; // refill threshold of the second launch (continuations)
     uint32_t voteBias = 0;        // node step when nodeLanes + voteBias >= leafLanes
+    uint32_t doubleNode = 0;      // > 0: after a node step that nodeLanes * 32 >= doubleNode * walking lanes chose, a second one without a vote
 };
 
 struct Tally
@@ -118,6 +119,7 @@ struct Sim
     std::vector<Hit> results; // by ray id
     bool single;
     uint64_t enterIters = 0, enterLanes = 0, exitIters = 0, exitLanes = 0;
+    uint64_t spHist[97] = {}; // stack pointer after every node step
     Sim(const DScene &s, const Policy &pol, size_t rays) : S(s), p(pol), results(rays), single(s.objectCount == 1) {}
     bool finishedLane(const Lane &l) const { return l.have && l.pending == NONE && (l.st.cur == SPB_NODE_DONE || (single && l.st.cur == SPB_NODE_EXIT)); }
 
@@ -234,11 +236,24 @@ struct Sim
                         if (walking(l) && trav_is_walking(l.st) && trav_is_node(l.st))
                         {
                             trav_node<true>(S, l.st, l.stack, nullptr);
+                            spHist[l.st.sp < 96 ? l.st.sp : 96]++;
                             if (p.speculate) pops += park_leaves(l);
                         }
                     t.add(w.node, nodeLanes);
                     if (pops) t.add(w.pop, std::min(pops, nodeLanes));
                     t.nodeIters++; t.nodeLanes += nodeLanes; t.nodeSteps += nodeLanes;
+                    if (p.doubleNode && nodeLanes * 32 >= p.doubleNode * nwalk)
+                    {
+                        unsigned again = 0;
+                        for (auto &l : lanes)
+                            if (walking(l) && trav_is_walking(l.st) && trav_is_node(l.st))
+                            {
+                                trav_node<true>(S, l.st, l.stack, nullptr);
+                                again++;
+                            }
+                        if (again) { t.add(w.node + 4, again); t.nodeIters++; t.nodeLanes += again; t.nodeSteps += again; }
+                        else t.add(4, 32);
+                    }
                 }
                 else
                 {
@@ -315,6 +330,7 @@ struct Sim
 };
 
 // direction bin of k_shade_hit_tiles (spb_wavefront.cu direction_bin, 256 bins)
+unsigned g_binRes = 16;
 unsigned direction_bin(f3 d)
 {
     float n = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
@@ -326,11 +342,12 @@ unsigned direction_bin(f3 d)
         float fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
         u = fu; v = fv;
     }
-    int iu = (int)((u * 0.5f + 0.5f) * 16.0f), iv = (int)((v * 0.5f + 0.5f) * 16.0f);
-    unsigned qu = (unsigned)(iu < 0 ? 0 : (iu > 15 ? 15 : iu)), qv = (unsigned)(iv < 0 ? 0 : (iv > 15 ? 15 : iv));
-    qu = (qu | (qu << 2)) & 0x33u; qu = (qu | (qu << 1)) & 0x55u;
-    qv = (qv | (qv << 2)) & 0x33u; qv = (qv | (qv << 1)) & 0x55u;
-    return qu | (qv << 1);
+    const int R = (int)g_binRes;
+    int iu = (int)((u * 0.5f + 0.5f) * (float)R), iv = (int)((v * 0.5f + 0.5f) * (float)R);
+    unsigned qu = (unsigned)(iu < 0 ? 0 : (iu > R - 1 ? R - 1 : iu)), qv = (unsigned)(iv < 0 ? 0 : (iv > R - 1 ? R - 1 : iv));
+    // Morton interleave of two coordinates of up to 8 bits
+    auto spread = [](unsigned x) { x = (x | (x << 4)) & 0x0F0Fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u; return x; };
+    return spread(qu) | (spread(qv) << 1);
 }
 
 // the next ray of a hit (shade_hit_one without the BSDF terms)
@@ -365,6 +382,9 @@ extern "C" void warpsim_run(ora_Scene *s, uint32_t blockStep, uint32_t spp, uint
     pol.refillThreshold = policy[0]; pol.speculate = policy[1]; pol.earlyLanes = policy[2]; pol.earlyMinSteps = policy[3];
     pol.secondThreshold = policy[4]; pol.voteBias = policy[5];
     const uint32_t laterThreshold = policy[6];
+    g_binRes = policy[7] ? policy[7] : 16;
+    const uint32_t pixelMajor = policy[8];
+    pol.doubleNode = policy[9];
     Weights w;
     if (weights) { w.node = weights[0]; w.leaf = weights[1]; w.vote = weights[2]; w.begin = weights[3]; w.retire = weights[4]; w.pop = weights[5]; w.suspend = weights[6]; w.resume = weights[7]; w.perEntry = weights[8]; w.enter = weights[9]; w.exitStep = weights[10]; }
 
@@ -400,7 +420,8 @@ extern "C" void warpsim_run(ora_Scene *s, uint32_t blockStep, uint32_t spp, uint
                     if (bounce_ray(S, r, h, nr))
                     {
                         tile.push_back(nr);
-                        bins.push_back(direction_bin(nr.d));
+                        // pixelMajor: 0 = direction bin only; k = pixel group (l / k) above the direction bin
+                        bins.push_back(direction_bin(nr.d) + (pixelMajor ? (l / pixelMajor) * 65536u : 0u));
                     }
                 }
         // bin by direction, item order inside a bin; the tile's unused slots are holes
@@ -477,6 +498,14 @@ extern "C" void warpsim_run(ora_Scene *s, uint32_t blockStep, uint32_t spp, uint
         o[16] = (double)sim.enterIters; o[17] = (double)sim.enterLanes; o[18] = (double)sim.exitIters; o[19] = (double)sim.exitLanes;
         if (bounce == 1 && hist)
             for (int i = 0; i < 33; ++i) hist[i] = (double)first.walkHist[i];
+        if (getenv("WARPSIM_SP"))
+        {
+            double tot = 0, acc = 0;
+            for (int i = 0; i < 97; ++i) tot += (double)sim.spHist[i];
+            fprintf(stderr, "bounce %u: stack pointer after a node step, cumulative:", bounce);
+            for (int i = 0; i < 40; ++i) { acc += (double)sim.spHist[i]; fprintf(stderr, " %d:%.4f", i, acc / tot); }
+            fprintf(stderr, "\n");
+        }
         // next queue: the hits in retire order ~ slot order (k_shade_hit: slot for slot)
         std::vector<SimRay> nextq;
         for (size_t i = 0; i < queue.size(); ++i)

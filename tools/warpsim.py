@@ -28,9 +28,9 @@ def build():
                            os.path.join(CSRC, "spb_bvh.cpp"), "-lm"])
 
 
-KEYS = ["refill", "speculate", "early_lanes", "early_min_steps", "second_threshold", "vote_bias", "later_threshold"]
+KEYS = ["refill", "speculate", "early_lanes", "early_min_steps", "second_threshold", "vote_bias", "later_threshold", "bin_res", "pixel_major", "double_node"]
 DEFAULT = {"refill": 1, "speculate": 0, "early_lanes": 0, "early_min_steps": 0, "second_threshold": 1, "vote_bias": 0,
-           "later_threshold": 12}
+           "later_threshold": 12, "bin_res": 16, "pixel_major": 0, "double_node": 0}
 
 
 def run(scene, lib, policy, block_step, spp, bounces, weights=None, sort_later=0):

@@ -67,20 +67,63 @@ struct DeviceBuffer
 {
     void *ptr = nullptr;
     size_t bytes = 0;
+    // Stream-ordered form (the arrays of a scene): allocated on `allocStream` from the device's memory pool and
+    // freed in the order of `freeStream` -- behind whatever frames in flight still read them -- instead of
+    // with cudaMalloc / cudaFree, which wait for the whole device (sp_BuildSceneBroadphase between
+    // sp_b200_RenderRowsBegin and End must not stall the frame in flight).
+    const cudaStream_t *freeStream = nullptr; // (the owner's render stream variable: read when the buffer is freed)
+    bool pooled = false;
     void ensure(size_t need)
     {
         if (need <= bytes) return;
-        if (ptr) SPB_CUDA(cudaFree(ptr));
+        release();
         size_t grow = need + need / 4;
         SPB_CUDA(cudaMalloc(&ptr, grow));
         bytes = grow;
     }
+    void ensure_pooled(size_t need, cudaStream_t allocStream, const cudaStream_t *freeOn)
+    {
+        release();
+        SPB_CUDA(cudaMallocAsync(&ptr, need, allocStream));
+        bytes = need;
+        pooled = true;
+        freeStream = freeOn;
+    }
     void release()
     {
-        if (ptr) cudaFree(ptr);
+        if (ptr)
+        {
+            if (pooled) cudaFreeAsync(ptr, *freeStream);
+            else cudaFree(ptr);
+        }
         ptr = nullptr;
         bytes = 0;
+        pooled = false;
     }
+};
+
+// What ONE frame in flight owns (sp_b200_RenderRowsBegin / End keep up to two): the events its launches
+// are bracketed with, the pinned words its counters come back to, its device image.  Everything else a
+// frame uses -- the wavefront working set, the device-side counters -- is shared: frames run one after
+// the other on the render stream, and a frame's counters are copied out (in stream order) before the
+// next frame's memset clears them.
+struct FrameState
+{
+    cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
+    cudaEvent_t evRowsReady = nullptr, evCopyDone = nullptr;
+    cudaEvent_t evSky0 = nullptr, evSky1 = nullptr; // around the sky kernels of a wavefront frame
+    bool skyTimed = false;
+    // CUDA events around every k_trace launch of the frame (sp_b200_Stats::traceMs)
+    std::vector<cudaEvent_t> traceEvents;
+    size_t traceEventsUsed = 0;
+    uint32_t *coveredPinned = nullptr; // pinned words the asynchronous read-back of the coverage pass lands in
+    bool coverSpeculated = false;      // render_wavefront ran on the cached covered-block count
+    DeviceBuffer image;
+    // pinned landing zones of the frame's counters (device counters + per-tile-row cost; wave counters)
+    unsigned long long *hostCounters = nullptr;
+    uint32_t *hostWave = nullptr;
+    size_t hostCountersCap = 0, hostWaveCap = 0; // elements
+    bool pending = false;              // begun, not ended
 };
 
 struct DeviceScene
@@ -144,9 +187,8 @@ struct Library
         std::vector<Probe> probes;
         std::vector<cudaEvent_t> pool;
     } tuner;
-    // CUDA events around every k_trace launch of the last wavefront frame (sp_b200_Stats::traceMs)
-    std::vector<cudaEvent_t> traceEvents;
-    size_t traceEventsUsed = 0;
+    FrameState frames[2];
+    FrameState *f = &frames[0]; // the frame the entry point at hand works on
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
     std::map<void *, std::unique_ptr<DeviceScene>> scenes;
@@ -158,32 +200,32 @@ struct Library
     // flush forgets contents, not memory: cudaMalloc/cudaFree of 128 MiB per frame is slow)
     std::vector<std::unique_ptr<TextureEntry>> texturePool;
     std::unique_ptr<DeviceScene> emptyScene;
-    DeviceBuffer image, counters, materials, scratchA, scratchB, scratchC;
+    DeviceBuffer counters, materials, scratchA, scratchB, scratchC;
     // wavefront working set (DESIGN.md "Data layout")
     DeviceBuffer wRays[2], wHitRec, wHitQ, wMissQ, wTerms, wRad, wCtr, wMask, wBlockList, wStage, wCand, wSkyList, wCont;
-    cudaEvent_t evStart = nullptr, evKernel0 = nullptr, evKernel1 = nullptr, evEnd = nullptr;
     // Copy engine side of a frame (DESIGN.md "End to end"): texture uploads run on copyStream and
     // the render stream waits for them only where the first kernel that reads a texture is
     // launched; finished rows go back to a pinned host image band by band on the same stream
     // while later bands render.
     cudaStream_t copyStream = nullptr;
-    cudaEvent_t evTextures = nullptr, evRowsReady = nullptr, evCopyDone = nullptr, evOrder = nullptr;
-    cudaEvent_t evSky0 = nullptr, evSky1 = nullptr; // around the sky kernels of a wavefront frame
-    bool skyTimed = false;
+    cudaStream_t uploadStream = nullptr; // scene uploads (upload_scene)
+    cudaEvent_t evScene = nullptr;
+    cudaEvent_t evTextures = nullptr, evOrder = nullptr;
     // Covered-block count of the last wavefront strip, keyed by everything the coverage pass depends
     // on: the next frame of the same strip is launched on that number without waiting for its own
     // coverage pass, and checked against it afterwards (render_wavefront).
     struct CoverCache
     {
         bool valid = false;
-        const void *nodes = nullptr;
         uint64_t triangles = 0;
+        uint32_t objects = 0;
         DCamera camera;
-        uint32_t y0 = 0, y1 = 0, covered = 0;
+        uint32_t y0 = 0, y1 = 0, covered = 0, listHash = 0;
         bool skyCulling = true;
+        // what the host derives from the list for the row copies: first block, last block of every band
+        uint32_t firstBlock = 0, bandBlocks = 0;
+        std::vector<uint32_t> bandLast;
     } coverCache;
-    uint32_t *coveredPinned = nullptr; // pinned word the asynchronous read-back lands in
-    bool coverSpeculated = false; // the last render_wavefront ran on the cached count
     bool texturesPending = false; // an upload was issued on copyStream and nobody waited for it yet
     std::vector<cudaEvent_t> externalReady; // events of sp_b200_SetDeviceTexture copies nobody waited for yet
     bool overlapCopies = true;    // sp_b200_SetCopyOverlap
@@ -330,18 +372,39 @@ void ensure_init()
         log_message("libspb200: L2 fetch granularity %zu -> %zu (%s)", before, after, cudaGetErrorString(e));
         cudaGetLastError();
     }
-    SPB_CUDA(cudaEventCreate(&L.evStart));
-    SPB_CUDA(cudaEventCreate(&L.evKernel0));
-    SPB_CUDA(cudaEventCreate(&L.evKernel1));
-    SPB_CUDA(cudaEventCreate(&L.evEnd));
     SPB_CUDA(cudaStreamCreateWithFlags(&L.copyStream, cudaStreamNonBlocking));
+    SPB_CUDA(cudaStreamCreateWithFlags(&L.uploadStream, cudaStreamNonBlocking));
+    SPB_CUDA(cudaEventCreateWithFlags(&L.evScene, cudaEventDisableTiming));
+    {
+        // the pool keeps what scenes free (a rebuild per frame is the reference's own pattern, main.cpp:1545-1552)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, L.device) == cudaSuccess)
+        {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     SPB_CUDA(cudaEventCreateWithFlags(&L.evTextures, cudaEventDisableTiming));
-    SPB_CUDA(cudaEventCreateWithFlags(&L.evRowsReady, cudaEventDisableTiming));
-    SPB_CUDA(cudaEventCreateWithFlags(&L.evCopyDone, cudaEventDisableTiming));
     SPB_CUDA(cudaEventCreateWithFlags(&L.evOrder, cudaEventDisableTiming));
-    SPB_CUDA(cudaEventCreate(&L.evSky0));
-    SPB_CUDA(cudaEventCreate(&L.evSky1));
-    SPB_CUDA(cudaHostAlloc((void **)&L.coveredPinned, 64, cudaHostAllocDefault));
+    for (FrameState &F : L.frames)
+    {
+        SPB_CUDA(cudaEventCreate(&F.evStart));
+        SPB_CUDA(cudaEventCreate(&F.evKernel0));
+        SPB_CUDA(cudaEventCreate(&F.evKernel1));
+        SPB_CUDA(cudaEventCreate(&F.evEnd));
+        SPB_CUDA(cudaEventCreateWithFlags(&F.evRowsReady, cudaEventDisableTiming));
+        SPB_CUDA(cudaEventCreate(&F.evCopyDone));
+        SPB_CUDA(cudaEventCreate(&F.evSky0));
+        SPB_CUDA(cudaEventCreate(&F.evSky1));
+        SPB_CUDA(cudaHostAlloc((void **)&F.coveredPinned, 64, cudaHostAllocDefault));
+        F.hostCountersCap = 8192;
+        F.hostWaveCap = 16384;
+        SPB_CUDA(cudaHostAlloc((void **)&F.hostCounters, F.hostCountersCap * 8, cudaHostAllocDefault));
+        SPB_CUDA(cudaHostAlloc((void **)&F.hostWave, F.hostWaveCap * 4, cudaHostAllocDefault));
+        F.pending = false;
+    }
+    L.f = &L.frames[0];
     L.initialized = true;
 }
 
@@ -363,22 +426,35 @@ void upload(DeviceBuffer &dst, const std::vector<T> &src, cudaStream_t stream)
     dst.ensure(bytes ? bytes : 16);
     if (bytes) SPB_CUDA(cudaMemcpyAsync(dst.ptr, src.data(), bytes, cudaMemcpyHostToDevice, stream));
 }
+// (a scene's array: pool memory, allocated and filled on the upload stream, freed in render-stream order)
+template <class T>
+void upload_pooled(DeviceBuffer &dst, const std::vector<T> &src, cudaStream_t uploadStream, const cudaStream_t *renderStream)
+{
+    size_t bytes = src.size() * sizeof(T);
+    dst.ensure_pooled(bytes ? bytes : 16, uploadStream, renderStream);
+    if (bytes) SPB_CUDA(cudaMemcpyAsync(dst.ptr, src.data(), bytes, cudaMemcpyHostToDevice, uploadStream));
+}
 
 std::unique_ptr<DeviceScene> upload_scene(const FlatScene &fs)
 {
     Library &L = lib();
     auto ds = std::make_unique<DeviceScene>();
-    upload(ds->nodes, fs.nodes, L.stream);
-    upload(ds->tris, fs.tris, L.stream);
-    upload(ds->shade, fs.shade, L.stream);
-    upload(ds->objInv, fs.objInv, L.stream);
-    upload(ds->objModel, fs.objModel, L.stream);
-    upload(ds->objInfo, fs.objInfo, L.stream);
+    // On the upload stream, which nothing else uses: a copy from pageable memory first waits for the stream it is
+    // issued on, and the render stream may hold a frame in flight (sp_b200_RenderRowsBegin).  The copies have left
+    // the host arrays when the calls return (staged); the render stream waits for their arrival on the device.
+    upload_pooled(ds->nodes, fs.nodes, L.uploadStream, &L.stream);
+    upload_pooled(ds->tris, fs.tris, L.uploadStream, &L.stream);
+    upload_pooled(ds->shade, fs.shade, L.uploadStream, &L.stream);
+    upload_pooled(ds->objInv, fs.objInv, L.uploadStream, &L.stream);
+    upload_pooled(ds->objModel, fs.objModel, L.uploadStream, &L.stream);
+    upload_pooled(ds->objInfo, fs.objInfo, L.uploadStream, &L.stream);
     std::vector<uint32_t> objTris = fs.objTris;
     if (objTris.empty()) objTris.push_back(0);
-    upload(ds->objTris, objTris, L.stream);
-    upload(ds->objBox, fs.objBox, L.stream);
-    SPB_CUDA(cudaStreamSynchronize(L.stream));
+    upload_pooled(ds->objTris, objTris, L.uploadStream, &L.stream);
+    upload_pooled(ds->objBox, fs.objBox, L.uploadStream, &L.stream);
+    SPB_CUDA(cudaEventRecord(L.evScene, L.uploadStream));
+    SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evScene, 0));
+    SPB_CUDA(cudaStreamWaitEvent(L.copyStream, L.evScene, 0));
     ds->d.nodes = (const v4f *)ds->nodes.ptr;
     ds->d.tris = (const v4f *)ds->tris.ptr;
     ds->d.shade = (const v4f *)ds->shade.ptr;
@@ -639,7 +715,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     const uint32_t blocksX = (width + 7) / 8, blocksY = (height + 3) / 4;
     const uint32_t blocks = blocksX * blocksY;
     // (statistics of this frame only, whatever path it takes below)
-    L.traceEventsUsed = 0;
+    L.f->traceEventsUsed = 0;
     L.tuner.probes.clear();
     countersOut.clear();
 
@@ -668,7 +744,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     // (sized for the whole image: a strip that grows at the next re-cut must not reallocate)
     const size_t imageBlocks = (size_t)blocksX * ((ra.camera.height + 3) / 4 + 1);
     L.wMask.ensure((imageBlocks > blocks ? imageBlocks : blocks) + 1);
-    L.wBlockList.ensure((imageBlocks > blocks ? imageBlocks : blocks) * 4 + 4);
+    L.wBlockList.ensure((imageBlocks > blocks ? imageBlocks : blocks) * 4 + 8);
     uint32_t *listCount = (uint32_t *)L.wBlockList.ptr + blocks;
     a.blockMask = (const uint8_t *)L.wMask.ptr;
     launch_coverage(a, instancedTriangles, !L.skyCulling, (uint8_t *)L.wMask.ptr, (uint32_t *)L.wBlockList.ptr,
@@ -705,32 +781,39 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     // launched on the cached count at once (no host wait in the middle of the frame: at 8 ms per
     // strip the round trip is 1 % of a GPU left idle) while the fresh count goes to a pinned word;
     // the caller compares the two when the frame is done and renders again, waiting this time, in the
-    // case nobody has produced yet that they differ (`coverMismatch`).
+    // case nobody has produced yet that they differ.  The key is what the coverage depends on as far as
+    // the host can see cheaply (triangle and object counts, camera, rows): a scene rebuilt with the same
+    // content keeps the cache, one whose triangles moved is caught by the comparison -- of the count and of
+    // a fingerprint of the block list (k_list_blocks).
     Library::CoverCache &cc = L.coverCache;
-    const bool sameCover = cc.valid && allowCached && cc.nodes == (const void *)ra.scene.nodes && cc.triangles == instancedTriangles &&
+    const bool sameCover = cc.valid && allowCached && cc.triangles == instancedTriangles && cc.objects == ra.scene.objectCount &&
                            cc.y0 == ra.y0 && cc.y1 == ra.y1 && cc.skyCulling == L.skyCulling &&
                            memcmp(&cc.camera, &ra.camera, sizeof(DCamera)) == 0;
     uint32_t covered = 0;
-    L.coveredPinned[0] = 0xFFFFFFFFu;
-    SPB_CUDA(cudaMemcpyAsync(L.coveredPinned, listCount, 4, cudaMemcpyDeviceToHost, L.stream));
+    L.f->coveredPinned[0] = 0xFFFFFFFFu;
+    L.f->coveredPinned[1] = 0xFFFFFFFFu;
+    SPB_CUDA(cudaMemcpyAsync(L.f->coveredPinned, listCount, 8, cudaMemcpyDeviceToHost, L.stream));
     if (sameCover)
     {
         covered = cc.covered;
-        L.coverSpeculated = true;
+        L.f->coverSpeculated = true;
     }
     else
     {
         SPB_CUDA(cudaStreamSynchronize(L.stream));
-        covered = L.coveredPinned[0];
-        L.coverSpeculated = false;
+        covered = L.f->coveredPinned[0];
+        L.f->coverSpeculated = false;
         cc.valid = true;
-        cc.nodes = (const void *)ra.scene.nodes;
         cc.triangles = instancedTriangles;
+        cc.objects = ra.scene.objectCount;
         cc.camera = ra.camera;
         cc.y0 = ra.y0;
         cc.y1 = ra.y1;
         cc.covered = covered;
+        cc.listHash = L.f->coveredPinned[1];
         cc.skyCulling = L.skyCulling;
+        cc.bandLast.clear();
+        cc.bandBlocks = 0;
     }
 
     // rows -> host, band by band, on the copy stream (pinned destinations only: a pageable one
@@ -745,21 +828,21 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     // rows [rowBegin, rowEnd) are final once everything launched on the render stream so far is done
     auto copy_rows = [&](uint32_t rowBegin, uint32_t rowEnd) {
         if (!streamRows || rowEnd <= rowBegin) return;
-        SPB_CUDA(cudaEventRecord(L.evRowsReady, L.stream));
-        SPB_CUDA(cudaStreamWaitEvent(L.copyStream, L.evRowsReady, 0));
+        SPB_CUDA(cudaEventRecord(L.f->evRowsReady, L.stream));
+        SPB_CUDA(cudaStreamWaitEvent(L.copyStream, L.f->evRowsReady, 0));
         const size_t offset = (size_t)rowBegin * ra.camera.width;
         SPB_CUDA(cudaMemcpyAsync(hostOut + offset * 4, ra.out + offset, (size_t)(rowEnd - rowBegin) * ra.camera.width * 16,
                                  cudaMemcpyDeviceToHost, L.copyStream));
-        SPB_CUDA(cudaEventRecord(L.evCopyDone, L.copyStream));
+        SPB_CUDA(cudaEventRecord(L.f->evCopyDone, L.copyStream));
     };
     uint32_t rowsCopied = ra.y0, rowsBottom = ra.y1; // rows outside [rowsCopied, rowsBottom) are on their way
     auto launch_sky_kernels = [&]() {
         wait_textures();
-        SPB_CUDA(cudaEventRecord(L.evSky0, L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->evSky0, L.stream));
         launch_sky(cfg, a, L.stream);
         if (a.skyList) launch_sky_listed(cfg, a, L.stream);
-        SPB_CUDA(cudaEventRecord(L.evSky1, L.stream));
-        L.skyTimed = true;
+        SPB_CUDA(cudaEventRecord(L.f->evSky1, L.stream));
+        L.f->skyTimed = true;
     };
     if (covered == 0)
     {
@@ -784,7 +867,13 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     // final once the band is done.  One more small read-back, the stream is idle anyway.
     std::vector<uint32_t> bandLast(bands, 0);
     uint32_t firstBlock = 0;
-    if (streamRows)
+    if (streamRows && L.f->coverSpeculated && cc.bandBlocks == bandBlocks && cc.bandLast.size() == bands)
+    {
+        // (the list this frame will find is the one these were read from: its fingerprint is checked with the count)
+        bandLast = cc.bandLast;
+        firstBlock = cc.firstBlock;
+    }
+    else if (streamRows)
     {
         const uint32_t *list = (const uint32_t *)L.wBlockList.ptr;
         SPB_CUDA(cudaMemcpyAsync(&firstBlock, list, 4, cudaMemcpyDeviceToHost, L.stream));
@@ -794,6 +883,17 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             SPB_CUDA(cudaMemcpyAsync(&bandLast[b], list + last, 4, cudaMemcpyDeviceToHost, L.stream));
         }
         SPB_CUDA(cudaStreamSynchronize(L.stream));
+        if (L.f->coverSpeculated && (L.f->coveredPinned[0] != cc.covered || L.f->coveredPinned[1] != cc.listHash))
+        {
+            // (the stream has just been waited for: the fresh count is here already and differs from the cached one)
+            cc.valid = false;
+        }
+        else
+        {
+            cc.bandLast = bandLast;
+            cc.firstBlock = firstBlock;
+            cc.bandBlocks = bandBlocks;
+        }
     }
     SPB_ASSERT(32ull * bandBlocks * S < 0xFFFFFFFFull - SPB_QUEUE_SLACK);
     const uint32_t capacity = 32u * bandBlocks * S; // ray slots and path ids both fit
@@ -869,14 +969,14 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     }
 
     auto timed_trace = [&](uint32_t bounce, bool primary, uint32_t evictBelow = 0) {
-        if (L.traceEventsUsed + 2 > L.traceEvents.size())
+        if (L.f->traceEventsUsed + 2 > L.f->traceEvents.size())
             for (int k = 0; k < 64; ++k)
             {
                 cudaEvent_t e;
                 SPB_CUDA(cudaEventCreate(&e));
-                L.traceEvents.push_back(e);
+                L.f->traceEvents.push_back(e);
             }
-        SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->traceEvents[L.f->traceEventsUsed++], L.stream));
         if (evictBelow && !primary)
         {
             // the packets' stragglers are parked (EVICT), then walked on together (RESUME)
@@ -888,7 +988,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             a.refillThreshold = keep;
         }
         else launch_wave_trace(cfg, a, bounce, primary ? SPB_TRACE_PRIMARY : SPB_TRACE_QUEUE, L.stream);
-        SPB_CUDA(cudaEventRecord(L.traceEvents[L.traceEventsUsed++], L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->traceEvents[L.f->traceEventsUsed++], L.stream));
     };
 
     uint32_t *ctr = (uint32_t *)L.wCtr.ptr;
@@ -1018,29 +1118,42 @@ void shutdown_library(Library &L)
     L.textures.clear();
     L.texturePool.clear();
     L.emptyScene.reset();
-    L.image.release(); L.counters.release(); L.materials.release();
+    for (FrameState &F : L.frames) F.image.release();
+    L.counters.release(); L.materials.release();
     L.scratchA.release(); L.scratchB.release(); L.scratchC.release();
     L.wRays[0].release(); L.wRays[1].release(); L.wHitRec.release();
     L.wHitQ.release(); L.wMissQ.release(); L.wTerms.release(); L.wRad.release(); L.wCtr.release();
     L.wMask.release(); L.wBlockList.release(); L.wStage.release(); L.wCand.release(); L.wSkyList.release(); L.wCont.release();
-    for (cudaEvent_t e : L.traceEvents) cudaEventDestroy(e);
-    L.traceEvents.clear();
-    L.traceEventsUsed = 0;
+    for (FrameState &F : L.frames)
+    {
+        for (cudaEvent_t e : F.traceEvents) cudaEventDestroy(e);
+        F.traceEvents.clear();
+        F.traceEventsUsed = 0;
+    }
     for (cudaEvent_t e : L.tuner.pool) cudaEventDestroy(e);
     L.tuner.pool.clear();
     L.tuner.probes.clear();
     L.tuner.signature = 0;
     if (L.initialized)
     {
-        cudaEventDestroy(L.evStart); cudaEventDestroy(L.evKernel0);
-        cudaEventDestroy(L.evKernel1); cudaEventDestroy(L.evEnd);
-        cudaEventDestroy(L.evTextures); cudaEventDestroy(L.evRowsReady); cudaEventDestroy(L.evCopyDone); cudaEventDestroy(L.evOrder);
-        cudaEventDestroy(L.evSky0); cudaEventDestroy(L.evSky1);
-        cudaFreeHost(L.coveredPinned);
-        L.coveredPinned = nullptr;
+        for (FrameState &F : L.frames)
+        {
+            cudaEventDestroy(F.evStart); cudaEventDestroy(F.evKernel0);
+            cudaEventDestroy(F.evKernel1); cudaEventDestroy(F.evEnd);
+            cudaEventDestroy(F.evRowsReady); cudaEventDestroy(F.evCopyDone);
+            cudaEventDestroy(F.evSky0); cudaEventDestroy(F.evSky1);
+            cudaFreeHost(F.coveredPinned); cudaFreeHost(F.hostCounters); cudaFreeHost(F.hostWave);
+            F.coveredPinned = nullptr; F.hostCounters = nullptr; F.hostWave = nullptr;
+            F.pending = false;
+        }
+        cudaEventDestroy(L.evTextures); cudaEventDestroy(L.evOrder);
         L.coverCache.valid = false;
         cudaStreamDestroy(L.copyStream);
         L.copyStream = nullptr;
+        cudaStreamDestroy(L.uploadStream);
+        L.uploadStream = nullptr;
+        cudaEventDestroy(L.evScene);
+        L.evScene = nullptr;
     }
     L.texturesPending = false;
     L.initialized = false;
@@ -1512,7 +1625,7 @@ extern "C" void sp_BuildSceneBroadphase(sp_Scene *scene)
     // rebuilds per render, main.cpp:1545-1552)
     if (scene->broadphaseTree.root && L.scenes.count(scene->broadphaseTree.root))
     {
-        if (L.initialized) cudaDeviceSynchronize();
+        // (no wait: the old arrays are freed in render-stream order, behind the frames that still read them)
         L.scenes.erase(scene->broadphaseTree.root);
         forget_scene_on_devices(scene->broadphaseTree.root);
     }
@@ -1576,23 +1689,23 @@ extern "C" int sp_b200_RayIntersectSceneBatch(sp_Scene *scene, u32 count, const 
     L.scratchB.ensure(rayBytes);
     L.scratchC.ensure((size_t)count * sizeof(HitRecord));
     unsigned long long *ctr = reset_counters();
-    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evStart, L.stream));
     SPB_CUDA(cudaMemcpyAsync(L.scratchA.ptr, rayOrigins, rayBytes, cudaMemcpyHostToDevice, L.stream));
     SPB_CUDA(cudaMemcpyAsync(L.scratchB.ptr, rayDirections, rayBytes, cudaMemcpyHostToDevice, L.stream));
-    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel0, L.stream));
     launch_intersect_batch(kernel_config(), launch_scene(ds), count, (const float *)L.scratchA.ptr,
                            (const float *)L.scratchB.ptr, (HitRecord *)L.scratchC.ptr, ctr, L.stream);
     SPB_CUDA(cudaGetLastError());
-    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel1, L.stream));
     std::vector<HitRecord> host(count);
     unsigned long long c[CTR_COUNT];
     SPB_CUDA(cudaMemcpyAsync(host.data(), L.scratchC.ptr, (size_t)count * sizeof(HitRecord), cudaMemcpyDeviceToHost, L.stream));
     SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
-    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evEnd, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float kernelMs = 0, totalMs = 0;
-    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
-    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.f->evKernel0, L.f->evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.f->evStart, L.f->evEnd));
     for (u32 i = 0; i < count; ++i)
     {
         if (results)
@@ -1728,14 +1841,14 @@ static int mesh_batch(sp_Mesh mesh, u32 count, const vec3 *origins, const vec3 *
     char *in = (char *)L.scratchA.ptr;
     SPB_CUDA(cudaMemcpyAsync(in, origins, vecBytes, cudaMemcpyHostToDevice, L.stream));
     SPB_CUDA(cudaMemcpyAsync(in + vecBytes, dirs, vecBytes, cudaMemcpyHostToDevice, L.stream));
-    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel0, L.stream));
     if (what == 0)
         launch_collect_leaves_batch(launch_scene(ds), count, (const float *)in, (const float *)(in + vecBytes), (uint32_t *)L.scratchB.ptr, L.stream);
     else
         launch_intersect_mesh_batch(kernel_config(), launch_scene(ds), count, (const float *)in, (const float *)(in + vecBytes),
                                     (float *)L.scratchB.ptr, (int32_t *)((float *)L.scratchB.ptr + count), L.stream);
     SPB_CUDA(cudaGetLastError());
-    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel1, L.stream));
     if (what == 0)
         SPB_CUDA(cudaMemcpyAsync(leafOut3, L.scratchB.ptr, (size_t)count * 12, cudaMemcpyDeviceToHost, L.stream));
     else
@@ -1745,7 +1858,7 @@ static int mesh_batch(sp_Mesh mesh, u32 count, const vec3 *origins, const vec3 *
     }
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float ms = 0.0f;
-    SPB_CUDA(cudaEventElapsedTime(&ms, L.evKernel0, L.evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&ms, L.f->evKernel0, L.f->evKernel1));
     if (kernelMs) *kernelMs = ms;
     return 0;
 }
@@ -2008,17 +2121,44 @@ extern "C" void *WorkQueuePop(WorkQueue *queue, u32 objectSize)
 // =============================================================================================
 // rendering
 
-extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame,
-                                  f32 *hostPixels, void *devicePixels, sp_Metrics *metrics,
-                                  u64 *tileRowCost)
+// What sp_b200_RenderRowsBegin leaves for sp_b200_RenderRowsEnd (one per FrameState).
+struct PendingFrame
+{
+    RenderArgs args;
+    DCamera cam;
+    u32 rowBegin = 0, rowEnd = 0, tileRows = 0, spp = 0;
+    bool wavefront = false, rowsStreamed = false, wantCost = false, pinnedCounters = false;
+    uint64_t instancedTriangles = 0;
+    f32 *hostPixels = nullptr;
+    v4f *image = nullptr;
+    unsigned long long *ctr = nullptr; // device counters of the frame
+    size_t cCount = 0, waveCount = 0;
+    std::vector<unsigned long long> c; // (only when the counters do not fit the pinned landing zone)
+    std::vector<uint32_t> waveCounters;
+};
+static PendingFrame &pending_of(Library &L, FrameState *F)
+{
+    static thread_local std::map<FrameState *, PendingFrame> table; // (a Library is only ever driven by one thread at a time)
+    (void)L;
+    return table[F];
+}
+
+// Enqueues everything a strip needs -- coverage pass, kernels, read-back of the counters, rows to the
+// host -- on the render / copy streams and returns without waiting for the device.
+static int render_rows_begin(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame, f32 *hostPixels, void *devicePixels,
+                             bool wantCost, FrameState *F)
 {
     Library &L = lib();
-    std::lock_guard<std::recursive_mutex> lock(L.mutex);
-    ensure_init();
+    L.f = F;
     SPB_ASSERT(ctx && ctx->camera && ctx->camera->imagePlane);
+    PendingFrame &P = pending_of(L, F);
     DCamera cam;
     convert_camera(ctx->camera, &cam);
     if (rowEnd > cam.height) rowEnd = cam.height;
+    P.rowBegin = rowBegin;
+    P.rowEnd = rowEnd;
+    P.cam = cam;
+    P.tileRows = 0;
     if (rowBegin >= rowEnd || cam.width == 0) return 0;
     DeviceScene *ds = find_scene(ctx->scene);
 
@@ -2026,8 +2166,8 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     v4f *image = (v4f *)devicePixels;
     if (!image)
     {
-        L.image.ensure(imageBytes);
-        image = (v4f *)L.image.ptr;
+        F->image.ensure(imageBytes);
+        image = (v4f *)F->image.ptr;
     }
     u32 tileH = L.params.tileHeight;
     u32 firstTileRow = rowBegin / tileH;
@@ -2037,14 +2177,14 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     // with the per-pixel kernel, whose walk carries the padded box tests that option needs)
     const bool wavefront = L.params.renderMode != SP_B200_RENDER_PER_PIXEL &&
                            L.params.triangleTest == SP_B200_TRIANGLE_MOLLER_TRUMBORE;
-    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    SPB_CUDA(cudaEventRecord(F->evStart, L.stream));
     // (the wavefront path waits for texture uploads where its first texture-reading kernel starts)
     const DMaterials *dm = upload_materials(ctx->materialSystem, nullptr, wavefront);
     // two cost classes per tile row (queue kernels, sky kernels): 2 x tileRows slots behind the counters
     unsigned long long *ctr = reset_counters((size_t)tileRows * 2);
-    L.skyTimed = false;
+    F->skyTimed = false;
 
-    RenderArgs args;
+    RenderArgs &args = P.args;
     args.scene = launch_scene(ds);
     args.materials = dm;
     args.camera = cam;
@@ -2058,70 +2198,115 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     args.clampValue = L.params.radianceClamp;
     args.out = image;
     args.counters = ctr;
-    args.tileRowCost = tileRowCost ? ctr + CTR_COUNT : nullptr;
+    args.tileRowCost = wantCost ? ctr + CTR_COUNT : nullptr;
     args.tileHeight = tileH;
     // the kernel tiles the rectangle from y0 in 16-row CTAs; keep CTA rows inside one tile row
     // by starting at a multiple of 4 (tileHeight % 4 == 0 is enforced by sp_b200_SetParams)
-    SPB_ASSERT(rowBegin % 4 == 0 || tileRowCost == nullptr);
+    SPB_ASSERT(rowBegin % 4 == 0 || !wantCost);
 
-    std::vector<unsigned long long> c(CTR_COUNT + (size_t)tileRows * 2);
-    std::vector<uint32_t> waveCounters;
-    bool rowsStreamed = false;
-    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    P.tileRows = tileRows;
+    P.spp = L.params.samplesPerPixel;
+    P.wavefront = wavefront;
+    P.wantCost = wantCost;
+    P.instancedTriangles = ds->instancedTriangles;
+    P.hostPixels = hostPixels;
+    P.image = image;
+    P.ctr = ctr;
+    P.cCount = CTR_COUNT + (size_t)tileRows * 2;
+    P.waveCounters.clear();
+    SPB_CUDA(cudaEventRecord(F->evKernel0, L.stream));
     if (!wavefront)
         launch_render(kernel_config(), args, L.stream);
     else
-        rowsStreamed = render_wavefront(args, ds->instancedTriangles, waveCounters, hostPixels);
+        P.rowsStreamed = render_wavefront(args, ds->instancedTriangles, P.waveCounters, hostPixels);
+    if (!wavefront) P.rowsStreamed = false;
     SPB_CUDA(cudaGetLastError());
-    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    SPB_CUDA(cudaEventRecord(F->evKernel1, L.stream));
 
-    SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
-    if (!waveCounters.empty())
-        SPB_CUDA(cudaMemcpyAsync(waveCounters.data(), L.wCtr.ptr, waveCounters.size() * 4,
+    // counters -> host: pinned landing zones (an asynchronous copy to pageable memory would make this call
+    // wait for the whole frame), vectors only when a frame has more counters than the zones hold
+    P.waveCount = P.waveCounters.size();
+    P.pinnedCounters = P.cCount <= F->hostCountersCap && P.waveCount <= F->hostWaveCap;
+    if (!P.pinnedCounters) P.c.resize(P.cCount);
+    SPB_CUDA(cudaMemcpyAsync(P.pinnedCounters ? F->hostCounters : P.c.data(), ctr, P.cCount * 8, cudaMemcpyDeviceToHost, L.stream));
+    if (P.waveCount)
+        SPB_CUDA(cudaMemcpyAsync(P.pinnedCounters ? F->hostWave : P.waveCounters.data(), L.wCtr.ptr, P.waveCount * 4,
                                  cudaMemcpyDeviceToHost, L.stream));
-    if (hostPixels && !rowsStreamed)
+    if (hostPixels && !P.rowsStreamed)
     {
         size_t offset = (size_t)rowBegin * cam.width;
         SPB_CUDA(cudaMemcpyAsync(hostPixels + offset * 4, image + offset,
                                  (size_t)(rowEnd - rowBegin) * cam.width * 16,
                                  cudaMemcpyDeviceToHost, L.stream));
     }
-    // (rows that went out on the copy stream: the frame ends when the last of them has landed)
-    if (rowsStreamed) SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evCopyDone, 0));
-    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
-    SPB_CUDA(cudaStreamSynchronize(L.stream));
-    if (wavefront && L.coverSpeculated && L.coveredPinned[0] != L.coverCache.covered)
+    // (rows that went out on the copy stream: the render stream does NOT wait for them -- the next frame's
+    // kernels may start under the tail of this frame's copies; sp_b200_RenderRowsEnd waits for both)
+    SPB_CUDA(cudaEventRecord(F->evEnd, L.stream));
+    F->pending = true;
+    return 0;
+}
+
+// Waits for a frame begun above and turns its counters into metrics, statistics and per-row cost.
+static int render_rows_end(FrameState *F, sp_Metrics *metrics, u64 *tileRowCost)
+{
+    Library &L = lib();
+    L.f = F;
+    PendingFrame &P = pending_of(L, F);
+    F->pending = false;
+    if (P.tileRows == 0) return 0; // (an empty strip)
+    const bool wavefront = P.wavefront;
+    const DCamera &cam = P.cam;
+    const u32 rowBegin = P.rowBegin, rowEnd = P.rowEnd, tileRows = P.tileRows;
+    SPB_CUDA(cudaEventSynchronize(F->evEnd));
+    if (P.rowsStreamed) SPB_CUDA(cudaEventSynchronize(F->evCopyDone));
+    if (wavefront && F->coverSpeculated && (F->coveredPinned[0] != L.coverCache.covered || F->coveredPinned[1] != L.coverCache.listHash))
     {
-        // the frame was launched on a stale covered-block count (the scene's arrays were rewritten in
-        // place, or something this cache's key does not see): render it again on the fresh one
+        // the frame was launched on a stale covered-block count / block list (the scene's arrays were
+        // rewritten in place, or something this cache's key does not see): render it again on the fresh one
         L.coverCache.valid = false;
-        SPB_CUDA(cudaMemsetAsync(ctr, 0, (CTR_COUNT + (size_t)tileRows * 2) * sizeof(unsigned long long), L.stream));
-        SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
-        rowsStreamed = render_wavefront(args, ds->instancedTriangles, waveCounters, hostPixels, false);
+        SPB_CUDA(cudaStreamSynchronize(L.stream)); // (a later frame begun on the same stale numbers finishes first; its End renders it again too)
+        SPB_CUDA(cudaMemsetAsync(P.ctr, 0, P.cCount * sizeof(unsigned long long), L.stream));
+        SPB_CUDA(cudaEventRecord(F->evStart, L.stream));
+        SPB_CUDA(cudaEventRecord(F->evKernel0, L.stream));
+        P.waveCounters.clear();
+        P.rowsStreamed = render_wavefront(P.args, P.instancedTriangles, P.waveCounters, P.hostPixels, false);
         SPB_CUDA(cudaGetLastError());
-        SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
-        SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
-        if (!waveCounters.empty())
-            SPB_CUDA(cudaMemcpyAsync(waveCounters.data(), L.wCtr.ptr, waveCounters.size() * 4, cudaMemcpyDeviceToHost, L.stream));
-        if (hostPixels && !rowsStreamed)
+        SPB_CUDA(cudaEventRecord(F->evKernel1, L.stream));
+        P.waveCount = P.waveCounters.size();
+        P.pinnedCounters = false;
+        P.c.resize(P.cCount);
+        SPB_CUDA(cudaMemcpyAsync(P.c.data(), P.ctr, P.cCount * 8, cudaMemcpyDeviceToHost, L.stream));
+        if (P.waveCount)
+            SPB_CUDA(cudaMemcpyAsync(P.waveCounters.data(), L.wCtr.ptr, P.waveCount * 4, cudaMemcpyDeviceToHost, L.stream));
+        if (P.hostPixels && !P.rowsStreamed)
         {
             size_t offset = (size_t)rowBegin * cam.width;
-            SPB_CUDA(cudaMemcpyAsync(hostPixels + offset * 4, image + offset, (size_t)(rowEnd - rowBegin) * cam.width * 16,
+            SPB_CUDA(cudaMemcpyAsync(P.hostPixels + offset * 4, P.image + offset, (size_t)(rowEnd - rowBegin) * cam.width * 16,
                                      cudaMemcpyDeviceToHost, L.stream));
         }
-        if (rowsStreamed) SPB_CUDA(cudaStreamWaitEvent(L.stream, L.evCopyDone, 0));
-        SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+        SPB_CUDA(cudaEventRecord(F->evEnd, L.stream));
         SPB_CUDA(cudaStreamSynchronize(L.stream));
+        if (P.rowsStreamed) SPB_CUDA(cudaEventSynchronize(F->evCopyDone));
     }
+    unsigned long long *c = P.pinnedCounters ? F->hostCounters : P.c.data();
+    const uint32_t *waveCounters = P.pinnedCounters ? F->hostWave : P.waveCounters.data();
+    const size_t waveCount = P.waveCount;
     float kernelMs = 0, totalMs = 0;
-    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
-    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, F->evKernel0, F->evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, F->evStart, F->evEnd));
+    if (P.rowsStreamed)
+    {
+        // the copies' tail beyond the last kernel belongs to the call's device time
+        float tail = 0.0f;
+        if (cudaEventElapsedTime(&tail, F->evEnd, F->evCopyDone) == cudaSuccess && tail > 0.0f) totalMs += tail;
+        else cudaGetLastError();
+    }
     float traceMs = 0.0f;
     if (wavefront)
-        for (size_t i = 0; i + 1 < L.traceEventsUsed; i += 2)
+        for (size_t i = 0; i + 1 < F->traceEventsUsed; i += 2)
         {
             float ms = 0.0f;
-            SPB_CUDA(cudaEventElapsedTime(&ms, L.traceEvents[i], L.traceEvents[i + 1]));
+            SPB_CUDA(cudaEventElapsedTime(&ms, F->traceEvents[i], F->traceEvents[i + 1]));
             traceMs += ms;
         }
     if (wavefront && !L.tuner.probes.empty())
@@ -2133,7 +2318,7 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
         {
             float ms = 0.0f;
             SPB_CUDA(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
-            double rays = pr.ctrIndex + WCTR_NHITS < waveCounters.size() ? (double)waveCounters[pr.ctrIndex + WCTR_NHITS] : 0.0;
+            double rays = pr.ctrIndex + WCTR_NHITS < waveCount ? (double)waveCounters[pr.ctrIndex + WCTR_NHITS] : 0.0;
             if (rays < 1.0) continue;
             tn.ms[pr.candidate] += ms;
             tn.rays[pr.candidate] += rays;
@@ -2151,25 +2336,25 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
         // queue lengths are the path counters: rays = rays entering each traversal, and every
         // ray ends in exactly one of the hit / miss queues; a sky pixel is spp rays, spp misses
         unsigned long long rays = 0, hits = 0, misses = 0;
-        for (size_t i = 0; i + WCTR_STRIDE <= waveCounters.size(); i += WCTR_STRIDE)
+        for (size_t i = 0; i + WCTR_STRIDE <= waveCount; i += WCTR_STRIDE)
         {
             hits += waveCounters[i + WCTR_NHITS];
             misses += waveCounters[i + WCTR_NMISSES];
         }
         // a sky-kernel pixel is spp rays, spp misses (its row cost was added on the device)
-        misses += c[CTR_SKY_PIXELS] * L.params.samplesPerPixel;
+        misses += c[CTR_SKY_PIXELS] * P.spp;
         rays = hits + misses;
-        c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * L.params.samplesPerPixel;
+        c[CTR_PATHS] = (unsigned long long)(rowEnd - rowBegin) * cam.width * P.spp;
         c[CTR_RAYS] = rays;
         c[CTR_HITS] = hits;
         c[CTR_MISSES] = misses;
     }
-    add_metrics(metrics, c.data(), kernelMs);
-    record_stats(c.data(), kernelMs, totalMs);
+    add_metrics(metrics, c, kernelMs);
+    record_stats(c, kernelMs, totalMs);
     L.lastStats.traceMs = wavefront ? traceMs : kernelMs;
-    L.lastStats.traceLaunches = wavefront ? (u32)(L.traceEventsUsed / 2) : 1u;
-    L.lastStats.tracedRays = c[CTR_RAYS] - (wavefront ? c[CTR_SKY_PIXELS] * L.params.samplesPerPixel : 0);
-    if (tileRowCost)
+    L.lastStats.traceLaunches = wavefront ? (u32)(F->traceEventsUsed / 2) : 1u;
+    L.lastStats.tracedRays = c[CTR_RAYS] - (wavefront ? c[CTR_SKY_PIXELS] * P.spp : 0);
+    if (tileRowCost && P.wantCost)
     {
         // Cost of every tile row in NANOSECONDS of this device: the units the kernels counted,
         // converted class by class with the time that class took in this very call -- the sky
@@ -2177,7 +2362,7 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
         // by the rest.  A unit of sky is not a unit of bunny, and how much not depends on the
         // scene and the strip; measuring the two apart takes that guess out of the re-cut.
         float skyMs = 0.0f;
-        if (wavefront && L.skyTimed) SPB_CUDA(cudaEventElapsedTime(&skyMs, L.evSky0, L.evSky1));
+        if (wavefront && F->skyTimed) SPB_CUDA(cudaEventElapsedTime(&skyMs, F->evSky0, F->evSky1));
         double unitsQueue = 0.0, unitsSky = 0.0;
         for (u32 i = 0; i < tileRows; ++i)
         {
@@ -2194,6 +2379,46 @@ extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32
     }
     return 0;
 }
+
+extern "C" int sp_b200_RenderRows(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame,
+                                  f32 *hostPixels, void *devicePixels, sp_Metrics *metrics,
+                                  u64 *tileRowCost)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    FrameState *F = !L.frames[0].pending ? &L.frames[0] : (!L.frames[1].pending ? &L.frames[1] : nullptr);
+    if (!F)
+    {
+        log_message("sp_b200_RenderRows: two frames are already in flight (sp_b200_RenderRowsBegin): end one first");
+        return -1;
+    }
+    if (render_rows_begin(ctx, rowBegin, rowEnd, frame, hostPixels, devicePixels, tileRowCost != nullptr, F) != 0) return -1;
+    return render_rows_end(F, metrics, tileRowCost);
+}
+
+extern "C" int sp_b200_RenderRowsBegin(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 frame,
+                                       f32 *hostPixels, void *devicePixels, int wantTileRowCost)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    ensure_init();
+    int slot = !L.frames[0].pending ? 0 : (!L.frames[1].pending ? 1 : -1);
+    if (slot < 0) return -1;
+    // the frame begun before this one, if any, is the other slot: alternate, so that frames end in the order they began
+    if (render_rows_begin(ctx, rowBegin, rowEnd, frame, hostPixels, devicePixels, wantTileRowCost != 0, &L.frames[slot]) != 0) return -1;
+    L.frames[slot].pending = true; // (also for an empty strip: End is due either way)
+    return slot;
+}
+
+extern "C" int sp_b200_RenderRowsEnd(int slot, sp_Metrics *metrics, u64 *tileRowCost)
+{
+    Library &L = lib();
+    std::lock_guard<std::recursive_mutex> lock(L.mutex);
+    if (slot < 0 || slot > 1 || !L.frames[slot].pending) return -1;
+    return render_rows_end(&L.frames[slot], metrics, tileRowCost);
+}
+
 
 // Output stage: tone mapping + 8-bit store (post_processing.frag.glsl:19-26).  Source: device
 // pixels if given, else host pixels (uploaded); result to hostRGBA8 and/or deviceRGBA8.
@@ -2396,7 +2621,7 @@ static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, voi
         if (p > 0 && primaryDevicePixels)
         {
             const size_t offset = (size_t)b * width * 16, bytes = (size_t)(e - b) * width * 16;
-            SPB_CUDA(cudaMemcpyPeerAsync((char *)primaryDevicePixels + offset, primaryDevice, (const char *)L.image.ptr + offset,
+            SPB_CUDA(cudaMemcpyPeerAsync((char *)primaryDevicePixels + offset, primaryDevice, (const char *)L.f->image.ptr + offset,
                                          L.device, bytes, L.stream));
             SPB_CUDA(cudaStreamSynchronize(L.stream));
         }
@@ -2517,8 +2742,8 @@ static void render_tile_group(const std::vector<TileRequest *> &group)
     convert_camera(ctx->camera, &cam);
     DeviceScene *ds = find_scene(ctx->scene);
     size_t imageBytes = (size_t)cam.width * cam.height * 16;
-    L.image.ensure(imageBytes ? imageBytes : 16);
-    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+    L.f->image.ensure(imageBytes ? imageBytes : 16);
+    SPB_CUDA(cudaEventRecord(L.f->evStart, L.stream));
     const DMaterials *dm = upload_materials(ctx->materialSystem);
     unsigned long long *ctr = reset_counters((size_t)(count - 1) * CTR_COUNT);
     L.scratchA.ensure(staging.size() * 4);
@@ -2534,12 +2759,12 @@ static void render_tile_group(const std::vector<TileRequest *> &group)
     args.spp = L.params.samplesPerPixel;
     args.bounces = L.params.bounceCount;
     args.clampValue = L.params.radianceClamp;
-    args.out = (v4f *)L.image.ptr;
+    args.out = (v4f *)L.f->image.ptr;
     args.counters = ctr;
-    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel0, L.stream));
     launch_tiles_serial(kernel_config(), args, L.stream);
     SPB_CUDA(cudaGetLastError());
-    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel1, L.stream));
 
     std::vector<unsigned long long> c((size_t)count * CTR_COUNT);
     std::vector<uint32_t> states(count);
@@ -2553,15 +2778,15 @@ static void render_tile_group(const std::vector<TileRequest *> &group)
             if (t[2] <= t[0] || t[3] <= t[1]) continue;
             size_t pitch = (size_t)cam.width * 16;
             size_t offset = (size_t)t[1] * cam.width + t[0];
-            SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
+            SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.f->image.ptr + offset,
                                        pitch, (size_t)(t[2] - t[0]) * 16, t[3] - t[1],
                                        cudaMemcpyDeviceToHost, L.stream));
         }
-    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evEnd, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float kernelMs = 0, totalMs = 0;
-    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
-    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.f->evKernel0, L.f->evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.f->evStart, L.f->evEnd));
     int clockKHz = 0;
     cudaDeviceGetAttribute(&clockKHz, cudaDevAttrClockRate, L.device);
     std::vector<unsigned long long> total(CTR_COUNT, 0);
@@ -2702,8 +2927,8 @@ extern "C" u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *me
         convert_camera(ctx->camera, &cam);
         DeviceScene *ds = find_scene(ctx->scene);
         size_t imageBytes = (size_t)cam.width * cam.height * 16;
-        L.image.ensure(imageBytes ? imageBytes : 16);
-        SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
+        L.f->image.ensure(imageBytes ? imageBytes : 16);
+        SPB_CUDA(cudaEventRecord(L.f->evStart, L.stream));
         const DMaterials *dm = upload_materials(ctx->materialSystem);
         unsigned long long *ctr = reset_counters((size_t)(count - 1) * CTR_COUNT);
         L.scratchA.ensure(staging.size() * 4);
@@ -2719,12 +2944,12 @@ extern "C" u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *me
         args.spp = L.params.samplesPerPixel;
         args.bounces = L.params.bounceCount;
         args.clampValue = L.params.radianceClamp;
-        args.out = (v4f *)L.image.ptr;
+        args.out = (v4f *)L.f->image.ptr;
         args.counters = ctr;
-        SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->evKernel0, L.stream));
         launch_tiles_serial(kernel_config(), args, L.stream);
         SPB_CUDA(cudaGetLastError());
-        SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->evKernel1, L.stream));
 
         std::vector<unsigned long long> c((size_t)count * CTR_COUNT);
         SPB_CUDA(cudaMemcpyAsync(c.data(), ctr, c.size() * 8, cudaMemcpyDeviceToHost, L.stream));
@@ -2735,15 +2960,15 @@ extern "C" u32 sp_b200_DrainRayTracingWorkQueue(WorkQueue *queue, sp_Metrics *me
                 if (t[2] <= t[0] || t[3] <= t[1]) continue;
                 size_t pitch = (size_t)cam.width * 16;
                 size_t offset = (size_t)t[1] * cam.width + t[0];
-                SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.image.ptr + offset,
+                SPB_CUDA(cudaMemcpy2DAsync((f32 *)plane->pixels + offset * 4, pitch, (v4f *)L.f->image.ptr + offset,
                                            pitch, (size_t)(t[2] - t[0]) * 16, t[3] - t[1],
                                            cudaMemcpyDeviceToHost, L.stream));
             }
-        SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+        SPB_CUDA(cudaEventRecord(L.f->evEnd, L.stream));
         SPB_CUDA(cudaStreamSynchronize(L.stream));
         float kernelMs = 0, totalMs = 0;
-        SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
-        SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+        SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.f->evKernel0, L.f->evKernel1));
+        SPB_CUDA(cudaEventElapsedTime(&totalMs, L.f->evStart, L.f->evEnd));
         int clockKHz = 0;
         cudaDeviceGetAttribute(&clockKHz, cudaDevAttrClockRate, L.device);
         std::vector<unsigned long long> total(CTR_COUNT, 0);
@@ -2784,22 +3009,22 @@ extern "C" int sp_b200_PrimaryHits(sp_Context *ctx, u32 sample, u32 frame, i32 *
     L.scratchB.ensure(n * 4);
     L.scratchC.ensure(n * 4);
     unsigned long long *ctr = reset_counters();
-    SPB_CUDA(cudaEventRecord(L.evStart, L.stream));
-    SPB_CUDA(cudaEventRecord(L.evKernel0, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evStart, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel0, L.stream));
     launch_primary_hits(kernel_config(), launch_scene(ds), cam, sample, frame, (int32_t *)L.scratchA.ptr,
                         (int32_t *)L.scratchB.ptr, (float *)L.scratchC.ptr, ctr, L.stream);
     SPB_CUDA(cudaGetLastError());
-    SPB_CUDA(cudaEventRecord(L.evKernel1, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evKernel1, L.stream));
     unsigned long long c[CTR_COUNT];
     SPB_CUDA(cudaMemcpyAsync(c, ctr, sizeof(c), cudaMemcpyDeviceToHost, L.stream));
     if (triangleIndex) SPB_CUDA(cudaMemcpyAsync(triangleIndex, L.scratchA.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
     if (objectIndex) SPB_CUDA(cudaMemcpyAsync(objectIndex, L.scratchB.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
     if (t) SPB_CUDA(cudaMemcpyAsync(t, L.scratchC.ptr, n * 4, cudaMemcpyDeviceToHost, L.stream));
-    SPB_CUDA(cudaEventRecord(L.evEnd, L.stream));
+    SPB_CUDA(cudaEventRecord(L.f->evEnd, L.stream));
     SPB_CUDA(cudaStreamSynchronize(L.stream));
     float kernelMs = 0, totalMs = 0;
-    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.evKernel0, L.evKernel1));
-    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.evStart, L.evEnd));
+    SPB_CUDA(cudaEventElapsedTime(&kernelMs, L.f->evKernel0, L.f->evKernel1));
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, L.f->evStart, L.f->evEnd));
     record_stats(c, kernelMs, totalMs);
     return 0;
 }

@@ -717,6 +717,14 @@ SPB_HD TravEntry load_entry(const TravEntry *p)
 #endif
 }
 
+// Where a lane's stack lives.  The traversal functions below take any STK with stack_put / stack_get: a plain
+// array (host builds, per-pixel and query kernels), or the trace kernel's hybrid (spb_wavefront.cu: the first
+// entries -- all a walk needs 99.9 % of the time -- in shared memory, one column per thread, so a push or a pop
+// is two conflict-free wavefronts however far the lanes' stack pointers have drifted apart; a local-memory
+// access costs two per distinct stack pointer in the warp, on the L1 the node fetches need).
+SPB_HD void stack_put(TravEntry *stack, int sp, TravEntry e) { stack[sp] = e; }
+SPB_HD TravEntry stack_get(const TravEntry *stack, int sp) { return load_entry(stack + sp); }
+
 // Hot state: what every NODE / LEAF step touches.
 struct Trav
 {
@@ -777,8 +785,8 @@ SPB_HD void trav_world_ray(const v4f *ray, f3 &wo, f3 &wd)
 
 // Pops until there is an entry to process (st.cur), the walk inside an object ends
 // (SPB_NODE_EXIT) or the query ends (SPB_NODE_DONE).
-template <bool CULL>
-SPB_HD void trav_pop(Trav &st, const TravEntry *stack)
+template <bool CULL, class STK>
+SPB_HD void trav_pop(Trav &st, STK stack)
 {
     for (;;)
     {
@@ -789,7 +797,7 @@ SPB_HD void trav_pop(Trav &st, const TravEntry *stack)
             return;
         }
         st.sp--;
-        TravEntry e = load_entry(stack + st.sp);
+        TravEntry e = stack_get(stack, st.sp);
         if (CULL && !(e.tnear <= st.tcull)) continue;
         st.cur = e.ref;
         return;
@@ -798,8 +806,8 @@ SPB_HD void trav_pop(Trav &st, const TravEntry *stack)
 
 // EXIT step (st.cur == SPB_NODE_EXIT): leave the object -- sp_scene.cpp:296-322 on its closest
 // hit -- and go on with the TLAS entries below.
-template <bool CULL>
-SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, const TravEntry *stack)
+template <bool CULL, class STK>
+SPB_HD void trav_exit(const DScene &S, Trav &st, TravCold &c, const v4f *ray, STK stack)
 {
     f3 wo, wd;
     trav_world_ray(ray, wo, wd);
@@ -885,12 +893,13 @@ SPB_HD void trav_begin_single(const DScene &S, f3 o, f3 d, Trav &st, TravCold &c
 
 // No bound check: flatten_scene() refuses scenes whose worst-case stack use (three entries per
 // level of the TLAS plus three per level of the deepest mesh tree) exceeds SPB_STACK_SIZE.
-SPB_HD void trav_push(Trav &st, TravEntry *stack, uint32_t ref, float tnear)
+template <class STK>
+SPB_HD void trav_push(Trav &st, STK stack, uint32_t ref, float tnear)
 {
     TravEntry e;
     e.ref = ref;
     e.tnear = tnear;
-    stack[st.sp] = e;
+    stack_put(stack, st.sp, e);
     st.sp++;
 }
 
@@ -903,17 +912,27 @@ SPB_HD void sortx(float &ka, uint32_t &ra, float &kb, uint32_t &rb)
     ka = lo; kb = hi; ra = rlo; rb = rhi;
 }
 
-// NODE step: st.cur is a node index.
-template <bool CULL>
-SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *counters)
+// The 128 bytes of a node as the NODE step reads them.
+struct NodeData { v4f minx, miny, minz, maxx, maxy, maxz, refsf, meta; };
+// The fetch of a NODE step alone, where `take` is set: the trace kernel issues it as soon as a lane's next
+// entry is known to be a node, ahead of the warp's vote on the kind of the next step, so that the L1 round
+// trip runs under the vote instead of in front of the first slab test.
+SPB_HD void trav_node_fetch(const DScene &S, bool take, uint32_t cur, NodeData &nd)
+{
+    // (every lane loads: a predicated load would leave its registers "maybe written", which keeps them alive
+    // around the whole loop; lanes without a node read node 0, one line for all of them)
+    const v4f *n = S.nodes + (size_t)(take ? cur : 0u) * 8;
+    ld8(n + 0, nd.minx, nd.miny);
+    ld8(n + 2, nd.minz, nd.maxx);
+    ld8(n + 4, nd.maxy, nd.maxz);
+    ld8(n + 6, nd.refsf, nd.meta);
+}
+// NODE step on fetched data: st.cur is the node index nd was fetched for.
+template <bool CULL, class STK>
+SPB_HD void trav_node_apply(const DScene &S, Trav &st, STK stack, Counters *counters, const NodeData &nd)
 {
     const float inf = u2f(0x7F800000u);
-    const v4f *n = S.nodes + (size_t)st.cur * 8;
-    v4f minx, miny, minz, maxx, maxy, maxz, refsf, meta;
-    ld8(n + 0, minx, miny);
-    ld8(n + 2, minz, maxx);
-    ld8(n + 4, maxy, maxz);
-    ld8(n + 6, refsf, meta);
+    const v4f minx = nd.minx, miny = nd.miny, minz = nd.minz, maxx = nd.maxx, maxy = nd.maxy, maxz = nd.maxz, refsf = nd.refsf;
     v4u refs;
     refs.x = f2u(refsf.x); refs.y = f2u(refsf.y); refs.z = f2u(refsf.z); refs.w = f2u(refsf.w);
     if (counters) counters->nodeVisits++;
@@ -973,10 +992,22 @@ SPB_HD void trav_node(const DScene &S, Trav &st, TravEntry *stack, Counters *cou
     }
     trav_pop<CULL>(st, stack);
 }
+// NODE step: st.cur is a node index.
+template <bool CULL, class STK>
+SPB_HD void trav_node(const DScene &S, Trav &st, STK stack, Counters *counters)
+{
+    NodeData nd;
+    const v4f *n = S.nodes + (size_t)st.cur * 8;
+    ld8(n + 0, nd.minx, nd.miny);
+    ld8(n + 2, nd.minz, nd.maxx);
+    ld8(n + 4, nd.maxy, nd.maxz);
+    ld8(n + 6, nd.refsf, nd.meta);
+    trav_node_apply<CULL>(S, st, stack, counters, nd);
+}
 
 // LEAF step: st.cur is SPB_REF_LEAF | slot.
-template <bool CULL>
-SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, TravEntry *stack,
+template <bool CULL, class STK>
+SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, STK stack,
                       Counters *counters)
 {
     const float inf = u2f(0x7F800000u);

@@ -373,6 +373,35 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     }
 }
 #else // the production kernel: the first machine (exact box tests at every node)
+// The trace kernel's stack (spb_core.cuh stack_put / stack_get): entries below SPB_SMEM_STACK in shared memory --
+// entry k of thread t at column t of row k, so the 32 lanes of a warp hit 32 different bank pairs whatever their
+// stack pointers are -- the rest in the lane's local-memory array.
+#ifndef SPB_SMEM_STACK
+#define SPB_SMEM_STACK 0
+#endif
+struct HybridStack
+{
+    unsigned long long *column; // this thread's column: entry k at column[k * SPB_TRACE_THREADS]
+    TravEntry *local;
+};
+__device__ __forceinline__ void stack_put(const HybridStack &s, int sp, TravEntry e)
+{
+    if (sp < SPB_SMEM_STACK) s.column[sp * SPB_TRACE_THREADS] = (unsigned long long)e.ref | ((unsigned long long)f2u(e.tnear) << 32);
+    else s.local[sp] = e;
+}
+__device__ __forceinline__ TravEntry stack_get(const HybridStack &s, int sp)
+{
+    if (sp < SPB_SMEM_STACK)
+    {
+        unsigned long long raw = s.column[sp * SPB_TRACE_THREADS];
+        TravEntry e;
+        e.ref = (uint32_t)raw;
+        e.tnear = u2f((uint32_t)(raw >> 32));
+        return e;
+    }
+    return load_entry(s.local + sp);
+}
+
 // Primary ray of item `idx` resolved from its pixel's candidate list (spb_core.cuh
 // resolve_from_candidates); leaves the lane finished, or untouched when the pixel falls back.
 template <bool CULL>
@@ -420,7 +449,13 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 
     // per-lane stack in local memory; state that is touched only when an object is entered or
     // left, or the ray retired, lives in shared memory (6 + 1 words per lane, conflict-free stride)
-    TravEntry stack[SPB_STACK_SIZE];
+    TravEntry localStack[SPB_STACK_SIZE];
+#if SPB_SMEM_STACK > 0
+    __shared__ unsigned long long stackRows[SPB_SMEM_STACK][SPB_TRACE_THREADS];
+    const HybridStack stack = {&stackRows[0][threadIdx.x], localStack};
+#else
+    TravEntry *const stack = localStack;
+#endif
     __shared__ TravCold coldAll[SPB_TRACE_THREADS];
     __shared__ unsigned slotAll[SPB_TRACE_THREADS];
     TravCold &cold = coldAll[threadIdx.x];
@@ -472,8 +507,9 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                         rec[2] = q;
                         for (int k = 0; k < st.sp; k += 2)
                         {
-                            q.x = stack[k].ref; q.y = f2u(stack[k].tnear);
-                            q.z = k + 1 < st.sp ? stack[k + 1].ref : 0u; q.w = k + 1 < st.sp ? f2u(stack[k + 1].tnear) : 0u;
+                            TravEntry e0 = stack_get(stack, k), e1 = stack_get(stack, k + 1 < st.sp ? k + 1 : k);
+                            q.x = e0.ref; q.y = f2u(e0.tnear);
+                            q.z = e1.ref; q.w = f2u(e1.tnear);
                             rec[3 + (k >> 1)] = q;
                         }
                         have = false;
@@ -559,8 +595,11 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                         for (int k = 0; k < st.sp; k += 2)
                         {
                             v4u q = rec[3 + (k >> 1)];
-                            stack[k].ref = q.x; stack[k].tnear = u2f(q.y);
-                            if (k + 1 < st.sp) { stack[k + 1].ref = q.z; stack[k + 1].tnear = u2f(q.w); }
+                            TravEntry e0, e1;
+                            e0.ref = q.x; e0.tnear = u2f(q.y);
+                            e1.ref = q.z; e1.tnear = u2f(q.w);
+                            stack_put(stack, k, e0);
+                            if (k + 1 < st.sp) stack_put(stack, k + 1, e1);
                         }
                         f3 wo, wd;
                         trav_world_ray(rays + (size_t)slot * 2, wo, wd);
@@ -637,6 +676,58 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             if (!__any_sync(SPB_FULL, have) && exhausted) break;
             continue; // everything in flight finished at once
         }
+#if SPB_EARLY_FETCH == 2
+        // The node a lane wants to visit is fetched BEFORE the warp votes on the kind of the next step, so the
+        // L1 round trip runs under the vote and the branch instead of in front of the first slab test; in an
+        // iteration that runs a leaf step the data is dropped (and fetched again next time: an L1 hit).
+        do
+        {
+            const bool live = have && trav_is_walking(st);
+            const bool wantNode = live && trav_is_node(st);
+            const bool wantLeaf = live && !wantNode;
+            NodeData nd;
+            trav_node_fetch(a.scene, wantNode, st.cur, nd);
+            unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
+            unsigned leafMask = walking & ~nodeMask;
+            if (__popc(nodeMask) >= __popc(leafMask))
+            {
+                if (wantNode) trav_node_apply<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
+            }
+            else
+            {
+                if (wantLeaf)
+                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+            }
+            walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
+        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
+#elif SPB_EARLY_FETCH == 1
+        // The node a lane will visit next is fetched the moment it is known -- at the end of the step that
+        // made it the current entry -- so the L1 round trip runs under the two votes and the branch to the
+        // next step instead of in front of its first slab test.  A lane that wants a node while the warp runs
+        // a leaf step fetches it again afterwards (an L1 hit).
+        bool live = have && trav_is_walking(st);
+        bool wantNode = live && trav_is_node(st);
+        NodeData nd;
+        trav_node_fetch(a.scene, wantNode, st.cur, nd);
+        unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
+        do
+        {
+            if (__popc(nodeMask) >= __popc(walking & ~nodeMask))
+            {
+                if (wantNode) trav_node_apply<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
+            }
+            else
+            {
+                if (live && !wantNode)
+                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+            }
+            live = have && trav_is_walking(st);
+            wantNode = live && trav_is_node(st);
+            trav_node_fetch(a.scene, wantNode, st.cur, nd);
+            walking = __ballot_sync(SPB_FULL, live);
+            nodeMask = __ballot_sync(SPB_FULL, wantNode);
+        } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
+#else
         do
         {
             const bool live = have && trav_is_walking(st);
@@ -655,6 +746,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
+#endif
     }
 
 
@@ -1019,6 +1111,8 @@ __global__ void __launch_bounds__(1024)
 k_list_blocks(unsigned blocks, uint8_t *coverage, uint32_t *blockList, uint32_t *listCount)
 {
     __shared__ unsigned sums[1024];
+    __shared__ unsigned listHash;
+    if (threadIdx.x == 0) listHash = 0;
     const bool all = coverage[blocks] != 0;
     const unsigned per = (blocks + 1023u) / 1024u;
     const unsigned b0 = threadIdx.x * per, b1 = b0 + per < blocks ? b0 + per : blocks;
@@ -1038,9 +1132,19 @@ k_list_blocks(unsigned blocks, uint8_t *coverage, uint32_t *blockList, uint32_t 
         __syncthreads();
     }
     unsigned at = sums[threadIdx.x] - n;
+    // listCount[1]: a fingerprint of the list (which block at which position), for the host's cached copy of
+    // what it derives from the list (spb_api.cu render_wavefront)
+    unsigned h = 0;
     for (unsigned b = b0; b < b1; ++b)
-        if (coverage[b]) blockList[at++] = b;
+        if (coverage[b])
+        {
+            h += (b + 1u) * (2654435761u * at + 1u);
+            blockList[at++] = b;
+        }
+    if (h) atomicAdd(&listHash, h);
+    __syncthreads();
     if (threadIdx.x == 1023) listCount[0] = sums[1023];
+    if (threadIdx.x == 0) listCount[1] = listHash;
 }
 
 // Pixels whose block is not covered: the sample loop of sp_PathTraceTile

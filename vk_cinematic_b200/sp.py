@@ -294,6 +294,8 @@ _SIGNATURES = {
     "sp_b200_Seed": (u32, [u32, u32, u32]),
     "sp_b200_RenderRows": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p,
                                      _P(sp_Metrics), C.c_void_p]),
+    "sp_b200_RenderRowsBegin": (C.c_int, [_P(sp_Context), u32, u32, u32, C.c_void_p, C.c_void_p, C.c_int]),
+    "sp_b200_RenderRowsEnd": (C.c_int, [C.c_int, _P(sp_Metrics), C.c_void_p]),
     "sp_b200_RenderFrame": (C.c_int, [_P(sp_Context), u32, _P(sp_Metrics)]),
     "LoadExrImage": (C.c_int, [_P(HdrImage), C.c_char_p]),
     "sp_b200_LoadObj": (C.c_int, [C.c_char_p, _P(sp_b200_MeshData)]),
@@ -603,6 +605,33 @@ class Renderer:
                                     C.byref(m), cost.ctypes.data if cost is not None else None)
         if rc != 0:
             raise RuntimeError("sp_b200_RenderRows failed")
+        return np.array(list(m.values), dtype=np.uint64), cost
+
+    def render_rows_begin(self, row_begin, row_end, frame=0, host=True, device_ptr=None, want_cost=False, host_ptr=None):
+        """First half of render_rows (sp_b200_RenderRowsBegin): everything is enqueued, nothing waited for.
+        Returns the slot to hand to render_rows_end; up to two frames may be in flight."""
+        if host_ptr is None:
+            host_ptr = self.image.ctypes.data if host else None
+        slot = lib.sp_b200_RenderRowsBegin(C.byref(self.ctx), row_begin, row_end, frame, host_ptr, device_ptr,
+                                           1 if want_cost else 0)
+        if slot < 0:
+            raise RuntimeError("sp_b200_RenderRowsBegin failed (two frames in flight already?)")
+        if not hasattr(self, "_begun"):
+            self._begun = {}
+        self._begun[slot] = (row_begin, row_end, want_cost)
+        return slot
+
+    def render_rows_end(self, slot):
+        """Second half: waits for the frame begun in `slot`; returns (metrics, per-tile-row cost or None)."""
+        row_begin, row_end, want_cost = self._begun.pop(slot)
+        m = sp_Metrics()
+        cost = None
+        if want_cost and row_end > row_begin:
+            th = default_tile_height()
+            cost = np.zeros((row_end - 1) // th - row_begin // th + 1, np.uint64)
+        rc = lib.sp_b200_RenderRowsEnd(slot, C.byref(m), cost.ctypes.data if cost is not None else None)
+        if rc != 0:
+            raise RuntimeError("sp_b200_RenderRowsEnd failed")
         return np.array(list(m.values), dtype=np.uint64), cost
 
     def path_trace_tile(self, tile, rng_state):
