@@ -77,6 +77,8 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity block")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 secondary block")
     ap.add_argument("--no-copy-overlap", action="store_true", help="development: sp_b200_SetCopyOverlap(0)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="development: one sp_b200_RenderRows call per step instead of RenderRowsBegin / End with two frames in flight")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -446,6 +448,10 @@ def main():
         # stdout carries exactly one JSON line: whatever NCCL_DEBUG asks for goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        # "the frame is complete in host memory on every rank" is a statement about the hosts: the end-to-end steps
+        # mark it with a CPU barrier (gloo).  An NCCL barrier is a kernel on the render stream -- it would run behind
+        # the NEXT frame, already enqueued there (two frames in flight), and make every step wait for it.
+        host_group = dist.new_group(backend="gloo")
     assert sp.lib.sp_b200_Init(local) == 0
     stream = torch.cuda.current_stream()
     sp.lib.sp_b200_SetStream(stream.cuda_stream)
@@ -470,14 +476,18 @@ def main():
         shared_path = name[0]
         if rank == 0:
             with open(shared_path, "wb") as f:
-                f.truncate(H * Wd * 16)
+                f.truncate(2 * H * Wd * 16)
         dist.barrier()
-        host_np = np.memmap(shared_path, dtype=np.float32, mode="r+", shape=(H, Wd, 4))
-        host_image = torch.from_numpy(host_np)
-        rc = torch.cuda.cudart().cudaHostRegister(host_image.data_ptr(), host_image.numel() * 4, 0)
+        # (two images: with two frames in flight -- sp_b200_RenderRowsBegin / End -- consecutive frames must not
+        # share their destination)
+        host_np = np.memmap(shared_path, dtype=np.float32, mode="r+", shape=(2, H, Wd, 4))
+        host_both = torch.from_numpy(host_np)
+        rc = torch.cuda.cudart().cudaHostRegister(host_both.data_ptr(), host_both.numel() * 4, 0)
         assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
+        host_images = [host_both[0], host_both[1]]
     else:
-        host_image = torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory()
+        host_images = [torch.zeros((H, Wd, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_image = host_images[0]
     if args.device_builder:
         sp.lib.sp_b200_SetMeshBuilder(sp.BUILDER_DEVICE_LBVH)
     r = sp.Renderer(local).load_workload(wl, pixels=host_image.numpy())
@@ -505,7 +515,8 @@ def main():
     TH = args.strip_rows   # strip boundaries and cost accounting: rows of TH pixels
     # Two device images, used alternately: the strips of frame k are on their way to rank 0 (NCCL, on
     # its own stream) while frame k + 1 renders into the other one.
-    images = [torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    pipelined = not args.no_pipeline
+    images = [torch.zeros((H, Wd, 4), dtype=torch.float32, device=dev) for _ in range(2 if (world > 1 or pipelined) else 1)]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     gathered = [torch.cuda.Event() for _ in images]
 
@@ -519,10 +530,13 @@ def main():
     trace_log = []
     step_counter = [0]
 
-    def gather_async(image, bounds, slot):
+    def gather_async(image, bounds, slot, after=None):
         """The one exchange step: strips to rank 0, one batched send/recv group on the
         communication stream; the render stream goes on with the next frame."""
-        comm.wait_stream(stream)
+        if after is not None:
+            comm.wait_event(after)               # (the frame's last kernel; later frames may already be enqueued)
+        else:
+            comm.wait_stream(stream)
         with torch.cuda.stream(comm):
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(comm)
@@ -538,9 +552,9 @@ def main():
     issuer = ThreadPoolExecutor(max_workers=1) if world > 1 else None
     pending = [None for _ in images]
 
-    def issue_gather(image, bounds, slot):
+    def issue_gather(image, bounds, slot, after=None):
         torch.cuda.set_device(local)
-        gather_async(image, bounds, slot)
+        gather_async(image, bounds, slot, after)
 
     def drain_gathers():
         for i, f in enumerate(pending):
@@ -571,6 +585,34 @@ def main():
                 pending[slot] = issuer.submit(issue_gather, image, bounds, slot)
         trace_log.append((st.traceMs, st.traceLaunches, int(st.tracedRays)) if e > b else (0.0, 0, 0))
         return m, cost, (st.kernelMs if e > b else 0.0), image
+
+    # The same step in two halves (sp_b200_RenderRowsBegin / End, two frames in flight): begin frame k + 1, then
+    # end frame k -- the host-side epilogue of k (event times, metrics) and the prologue of k + 1 run under
+    # k + 1's kernels, and the device does not idle across the frame boundary.
+    def step_begin(frame, bounds):
+        slot = step_counter[0] % len(images)
+        step_counter[0] += 1
+        image = images[slot]
+        if pending[slot] is not None:
+            pending[slot].result()
+            pending[slot] = None
+        stream.wait_event(gathered[slot])
+        b, e = bounds[rank]
+        h = r.render_rows_begin(b, e, frame=frame, host=False, device_ptr=image.data_ptr()) if e > b else None
+        if world > 1:
+            done = torch.cuda.Event()
+            done.record(stream)
+            pending[slot] = issuer.submit(issue_gather, image, bounds, slot, done)
+        return h
+
+    def step_end(h):
+        if h is None:
+            trace_log.append((0.0, 0, 0))
+            return np.zeros(12, np.uint64), 0.0
+        m, _ = r.render_rows_end(h)
+        st = sp.last_stats()
+        trace_log.append((st.traceMs, st.traceLaunches, int(st.tracedRays)))
+        return m, st.kernelMs
 
     # ---- warm-up.  With several ranks every warm-up frame but the first is also one iteration of the
     # strip rebalancing: the cut of the next frame is made from this frame's per-row cost (nanoseconds,
@@ -612,11 +654,22 @@ def main():
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for k in range(args.steps):
-        m, _, kms, _ = render_step(frame, bounds)
-        rays += int(m[sp.sp_Metric_RaysTraced])
-        kernel_ms.append(kms)
-        frame += 1
+    if pipelined:
+        handle = None
+        for k in range(args.steps + 1):
+            nxt = step_begin(frame, bounds) if k < args.steps else None
+            frame += 1 if k < args.steps else 0
+            if k > 0:
+                m, kms = step_end(handle)
+                rays += int(m[sp.sp_Metric_RaysTraced])
+                kernel_ms.append(kms)
+            handle = nxt
+    else:
+        for k in range(args.steps):
+            m, _, kms, _ = render_step(frame, bounds)
+            rays += int(m[sp.sp_Metric_RaysTraced])
+            kernel_ms.append(kms)
+            frame += 1
     if world > 1:
         drain_gathers()
         stream.wait_stream(comm)                 # the last strips have arrived
@@ -694,7 +747,9 @@ def main():
     e2e_phases = np.zeros(4)                          # host seconds: inputs, scene build, render call, barrier
     e2e_device = np.zeros(2)                          # device ms inside the render call: kernels, whole call
 
-    def e2e_step(frame):
+    def e2e_begin(frame):
+        """First half of an end-to-end step: inputs to the device, scene re-built, the strip enqueued with its rows
+        going to host image k % 2.  With --no-pipeline the frame is also waited for here."""
         b, e = bounds[rank]
         k = e2e_counter[0]
         e2e_counter[0] += 1
@@ -707,31 +762,51 @@ def main():
         t_b = time.perf_counter()
         r.build()                                     # scene flattened and re-uploaded
         t_c = time.perf_counter()
-        m = np.zeros(12, np.uint64)
         if world > 1:
             upload_env(k + 1)                         # next step's copy goes up under this step's kernels
+        h = None
         if e > b:
-            m, _ = r.render_rows(b, e, frame=frame, host=True)   # rows -> pinned host image
+            h = r.render_rows_begin(b, e, frame=frame, host_ptr=host_images[k % 2].data_ptr())   # rows -> pinned host image
+        t_d = time.perf_counter()
+        e2e_phases[:3] += (t_b - t_a, t_c - t_b, t_d - t_c)
+        return h
+
+    def e2e_end(h):
+        """Second half: the frame is complete in host memory on every rank."""
+        t_a = time.perf_counter()
+        m = np.zeros(12, np.uint64)
+        if h is not None:
+            m, _ = r.render_rows_end(h)
             st_ = sp.last_stats()
             e2e_device[:] += (st_.kernelMs, st_.totalMs)
-        t_d = time.perf_counter()
+        t_b = time.perf_counter()
         if world > 1:
-            dist.barrier()                            # the frame is complete in host memory
-        t_e = time.perf_counter()
-        e2e_phases[:] += (t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d)
+            dist.barrier(group=host_group)            # the frame is complete in host memory
+        t_c = time.perf_counter()
+        e2e_phases[2:] += (t_b - t_a, t_c - t_b)
         return m
-    for _ in range(2):
-        e2e_step(frame)
-        frame += 1
+
+    def e2e_run(steps, frame):
+        """`steps` end-to-end frames, frame k + 1 begun before frame k is ended (two in flight) unless --no-pipeline."""
+        total = 0
+        handle = None
+        for k in range(steps + (1 if pipelined else 0)):
+            nxt = e2e_begin(frame + k) if k < steps else None
+            if not pipelined:
+                total += int(e2e_end(nxt)[sp.sp_Metric_RaysTraced])
+                continue
+            if k > 0:
+                total += int(e2e_end(handle)[sp.sp_Metric_RaysTraced])
+            handle = nxt
+        return total
+    e2e_run(2, frame)
+    frame += 2
     barrier()
     e2e_phases[:] = 0
     e2e_device[:] = 0
     t0 = time.perf_counter()
-    e2e_rays = 0
-    for k in range(args.steps):
-        m = e2e_step(frame)
-        e2e_rays += int(m[sp.sp_Metric_RaysTraced])
-        frame += 1
+    e2e_rays = e2e_run(args.steps, frame)
+    frame += args.steps
     barrier()
     e2e_secs = time.perf_counter() - t0
     if world > 1:
@@ -746,6 +821,14 @@ def main():
         dist.all_reduce(b_, op=dist.ReduceOp.SUM)
         e2e_secs, e2e_rays = float(a[0]), float(b_[1])
     e2e_value = e2e_rays / e2e_secs / 1e6
+    e2e_ranks = None
+    if world > 1:
+        mine = torch.tensor([e2e_device[0] / args.steps, e2e_device[1] / args.steps, e2e_phases[3] / args.steps * 1e3],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        e2e_ranks = [{"kernels_ms": round(float(t[0]), 3), "call_device_ms": round(float(t[1]), 3),
+                      "host_barrier_wait_ms": round(float(t[2]), 3)} for t in allr]
     scene_bytes = int(sp.lib.sp_b200_SceneDeviceBytes(r.scene))
     env_bytes = int(env_pinned.numel() * 4)
     h2d = (scene_bytes + 2048) * world + env_bytes * (1 if world > 1 else 1)
@@ -818,11 +901,15 @@ def main():
                     "rank0_host_phases_ms": dict(zip(("inputs", "scene_build", "render_call", "barrier"),
                                                      [round(float(x) / args.steps * 1e3, 4) for x in e2e_phases])),
                     "rank0_render_call_device_ms": {"kernels": round(float(e2e_device[0]) / args.steps, 4), "call": round(float(e2e_device[1]) / args.steps, 4)},
+                    "ranks": e2e_ranks,
                     "how": "per step: texture cache flushed, scene re-built and re-uploaded, environment map re-uploaded "
                            + ("(one slice per rank + NCCL all-gather over NVLink, double-buffered: step k + 1's copy goes up under step k's "
                               "kernels), rows copied by every rank into one shared pinned host image, barrier"
                               if world > 1 else "(copy stream, overlapped with coverage / candidates / first primary trace), "
-                              "rows copied to the pinned host image band by band while later bands render")},
+                              "rows copied to the pinned host image band by band while later bands render")
+                           + ("; two frames in flight (sp_b200_RenderRowsBegin / End): step k + 1's inputs, scene and launches are issued before "
+                              "step k's frame is waited for, consecutive frames go to two pinned host images"
+                              + ("; frame completion on all ranks marked by a host (gloo) barrier" if world > 1 else "") if pipelined else "")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "strips": [list(map(int, b)) for b in bounds],
         }

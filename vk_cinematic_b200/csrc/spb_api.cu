@@ -1327,7 +1327,14 @@ extern "C" void sp_b200_FlushTextureCache(void)
 {
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
-    if (L.initialized) cudaDeviceSynchronize();
+    // The host pixels may change after this call: wait until every upload issued so far has left them.  Not for
+    // the device -- a frame in flight (sp_b200_RenderRowsBegin) keeps reading its device copies, and whoever
+    // reuses a pooled buffer orders its copy behind the render stream (device_texture).
+    if (L.initialized)
+    {
+        if (L.overlapCopies) cudaEventSynchronize(L.evTextures);
+        else cudaDeviceSynchronize();
+    }
     for (auto &t : L.textures)
         if (!t.second->external) L.texturePool.push_back(std::move(t.second));
     L.textures.clear();

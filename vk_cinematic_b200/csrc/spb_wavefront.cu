@@ -835,6 +835,12 @@ __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool
         atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
 }
 
+// Escaped rays.  Every record a miss touches -- its queue entry, its ray, the vertex terms of its path, one texel
+// of the environment map, its radiance slot -- is a scattered 16- or 32-byte read behind the one before
+// (profiles/r2/s8_shade_miss_ncu_full.txt: 33 warps per issue waiting on memory, DRAM at 56 %).  The chain is
+// cut by running it two items ahead: the queue entry of item k + 2 is loaded and the ray of item k + 1
+// prefetched into L2 while item k is shaded, and item k's vertex terms are prefetched the moment its path is
+// known, in front of the direction -> texel arithmetic (two double-rounded atan2) that hides them.
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -846,21 +852,28 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
     Counters cnt = {0, 0, 0, 0};
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned rounds = (total + stride - 1) / stride;
+    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned slot = first < total ? a.missQ[first] : SPB_QUEUE_HOLE;
+    unsigned slot1 = first + stride < total && first + stride >= first ? a.missQ[first + stride] : SPB_QUEUE_HOLE;
+    if (slot1 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot1 * 2 + 1);
     for (unsigned k = 0; k < rounds; ++k)
     {
-        unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool active = i < total;
+        const unsigned i2 = (k + 2) * stride + first;
+        const unsigned slot2 = (k + 2 < rounds && i2 < total) ? a.missQ[i2] : SPB_QUEUE_HOLE;
+        const bool active = slot != SPB_QUEUE_HOLE;
         uint32_t path = 0;
-        unsigned slot = active ? a.missQ[i] : SPB_QUEUE_HOLE;
-        active = slot != SPB_QUEUE_HOLE;
         if (active)
         {
             v4f rb = rays[(size_t)slot * 2 + 1];
             path = f2u(rb.w);
+            for (int i = (int)bounce - 1; i >= 0; --i) prefetch_l2(a.pathTerms + ((size_t)i * a.pathCapacity + path) * 2);
             f3 V = neg3(mk3(rb.x, rb.y, rb.z));
             finish_path_from(a, miss_radiance<MATH, ENVFILTER>(M, V, a.clampValue, &cnt), bounce, path);
         }
         count_row(a, path, active, SPB_COST_MISS);
+        if (slot2 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot2 * 2 + 1);
+        slot = slot1;
+        slot1 = slot2;
     }
     if (a.countStats)
     {
