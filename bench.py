@@ -699,6 +699,7 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": elapsed_ms / args.steps, "kernel_ms": float(np.mean(kernel_ms)),
+                              "trace_ms": float(np.mean([t[0] for t in timed_trace])) if timed_trace else 0.0,
                               "rays_per_step": rays / args.steps, "traced_rays_per_step": traced / args.steps,
                               "launches": int(launches), "strips": [list(map(int, b)) for b in bounds],
                               "ranks": per_rank, "rebalance_history": history}), file=RESULT_OUT, flush=True)

@@ -118,6 +118,7 @@ struct FrameState
     size_t traceEventsUsed = 0;
     uint32_t *coveredPinned = nullptr; // pinned words the asynchronous read-back of the coverage pass lands in
     bool coverSpeculated = false;      // render_wavefront ran on the cached covered-block count
+    uint32_t specCovered = 0, specHash = 0; // ... namely these (the cache itself may belong to a later frame's strip by the time this one ends)
     DeviceBuffer image;
     // pinned landing zones of the frame's counters (device counters + per-tile-row cost; wave counters)
     unsigned long long *hostCounters = nullptr;
@@ -797,6 +798,8 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     {
         covered = cc.covered;
         L.f->coverSpeculated = true;
+        L.f->specCovered = cc.covered;
+        L.f->specHash = cc.listHash;
     }
     else
     {
@@ -883,7 +886,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             SPB_CUDA(cudaMemcpyAsync(&bandLast[b], list + last, 4, cudaMemcpyDeviceToHost, L.stream));
         }
         SPB_CUDA(cudaStreamSynchronize(L.stream));
-        if (L.f->coverSpeculated && (L.f->coveredPinned[0] != cc.covered || L.f->coveredPinned[1] != cc.listHash))
+        if (L.f->coverSpeculated && (L.f->coveredPinned[0] != L.f->specCovered || L.f->coveredPinned[1] != L.f->specHash))
         {
             // (the stream has just been waited for: the fresh count is here already and differs from the cached one)
             cc.valid = false;
@@ -2139,6 +2142,7 @@ struct PendingFrame
     f32 *hostPixels = nullptr;
     v4f *image = nullptr;
     unsigned long long *ctr = nullptr; // device counters of the frame
+    sp_Scene *sceneHandle = nullptr;
     size_t cCount = 0, waveCount = 0;
     std::vector<unsigned long long> c; // (only when the counters do not fit the pinned landing zone)
     std::vector<uint32_t> waveCounters;
@@ -2219,6 +2223,7 @@ static int render_rows_begin(sp_Context *ctx, u32 rowBegin, u32 rowEnd, u32 fram
     P.hostPixels = hostPixels;
     P.image = image;
     P.ctr = ctr;
+    P.sceneHandle = ctx->scene;
     P.cCount = CTR_COUNT + (size_t)tileRows * 2;
     P.waveCounters.clear();
     SPB_CUDA(cudaEventRecord(F->evKernel0, L.stream));
@@ -2266,8 +2271,10 @@ static int render_rows_end(FrameState *F, sp_Metrics *metrics, u64 *tileRowCost)
     const u32 rowBegin = P.rowBegin, rowEnd = P.rowEnd, tileRows = P.tileRows;
     SPB_CUDA(cudaEventSynchronize(F->evEnd));
     if (P.rowsStreamed) SPB_CUDA(cudaEventSynchronize(F->evCopyDone));
-    if (wavefront && F->coverSpeculated && (F->coveredPinned[0] != L.coverCache.covered || F->coveredPinned[1] != L.coverCache.listHash))
+    if (wavefront && F->coverSpeculated && (F->coveredPinned[0] != F->specCovered || F->coveredPinned[1] != F->specHash))
     {
+        // (the scene may have been rebuilt since Begin: the arrays the frame was launched on are freed behind it)
+        if (P.sceneHandle) P.args.scene = launch_scene(find_scene(P.sceneHandle));
         // the frame was launched on a stale covered-block count / block list (the scene's arrays were
         // rewritten in place, or something this cache's key does not see): render it again on the fresh one
         L.coverCache.valid = false;

@@ -750,11 +750,18 @@ static int load_exr_image(HdrImage *image, const char *path)
         tilesY = (size_t)((height + tileH - 1) / tileH);
     }
     const size_t chunks = tiled ? tilesX * tilesY : (size_t)((height + linesPerBlock - 1) / linesPerBlock);
+    // The header alone must not size anything: the offset table has to fit in what is left of the file, and the
+    // image in what a file of this size could hold at all (RLE, the densest coding read here, expands a run of
+    // 2 bytes to at most 128; a crafted 65536 x 65536 header would otherwise ask for 64 GiB before a byte is read).
+    if (b.at > file.size() || chunks > (file.size() - b.at) / 8) return 1;
+    if ((uint64_t)width * (uint64_t)height * bytesPerPixel / 64 > (uint64_t)file.size()) return 1;
     std::vector<uint64_t> offsets(chunks);
     for (size_t i = 0; i < chunks; ++i) offsets[i] = b.u64();
     if (!b.ok) return 1;
     float *out = (float *)calloc((size_t)width * (size_t)height * 4, sizeof(float)); // free()d by the caller
     if (!out) return 1;
+    std::vector<std::atomic<uint8_t>> claimed(chunks); // one owner per block of rows / tile
+    for (auto &c : claimed) c.store(0);
     // chunks are independent (own pixels of the output): decoded by up to 8 threads
     auto decode_chunk = [&](size_t i, std::vector<uint8_t> &raw, std::vector<uint8_t> &tmp) -> bool
     {
@@ -770,6 +777,7 @@ static int load_exr_image(HdrImage *image, const char *path)
         {
             uint32_t tx = c.u32(), ty = c.u32(), lx = c.u32(), ly = c.u32();
             if (!c.ok || lx != 0 || ly != 0 || tx >= tilesX || ty >= tilesY) return false;
+            if (claimed[(size_t)ty * tilesX + tx].exchange(1) != 0) return false;
             bx = (int64_t)tx * tileW;
             by = (int64_t)ty * tileH;
             bw = std::min<int64_t>(tileW, width - bx);
@@ -780,6 +788,9 @@ static int load_exr_image(HdrImage *image, const char *path)
             int32_t y = (int32_t)c.u32();
             if (!c.ok || y < dw[1] || y > dw[3]) return false;
             by = (int64_t)y - dw[1];
+            // (blocks start on multiples of linesPerBlock: two chunks of a crafted file must not cover the same
+            // rows -- the decoding threads own disjoint rows of `out`)
+            if (by % linesPerBlock != 0 || claimed[(size_t)(by / linesPerBlock)].exchange(1) != 0) return false;
             lines = std::min<int64_t>(linesPerBlock, height - by);
         }
         uint32_t dataSize = c.u32();

@@ -795,15 +795,18 @@ SPB_HD void trav_world_ray(const v4f *ray, f3 &wo, f3 &wd)
 
 // Pops until there is an entry to process (st.cur), the walk inside an object ends
 // (SPB_NODE_EXIT) or the query ends (SPB_NODE_DONE).
-template <bool CULL, class STK>
+// SINGLE (here and in the steps below): the walk is known to be inside the one object of a single-object
+// scene from its first step to its last (trav_begin_single) -- the stack base is 0, an empty stack is the
+// end of the object, and a leaf is always a triangle; the trace kernel is compiled once for such scenes.
+template <bool CULL, bool SINGLE = false, class STK>
 SPB_HD void trav_pop(Trav &st, STK stack)
 {
     for (;;)
     {
-        int base = st.blasBase >= 0 ? st.blasBase : 0;
+        int base = SINGLE ? 0 : (st.blasBase >= 0 ? st.blasBase : 0);
         if (st.sp == base)
         {
-            st.cur = st.blasBase < 0 ? SPB_NODE_DONE : SPB_NODE_EXIT;
+            st.cur = (SINGLE || st.blasBase >= 0) ? SPB_NODE_EXIT : SPB_NODE_DONE;
             return;
         }
         st.sp--;
@@ -938,7 +941,7 @@ SPB_HD void trav_node_fetch(const DScene &S, bool take, uint32_t cur, NodeData &
     ld8(n + 6, nd.refsf, nd.meta);
 }
 // NODE step on fetched data: st.cur is the node index nd was fetched for.
-template <bool CULL, class STK>
+template <bool CULL, bool SINGLE = false, class STK>
 SPB_HD void trav_node_apply(const DScene &S, Trav &st, STK stack, Counters *counters, const NodeData &nd)
 {
     const float inf = u2f(0x7F800000u);
@@ -1000,10 +1003,10 @@ SPB_HD void trav_node_apply(const DScene &S, Trav &st, STK stack, Counters *coun
         st.cur = r0;
         return;
     }
-    trav_pop<CULL>(st, stack);
+    trav_pop<CULL, SINGLE>(st, stack);
 }
 // NODE step: st.cur is a node index.
-template <bool CULL, class STK>
+template <bool CULL, bool SINGLE = false, class STK>
 SPB_HD void trav_node(const DScene &S, Trav &st, STK stack, Counters *counters)
 {
     NodeData nd;
@@ -1012,17 +1015,17 @@ SPB_HD void trav_node(const DScene &S, Trav &st, STK stack, Counters *counters)
     ld8(n + 2, nd.minz, nd.maxx);
     ld8(n + 4, nd.maxy, nd.maxz);
     ld8(n + 6, nd.refsf, nd.meta);
-    trav_node_apply<CULL>(S, st, stack, counters, nd);
+    trav_node_apply<CULL, SINGLE>(S, st, stack, counters, nd);
 }
 
 // LEAF step: st.cur is SPB_REF_LEAF | slot.
-template <bool CULL, class STK>
+template <bool CULL, bool SINGLE = false, class STK>
 SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, STK stack,
                       Counters *counters)
 {
     const float inf = u2f(0x7F800000u);
     uint32_t index = st.cur & ~SPB_REF_LEAF;
-    if (st.blasBase >= 0)
+    if (SINGLE || st.blasBase >= 0)
     {
         // a triangle whose own box the ray passes (sp_scene.cpp:161-196)
         const v4f *tp = S.tris + (size_t)index * 3;
@@ -1074,7 +1077,7 @@ SPB_HD void trav_leaf(const DScene &S, Trav &st, TravCold &c, const v4f *ray, ST
             return;
         }
     }
-    trav_pop<CULL>(st, stack);
+    trav_pop<CULL, SINGLE>(st, stack);
 }
 
 // Barycentrics of the winning triangle, recomputed from the same inputs with the same code the

@@ -159,7 +159,7 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
 // Registers hold what a node step touches (12 test constants, cull distance, current entry, stack
 // pointer, object); the rest of a lane's state is a 25-word record in shared memory, word-major so
 // that the lanes of a warp hit 32 different banks.
-template <bool CULL, bool STATS, int MODE>
+template <bool CULL, bool STATS, int MODE, bool SINGLE>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
@@ -404,6 +404,15 @@ __device__ __forceinline__ TravEntry stack_get(const HybridStack &s, int sp)
 
 // Primary ray of item `idx` resolved from its pixel's candidate list (spb_core.cuh
 // resolve_from_candidates); leaves the lane finished, or untouched when the pixel falls back.
+#ifndef SPB_VOTE_CLASSES
+#define SPB_VOTE_CLASSES 4
+#endif
+#ifndef SPB_EXIT_WEIGHT
+#define SPB_EXIT_WEIGHT 1 // (measured on C5, profiles/r2/s15_*: 182.4 ms per frame with 1, 191.4 with 2, 195.8 with 4; two classes 196.3)
+#endif
+#ifndef SPB_VOTE_BUSY_EXIT
+#define SPB_VOTE_BUSY_EXIT 0
+#endif
 template <bool CULL>
 __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsigned idx, f3 o, f3 d, Trav &st,
                                                         TravCold &cold, Counters *counters)
@@ -426,7 +435,7 @@ __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsig
 // with all 32 lanes; RESUME -- the second launch of such a step: lanes are refilled from the continuation
 // buffer, so the stragglers of many packets walk on together instead of alone in their warps.  The walk
 // of a ray is the same sequence of steps either way (spb_core.cuh trav_*), hence the same result.
-template <bool CULL, bool STATS, int MODE>
+template <bool CULL, bool STATS, int MODE, bool SINGLE>
 __global__ void __launch_bounds__(SPB_TRACE_THREADS, SPB_TRACE_MIN_BLOCKS)
 k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 {
@@ -438,13 +447,15 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
     uint32_t *cursor = &ctr[RESUME ? WCTR_CONT_CURSOR : WCTR_CURSOR];
     v4f *rays = a.rays[bounce & 1u];
 #if defined(SPB_NO_FUSED_ENTRY)
-    const bool single = false; // (A/B build: round 1's behaviour)
+    constexpr bool single = false; // (A/B build: round 1's behaviour; SINGLE is never set, launch_wave_trace)
 #else
     // Single-object scenes (C1-C4): the object is entered when the ray starts and left when it
     // retires, both with every lane of the warp busy, instead of through three more rounds of the
     // step loop (TLAS root, object entry, exit) at whatever lane count the votes give them.
     // Measured on C3: 64.1 ms per frame against 68.2 without (profiles/r2/s6_ab_first_machine_fused_entry.txt).
-    const bool single = a.scene.objectCount == 1;
+    // The kernel is compiled once for such scenes (SINGLE; launch_wave_trace picks it): the steps below then
+    // carry no object entry, no exit and no stack base (spb_core.cuh trav_pop / trav_leaf).
+    constexpr bool single = SINGLE;
 #endif
 
     // per-lane stack in local memory; state that is touched only when an object is entered or
@@ -501,7 +512,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                         v4u q;
                         q.x = slot; q.y = st.cur; q.z = f2u(st.tcull); q.w = f2u(st.lT);
                         rec[0] = q;
-                        q.x = st.lSlot; q.y = (uint32_t)st.sp | ((uint32_t)(st.blasBase + 1) << 16); q.z = f2u(cold.worldCull); q.w = cold.object;
+                        q.x = st.lSlot; q.y = (uint32_t)st.sp | ((uint32_t)((SINGLE ? 0 : st.blasBase) + 1) << 16); q.z = f2u(cold.worldCull); q.w = cold.object;
                         rec[1] = q;
                         q.x = f2u(cold.bT); q.y = cold.bSlot; q.z = (uint32_t)cold.bObject; q.w = 0;
                         rec[2] = q;
@@ -603,7 +614,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                         }
                         f3 wo, wd;
                         trav_world_ray(rays + (size_t)slot * 2, wo, wd);
-                        if (st.blasBase >= 0)
+                        if (SINGLE || st.blasBase >= 0)
                         {
                             m4 invModel = load_m4(a.scene.objInv + (size_t)cold.object * 4);
                             st.o = xform(invModel, wo, 1.0f);
@@ -691,12 +702,12 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             unsigned leafMask = walking & ~nodeMask;
             if (__popc(nodeMask) >= __popc(leafMask))
             {
-                if (wantNode) trav_node_apply<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
+                if (wantNode) trav_node_apply<CULL, SINGLE>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
             }
             else
             {
                 if (wantLeaf)
-                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                    trav_leaf<CULL, SINGLE>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
@@ -714,12 +725,12 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
         {
             if (__popc(nodeMask) >= __popc(walking & ~nodeMask))
             {
-                if (wantNode) trav_node_apply<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
+                if (wantNode) trav_node_apply<CULL, SINGLE>(a.scene, st, stack, STATS ? &cnt : nullptr, nd);
             }
             else
             {
                 if (live && !wantNode)
-                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                    trav_leaf<CULL, SINGLE>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
             }
             live = have && trav_is_walking(st);
             wantNode = live && trav_is_node(st);
@@ -728,6 +739,49 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             nodeMask = __ballot_sync(SPB_FULL, wantNode);
         } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
 #else
+#if SPB_VOTE_CLASSES == 4
+        // Several objects: four kinds of step -- node visit, triangle test, object entry, object exit -- and the
+        // warp runs the one most of its lanes wait for (an exit counts SPB_EXIT_WEIGHT times: it is the
+        // cheapest step and gives a lane back to the other three).  With two classes (node / leaf) an entry and
+        // a triangle test in the same leaf step ran one after the other, and a lane whose object had ended idled
+        // until the warp went round the outer loop.
+        if (!SINGLE)
+        {
+            do
+            {
+                const bool live = have && trav_is_walking(st);
+                const bool wantNode = live && trav_is_node(st);
+                const bool inObject = st.blasBase >= 0;
+                const bool wantTri = live && !wantNode && inObject;
+                const bool wantEnter = live && !wantNode && !inObject;
+                const bool wantExit = have && st.cur == SPB_NODE_EXIT;
+                const int n = __popc(__ballot_sync(SPB_FULL, wantNode)), t = __popc(__ballot_sync(SPB_FULL, wantTri)),
+                          e = __popc(__ballot_sync(SPB_FULL, wantEnter)), x = __popc(__ballot_sync(SPB_FULL, wantExit)) * SPB_EXIT_WEIGHT;
+                if (n >= t && n >= e && n >= x)
+                {
+                    if (wantNode) trav_node<CULL, false>(a.scene, st, stack, STATS ? &cnt : nullptr);
+                }
+                else if (t >= e && t >= x)
+                {
+                    if (wantTri) trav_leaf<CULL, false>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                }
+                else if (e >= x)
+                {
+                    if (wantEnter) trav_leaf<CULL, false>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                }
+                else
+                {
+                    if (wantExit) trav_exit<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack);
+                }
+#if SPB_VOTE_BUSY_EXIT
+                walking = __ballot_sync(SPB_FULL, have && st.cur <= SPB_NODE_EXIT); // (a lane about to leave its object has work in this loop)
+#else
+                walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
+#endif
+            } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
+            continue;
+        }
+#endif
         do
         {
             const bool live = have && trav_is_walking(st);
@@ -737,12 +791,12 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             unsigned leafMask = walking & ~nodeMask;
             if (__popc(nodeMask) >= __popc(leafMask))
             {
-                if (wantNode) trav_node<CULL>(a.scene, st, stack, STATS ? &cnt : nullptr);
+                if (wantNode) trav_node<CULL, SINGLE>(a.scene, st, stack, STATS ? &cnt : nullptr);
             }
             else
             {
                 if (wantLeaf)
-                    trav_leaf<CULL>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
+                    trav_leaf<CULL, SINGLE>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
             }
             walking = __ballot_sync(SPB_FULL, have && trav_is_walking(st));
         } while (walking && ((unsigned)__popc(walking) >= a.refillThreshold || (exhausted && !EVICT)));
@@ -841,6 +895,9 @@ __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool
 // cut by running it two items ahead: the queue entry of item k + 2 is loaded and the ray of item k + 1
 // prefetched into L2 while item k is shaded, and item k's vertex terms are prefetched the moment its path is
 // known, in front of the direction -> texel arithmetic (two double-rounded atan2) that hides them.
+#ifndef SPB_MISS_PREFETCH
+#define SPB_MISS_PREFETCH 0 // (measured on C3, profiles/r2/s15_*: 57.5 ms per frame with 0, 58.1 with 1, 57.6 with 2, 58.6 with 3)
+#endif
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -853,27 +910,38 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned rounds = (total + stride - 1) / stride;
     const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+#if SPB_MISS_PREFETCH & 1
     unsigned slot = first < total ? a.missQ[first] : SPB_QUEUE_HOLE;
     unsigned slot1 = first + stride < total && first + stride >= first ? a.missQ[first + stride] : SPB_QUEUE_HOLE;
     if (slot1 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot1 * 2 + 1);
+#endif
     for (unsigned k = 0; k < rounds; ++k)
     {
+#if SPB_MISS_PREFETCH & 1
         const unsigned i2 = (k + 2) * stride + first;
         const unsigned slot2 = (k + 2 < rounds && i2 < total) ? a.missQ[i2] : SPB_QUEUE_HOLE;
+#else
+        const unsigned i = k * stride + first;
+        const unsigned slot = i < total ? a.missQ[i] : SPB_QUEUE_HOLE;
+#endif
         const bool active = slot != SPB_QUEUE_HOLE;
         uint32_t path = 0;
         if (active)
         {
             v4f rb = rays[(size_t)slot * 2 + 1];
             path = f2u(rb.w);
+#if SPB_MISS_PREFETCH & 2
             for (int i = (int)bounce - 1; i >= 0; --i) prefetch_l2(a.pathTerms + ((size_t)i * a.pathCapacity + path) * 2);
+#endif
             f3 V = neg3(mk3(rb.x, rb.y, rb.z));
             finish_path_from(a, miss_radiance<MATH, ENVFILTER>(M, V, a.clampValue, &cnt), bounce, path);
         }
         count_row(a, path, active, SPB_COST_MISS);
+#if SPB_MISS_PREFETCH & 1
         if (slot2 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot2 * 2 + 1);
         slot = slot1;
         slot1 = slot2;
+#endif
     }
     if (a.countStats)
     {
@@ -1274,13 +1342,13 @@ k_sky_listed(const __grid_constant__ WaveArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool CULL, bool STATS, int MODE>
+template <bool CULL, bool STATS, int MODE, bool SINGLE>
 static void launch_trace_t(const WaveArgs &a, uint32_t bounce, unsigned grid, cudaStream_t stream)
 {
-    k_trace<CULL, STATS, MODE><<<grid, SPB_TRACE_THREADS, 0, stream>>>(a, bounce);
+    k_trace<CULL, STATS, MODE, SINGLE><<<grid, SPB_TRACE_THREADS, 0, stream>>>(a, bounce);
 }
 
-template <bool CULL, bool STATS, int MODE>
+template <bool CULL, bool STATS, int MODE, bool SINGLE>
 static unsigned trace_grid_t()
 {
     static unsigned cached = 0;
@@ -1289,7 +1357,7 @@ static unsigned trace_grid_t()
         int device = 0, sms = 0, perSm = 0;
         cudaGetDevice(&device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, MODE>, SPB_TRACE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<CULL, STATS, MODE, SINGLE>, SPB_TRACE_THREADS, 0);
         if (perSm < 1) perSm = 1;
         cached = (unsigned)(sms * perSm); // persistent: every CTA resident, a multiple of the SM count
         // every warp in flight may leave one partly filled chunk in each queue: the slack the queues
@@ -1336,7 +1404,13 @@ void launch_wave_trace(const KernelConfig &cfg, const WaveArgs &a, uint32_t boun
     if (mode == SPB_TRACE_RESUME) return;
 #endif
     g_kernelLaunches++;
-#define SPB_CALL(C, S, M) launch_trace_t<C, S, M>(a, bounce, trace_grid_t<C, S, M>(), stream)
+#if defined(SPB_TRAV2) || defined(SPB_NO_FUSED_ENTRY)
+    const bool one = false;
+#else
+    const bool one = a.scene.objectCount == 1; // (C1-C4: the kernel without object entry / exit in its steps)
+#endif
+#define SPB_CALL(C, S, M) (one ? launch_trace_t<C, S, M, true>(a, bounce, trace_grid_t<C, S, M, true>(), stream) \
+                               : launch_trace_t<C, S, M, false>(a, bounce, trace_grid_t<C, S, M, false>(), stream))
     SPB_TRACE_DISPATCH(SPB_CALL);
 #undef SPB_CALL
 }
