@@ -378,7 +378,8 @@ void sp_b200_SetCopyOverlap(int enable);
 void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u32 width, u32 height, void *readyEvent);
 /* Wavefront mode tuning: a warp of the trace kernel retires and refills its lanes when fewer than
  * this many are still walking (1 = the whole warp starts and ends together), for primary rays,
- * direction-sorted bounce rays and all other rays; 0 keeps the default (1, 1, 12). */
+ * direction-sorted bounce rays and all other rays; 0 keeps the default (1; measured choice of 1 or 12 per
+ * scene; 12 for one object, 16 for several). */
 void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
 /* Wavefront mode tuning: straggler eviction of the bounce traces.  A warp of the trace kernel walks a
  * packet of 32 rays; the rays of a packet end at different times, and the last few would keep the warp
@@ -387,7 +388,8 @@ void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
  * starts the next packet; a second launch of the kernel refills its lanes from the parked records, so the
  * stragglers of many packets walk on together.  Every ray takes the same sequence of traversal steps
  * either way: results are bit-identical.  `sorted`: threshold for the direction-sorted launch (the first
- * bounce), `other`: for the later bounces; 0 = off (then sp_b200_SetRefillThresholds applies). */
+ * bounce), `other`: for the later bounces; 0 = off (then sp_b200_SetRefillThresholds applies).  Until this is
+ * called the thresholds follow the scene: 8 / off for one object, 16 / 16 for several (measured on C3 and C5). */
 void sp_b200_SetStragglerEviction(u32 sorted, u32 other);
 /* `count` draws of the reference's XorShift32 (math_utils.h:184-196) continuing *state (host side,
  * integer only): what seeded inputs like the reference's perf tests' are generated from. */

@@ -218,7 +218,12 @@ struct Sim
                 unsigned blocked = p.speculate ? nwalk - nodeLanes : leafLanes;
                 t.walkHist[nwalk]++;
                 t.add(w.vote, 32);
-                if (nodeLanes + p.voteBias >= blocked && nodeLanes)
+                // (voteBias 1000: the step that leaves the fewest lane-slots idle -- cost x (32 - lanes) -- instead of the one with more lanes;
+                //  1001: the same with equal costs, i.e. the plain majority but without the preference for nodes on a tie)
+                const bool chooseNode = p.voteBias == 1000 ? (nodeLanes && (!blocked || w.node * (32 - nodeLanes) <= w.leaf * (32 - blocked)))
+                                        : p.voteBias == 1001 ? (nodeLanes && nodeLanes > blocked)
+                                                             : (nodeLanes + p.voteBias >= blocked && nodeLanes);
+                if (chooseNode)
                 {
                     unsigned pops = 0;
                     {

@@ -152,6 +152,8 @@ struct TextureEntry
     ~TextureEntry() { buffer.release(); }
 };
 
+#define SPB_EVICT_AUTO 0xFFFFFFFFu // (eviction threshold chosen by scene: evict_below())
+
 struct Library
 {
     std::recursive_mutex mutex;
@@ -171,11 +173,11 @@ struct Library
     // 0 for the sorted class = measured choice between packet mode (1) and SPB_REFILL_THRESHOLD:
     // packets win when a tile's sorted rays are coherent (C3: one 8x4 block, 64 spp: -6 % frame
     // time), and lose on scenes of sub-pixel triangles (C5: +11 %).
-    uint32_t refillThreshold[3] = {1, 0, SPB_REFILL_THRESHOLD};
+    uint32_t refillThreshold[3] = {1, 0, 0}; // primary, sorted (0: measured), other (0: refill_other())
     // straggler eviction of the bounce traces (sp_b200_SetStragglerEviction): a packet of the direction-sorted
     // launch [0] / of the later launches [1] whose walking lanes drop below this many parks them in the
     // continuation buffer and a second launch walks the parked rays on, compacted; 0 = off
-    uint32_t evictBelow[2] = {8, 0};
+    uint32_t evictBelow[2] = {SPB_EVICT_AUTO, SPB_EVICT_AUTO}; // sorted, other launches (AUTO: by scene, evict_below())
     struct SortedTuner
     {
         unsigned long long signature = 0;
@@ -696,6 +698,25 @@ DeviceScene *mesh_device_scene(const std::shared_ptr<MeshAccel> &accel, uint32_t
     return (DeviceScene *)accel->deviceScene;
 }
 
+// Refill threshold of the unsorted bounce launches: a warp goes back to the queue when fewer lanes than this still
+// have work.  Measured: 12 for one object (round 1), 16 for several (C5 with the four-class vote: 168.8 ms per
+// frame against 171.8 with 12 and 173.0 with 8; profiles/r2/s16_ab_c5_vote_thresholds.txt).
+// Straggler eviction thresholds (0: off) of the sorted (k = 0) and the other (k = 1) bounce launches.  Measured: one
+// object 8 / off (C3 60.1 -> 58.8 ms, profiles/r2/s9_*); several objects 16 / 16 (C5 170.0 -> 165.5 ms against 8 / off,
+// 167.8 with 12 / off, 171.7 with off / 12; profiles/r2/s17_*).
+static uint32_t evict_below(int k, uint32_t objectCount)
+{
+    Library &L = lib();
+    if (L.evictBelow[k] != SPB_EVICT_AUTO) return L.evictBelow[k];
+    return objectCount > 1 ? 16u : (k == 0 ? 8u : 0u);
+}
+static uint32_t refill_other(uint32_t objectCount)
+{
+    Library &L = lib();
+    if (L.refillThreshold[2]) return L.refillThreshold[2];
+    return objectCount > 1 ? 16u : SPB_REFILL_THRESHOLD;
+}
+
 // Wavefront render of args' rectangle (the strip).  A coverage pass marks the 8x4 pixel blocks some
 // triangle may project into; the pixels of all other blocks go to the sky kernel (one thread per
 // pixel, no queues).  The covered blocks are rendered in bands of consecutive list entries, a band
@@ -960,7 +981,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     const bool tuning = a.sortPrimaryHits && L.refillThreshold[1] == 0 && tn.choice < 0;
 
     // continuation buffer of the evicting launches: half the ray slots (a launch that fills it stops evicting)
-    const bool evicting = L.evictBelow[0] || L.evictBelow[1];
+    const bool evicting = evict_below(0, ra.scene.objectCount) || evict_below(1, ra.scene.objectCount);
     a.cont = nullptr;
     a.contCapacity = 0;
     if (evicting)
@@ -986,7 +1007,7 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
             const uint32_t keep = a.refillThreshold;
             a.refillThreshold = evictBelow;
             launch_wave_trace(cfg, a, bounce, SPB_TRACE_EVICT, L.stream);
-            a.refillThreshold = L.refillThreshold[2];
+            a.refillThreshold = refill_other(a.scene.objectCount);
             launch_wave_trace(cfg, a, bounce, SPB_TRACE_RESUME, L.stream);
             a.refillThreshold = keep;
         }
@@ -1041,13 +1062,13 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
                 else launch_wave_shade(cfg, a, b, L.stream);
                 if (b + 1 >= bounces) break;
                 int probe = -1;
-                const uint32_t evictBelow = L.evictBelow[sortedNext ? 0 : 1];
+                const uint32_t evictBelow = evict_below(sortedNext ? 0 : 1, ra.scene.objectCount);
                 if (evictBelow)
                 {
                     timed_trace(b + 1, false, evictBelow);
                     continue;
                 }
-                if (!sortedNext) a.refillThreshold = L.refillThreshold[2];
+                if (!sortedNext) a.refillThreshold = refill_other(a.scene.objectCount);
                 else if (L.refillThreshold[1]) a.refillThreshold = L.refillThreshold[1];
                 else if (tn.choice >= 0) a.refillThreshold = kCandidates[tn.choice];
                 else
@@ -1407,7 +1428,7 @@ extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
     Library &L = lib();
     L.refillThreshold[0] = primary ? primary : 1;
     L.refillThreshold[1] = sorted; // 0: measured
-    L.refillThreshold[2] = other ? other : SPB_REFILL_THRESHOLD;
+    L.refillThreshold[2] = other; // 0: by scene (refill_other)
 }
 
 extern "C" void sp_b200_SetStragglerEviction(u32 sorted, u32 other)

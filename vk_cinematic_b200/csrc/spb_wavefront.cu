@@ -25,6 +25,7 @@
 // the per-pixel kernel and to the oracle in deterministic-math mode.
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 
@@ -410,8 +411,11 @@ __device__ __forceinline__ TravEntry stack_get(const HybridStack &s, int sp)
 #ifndef SPB_EXIT_WEIGHT
 #define SPB_EXIT_WEIGHT 1 // (measured on C5, profiles/r2/s15_*: 182.4 ms per frame with 1, 191.4 with 2, 195.8 with 4; two classes 196.3)
 #endif
+#ifndef SPB_VOTE_POLICY
+#define SPB_VOTE_POLICY 0
+#endif
 #ifndef SPB_VOTE_BUSY_EXIT
-#define SPB_VOTE_BUSY_EXIT 0
+#define SPB_VOTE_BUSY_EXIT 1 // (C5: 171.8 ms per frame against 181.4 without; profiles/r2/s16_ab_c5_vote_thresholds.txt)
 #endif
 template <bool CULL>
 __device__ __forceinline__ void primary_from_candidates(const WaveArgs &a, unsigned idx, f3 o, f3 d, Trav &st,
@@ -757,15 +761,25 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                 const bool wantExit = have && st.cur == SPB_NODE_EXIT;
                 const int n = __popc(__ballot_sync(SPB_FULL, wantNode)), t = __popc(__ballot_sync(SPB_FULL, wantTri)),
                           e = __popc(__ballot_sync(SPB_FULL, wantEnter)), x = __popc(__ballot_sync(SPB_FULL, wantExit)) * SPB_EXIT_WEIGHT;
-                if (n >= t && n >= e && n >= x)
+#if SPB_VOTE_POLICY == 1
+                // (A/B) the step that leaves the fewest lane-slots idle: cost x (32 - lanes), costs in SASS instructions
+                const int wn = n ? 145 * (32 - n) : 0x7FFFFFFF, wt = t ? 110 * (32 - t) : 0x7FFFFFFF,
+                          we = e ? 250 * (32 - e) : 0x7FFFFFFF, wx = x ? 90 * (32 - x) : 0x7FFFFFFF;
+                const bool pickNode = wn <= wt && wn <= we && wn <= wx, pickTri = !pickNode && wt <= we && wt <= wx,
+                           pickEnter = !pickNode && !pickTri && we <= wx;
+#else
+                const bool pickNode = n >= t && n >= e && n >= x, pickTri = !pickNode && t >= e && t >= x,
+                           pickEnter = !pickNode && !pickTri && e >= x;
+#endif
+                if (pickNode)
                 {
                     if (wantNode) trav_node<CULL, false>(a.scene, st, stack, STATS ? &cnt : nullptr);
                 }
-                else if (t >= e && t >= x)
+                else if (pickTri)
                 {
                     if (wantTri) trav_leaf<CULL, false>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
                 }
-                else if (e >= x)
+                else if (pickEnter)
                 {
                     if (wantEnter) trav_leaf<CULL, false>(a.scene, st, cold, rays + (size_t)slot * 2, stack, STATS ? &cnt : nullptr);
                 }
@@ -789,7 +803,13 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             const bool wantLeaf = live && !wantNode;
             unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
             unsigned leafMask = walking & ~nodeMask;
-            if (__popc(nodeMask) >= __popc(leafMask))
+#if SPB_VOTE_POLICY == 1
+            // (A/B) 145 (32 - n) <= 110 (32 - l): the step that leaves fewer lane-slots idle (tools/warpsim: -2 % warp instructions)
+            const bool pickNode = nodeMask && (!leafMask || 29 * __popc(nodeMask) - 22 * __popc(leafMask) >= 224);
+#else
+            const bool pickNode = __popc(nodeMask) >= __popc(leafMask);
+#endif
+            if (pickNode)
             {
                 if (wantNode) trav_node<CULL, SINGLE>(a.scene, st, stack, STATS ? &cnt : nullptr);
             }
@@ -898,6 +918,8 @@ __device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool
 #ifndef SPB_MISS_PREFETCH
 #define SPB_MISS_PREFETCH 0 // (measured on C3, profiles/r2/s15_*: 57.5 ms per frame with 0, 58.1 with 1, 57.6 with 2, 58.6 with 3)
 #endif
+// (occupancy, measured on C3, profiles/r2/s18_*: 40 registers = 6 CTAs per SM as compiled here; forced to 7 / 8 CTAs
+//  (36 / 32 registers, spills) the frame takes 1.3 / 1.8 ms longer, at 56-64 registers (4 CTAs) 0.9 ms longer)
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -1428,31 +1450,61 @@ static unsigned shade_grid()
     return cached;
 }
 
+// Grid of a grid-stride shading kernel: every CTA resident at once (SM count x the kernel's own occupancy), so that
+// all of them run for the whole launch.  With the fixed 8 CTAs per SM a kernel compiled to 40 registers (6 resident)
+// ran 1.33 waves: the last third of its CTAs alone on the GPU, at a third of the memory-level parallelism a
+// latency-bound kernel lives on.  (SPB_RESIDENT_SHADE_GRIDS 0: the fixed grid; 1: k_shade_miss only; 2: the hit kernels too.)
+#ifndef SPB_RESIDENT_SHADE_GRIDS
+#define SPB_RESIDENT_SHADE_GRIDS 2
+#endif
+template <class K>
+static unsigned resident_grid(K kernel, int level)
+{
+    if (SPB_RESIDENT_SHADE_GRIDS < level) return shade_grid();
+    // (per thread: a Library is driven by one thread, and every device of a multi-device host has its own)
+    static thread_local std::map<const void *, unsigned> cache;
+    unsigned &grid = cache[(const void *)kernel];
+    if (!grid)
+    {
+        int device = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, 256, 0);
+        if (perSm < 1) perSm = 1;
+        grid = (unsigned)(sms * perSm);
+    }
+    return grid;
+}
+
+#define SPB_SHADE_LAUNCH(MISS, HIT)                                                                   \
+    do {                                                                                              \
+        MISS<<<resident_grid(MISS, 1), 256, 0, stream>>>(a, bounce);                                  \
+        HIT<<<resident_grid(HIT, 2), 256, 0, stream>>>(a, bounce);                                    \
+    } while (0)
+
 void launch_wave_shade(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, cudaStream_t stream)
 {
     g_kernelLaunches += 2;
-    unsigned grid = shade_grid();
     int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
     switch (key)
     {
-    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
-    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
-    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
-    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 0: SPB_SHADE_LAUNCH((k_shade_miss<0, 0>), (k_shade_hit<0, 0>)); break;
+    case 1: SPB_SHADE_LAUNCH((k_shade_miss<0, 1>), (k_shade_hit<0, 1>)); break;
+    case 2: SPB_SHADE_LAUNCH((k_shade_miss<1, 0>), (k_shade_hit<1, 0>)); break;
+    default: SPB_SHADE_LAUNCH((k_shade_miss<1, 1>), (k_shade_hit<1, 1>)); break;
     }
 }
 
 void launch_wave_shade_sorted(const KernelConfig &cfg, const WaveArgs &a, uint32_t bounce, cudaStream_t stream)
 {
     g_kernelLaunches += 2;
-    unsigned grid = shade_grid();
     int key = (cfg.math ? 2 : 0) | (cfg.envFilter ? 1 : 0);
     switch (key)
     {
-    case 0: k_shade_miss<0, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<0, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
-    case 1: k_shade_miss<0, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<0, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
-    case 2: k_shade_miss<1, 0><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<1, 0><<<grid, 256, 0, stream>>>(a, bounce); break;
-    default: k_shade_miss<1, 1><<<grid, 256, 0, stream>>>(a, bounce); k_shade_hit_tiles<1, 1><<<grid, 256, 0, stream>>>(a, bounce); break;
+    case 0: SPB_SHADE_LAUNCH((k_shade_miss<0, 0>), (k_shade_hit_tiles<0, 0>)); break;
+    case 1: SPB_SHADE_LAUNCH((k_shade_miss<0, 1>), (k_shade_hit_tiles<0, 1>)); break;
+    case 2: SPB_SHADE_LAUNCH((k_shade_miss<1, 0>), (k_shade_hit_tiles<1, 0>)); break;
+    default: SPB_SHADE_LAUNCH((k_shade_miss<1, 1>), (k_shade_hit_tiles<1, 1>)); break;
     }
 }
 
