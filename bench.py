@@ -77,6 +77,8 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity block")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 secondary block")
     ap.add_argument("--no-copy-overlap", action="store_true", help="development: sp_b200_SetCopyOverlap(0)")
+    ap.add_argument("--nccl-channels", type=int, default=0,
+                    help="development: NCCL_MAX_NCHANNELS for this run (the env-map all-gather of the e2e steps runs beside the kernels)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="development: one sp_b200_RenderRows call per step instead of RenderRowsBegin / End with two frames in flight")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -447,6 +449,9 @@ def main():
     if world > 1:
         # stdout carries exactly one JSON line: whatever NCCL_DEBUG asks for goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if args.nccl_channels:
+            os.environ["NCCL_MAX_NCHANNELS"] = str(args.nccl_channels)
+            os.environ["NCCL_MIN_NCHANNELS"] = str(min(args.nccl_channels, 2))
         dist.init_process_group("nccl", device_id=dev)
         # "the frame is complete in host memory on every rank" is a statement about the hosts: the end-to-end steps
         # mark it with a CPU barrier (gloo).  An NCCL barrier is a kernel on the render stream -- it would run behind
