@@ -58,9 +58,15 @@ extern "C" ora_Scene *ora_create(void)
 extern "C" void ora_destroy(ora_Scene *s) { delete s; }
 
 // 1: mesh trees come from the host emulation of the device LBVH builder (spb_lbvh.cuh functions in a
-// loop + bvh4_from_binary), 0: the host SAH builder
+// loop + bvh4_from_binary), 2: the same binary tree collapsed by the host emulation of the DEVICE collapse
+// (lbvh_dp / lbvh_emit level by level + bvh4_adopt_device_tree), 0: the host SAH builder
 static int g_hostsimBuilder = 0;
 extern "C" void hostsim_set_builder(int builder) { g_hostsimBuilder = builder; }
+typedef Bvh4 (*BuilderFn)(const float *, const float *, uint32_t);
+static BuilderFn builder_fn(int builder)
+{
+    return builder == 2 ? &build_bvh4_lbvh_host_device_collapse : builder == 1 ? &build_bvh4_lbvh_host : nullptr;
+}
 
 // out8: nodeCount, maxDepth, stackNeed, leafCount, fellBack (1 if the LBVH path refused and the SAH
 // builder made the tree), summed node half-area x 1e3 (a cost proxy), 0, 0
@@ -68,7 +74,7 @@ extern "C" void hostsim_build_info(const float *vertices, uint32_t vertexCount, 
                                    uint32_t indexCount, int builder, uint32_t *out8)
 {
     auto accel = build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount,
-                                  builder ? &build_bvh4_lbvh_host : nullptr);
+                                  builder_fn(builder));
     const Bvh4 &b = accel->bvh;
     out8[0] = (uint32_t)b.nodes.size();
     out8[1] = b.maxDepth;
@@ -93,11 +99,56 @@ extern "C" void hostsim_build_info(const float *vertices, uint32_t vertexCount, 
     out8[6] = out8[7] = 0;
 }
 
+// bvh4_adopt_device_tree on a deliberately damaged tree (what a faulty device pass could return): builds the
+// emulated device tree of `count` boxes, applies damage `kind` and returns what the check says (1 = accepted).
+// kind 0: none; 1: a leaf slot referenced twice; 2: a node referenced twice; 3: a reference to an earlier node
+// (a cycle); 4: child count that hides a child; 5: wrong depth; 6: a primitive twice in slotPrim; 7: a child box
+// that sticks out of the box its parent holds for the node; 8: a reference beyond the node array; 9: an
+// unreferenced (orphan) node appended.
+extern "C" int hostsim_adopt_damaged(const float *aabbMin, const float *aabbMax, uint32_t count, int kind)
+{
+    DeviceTree4 t;
+    if (!lbvh_collapse_host_emulation(aabbMin, aabbMax, count, lbvh_build_binary_host(aabbMin, aabbMax, count), &t)) return -1;
+    const uint32_t nodes = (uint32_t)(t.nodes.size() / 32);
+    auto ref = [&](uint32_t n, uint32_t k) -> uint32_t & { return t.nodes[(size_t)n * 32 + 24 + k]; };
+    // first node with an internal child / a leaf child beyond the root
+    uint32_t withInner = 0xFFFFFFFFu, innerK = 0, withLeaf = 0xFFFFFFFFu, leafK = 0;
+    for (uint32_t n = 0; n < nodes; ++n)
+        for (uint32_t k = 0; k < t.nodes[(size_t)n * 32 + 28]; ++k)
+        {
+            if ((ref(n, k) & SPB_REF_LEAF) && withLeaf == 0xFFFFFFFFu) { withLeaf = n; leafK = k; }
+            if (!(ref(n, k) & SPB_REF_LEAF) && withInner == 0xFFFFFFFFu && n > 0) { withInner = n; innerK = k; }
+        }
+    if (withLeaf == 0xFFFFFFFFu || withInner == 0xFFFFFFFFu) return -2;
+    switch (kind)
+    {
+    case 1: ref(withInner, innerK) = ref(withLeaf, leafK); break;
+    case 2: ref(withLeaf, leafK) = ref(withInner, innerK); break;
+    case 3: ref(withInner, innerK) = 0; break;
+    case 4: t.nodes[(size_t)withInner * 32 + 28] -= 1; break;
+    case 5: t.nodes[(size_t)withInner * 32 + 29] += 1; break;
+    case 6: t.slotPrim[1] = t.slotPrim[0]; break;
+    case 7:
+    {
+        // the box the parent holds for its child shrinks to nothing: the child's own children stick out of it
+        // (a damaged LEAF box would simply be healed: leaf boxes are overwritten with the caller's AABBs)
+        float tiny = -3.0e30f;
+        memcpy(&t.nodes[(size_t)withInner * 32 + 12 + innerK], &tiny, 4); // bmax[0][innerK]
+        break;
+    }
+    case 8: ref(withInner, innerK) = nodes + 7; break;
+    case 9: t.nodes.resize(t.nodes.size() + 32, 0); t.nodes[t.nodes.size() - 32 + 28] = 1; break;
+    default: break;
+    }
+    Bvh4 out;
+    return bvh4_adopt_device_tree(aabbMin, aabbMax, count, t, &out) ? 1 : 0;
+}
+
 extern "C" int ora_add_mesh(ora_Scene *s, const float *vertices, uint32_t vertexCount,
                             const uint32_t *indices, uint32_t indexCount, uint32_t smooth)
 {
     s->meshes.push_back(build_mesh_accel((const VertexPNT *)vertices, vertexCount, indices, indexCount,
-                                         g_hostsimBuilder ? &build_bvh4_lbvh_host : nullptr));
+                                         builder_fn(g_hostsimBuilder)));
     s->meshSmooth.push_back(smooth);
     return (int)s->meshes.size() - 1;
 }

@@ -1173,7 +1173,8 @@ def test_work_queue_driver_matches_reference_scheduling(gpu_sp):
 
 def test_device_lbvh_builder(gpu_sp):
     """sp_BuildMeshMidphase with SP_B200_BUILDER_DEVICE_LBVH (k_lbvh_keys, radix
-    sort, k_lbvh_nodes, k_lbvh_fit on the GPU, collapse on the host).  (1) The tree has the shape the
+    sort, k_lbvh_nodes, k_lbvh_fit with the collapse's dynamic programme, k_lbvh_emit level by level: the
+    finished 4-wide tree comes back and the host only checks it).  (1) The tree has the shape the
     host emulation of the same per-element functions gives (node count, depth, stack need) -- the
     device passes computed the same binary tree; (2) results do not depend on the builder: the
     fixtures made by the unmodified reference (image, hit ids, ray queries, serial tile stream) are

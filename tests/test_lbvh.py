@@ -22,9 +22,9 @@ def same_bits(a, b):
                           np.ascontiguousarray(b, np.float32).view(np.uint32))
 
 
-@pytest.fixture
-def lbvh(hostsim):
-    hostsim.set_builder(1)
+@pytest.fixture(params=[1, 2], ids=["host_collapse", "device_collapse_emulation"])
+def lbvh(hostsim, request):
+    hostsim.set_builder(request.param)
     yield hostsim
     hostsim.set_builder(0)
     hostsim.lib.hostsim_set_stepped(0)
@@ -67,6 +67,43 @@ def test_lbvh_tree_shape(hostsim):
     sphere = W.icosphere_mesh(5)
     lb = hostsim.build_info(sphere.vertices, sphere.indices, 1)
     assert lb["leafCount"] == 20480 and lb["fellBack"] == 0
+
+
+def test_device_collapse_emulation_matches_host_collapse(hostsim):
+    """The device form of the 4-wide collapse (spb_lbvh.cuh lbvh_dp / lbvh_gather / lbvh_emit run level by level
+    in a loop, then bvh4_adopt_device_tree) makes the tree the host collapse makes from the same binary tree:
+    same node count, depth, stack need, leaves and summed area -- the dynamic programme is the same arithmetic
+    in the same order; only the numbering inside a level may differ."""
+    rng = np.random.RandomState(11)
+    soups = [rng.rand(n, 3, 3).astype(np.float32) * np.float32(s) for n, s in ((9, 1.0), (64, 3.0), (1000, 0.25), (4097, 10.0))]
+    meshes = [(W.load_mesh(n).vertices, W.load_mesh(n).indices) for n in ("bunny", "monkey")]
+    meshes += [(W.icosphere_mesh(4).vertices, W.icosphere_mesh(4).indices)]
+    meshes += [_mesh_from_triangles(t) for t in soups]
+    one = [[0, 0, 0], [1, 0, 0], [0, 1, 0]]
+    meshes.append(_mesh_from_triangles([one] * 300))
+    for v, i in meshes:
+        a = hostsim.build_info(v, i, 1)
+        b = hostsim.build_info(v, i, 2)
+        assert a["fellBack"] == 0 and b["fellBack"] == 0
+        assert a == b, (a, b)
+
+
+def test_damaged_device_trees_are_refused(hostsim):
+    """bvh4_adopt_device_tree is the gate between what the GPU returns and what the traversal kernels walk (their
+    pushes have no bound check): a tree with a leaf or node referenced twice, a cycle, a hidden child, a wrong
+    depth, a repeated primitive, a child sticking out of its parent's box, a reference past the array or an orphan
+    node is refused (the caller then builds on the host); the undamaged tree is accepted."""
+    import ctypes as C
+    f = C.POINTER(C.c_float)
+    hostsim.lib.hostsim_adopt_damaged.argtypes = [f, f, C.c_uint32, C.c_int]
+    hostsim.lib.hostsim_adopt_damaged.restype = C.c_int
+    rng = np.random.RandomState(5)
+    for n in (40, 700, 5000):
+        c = rng.rand(n, 3).astype(np.float32) * 10
+        mn = np.ascontiguousarray(c - rng.rand(n, 3).astype(np.float32) * 0.2)
+        mx = np.ascontiguousarray(c + rng.rand(n, 3).astype(np.float32) * 0.2)
+        got = [hostsim.lib.hostsim_adopt_damaged(mn.ctypes.data_as(f), mx.ctypes.data_as(f), n, k) for k in range(10)]
+        assert got == [1] + [0] * 9, (n, got)
 
 
 def _mesh_from_triangles(tris):

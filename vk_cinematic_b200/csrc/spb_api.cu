@@ -1497,8 +1497,22 @@ static Bvh4 device_tree_builder(const float *aabbMin, const float *aabbMax, uint
     Bvh4 out;
     if (count >= 8)
     {
-        BinaryTree tree;
+        // the whole build on the device, the 4-wide collapse included; the host checks the finished tree
+        // (SPB_B200_LBVH_HOST_COLLAPSE=1: round 1's path -- the binary tree comes back and the host collapses it)
+        static const bool hostCollapse = getenv("SPB_B200_LBVH_HOST_COLLAPSE") && atoi(getenv("SPB_B200_LBVH_HOST_COLLAPSE")) != 0;
         float ms = 0.0f;
+        if (!hostCollapse)
+        {
+            DeviceTree4 tree4;
+            if (lbvh_build_bvh4_device(aabbMin, aabbMax, count, &tree4, &ms, L.stream) &&
+                bvh4_adopt_device_tree(aabbMin, aabbMax, count, tree4, &out))
+            {
+                g_lastBuild.fellBack = 0;
+                g_lastBuild.deviceMs = ms;
+                return out;
+            }
+        }
+        BinaryTree tree;
         if (lbvh_build_binary_device(aabbMin, aabbMax, count, &tree, &ms, L.stream) &&
             bvh4_from_binary(aabbMin, aabbMax, count, tree, &out))
         {

@@ -584,6 +584,154 @@ bool bvh4_from_binary(const float *aabbMin, const float *aabbMax, uint32_t count
     return true;
 }
 
+bool bvh4_adopt_device_tree(const float *aabbMin, const float *aabbMax, uint32_t count, const DeviceTree4 &tree,
+                            Bvh4 *out)
+{
+    if (count < 2 || tree.slotPrim.size() != count || tree.nodes.empty() || tree.nodes.size() % 32 != 0) return false;
+    const uint32_t nodeCount = (uint32_t)(tree.nodes.size() / 32);
+    if (nodeCount > count - 1) return false;
+    {
+        std::vector<uint8_t> seen(count, 0);
+        for (uint32_t p : tree.slotPrim)
+        {
+            if (p >= count || seen[p]) return false;
+            seen[p] = 1;
+        }
+    }
+    Bvh4 result;
+    result.nodes.resize(nodeCount);
+    static_assert(sizeof(Node4) == 32 * sizeof(uint32_t), "DeviceTree4 nodes are Node4s");
+    memcpy(result.nodes.data(), tree.nodes.data(), (size_t)nodeCount * sizeof(Node4));
+    result.slotPrim = tree.slotPrim;
+    // what a node's parent says about it: the box it holds for it, its depth, the stack entries in use above it
+    struct Entry { float mn[3], mx[3]; uint32_t depth, stackBefore; uint8_t referenced; };
+    std::vector<Entry> entry(nodeCount);
+    memset(entry.data(), 0, entry.size() * sizeof(Entry));
+    for (int a = 0; a < 3; ++a) { entry[0].mn[a] = tree.rootBox[a]; entry[0].mx[a] = tree.rootBox[3 + a]; }
+    entry[0].referenced = 1;
+    std::vector<uint8_t> slotSeen(count, 0);
+    uint32_t worstStack = 0, maxDepth = 0;
+    for (uint32_t i = 0; i < nodeCount; ++i)
+    {
+        Node4 &nd = result.nodes[i];
+        const Entry &me = entry[i];
+        if (!me.referenced) return false; // (parents come before their children: an unreferenced node here stays so)
+        const uint32_t n = nd.meta[0];
+        if (n < 1 || n > 4 || nd.meta[1] != me.depth) return false;
+        const uint32_t stackHere = me.stackBefore + (n - 1);
+        worstStack = std::max(worstStack, stackHere);
+        maxDepth = std::max(maxDepth, me.depth);
+        for (uint32_t k = 0; k < 4; ++k)
+        {
+            const uint32_t ref = nd.ref[k];
+            if (k >= n)
+            {
+                if (ref != SPB_REF_EMPTY) return false;
+                for (int a = 0; a < 3; ++a) { nd.bmin[a][k] = NAN; nd.bmax[a][k] = NAN; }
+                continue;
+            }
+            if (ref == SPB_REF_EMPTY) return false;
+            if (ref & SPB_REF_LEAF)
+            {
+                const uint32_t slot = ref & ~SPB_REF_LEAF;
+                if (slot >= count || slotSeen[slot]) return false;
+                slotSeen[slot] = 1;
+                const uint32_t prim = result.slotPrim[slot];
+                for (int a = 0; a < 3; ++a) { nd.bmin[a][k] = aabbMin[(size_t)prim * 3 + a]; nd.bmax[a][k] = aabbMax[(size_t)prim * 3 + a]; }
+            }
+            else
+            {
+                if (ref <= i || ref >= nodeCount || entry[ref].referenced) return false;
+                Entry &e = entry[ref];
+                e.referenced = 1;
+                e.depth = me.depth + 1;
+                e.stackBefore = stackHere;
+                for (int a = 0; a < 3; ++a) { e.mn[a] = nd.bmin[a][k]; e.mx[a] = nd.bmax[a][k]; }
+            }
+            // inside the box the parent holds for this node (NaN boxes aside, as in bvh4_from_binary)
+            for (int a = 0; a < 3; ++a)
+                if (nd.bmin[a][k] < me.mn[a] || nd.bmax[a][k] > me.mx[a]) return false;
+        }
+    }
+    for (uint32_t slot = 0; slot < count; ++slot)
+        if (!slotSeen[slot]) return false;
+    if (worstStack > SPB_MESH_STACK_LIMIT) return false;
+    result.maxDepth = maxDepth;
+    result.stackNeed = worstStack;
+    for (int a = 0; a < 3; ++a) { result.rootMin[a] = tree.rootBox[a]; result.rootMax[a] = tree.rootBox[3 + a]; }
+    *out = std::move(result);
+    return true;
+}
+
+bool lbvh_collapse_host_emulation(const float *aabbMin, const float *aabbMax, uint32_t count, const BinaryTree &tree,
+                                  DeviceTree4 *out)
+{
+    if (count < 2) return false;
+    const uint32_t internal = count - 1;
+    if (tree.sortedPrim.size() != count || tree.children.size() != (size_t)internal * 2 || tree.boxes.size() != (size_t)internal * 6)
+        return false;
+    // the dynamic programme bottom-up, the way k_lbvh_fit reaches the nodes: a node after both its children
+    std::vector<uint32_t> parent(internal, 0xFFFFFFFFu), pendingKids(internal, 0), ready;
+    for (uint32_t i = 0; i < internal; ++i)
+        for (int c = 0; c < 2; ++c)
+        {
+            uint32_t ref = tree.children[(size_t)i * 2 + c];
+            if (ref & SPB_REF_LEAF) continue;
+            if (ref >= internal) return false;
+            parent[ref] = i;
+            pendingKids[i]++;
+        }
+    for (uint32_t i = 0; i < internal; ++i)
+        if (!pendingKids[i]) ready.push_back(i);
+    std::vector<float> cost((size_t)internal * 3, 0.0f);
+    std::vector<uint32_t> picks(internal, 0);
+    size_t done = 0;
+    while (done < ready.size())
+    {
+        uint32_t n = ready[done++];
+        const uint32_t l = tree.children[(size_t)n * 2], r = tree.children[(size_t)n * 2 + 1];
+        float zero[3] = {0.0f, 0.0f, 0.0f};
+        lbvh_dp(&tree.boxes[(size_t)n * 6], (l & SPB_REF_LEAF) ? zero : &cost[(size_t)l * 3], (r & SPB_REF_LEAF) ? zero : &cost[(size_t)r * 3],
+                &cost[(size_t)n * 3], &picks[n]);
+        if (parent[n] != 0xFFFFFFFFu && --pendingKids[parent[n]] == 0) ready.push_back(parent[n]);
+    }
+    if (done != internal) return false;
+    LbvhDpView view = {tree.children.data(), cost.data(), picks.data()};
+    std::vector<uint32_t> nodes4((size_t)internal * 32, 0);
+    out->slotPrim.assign(count, 0);
+    uint32_t counters[5] = {1, 0, 0, 0, 0};
+    std::vector<LbvhEmitItem> items[2];
+    items[0].push_back({0, 0, 0, 0});
+    for (uint32_t level = 0; !items[level & 1].empty(); ++level)
+    {
+        if (level >= 192) return false;
+        std::vector<LbvhEmitItem> &cur = items[level & 1], &next = items[(level + 1) & 1];
+        next.assign(internal, LbvhEmitItem());
+        uint32_t nextCount = 0;
+        for (const LbvhEmitItem &it : cur)
+            lbvh_emit(view, tree.sortedPrim.data(), aabbMin, aabbMax, tree.boxes.data(), it, nodes4.data(), out->slotPrim.data(), counters,
+                      next.data(), &nextCount);
+        next.resize(nextCount);
+    }
+    if (counters[0] > internal || counters[1] != count) return false;
+    nodes4.resize((size_t)counters[0] * 32);
+    out->nodes = std::move(nodes4);
+    out->maxDepth = counters[3];
+    out->stackNeed = counters[4];
+    for (int a = 0; a < 6; ++a) out->rootBox[a] = tree.boxes[a];
+    return true;
+}
+
+Bvh4 build_bvh4_lbvh_host_device_collapse(const float *aabbMin, const float *aabbMax, uint32_t count)
+{
+    Bvh4 out;
+    DeviceTree4 tree;
+    if (count >= 2 && lbvh_collapse_host_emulation(aabbMin, aabbMax, count, lbvh_build_binary_host(aabbMin, aabbMax, count), &tree) &&
+        bvh4_adopt_device_tree(aabbMin, aabbMax, count, tree, &out))
+        return out;
+    return build_bvh4(aabbMin, aabbMax, count);
+}
+
 Bvh4 build_bvh4_lbvh_host(const float *aabbMin, const float *aabbMax, uint32_t count)
 {
     Bvh4 out;

@@ -54,6 +54,28 @@ struct BinaryTree
 };
 bool bvh4_from_binary(const float *aabbMin, const float *aabbMax, uint32_t count, const BinaryTree &tree,
                       Bvh4 *out);
+// The finished 4-wide tree as the device builder returns it (lbvh_build_bvh4_device): nodes in the layout of
+// Node4 (32 words each), numbered level by level -- children after their parents -- but in no particular order
+// inside a level (atomic counters); leaf slot -> primitive; what the emission counted.
+struct DeviceTree4
+{
+    std::vector<uint32_t> nodes;    // 32 words per node
+    std::vector<uint32_t> slotPrim; // n
+    uint32_t maxDepth = 0, stackNeed = 0;
+    float rootBox[6] = {0, 0, 0, 0, 0, 0}; // min xyz, max xyz of binary node 0
+};
+// Checks a DeviceTree4 and turns it into a Bvh4: every primitive in exactly one leaf slot, every node referenced
+// exactly once by a node before it, child counts and depths consistent, every node's children inside the box its
+// parent holds for it; leaf boxes are OVERWRITTEN with the caller's own AABBs (the parity contract rests on
+// those, not on anything the device computed); depth and stack need are recomputed, not trusted.  false --
+// the caller falls back to build_bvh4 -- when anything is off or the tree needs more stack than a mesh tree may.
+bool bvh4_adopt_device_tree(const float *aabbMin, const float *aabbMax, uint32_t count, const DeviceTree4 &tree,
+                            Bvh4 *out);
+// Host emulation of the device collapse (the per-element functions of spb_lbvh.cuh run level by level in a loop)
+// on the host's binary tree: what tests/hostsim builds with builder 2.
+bool lbvh_collapse_host_emulation(const float *aabbMin, const float *aabbMax, uint32_t count, const BinaryTree &tree,
+                                  DeviceTree4 *out);
+Bvh4 build_bvh4_lbvh_host_device_collapse(const float *aabbMin, const float *aabbMax, uint32_t count);
 // The same binary tree computed on the host with the per-element functions the kernels run
 // (spb_lbvh.cuh): the reference the device result is compared with, and what tests/hostsim uses.
 BinaryTree lbvh_build_binary_host(const float *aabbMin, const float *aabbMax, uint32_t count);

@@ -134,6 +134,10 @@ void launch_irradiance(const KernelConfig &cfg, const IrradianceArgs &args, int 
 // false on a CUDA error; the tree is validated and collapsed by bvh4_from_binary (spb_bvh.h).
 bool lbvh_build_binary_device(const float *aabbMin, const float *aabbMax, uint32_t count, BinaryTree *tree,
                               float *kernelMs, cudaStream_t stream);
+// The whole build on the device, 4-wide collapse included (spb_lbvh.cu): the finished tree comes back and
+// bvh4_adopt_device_tree (spb_bvh.cpp) checks it.  false on a CUDA error or a tree the emission cannot finish.
+bool lbvh_build_bvh4_device(const float *aabbMin, const float *aabbMax, uint32_t count, DeviceTree4 *tree,
+                            float *kernelMs, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // wavefront renderer (spb_wavefront.cu)
