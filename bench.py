@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity block")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 secondary block")
     ap.add_argument("--no-copy-overlap", action="store_true", help="development: sp_b200_SetCopyOverlap(0)")
+    ap.add_argument("--fuse-miss", type=int, default=-1, help="development: sp_b200_SetMissFusion(0 / 1 / 2)")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="development: NCCL_MAX_NCHANNELS for this run (the env-map all-gather of the e2e steps runs beside the kernels)")
     ap.add_argument("--no-pipeline", action="store_true",
@@ -515,6 +516,8 @@ def main():
         sp.lib.sp_b200_SetRefillThresholds(*[int(x) for x in args.refill.split(",")])
     if args.evict:
         sp.lib.sp_b200_SetStragglerEviction(*[int(x) for x in args.evict.split(",")])
+    if args.fuse_miss >= 0:
+        sp.lib.sp_b200_SetMissFusion(args.fuse_miss)
     if args.no_copy_overlap:
         sp.lib.sp_b200_SetCopyOverlap(0)
     TH = args.strip_rows   # strip boundaries and cost accounting: rows of TH pixels

@@ -381,6 +381,11 @@ void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u
  * direction-sorted bounce rays and all other rays; 0 keeps the default (1; measured choice of 1 or 12 per
  * scene; 12 for one object, 16 for several). */
 void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
+/* Wavefront mode tuning: 1 = a ray that escapes is shaded by the trace kernel where it retires it (background
+ * radiance, path folded back, radiance slot written) instead of going through the miss queue and a second kernel;
+ * 2 = the same with the path's stored vertex terms prefetched when the ray starts; 0 = off; -1 (default) = by
+ * scene: on for one object, off for several (measured, profiles/r2/README.md).  Same functions, same bits. */
+void sp_b200_SetMissFusion(int mode);
 /* Wavefront mode tuning: straggler eviction of the bounce traces.  A warp of the trace kernel walks a
  * packet of 32 rays; the rays of a packet end at different times, and the last few would keep the warp
  * busy at a fraction of its lanes.  With a threshold > 0, a packet whose walking lanes drop below it

@@ -152,6 +152,9 @@ struct TextureEntry
     ~TextureEntry() { buffer.release(); }
 };
 
+#ifndef SPB_FUSE_MISS_DEFAULT
+#define SPB_FUSE_MISS_DEFAULT 1 // (single-object scenes; sp_b200_SetMissFusion)
+#endif
 #define SPB_EVICT_AUTO 0xFFFFFFFFu // (eviction threshold chosen by scene: evict_below())
 
 struct Library
@@ -167,6 +170,7 @@ struct Library
     bool sortBounceRays = true; // sp_b200_SetRaySorting
     bool primaryCandidates = true; // sp_b200_SetPrimaryCandidates
     uint32_t meshBuilder = 0;      // sp_b200_SetMeshBuilder
+    int fuseMiss = -1;             // sp_b200_SetMissFusion: escaped rays shaded by the trace kernel where it retires them (-1: by scene)
     bool skyOneLookup = true;      // sp_b200_SetSkyCulling(2 = on with, 1 = on without the one-lookup path)
     uint32_t sortBounces = 1;   // bounces whose outgoing rays are direction-sorted (A/B knob)
     // refill thresholds of the trace kernel: primary rays, direction-sorted bounce rays, the rest.
@@ -375,6 +379,7 @@ void ensure_init()
         log_message("libspb200: L2 fetch granularity %zu -> %zu (%s)", before, after, cudaGetErrorString(e));
         cudaGetLastError();
     }
+    if (const char *f = getenv("SPB_B200_FUSE_MISS")) L.fuseMiss = atoi(f); // (A/B and test runs; sp_b200_SetMissFusion)
     SPB_CUDA(cudaStreamCreateWithFlags(&L.copyStream, cudaStreamNonBlocking));
     SPB_CUDA(cudaStreamCreateWithFlags(&L.uploadStream, cudaStreamNonBlocking));
     SPB_CUDA(cudaEventCreateWithFlags(&L.evScene, cudaEventDisableTiming));
@@ -963,6 +968,12 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.missQ = (uint32_t *)L.wMissQ.ptr;
     a.pathTerms = (v4f *)L.wTerms.ptr;
     a.rad = (v4f *)L.wRad.ptr;
+    {
+        // by scene: on for one object (C3: 57.4 -> 56.4 ms per frame), off for several (C5: 165.5 -> 166.8);
+        // profiles/r2/s24_*.  Mode 2 also prefetches the path's vertex terms when the ray starts.
+        const int mode = L.fuseMiss >= 0 ? L.fuseMiss : (ra.scene.objectCount == 1 ? SPB_FUSE_MISS_DEFAULT : 0);
+        a.fuseMiss = mode ? (1u | (cfg.math ? 2u : 0u) | (cfg.envFilter ? 4u : 0u) | (mode == 2 ? 8u : 0u)) : 0u;
+    }
 
     // sorted-class refill threshold: fixed, chosen earlier, or being measured (alternating
     // candidates over the passes of the first frames, timed with events around the bounce-1 trace)
@@ -1430,6 +1441,8 @@ extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
     L.refillThreshold[1] = sorted; // 0: measured
     L.refillThreshold[2] = other; // 0: by scene (refill_other)
 }
+
+extern "C" void sp_b200_SetMissFusion(int mode) { lib().fuseMiss = mode < 0 ? -1 : (mode > 2 ? 2 : mode); }
 
 extern "C" void sp_b200_SetStragglerEviction(u32 sorted, u32 other)
 {
@@ -2647,8 +2660,8 @@ static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, voi
     // what the host set on the primary holds for every device
     struct Settings
     {
-        sp_b200_Params params; bool stats, sky, sort, cand, one, overlap; uint32_t paths, sortBounces, refill[3], evict[2];
-    } set = {P.params, P.statsEnabled, P.skyCulling, P.sortBounceRays, P.primaryCandidates, P.skyOneLookup, P.overlapCopies,
+        sp_b200_Params params; bool stats, sky, sort, cand, one, overlap; int fuse; uint32_t paths, sortBounces, refill[3], evict[2];
+    } set = {P.params, P.statsEnabled, P.skyCulling, P.sortBounceRays, P.primaryCandidates, P.skyOneLookup, P.overlapCopies, P.fuseMiss,
              P.pathsPerPass, P.sortBounces, {P.refillThreshold[0], P.refillThreshold[1], P.refillThreshold[2]}, {P.evictBelow[0], P.evictBelow[1]}};
     const int primaryDevice = M.devices[0];
     auto render_part = [&](u32 p) {
@@ -2658,7 +2671,7 @@ static int render_frame_devices(sp_Context *ctx, u32 frame, f32 *hostPixels, voi
         if (p > 0)
         {
             L.params = set.params; L.statsEnabled = set.stats; L.skyCulling = set.sky; L.sortBounceRays = set.sort;
-            L.primaryCandidates = set.cand; L.skyOneLookup = set.one; L.overlapCopies = set.overlap;
+            L.primaryCandidates = set.cand; L.skyOneLookup = set.one; L.overlapCopies = set.overlap; L.fuseMiss = set.fuse;
             L.pathsPerPass = set.paths; L.sortBounces = set.sortBounces;
             for (int k = 0; k < 3; ++k) L.refillThreshold[k] = set.refill[k];
             L.evictBelow[0] = set.evict[0]; L.evictBelow[1] = set.evict[1];

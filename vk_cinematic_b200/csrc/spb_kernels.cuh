@@ -236,6 +236,9 @@ struct WaveArgs
     // and pixel angle of the camera).  skyList[0] counts, skyList[1..] lists the other pixels.
     float skyDirectionSpread;
     uint32_t *skyList;
+    // 0: escaped rays go to the miss queue and k_shade_miss shades them; else 1 | mathMode << 1 | envFilter << 2:
+    // the trace kernel shades a ray that escapes where it retires it (no queue entry, no k_shade_miss launch)
+    uint32_t fuseMiss;
 };
 // (SPB_CAND_MAX / SPB_CAND_STRIDE / SPB_CAND_FALLBACK: spb_core.cuh)
 // items (pixel x sample, block-major) whose bounce rays are ordered together

@@ -140,6 +140,87 @@ __device__ __noinline__ Hit slow_intersect(const DScene &S, f3 o, f3 d)
     return h;
 }
 
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_terms(v4f *pathTerms, size_t index, const VertexTerms &vt)
+{
+    v4f a, b;
+    a.x = vt.E.x; a.y = vt.E.y; a.z = vt.E.z; a.w = vt.cosine;
+    b.x = vt.W.x; b.y = vt.W.y; b.z = vt.W.z; b.w = 0.0f;
+    pathTerms[index * 2 + 0] = a;
+    pathTerms[index * 2 + 1] = b;
+}
+
+__device__ __forceinline__ VertexTerms load_terms(const v4f *pathTerms, size_t index)
+{
+    v4f a = pathTerms[index * 2 + 0], b = pathTerms[index * 2 + 1];
+    VertexTerms vt;
+    vt.E = mk3(a.x, a.y, a.z);
+    vt.cosine = a.w;
+    vt.W = mk3(b.x, b.y, b.z);
+    return vt;
+}
+
+// radiance of the finished path: the last vertex's radiance, then the stored vertices folded back
+// to the eye
+__device__ __forceinline__ void finish_path_from(const WaveArgs &a, f3 radiance, uint32_t bounce, uint32_t path)
+{
+    for (int i = (int)bounce - 1; i >= 0; --i)
+        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
+    v4f r;
+    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
+    a.rad[path] = r;
+}
+
+__device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms &last, uint32_t bounce,
+                                            uint32_t path)
+{
+    f3 radiance = fold_radiance(last, mk3(0.0f, 0.0f, 0.0f), a.clampValue);
+    for (int i = (int)bounce - 1; i >= 0; --i)
+        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
+    v4f r;
+    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
+    a.rad[path] = r;
+}
+
+// cost per tile row (strip rebalancing feedback): SPB_COST_MISS units per escaped ray,
+// SPB_COST_HIT per surface hit (a hit costs a shading step and, unless it is the last bounce, a
+// far more expensive incoherent traversal); one atomic per distinct row per warp
+__device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active, unsigned weight)
+{
+    if (!a.tileRowCost) return;
+    unsigned row = 0xFFFFFFFFu;
+    if (active) // (an inactive lane's path id may be a hole: not a valid index into the block list)
+    {
+        unsigned x, y, sLocal;
+        item_pixel(a, path, x, y, sLocal);
+        row = y / a.tileHeight - a.costRow0;
+    }
+    unsigned peers = __match_any_sync(SPB_FULL, row);
+    if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
+        atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
+}
+
+// An escaped ray shaded where the trace kernel retires it (WaveArgs::fuseMiss): what k_shade_miss does for one
+// entry of the miss queue -- background radiance, the path folded back to the eye, its radiance slot written --
+// without the queue entry and the second pass over the ray record.  Out of line: the direction -> texel
+// arithmetic (two double-rounded atan2) must not take part in the register allocation of the walk.
+__device__ __noinline__ void shade_miss_fused(const WaveArgs &a, float vx, float vy, float vz, uint32_t bounce, uint32_t path)
+{
+    const DMaterials &M = *a.materials;
+    Counters cnt = {0, 0, 0, 0};
+    const f3 V = mk3(vx, vy, vz);
+    f3 radiance;
+    switch ((a.fuseMiss >> 1) & 3u)
+    {
+    case 0: radiance = miss_radiance<0, 0>(M, V, a.clampValue, &cnt); break;
+    case 1: radiance = miss_radiance<1, 0>(M, V, a.clampValue, &cnt); break;
+    case 2: radiance = miss_radiance<0, 1>(M, V, a.clampValue, &cnt); break;
+    default: radiance = miss_radiance<1, 1>(M, V, a.clampValue, &cnt); break;
+    }
+    finish_path_from(a, radiance, bounce, path);
+    if (a.countStats && cnt.envClamped) atomicAdd(&a.stats[CTR_ENV_CLAMPED], (unsigned long long)cnt.envClamped);
+}
+
 #if defined(SPB_TRAV2)
 // ---------------------------------------------------------------------------------------------
 // A/B BUILD (-DSPB_TRAV2), not the production kernel: the second traversal machine, built on VERDICT
@@ -564,7 +645,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             const bool queueHits = !(PRIMARY && a.sortPrimaryHits);
             unsigned hs = 0, ms = 0;
             if (hitMask && queueHits) hs = chunk_take(&ctr[WCTR_HITS], ws + WS_HIT_NEXT, hitMask, chunk);
-            if (missMask) ms = chunk_take(&ctr[WCTR_MISSES], ws + WS_MISS_NEXT, missMask, chunk);
+            if (missMask && !a.fuseMiss) ms = chunk_take(&ctr[WCTR_MISSES], ws + WS_MISS_NEXT, missMask, chunk);
             if (lane == 0)
             {
                 ws[WS_NHITS] += __popc(hitMask);
@@ -580,8 +661,19 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             }
             if (isMiss)
             {
-                a.missQ[ms] = slot;
+                if (!a.fuseMiss) a.missQ[ms] = slot;
                 if (!queueHits) a.hitRec[slot] = mk4f(-1.0f, 0.0f, 0.0f, 0.0f);
+            }
+            if (a.fuseMiss)
+            {
+                uint32_t path = 0;
+                if (isMiss)
+                {
+                    const v4f rb = rays[(size_t)slot * 2 + 1]; // (direction, path id)
+                    path = f2u(rb.w);
+                    shade_miss_fused(a, -rb.x, -rb.y, -rb.z, bounce, path);
+                }
+                if (missMask) count_row(a, path, isMiss, SPB_COST_MISS);
             }
             if (finished) have = false;
         }
@@ -655,8 +747,13 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                     else
                     {
                         // a slot that stands for a hole of the hit queue it was made from
-                        valid = f2u(rays[(size_t)idx * 2 + 1].w) != SPB_QUEUE_HOLE;
+                        const uint32_t path = f2u(rays[(size_t)idx * 2 + 1].w);
+                        valid = path != SPB_QUEUE_HOLE;
                         if (valid) trav_world_ray(rays + (size_t)idx * 2, o, d);
+                        // (fused miss shading, mode 2: four in five of these rays escape and fold their path back
+                        // where they retire -- start the path's vertex terms on their way to L2 now)
+                        if (valid && (a.fuseMiss & 8u))
+                            for (uint32_t i = 0; i < bounce; ++i) prefetch_l2(a.pathTerms + ((size_t)i * a.pathCapacity + path) * 2);
                     }
                     if (valid)
                     {
@@ -848,66 +945,6 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 }
 
 #endif // SPB_TRAV2
-
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_terms(v4f *pathTerms, size_t index, const VertexTerms &vt)
-{
-    v4f a, b;
-    a.x = vt.E.x; a.y = vt.E.y; a.z = vt.E.z; a.w = vt.cosine;
-    b.x = vt.W.x; b.y = vt.W.y; b.z = vt.W.z; b.w = 0.0f;
-    pathTerms[index * 2 + 0] = a;
-    pathTerms[index * 2 + 1] = b;
-}
-
-__device__ __forceinline__ VertexTerms load_terms(const v4f *pathTerms, size_t index)
-{
-    v4f a = pathTerms[index * 2 + 0], b = pathTerms[index * 2 + 1];
-    VertexTerms vt;
-    vt.E = mk3(a.x, a.y, a.z);
-    vt.cosine = a.w;
-    vt.W = mk3(b.x, b.y, b.z);
-    return vt;
-}
-
-// radiance of the finished path: the last vertex's radiance, then the stored vertices folded back
-// to the eye
-__device__ __forceinline__ void finish_path_from(const WaveArgs &a, f3 radiance, uint32_t bounce, uint32_t path)
-{
-    for (int i = (int)bounce - 1; i >= 0; --i)
-        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
-    v4f r;
-    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
-    a.rad[path] = r;
-}
-
-__device__ __forceinline__ void finish_path(const WaveArgs &a, const VertexTerms &last, uint32_t bounce,
-                                            uint32_t path)
-{
-    f3 radiance = fold_radiance(last, mk3(0.0f, 0.0f, 0.0f), a.clampValue);
-    for (int i = (int)bounce - 1; i >= 0; --i)
-        radiance = fold_radiance(load_terms(a.pathTerms, (size_t)i * a.pathCapacity + path), radiance, a.clampValue);
-    v4f r;
-    r.x = radiance.x; r.y = radiance.y; r.z = radiance.z; r.w = 0.0f;
-    a.rad[path] = r;
-}
-
-// cost per tile row (strip rebalancing feedback): SPB_COST_MISS units per escaped ray,
-// SPB_COST_HIT per surface hit (a hit costs a shading step and, unless it is the last bounce, a
-// far more expensive incoherent traversal); one atomic per distinct row per warp
-__device__ __forceinline__ void count_row(const WaveArgs &a, uint32_t path, bool active, unsigned weight)
-{
-    if (!a.tileRowCost) return;
-    unsigned row = 0xFFFFFFFFu;
-    if (active) // (an inactive lane's path id may be a hole: not a valid index into the block list)
-    {
-        unsigned x, y, sLocal;
-        item_pixel(a, path, x, y, sLocal);
-        row = y / a.tileHeight - a.costRow0;
-    }
-    unsigned peers = __match_any_sync(SPB_FULL, row);
-    if (active && lane_id() == (unsigned)(__ffs(peers) - 1))
-        atomicAdd(&a.tileRowCost[row], (unsigned long long)__popc(peers) * weight);
-}
 
 // Escaped rays.  Every record a miss touches -- its queue entry, its ray, the vertex terms of its path, one texel
 // of the environment map, its radiance slot -- is a scattered 16- or 32-byte read behind the one before
@@ -1478,7 +1515,8 @@ static unsigned resident_grid(K kernel, int level)
 
 #define SPB_SHADE_LAUNCH(MISS, HIT)                                                                   \
     do {                                                                                              \
-        MISS<<<resident_grid(MISS, 1), 256, 0, stream>>>(a, bounce);                                  \
+        if (!a.fuseMiss) MISS<<<resident_grid(MISS, 1), 256, 0, stream>>>(a, bounce);                 \
+        else g_kernelLaunches--; /* (the trace kernel shaded the escaped rays as it retired them) */  \
         HIT<<<resident_grid(HIT, 2), 256, 0, stream>>>(a, bounce);                                    \
     } while (0)
 

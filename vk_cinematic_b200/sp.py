@@ -279,6 +279,7 @@ _SIGNATURES = {
     "sp_b200_FlushTextureCache": (None, []),
     "sp_b200_SetPathsPerPass": (None, [u32]),
     "sp_b200_SetSkyCulling": (None, [C.c_int]),
+    "sp_b200_SetMissFusion": (None, [C.c_int]),
     "sp_b200_SetRaySorting": (None, [C.c_int]),
     "sp_b200_SetPrimaryCandidates": (None, [C.c_int]),
     "sp_b200_SetCopyOverlap": (None, [C.c_int]),
