@@ -927,6 +927,46 @@ def test_coverage_mask_and_ray_sorting_edge_cases(gpu_sp, case):
     r.close()
 
 
+def test_miss_fusion_gives_the_same_bits(gpu_sp):
+    """sp_b200_SetMissFusion: escaped rays shaded by the trace kernel where it retires them (modes 1, 2) give the
+    image, the path / ray / hit / miss counters and the per-row cost units of the miss queue + k_shade_miss
+    (mode 0): a single-object scene (packet mode, straggler eviction, candidate lists) and a multi-object one
+    (four-class vote), nearest and bilinear environment filter, sky culling on and off, and the reference's
+    fixture itself with the fusion on."""
+    sp = gpu_sp
+    try:
+        for wl, spp, bounces in ((W.config1(200, 150, env_size=(256, 128)), 7, 5),
+                                 (W.multi_object_workload(width=160, height=120, spp=4, env_size=(256, 128)), 4, 4)):
+            r = sp.Renderer().load_workload(wl)
+            for env_filter in (0, 1):
+                for sky in (2, 0):
+                    sp.lib.sp_b200_SetSkyCulling(sky)
+                    sp.set_params(samplesPerPixel=spp, bounceCount=bounces, renderMode=0, mathMode=0, envFilter=env_filter,
+                                  cullByDistance=1, radianceClamp=10.0, tileHeight=8, tileWidth=64)
+                    want = None
+                    for mode in (0, 1, 2):
+                        sp.lib.sp_b200_SetMissFusion(mode)
+                        r.image[...] = 0
+                        m, cost = r.render_rows(0, wl.height, frame=2, host=True, want_cost=True)
+                        got = (r.image.copy(), m[1:5].copy(), cost > 0)
+                        if want is None:
+                            want = got
+                        assert same_bits(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), (env_filter, sky, mode)
+            r.close()
+        sp.lib.sp_b200_SetSkyCulling(2)
+        sp.lib.sp_b200_SetMissFusion(1)
+        g = np.load(os.path.join(GOLD, "g1_bunny_96x64.npz"))
+        sp.set_params(samplesPerPixel=2, bounceCount=3, mathMode=0, envFilter=0, renderMode=0, cullByDistance=1, tileHeight=64)
+        r = sp.Renderer().load_workload(W.config1(96, 64, env_size=(512, 256)))
+        img, m = r.render_frame(frame=1)
+        assert same_bits(img, g["image_ref_dm"]) and np.array_equal(m[1:5], g["metrics_ref_dm"])
+        r.close()
+    finally:
+        sp.lib.sp_b200_SetMissFusion(-1)
+        sp.lib.sp_b200_SetSkyCulling(2)
+        sp.set_params(samplesPerPixel=1, bounceCount=3, envFilter=0, tileHeight=64)
+
+
 def test_wavefront_pass_split_and_stats(gpu_sp):
     """Wavefront scheduling details: any samples-per-pass split gives the same bits (the sample
     order of the accumulation is kept, simd_path_tracer.cpp:321); the stats launch counts the same

@@ -153,7 +153,7 @@ struct TextureEntry
 };
 
 #ifndef SPB_FUSE_MISS_DEFAULT
-#define SPB_FUSE_MISS_DEFAULT 1 // (single-object scenes; sp_b200_SetMissFusion)
+#define SPB_FUSE_MISS_DEFAULT 0 // (what -1, "by scene", means for single-object scenes; see render_wavefront)
 #endif
 #define SPB_EVICT_AUTO 0xFFFFFFFFu // (eviction threshold chosen by scene: evict_below())
 
@@ -969,8 +969,10 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.pathTerms = (v4f *)L.wTerms.ptr;
     a.rad = (v4f *)L.wRad.ptr;
     {
-        // by scene: on for one object (C3: 57.4 -> 56.4 ms per frame), off for several (C5: 165.5 -> 166.8);
-        // profiles/r2/s24_*.  Mode 2 also prefetches the path's vertex terms when the ray starts.
+        // Measured (profiles/r2/s24_* ... s26_*): C3 57.4 -> 56.3 ms per frame with it (k_trace +7.1 ms, k_shade_miss
+        // -8.1), C5 165.5 -> 166.8, mode 2 (the path's vertex terms prefetched when the ray starts) = mode 1.  Off by
+        // default: 1.8 % on one configuration, for 7 ms of DRAM-latency-bound shading inside the kernel whose
+        // roofline the bench reports as traversal; a host that wants the frame time turns it on (mode 1).
         const int mode = L.fuseMiss >= 0 ? L.fuseMiss : (ra.scene.objectCount == 1 ? SPB_FUSE_MISS_DEFAULT : 0);
         a.fuseMiss = mode ? (1u | (cfg.math ? 2u : 0u) | (cfg.envFilter ? 4u : 0u) | (mode == 2 ? 8u : 0u)) : 0u;
     }
