@@ -77,7 +77,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-frame parity block")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C5 secondary block")
     ap.add_argument("--no-copy-overlap", action="store_true", help="development: sp_b200_SetCopyOverlap(0)")
-    ap.add_argument("--fuse-miss", type=int, default=-1, help="development: sp_b200_SetMissFusion(0 / 1 / 2)")
+    ap.add_argument("--fuse-miss", type=int, default=-1, help="development: sp_b200_SetMissFusion(0 / 1)")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="development: NCCL_MAX_NCHANNELS for this run (the env-map all-gather of the e2e steps runs beside the kernels)")
     ap.add_argument("--no-pipeline", action="store_true",

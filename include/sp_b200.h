@@ -383,9 +383,8 @@ void sp_b200_SetDeviceTexture(const f32 *hostPixels, const void *devicePixels, u
 void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other);
 /* Wavefront mode tuning: 1 = a ray that escapes is shaded by the trace kernel where it retires it (background
  * radiance, path folded back, radiance slot written) instead of going through the miss queue and a second kernel;
- * 2 = the same with the path's stored vertex terms prefetched when the ray starts; 0 = off; -1 (default) = the
- * library's choice, currently off (measured, profiles/r2/README.md: C3 frame -1.8 % with mode 1, C5 +0.8 %).
- * Same functions, same bits. */
+ * 0 = off; -1 (default) = the library's choice, currently off (measured, profiles/r2/README.md: C3 frame -1.8 %
+ * with it on, C5 +0.8 %).  Same functions, same bits. */
 void sp_b200_SetMissFusion(int mode);
 /* Wavefront mode tuning: straggler eviction of the bounce traces.  A warp of the trace kernel walks a
  * packet of 32 rays; the rays of a packet end at different times, and the last few would keep the warp

@@ -928,7 +928,7 @@ def test_coverage_mask_and_ray_sorting_edge_cases(gpu_sp, case):
 
 
 def test_miss_fusion_gives_the_same_bits(gpu_sp):
-    """sp_b200_SetMissFusion: escaped rays shaded by the trace kernel where it retires them (modes 1, 2) give the
+    """sp_b200_SetMissFusion: escaped rays shaded by the trace kernel where it retires them (mode 1) give the
     image, the path / ray / hit / miss counters and the per-row cost units of the miss queue + k_shade_miss
     (mode 0): a single-object scene (packet mode, straggler eviction, candidate lists) and a multi-object one
     (four-class vote), nearest and bilinear environment filter, sky culling on and off, and the reference's
@@ -944,7 +944,7 @@ def test_miss_fusion_gives_the_same_bits(gpu_sp):
                     sp.set_params(samplesPerPixel=spp, bounceCount=bounces, renderMode=0, mathMode=0, envFilter=env_filter,
                                   cullByDistance=1, radianceClamp=10.0, tileHeight=8, tileWidth=64)
                     want = None
-                    for mode in (0, 1, 2):
+                    for mode in (0, 1):
                         sp.lib.sp_b200_SetMissFusion(mode)
                         r.image[...] = 0
                         m, cost = r.render_rows(0, wl.height, frame=2, host=True, want_cost=True)

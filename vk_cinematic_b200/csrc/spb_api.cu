@@ -970,11 +970,11 @@ bool render_wavefront(const RenderArgs &ra, uint64_t instancedTriangles, std::ve
     a.rad = (v4f *)L.wRad.ptr;
     {
         // Measured (profiles/r2/s24_* ... s26_*): C3 57.4 -> 56.3 ms per frame with it (k_trace +7.1 ms, k_shade_miss
-        // -8.1), C5 165.5 -> 166.8, mode 2 (the path's vertex terms prefetched when the ray starts) = mode 1.  Off by
+        // -8.1), C5 165.5 -> 166.8; with the path's vertex terms prefetched when the ray starts: the same.  Off by
         // default: 1.8 % on one configuration, for 7 ms of DRAM-latency-bound shading inside the kernel whose
         // roofline the bench reports as traversal; a host that wants the frame time turns it on (mode 1).
         const int mode = L.fuseMiss >= 0 ? L.fuseMiss : (ra.scene.objectCount == 1 ? SPB_FUSE_MISS_DEFAULT : 0);
-        a.fuseMiss = mode ? (1u | (cfg.math ? 2u : 0u) | (cfg.envFilter ? 4u : 0u) | (mode == 2 ? 8u : 0u)) : 0u;
+        a.fuseMiss = mode ? (1u | (cfg.math ? 2u : 0u) | (cfg.envFilter ? 4u : 0u)) : 0u;
     }
 
     // sorted-class refill threshold: fixed, chosen earlier, or being measured (alternating
@@ -1444,7 +1444,7 @@ extern "C" void sp_b200_SetRefillThresholds(u32 primary, u32 sorted, u32 other)
     L.refillThreshold[2] = other; // 0: by scene (refill_other)
 }
 
-extern "C" void sp_b200_SetMissFusion(int mode) { lib().fuseMiss = mode < 0 ? -1 : (mode > 2 ? 2 : mode); }
+extern "C" void sp_b200_SetMissFusion(int mode) { lib().fuseMiss = mode < 0 ? -1 : (mode > 0 ? 1 : 0); }
 
 extern "C" void sp_b200_SetStragglerEviction(u32 sorted, u32 other)
 {

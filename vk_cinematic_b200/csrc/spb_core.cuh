@@ -63,16 +63,6 @@ SPB_HD void prefetch_l1(const void *p)
     (void)p;
 #endif
 }
-// Start a line on its way from DRAM to L2 (no register, no scoreboard): for a record whose address is known
-// well before its contents are needed.
-SPB_HD void prefetch_l2(const void *p)
-{
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
 // 32-byte load through the read-only path (LDG.E.256 on sm_100a): half as many L1 wavefronts per
 // node as 16-byte loads when every lane of a warp reads a different node.
 SPB_HD void ld8(const v4f *p, v4f &a, v4f &b)

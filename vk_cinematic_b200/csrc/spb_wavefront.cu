@@ -492,9 +492,6 @@ __device__ __forceinline__ TravEntry stack_get(const HybridStack &s, int sp)
 #ifndef SPB_EXIT_WEIGHT
 #define SPB_EXIT_WEIGHT 1 // (measured on C5, profiles/r2/s15_*: 182.4 ms per frame with 1, 191.4 with 2, 195.8 with 4; two classes 196.3)
 #endif
-#ifndef SPB_VOTE_POLICY
-#define SPB_VOTE_POLICY 0
-#endif
 #ifndef SPB_VOTE_BUSY_EXIT
 #define SPB_VOTE_BUSY_EXIT 1 // (C5: 171.8 ms per frame against 181.4 without; profiles/r2/s16_ab_c5_vote_thresholds.txt)
 #endif
@@ -747,13 +744,8 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                     else
                     {
                         // a slot that stands for a hole of the hit queue it was made from
-                        const uint32_t path = f2u(rays[(size_t)idx * 2 + 1].w);
-                        valid = path != SPB_QUEUE_HOLE;
+                        valid = f2u(rays[(size_t)idx * 2 + 1].w) != SPB_QUEUE_HOLE;
                         if (valid) trav_world_ray(rays + (size_t)idx * 2, o, d);
-                        // (fused miss shading, mode 2: four in five of these rays escape and fold their path back
-                        // where they retire -- start the path's vertex terms on their way to L2 now)
-                        if (valid && (a.fuseMiss & 8u))
-                            for (uint32_t i = 0; i < bounce; ++i) prefetch_l2(a.pathTerms + ((size_t)i * a.pathCapacity + path) * 2);
                     }
                     if (valid)
                     {
@@ -858,16 +850,10 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
                 const bool wantExit = have && st.cur == SPB_NODE_EXIT;
                 const int n = __popc(__ballot_sync(SPB_FULL, wantNode)), t = __popc(__ballot_sync(SPB_FULL, wantTri)),
                           e = __popc(__ballot_sync(SPB_FULL, wantEnter)), x = __popc(__ballot_sync(SPB_FULL, wantExit)) * SPB_EXIT_WEIGHT;
-#if SPB_VOTE_POLICY == 1
-                // (A/B) the step that leaves the fewest lane-slots idle: cost x (32 - lanes), costs in SASS instructions
-                const int wn = n ? 145 * (32 - n) : 0x7FFFFFFF, wt = t ? 110 * (32 - t) : 0x7FFFFFFF,
-                          we = e ? 250 * (32 - e) : 0x7FFFFFFF, wx = x ? 90 * (32 - x) : 0x7FFFFFFF;
-                const bool pickNode = wn <= wt && wn <= we && wn <= wx, pickTri = !pickNode && wt <= we && wt <= wx,
-                           pickEnter = !pickNode && !pickTri && we <= wx;
-#else
+                // (the majority; voting for the step that leaves the fewest lane-slots idle, cost x (32 - lanes), which a
+                // host lane model favoured by 2 %, measured 1.7 % slower on C3 and 22 % slower on C5: profiles/r2/s17_*)
                 const bool pickNode = n >= t && n >= e && n >= x, pickTri = !pickNode && t >= e && t >= x,
                            pickEnter = !pickNode && !pickTri && e >= x;
-#endif
                 if (pickNode)
                 {
                     if (wantNode) trav_node<CULL, false>(a.scene, st, stack, STATS ? &cnt : nullptr);
@@ -900,12 +886,7 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
             const bool wantLeaf = live && !wantNode;
             unsigned nodeMask = __ballot_sync(SPB_FULL, wantNode);
             unsigned leafMask = walking & ~nodeMask;
-#if SPB_VOTE_POLICY == 1
-            // (A/B) 145 (32 - n) <= 110 (32 - l): the step that leaves fewer lane-slots idle (tools/warpsim: -2 % warp instructions)
-            const bool pickNode = nodeMask && (!leafMask || 29 * __popc(nodeMask) - 22 * __popc(leafMask) >= 224);
-#else
             const bool pickNode = __popc(nodeMask) >= __popc(leafMask);
-#endif
             if (pickNode)
             {
                 if (wantNode) trav_node<CULL, SINGLE>(a.scene, st, stack, STATS ? &cnt : nullptr);
@@ -946,17 +927,12 @@ k_trace(const __grid_constant__ WaveArgs a, uint32_t bounce)
 
 #endif // SPB_TRAV2
 
-// Escaped rays.  Every record a miss touches -- its queue entry, its ray, the vertex terms of its path, one texel
-// of the environment map, its radiance slot -- is a scattered 16- or 32-byte read behind the one before
-// (profiles/r2/s8_shade_miss_ncu_full.txt: 33 warps per issue waiting on memory, DRAM at 56 %).  The chain is
-// cut by running it two items ahead: the queue entry of item k + 2 is loaded and the ray of item k + 1
-// prefetched into L2 while item k is shaded, and item k's vertex terms are prefetched the moment its path is
-// known, in front of the direction -> texel arithmetic (two double-rounded atan2) that hides them.
-#ifndef SPB_MISS_PREFETCH
-#define SPB_MISS_PREFETCH 0 // (measured on C3, profiles/r2/s15_*: 57.5 ms per frame with 0, 58.1 with 1, 57.6 with 2, 58.6 with 3)
-#endif
-// (occupancy, measured on C3, profiles/r2/s18_*: 40 registers = 6 CTAs per SM as compiled here; forced to 7 / 8 CTAs
-//  (36 / 32 registers, spills) the frame takes 1.3 / 1.8 ms longer, at 56-64 registers (4 CTAs) 0.9 ms longer)
+// Escaped rays: one thread per entry of the miss queue.  Every record a miss touches -- its queue entry, its ray,
+// the vertex terms of its path, one texel of the environment map, its radiance slot -- is a scattered 16- or
+// 32-byte access behind the one before (profiles/r2/s8_shade_miss_ncu_full.txt: 33 warps per issue waiting on
+// memory, DRAM at 56 %).  Measured and NOT adopted (profiles/r2/README.md): running the chain one and two items
+// ahead with prefetch.global.L2 (+0.1 ... +1.1 ms per frame), 32 / 36 / 56-64 registers instead of 40 (+0.9 ...
+// +1.8 ms); adopted: a grid of exactly the resident CTAs (launch_wave_shade).
 template <int MATH, int ENVFILTER>
 __global__ void __launch_bounds__(256)
 k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
@@ -968,39 +944,21 @@ k_shade_miss(const __grid_constant__ WaveArgs a, uint32_t bounce)
     Counters cnt = {0, 0, 0, 0};
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned rounds = (total + stride - 1) / stride;
-    const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
-#if SPB_MISS_PREFETCH & 1
-    unsigned slot = first < total ? a.missQ[first] : SPB_QUEUE_HOLE;
-    unsigned slot1 = first + stride < total && first + stride >= first ? a.missQ[first + stride] : SPB_QUEUE_HOLE;
-    if (slot1 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot1 * 2 + 1);
-#endif
     for (unsigned k = 0; k < rounds; ++k)
     {
-#if SPB_MISS_PREFETCH & 1
-        const unsigned i2 = (k + 2) * stride + first;
-        const unsigned slot2 = (k + 2 < rounds && i2 < total) ? a.missQ[i2] : SPB_QUEUE_HOLE;
-#else
-        const unsigned i = k * stride + first;
-        const unsigned slot = i < total ? a.missQ[i] : SPB_QUEUE_HOLE;
-#endif
-        const bool active = slot != SPB_QUEUE_HOLE;
+        unsigned i = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool active = i < total;
         uint32_t path = 0;
+        unsigned slot = active ? a.missQ[i] : SPB_QUEUE_HOLE;
+        active = slot != SPB_QUEUE_HOLE;
         if (active)
         {
             v4f rb = rays[(size_t)slot * 2 + 1];
             path = f2u(rb.w);
-#if SPB_MISS_PREFETCH & 2
-            for (int i = (int)bounce - 1; i >= 0; --i) prefetch_l2(a.pathTerms + ((size_t)i * a.pathCapacity + path) * 2);
-#endif
             f3 V = neg3(mk3(rb.x, rb.y, rb.z));
             finish_path_from(a, miss_radiance<MATH, ENVFILTER>(M, V, a.clampValue, &cnt), bounce, path);
         }
         count_row(a, path, active, SPB_COST_MISS);
-#if SPB_MISS_PREFETCH & 1
-        if (slot2 != SPB_QUEUE_HOLE) prefetch_l2(rays + (size_t)slot2 * 2 + 1);
-        slot = slot1;
-        slot1 = slot2;
-#endif
     }
     if (a.countStats)
     {
