@@ -703,6 +703,15 @@ def test_pipelined_frames_begin_end(gpu_sp):
     assert same_bits(r.image, want[0][0])
     r.render_rows_end(s0)
     assert same_bits(hosts[0].numpy(), want[1][0])
+    # a frame begun on one thread and ended on another (what Begin leaves for End lives with the library)
+    import threading
+    hosts[1].zero_()
+    s1 = r.render_rows_begin(0, H, frame=5, host_ptr=hosts[1].data_ptr())
+    ended = []
+    t = threading.Thread(target=lambda: ended.append(r.render_rows_end(s1)))
+    t.start()
+    t.join()
+    assert len(ended) == 1 and np.array_equal(ended[0][0][1:5], want[5][1][1:5]) and same_bits(hosts[1].numpy(), want[5][0])
     sp.set_params(samplesPerPixel=1, bounceCount=3, tileHeight=64)
     r.close()
 

@@ -25,6 +25,8 @@
 
 using namespace spb;
 
+struct PendingFrame; // (what sp_b200_RenderRowsBegin leaves for End; defined with the render entry points)
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -195,6 +197,9 @@ struct Library
         std::vector<cudaEvent_t> pool;
     } tuner;
     FrameState frames[2];
+    // what Begin leaves for End, per frame slot (kept with the Library, not with the calling thread: a host may
+    // begin a frame on one thread and end it on another)
+    std::shared_ptr<::PendingFrame> pendingFrames[2];
     FrameState *f = &frames[0]; // the frame the entry point at hand works on
     sp_b200_Stats lastStats;
     std::map<void *, std::shared_ptr<MeshAccel>> meshes;
@@ -2199,9 +2204,9 @@ struct PendingFrame
 };
 static PendingFrame &pending_of(Library &L, FrameState *F)
 {
-    static thread_local std::map<FrameState *, PendingFrame> table; // (a Library is only ever driven by one thread at a time)
-    (void)L;
-    return table[F];
+    std::shared_ptr<PendingFrame> &p = L.pendingFrames[F == &L.frames[1] ? 1 : 0];
+    if (!p) p = std::make_shared<PendingFrame>();
+    return *p;
 }
 
 // Enqueues everything a strip needs -- coverage pass, kernels, read-back of the counters, rows to the
@@ -2480,6 +2485,7 @@ extern "C" int sp_b200_RenderRowsEnd(int slot, sp_Metrics *metrics, u64 *tileRow
     Library &L = lib();
     std::lock_guard<std::recursive_mutex> lock(L.mutex);
     if (slot < 0 || slot > 1 || !L.frames[slot].pending) return -1;
+    SPB_CUDA(cudaSetDevice(L.device)); // (the calling thread need not be the one that began the frame)
     return render_rows_end(&L.frames[slot], metrics, tileRowCost);
 }
 
