@@ -703,6 +703,11 @@ def test_pipelined_frames_begin_end(gpu_sp):
     assert same_bits(r.image, want[0][0])
     r.render_rows_end(s0)
     assert same_bits(hosts[0].numpy(), want[1][0])
+    # an empty strip is a frame too: a slot to end, nothing rendered, nothing counted
+    hosts[0].zero_()
+    se = r.render_rows_begin(48, 48, frame=0, host_ptr=hosts[0].data_ptr())
+    me, _ = r.render_rows_end(se)
+    assert not me.any() and not hosts[0].numpy().any()
     # a frame begun on one thread and ended on another (what Begin leaves for End lives with the library)
     import threading
     hosts[1].zero_()
